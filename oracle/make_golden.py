@@ -1,0 +1,340 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates `tests/golden/*.npz` by running the REAL reference classes
+(imported from /root/reference through `oracle/ref_shim.py`) on seeded synthetic inputs, and checks the
+oracle restatement (`oracle/port.py`) against them while doing so.
+
+Run here (build container, CPU):   python oracle/make_golden.py
+The reference tree does not exist on the GPU box; tests only read the committed .npz files.
+
+Everything random comes from `numpy.random.default_rng(seed)` (PCG64 — platform-stable), never from the
+torch RNG, so the tests can regenerate the inputs and initial weights bit-exactly from the seed alone.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import port  # noqa: E402
+from oracle.ref_shim import import_reference  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+KEEP_FULL = ("conv_1_3x3.weight", "stage_1.0.conv_a.weight", "stage_2.0.conv_a.weight", "stage_2.0.downsample.0.weight",
+             "stage_3.4.conv_b.weight")
+
+
+# ---- shared synthetic-input helpers (tests import these too) -----------------------------------
+def synth_resnet_state(seed: int, n_head: int, feat: int = 64):
+    rng = np.random.default_rng(seed)
+    p, b = port.cifar_resnet_init(rng)
+    bound = 1.0 / np.sqrt(feat)
+    fc_w = torch.from_numpy(rng.uniform(-bound, bound, (n_head, feat)).astype(np.float32))
+    fc_b = torch.from_numpy(rng.uniform(-bound, bound, (n_head,)).astype(np.float32))
+    return p, b, fc_w, fc_b
+
+
+def synth_batch(seed: int, B: int, lo: int, hi: int, img: int = 32):
+    rng = np.random.default_rng(seed)
+    x = torch.from_numpy(rng.standard_normal((B, 3, img, img)).astype(np.float32))
+    y = torch.from_numpy(rng.integers(lo, hi, (B,)).astype(np.int64))
+    return x, y
+
+
+class FakeLoader:
+    """Stands in for the DataLoader that `EWC.getFisher` iterates (ewc.py:185-202): needs iteration,
+    `len()` and `.batch_size` only."""
+
+    def __init__(self, batches, batch_size):
+        self.batches, self.batch_size = batches, batch_size
+
+    def __iter__(self):
+        return iter({"image": x, "label": y} for x, y in self.batches)
+
+    def __len__(self):
+        return len(self.batches)
+
+
+def summarize(prefix, named, out):
+    """Per-tensor (sum, L2 norm) for every tensor + full copies of a few."""
+    names = list(named.keys())
+    out[prefix + "/names"] = np.array(names)
+    out[prefix + "/sum"] = np.array([float(named[n].double().sum()) for n in names])
+    out[prefix + "/norm"] = np.array([float(named[n].double().norm()) for n in names])
+    for n in names:
+        short = n.replace("backbone.", "").replace("network.", "")
+        if short in KEEP_FULL or "bn" in short or "classifier" in n or "downsample.1" in short:
+            out[prefix + "/full/" + n] = named[n].detach().numpy().copy()
+
+
+def close(a, b, rtol, atol, what):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    ok = torch.allclose(a, b, rtol=rtol, atol=atol)
+    print(f"   [{'ok' if ok else 'MISMATCH'}] {what}: max|d|={err:.3e}")
+    assert ok, what
+
+
+def load_ref_backbone(bb, p, b):
+    sd = {**p, **b}
+    missing = bb.load_state_dict(sd, strict=True)
+    return missing
+
+
+# ---- EWC ---------------------------------------------------------------------------------------
+def golden_ewc(core):
+    import core.model as M
+    print("EWC / cifar_resnet32")
+    B, init_cls, inc_cls, lamda = 8, 10, 10, 1000.0
+    p, b, fc_w, fc_b = synth_resnet_state(101, 20)
+    out = {}
+
+    bb = M.cifar_resnet32()
+    load_ref_backbone(bb, p, b)
+    ref = M.EWC(bb, 64, 100, device=torch.device("cpu"), init_cls_num=init_cls, inc_cls_num=inc_cls, lamda=lamda)
+    ref.before_task(0, None, None, None)
+    with torch.no_grad():
+        ref.network.classifier.weight.copy_(fc_w[:10]); ref.network.classifier.bias.copy_(fc_b[:10])
+    ref.train()
+    opt = torch.optim.SGD(ref.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4)
+
+    orc = port.ResNetMethodOracle("ewc", p, b, fc_w[:10], fc_b[:10], init_cls=init_cls, inc_cls=inc_cls, lamda=lamda)
+
+    def ref_step(x, y, tag):
+        pred, acc, loss = ref.observe({"image": x, "label": y})
+        opt.zero_grad(); loss.backward()
+        grads = {n: q.grad.clone() for n, q in ref.network.named_parameters()}
+        opt.step()
+        out[tag + "/loss"] = np.float64(loss.item()); out[tag + "/pred"] = pred.numpy().copy(); out[tag + "/acc"] = np.float64(acc)
+        summarize(tag + "/grad", grads, out)
+        return pred, acc, loss.detach(), grads
+
+    def both(x, y, tag):
+        pr, ar, lr_, gr = ref_step(x, y, tag)
+        po, ao, lo, go = orc.step(x, y)
+        close(lo, lr_, 1e-5, 1e-6, tag + " loss")
+        assert torch.equal(po, pr) and ao == ar
+        for n in gr:
+            close(go[n], gr[n], 1e-4, 1e-6, tag + " grad " + n) if n.endswith(KEEP_FULL) or "classifier" in n else None
+        worst = max(float((go[n] - gr[n]).abs().max() / (gr[n].abs().max() + 1e-12)) for n in gr)
+        print(f"   worst rel grad err over all tensors: {worst:.3e}")
+        assert worst < 1e-3
+
+    # task 0: two steps
+    for s in range(2):
+        x, y = synth_batch(1000 + s, B, 0, 10)
+        both(x, y, f"t0s{s}")
+    summarize("t0/param", dict(ref.network.named_parameters()), out)
+    # task boundary: Fisher over 3 batches (last ragged), in train() mode
+    fb = [synth_batch(1100 + i, B if i < 2 else 5, 0, 10) for i in range(3)]
+    ref.after_task(0, None, FakeLoader(fb, B), None)
+    orc.ewc_after_task(fb, B)
+    summarize("t0/fisher", ref.fisher, out)
+    for n in ref.fisher:
+        close(orc.fisher[n], ref.fisher[n], 2e-4, 1e-9, "fisher " + n) if n.endswith(KEEP_FULL) or "classifier" in n else None
+    # task 1
+    ref.before_task(1, None, None, None)
+    with torch.no_grad():
+        ref.network.classifier.weight[10:].copy_(fc_w[10:20]); ref.network.classifier.bias[10:].copy_(fc_b[10:20])
+    opt = torch.optim.SGD(ref.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    ref.train()
+    orc.task_idx = 1
+    orc.grow_head(fc_w[:20], fc_b[:20]); orc.reset_optimizer()
+    for s in range(3):
+        x, y = synth_batch(1200 + s, B, 10, 20)
+        both(x, y, f"t1s{s}")
+    summarize("t1/param", dict(ref.network.named_parameters()), out)
+    summarize("t1/bnbuf", {n: v.float() for n, v in ref.network.named_buffers() if "num_batches" not in n}, out)
+    # second boundary exercises the alpha merge with a grown head (ewc.py:129-131)
+    fb = [synth_batch(1300 + i, B, 10, 20) for i in range(2)]
+    ref.after_task(1, None, FakeLoader(fb, B), None)
+    orc.ewc_after_task(fb, B)
+    summarize("t1/fisher", ref.fisher, out)
+    close(orc.fisher["classifier.weight"], ref.fisher["classifier.weight"], 2e-4, 1e-9, "fisher merge classifier.weight")
+    np.savez_compressed(os.path.join(OUT, "ewc_resnet32.npz"), **out)
+
+
+# ---- iCaRL -------------------------------------------------------------------------------------
+def golden_icarl(core):
+    import copy
+    import core.model as M
+    print("iCaRL / cifar_resnet32")
+    B, init_cls, inc_cls = 8, 10, 5
+    p, b, fc_w, fc_b = synth_resnet_state(202, 100)
+    out = {}
+    bb = M.cifar_resnet32()
+    load_ref_backbone(bb, p, b)
+    ref = M.ICarl(bb, 64, 100, device=torch.device("cpu"), init_cls_num=init_cls, inc_cls_num=inc_cls, task_num=11)
+    with torch.no_grad():
+        ref.network.classifier.weight.copy_(fc_w); ref.network.classifier.bias.copy_(fc_b)
+    ref.before_task(0, None, None, None)
+    ref.train()
+    opt = torch.optim.SGD(ref.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    orc = port.ResNetMethodOracle("icarl", p, b, fc_w, fc_b, init_cls=init_cls, inc_cls=inc_cls)
+
+    def both(x, y, tag):
+        pred, acc, loss = ref.observe({"image": x, "label": y})
+        opt.zero_grad(); loss.backward()
+        grads = {n: q.grad.clone() for n, q in ref.network.named_parameters()}
+        opt.step()
+        out[tag + "/loss"] = np.float64(loss.item()); out[tag + "/pred"] = pred.numpy().copy(); out[tag + "/acc"] = np.float64(acc)
+        summarize(tag + "/grad", grads, out)
+        po, ao, lo, go = orc.step(x, y)
+        close(lo, loss.detach(), 1e-5, 1e-6, tag + " loss")
+        assert torch.equal(po, pred) and ao == acc
+        worst = max(float((go[n] - grads[n]).abs().max() / (grads[n].abs().max() + 1e-12)) for n in grads)
+        print(f"   worst rel grad err over all tensors: {worst:.3e}")
+        assert worst < 1e-3
+
+    for s in range(2):
+        x, y = synth_batch(2000 + s, B, 0, 10)
+        both(x, y, f"t0s{s}")
+    # after_task without the disk-backed buffer: the teacher snapshot lines of icarl.py:172-176 only
+    ref.old_network = copy.deepcopy(ref.network); ref.old_network.eval()
+    ref.prev_cls_num = ref.accu_cls_num; ref.cur_task_id += 1
+    ref.before_task(1, None, None, None)
+    opt = torch.optim.SGD(ref.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    orc.snapshot_teacher(); orc.prev_cls = 10; orc.accu_cls = 15; orc.task_idx = 1; orc.reset_optimizer()
+    for s in range(2):
+        x, y = synth_batch(2100 + s, B, 0, 15)     # new classes mixed with exemplars of old ones
+        both(x, y, f"t1s{s}")
+    summarize("t1/param", dict(ref.network.named_parameters()), out)
+    np.savez_compressed(os.path.join(OUT, "icarl_resnet32.npz"), **out)
+
+
+# ---- LwF ---------------------------------------------------------------------------------------
+def golden_lwf(core):
+    import core.model as M
+    print("LwF / cifar_resnet32 backbone")
+    B, init_cls, inc_cls = 8, 10, 10
+    p, b, fc_w, fc_b = synth_resnet_state(303, 20)
+    out = {}
+    bb = M.cifar_resnet32()
+    load_ref_backbone(bb, p, b)
+    ref = M.LWF(bb, 64, 100, device=torch.device("cpu"), init_cls_num=init_cls, inc_cls_num=inc_cls)
+    ref.before_task(0, None, None, None)
+    with torch.no_grad():
+        ref.classifier.weight.copy_(fc_w[:10]); ref.classifier.bias.copy_(fc_b[:10])
+    ref.train()
+
+    def params():
+        return list(ref.backbone.parameters()) + list(ref.classifier.parameters())
+
+    def named():
+        d = {"backbone." + n: q for n, q in ref.backbone.named_parameters()}
+        d.update({"classifier." + n: q for n, q in ref.classifier.named_parameters()})
+        return d
+
+    opt = torch.optim.SGD(params(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    orc = port.ResNetMethodOracle("lwf", p, b, fc_w[:10], fc_b[:10], init_cls=init_cls, inc_cls=inc_cls)
+
+    def both(x, y, tag):
+        pred, acc, loss = ref.observe({"image": x, "label": y})
+        opt.zero_grad(); loss.backward()
+        grads = {n: q.grad.clone() for n, q in named().items()}
+        opt.step()
+        out[tag + "/loss"] = np.float64(loss.item()); out[tag + "/pred"] = pred.numpy().copy()
+        summarize(tag + "/grad", grads, out)
+        po, ao, lo, go = orc.step(x, y)
+        close(lo, loss.detach(), 1e-5, 1e-6, tag + " loss")
+        assert torch.equal(po, pred)
+        worst = max(float((go[n] - grads[n]).abs().max() / (grads[n].abs().max() + 1e-12)) for n in grads)
+        print(f"   worst rel grad err over all tensors: {worst:.3e}")
+        assert worst < 1e-3
+
+    x, y = synth_batch(3000, B, 0, 10)
+    both(x, y, "t0s0")
+    ref.before_task(1, None, None, None)          # update_fc + frozen deepcopy of the backbone (lwf.py:44-50)
+    with torch.no_grad():
+        ref.classifier.weight[10:].copy_(fc_w[10:20]); ref.classifier.bias[10:].copy_(fc_b[10:20])
+    ref.train(); ref.old_backbone.eval(); ref.old_fc.eval()
+    opt = torch.optim.SGD(params(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    orc.snapshot_teacher(); orc.prev_cls = 10; orc.task_idx = 1
+    orc.grow_head(fc_w[:20], fc_b[:20]); orc.reset_optimizer()
+    for s in range(2):
+        x, y = synth_batch(3100 + s, B, 10, 20)
+        both(x, y, f"t1s{s}")
+    np.savez_compressed(os.path.join(OUT, "lwf_resnet32.npz"), **out)
+
+
+# ---- small op-level goldens -----------------------------------------------------------------------
+def golden_ops(core):
+    from core.model.backbone.prompt import L2P as RefL2PPool
+    from core.model.backbone.resnet import CosineLinear, SplitCosineLinear
+    print("op-level: L2P pool select, cosine heads, KD, GPM project")
+    out = {}
+    rng = np.random.default_rng(404)
+    # L2P pool (prompt.py:346-406) — several batches, including one with exact score ties
+    for case, (B, pool, topk, length, D) in enumerate([(16, 10, 5, 5, 768), (128, 10, 5, 5, 768), (7, 10, 5, 5, 64), (4, 6, 2, 3, 32)]):
+        mod = RefL2PPool(length=length, prompt_key=True, pool_size=pool, top_k=topk, num_layers=1, embed_dim=D)
+        prm = torch.from_numpy(rng.uniform(0, 1, (1, pool, length, D)).astype(np.float32))
+        key = torch.from_numpy(rng.uniform(0, 1, (pool, D)).astype(np.float32))
+        q = torch.from_numpy(rng.standard_normal((B, D)).astype(np.float32))
+        if case == 3:
+            key[1] = key[0]; key[4] = key[0]       # exact ties in the similarity
+        with torch.no_grad():
+            mod.prompt.copy_(prm); mod.prompt_key.copy_(key)
+        xe = torch.zeros(B, 3, D)
+        bp, rs = mod(xe, cls_features=q)
+        obp, ors, oid = port.l2p_select(prm, key, q, topk)
+        close(obp, bp, 0, 0, f"l2p case{case} prompts"); close(ors, rs, 1e-6, 1e-7, f"l2p case{case} reduce_sim")
+        kn = F.normalize(key, dim=-1); qn = F.normalize(q, dim=-1)
+        sim_np = (qn @ kn.T).numpy()
+        ids_np = port.l2p_majority_ids_numpy(sim_np, topk)
+        # `torch.topk` over the integer histogram (prompt.py:387) breaks count ties in an implementation-defined
+        # order (CPU partial sort vs CUDA radix select differ), so: the reference's ids must be A valid top-k of the
+        # histogram, and must equal the product rule (count desc, id asc) whenever the top-(k+1) counts are distinct.
+        hist = np.bincount(sim_np.argsort(axis=1, kind="stable")[:, ::-1][:, :topk].ravel(), minlength=pool) if case != 3 else None
+        if hist is not None:
+            top_counts = np.sort(hist)[::-1]
+            assert sorted(hist[oid.numpy()].tolist(), reverse=True) == top_counts[:topk].tolist()
+            strict = len(set(top_counts[: topk + 1].tolist())) == min(topk + 1, pool)
+            if strict:
+                assert np.array_equal(ids_np, oid.numpy()), (ids_np, oid, hist)
+            else:
+                assert sorted(hist[ids_np].tolist(), reverse=True) == top_counts[:topk].tolist()
+            out[f"l2p{case}/hist"] = hist; out[f"l2p{case}/strict"] = np.int64(strict)
+        out[f"l2p{case}/ids_rule"] = ids_np
+        out[f"l2p{case}/shape"] = np.array([B, pool, topk, length, D]); out[f"l2p{case}/ids"] = oid.numpy()
+        out[f"l2p{case}/reduce_sim"] = np.float64(rs.item()); out[f"l2p{case}/prompt_sum"] = np.float64(bp.double().sum().item())
+        out[f"l2p{case}/ties"] = np.int64(case == 3)
+        # gradient of the pull term wrt key (drives the only trainables besides the head)
+        mod.zero_grad(); (-rs).backward()
+        out[f"l2p{case}/dkey"] = mod.prompt_key.grad.numpy().copy()
+    # cosine heads (resnet.py:418-463)
+    B, D = 16, 64
+    feat = torch.from_numpy(rng.standard_normal((B, D)).astype(np.float32))
+    cl = CosineLinear(D, 10)
+    w1 = torch.from_numpy(rng.uniform(-0.125, 0.125, (10, D)).astype(np.float32))
+    with torch.no_grad():
+        cl.weight.copy_(w1); cl.sigma.fill_(1.7)
+    o = cl(feat)
+    close(port.cosine_head(feat, w1, torch.tensor([1.7])), o, 1e-6, 1e-7, "CosineLinear")
+    out["cos/out"] = o.detach().numpy().copy()
+    sc = SplitCosineLinear(D, 10, 5)
+    w2 = torch.from_numpy(rng.uniform(-0.125, 0.125, (5, D)).astype(np.float32))
+    with torch.no_grad():
+        sc.fc1.weight.copy_(w1); sc.fc2.weight.copy_(w2); sc.sigma.fill_(2.5)
+    o2 = sc(feat)
+    close(port.cosine_head(feat, torch.cat([w1, w2]), torch.tensor([2.5])), o2, 1e-6, 1e-7, "SplitCosineLinear")
+    out["cos/split_out"] = o2.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "ops_small.npz"), **out)
+
+
+def main():
+    torch.set_num_threads(8)
+    os.makedirs(OUT, exist_ok=True)
+    core = import_reference()
+    golden_ewc(core)
+    golden_icarl(core)
+    golden_lwf(core)
+    golden_ops(core)
+    print("golden vectors written to", OUT)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,379 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Never imported by the product path (`libcontinual_b200/`).
+
+CPU restatement (PyTorch fp32, functional style, autograd for derivatives) of the reference's per-step
+training hot path (RL-VIG/LibContinual @ a399ed4).  Allowed importers: `tests/`,
+`__graft_entry__.smoke()`, `bench.py` (`cpu_baseline` leg and `--impl reference`).
+
+Parity pinning: the reference ships no tests / golden vectors, so this restatement is
+pinned against outputs of the reference ITSELF, imported in the build container through
+`oracle/ref_shim.py` by `oracle/make_golden.py`; the vectors live in `tests/golden/*.npz` and are
+re-checked by `tests/test_oracle_golden.py` on every CPU run.
+
+All `file:line` citations are relative to the reference root.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+BN_EPS = 1e-5       # nn.BatchNorm2d default, used by core/model/backbone/resnet.py:296,299,332
+BN_MOMENTUM = 0.1   # nn.BatchNorm2d default
+
+
+# ----------------------------------------------------------------------------------------------
+# cifar_resnet32  (core/model/backbone/resnet.py:289-412, factory :760-763)
+# ----------------------------------------------------------------------------------------------
+def cifar_resnet_layout(depth: int = 32, in_ch: int = 3) -> Tuple[List[Tuple[str, Tuple[int, ...]]], List[Tuple[str, Tuple[int, ...]]]]:
+    """Parameter and buffer (name, shape) lists in the reference's `named_parameters()` /
+    `named_buffers()` order (module registration order of resnet.py:334-340, 294-301, 361-376)."""
+    assert (depth - 2) % 6 == 0
+    nblk = (depth - 2) // 6
+    params: List[Tuple[str, Tuple[int, ...]]] = []
+    bufs: List[Tuple[str, Tuple[int, ...]]] = []
+
+    def bn(prefix, c):
+        params.append((prefix + ".weight", (c,)))
+        params.append((prefix + ".bias", (c,)))
+        bufs.append((prefix + ".running_mean", (c,)))
+        bufs.append((prefix + ".running_var", (c,)))
+        bufs.append((prefix + ".num_batches_tracked", ()))
+
+    params.append(("conv_1_3x3.weight", (16, in_ch, 3, 3)))
+    bn("bn_1", 16)
+    inpl = 16
+    for s, planes in enumerate((16, 32, 64), start=1):
+        for b in range(nblk):
+            pre = f"stage_{s}.{b}"
+            cin = inpl if b == 0 else planes
+            params.append((pre + ".conv_a.weight", (planes, cin, 3, 3)))
+            bn(pre + ".bn_a", planes)
+            params.append((pre + ".conv_b.weight", (planes, planes, 3, 3)))
+            bn(pre + ".bn_b", planes)
+            if b == 0 and (s > 1):
+                params.append((pre + ".downsample.0.weight", (planes, cin, 1, 1)))
+                bn(pre + ".downsample.1", planes)
+        inpl = planes
+    return params, bufs
+
+
+def cifar_resnet_init(rng: np.random.Generator, depth: int = 32, in_ch: int = 3) -> Tuple[Dict[str, Tensor], Dict[str, Tensor]]:
+    """Same init DISTRIBUTIONS as resnet.py:345-352 (conv ~ N(0, sqrt(2/(k*k*Cout))), BN weight 1 / bias 0),
+    drawn from a numpy Generator so that the values are platform-stable for fixtures."""
+    pl, bl = cifar_resnet_layout(depth, in_ch)
+    params, bufs = {}, {}
+    for name, shape in pl:
+        if len(shape) == 4:
+            n = shape[2] * shape[3] * shape[0]
+            params[name] = torch.from_numpy((rng.standard_normal(shape) * math.sqrt(2.0 / n)).astype(np.float32))
+        elif name.endswith(".weight"):
+            params[name] = torch.ones(shape)
+        else:
+            params[name] = torch.zeros(shape)
+    for name, shape in bl:
+        if name.endswith("running_var"):
+            bufs[name] = torch.ones(shape)
+        elif name.endswith("num_batches_tracked"):
+            bufs[name] = torch.zeros((), dtype=torch.int64)
+        else:
+            bufs[name] = torch.zeros(shape)
+    return params, bufs
+
+
+def _bn(x: Tensor, p: Dict[str, Tensor], b: Dict[str, Tensor], prefix: str, train: bool) -> Tensor:
+    # nn.BatchNorm2d forward: batch statistics (biased var) in train mode and in-place running-stat
+    # update with momentum 0.1 / unbiased var; running statistics in eval mode.
+    if train:
+        b[prefix + ".num_batches_tracked"] += 1
+    return F.batch_norm(x, b[prefix + ".running_mean"], b[prefix + ".running_var"], p[prefix + ".weight"],
+                        p[prefix + ".bias"], training=train, momentum=BN_MOMENTUM, eps=BN_EPS)
+
+
+def cifar_resnet_forward(p: Dict[str, Tensor], b: Dict[str, Tensor], x: Tensor, train: bool, depth: int = 32) -> Dict[str, object]:
+    """resnet.py:381-395 (network) and :303-316 (basic block).  Returns {'fmaps': [x1, x2, x3], 'features': [B, 64]}."""
+    nblk = (depth - 2) // 6
+    h = F.conv2d(x, p["conv_1_3x3.weight"], None, 1, 1)
+    h = F.relu(_bn(h, p, b, "bn_1", train))
+    fmaps = []
+    for s in (1, 2, 3):
+        for k in range(nblk):
+            pre = f"stage_{s}.{k}"
+            stride = 2 if (k == 0 and s > 1) else 1
+            r = h
+            y = F.conv2d(h, p[pre + ".conv_a.weight"], None, stride, 1)
+            y = F.relu(_bn(y, p, b, pre + ".bn_a", train))
+            y = F.conv2d(y, p[pre + ".conv_b.weight"], None, 1, 1)
+            y = _bn(y, p, b, pre + ".bn_b", train)
+            if (pre + ".downsample.0.weight") in p:
+                r = F.conv2d(h, p[pre + ".downsample.0.weight"], None, stride, 0)
+                r = _bn(r, p, b, pre + ".downsample.1", train)
+            h = F.relu(r + y)
+        fmaps.append(h)
+    feats = F.avg_pool2d(h, 8).flatten(1)          # nn.AvgPool2d(8), resnet.py:340,389-390
+    return {"fmaps": fmaps, "features": feats}
+
+
+# ----------------------------------------------------------------------------------------------
+# heads and losses
+# ----------------------------------------------------------------------------------------------
+def linear_head(feat: Tensor, w: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """nn.Linear(feat_dim, n_cls) — ewc.py:52-57, icarl.py:24-38, finetune.py:10,19."""
+    return F.linear(feat, w, bias)
+
+
+def cosine_head(feat: Tensor, w: Tensor, sigma: Optional[Tensor]) -> Tensor:
+    """CosineLinear.forward, resnet.py:436-441: sigma * normalize(x) @ normalize(W)^T (eps 1e-12)."""
+    out = F.linear(F.normalize(feat, p=2, dim=1), F.normalize(w, p=2, dim=1))
+    return out if sigma is None else sigma * out
+
+
+def kd_loss(student: Tensor, teacher: Tensor, T: float = 2.0) -> Tensor:
+    """`_KD_loss` of lwf.py:75-78 / icarl.py:198-206: -(1/B) sum softmax(t/T) * log_softmax(s/T).  No T^2 factor."""
+    return -(torch.softmax(teacher / T, dim=1) * torch.log_softmax(student / T, dim=1)).sum() / student.shape[0]
+
+
+def ewc_penalty(named_params: Dict[str, Tensor], ref: Dict[str, Tensor], fisher: Dict[str, Tensor]) -> Tensor:
+    """`EWC.compute_ewc`, ewc.py:207-225: sum_n sum(F_n * (p_n[:len(ref_n)] - ref_n)^2) / 2."""
+    total = torch.zeros(())
+    for n, prm in named_params.items():
+        if n in fisher:
+            total = total + (fisher[n] * (prm[: len(ref[n])] - ref[n]).pow(2)).sum() / 2
+    return total
+
+
+def ewc_loss(logits: Tensor, y: Tensor, task_idx: int, inc_cls: int, lamda: float,
+             named_params: Dict[str, Tensor], ref: Dict[str, Tensor], fisher: Dict[str, Tensor]) -> Tensor:
+    """`EWC.observe`, ewc.py:82-100."""
+    if task_idx == 0:
+        return F.cross_entropy(logits, y)
+    old = logits.shape[1] - inc_cls
+    return F.cross_entropy(logits[:, old:], y - old) + lamda * ewc_penalty(named_params, ref, fisher)
+
+
+def icarl_loss(cur_logits_all: Tensor, y: Tensor, accu: int, prev: int, old_logits_all: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """`ICarl.criterion`, icarl.py:197-221.  `cur_logits_all` = network(x) over the fixed `num_class` head."""
+    cur = cur_logits_all[:, :accu]
+    loss = F.cross_entropy(cur, y)
+    if old_logits_all is not None:
+        loss = loss + kd_loss(cur[:, :prev], old_logits_all[:, :prev], 2.0)
+    return cur, loss
+
+
+def lwf_loss(logits: Tensor, y: Tensor, known: int, teacher_logits: Optional[Tensor]) -> Tensor:
+    """`LWF.observe`, lwf.py:52-70 (lamda=3 and T=2 are hard-coded at :63-65)."""
+    if teacher_logits is None:
+        return F.cross_entropy(logits, y)
+    return 3 * kd_loss(logits[:, :known], teacher_logits, 2.0) + F.cross_entropy(logits[:, known:], y - known)
+
+
+def lucir_loss(feat: Tensor, ref_feat: Tensor, logits: Tensor, scores_bs: Tensor, y: Tensor, num_old: int,
+               cur_lamda: float, K: int, dist: float, lw_mr: float) -> Tensor:
+    """`LUCIR.observe` task>0 branch, lucir.py:184-205.
+    feat/ref_feat: inputs of the cosine classifiers (student / frozen ref); logits = sigma*scores_bs."""
+    B = y.shape[0]
+    loss = F.cosine_embedding_loss(feat, ref_feat.detach(), torch.ones(B)) * cur_lamda
+    loss = loss + F.cross_entropy(logits, y)
+    gt = scores_bs.gather(1, y.view(-1, 1)).squeeze(1)
+    max_novel = scores_bs[:, num_old:].topk(K, dim=1)[0]
+    hard = y.lt(num_old)
+    n_hard = int(hard.sum())
+    if n_hard > 0:
+        g = gt[hard].view(-1, 1).repeat(1, K)
+        m = max_novel[hard]
+        loss = loss + F.margin_ranking_loss(g.view(-1, 1), m.view(-1, 1), torch.ones(n_hard * K, 1), margin=dist) * lw_mr
+    return loss
+
+
+# ----------------------------------------------------------------------------------------------
+# optimizers  (torch.optim.SGD / Adam as configured by trainer.py:159-182; restated from their documented update rules)
+# ----------------------------------------------------------------------------------------------
+def sgd_momentum_step(p: Tensor, g: Tensor, m: Optional[Tensor], lr: float, momentum: float, wd: float) -> Tuple[Tensor, Tensor]:
+    """torch.optim.SGD (dampening 0, no nesterov): g' = g + wd*p ; m = g' (first step) or mu*m + g' ; p -= lr*m."""
+    g = g.add(p, alpha=wd) if wd != 0 else g
+    m = g.clone() if m is None else m.mul(momentum).add_(g)
+    return p.add(m, alpha=-lr), m
+
+
+def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, b1: float, b2: float, eps: float, wd: float):
+    """torch.optim.Adam (no amsgrad), L2-style weight decay."""
+    g = g + wd * p
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+    denom = v.sqrt() / math.sqrt(bc2) + eps
+    return p - (lr / bc1) * m / denom, m, v
+
+
+# ----------------------------------------------------------------------------------------------
+# L2P prompt pool selection  (core/model/backbone/prompt.py:369-406)
+# ----------------------------------------------------------------------------------------------
+def l2p_select(prompt: Tensor, prompt_key: Tensor, cls_features: Tensor, top_k: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Returns (batched_prompt [L, B, top_k*len, D], reduce_sim scalar, major_prompt_id [top_k] int64).
+    Batch-wide majority vote (prompt.py:381-390): per-sample top-k ids -> histogram -> top-k most frequent ids,
+    shared by every sample."""
+    pool = prompt_key.shape[0]
+    B = cls_features.shape[0]
+    kn = F.normalize(prompt_key, p=2, dim=-1, eps=1e-12)
+    qn = F.normalize(cls_features, p=2, dim=-1, eps=1e-12)
+    sim = qn @ kn.T
+    idx = sim.topk(top_k, dim=1)[1]
+    ids, counts = torch.unique(idx, return_counts=True, sorted=True)
+    ids = F.pad(ids, (0, pool - len(ids)), "constant", int(ids[0]))
+    counts = F.pad(counts, (0, pool - len(counts)), "constant", 0)
+    major = ids[counts.topk(top_k)[1]]
+    sel = major.unsqueeze(0).repeat(B, 1)
+    raw = prompt[:, sel]                                    # [L, B, top_k, len, D]
+    batched = raw.reshape(raw.shape[0], raw.shape[1], -1, raw.shape[-1])
+    reduce_sim = (kn[sel] * qn.unsqueeze(1)).sum() / B
+    return batched, reduce_sim, major
+
+
+def l2p_majority_ids_numpy(sim: np.ndarray, top_k: int) -> np.ndarray:
+    """Integer-only restatement of the id selection above with an explicit tie rule, used to define the
+    product's deterministic behaviour: per-sample top-k by (value desc, index asc); histogram over the pool;
+    majority top-k by (count desc, id asc).  `torch.topk` on CPU resolves ties the same way for these sizes
+    (checked against the reference in tests/test_oracle_golden.py)."""
+    B, pool = sim.shape
+    hist = np.zeros(pool, dtype=np.int64)
+    for b in range(B):
+        order = sorted(range(pool), key=lambda j: (-float(sim[b, j]), j))[:top_k]
+        for j in order:
+            hist[j] += 1
+    present = [j for j in range(pool) if hist[j] > 0]
+    # reference pads the id list with ids[0] / count 0 (prompt.py:384-385)
+    ids = present + [present[0]] * (pool - len(present))
+    cnt = [int(hist[j]) for j in present] + [0] * (pool - len(present))
+    order = sorted(range(pool), key=lambda i: (-cnt[i], i))[:top_k]
+    return np.array([ids[i] for i in order], dtype=np.int64)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPM gradient projection  (core/model/gpm.py:78-81, M = U U^T from gpm.py:124)
+# ----------------------------------------------------------------------------------------------
+def gpm_project(grad: Tensor, feature_mat: Tensor) -> Tensor:
+    sz = grad.shape[0]
+    return grad - (grad.view(sz, -1) @ feature_mat).view(grad.shape)
+
+
+# ----------------------------------------------------------------------------------------------
+# InfLoRA_OPT weight-side LoRA (core/model/backbone/transformer.py:246-254)
+# ----------------------------------------------------------------------------------------------
+def lora_merge_qkv(qkv_w: Tensor, A_k: Tensor, B_k: Tensor, A_v: Tensor, B_v: Tensor) -> Tensor:
+    """W' = cat(W_q, W_k + B_k A_k, W_v + B_v A_v).  qkv_w [3D, D]; A [r, D]; B [D, r]."""
+    D = qkv_w.shape[1]
+    wq, wk, wv = qkv_w[:D], qkv_w[D:2 * D], qkv_w[2 * D:]
+    return torch.cat([wq, wk + B_k @ A_k, wv + B_v @ A_v], dim=0)
+
+
+# ----------------------------------------------------------------------------------------------
+# Method-level steppers used by parity tests, the CPU baseline and `bench.py --impl reference`
+# ----------------------------------------------------------------------------------------------
+class ResNetMethodOracle:
+    """EWC / iCaRL / LwF / Finetune on cifar_resnet32 with the reference's step order
+    (observe -> zero_grad -> backward -> SGD step; trainer.py:601-606).
+
+    State: `p` (backbone params + 'classifier.weight'/'classifier.bias'), `b` (BN buffers), optional teacher copy,
+    EWC `ref`/`fisher` dicts (names follow ewc.py `self.network.named_parameters()`: 'backbone.<n>', 'classifier.<n>')."""
+
+    def __init__(self, method: str, p: Dict[str, Tensor], b: Dict[str, Tensor], fc_w: Tensor, fc_b: Tensor, *,
+                 init_cls: int, inc_cls: int, lamda: float = 1000.0, lr: float = 0.1, momentum: float = 0.9, wd: float = 5e-4,
+                 depth: int = 32):
+        assert method in ("finetune", "ewc", "icarl", "lwf")
+        self.method, self.depth = method, depth
+        self.p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+        self.b = {k: v.clone() for k, v in b.items()}
+        self.fc_w = fc_w.clone().requires_grad_(True)
+        self.fc_b = fc_b.clone().requires_grad_(True)
+        self.init_cls, self.inc_cls, self.lamda = init_cls, inc_cls, lamda
+        self.lr, self.mu, self.wd = lr, momentum, wd
+        self.task_idx = 0
+        self.mom: Dict[str, Optional[Tensor]] = {}
+        self.teacher = None            # (p, b, fc_w, fc_b) frozen copies
+        self.ref: Dict[str, Tensor] = {}
+        self.fisher: Dict[str, Tensor] = {}
+        self.prev_cls = 0
+        self.accu_cls = init_cls
+
+    # -- helpers -------------------------------------------------------------------------------
+    def named(self) -> Dict[str, Tensor]:
+        d = {"backbone." + k: v for k, v in self.p.items()}
+        d["classifier.weight"] = self.fc_w
+        d["classifier.bias"] = self.fc_b
+        return d
+
+    def logits(self, x: Tensor, train: bool) -> Tensor:
+        feat = cifar_resnet_forward(self.p, self.b, x, train, self.depth)["features"]
+        return linear_head(feat, self.fc_w, self.fc_b)
+
+    def teacher_logits(self, x: Tensor) -> Tensor:
+        tp, tb, tw, tbias = self.teacher
+        with torch.no_grad():
+            feat = cifar_resnet_forward(tp, tb, x, False, self.depth)["features"]
+            return linear_head(feat, tw, tbias)
+
+    def snapshot_teacher(self):
+        self.teacher = ({k: v.detach().clone() for k, v in self.p.items()}, {k: v.clone() for k, v in self.b.items()},
+                        self.fc_w.detach().clone(), self.fc_b.detach().clone())
+
+    def grow_head(self, new_w: Tensor, new_b: Tensor):
+        """ewc.py:71-80 / lwf.py:28-42: new Linear whose first rows are the old head."""
+        n_old = self.fc_w.shape[0]
+        w, bias = new_w.clone(), new_b.clone()
+        w[:n_old] = self.fc_w.detach()
+        bias[:n_old] = self.fc_b.detach()
+        self.fc_w, self.fc_b = w.requires_grad_(True), bias.requires_grad_(True)
+
+    def reset_optimizer(self):
+        self.mom = {}       # trainer.py:294 rebuilds the optimizer every task
+
+    # -- one training step ---------------------------------------------------------------------
+    def loss(self, x: Tensor, y: Tensor) -> Tuple[Tensor, Tensor]:
+        lg = self.logits(x, True)
+        if self.method == "finetune":
+            return lg, F.cross_entropy(lg, y)
+        if self.method == "ewc":
+            return lg, ewc_loss(lg, y, self.task_idx, self.inc_cls, self.lamda, self.named(), self.ref, self.fisher)
+        if self.method == "icarl":
+            old = self.teacher_logits(x) if self.teacher is not None else None
+            cur, l = icarl_loss(lg, y, self.accu_cls, self.prev_cls, old)
+            return cur, l
+        old = self.teacher_logits(x) if self.teacher is not None else None
+        return lg, lwf_loss(lg, y, self.prev_cls, old)
+
+    def step(self, x: Tensor, y: Tensor, apply_update: bool = True):
+        """Returns (pred, acc, loss, grads dict)."""
+        lg, loss = self.loss(x, y)
+        named = self.named()
+        grads = torch.autograd.grad(loss, list(named.values()), allow_unused=True)
+        gd = {n: (g if g is not None else torch.zeros_like(v)) for (n, v), g in zip(named.items(), grads)}
+        pred = lg.argmax(dim=1)
+        acc = float((pred == y).sum()) / x.shape[0]
+        if apply_update:
+            with torch.no_grad():
+                for n, v in named.items():
+                    newp, m = sgd_momentum_step(v.detach(), gd[n], self.mom.get(n), self.lr, self.mu, self.wd)
+                    self.mom[n] = m
+                    v.copy_(newp)
+        return pred, acc, loss.detach(), gd
+
+    # -- EWC task boundary (ewc.py:110-133, 147-205) ---------------------------------------------
+    def ewc_after_task(self, batches: Sequence[Tuple[Tensor, Tensor]], loader_batch_size: int):
+        named = self.named()
+        self.ref = {n: v.detach().clone() for n, v in named.items()}
+        new_f = {n: torch.zeros_like(v) for n, v in named.items()}
+        for x, y in batches:
+            lg = self.logits(x, True)                       # train() mode: BN stats keep moving (ewc.py:182)
+            l = F.cross_entropy(lg, y)                      # over ALL logits (ewc.py:192-193)
+            gs = torch.autograd.grad(l, list(self.named().values()))
+            for (n, _), g in zip(named.items(), gs):
+                new_f[n] += g.pow(2) * len(y)               # ewc.py:173
+        n_samples = loader_batch_size * len(batches)        # ewc.py:202 (over-counts a ragged last batch)
+        new_f = {n: f / n_samples for n, f in new_f.items()}
+        alpha = 1 - self.inc_cls / self.fc_w.shape[0]       # ewc.py:129
+        for n, old in self.fisher.items():
+            new_f[n][: len(old)] = alpha * old + (1 - alpha) * new_f[n][: len(old)]
+        self.fisher = new_f

@@ -1,0 +1,112 @@
+"""CPU: the oracle restatement (oracle/port.py) reproduces the golden vectors that oracle/make_golden.py recorded
+from the real reference classes (imported from /root/reference in the build container)."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import port
+from tests.golden_util import check_summary, load, synth_batch, synth_resnet_state
+
+B = 8
+
+
+def _run(orc, g, tag, x, y, rtol=1e-5):
+    pred, acc, loss, grads = orc.step(x, y)
+    assert abs(float(loss) - float(g[tag + "/loss"])) <= 1e-5 * abs(float(g[tag + "/loss"])) + 1e-6
+    assert np.array_equal(pred.numpy(), g[tag + "/pred"])
+    check_summary(g, tag + "/grad", grads, rtol=rtol)
+
+
+def test_ewc_trajectory_matches_reference():
+    g = load("ewc_resnet32.npz")
+    p, b, fc_w, fc_b = synth_resnet_state(101, 20)
+    orc = port.ResNetMethodOracle("ewc", p, b, fc_w[:10], fc_b[:10], init_cls=10, inc_cls=10, lamda=1000.0)
+    for s in range(2):
+        _run(orc, g, f"t0s{s}", *synth_batch(1000 + s, B, 0, 10))
+    check_summary(g, "t0/param", orc.named())
+    fb = [synth_batch(1100 + i, B if i < 2 else 5, 0, 10) for i in range(3)]
+    orc.ewc_after_task(fb, B)
+    check_summary(g, "t0/fisher", orc.fisher, rtol=2e-4, atol=1e-10)
+    orc.task_idx = 1
+    orc.grow_head(fc_w[:20], fc_b[:20]); orc.reset_optimizer()
+    for s in range(3):
+        _run(orc, g, f"t1s{s}", *synth_batch(1200 + s, B, 10, 20))
+    check_summary(g, "t1/param", orc.named())
+    check_summary(g, "t1/bnbuf", {"backbone." + k: v.float() for k, v in orc.b.items()})
+    orc.ewc_after_task([synth_batch(1300 + i, B, 10, 20) for i in range(2)], B)
+    check_summary(g, "t1/fisher", orc.fisher, rtol=2e-4, atol=1e-10)
+
+
+def test_ewc_penalty_is_active_in_task1():
+    g = load("ewc_resnet32.npz")
+    # first task-1 step has theta == theta*, so loss is pure CE; the next ones carry lamda * penalty
+    assert float(g["t1s1/loss"]) > 0 and float(g["t1s2/loss"]) > 0
+
+
+def test_icarl_trajectory_matches_reference():
+    g = load("icarl_resnet32.npz")
+    p, b, fc_w, fc_b = synth_resnet_state(202, 100)
+    orc = port.ResNetMethodOracle("icarl", p, b, fc_w, fc_b, init_cls=10, inc_cls=5)
+    for s in range(2):
+        _run(orc, g, f"t0s{s}", *synth_batch(2000 + s, B, 0, 10))
+    orc.snapshot_teacher(); orc.prev_cls = 10; orc.accu_cls = 15; orc.task_idx = 1; orc.reset_optimizer()
+    for s in range(2):
+        _run(orc, g, f"t1s{s}", *synth_batch(2100 + s, B, 0, 15))
+    check_summary(g, "t1/param", {"backbone." + k: v for k, v in orc.p.items()} | {"classifier.weight": orc.fc_w, "classifier.bias": orc.fc_b})
+
+
+def test_lwf_trajectory_matches_reference():
+    g = load("lwf_resnet32.npz")
+    p, b, fc_w, fc_b = synth_resnet_state(303, 20)
+    orc = port.ResNetMethodOracle("lwf", p, b, fc_w[:10], fc_b[:10], init_cls=10, inc_cls=10)
+    _run(orc, g, "t0s0", *synth_batch(3000, B, 0, 10))
+    orc.snapshot_teacher(); orc.prev_cls = 10; orc.task_idx = 1
+    orc.grow_head(fc_w[:20], fc_b[:20]); orc.reset_optimizer()
+    for s in range(2):
+        _run(orc, g, f"t1s{s}", *synth_batch(3100 + s, B, 10, 20))
+
+
+def test_l2p_select_matches_reference():
+    g = load("ops_small.npz")
+    rng = np.random.default_rng(404)
+    for case in range(4):
+        Bq, pool, topk, length, D = [int(v) for v in g[f"l2p{case}/shape"]]
+        prm = torch.from_numpy(rng.uniform(0, 1, (1, pool, length, D)).astype(np.float32))
+        key = torch.from_numpy(rng.uniform(0, 1, (pool, D)).astype(np.float32))
+        q = torch.from_numpy(rng.standard_normal((Bq, D)).astype(np.float32))
+        if case == 3:
+            key[1] = key[0]; key[4] = key[0]
+        key.requires_grad_(True)
+        bp, rs, ids = port.l2p_select(prm, key, q, topk)
+        assert np.array_equal(ids.numpy(), g[f"l2p{case}/ids"])
+        assert abs(float(rs) - float(g[f"l2p{case}/reduce_sim"])) < 1e-6
+        assert abs(float(bp.double().sum()) - float(g[f"l2p{case}/prompt_sum"])) < 1e-6 * abs(float(g[f"l2p{case}/prompt_sum"]))
+        (-rs).backward()
+        assert np.allclose(key.grad.numpy(), g[f"l2p{case}/dkey"], rtol=1e-5, atol=1e-7)
+        if f"l2p{case}/strict" in g.files and int(g[f"l2p{case}/strict"]):
+            kn = F.normalize(key.detach(), dim=-1); qn = F.normalize(q, dim=-1)
+            assert np.array_equal(port.l2p_majority_ids_numpy((qn @ kn.T).numpy(), topk), g[f"l2p{case}/ids"])
+    # the draws for the cosine-head fixtures follow in the same stream
+    feat = torch.from_numpy(rng.standard_normal((16, 64)).astype(np.float32))
+    w1 = torch.from_numpy(rng.uniform(-0.125, 0.125, (10, 64)).astype(np.float32))
+    w2 = torch.from_numpy(rng.uniform(-0.125, 0.125, (5, 64)).astype(np.float32))
+    assert np.allclose(port.cosine_head(feat, w1, torch.tensor([1.7])).numpy(), g["cos/out"], rtol=1e-6, atol=1e-7)
+    assert np.allclose(port.cosine_head(feat, torch.cat([w1, w2]), torch.tensor([2.5])).numpy(), g["cos/split_out"], rtol=1e-6, atol=1e-7)
+
+
+def test_known_answer_properties():
+    """Reference-free properties listed in SURVEY.md §4."""
+    rng = np.random.default_rng(7)
+    t = torch.from_numpy(rng.standard_normal((6, 9)).astype(np.float32))
+    s = t.clone().requires_grad_(True)
+    port.kd_loss(s, t, 2.0).backward()
+    assert float(s.grad.abs().max()) < 1e-7                       # KD minimised at s == t
+    U = torch.linalg.qr(torch.from_numpy(rng.standard_normal((32, 5)).astype(np.float32)))[0]
+    gproj = port.gpm_project(torch.from_numpy(rng.standard_normal((7, 32)).astype(np.float32)), U @ U.T)
+    assert float((gproj @ U).abs().max()) < 1e-5                  # projected gradient is orthogonal to the stored basis
+    feat = torch.from_numpy(rng.standard_normal((4, 64)).astype(np.float32))
+    w = torch.from_numpy(rng.standard_normal((10, 64)).astype(np.float32))
+    assert float(port.cosine_head(feat, w, torch.tensor([3.0])).abs().max()) <= 3.0 + 1e-5
+    qkv = torch.from_numpy(rng.standard_normal((12, 4)).astype(np.float32))
+    A = torch.from_numpy(rng.standard_normal((2, 4)).astype(np.float32))
+    assert torch.equal(port.lora_merge_qkv(qkv, A, torch.zeros(4, 2), A, torch.zeros(4, 2)), qkv)   # B = 0 -> frozen model
