@@ -1,0 +1,128 @@
+/* libcontinual_b200 — C ABI of the B200-native per-step training hot path of RL-VIG/LibContinual.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a cudaStream_t (passed as void*), launches
+ * asynchronously on that stream, performs no allocation and no host synchronisation (except the *_create / *_destroy
+ * calls), and returns 0 on success or a negative errno-style code (-22 invalid argument / unsupported shape, -5 CUDA
+ * error).  All tensors are fp32 unless stated; labels are int64.  Activations are NHWC (torch channels_last memory).
+ *
+ * The reference has no FFI: these calls replace eager ATen/cuDNN/cuBLAS op sequences issued by the Python classes cited on
+ * each entry (paths relative to the reference root).  The Python host that mirrors the reference plugin surface and binds
+ * this library through ctypes is `libcontinual_b200/`; INTEGRATION.md shows the stub a reference maintainer would add.
+ */
+#ifndef LC_B200_H
+#define LC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LC_OK 0
+#define LC_ERR_INVALID (-22)
+#define LC_ERR_CUDA (-5)
+
+typedef void* lc_stream_t; /* cudaStream_t */
+
+const char* lc_version(void);
+/* 0 when the current CUDA device is compute capability 10.x (the only target this library is built for). */
+int lc_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * CIFAR ResNet backbone (core/model/backbone/resnet.py:289-412 `CifarResNet`/`ResNetBasicblock`, factory :760-763).
+ * Parameter arena: the reference's `named_parameters()` order, conv weights OIHW.  Running-stat arena: per BN layer
+ * (mean[C], var[C]) in `named_buffers()` order (num_batches_tracked is kept by the host).  Workspace: opaque scratch of
+ * lc_resnet_workspace_floats() floats that the caller zero-fills ONCE after allocation.
+ * ------------------------------------------------------------------------------------------------------------------- */
+typedef struct lc_resnet lc_resnet;
+
+int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** out);
+void lc_resnet_destroy(lc_resnet* net);
+long long lc_resnet_param_count(const lc_resnet* net);
+long long lc_resnet_rstat_count(const lc_resnet* net);
+long long lc_resnet_workspace_floats(const lc_resnet* net);
+int lc_resnet_num_convs(const lc_resnet* net);
+int lc_resnet_num_launches(const lc_resnet* net, int backward);
+/* Layout of conv layer `idx` (reference registration order) inside the arenas; any out pointer may be NULL. */
+int lc_resnet_conv_info(const lc_resnet* net, int idx, long long* w_off, int* cout, int* cin, int* ksize, int* stride,
+                        long long* gamma_off, long long* beta_off, long long* rstat_off);
+enum { LC_WS_FEAT = 0, LC_WS_GRAD_LAST = 1, LC_WS_FMAP1 = 2, LC_WS_FMAP2 = 3, LC_WS_FMAP3 = 4, LC_WS_DFEAT = 5 };
+/* Float offset inside the workspace of: pooled features [B][64]; gradient w.r.t. the last feature map [B][8][8][64]
+ * (written by lc_head_backward, consumed by lc_resnet_backward); the three stage outputs (NHWC). */
+long long lc_resnet_ws_offset(const lc_resnet* net, int what);
+
+/* `CifarResNet.forward` up to the last residual block (pooling lives in lc_head_forward).  train != 0: batch statistics,
+ * running stats updated when update_running != 0 (nn.BatchNorm2d train mode); train == 0: running statistics. */
+int lc_resnet_forward(lc_resnet* net, const float* x_nchw, int batch, const float* params, float* rstat, float* workspace,
+                      int train, int update_running, lc_stream_t stream);
+/* Autograd of the above for every backbone parameter: consumes LC_WS_GRAD_LAST, writes grads[0 .. param_count). */
+int lc_resnet_backward(lc_resnet* net, const float* x_nchw, int batch, const float* params, float* workspace, float* grads,
+                       lc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Head + losses.
+ * lc_head_forward  : nn.AvgPool2d(8)+flatten (resnet.py:389-390) and nn.Linear (ewc.py:52-57, icarl.py:24-38, finetune.py:19).
+ * lc_loss_ce_kd    : F.cross_entropy over logits[:, ce_lo:ce_hi) with targets y-ce_lo (ewc.py:90-99, icarl.py:208-209,
+ *                    lwf.py:57-62) + kd_w * `_KD_loss`(logits[:, :kd_n], teacher[:, :kd_n], T) (icarl.py:198-206, lwf.py:75-78),
+ *                    d(loss)/d(logits), argmax over logits[:, :pred_n), #correct.  scal: [0] loss [1] #correct [2] ce [3] kd.
+ * lc_head_backward : Linear + AvgPool autograd: dW[ncls][C], db[ncls], dfeat[B][C], and the broadcast gradient of the last
+ *                    feature map (nullable).
+ * ------------------------------------------------------------------------------------------------------------------- */
+int lc_head_forward(const float* act_nhwc, int batch, int hw, int feat_dim, const float* W, const float* bias, int ncls,
+                    float* feat, float* logits, int ldl, lc_stream_t stream);
+int lc_loss_ce_kd(const float* logits, int ldl, const float* teacher, int ldt, const int64_t* y, int batch, int ce_lo, int ce_hi,
+                  int kd_n, float kd_w, float T, int pred_n, float* dlogits, int64_t* pred, float* scal, lc_stream_t stream);
+int lc_head_backward(const float* dlogits, int ldl, const float* feat, const float* W, int ncls, int batch, int feat_dim, float* dW,
+                     float* db, float* dfeat, float* gact, int hw, lc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Flat-arena kernels.  `hp` arrays live in DEVICE memory (CUDA-graph friendly).
+ * lc_ewc_penalty_grad : `EWC.compute_ewc` + autograd (ewc.py:207-225,100): grad += lamda*F*(theta-theta*);
+ *                       scal[4] = sum F (theta-theta*)^2 / 2 ; scal[0] += lamda * scal[4].   scratch >= 2*296+2 floats.
+ * lc_fisher_accumulate: fisher += grad^2 * weight (ewc.py:173).   lc_fisher_merge: fisher/num_samples, alpha-EMA (ewc.py:129-131,202-204).
+ * lc_sgd_momentum     : torch.optim.SGD step, hp = {lr, momentum, weight_decay}.
+ * lc_adam             : torch.optim.Adam step, hp = {lr, b1, b2, eps, wd, 1-b1^t, 1-b2^t}.
+ * lc_clip_grad_norm   : torch.nn.utils.clip_grad_norm_(.., max_norm) over one arena (l2p.py:104); scratch >= 2*296 floats.
+ * ------------------------------------------------------------------------------------------------------------------- */
+int lc_ewc_penalty_grad(const float* theta, const float* theta_ref, const float* fisher, float* grad, long long n, const float* hp_lamda,
+                        float* scratch, uint32_t* counter, float* scal, lc_stream_t stream);
+int lc_fisher_accumulate(float* fisher, const float* grad, long long n, float weight, lc_stream_t stream);
+int lc_fisher_merge(float* f_new, const float* f_old, long long n, float num_samples, float alpha, lc_stream_t stream);
+int lc_sgd_momentum(float* p, const float* g, float* m, long long n, const float* hp, lc_stream_t stream);
+int lc_adam(float* p, const float* g, float* m, float* v, long long n, const float* hp, lc_stream_t stream);
+int lc_clip_grad_norm(float* g, long long n, float max_norm, float* scratch, float* norm_out, lc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Per-kernel entry points (unit-tested individually; the network-level calls above are compositions of these).
+ * conv3x3: NHWC fp32, pad 1.  `w_oihw` is the native nn.Conv2d weight; mode 0 = forward, 1 = data gradient (input is dy).
+ * Supported (cin, cout, width_out, stride): the CifarResNet layer shapes.  `in_nchw` != 0: input is NCHW (network stem).
+ * Optional prologue relu(in*pro_scale+pro_shift) (per input channel), optional addend, optional BN statistics:
+ * stat_out = {scale[C], shift[C], mean[C], invstd[C]} and running-stat update (rstat = {mean[C], var[C]}, nullable).
+ * scratch: >= lc_conv_scratch_floats(...) floats, first 64 words zero.
+ * ------------------------------------------------------------------------------------------------------------------- */
+long long lc_conv_scratch_floats(int batch, int cin, int cout, int width_out);
+int lc_conv3x3(const float* in, const float* w_oihw, float* out, int batch, int cin, int cout, int width_out, int stride, int mode,
+               int in_nchw, const float* pro_scale, const float* pro_shift, const float* addend, const float* gamma,
+               const float* beta, float* rstat, float* stat_out, float* scratch, lc_stream_t stream);
+/* One launch of the forward conv kernel on pre-packed weights [cin][9][cout] (lc_conv3x3 leaves them at scratch+80). */
+int lc_conv3x3_packed(const float* in, const float* wpack, float* out, int batch, int cin, int cout, int width_out, int stride,
+                      const float* pro_scale, const float* pro_shift, lc_stream_t stream);
+int lc_conv3x3_wgrad(const float* in, const float* dy, float* dw_oihw, int batch, int cin, int cout, int width_out, int stride,
+                     int in_nchw, const float* pro_scale, const float* pro_shift, float* scratch, lc_stream_t stream);
+/* 1x1 stride-2 shortcut conv: mode 0 forward (+stats as above), 1 data gradient ACCUMULATED into `out` (shape of the conv
+ * input), 2 weight gradient into `out` ([cout][cin]). */
+int lc_conv1x1s2(const float* a, const float* b, float* out, int batch, int cin, int cout, int width_out, int mode, const float* gamma,
+                 const float* beta, float* rstat, float* stat_out, float* scratch, lc_stream_t stream);
+/* out = relu(y*scale+shift (+ res | + res*res_scale+res_shift)) over NHWC [npix][C]. */
+int lc_bn_act_forward(const float* y, const float* scale, const float* shift, const float* res, const float* res_scale,
+                      const float* res_shift, float* out, long long npix, int C, lc_stream_t stream);
+/* BatchNorm(+ReLU) backward. mask_mode 0: none, 1: g *= (mask_src > 0), 2: g *= (y*scale+shift > 0).  stat = {scale, shift,
+ * mean, invstd}.  Writes dy, dgamma[C], dbeta[C]; g_out (nullable) receives the masked g.  scratch >= 296*2*C + 3*C + 64. */
+int lc_bn_backward(const float* g, const float* mask_src, int mask_mode, const float* y, const float* stat, float* dy, float* g_out,
+                   float* dgamma, float* dbeta, long long npix, int C, float* scratch, lc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LC_B200_H */

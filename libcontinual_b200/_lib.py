@@ -1,0 +1,87 @@
+"""ctypes binding of the C-ABI CUDA library (`include/lc_b200.h`).  No fallback: if the shared object is missing or a
+call fails the product path raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_longlong, c_uint32, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "liblc_b200.so")
+
+_lib = None
+
+# name -> (restype, argtypes).  Kept in one table so the symbol-export test can walk it.
+P = c_void_p
+SIGNATURES = {
+    "lc_version": (c_char_p, []),
+    "lc_device_check": (c_int, []),
+    "lc_resnet_create": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "lc_resnet_destroy": (None, [P]),
+    "lc_resnet_param_count": (c_longlong, [P]),
+    "lc_resnet_rstat_count": (c_longlong, [P]),
+    "lc_resnet_workspace_floats": (c_longlong, [P]),
+    "lc_resnet_num_convs": (c_int, [P]),
+    "lc_resnet_num_launches": (c_int, [P, c_int]),
+    "lc_resnet_conv_info": (c_int, [P, c_int, POINTER(c_longlong), POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                                    POINTER(c_longlong), POINTER(c_longlong), POINTER(c_longlong)]),
+    "lc_resnet_ws_offset": (c_longlong, [P, c_int]),
+    "lc_resnet_forward": (c_int, [P, P, c_int, P, P, P, c_int, c_int, P]),
+    "lc_resnet_backward": (c_int, [P, P, c_int, P, P, P, P]),
+    "lc_head_forward": (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, P, c_int, P]),
+    "lc_loss_ce_kd": (c_int, [P, c_int, P, c_int, P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P]),
+    "lc_head_backward": (c_int, [P, c_int, P, P, c_int, c_int, c_int, P, P, P, P, c_int, P]),
+    "lc_ewc_penalty_grad": (c_int, [P, P, P, P, c_longlong, P, P, P, P, P]),
+    "lc_fisher_accumulate": (c_int, [P, P, c_longlong, c_float, P]),
+    "lc_fisher_merge": (c_int, [P, P, c_longlong, c_float, c_float, P]),
+    "lc_sgd_momentum": (c_int, [P, P, P, c_longlong, P, P]),
+    "lc_adam": (c_int, [P, P, P, P, c_longlong, P, P]),
+    "lc_clip_grad_norm": (c_int, [P, c_longlong, c_float, P, P, P]),
+    "lc_conv_scratch_floats": (c_longlong, [c_int, c_int, c_int, c_int]),
+    "lc_conv3x3": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P]),
+    "lc_conv3x3_packed": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "lc_conv3x3_wgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "lc_conv1x1s2": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
+    "lc_bn_act_forward": (c_int, [P, P, P, P, P, P, P, c_longlong, c_int, P]),
+    "lc_bn_backward": (c_int, [P, P, c_int, P, P, P, P, P, P, c_longlong, c_int, P, P]),
+}
+
+
+class LcError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the library once.  Raises if it has not been built (`python -m libcontinual_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LcError(f"{LIB_PATH} is missing: build it with `python -m libcontinual_b200.build` (nvcc, sm_100a). "
+                      "There is no CPU / PyTorch fallback for the hot path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise LcError(f"libcontinual_b200 call failed ({what}): code {rc}" + (" [invalid argument / unsupported shape]" if rc == -22 else " [CUDA error]"))
+
+
+def ptr(t):
+    """Device pointer of a tensor (or NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device-resident contiguous tensors only"
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream

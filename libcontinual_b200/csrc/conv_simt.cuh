@@ -1,0 +1,491 @@
+// fp32 NHWC direct-convolution kernels (CUDA-core path).  This is the "exact" arithmetic class: plain fp32 FMA,
+// deterministic reduction order, used as the parity anchor against the CPU oracle and by the exact-mode step.
+//
+// Replaces, for the CIFAR ResNet of core/model/backbone/resnet.py:289-412, the cuDNN fprop / dgrad / wgrad calls made
+// by nn.Conv2d(k=3, pad=1, bias=False) (resnet.py:295,298,334) and the 1x1 stride-2 shortcut conv (resnet.py:365-366),
+// with the BatchNorm batch-statistics reduction (resnet.py:296,299,335) fused into the conv epilogue and the
+// BN-apply + ReLU of the producer layer fused into the conv prologue.
+#pragma once
+#include "common.cuh"
+
+namespace lc {
+
+// ---------------------------------------------------------------------------------------------------------------
+// BatchNorm statistics: per-CTA partial (sum, sumsq) -> last CTA reduces in double, writes the affine form and
+// updates running statistics (nn.BatchNorm2d train-mode semantics: biased var for normalisation, unbiased for the
+// running estimate, momentum 0.1).
+// ---------------------------------------------------------------------------------------------------------------
+struct BnStatArgs {
+    float* partial;            // [nparts][2][C]  (null -> no statistics)
+    unsigned int* counter;     // self-resetting election counter
+    const float* gamma;        // [C]
+    const float* beta;         // [C]
+    float* running_mean;       // [C]  (updated when update_running != 0)
+    float* running_var;        // [C]
+    float* scale;              // out [C] : gamma * invstd
+    float* shift;              // out [C] : beta - mean * gamma * invstd
+    float* mean;               // out [C]
+    float* invstd;             // out [C]
+    float momentum;
+    float eps;
+    int update_running;
+};
+
+template <int C, int NT>
+__device__ __forceinline__ void bn_finalize_last_block(const BnStatArgs& s, int nparts, double count, float* s_red /* >= NT floats*2 as double */) {
+    // every thread: one (stat, channel) column j = tid % (2C), slice = tid / (2C)
+    constexpr int COLS = 2 * C;
+    static_assert(NT % COLS == 0 || COLS % NT == 0, "thread count vs channel count");
+    double* red = reinterpret_cast<double*>(s_red);
+    if (NT >= COLS) {
+        constexpr int NSL = NT >= COLS ? NT / COLS : 1;
+        const int j = threadIdx.x % COLS, sl = threadIdx.x / COLS;
+        double acc = 0.0;
+        for (int p = sl; p < nparts; p += NSL) acc += (double)__ldcg(s.partial + (size_t)p * COLS + j);
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.x < COLS) {
+            double t = 0.0;
+            for (int q = 0; q < NSL; ++q) t += red[q * COLS + threadIdx.x];
+            red[threadIdx.x] = t;
+        }
+        __syncthreads();
+    } else {
+        for (int j = threadIdx.x; j < COLS; j += NT) {
+            double acc = 0.0;
+            for (int p = 0; p < nparts; ++p) acc += (double)__ldcg(s.partial + (size_t)p * COLS + j);
+            red[j] = acc;
+        }
+        __syncthreads();
+    }
+    for (int c = threadIdx.x; c < C; c += NT) {
+        const double m = red[c] / count;
+        double var = red[C + c] / count - m * m;
+        if (var < 0.0) var = 0.0;
+        const double istd = 1.0 / sqrt(var + (double)s.eps);
+        const float g = s.gamma[c], b = s.beta[c];
+        const float sc = (float)((double)g * istd);
+        s.scale[c] = sc;
+        s.shift[c] = (float)((double)b - m * (double)g * istd);
+        s.mean[c] = (float)m;
+        s.invstd[c] = (float)istd;
+        if (s.update_running) {
+            const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+            s.running_mean[c] = (float)((1.0 - (double)s.momentum) * (double)s.running_mean[c] + (double)s.momentum * m);
+            s.running_var[c] = (float)((1.0 - (double)s.momentum) * (double)s.running_var[c] + (double)s.momentum * unb);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3x3 convolution, pad 1, stride 1 or 2; forward and (with packed-transposed weights) data-gradient.
+// ---------------------------------------------------------------------------------------------------------------
+struct Conv3x3Args {
+    const float* in;          // NHWC [B][HI][WI][CIN] (HI = HO*STRIDE; DILATE: real tensor is [B][HO/2][WO/2][CIN]) or NCHW (IN_NCHW)
+    const float* wpack;       // [CIN][9][COUT]
+    float* out;               // NHWC [B][HO][WO][COUT]
+    const float* pro_scale;   // nullable: input transform relu(x*scale[c]+shift[c]) applied on load (zero padding stays zero)
+    const float* pro_shift;
+    const float* addend;      // nullable: out += addend   (may alias out)
+    BnStatArgs stat;          // stat.partial nullable
+    int B;
+};
+
+constexpr int conv_row_pitch(int iw_t, int lr, int pt, int stride) {
+    // smallest pitch >= iw_t that keeps the LR row-groups of a warp on disjoint banks
+    int want = lr == 1 ? -1 : (lr == 2 ? 16 : 8);
+    for (int rp = iw_t; rp < iw_t + 33; ++rp) {
+        if (lr == 1) return rp;
+        int m = (pt * stride * rp) % 32;
+        if (m == want || (lr == 4 && m == 24)) return rp;
+    }
+    return iw_t;
+}
+constexpr int conv_plane_stride(int n, int cin) {
+    if (cin == 16) { while (n % 8 != 2) ++n; return n; }
+    return n | 1;
+}
+
+template <int CIN, int COUT, int WO, int PT, int CT, int RS, int COUT_CTA, int CIN_CHUNK, int STRIDE, bool DILATE, bool IN_NCHW>
+struct Conv3x3Cfg {
+    static constexpr int HO = WO;
+    static constexpr int LR = 32 / WO;
+    static constexpr int TILE_H = RS * LR * PT;
+    static constexpr int CG = COUT_CTA / CT;
+    static constexpr int NWARP = RS * CG;
+    static constexpr int NT = NWARP * 32;
+    static constexpr int IH_T = (TILE_H - 1) * STRIDE + 3;
+    static constexpr int IW_T = (WO - 1) * STRIDE + 3;
+    static constexpr int RP = conv_row_pitch(IW_T, LR, PT, STRIDE);
+    static constexpr int PS = conv_plane_stride(IH_T * RP, CIN);
+    static constexpr int TILES_PER_IMG = HO / TILE_H;
+    static constexpr int COUT_SPLIT = COUT / COUT_CTA;
+    static constexpr int HI = HO * STRIDE;   // virtual input extent
+    static constexpr int WI = WO * STRIDE;
+    static constexpr int SMEM_IN = ((CIN * PS + 3) / 4) * 4;   // keeps s_w 16-byte aligned
+    static constexpr int SMEM_W = CIN_CHUNK * 9 * COUT_CTA;
+    static constexpr int SMEM_STAT = NWARP * CT * 2;
+    static constexpr int SMEM_RED = 2 * NT > 4 * COUT ? 2 * NT : 4 * COUT;   // doubles for the finalize
+    static constexpr size_t SMEM_BYTES = sizeof(float) * (SMEM_IN + SMEM_W + (SMEM_STAT > SMEM_RED ? SMEM_STAT : SMEM_RED) + 4);
+    static_assert(32 % WO == 0 && HO % TILE_H == 0 && COUT % COUT_CTA == 0 && COUT_CTA % CT == 0 && CT % 4 == 0, "tiling");
+    static_assert(CIN % CIN_CHUNK == 0, "cin chunk");
+    static_assert(!(DILATE && STRIDE != 1), "dilated input implies stride 1");
+};
+
+template <int CIN, int COUT, int WO, int PT, int CT, int RS, int COUT_CTA, int CIN_CHUNK, int STRIDE, bool DILATE, bool IN_NCHW>
+__global__ void __launch_bounds__(Conv3x3Cfg<CIN, COUT, WO, PT, CT, RS, COUT_CTA, CIN_CHUNK, STRIDE, DILATE, IN_NCHW>::NT)
+conv3x3_kernel(Conv3x3Args a) {
+    using K = Conv3x3Cfg<CIN, COUT, WO, PT, CT, RS, COUT_CTA, CIN_CHUNK, STRIDE, DILATE, IN_NCHW>;
+    extern __shared__ __align__(16) float smem[];
+    float* s_in = smem;
+    float* s_w = smem + K::SMEM_IN;
+    float* s_x = s_w + K::SMEM_W;   // stats / finalize scratch (8-byte aligned: SMEM_IN + SMEM_W is even, see below)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.y;
+    const int tile = blockIdx.x % K::TILES_PER_IMG;
+    const int cosplit = blockIdx.x / K::TILES_PER_IMG;
+    const int co_base = cosplit * COUT_CTA;
+    const int oh0 = tile * K::TILE_H;
+    const int ih0 = oh0 * STRIDE - 1;   // first (virtual) input row of the tile
+
+    // ---- stage the input tile, channel-planar, applying the producer's BN+ReLU on the fly ----------------------
+    if constexpr (IN_NCHW) {
+        constexpr int TOT = CIN * K::IH_T * K::IW_T;
+        for (int e = tid; e < TOT; e += K::NT) {
+            const int c = e % K::IW_T, r = (e / K::IW_T) % K::IH_T, ci = e / (K::IW_T * K::IH_T);
+            const int ih = ih0 + r, iw = c - 1;
+            float v = 0.f;
+            if (ih >= 0 && ih < K::HI && iw >= 0 && iw < K::WI) v = __ldg(a.in + (((size_t)n * CIN + ci) * K::HI + ih) * K::WI + iw);
+            s_in[ci * K::PS + r * K::RP + c] = v;
+        }
+    } else {
+        constexpr int G4 = CIN / 4;
+        constexpr int TOT = K::IH_T * K::IW_T * G4;
+        const bool pro = a.pro_scale != nullptr;
+        for (int e = tid; e < TOT; e += K::NT) {
+            const int g = e % G4, c = (e / G4) % K::IW_T, r = e / (G4 * K::IW_T);
+            const int ih = ih0 + r, iw = c - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool ok = ih >= 0 && ih < K::HI && iw >= 0 && iw < K::WI;
+            size_t off;
+            if constexpr (DILATE) {
+                ok = ok && ((ih & 1) == 0) && ((iw & 1) == 0);
+                off = (((size_t)n * (K::HI / 2) + (ih >> 1)) * (K::WI / 2) + (iw >> 1)) * CIN + g * 4;
+            } else {
+                off = (((size_t)n * K::HI + ih) * K::WI + iw) * CIN + g * 4;
+            }
+            if (ok) {
+                v = ldg4(a.in + off);
+                if (pro) {
+                    const float4 sc = ldg4(a.pro_scale + g * 4), sh = ldg4(a.pro_shift + g * 4);
+                    v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
+                    v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+                    v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
+                    v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+                }
+            }
+            float* d = s_in + (g * 4) * K::PS + r * K::RP + c;
+            d[0] = v.x; d[K::PS] = v.y; d[2 * K::PS] = v.z; d[3 * K::PS] = v.w;
+        }
+    }
+
+    // ---- thread tile --------------------------------------------------------------------------------------------
+    const int strip = warp / K::CG, cg = warp % K::CG;
+    const int c = lane % WO, rsub = lane / WO;
+    const int orow0 = (strip * K::LR + rsub) * PT;       // tile-local first output row of this thread
+    constexpr int NV = (PT - 1) * STRIDE + 3;
+    float acc[PT][CT];
+#pragma unroll
+    for (int i = 0; i < PT; ++i)
+#pragma unroll
+        for (int k = 0; k < CT; ++k) acc[i][k] = 0.f;
+
+    for (int c0 = 0; c0 < CIN; c0 += CIN_CHUNK) {
+        __syncthreads();   // previous chunk's weights consumed (and, first time, nothing)
+        {
+            constexpr int W4 = COUT_CTA / 4;
+            constexpr int TOTW = CIN_CHUNK * 9 * W4;
+            for (int e = tid; e < TOTW; e += K::NT) {
+                const int q = e % W4, row = e / W4;                 // row = ci_local*9 + tap
+                const float4 w = ldg4(a.wpack + ((size_t)(c0 * 9 + row)) * COUT + co_base + q * 4);
+                *reinterpret_cast<float4*>(s_w + row * COUT_CTA + q * 4) = w;
+            }
+        }
+        __syncthreads();   // weights (and, first time, the input tile) visible
+#pragma unroll 1
+        for (int ci = 0; ci < CIN_CHUNK; ++ci) {
+            const float* plane = s_in + (c0 + ci) * K::PS + (orow0 * STRIDE) * K::RP + c * STRIDE;
+            const float* wrow = s_w + ci * 9 * COUT_CTA + cg * CT;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                float v[NV];
+#pragma unroll
+                for (int j = 0; j < NV; ++j) v[j] = plane[j * K::RP + s];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    float w[CT];
+#pragma unroll
+                    for (int k4 = 0; k4 < CT / 4; ++k4) {
+                        const float4 t = *reinterpret_cast<const float4*>(wrow + (r * 3 + s) * COUT_CTA + k4 * 4);
+                        w[k4 * 4 + 0] = t.x; w[k4 * 4 + 1] = t.y; w[k4 * 4 + 2] = t.z; w[k4 * 4 + 3] = t.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < PT; ++i)
+#pragma unroll
+                        for (int k = 0; k < CT; ++k) acc[i][k] = fmaf(v[i * STRIDE + r], w[k], acc[i][k]);
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: optional addend, store, optional BN statistics ----------------------------------------------------
+    const int co0 = co_base + cg * CT;
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+        const int oh = oh0 + orow0 + i;
+        const size_t o = (((size_t)n * K::HO + oh) * WO + c) * COUT + co0;
+        if (a.addend != nullptr) {
+#pragma unroll
+            for (int k4 = 0; k4 < CT / 4; ++k4) {
+                const float4 t = *reinterpret_cast<const float4*>(a.addend + o + k4 * 4);
+                acc[i][k4 * 4 + 0] += t.x; acc[i][k4 * 4 + 1] += t.y; acc[i][k4 * 4 + 2] += t.z; acc[i][k4 * 4 + 3] += t.w;
+            }
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < CT / 4; ++k4)
+            *reinterpret_cast<float4*>(a.out + o + k4 * 4) = make_float4(acc[i][k4 * 4], acc[i][k4 * 4 + 1], acc[i][k4 * 4 + 2], acc[i][k4 * 4 + 3]);
+    }
+
+    if (a.stat.partial != nullptr) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < CT; ++k) {
+            float sm = 0.f, sq = 0.f;
+#pragma unroll
+            for (int i = 0; i < PT; ++i) { sm += acc[i][k]; sq = fmaf(acc[i][k], acc[i][k], sq); }
+            sm = warp_sum(sm); sq = warp_sum(sq);
+            if (lane == 0) { s_x[(warp * CT + k) * 2] = sm; s_x[(warp * CT + k) * 2 + 1] = sq; }
+        }
+        __syncthreads();
+        const int part = n * K::TILES_PER_IMG + tile;
+        const int nparts = a.B * K::TILES_PER_IMG;
+        if (tid < COUT_CTA * 2) {
+            const int stat = tid / COUT_CTA, ch = tid % COUT_CTA;          // ch within this CTA's cout slice
+            const int cgi = ch / CT, k = ch % CT;
+            float t = 0.f;
+#pragma unroll
+            for (int st = 0; st < RS; ++st) t += s_x[((st * K::CG + cgi) * CT + k) * 2 + stat];
+            a.stat.partial[((size_t)part * 2 + stat) * COUT + co_base + ch] = t;
+        }
+        const unsigned int nblocks = gridDim.x * gridDim.y;
+        if (last_block_done(a.stat.counter, nblocks)) {
+            bn_finalize_last_block<COUT, K::NT>(a.stat, nparts, (double)a.B * K::HO * WO, s_x);
+        }
+    }
+}
+
+template <typename KCfg, typename Kern>
+static inline int conv_launch(Kern kern, const Conv3x3Args& a, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (KCfg::SMEM_BYTES > 48 * 1024) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KCfg::SMEM_BYTES) != cudaSuccess) return LC_ERR_CUDA;
+        }
+        attr_done = true;
+    }
+    dim3 grid(KCfg::TILES_PER_IMG * KCfg::COUT_SPLIT, a.B);
+    kern<<<grid, KCfg::NT, KCfg::SMEM_BYTES, st>>>(a);
+    return lc_launch_status();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3x3 weight gradient:  dW[o][i][r][s] = sum_{n,oh,ow} dy[n,oh,ow,o] * a[n, oh*S+r-1, ow*S+s-1, i]
+// Each CTA accumulates a K-slice (a strided set of (image,row-tile)s) in registers and writes one partial
+// [COUT][CIN][9]; all layers' partials are summed in fixed order by wgrad_reduce_all_kernel (deterministic).
+// ---------------------------------------------------------------------------------------------------------------
+struct WgradArgs {
+    const float* in;          // NHWC [B][HI][WI][CIN] or NCHW (IN_NCHW)
+    const float* dy;          // NHWC [B][HO][WO][COUT]
+    float* partial;           // [nsplit][COUT][CIN][9]
+    const float* pro_scale;   // nullable prologue on `in`
+    const float* pro_shift;
+    int B;
+    int nsplit;
+};
+
+template <int CIN, int COUT, int WO, int STRIDE, int CI_CTA, int KS, int TILE_H, bool IN_NCHW>
+struct WgradCfg {
+    static constexpr int HO = WO;
+    static constexpr int OG = COUT / 4;
+    static constexpr int NT = CI_CTA * OG * KS;
+    static constexpr int IH_T = (TILE_H - 1) * STRIDE + 3;
+    static constexpr int IW_T = (WO - 1) * STRIDE + 3;
+    static constexpr int RP = IW_T;
+    static constexpr int PS = (IH_T * RP) | 1;
+    static constexpr int HI = HO * STRIDE, WI = WO * STRIDE;
+    static constexpr int TILES_PER_IMG = HO / TILE_H;
+    static constexpr int SMEM_A = ((CI_CTA * PS + 3) / 4) * 4;
+    static constexpr int SMEM_DY = TILE_H * WO * COUT;
+    static constexpr int SMEM_RED = CI_CTA * OG * 36;
+    static constexpr int SMEM_MAIN = SMEM_A + SMEM_DY;
+    static constexpr size_t SMEM_BYTES = sizeof(float) * (SMEM_MAIN > SMEM_RED ? SMEM_MAIN : SMEM_RED);
+    static constexpr int CIN_SPLIT = (CIN + CI_CTA - 1) / CI_CTA;
+    static_assert(HO % TILE_H == 0 && COUT % 4 == 0 && NT <= 1024 && NT % 32 == 0, "wgrad tiling");
+};
+
+template <int CIN, int COUT, int WO, int STRIDE, int CI_CTA, int KS, int TILE_H, bool IN_NCHW>
+__global__ void __launch_bounds__(WgradCfg<CIN, COUT, WO, STRIDE, CI_CTA, KS, TILE_H, IN_NCHW>::NT)
+wgrad3x3_kernel(WgradArgs a) {
+    using K = WgradCfg<CIN, COUT, WO, STRIDE, CI_CTA, KS, TILE_H, IN_NCHW>;
+    extern __shared__ __align__(16) float smem[];
+    float* s_a = smem;
+    float* s_dy = smem + K::SMEM_A;   // 16-byte aligned
+
+    const int tid = threadIdx.x;
+    const int ci_l = tid % CI_CTA;
+    const int og = (tid / CI_CTA) % K::OG;
+    const int ks = tid / (CI_CTA * K::OG);
+    const int ci0 = blockIdx.y * CI_CTA;
+    const bool ci_ok = (ci0 + ci_l) < CIN;
+
+    float acc[4][9];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[k][t] = 0.f;
+
+    const int ntiles = a.B * K::TILES_PER_IMG;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int n = t / K::TILES_PER_IMG, tile = t % K::TILES_PER_IMG;
+        const int oh0 = tile * TILE_H, ih0 = oh0 * STRIDE - 1;
+        __syncthreads();
+        // input tile, planar [ci][row][col]
+        if constexpr (IN_NCHW) {
+            constexpr int TOT = CI_CTA * K::IH_T * K::IW_T;
+            for (int e = tid; e < TOT; e += K::NT) {
+                const int c = e % K::IW_T, r = (e / K::IW_T) % K::IH_T, ci = e / (K::IW_T * K::IH_T);
+                const int ih = ih0 + r, iw = c - 1;
+                float v = 0.f;
+                if ((ci0 + ci) < CIN && ih >= 0 && ih < K::HI && iw >= 0 && iw < K::WI)
+                    v = __ldg(a.in + (((size_t)n * CIN + ci0 + ci) * K::HI + ih) * K::WI + iw);
+                s_a[ci * K::PS + r * K::RP + c] = v;
+            }
+        } else {
+            constexpr int G4 = CI_CTA / 4;
+            constexpr int TOT = K::IH_T * K::IW_T * G4;
+            const bool pro = a.pro_scale != nullptr;
+            for (int e = tid; e < TOT; e += K::NT) {
+                const int g = e % G4, c = (e / G4) % K::IW_T, r = e / (G4 * K::IW_T);
+                const int ih = ih0 + r, iw = c - 1;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ih >= 0 && ih < K::HI && iw >= 0 && iw < K::WI) {
+                    v = ldg4(a.in + (((size_t)n * K::HI + ih) * K::WI + iw) * CIN + ci0 + g * 4);
+                    if (pro) {
+                        const float4 sc = ldg4(a.pro_scale + ci0 + g * 4), sh = ldg4(a.pro_shift + ci0 + g * 4);
+                        v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
+                        v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+                        v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
+                        v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+                    }
+                }
+                float* d = s_a + (g * 4) * K::PS + r * K::RP + c;
+                d[0] = v.x; d[K::PS] = v.y; d[2 * K::PS] = v.z; d[3 * K::PS] = v.w;
+            }
+        }
+        // dy tile [pixel][COUT] (contiguous in NHWC)
+        {
+            constexpr int TOT4 = TILE_H * WO * COUT / 4;
+            const float* src = a.dy + (((size_t)n * K::HO + oh0) * WO) * COUT;
+            for (int e = tid; e < TOT4; e += K::NT) *reinterpret_cast<float4*>(s_dy + e * 4) = ldg4(src + e * 4);
+        }
+        __syncthreads();
+
+        const float* plane = s_a + ci_l * K::PS;
+        for (int ohl = ks; ohl < TILE_H; ohl += KS) {
+            const float* prow = plane + (ohl * STRIDE) * K::RP;
+            if constexpr (STRIDE == 1) {
+                float w0[3], w1[3], w2[3];   // window columns: w0 = iw-1, w1 = iw, w2 = iw+1 (each 3 rows)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { w1[r] = prow[r * K::RP + 0]; w2[r] = prow[r * K::RP + 1]; }
+#pragma unroll 4
+                for (int ow = 0; ow < WO; ++ow) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) { w0[r] = w1[r]; w1[r] = w2[r]; w2[r] = prow[r * K::RP + ow + 2]; }
+                    const float4 d = *reinterpret_cast<const float4*>(s_dy + (ohl * WO + ow) * COUT + og * 4);
+                    const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            acc[k][r * 3 + 0] = fmaf(dd[k], w0[r], acc[k][r * 3 + 0]);
+                            acc[k][r * 3 + 1] = fmaf(dd[k], w1[r], acc[k][r * 3 + 1]);
+                            acc[k][r * 3 + 2] = fmaf(dd[k], w2[r], acc[k][r * 3 + 2]);
+                        }
+                }
+            } else {
+#pragma unroll 2
+                for (int ow = 0; ow < WO; ++ow) {
+                    float w[9];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int s = 0; s < 3; ++s) w[r * 3 + s] = prow[r * K::RP + ow * STRIDE + s];
+                    const float4 d = *reinterpret_cast<const float4*>(s_dy + (ohl * WO + ow) * COUT + og * 4);
+                    const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) acc[k][q] = fmaf(dd[k], w[q], acc[k][q]);
+                }
+            }
+        }
+    }
+
+    // ---- reduce the KS in-CTA slices in fixed order, then write this CTA's partial ---------------------------------
+    if constexpr (KS > 1) {
+        float* s_red = smem;
+        const int slot = (og * CI_CTA + ci_l) * 36;
+        for (int q = 1; q < KS; ++q) {
+            __syncthreads();
+            if (ks == q) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) s_red[slot + k * 9 + t] = acc[k][t];
+            }
+            __syncthreads();
+            if (ks == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) acc[k][t] += s_red[slot + k * 9 + t];
+            }
+        }
+    }
+    if (ks == 0 && ci_ok) {
+        float* dst = a.partial + (size_t)blockIdx.x * COUT * CIN * 9;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float* p = dst + ((size_t)(og * 4 + k) * CIN + ci0 + ci_l) * 9;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) p[t] = acc[k][t];
+        }
+    }
+}
+
+template <typename KCfg, typename Kern>
+static inline int wgrad_launch(Kern kern, const WgradArgs& a, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (KCfg::SMEM_BYTES > 48 * 1024) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KCfg::SMEM_BYTES) != cudaSuccess) return LC_ERR_CUDA;
+        }
+        attr_done = true;
+    }
+    dim3 grid(a.nsplit, KCfg::CIN_SPLIT);
+    kern<<<grid, KCfg::NT, KCfg::SMEM_BYTES, st>>>(a);
+    return lc_launch_status();
+}
+
+}  // namespace lc

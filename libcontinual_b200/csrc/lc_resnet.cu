@@ -1,0 +1,655 @@
+// Network-level driver for the CIFAR ResNet backbone + the per-kernel C entry points.  Host code only launches kernels;
+// all arithmetic lives in the .cuh kernels.  See include/lc_b200.h for the contract of every exported symbol.
+#include "../../include/lc_b200.h"
+#include "bn_elem.cuh"
+#include "conv_aux.cuh"
+#include "conv_simt.cuh"
+#include "flat_ops.cuh"
+#include "head_loss.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace lc;
+
+namespace {
+
+constexpr float kBnEps = 1e-5f;       // nn.BatchNorm2d defaults (resnet.py:296)
+constexpr float kBnMomentum = 0.1f;
+constexpr int kBnBwdBlocks = 296;
+
+// ---- kernel configurations for the CifarResNet layer shapes ------------------------------------------------------
+//                      CIN COUT WO PT CT RS COUT_CTA CHUNK STRIDE DILATE NCHW
+using CfgStem = Conv3x3Cfg<3, 16, 32, 4, 8, 2, 16, 3, 1, false, true>;
+using CfgS1 = Conv3x3Cfg<16, 16, 32, 4, 8, 2, 16, 16, 1, false, false>;
+using CfgS2F = Conv3x3Cfg<16, 32, 16, 2, 8, 1, 32, 16, 2, false, false>;
+using CfgS2 = Conv3x3Cfg<32, 32, 16, 4, 8, 1, 32, 16, 1, false, false>;
+using CfgS3F = Conv3x3Cfg<32, 64, 8, 2, 8, 1, 32, 8, 2, false, false>;
+using CfgS3 = Conv3x3Cfg<64, 64, 8, 2, 8, 1, 32, 16, 1, false, false>;
+using CfgD2 = Conv3x3Cfg<32, 16, 32, 4, 8, 2, 16, 8, 1, true, false>;   // dgrad of S2F
+using CfgD3 = Conv3x3Cfg<64, 32, 16, 4, 8, 1, 32, 8, 1, true, false>;   // dgrad of S3F
+
+#define LC_CONV_KERNEL(CFG, ...) conv3x3_kernel<__VA_ARGS__>
+
+int launch_conv3x3(int cin, int cout, int wo, int stride, bool dilate, bool nchw, const Conv3x3Args& a, cudaStream_t st) {
+    if (nchw && cin == 3 && cout == 16 && wo == 32 && stride == 1 && !dilate)
+        return conv_launch<CfgStem>(conv3x3_kernel<3, 16, 32, 4, 8, 2, 16, 3, 1, false, true>, a, st);
+    if (nchw) return LC_ERR_INVALID;
+    if (!dilate) {
+        if (cin == 16 && cout == 16 && wo == 32 && stride == 1) return conv_launch<CfgS1>(conv3x3_kernel<16, 16, 32, 4, 8, 2, 16, 16, 1, false, false>, a, st);
+        if (cin == 16 && cout == 32 && wo == 16 && stride == 2) return conv_launch<CfgS2F>(conv3x3_kernel<16, 32, 16, 2, 8, 1, 32, 16, 2, false, false>, a, st);
+        if (cin == 32 && cout == 32 && wo == 16 && stride == 1) return conv_launch<CfgS2>(conv3x3_kernel<32, 32, 16, 4, 8, 1, 32, 16, 1, false, false>, a, st);
+        if (cin == 32 && cout == 64 && wo == 8 && stride == 2) return conv_launch<CfgS3F>(conv3x3_kernel<32, 64, 8, 2, 8, 1, 32, 8, 2, false, false>, a, st);
+        if (cin == 64 && cout == 64 && wo == 8 && stride == 1) return conv_launch<CfgS3>(conv3x3_kernel<64, 64, 8, 2, 8, 1, 32, 16, 1, false, false>, a, st);
+    } else {
+        if (cin == 32 && cout == 16 && wo == 32) return conv_launch<CfgD2>(conv3x3_kernel<32, 16, 32, 4, 8, 2, 16, 8, 1, true, false>, a, st);
+        if (cin == 64 && cout == 32 && wo == 16) return conv_launch<CfgD3>(conv3x3_kernel<64, 32, 16, 4, 8, 1, 32, 8, 1, true, false>, a, st);
+    }
+    return LC_ERR_INVALID;
+}
+
+//                     CIN COUT WO STRIDE CI_CTA KS TILE_H NCHW
+using WCfgStem = WgradCfg<3, 16, 32, 1, 4, 16, 16, true>;
+using WCfgS1 = WgradCfg<16, 16, 32, 1, 16, 4, 8, false>;
+using WCfgS2F = WgradCfg<16, 32, 16, 2, 16, 2, 8, false>;
+using WCfgS2 = WgradCfg<32, 32, 16, 1, 32, 1, 8, false>;
+using WCfgS3F = WgradCfg<32, 64, 8, 2, 16, 1, 8, false>;
+using WCfgS3 = WgradCfg<64, 64, 8, 1, 16, 1, 8, false>;
+
+int launch_wgrad3x3(int cin, int cout, int wo, int stride, bool nchw, const WgradArgs& a, cudaStream_t st) {
+    if (nchw && cin == 3 && cout == 16 && wo == 32 && stride == 1) return wgrad_launch<WCfgStem>(wgrad3x3_kernel<3, 16, 32, 1, 4, 16, 16, true>, a, st);
+    if (nchw) return LC_ERR_INVALID;
+    if (cin == 16 && cout == 16 && wo == 32 && stride == 1) return wgrad_launch<WCfgS1>(wgrad3x3_kernel<16, 16, 32, 1, 16, 4, 8, false>, a, st);
+    if (cin == 16 && cout == 32 && wo == 16 && stride == 2) return wgrad_launch<WCfgS2F>(wgrad3x3_kernel<16, 32, 16, 2, 16, 2, 8, false>, a, st);
+    if (cin == 32 && cout == 32 && wo == 16 && stride == 1) return wgrad_launch<WCfgS2>(wgrad3x3_kernel<32, 32, 16, 1, 32, 1, 8, false>, a, st);
+    if (cin == 32 && cout == 64 && wo == 8 && stride == 2) return wgrad_launch<WCfgS3F>(wgrad3x3_kernel<32, 64, 8, 2, 16, 1, 8, false>, a, st);
+    if (cin == 64 && cout == 64 && wo == 8 && stride == 1) return wgrad_launch<WCfgS3>(wgrad3x3_kernel<64, 64, 8, 1, 16, 1, 8, false>, a, st);
+    return LC_ERR_INVALID;
+}
+
+int wgrad_nsplit(int cin, int cout) {
+    if (cout == 16) return 256;
+    if (cout == 32) return 128;
+    return 32;      // cout 64 (x CIN_SPLIT CTAs)
+}
+
+int launch_conv1x1_fwd(int cin, int cout, int wo, const Conv1x1Args& a, cudaStream_t st) {
+    const long long npix = (long long)a.B * wo * wo;
+    const int grid = (int)((npix + 127) / 128);
+    if (cin == 16 && cout == 32 && wo == 16) conv1x1s2_fwd_kernel<16, 32, 16><<<grid, 128, 0, st>>>(a);
+    else if (cin == 32 && cout == 64 && wo == 8) conv1x1s2_fwd_kernel<32, 64, 8><<<grid, 128, 0, st>>>(a);
+    else return LC_ERR_INVALID;
+    return lc_launch_status();
+}
+int launch_conv1x1_dgrad(int cin, int cout, int wo, const float* dy, const float* w, float* gin, int B, cudaStream_t st) {
+    const long long npix = (long long)B * wo * wo;
+    const int grid = (int)((npix + 127) / 128);
+    if (cin == 16 && cout == 32 && wo == 16) conv1x1s2_dgrad_accum_kernel<16, 32, 16><<<grid, 128, 0, st>>>(dy, w, gin, B);
+    else if (cin == 32 && cout == 64 && wo == 8) conv1x1s2_dgrad_accum_kernel<32, 64, 8><<<grid, 128, 0, st>>>(dy, w, gin, B);
+    else return LC_ERR_INVALID;
+    return lc_launch_status();
+}
+constexpr int k1x1Split = 64;
+int launch_conv1x1_wgrad(int cin, int cout, int wo, const float* in, const float* dy, float* partial, int B, cudaStream_t st) {
+    if (cin == 16 && cout == 32 && wo == 16) conv1x1s2_wgrad_kernel<16, 32, 16><<<k1x1Split, 256, 0, st>>>(in, dy, partial, B);
+    else if (cin == 32 && cout == 64 && wo == 8) conv1x1s2_wgrad_kernel<32, 64, 8><<<k1x1Split, 256, 0, st>>>(in, dy, partial, B);
+    else return LC_ERR_INVALID;
+    return lc_launch_status();
+}
+
+int launch_bn_bwd(const BnBwdArgs& a0, cudaStream_t st) {
+    BnBwdArgs a = a0;
+    long long blocks = (a.npix + 63) / 64;
+    const int grid = (int)(blocks < kBnBwdBlocks ? blocks : kBnBwdBlocks);
+    if (a.C == 16) bn_bwd_reduce_kernel<16><<<grid, 256, 0, st>>>(a);
+    else if (a.C == 32) bn_bwd_reduce_kernel<32><<<grid, 256, 0, st>>>(a);
+    else if (a.C == 64) bn_bwd_reduce_kernel<64><<<grid, 256, 0, st>>>(a);
+    else return LC_ERR_INVALID;
+    if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
+    bn_bwd_apply_kernel<<<elem_grid(a.npix * (a.C / 4)), 256, 0, st>>>(a);
+    return lc_launch_status();
+}
+
+int launch_bn_act(const BnActArgs& a, cudaStream_t st) {
+    bn_act_fwd_kernel<<<elem_grid(a.n4), 256, 0, st>>>(a);
+    return lc_launch_status();
+}
+
+// ---- plan ----------------------------------------------------------------------------------------------------------
+struct ConvL {
+    int cin, cout, ksize, stride, wo;     // wo = output width
+    long long w_off, gamma_off, beta_off; // parameter arena
+    long long rstat_off;                  // running-stat arena (mean[C], var[C])
+    long long aff_off;                    // workspace: scale, shift, mean, invstd (4*C)
+    long long y_off;                      // workspace: raw conv output
+    long long wf_off, wd_off, part_off;   // workspace-relative (packed weights / partials)
+    int nsplit;
+};
+struct BlockL {
+    int conv_a, conv_b, conv_d;   // conv indices (conv_d = -1: identity shortcut)
+    int stage;                    // 0,1,2
+    long long out_off;            // workspace: block output (post ReLU)
+};
+
+}  // namespace
+
+struct lc_resnet {
+    int depth, in_ch, img, max_batch, nblk;
+    std::vector<ConvL> convs;
+    std::vector<BlockL> blocks;
+    long long n_params = 0, n_rstat = 0, ws_floats = 0;
+    // workspace offsets (floats)
+    long long off_counters, off_aff, off_fpart, off_bpart, off_coef, off_packed, off_wpart, off_feat, off_dfeat, off_a0, off_G[3], off_T1, off_T2, off_T3;
+    long long packed_floats = 0, wpart_floats = 0;
+    ConvTabEntry* d_tab = nullptr;
+    BnEvalEntry* d_bntab = nullptr;
+    int tab_blocks = 0;
+    int launches_fwd = 0, launches_bwd = 0;
+};
+
+extern "C" {
+
+const char* lc_version(void) { return "libcontinual_b200 0.1 (sm_100a)"; }
+
+int lc_device_check(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return LC_ERR_CUDA;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return LC_ERR_CUDA;
+    return p.major == 10 ? LC_OK : LC_ERR_INVALID;
+}
+
+int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** out) {
+    LC_CHECK_ARG(out != nullptr && (depth - 2) % 6 == 0 && depth >= 8 && in_ch == 3 && img == 32 && max_batch >= 1 && max_batch <= 4096);
+    lc_resnet* n = new (std::nothrow) lc_resnet();
+    if (!n) return LC_ERR_INVALID;
+    n->depth = depth; n->in_ch = in_ch; n->img = img; n->max_batch = max_batch; n->nblk = (depth - 2) / 6;
+    const long long B = max_batch;
+    long long po = 0, ro = 0;
+    auto add_conv = [&](int cin, int cout, int k, int stride, int wo) {
+        ConvL c{};
+        c.cin = cin; c.cout = cout; c.ksize = k; c.stride = stride; c.wo = wo;
+        c.w_off = po; po += (long long)cout * cin * k * k;
+        c.gamma_off = po; po += cout;
+        c.beta_off = po; po += cout;
+        c.rstat_off = ro; ro += 2 * cout;
+        n->convs.push_back(c);
+        return (int)n->convs.size() - 1;
+    };
+    add_conv(in_ch, 16, 3, 1, 32);
+    int inpl = 16, w = 32;
+    const int planes[3] = {16, 32, 64};
+    for (int s = 0; s < 3; ++s) {
+        for (int b = 0; b < n->nblk; ++b) {
+            const int stride = (b == 0 && s > 0) ? 2 : 1;
+            if (stride == 2) w /= 2;
+            BlockL bl{};
+            bl.stage = s;
+            bl.conv_a = add_conv(b == 0 ? inpl : planes[s], planes[s], 3, stride, w);
+            bl.conv_b = add_conv(planes[s], planes[s], 3, 1, w);
+            bl.conv_d = (b == 0 && s > 0) ? add_conv(inpl, planes[s], 1, stride, w) : -1;
+            n->blocks.push_back(bl);
+        }
+        inpl = planes[s];
+    }
+    n->n_params = po; n->n_rstat = ro;
+
+    // workspace layout
+    long long o = 0;
+    auto take = [&](long long cnt) { long long r = o; o += (cnt + 3) / 4 * 4; return r; };
+    n->off_counters = take(64);
+    n->off_aff = take((long long)n->convs.size() * 4 * 64);
+    long long fpart = 0;
+    for (auto& c : n->convs) {
+        long long parts = c.ksize == 3 ? B * 8 : (B * c.wo * c.wo + 127) / 128;   // >= tiles per image of every 3x3 config
+        fpart = std::max(fpart, parts * 2 * c.cout);
+    }
+    n->off_fpart = take(fpart);
+    n->off_bpart = take((long long)kBnBwdBlocks * 2 * 64);
+    n->off_coef = take(3 * 64);
+    long long pk = 0, wp = 0;
+    for (auto& c : n->convs) {
+        const long long ne = (long long)c.cout * c.cin * c.ksize * c.ksize;
+        c.wf_off = pk; pk += ne;
+        if (c.ksize == 3) { c.wd_off = pk; pk += ne; } else c.wd_off = -1;
+        c.nsplit = c.ksize == 3 ? wgrad_nsplit(c.cin, c.cout) : k1x1Split;
+        c.part_off = wp; wp += ne * c.nsplit;
+    }
+    n->packed_floats = pk; n->wpart_floats = wp;
+    n->off_packed = take(pk);
+    n->off_wpart = take(wp);
+    n->off_feat = take(B * 64);
+    n->off_dfeat = take(B * 64);
+    for (size_t i = 0; i < n->convs.size(); ++i) {
+        auto& c = n->convs[i];
+        c.aff_off = n->off_aff + (long long)i * 4 * 64;
+        c.y_off = take(B * c.wo * c.wo * c.cout);
+    }
+    n->off_a0 = take(B * 32 * 32 * 16);
+    {
+        int wcur = 32;
+        for (auto& bl : n->blocks) {
+            wcur = n->convs[bl.conv_b].wo;
+            bl.out_off = take(B * wcur * wcur * n->convs[bl.conv_b].cout);
+        }
+    }
+    n->off_G[0] = take(B * 32 * 32 * 16);
+    n->off_G[1] = take(B * 16 * 16 * 32);
+    n->off_G[2] = take(B * 8 * 8 * 64);
+    n->off_T1 = take(B * 32 * 32 * 16);
+    n->off_T2 = take(B * 32 * 32 * 16);
+    n->off_T3 = take(B * 16 * 16 * 32);
+    n->ws_floats = o;
+
+    // device tables
+    std::vector<ConvTabEntry> tab;
+    int blk = 0;
+    for (auto& c : n->convs) {
+        ConvTabEntry t{};
+        t.w_off = c.w_off; t.wf_off = c.wf_off; t.wd_off = c.wd_off; t.part_off = c.part_off;
+        t.cout = c.cout; t.cin = c.cin; t.ntap = c.ksize * c.ksize; t.nsplit = c.nsplit; t.blk_begin = blk;
+        blk += (c.cout * c.cin * t.ntap + 255) / 256;
+        tab.push_back(t);
+    }
+    n->tab_blocks = blk;
+    std::vector<BnEvalEntry> bt;
+    for (auto& c : n->convs) {
+        BnEvalEntry e{};
+        e.gamma_off = c.gamma_off; e.beta_off = c.beta_off; e.rstat_off = c.rstat_off; e.aff_off = c.aff_off; e.C = c.cout;
+        bt.push_back(e);
+    }
+    if (cudaMalloc(&n->d_tab, tab.size() * sizeof(ConvTabEntry)) != cudaSuccess || cudaMalloc(&n->d_bntab, bt.size() * sizeof(BnEvalEntry)) != cudaSuccess ||
+        cudaMemcpy(n->d_tab, tab.data(), tab.size() * sizeof(ConvTabEntry), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(n->d_bntab, bt.data(), bt.size() * sizeof(BnEvalEntry), cudaMemcpyHostToDevice) != cudaSuccess) {
+        lc_resnet_destroy(n);
+        return LC_ERR_CUDA;
+    }
+    *out = n;
+    return LC_OK;
+}
+
+void lc_resnet_destroy(lc_resnet* n) {
+    if (!n) return;
+    if (n->d_tab) cudaFree(n->d_tab);
+    if (n->d_bntab) cudaFree(n->d_bntab);
+    delete n;
+}
+
+long long lc_resnet_param_count(const lc_resnet* n) { return n ? n->n_params : LC_ERR_INVALID; }
+long long lc_resnet_rstat_count(const lc_resnet* n) { return n ? n->n_rstat : LC_ERR_INVALID; }
+long long lc_resnet_workspace_floats(const lc_resnet* n) { return n ? n->ws_floats : LC_ERR_INVALID; }
+int lc_resnet_num_convs(const lc_resnet* n) { return n ? (int)n->convs.size() : LC_ERR_INVALID; }
+int lc_resnet_num_launches(const lc_resnet* n, int backward) { return n ? (backward ? n->launches_bwd : n->launches_fwd) : LC_ERR_INVALID; }
+
+int lc_resnet_conv_info(const lc_resnet* n, int idx, long long* w_off, int* cout, int* cin, int* ksize, int* stride, long long* gamma_off,
+                        long long* beta_off, long long* rstat_off) {
+    LC_CHECK_ARG(n && idx >= 0 && idx < (int)n->convs.size());
+    const ConvL& c = n->convs[idx];
+    if (w_off) *w_off = c.w_off;
+    if (cout) *cout = c.cout;
+    if (cin) *cin = c.cin;
+    if (ksize) *ksize = c.ksize;
+    if (stride) *stride = c.stride;
+    if (gamma_off) *gamma_off = c.gamma_off;
+    if (beta_off) *beta_off = c.beta_off;
+    if (rstat_off) *rstat_off = c.rstat_off;
+    return LC_OK;
+}
+
+long long lc_resnet_ws_offset(const lc_resnet* n, int what) {
+    if (!n) return LC_ERR_INVALID;
+    switch (what) {
+        case LC_WS_FEAT: return n->off_feat;
+        case LC_WS_DFEAT: return n->off_dfeat;
+        case LC_WS_GRAD_LAST: return n->off_G[2];
+        case LC_WS_FMAP1: return n->blocks[n->nblk - 1].out_off;
+        case LC_WS_FMAP2: return n->blocks[2 * n->nblk - 1].out_off;
+        case LC_WS_FMAP3: return n->blocks[3 * n->nblk - 1].out_off;
+        default: return LC_ERR_INVALID;
+    }
+}
+
+#define LC_TRY(expr)                  \
+    do {                              \
+        int _e = (expr);              \
+        if (_e != LC_OK) return _e;   \
+        ++launches;                   \
+    } while (0)
+
+int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* params, float* rstat, float* ws, int train, int update_running,
+                      lc_stream_t stream) {
+    LC_CHECK_ARG(n && x && params && ws && batch >= 1 && batch <= n->max_batch && (rstat || (train && !update_running)));
+    cudaStream_t st = (cudaStream_t)stream;
+    int launches = 0;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws + n->off_counters);
+    float* packed = ws + n->off_packed;
+    pack_weights_kernel<<<n->tab_blocks, 256, 0, st>>>(n->d_tab, (int)n->convs.size(), params, packed);
+    LC_TRY(lc_launch_status());
+    if (!train) {
+        bn_eval_affine_kernel<<<(int)n->convs.size(), 64, 0, st>>>(n->d_bntab, (int)n->convs.size(), params, rstat, ws, kBnEps);
+        LC_TRY(lc_launch_status());
+    }
+    auto stat_for = [&](const ConvL& c) {
+        BnStatArgs s{};
+        if (!train) return s;
+        s.partial = ws + n->off_fpart; s.counter = counters + 0;
+        s.gamma = params + c.gamma_off; s.beta = params + c.beta_off;
+        s.running_mean = rstat ? rstat + c.rstat_off : nullptr; s.running_var = rstat ? rstat + c.rstat_off + c.cout : nullptr;
+        float* aff = ws + c.aff_off;
+        s.scale = aff; s.shift = aff + c.cout; s.mean = aff + 2 * c.cout; s.invstd = aff + 3 * c.cout;
+        s.momentum = kBnMomentum; s.eps = kBnEps; s.update_running = (update_running && rstat) ? 1 : 0;
+        return s;
+    };
+    // stem
+    {
+        const ConvL& c = n->convs[0];
+        Conv3x3Args a{};
+        a.in = x; a.wpack = packed + c.wf_off; a.out = ws + c.y_off; a.stat = stat_for(c); a.B = batch;
+        LC_TRY(launch_conv3x3(c.cin, c.cout, c.wo, 1, false, true, a, st));
+        BnActArgs e{};
+        e.y = ws + c.y_off; e.scale = ws + c.aff_off; e.shift = ws + c.aff_off + c.cout; e.out = ws + n->off_a0;
+        e.n4 = (long long)batch * c.wo * c.wo * c.cout / 4; e.C = c.cout;
+        LC_TRY(launch_bn_act(e, st));
+    }
+    const float* cur = ws + n->off_a0;
+    for (const BlockL& bl : n->blocks) {
+        const ConvL& ca = n->convs[bl.conv_a];
+        const ConvL& cb = n->convs[bl.conv_b];
+        {
+            Conv3x3Args a{};
+            a.in = cur; a.wpack = packed + ca.wf_off; a.out = ws + ca.y_off; a.stat = stat_for(ca); a.B = batch;
+            LC_TRY(launch_conv3x3(ca.cin, ca.cout, ca.wo, ca.stride, false, false, a, st));
+        }
+        {
+            Conv3x3Args a{};
+            a.in = ws + ca.y_off; a.wpack = packed + cb.wf_off; a.out = ws + cb.y_off; a.stat = stat_for(cb); a.B = batch;
+            a.pro_scale = ws + ca.aff_off; a.pro_shift = ws + ca.aff_off + ca.cout;
+            LC_TRY(launch_conv3x3(cb.cin, cb.cout, cb.wo, 1, false, false, a, st));
+        }
+        BnActArgs e{};
+        e.y = ws + cb.y_off; e.scale = ws + cb.aff_off; e.shift = ws + cb.aff_off + cb.cout; e.out = ws + bl.out_off;
+        e.n4 = (long long)batch * cb.wo * cb.wo * cb.cout / 4; e.C = cb.cout;
+        if (bl.conv_d >= 0) {
+            const ConvL& cd = n->convs[bl.conv_d];
+            Conv1x1Args a{};
+            a.in = cur; a.w = packed + cd.wf_off; a.out = ws + cd.y_off; a.stat = stat_for(cd); a.B = batch;
+            LC_TRY(launch_conv1x1_fwd(cd.cin, cd.cout, cd.wo, a, st));
+            e.res = ws + cd.y_off; e.res_scale = ws + cd.aff_off; e.res_shift = ws + cd.aff_off + cd.cout;
+        } else {
+            e.res = cur;
+        }
+        LC_TRY(launch_bn_act(e, st));
+        cur = ws + bl.out_off;
+    }
+    n->launches_fwd = launches;
+    return LC_OK;
+}
+
+int lc_resnet_backward(lc_resnet* n, const float* x, int batch, const float* params, float* ws, float* grads, lc_stream_t stream) {
+    LC_CHECK_ARG(n && x && params && ws && grads && batch >= 1 && batch <= n->max_batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    int launches = 0;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws + n->off_counters);
+    float* packed = ws + n->off_packed;
+    float* wpart = ws + n->off_wpart;
+    float* T1 = ws + n->off_T1;
+    float* T2 = ws + n->off_T2;
+    float* T3 = ws + n->off_T3;
+
+    auto bn_bwd = [&](const ConvL& c, const float* g, const float* mask_src, int mask_mode, float* dy, float* g_out) {
+        BnBwdArgs a{};
+        const float* aff = ws + c.aff_off;
+        a.g = g; a.mask_src = mask_src; a.mask_mode = mask_mode; a.y = ws + c.y_off;
+        a.scale = aff; a.shift = aff + c.cout; a.mean = aff + 2 * c.cout; a.invstd = aff + 3 * c.cout;
+        a.partial = ws + n->off_bpart; a.counter = counters + 1; a.coef = ws + n->off_coef;
+        a.dgamma = grads + c.gamma_off; a.dbeta = grads + c.beta_off; a.dy = dy; a.g_out = g_out;
+        a.npix = (long long)batch * c.wo * c.wo; a.C = c.cout;
+        return launch_bn_bwd(a, st);
+    };
+
+    for (int bi = (int)n->blocks.size() - 1; bi >= 0; --bi) {
+        const BlockL& bl = n->blocks[bi];
+        const ConvL& ca = n->convs[bl.conv_a];
+        const ConvL& cb = n->convs[bl.conv_b];
+        float* G = ws + n->off_G[bl.stage];
+        const float* blk_in = bi == 0 ? ws + n->off_a0 : ws + n->blocks[bi - 1].out_off;
+        const float* blk_out = ws + bl.out_off;
+        // bn_b (+ ReLU of the block output): T1 = d(y2), G <- masked gradient (the residual-branch gradient)
+        LC_TRY(bn_bwd(cb, G, blk_out, LC_MASK_FROM_OUT, T1, G)); ++launches;
+        if (bl.conv_d >= 0) {
+            const ConvL& cd = n->convs[bl.conv_d];
+            LC_TRY(bn_bwd(cd, G, nullptr, LC_MASK_NONE, T3, nullptr)); ++launches;
+            LC_TRY(launch_conv1x1_wgrad(cd.cin, cd.cout, cd.wo, blk_in, T3, wpart + cd.part_off, batch, st));
+        }
+        {   // conv_b: weight gradient (input = relu(bn_a(y1)) recomputed on load) and data gradient
+            WgradArgs w{};
+            w.in = ws + ca.y_off; w.dy = T1; w.partial = wpart + cb.part_off; w.B = batch; w.nsplit = cb.nsplit;
+            w.pro_scale = ws + ca.aff_off; w.pro_shift = ws + ca.aff_off + ca.cout;
+            LC_TRY(launch_wgrad3x3(cb.cin, cb.cout, cb.wo, 1, false, w, st));
+            Conv3x3Args a{};
+            a.in = T1; a.wpack = packed + cb.wd_off; a.out = T2; a.B = batch;
+            LC_TRY(launch_conv3x3(cb.cout, cb.cin, cb.wo, 1, false, false, a, st));
+        }
+        // bn_a (+ ReLU): T1 = d(y1)
+        LC_TRY(bn_bwd(ca, T2, nullptr, LC_MASK_FROM_BN, T1, nullptr)); ++launches;
+        {
+            WgradArgs w{};
+            w.in = blk_in; w.dy = T1; w.partial = wpart + ca.part_off; w.B = batch; w.nsplit = ca.nsplit;
+            LC_TRY(launch_wgrad3x3(ca.cin, ca.cout, ca.wo, ca.stride, false, w, st));
+            Conv3x3Args a{};
+            a.in = T1; a.wpack = packed + ca.wd_off; a.B = batch;
+            if (ca.stride == 1) {
+                a.out = G; a.addend = G;     // identity shortcut: dX = dgrad + masked G (in place)
+                LC_TRY(launch_conv3x3(ca.cout, ca.cin, ca.wo, 1, false, false, a, st));
+            } else {
+                float* Gprev = ws + n->off_G[bl.stage - 1];
+                a.out = Gprev;
+                LC_TRY(launch_conv3x3(ca.cout, ca.cin, ca.wo * 2, 1, true, false, a, st));
+                const ConvL& cd = n->convs[bl.conv_d];
+                LC_TRY(launch_conv1x1_dgrad(cd.cin, cd.cout, cd.wo, T3, params + cd.w_off, Gprev, batch, st));
+            }
+        }
+    }
+    {   // stem
+        const ConvL& c = n->convs[0];
+        float* G = ws + n->off_G[0];
+        LC_TRY(bn_bwd(c, G, ws + n->off_a0, LC_MASK_FROM_OUT, T1, nullptr)); ++launches;
+        WgradArgs w{};
+        w.in = x; w.dy = T1; w.partial = wpart + c.part_off; w.B = batch; w.nsplit = c.nsplit;
+        LC_TRY(launch_wgrad3x3(c.cin, c.cout, c.wo, 1, true, w, st));
+    }
+    wgrad_reduce_all_kernel<<<n->tab_blocks, 256, 0, st>>>(n->d_tab, (int)n->convs.size(), wpart, grads);
+    LC_TRY(lc_launch_status());
+    n->launches_bwd = launches;
+    return LC_OK;
+}
+
+// ---- head / loss ----------------------------------------------------------------------------------------------------
+int lc_head_forward(const float* act, int batch, int hw, int feat_dim, const float* W, const float* bias, int ncls, float* feat, float* logits,
+                    int ldl, lc_stream_t stream) {
+    LC_CHECK_ARG(act && W && feat && logits && batch >= 1 && hw >= 1 && ncls >= 1 && ldl >= ncls && feat_dim == 64);
+    avgpool_fc_fwd_kernel<64><<<batch, 64, 0, (cudaStream_t)stream>>>(act, hw, W, bias, ncls, feat, logits, ldl);
+    return lc_launch_status();
+}
+
+int lc_loss_ce_kd(const float* logits, int ldl, const float* teacher, int ldt, const int64_t* y, int batch, int ce_lo, int ce_hi, int kd_n,
+                  float kd_w, float T, int pred_n, float* dlogits, int64_t* pred, float* scal, lc_stream_t stream) {
+    LC_CHECK_ARG(logits && y && dlogits && pred && scal && batch >= 1 && ce_lo >= 0 && ce_hi > ce_lo && ce_hi <= ldl && pred_n >= 1 && pred_n <= ldl);
+    LC_CHECK_ARG(kd_n == 0 || (teacher && kd_n <= ldl && kd_n <= ldt && T > 0.f));
+    LossArgs a{};
+    a.logits = logits; a.teacher = teacher; a.y = reinterpret_cast<const long long*>(y); a.dlogits = dlogits;
+    a.pred = reinterpret_cast<long long*>(pred); a.scal = scal; a.B = batch; a.ldl = ldl; a.ldt = ldt; a.ncols = ldl;
+    a.ce_lo = ce_lo; a.ce_hi = ce_hi; a.kd_n = kd_n; a.pred_n = pred_n; a.kd_w = kd_w; a.T = T;
+    ce_kd_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
+    return lc_launch_status();
+}
+
+int lc_head_backward(const float* dlogits, int ldl, const float* feat, const float* W, int ncls, int batch, int feat_dim, float* dW, float* db,
+                     float* dfeat, float* gact, int hw, lc_stream_t stream) {
+    LC_CHECK_ARG(dlogits && feat && W && dW && dfeat && ncls >= 1 && batch >= 1 && feat_dim == 64 && ldl >= ncls);
+    head_bwd_kernel<64><<<ncls + batch, 64, 0, (cudaStream_t)stream>>>(dlogits, ldl, feat, W, ncls, batch, dW, db, dfeat, gact, hw);
+    return lc_launch_status();
+}
+
+// ---- flat arena ops ---------------------------------------------------------------------------------------------------
+int lc_ewc_penalty_grad(const float* theta, const float* theta_ref, const float* fisher, float* grad, long long n, const float* hp_lamda,
+                        float* scratch, uint32_t* counter, float* scal, lc_stream_t stream) {
+    LC_CHECK_ARG(theta && theta_ref && fisher && grad && n > 0 && hp_lamda && scratch && counter && scal);
+    LC_CHECK_ARG(((uintptr_t)theta % 16 == 0) && ((uintptr_t)theta_ref % 16 == 0) && ((uintptr_t)fisher % 16 == 0) && ((uintptr_t)grad % 16 == 0) && ((uintptr_t)scratch % 8 == 0));
+    ewc_penalty_grad_kernel<<<kFlatBlocks, 256, 0, (cudaStream_t)stream>>>(theta, theta_ref, fisher, grad, n, hp_lamda, reinterpret_cast<double*>(scratch), counter, scal);
+    return lc_launch_status();
+}
+int lc_fisher_accumulate(float* fisher, const float* grad, long long n, float weight, lc_stream_t stream) {
+    LC_CHECK_ARG(fisher && grad && n > 0);
+    fisher_accumulate_kernel<<<kFlatBlocks, 256, 0, (cudaStream_t)stream>>>(fisher, grad, n, weight);
+    return lc_launch_status();
+}
+int lc_fisher_merge(float* f_new, const float* f_old, long long n, float num_samples, float alpha, lc_stream_t stream) {
+    LC_CHECK_ARG(f_new && n > 0 && num_samples > 0.f);
+    fisher_merge_kernel<<<kFlatBlocks, 256, 0, (cudaStream_t)stream>>>(f_new, f_old, n, num_samples, alpha);
+    return lc_launch_status();
+}
+int lc_sgd_momentum(float* p, const float* g, float* m, long long n, const float* hp, lc_stream_t stream) {
+    LC_CHECK_ARG(p && g && m && hp && n > 0 && ((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0));
+    sgd_momentum_kernel<<<kFlatBlocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, n, hp);
+    return lc_launch_status();
+}
+int lc_adam(float* p, const float* g, float* m, float* v, long long n, const float* hp, lc_stream_t stream) {
+    LC_CHECK_ARG(p && g && m && v && hp && n > 0);
+    adam_kernel<<<kFlatBlocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hp);
+    return lc_launch_status();
+}
+int lc_clip_grad_norm(float* g, long long n, float max_norm, float* scratch, float* norm_out, lc_stream_t stream) {
+    LC_CHECK_ARG(g && n > 0 && scratch && ((uintptr_t)scratch % 8 == 0));
+    double* part = reinterpret_cast<double*>(scratch);
+    sqnorm_partial_kernel<<<kFlatBlocks, 256, 0, (cudaStream_t)stream>>>(g, n, part);
+    if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
+    clip_scale_kernel<<<kFlatBlocks, 256, 0, (cudaStream_t)stream>>>(g, n, part, kFlatBlocks, max_norm, norm_out);
+    return lc_launch_status();
+}
+
+// ---- per-kernel entry points ------------------------------------------------------------------------------------------
+// scratch layout of the per-kernel entry points (floats): [0,64) election counters (caller-zeroed) | [64,80) one table
+// entry | [80, ...) packed weights / partial sums
+static inline long long round4(long long v) { return (v + 3) / 4 * 4; }
+
+long long lc_conv_scratch_floats(int batch, int cin, int cout, int width_out) {
+    const long long ne = (long long)cout * cin * 9;
+    const int cm = cout > cin ? cout : cin;
+    long long parts = (long long)batch * 8 * 2 * cm;
+    const long long p1 = ((long long)batch * width_out * width_out + 127) / 128 * 2 * cm;
+    if (p1 > parts) parts = p1;
+    return 80 + round4(2 * ne) + round4(parts) + ne * 256 + 64;
+}
+
+static void fill_stat(BnStatArgs& s, const float* gamma, const float* beta, float* rstat, float* stat_out, int C, float* partial, unsigned int* counter) {
+    s.partial = partial; s.counter = counter; s.gamma = gamma; s.beta = beta;
+    s.running_mean = rstat; s.running_var = rstat ? rstat + C : nullptr;
+    s.scale = stat_out; s.shift = stat_out + C; s.mean = stat_out + 2 * C; s.invstd = stat_out + 3 * C;
+    s.momentum = kBnMomentum; s.eps = kBnEps; s.update_running = rstat ? 1 : 0;
+}
+
+int lc_conv3x3(const float* in, const float* w_oihw, float* out, int batch, int cin, int cout, int width_out, int stride, int mode, int in_nchw,
+               const float* pro_scale, const float* pro_shift, const float* addend, const float* gamma, const float* beta, float* rstat,
+               float* stat_out, float* scratch, lc_stream_t stream) {
+    LC_CHECK_ARG(in && w_oihw && out && scratch && batch >= 1 && (mode == 0 || mode == 1) && ((uintptr_t)scratch % 16 == 0));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long ne = (long long)cout * cin * 9;
+    ConvTabEntry t{};
+    t.w_off = 0; t.wf_off = 0; t.wd_off = ne; t.cout = cout; t.cin = cin; t.ntap = 9; t.nsplit = 0; t.blk_begin = 0;
+    ConvTabEntry* d_t = reinterpret_cast<ConvTabEntry*>(scratch + 64);
+    float* packed = scratch + 80;
+    float* partial = packed + round4(2 * ne);
+    if (cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, st) != cudaSuccess) return LC_ERR_CUDA;
+    pack_weights_kernel<<<(int)((ne + 255) / 256), 256, 0, st>>>(d_t, 1, w_oihw, packed);
+    if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
+    Conv3x3Args a{};
+    a.in = in; a.out = out; a.pro_scale = pro_scale; a.pro_shift = pro_shift; a.addend = addend; a.B = batch;
+    if (mode == 0) {
+        a.wpack = packed;
+        if (stat_out) { LC_CHECK_ARG(gamma && beta); fill_stat(a.stat, gamma, beta, rstat, stat_out, cout, partial, reinterpret_cast<unsigned int*>(scratch)); }
+        return launch_conv3x3(cin, cout, width_out, stride, false, in_nchw != 0, a, st);
+    }
+    // data gradient of a (cin -> cout, stride) conv: `in` is dy [B][wo][wo][cout]; out is [B][wo*stride][wo*stride][cin]
+    a.wpack = packed + ne;
+    return launch_conv3x3(cout, cin, width_out * stride, 1, stride == 2, false, a, st);
+}
+
+// Single launch of the conv kernel on pre-packed weights ([cin][9][cout], as left at scratch+80 by lc_conv3x3): no packing,
+// no statistics.  Used by bench.py to time the dominant kernel in isolation.
+int lc_conv3x3_packed(const float* in, const float* wpack, float* out, int batch, int cin, int cout, int width_out, int stride,
+                      const float* pro_scale, const float* pro_shift, lc_stream_t stream) {
+    LC_CHECK_ARG(in && wpack && out && batch >= 1);
+    Conv3x3Args a{};
+    a.in = in; a.wpack = wpack; a.out = out; a.pro_scale = pro_scale; a.pro_shift = pro_shift; a.B = batch;
+    return launch_conv3x3(cin, cout, width_out, stride, false, false, a, (cudaStream_t)stream);
+}
+
+int lc_conv3x3_wgrad(const float* in, const float* dy, float* dw, int batch, int cin, int cout, int width_out, int stride, int in_nchw,
+                     const float* pro_scale, const float* pro_shift, float* scratch, lc_stream_t stream) {
+    LC_CHECK_ARG(in && dy && dw && scratch && batch >= 1 && ((uintptr_t)scratch % 16 == 0));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long ne = (long long)cout * cin * 9;
+    const int nsplit = wgrad_nsplit(cin, cout);
+    ConvTabEntry t{};
+    t.w_off = 0; t.part_off = 0; t.cout = cout; t.cin = cin; t.ntap = 9; t.nsplit = nsplit; t.blk_begin = 0; t.wd_off = -1;
+    ConvTabEntry* d_t = reinterpret_cast<ConvTabEntry*>(scratch + 64);
+    float* partial = scratch + 80;
+    if (cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, st) != cudaSuccess) return LC_ERR_CUDA;
+    WgradArgs w{};
+    w.in = in; w.dy = dy; w.partial = partial; w.pro_scale = pro_scale; w.pro_shift = pro_shift; w.B = batch; w.nsplit = nsplit;
+    int e = launch_wgrad3x3(cin, cout, width_out, stride, in_nchw != 0, w, st);
+    if (e != LC_OK) return e;
+    wgrad_reduce_all_kernel<<<(int)((ne + 255) / 256), 256, 0, st>>>(d_t, 1, partial, dw);
+    return lc_launch_status();
+}
+
+int lc_conv1x1s2(const float* a_, const float* b_, float* out, int batch, int cin, int cout, int width_out, int mode, const float* gamma,
+                 const float* beta, float* rstat, float* stat_out, float* scratch, lc_stream_t stream) {
+    LC_CHECK_ARG(a_ && b_ && out && scratch && batch >= 1 && mode >= 0 && mode <= 2 && ((uintptr_t)scratch % 16 == 0));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long ne = (long long)cout * cin;
+    ConvTabEntry t{};
+    t.w_off = 0; t.wf_off = 0; t.wd_off = -1; t.part_off = 0; t.cout = cout; t.cin = cin; t.ntap = 1; t.nsplit = k1x1Split; t.blk_begin = 0;
+    ConvTabEntry* d_t = reinterpret_cast<ConvTabEntry*>(scratch + 64);
+    if (cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, st) != cudaSuccess) return LC_ERR_CUDA;
+    float* buf = scratch + 80;
+    if (mode == 0) {          // a_ = in, b_ = W [cout][cin]
+        pack_weights_kernel<<<(int)((ne + 255) / 256), 256, 0, st>>>(d_t, 1, b_, buf);
+        if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
+        Conv1x1Args a{};
+        a.in = a_; a.w = buf; a.out = out; a.B = batch;
+        if (stat_out) { LC_CHECK_ARG(gamma && beta); fill_stat(a.stat, gamma, beta, rstat, stat_out, cout, buf + round4(ne), reinterpret_cast<unsigned int*>(scratch)); }
+        return launch_conv1x1_fwd(cin, cout, width_out, a, st);
+    }
+    if (mode == 1)            // a_ = dy, b_ = W; accumulate into out
+        return launch_conv1x1_dgrad(cin, cout, width_out, a_, b_, out, batch, st);
+    // mode 2: a_ = in, b_ = dy -> out = dW
+    int e = launch_conv1x1_wgrad(cin, cout, width_out, a_, b_, buf, batch, st);
+    if (e != LC_OK) return e;
+    wgrad_reduce_all_kernel<<<(int)((ne + 255) / 256), 256, 0, st>>>(d_t, 1, buf, out);
+    return lc_launch_status();
+}
+
+int lc_bn_act_forward(const float* y, const float* scale, const float* shift, const float* res, const float* res_scale, const float* res_shift,
+                      float* out, long long npix, int C, lc_stream_t stream) {
+    LC_CHECK_ARG(y && scale && shift && out && npix > 0 && C % 4 == 0);
+    BnActArgs e{};
+    e.y = y; e.scale = scale; e.shift = shift; e.res = res; e.res_scale = res_scale; e.res_shift = res_shift; e.out = out; e.n4 = npix * C / 4; e.C = C;
+    return launch_bn_act(e, (cudaStream_t)stream);
+}
+
+int lc_bn_backward(const float* g, const float* mask_src, int mask_mode, const float* y, const float* stat, float* dy, float* g_out,
+                   float* dgamma, float* dbeta, long long npix, int C, float* scratch, lc_stream_t stream) {
+    LC_CHECK_ARG(g && y && stat && dy && dgamma && dbeta && scratch && npix > 0 && (mask_mode != LC_MASK_FROM_OUT || mask_src));
+    BnBwdArgs a{};
+    a.g = g; a.mask_src = mask_src; a.mask_mode = mask_mode; a.y = y;
+    a.scale = stat; a.shift = stat + C; a.mean = stat + 2 * C; a.invstd = stat + 3 * C;
+    a.counter = reinterpret_cast<unsigned int*>(scratch); a.coef = scratch + 64; a.partial = scratch + 64 + 3 * C + (4 - (3 * C) % 4) % 4;
+    a.dgamma = dgamma; a.dbeta = dbeta; a.dy = dy; a.g_out = g_out; a.npix = npix; a.C = C;
+    return launch_bn_bwd(a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+"""`cifar_resnet32` backbone (mirrors core/model/backbone/resnet.py:324-412 and the factory at :760-763).
+
+The nn.Module keeps the reference's parameter / buffer names (`conv_1_3x3.weight`, `stage_1.0.bn_a.running_mean`, ...), so
+`state_dict()` / `load_state_dict()` interoperate with reference checkpoints, but every tensor is a view into the flat
+arenas of a `ResNetEngine`, and `forward` runs the hand-written CUDA kernels (autograd-aware through `_BackboneFn`).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from ...engine import ResNetEngine
+
+
+class _BackboneFn(torch.autograd.Function):
+    """features = backbone(x) with a hand-written backward.  Inputs: x, then every backbone parameter (so that autograd
+    routes the gradients); the arithmetic reads the arenas directly."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        eng: ResNetEngine = module.engine
+        train = module.training
+        eng.forward(x, train=train, update_running=train)
+        if train:
+            module._bump_num_batches_tracked()
+        B = x.shape[0]
+        ctx.module, ctx.x, ctx.train = module, x, train
+        feat = eng.features(B).clone()
+        fm = [f.clone() for f in eng.fmaps(B)]
+        ctx.mark_non_differentiable(*fm)
+        return (feat, *fm)
+
+    @staticmethod
+    def backward(ctx, gfeat, *_unused):
+        module, x = ctx.module, ctx.x
+        if not ctx.train:
+            raise RuntimeError("backward through the backbone is only supported in train() mode (batch-statistics BN)")
+        eng: ResNetEngine = module.engine
+        B = x.shape[0]
+        # avg-pool backward: broadcast dfeat / 64 over the 8x8 map into the plan's LC_WS_GRAD_LAST slot
+        from ...engine import LC_WS_GRAD_LAST
+        o = eng._off[LC_WS_GRAD_LAST]
+        eng.ws[o:o + B * 64 * 64].view(B, 64, 64).copy_((gfeat.contiguous() / 64.0).unsqueeze(1).expand(B, 64, 64))
+        eng.backward(x)
+        grads = tuple(eng.param_view(n, eng.grads) for n, _ in eng.layout)
+        return (None, None, *grads)
+
+
+class CifarResNet(nn.Module):
+    def __init__(self, depth: int = 32, channels: int = 3, device=None, max_batch: int = 128, num_class_cap: int = 100):
+        super().__init__()
+        self.engine = ResNetEngine(depth=depth, max_batch=max_batch, num_class_cap=num_class_cap, device=device, in_ch=channels)
+        self.out_dim = 64
+        self._names = []
+        eng = self.engine
+        # same init distributions and the same RNG draw order as resnet.py:345-352
+        for name, shape in eng.layout:
+            view = eng.param_view(name)
+            if len(shape) == 4:
+                n = shape[2] * shape[3] * shape[0]
+                view.copy_(torch.empty(shape).normal_(0, math.sqrt(2.0 / n)))
+            elif name.endswith(".weight"):
+                view.fill_(1.0)
+            else:
+                view.zero_()
+            self._register(name, nn.Parameter(view))
+        for bn in eng.bn_names:
+            m, v = eng.running_views(bn)
+            self._register_buffer(bn + ".running_mean", m)
+            self._register_buffer(bn + ".running_var", v)
+            self._register_buffer(bn + ".num_batches_tracked", torch.zeros((), dtype=torch.long))
+
+    # flat registration under dotted reference names --------------------------------------------------------------------
+    @staticmethod
+    def _key(name: str) -> str:
+        return name.replace(".", "__")
+
+    def _register(self, name, p):
+        self.register_parameter(self._key(name), p)
+        self._names.append(name)
+
+    def _register_buffer(self, name, b):
+        self.register_buffer(self._key(name), b)
+
+    def named_parameters(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True):
+        for k, p in super().named_parameters(prefix="", recurse=recurse, remove_duplicate=remove_duplicate):
+            yield (prefix + ("." if prefix else "") + k.replace("__", ".")), p
+
+    def named_buffers(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True):
+        for k, b in super().named_buffers(prefix="", recurse=recurse, remove_duplicate=remove_duplicate):
+            yield (prefix + ("." if prefix else "") + k.replace("__", ".")), b
+
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        sd = super().state_dict(*args, destination=None, prefix="", keep_vars=keep_vars)
+        out = destination if destination is not None else type(sd)()
+        for k, v in sd.items():
+            out[prefix + k.replace("__", ".")] = v
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        own = {k.replace("__", "."): v for k, v in super().state_dict(keep_vars=True).items()}
+        missing = [k for k in own if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in own]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"load_state_dict: missing {missing[:4]}..., unexpected {unexpected[:4]}...")
+        with torch.no_grad():
+            for k, v in state_dict.items():
+                if k in own:
+                    own[k].copy_(v)      # in place: the arenas keep owning the storage
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def _apply(self, fn, recurse=True):
+        # parameters are views into the engine arenas: moving/casting them would silently detach them from the kernels
+        probe = fn(torch.empty(0, device=self.engine.device))
+        if probe.device != self.engine.device or probe.dtype != torch.float32:
+            raise RuntimeError("libcontinual_b200 backbones live on the device they were built on, in fp32")
+        return self
+
+    def _bump_num_batches_tracked(self):
+        for bn in self.engine.bn_names:
+            getattr(self, self._key(bn + ".num_batches_tracked")).add_(1)
+
+    # reference interface -------------------------------------------------------------------------------------------------
+    def forward(self, x):
+        x = x.to(self.engine.device, torch.float32).contiguous()
+        if torch.is_grad_enabled() and self.training:
+            outs = _BackboneFn.apply(self, x, *[p for _, p in self.named_parameters()])
+        else:
+            with torch.no_grad():
+                outs = _BackboneFn.forward(_NoCtx(), self, x)
+        return {"fmaps": list(outs[1:]), "features": outs[0]}
+
+    def feature(self, x):
+        return self.forward(x)["features"]
+
+
+class _NoCtx:
+    def mark_non_differentiable(self, *a):
+        pass
+
+
+def cifar_resnet32(pretrained: bool = False, **kwargs):
+    """Factory named in the YAML recipes (`backbone.name: cifar_resnet32`, resnet.py:760-763).  Reference kwargs
+    (`num_classes`, `args`) are accepted and ignored exactly as the reference ignores them."""
+    return CifarResNet(32, device=kwargs.get("device"), max_batch=kwargs.get("max_batch", 128), num_class_cap=kwargs.get("num_classes", 100))
+
+
+def cifar_resnet20(pretrained: bool = False, **kwargs):
+    return CifarResNet(20, device=kwargs.get("device"), max_batch=kwargs.get("max_batch", 128), num_class_cap=kwargs.get("num_classes", 100))

@@ -1,0 +1,323 @@
+"""Finetune / EWC / iCaRL / LwF on the CIFAR ResNet — host-side mirror of the reference plugin classes
+(core/model/finetune.py, ewc.py, icarl.py, lwf.py): same constructor kwargs, `observe / inference / before_task /
+after_task / get_parameters` with the same return tuples, same RNG draw order for freshly initialised heads.
+
+`observe` issues one fixed kernel sequence (backbone fwd -> head -> CE/KD loss -> head bwd -> backbone bwd -> EWC penalty)
+that leaves every gradient in the flat gradient arena, and returns a `loss` whose `.backward()` hands those gradients to
+autograd unchanged, so the reference `Trainer._train` order (observe -> zero_grad -> backward -> step, trainer.py:601-606)
+runs unmodified on top of it.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ..engine import ResNetEngine, TeacherState
+from .backbone.resnet import CifarResNet
+
+
+class _ArenaLoss(torch.autograd.Function):
+    """loss tensor whose backward returns the arena gradient views produced by the fused step."""
+
+    @staticmethod
+    def forward(ctx, owner, loss_value, *params):
+        ctx.owner = owner
+        return loss_value.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        owner = ctx.owner
+        owner.engine.grads.mul_(g)        # identity for the usual g == 1
+        return (None, None, *owner._grad_views())
+
+
+class _Head(nn.Module):
+    """nn.Linear look-alike whose weight / bias are the first `out_features` rows of the engine's head arena."""
+
+    def __init__(self, eng: ResNetEngine, out_features: int):
+        super().__init__()
+        self.in_features, self.out_features = eng.feat_dim, out_features
+        w, b = eng.fc_views(out_features)
+        self.weight = nn.Parameter(w)
+        self.bias = nn.Parameter(b)
+
+    def forward(self, feat):
+        return torch.nn.functional.linear(feat, self.weight, self.bias)
+
+    def _apply(self, fn, recurse=True):
+        return self
+
+
+class _Network(nn.Module):
+    """`Model` of ewc.py:42-57 / icarl.py:24-38: backbone + classifier."""
+
+    def __init__(self, backbone: CifarResNet, head: _Head):
+        super().__init__()
+        self.backbone = backbone
+        self.classifier = head
+        self.feat_dim, self.num_class = head.in_features, head.out_features
+
+    def forward(self, x):
+        return self.classifier(self.backbone(x)["features"])
+
+    get_logits = forward
+
+
+def _draw_linear(in_f: int, out_f: int):
+    """Draws an nn.Linear exactly as the reference does (same torch RNG consumption) and returns (weight, bias)."""
+    m = nn.Linear(in_f, out_f)
+    return m.weight.data, m.bias.data
+
+
+class _ResNetMethod(nn.Module):
+    def __init__(self, backbone, feat_dim, num_class, **kwargs):
+        super().__init__()
+        if not isinstance(backbone, CifarResNet):
+            raise TypeError("libcontinual_b200 methods need a libcontinual_b200 backbone (e.g. cifar_resnet32); "
+                            "there is no eager-PyTorch fallback path")
+        assert feat_dim == backbone.out_dim
+        self.backbone = backbone
+        self.engine: ResNetEngine = backbone.engine
+        self.feat_dim, self.num_class = feat_dim, num_class
+        self.device = kwargs.get("device", self.engine.device)
+        self.kwargs = kwargs
+        self.task_idx = 0
+        assert num_class <= self.engine.cap, "head capacity (backbone kwarg num_classes) too small"
+
+    # -- head management -------------------------------------------------------------------------------------------------
+    def _set_head(self, weight: torch.Tensor, bias: torch.Tensor):
+        eng = self.engine
+        n = weight.shape[0]
+        w, b = eng.fc_views(n)
+        w.copy_(weight)
+        b.copy_(bias)
+        eng.ncls = n
+        self.network = _Network(self.backbone, _Head(eng, n))
+
+    def _grow_head(self, n_new: int):
+        """new Linear whose first rows are the old head (ewc.py:71-80, lwf.py:28-42); fresh rows use the reference's init."""
+        eng = self.engine
+        n_old = eng.ncls
+        w_new, b_new = _draw_linear(self.feat_dim, n_new)
+        w, b = eng.fc_views(n_new)
+        w[n_old:].copy_(w_new[n_old:])
+        b[n_old:].copy_(b_new[n_old:])
+        eng.ncls = n_new
+        self.network = _Network(self.backbone, _Head(eng, n_new))
+
+    def _params(self):
+        return [p for _, p in self.backbone.named_parameters()] + [self.network.classifier.weight, self.network.classifier.bias]
+
+    def _grad_views(self):
+        eng = self.engine
+        gw, gb = eng.fc_views(eng.ncls, eng.grads)
+        return tuple(eng.param_view(n, eng.grads) for n, _ in eng.layout) + (gw, gb)
+
+    def get_parameters(self, config):
+        return [{"params": self._params()}]
+
+    # -- shared step pieces --------------------------------------------------------------------------------------------------
+    def _to_device(self, data):
+        x = data["image"].to(self.engine.device, dtype=torch.float32, non_blocking=True).contiguous()
+        y = data["label"].to(self.engine.device, dtype=torch.int64, non_blocking=True).contiguous()
+        return x, y
+
+    def _finish(self, B, y):
+        eng = self.engine
+        loss = _ArenaLoss.apply(self, eng.scal[0], *self._params())
+        pred = eng.pred[:B].clone()
+        acc = eng.scal[1].item()                 # the reference syncs here too (finetune.py:24)
+        return pred, acc / B, loss
+
+    def _fused_step(self, x, y, *, ce_lo, ce_hi, pred_n, teacher=None, kd_n=0, kd_w=0.0, head_rows=None):
+        eng = self.engine
+        B = x.shape[0]
+        n = eng.ncls
+        tl = eng.teacher_logits(teacher, x) if (teacher is not None and kd_n > 0) else None
+        eng.forward(x, train=True, update_running=True)
+        self.backbone._bump_num_batches_tracked()
+        eng.head_forward(B, n)
+        eng.loss(y, B, ce_lo, ce_hi, pred_n, teacher_logits=tl, kd_n=kd_n, kd_w=kd_w, T=2.0)
+        eng.head_backward(B, n)
+        eng.backward(x)
+
+    def _infer_logits(self, x):
+        eng = self.engine
+        B = x.shape[0]
+        eng.forward(x, train=self.training, update_running=self.training)
+        if self.training:
+            self.backbone._bump_num_batches_tracked()
+        eng.head_forward(B, eng.ncls)
+        return eng.logits[:B, :eng.ncls]
+
+    def forward(self, x):
+        return self._infer_logits(x.to(self.engine.device, torch.float32).contiguous()).clone()
+
+    def before_task(self, task_idx, buffer, train_loader, test_loaders):
+        self.task_idx = task_idx
+
+    def after_task(self, task_idx, buffer, train_loader, test_loaders):
+        pass
+
+    def inference(self, data):
+        x, y = self._to_device(data)
+        logit = self._infer_logits(x)
+        pred = torch.argmax(logit, dim=1)
+        acc = torch.sum(pred == y).item()
+        return pred, acc / x.size(0)
+
+
+class Finetune(_ResNetMethod):
+    """core/model/finetune.py:4-51."""
+
+    def __init__(self, backbone, feat_dim, num_class, **kwargs):
+        super().__init__(backbone, feat_dim, num_class, **kwargs)
+        self._set_head(*_draw_linear(feat_dim, num_class))
+
+    def observe(self, data):
+        x, y = self._to_device(data)
+        n = self.engine.ncls
+        self._fused_step(x, y, ce_lo=0, ce_hi=n, pred_n=n)
+        return self._finish(x.shape[0], y)
+
+
+class EWC(_ResNetMethod):
+    """core/model/ewc.py:59-229.  State: theta* and Fisher as flat arenas with the parameter-arena layout."""
+
+    def __init__(self, backbone, feat_dim, num_class, **kwargs):
+        super().__init__(backbone, feat_dim, num_class, **kwargs)
+        _draw_linear(feat_dim, num_class)                          # Finetune.classifier (finetune.py:10): unused, but draws RNG
+        self._set_head(*_draw_linear(feat_dim, kwargs["init_cls_num"]))
+        self.lamda = kwargs["lamda"]
+        self.ref_param = self.engine.params.clone()
+        self.fisher = torch.zeros_like(self.engine.params)
+        self.fisher_rows = kwargs["init_cls_num"]                  # len(self.fisher['classifier.weight'])
+
+    def before_task(self, task_idx, buffer, train_loader, test_loaders):
+        self.task_idx = task_idx
+        self._grow_head(self.kwargs["init_cls_num"] + task_idx * self.kwargs["inc_cls_num"])
+
+    def observe(self, data):
+        x, y = self._to_device(data)
+        eng = self.engine
+        n = eng.ncls
+        if self.task_idx == 0:
+            self._fused_step(x, y, ce_lo=0, ce_hi=n, pred_n=n)
+        else:
+            old = n - self.kwargs["inc_cls_num"]
+            self._fused_step(x, y, ce_lo=old, ce_hi=n, pred_n=n)
+            eng.ewc_penalty(self.ref_param, self.fisher, float(self.lamda))
+        return self._finish(x.shape[0], y)
+
+    def after_task(self, task_idx, buffer, train_loader, test_loaders):
+        """theta* <- theta; Fisher pass over the task loader in train() mode, CE over ALL logits (ewc.py:110-133,147-205)."""
+        eng = self.engine
+        self.ref_param = eng.params.clone()
+        new_fisher = torch.zeros_like(eng.params)
+        n = eng.ncls
+        nb = 0
+        for data in train_loader:
+            x, y = self._to_device(data)
+            self._fused_step(x, y, ce_lo=0, ce_hi=n, pred_n=n)
+            eng.fisher_accumulate(new_fisher, float(x.shape[0]))
+            nb += 1
+        num_samples = float(train_loader.batch_size * len(train_loader))       # ewc.py:202 (over-counts a ragged last batch)
+        alpha = 1 - self.kwargs["inc_cls_num"] / n
+        lib, st = eng.lib, torch.cuda.current_stream().cuda_stream
+        from .._lib import check
+        r, fd = self.fisher_rows, eng.feat_dim
+        segs = [(0, eng.n_backbone, True), (eng.off_fc_w, r * fd, True), (eng.off_fc_w + r * fd, (n - r) * fd, False),
+                (eng.off_fc_b, r, True), (eng.off_fc_b + r, n - r, False)]
+        for off, cnt, merge in segs:
+            if cnt > 0:
+                check(lib.lc_fisher_merge(new_fisher.data_ptr() + 4 * off, (self.fisher.data_ptr() + 4 * off) if merge else None, cnt, num_samples,
+                                          float(alpha), st), "lc_fisher_merge")
+        self.fisher = new_fisher
+        self.fisher_rows = n
+
+
+class ICarl(_ResNetMethod):
+    """core/model/icarl.py:42-221 (training / distillation path; exemplar management is host-side)."""
+
+    def __init__(self, backbone, feat_dim, num_class, **kwargs):
+        super().__init__(backbone, feat_dim, num_class, **kwargs)
+        self._set_head(*_draw_linear(feat_dim, num_class))
+        self.cur_task_id = 0
+        self.cur_cls_indexes = None
+        self.old_network = None
+        self.prev_cls_num = 0
+        self.accu_cls_num = 0
+        self.init_cls_num, self.inc_cls_num, self.task_num = kwargs["init_cls_num"], kwargs["inc_cls_num"], kwargs["task_num"]
+        self.class_means = None
+
+    def get_parameters(self, config):
+        return self._params()
+
+    def before_task(self, task_idx, buffer, train_loader, test_loaders):
+        self.accu_cls_num = self.init_cls_num if self.cur_task_id == 0 else self.accu_cls_num + self.inc_cls_num
+        self.cur_cls_indexes = np.arange(self.prev_cls_num, self.accu_cls_num)
+
+    def snapshot_teacher(self):
+        """The teacher lines of after_task (icarl.py:172-176): frozen eval-mode copy of the current network."""
+        self.old_network = TeacherState(self.engine)
+        self.prev_cls_num = self.accu_cls_num
+
+    def after_task(self, task_idx, buffer, train_loader, test_loaders):
+        self.snapshot_teacher()
+        if buffer is not None and hasattr(buffer, "reduce_old_data"):
+            buffer.reduce_old_data(self.cur_task_id, self.accu_cls_num)
+            val_transform = test_loaders[0].dataset.trfms
+            buffer.update(self.network, train_loader, val_transform, self.cur_task_id, self.accu_cls_num, self.cur_cls_indexes, self.device)
+        self.cur_task_id += 1
+
+    def observe(self, data):
+        x, y = self._to_device(data)
+        kd = self.cur_task_id > 0 and self.old_network is not None
+        self._fused_step(x, y, ce_lo=0, ce_hi=self.accu_cls_num, pred_n=self.accu_cls_num, teacher=self.old_network if kd else None,
+                         kd_n=self.prev_cls_num if kd else 0, kd_w=1.0)
+        return self._finish(x.shape[0], y)
+
+    def inference(self, data):
+        x, y = self._to_device(data)
+        logits = self._infer_logits(x)[:, :self.accu_cls_num]
+        pred = torch.argmax(logits, dim=1)
+        return pred, torch.sum(pred == y).item() / x.size(0)
+
+
+class LWF(_ResNetMethod):
+    """core/model/lwf.py:9-81 (lamda = 3 and T = 2 are hard-coded by the reference at :63-65)."""
+
+    def __init__(self, backbone, feat_dim, num_class, **kwargs):
+        super().__init__(backbone, feat_dim, num_class, **kwargs)
+        _draw_linear(feat_dim, num_class)                          # Finetune.classifier, replaced right away (lwf.py:14)
+        self._set_head(*_draw_linear(feat_dim, kwargs["init_cls_num"]))
+        self.init_cls_num, self.inc_cls_num = kwargs["init_cls_num"], kwargs["inc_cls_num"]
+        self.known_cls_num = 0
+        self.total_cls_num = 0
+        self.old = None
+
+    def before_task(self, task_idx, buffer, train_loader, test_loaders):
+        self.task_idx = task_idx
+        self.known_cls_num = self.total_cls_num
+        self.total_cls_num = self.init_cls_num + task_idx * self.inc_cls_num
+        eng = self.engine
+        # update_fc (lwf.py:28-42): fresh Linear(total), old rows copied over
+        n_old = eng.ncls
+        w_new, b_new = _draw_linear(self.feat_dim, self.total_cls_num)
+        if task_idx != 0:
+            self.old = TeacherState(eng)                           # old_fc + old_backbone, frozen, eval (lwf.py:31,49-50)
+        w, b = eng.fc_views(self.total_cls_num)
+        w[n_old:].copy_(w_new[n_old:])
+        b[n_old:].copy_(b_new[n_old:])
+        eng.ncls = self.total_cls_num
+        self.network = _Network(self.backbone, _Head(eng, self.total_cls_num))
+
+    def observe(self, data):
+        x, y = self._to_device(data)
+        n = self.engine.ncls
+        if self.task_idx == 0:
+            self._fused_step(x, y, ce_lo=0, ce_hi=n, pred_n=n)
+        else:
+            self._fused_step(x, y, ce_lo=self.known_cls_num, ce_hi=n, pred_n=n, teacher=self.old, kd_n=self.known_cls_num, kd_w=3.0)
+        return self._finish(x.shape[0], y)

@@ -1,0 +1,46 @@
+"""Flat-arena optimizers: one fused kernel over the whole parameter arena instead of torch's per-tensor foreach kernels
+(reference: torch.optim.SGD / Adam built by trainer.py:159-182 and rebuilt every task at :294).
+
+They subclass torch.optim.Optimizer so that LR schedulers (`param_groups[i]['lr']`) keep working."""
+from __future__ import annotations
+
+import torch
+
+from ._lib import check
+
+
+class SGD(torch.optim.Optimizer):
+    def __init__(self, params, lr=0.1, momentum=0.0, weight_decay=0.0, *, engine=None, model=None):
+        if engine is None:
+            engine = getattr(model, "engine", None)
+        if engine is None:
+            raise ValueError("libcontinual_b200.optim.SGD needs engine= (or model= with an .engine)")
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+        self.engine = engine
+        self.buf = torch.zeros_like(engine.params)
+        self.hp = torch.zeros(4, device=engine.device)
+        self._hp_host = None
+        self._check_views = True
+
+    def zero_grad(self, set_to_none: bool = True):
+        # every gradient element is overwritten by the next fused step; nothing to clear
+        return None
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        g = self.param_groups[0]
+        hp = (float(g["lr"]), float(g["momentum"]), float(g["weight_decay"]))
+        if hp != self._hp_host:
+            self.hp[:3] = torch.tensor(hp, device=self.hp.device)
+            self._hp_host = hp
+        eng = self.engine
+        if self._check_views:
+            # gradients must still live in the arena (autograd keeps the views the fused step hands it)
+            lo, hi = eng.grads.data_ptr(), eng.grads.data_ptr() + 4 * eng.grads.numel()
+            for grp in self.param_groups:
+                for p in grp["params"]:
+                    if p.grad is not None and not (lo <= p.grad.data_ptr() < hi):
+                        off = (p.data_ptr() - eng.params.data_ptr()) // 4
+                        eng.grads[off:off + p.numel()].copy_(p.grad.reshape(-1))
+        eng.sgd_step(self.buf, self.hp)
+        return None

@@ -1,0 +1,282 @@
+"""GPU: network-level and method-level parity of the CUDA hot path (through the plugin classes, which call the C ABI)
+against the CPU oracle on the same seeded inputs, and against the golden vectors recorded from the reference.
+
+Tolerances (fp32 kernels, different summation order than ATen-CPU):
+  loss / logits / features          rtol 1e-4
+  gradients                         relative L2 per tensor <= 2e-2 and median <= 2e-3.  Gradients of a randomly initialised
+                                    BN+ReLU ResNet are discontinuous in the activations: an fp32-rounding-sized change flips
+                                    ReLU masks of near-zero pre-activations, each flip moving a weight gradient by ~1/sqrt(#terms)
+                                    (the fp32 CPU oracle differs from an fp64 run of itself by the same amount).
+  integer outputs (pred, #correct)  exact
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from tests.golden_util import load, synth_batch, synth_resnet_state
+
+pytestmark = pytest.mark.gpu
+B = 8
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def make_backbone(p, b, max_batch=B):
+    import libcontinual_b200.model as M
+    bb = M.cifar_resnet32(max_batch=max_batch)
+    sd = {**p, **b}
+    bb.load_state_dict(sd, strict=True)
+    return bb
+
+
+def load_head(method, fc_w, fc_b):
+    w, bias = method.engine.fc_views(fc_w.shape[0])
+    w.copy_(fc_w.cuda()); bias.copy_(fc_b.cuda())
+
+
+def grads_of(method):
+    eng = method.engine
+    d = {"backbone." + n: eng.param_view(n, eng.grads).clone().cpu() for n, _ in eng.layout}
+    gw, gb = eng.fc_views(eng.ncls, eng.grads)
+    d["classifier.weight"], d["classifier.bias"] = gw.clone().cpu(), gb.clone().cpu()
+    return d
+
+
+def check_step(method, orc, x, y, g=None, tag=None, opt=None):
+    pred, acc, loss = method.observe({"image": x, "label": y})
+    if opt is not None:
+        opt.zero_grad()
+    loss.backward()
+    got = grads_of(method)
+    po, ao, lo, go = orc.step(x, y, apply_update=False)
+    assert abs(float(loss) - float(lo)) <= 1e-4 * abs(float(lo)) + 1e-5, (float(loss), float(lo))
+    assert torch.equal(pred.cpu(), po) and abs(acc - ao) < 1e-9
+    errs = {n: rel_l2(got[n], go[n]) for n in go}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] <= 2e-2, (worst, errs[worst])
+    assert float(np.median(list(errs.values()))) <= 2e-3
+    if g is not None:       # the reference's own numbers
+        assert abs(float(loss) - float(g[tag + "/loss"])) <= 1e-4 * abs(float(g[tag + "/loss"])) + 1e-5
+        assert np.array_equal(pred.cpu().numpy(), g[tag + "/pred"])
+        names = [str(n) for n in g[tag + "/grad/names"]]
+        for i, n in enumerate(names):
+            ref_norm = float(g[tag + "/grad/norm"][i])
+            assert abs(float(got[n].double().norm()) - ref_norm) <= 2e-2 * ref_norm + 1e-7, n
+    return errs
+
+
+def sync_oracle_from(method, orc):
+    """Copy the CUDA path's post-step state into the oracle so that every step is compared from identical state."""
+    eng = method.engine
+    with torch.no_grad():
+        for n in orc.p:
+            orc.p[n].copy_(eng.param_view(n).cpu())
+        w, bias = eng.fc_views(eng.ncls)
+        orc.fc_w.copy_(w.cpu()); orc.fc_b.copy_(bias.cpu())
+        for bn in eng.bn_names:
+            m, v = eng.running_views(bn)
+            orc.b[bn + ".running_mean"].copy_(m.cpu()); orc.b[bn + ".running_var"].copy_(v.cpu())
+
+
+def test_backbone_forward_train_eval_matches_oracle():
+    p, b, _, _ = synth_resnet_state(101, 20)
+    bb = make_backbone(p, b)
+    x, _ = synth_batch(1000, B, 0, 10)
+    ob = {k: v.clone() for k, v in b.items()}
+    bb.train()
+    with torch.no_grad():
+        out = bb(x.cuda())
+    ref = port.cifar_resnet_forward(p, ob, x, True)
+    assert rel_l2(out["features"], ref["features"]) < 1e-4
+    for a, r in zip(out["fmaps"], ref["fmaps"]):
+        assert tuple(a.shape) == tuple(r.shape) and rel_l2(a, r) < 1e-4
+    sd = bb.state_dict()
+    for k, v in ob.items():      # running statistics moved exactly like nn.BatchNorm2d's
+        if "num_batches" in k:
+            assert int(sd[k]) == int(v)
+        else:
+            assert torch.allclose(sd[k].cpu(), v, rtol=1e-4, atol=1e-6), k
+    bb.eval()
+    with torch.no_grad():
+        out_e = bb(x.cuda())
+    ref_e = port.cifar_resnet_forward(p, ob, x, False)
+    assert rel_l2(out_e["features"], ref_e["features"]) < 1e-4
+
+
+def test_backbone_autograd_function_matches_oracle():
+    """Generic drop-in use: reference-style head on top of backbone(x)['features'] with torch autograd."""
+    p, b, fc_w, fc_b = synth_resnet_state(101, 20)
+    bb = make_backbone(p, b)
+    bb.train()
+    x, y = synth_batch(1000, B, 0, 10)
+    w = fc_w[:10].clone().cuda().requires_grad_(True)
+    feat = bb(x.cuda())["features"]
+    loss = torch.nn.functional.cross_entropy(torch.nn.functional.linear(feat, w, fc_b[:10].cuda()), y.cuda())
+    loss.backward()
+    orc = port.ResNetMethodOracle("finetune", p, b, fc_w[:10], fc_b[:10], init_cls=10, inc_cls=10)
+    _, _, lo, go = orc.step(x, y, apply_update=False)
+    assert abs(float(loss) - float(lo)) < 1e-4
+    errs = [rel_l2(q.grad, go["backbone." + n]) for n, q in bb.named_parameters()]
+    assert max(errs) < 2e-2 and float(np.median(errs)) < 2e-3
+    assert rel_l2(w.grad, go["classifier.weight"]) < 1e-3
+
+
+def test_ewc_trajectory_vs_oracle_and_reference_golden():
+    import libcontinual_b200.model as M
+    from libcontinual_b200.optim import SGD
+    g = load("ewc_resnet32.npz")
+    p, b, fc_w, fc_b = synth_resnet_state(101, 20)
+    bb = make_backbone(p, b)
+    m = M.EWC(bb, 64, 100, device=torch.device("cuda"), init_cls_num=10, inc_cls_num=10, lamda=1000.0)
+    m.before_task(0, None, None, None)
+    load_head(m, fc_w[:10], fc_b[:10])
+    m.train()
+    opt = SGD(m.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4, engine=m.engine)
+    orc = port.ResNetMethodOracle("ewc", p, b, fc_w[:10], fc_b[:10], init_cls=10, inc_cls=10, lamda=1000.0)
+    # step 0 starts from exactly the reference's state: compare with the golden too
+    x, y = synth_batch(1000, B, 0, 10)
+    check_step(m, orc, x, y, g, "t0s0", opt)
+    opt.step(); orc.step(x, y)                               # both advance
+    # SGD step parity (momentum buffer = grad on the first step)
+    for n in ("conv_1_3x3.weight", "stage_3.4.conv_b.weight"):
+        assert rel_l2(m.engine.param_view(n), orc.p[n]) < 1e-4
+    sync_oracle_from(m, orc)
+    x, y = synth_batch(1001, B, 0, 10)
+    check_step(m, orc, x, y, None, None, opt)
+    opt.step()
+    sync_oracle_from(m, orc)
+    # task boundary: Fisher over 3 batches (last one ragged), train-mode BN
+    fb = [synth_batch(1100 + i, B if i < 2 else 5, 0, 10) for i in range(3)]
+
+    class Loader(list):
+        batch_size = B
+    m.after_task(0, None, Loader([{"image": xx, "label": yy} for xx, yy in fb]), None)
+    orc.ewc_after_task(fb, B)
+    eng = m.engine
+    f_errs = []
+    for n in orc.p:
+        f_errs.append(rel_l2(eng.param_view(n, m.fisher), orc.fisher["backbone." + n]))
+    fw, fbias = eng.fc_views(10, m.fisher)
+    f_errs += [rel_l2(fw, orc.fisher["classifier.weight"]), rel_l2(fbias, orc.fisher["classifier.bias"])]
+    assert max(f_errs) < 5e-2 and float(np.median(f_errs)) < 5e-3, max(f_errs)
+    # identical state for task 1 (Fisher and theta* taken from the CUDA path)
+    sync_oracle_from(m, orc)
+    orc.ref = {k: v.detach().clone() for k, v in orc.named().items()}
+    for n in orc.p:
+        orc.fisher["backbone." + n] = eng.param_view(n, m.fisher).cpu().clone()
+    orc.fisher["classifier.weight"], orc.fisher["classifier.bias"] = fw.cpu().clone(), fbias.cpu().clone()
+    m.before_task(1, None, None, None)
+    load_head(m, fc_w[:20], fc_b[:20]); w10, b10 = eng.fc_views(10)
+    w10.copy_(orc.fc_w.detach().cuda()); b10.copy_(orc.fc_b.detach().cuda())
+    opt = SGD(m.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4, engine=m.engine)
+    orc.task_idx = 1
+    orc.grow_head(fc_w[:20], fc_b[:20]); orc.reset_optimizer()
+    for s in range(3):
+        x, y = synth_batch(1200 + s, B, 10, 20)
+        check_step(m, orc, x, y, None, None, opt)
+        if s > 0:
+            assert float(m.engine.scal[4]) > 0.0             # the penalty is live once theta has moved away from theta*
+        opt.step()
+        sync_oracle_from(m, orc)
+
+
+def test_icarl_kd_step_vs_oracle_and_golden():
+    import libcontinual_b200.model as M
+    from libcontinual_b200.optim import SGD
+    g = load("icarl_resnet32.npz")
+    p, b, fc_w, fc_b = synth_resnet_state(202, 100)
+    bb = make_backbone(p, b)
+    m = M.ICarl(bb, 64, 100, device=torch.device("cuda"), init_cls_num=10, inc_cls_num=5, task_num=11)
+    load_head(m, fc_w, fc_b)
+    m.before_task(0, None, None, None)
+    m.train()
+    opt = SGD(m.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4, engine=m.engine)
+    orc = port.ResNetMethodOracle("icarl", p, b, fc_w, fc_b, init_cls=10, inc_cls=5)
+    x, y = synth_batch(2000, B, 0, 10)
+    check_step(m, orc, x, y, g, "t0s0", opt)
+    opt.step()
+    sync_oracle_from(m, orc)
+    m.snapshot_teacher(); m.cur_task_id += 1
+    m.before_task(1, None, None, None)
+    orc.snapshot_teacher(); orc.prev_cls = 10; orc.accu_cls = 15; orc.task_idx = 1; orc.reset_optimizer()
+    opt = SGD(m.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4, engine=m.engine)
+    for s in range(2):
+        x, y = synth_batch(2100 + s, B, 0, 15)
+        check_step(m, orc, x, y, None, None, opt)
+        assert float(m.engine.scal[3]) > 0.0                  # KD term is live
+        opt.step()
+        sync_oracle_from(m, orc)
+
+
+def test_lwf_kd_step_vs_oracle():
+    import libcontinual_b200.model as M
+    p, b, fc_w, fc_b = synth_resnet_state(303, 20)
+    bb = make_backbone(p, b)
+    m = M.LWF(bb, 64, 100, device=torch.device("cuda"), init_cls_num=10, inc_cls_num=10)
+    m.before_task(0, None, None, None)
+    load_head(m, fc_w[:10], fc_b[:10])
+    m.train()
+    orc = port.ResNetMethodOracle("lwf", p, b, fc_w[:10], fc_b[:10], init_cls=10, inc_cls=10)
+    g = load("lwf_resnet32.npz")
+    x, y = synth_batch(3000, B, 0, 10)
+    check_step(m, orc, x, y, g, "t0s0")
+    m.before_task(1, None, None, None)
+    load_head(m, fc_w[:20], fc_b[:20])
+    orc.snapshot_teacher(); orc.prev_cls = 10; orc.task_idx = 1
+    orc.grow_head(fc_w[:20], fc_b[:20])
+    sync_oracle_from(m, orc)                                  # BN running stats moved in step 0 on both sides
+    orc.snapshot_teacher()
+    m.old = type(m.old)(m.engine); m.old.ncls = 10           # teacher = current weights on both sides
+    x, y = synth_batch(3100, B, 10, 20)
+    check_step(m, orc, x, y)
+
+
+def test_reference_trainer_order_with_torch_sgd():
+    """The unmodified reference step order with torch.optim.SGD on the plugin's parameters (trainer.py:601-606)."""
+    import libcontinual_b200.model as M
+    p, b, fc_w, fc_b = synth_resnet_state(101, 20)
+    bb = make_backbone(p, b)
+    m = M.EWC(bb, 64, 100, device=torch.device("cuda"), init_cls_num=10, inc_cls_num=10, lamda=1000.0)
+    m.before_task(0, None, None, None)
+    load_head(m, fc_w[:10], fc_b[:10])
+    m.train()
+    opt = torch.optim.SGD(m.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    orc = port.ResNetMethodOracle("ewc", p, b, fc_w[:10], fc_b[:10], init_cls=10, inc_cls=10, lamda=1000.0)
+    x, y = synth_batch(1000, B, 0, 10)
+    pred, acc, loss = m.observe({"image": x, "label": y})
+    opt.zero_grad(); loss.backward(); opt.step()
+    orc.step(x, y)
+    for n in ("conv_1_3x3.weight", "stage_2.0.downsample.0.weight", "stage_3.4.bn_b.bias"):
+        assert rel_l2(m.engine.param_view(n), orc.p[n]) < 1e-4, n
+    w, _ = m.engine.fc_views(10)
+    assert rel_l2(w, orc.fc_w) < 1e-4
+
+
+def test_full_batch_128_properties():
+    """BASELINE size (bs 128): reference-free properties — finite loss near ln(10) at init, EWC penalty exactly 0 with zero
+    gradient contribution when theta == theta*, deterministic replay (bit-identical gradients run to run)."""
+    import libcontinual_b200.model as M
+    p, b, fc_w, fc_b = synth_resnet_state(7, 20)
+    bb = make_backbone(p, b, max_batch=128)
+    m = M.EWC(bb, 64, 100, device=torch.device("cuda"), init_cls_num=10, inc_cls_num=10, lamda=1000.0)
+    m.before_task(0, None, None, None)
+    load_head(m, fc_w[:10], fc_b[:10])
+    m.train()
+    x, y = synth_batch(99, 128, 0, 10)
+    _, _, loss = m.observe({"image": x, "label": y})
+    g1 = m.engine.grads.clone()
+    assert 1.5 < float(loss) < 4.0
+    state = (m.engine.rstat.clone(),)
+    m.engine.rstat.copy_(state[0])
+    _, _, loss2 = m.observe({"image": x, "label": y})
+    assert float(loss2) == float(loss) and torch.equal(m.engine.grads, g1)
+    m.ref_param = m.engine.params.clone(); m.fisher = torch.rand_like(m.engine.params)
+    m.before_task(1, None, None, None)
+    m.ref_param = m.engine.params.clone()
+    x, y = synth_batch(100, 128, 10, 20)
+    m.observe({"image": x, "label": y})
+    assert float(m.engine.scal[4]) == 0.0
