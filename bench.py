@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — images/sec per task-step of the per-step training hot path (BASELINE.json metric).
+
+Workload (default, BASELINE.json configs[1]): iCaRL, cifar_resnet32, CIFAR-100 b50-5-10, batch 128, task 1 (distillation
+against the frozen teacher active: teacher forward + student forward/backward + CE/KD + SGD momentum step), synthetic
+N(0,1) 32x32 images, random-init weights.  `--workload ewc` runs configs[0] at bs 128 (task 1, penalty active).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload icarl|ewc]
+
+value : whole-job images/s, inputs resident in HBM, one CUDA-graph replay per step, timed with CUDA events, max over ranks.
+e2e   : the same metric through the plugin surface a reference Trainer uses (observe -> zero_grad -> backward -> step ->
+        loss.item()) with batches in pinned HOST memory: H2D copy and the D2H metric reads are inside the timed region.
+N > 1 : one process per GPU (torchrun), per-GPU batch fixed at 128 (weak scaling), flat-gradient NCCL all-reduce per step.
+--impl reference : the oracle port (oracle/port.py, PyTorch CPU, all host threads) on the same workload, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec/task-step"
+BATCH = 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="icarl", choices=["icarl", "ewc"])
+    ap.add_argument("--cpu-steps", type=int, default=12, help="timed oracle steps for the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(w):
+    return {"icarl": "iCaRL ResNet32 CIFAR-100 b50-5-10 (task 1: CE + KD vs frozen teacher), bs=128, synthetic 32x32",
+            "ewc": "EWC ResNet32 CIFAR-100 b0-10-10 (task 1: CE + lamda*Fisher penalty), bs=128, synthetic 32x32"}[w]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def make_oracle(workload, seed=1993):
+    import numpy as np
+    import torch
+    from oracle import port
+    rng = np.random.default_rng(seed)
+    p, b = port.cifar_resnet_init(rng)
+    bound = 1.0 / 8.0
+    if workload == "icarl":
+        fc_w = torch.from_numpy(rng.uniform(-bound, bound, (100, 64)).astype(np.float32))
+        fc_b = torch.from_numpy(rng.uniform(-bound, bound, (100,)).astype(np.float32))
+        orc = port.ResNetMethodOracle("icarl", p, b, fc_w, fc_b, init_cls=50, inc_cls=5)
+        orc.snapshot_teacher(); orc.prev_cls, orc.accu_cls, orc.task_idx = 50, 55, 1
+        hi = 55
+    else:
+        fc_w = torch.from_numpy(rng.uniform(-bound, bound, (20, 64)).astype(np.float32))
+        fc_b = torch.from_numpy(rng.uniform(-bound, bound, (20,)).astype(np.float32))
+        orc = port.ResNetMethodOracle("ewc", p, b, fc_w, fc_b, init_cls=10, inc_cls=10, lamda=1000.0)
+        orc.task_idx = 1
+        named = orc.named()
+        orc.ref = {n: v.detach().clone() for n, v in named.items()}
+        orc.ref["classifier.weight"], orc.ref["classifier.bias"] = orc.ref["classifier.weight"][:10], orc.ref["classifier.bias"][:10]
+        orc.fisher = {n: torch.rand_like(v) * 1e-3 for n, v in orc.ref.items()}
+        hi = 20
+    return orc, hi
+
+
+def synth_batches(n, hi, lo=0, seed=7):
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(seed)
+    return [(torch.from_numpy(rng.standard_normal((BATCH, 3, 32, 32)).astype(np.float32)),
+             torch.from_numpy(rng.integers(lo, hi, (BATCH,)).astype(np.int64))) for _ in range(n)]
+
+
+def time_oracle(workload, steps, warmup):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc, hi = make_oracle(workload)
+    lo = 10 if workload == "ewc" else 0
+    batches = synth_batches(2, hi, lo)
+    for i in range(warmup):
+        orc.step(*batches[i % 2])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        orc.step(*batches[i % 2])
+    dt = time.perf_counter() - t0
+    return BATCH * steps / dt, dt / steps * 1e3, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 40)), max(1, min(args.warmup, 3))
+    ips, ms, cores = time_oracle(args.workload, steps, warm)
+    line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(args.workload), "global_batch": BATCH, "device": "cpu"},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} full training steps of batch {BATCH} (oracle/port.py, PyTorch CPU fp32, {cores} threads)"},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, l in self.rows:
+            f = [v.strip() for v in l.split(",")]
+            if len(f) < 7:
+                continue
+            if t0 - 0.05 <= t <= t1 + 0.15:
+                try:
+                    sm.append(float(f[0])); mx = float(f[1])
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(workload, device):
+    import numpy as np
+    import torch
+    import libcontinual_b200.model as M
+    from libcontinual_b200.engine import TeacherState
+    torch.manual_seed(1993)
+    bb = M.cifar_resnet32(max_batch=BATCH, num_classes=100)
+    if workload == "icarl":
+        m = M.ICarl(bb, 64, 100, device=device, init_cls_num=50, inc_cls_num=5, task_num=11)
+        m.before_task(0, None, None, None)
+        m.snapshot_teacher(); m.cur_task_id += 1
+        m.before_task(1, None, None, None)                # accu 55, prev 50, teacher = frozen copy
+        lo, hi = 0, 55
+    else:
+        m = M.EWC(bb, 64, 100, device=device, init_cls_num=10, inc_cls_num=10, lamda=1000)
+        m.before_task(0, None, None, None)
+        m.before_task(1, None, None, None)
+        m.ref_param = m.engine.params.clone()
+        m.fisher = torch.rand_like(m.engine.params) * 1e-3
+        e = m.engine                                      # Fisher exists for the old head rows only (ewc.py:224)
+        m.fisher[e.off_fc_w + 10 * 64:e.off_fc_b] = 0
+        m.fisher[e.off_fc_b + 10:] = 0
+        lo, hi = 10, 20
+    m.train()
+    return m, lo, hi
+
+
+def time_dominant_kernel(eng, reps=40):
+    """conv3x3 16->16 @32x32 (stage-1 forward/dgrad kernel) timed alone with CUDA events on its launch stream, rotating over
+    enough distinct (input, output) pairs that every launch reads cold HBM (set > L2)."""
+    import torch
+    from libcontinual_b200._lib import check
+    lib = eng.lib
+    B, C, W = BATCH, 16, 32
+    n = B * W * W * C
+    pairs = 24                                    # 24 * 2 * 8.4 MB = 403 MB > 126 MB L2
+    xs = [torch.randn(n, device=eng.device) for _ in range(pairs)]
+    ys = [torch.empty(n, device=eng.device) for _ in range(pairs)]
+    w = torch.randn(C, C, 3, 3, device=eng.device) * 0.1
+    scratch = torch.zeros(int(lib.lc_conv_scratch_floats(B, C, C, W)), device=eng.device)
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib.lc_conv3x3(xs[0].data_ptr(), w.data_ptr(), ys[0].data_ptr(), B, C, C, W, 1, 0, 0, None, None, None, None, None, None, None, scratch.data_ptr(), st))
+    wpack = scratch.data_ptr() + 4 * 80
+    for i in range(pairs):
+        check(lib.lc_conv3x3_packed(xs[i].data_ptr(), wpack, ys[i].data_ptr(), B, C, C, W, 1, None, None, st))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        check(lib.lc_conv3x3_packed(xs[i % pairs].data_ptr(), wpack, ys[i % pairs].data_ptr(), B, C, C, W, 1, None, None, st))
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    algo_bytes = 2 * n * 4 + C * C * 9 * 4          # read X, write Y, read W   (|X|+|Y| per conv)
+    return us, algo_bytes
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from libcontinual_b200.optim import SGD
+    from libcontinual_b200.trainer import GraphedStep, train_step_eager
+
+    m, lo, hi = build_model(args.workload, device)
+    opt = SGD(m.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4, engine=m.engine)
+    eng = m.engine
+    host = synth_batches(8, hi, lo, seed=7 + rank)
+    host = [(x.pin_memory(), y.pin_memory()) for x, y in host]
+    devb = [(x.to(device), y.to(device)) for x, y in host]
+    K, W = args.steps, max(3, args.warmup)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: HBM-resident inputs, graph replay ---------------------------------------------------------------------
+    step = GraphedStep(m, opt, BATCH)
+    for i in range(W):
+        step.run(*devb[i % len(devb)])
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(K):
+        step.run(*devb[i % len(devb)])
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    final_loss = float(step.loss())
+    t = torch.tensor([ms_total], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t) / K
+    value = world * BATCH / (ms_step * 1e-3)
+    launches = step.launches_per_step * K + (K if world > 1 else 0)
+
+    # ---- e2e: public step API with pinned HOST batches; H2D copy and the D2H loss read are inside the timed region -------
+    Ke = max(10, min(K, 200))
+    for i in range(3):
+        step.run(*host[i % 8]); float(step.loss())
+    barrier()
+    e0.record()
+    for i in range(Ke):
+        step.run(*host[i % 8])
+        lossv = step.loss().item()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t) / Ke
+    e2e = {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": BATCH * 3 * 32 * 32 * 4 + BATCH * 8,
+           "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
+           "path": "libcontinual_b200.trainer.GraphedStep.run(pinned host batch) + loss().item() every step"}
+    # the literal reference Trainer order on the plugin surface (eager, autograd hand-off), single replica
+    plugin = None
+    if world == 1:
+        for i in range(3):
+            train_step_eager(m, opt, {"image": host[i % 8][0], "label": host[i % 8][1]})
+        torch.cuda.synchronize()
+        Kp = max(10, min(K, 50))
+        e0.record()
+        for i in range(Kp):
+            train_step_eager(m, opt, {"image": host[i % 8][0], "label": host[i % 8][1]})
+        e1.record()
+        torch.cuda.synchronize()
+        pm = e0.elapsed_time(e1) / Kp
+        plugin = {"value": BATCH / (pm * 1e-3), "unit": "images/s", "ms_per_step": pm,
+                  "path": "plugin observe->zero_grad->loss.backward()->optim.step->loss.item() (trainer.py:601-612), eager launches"}
+    e2e["plugin_eager"] = plugin
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel + cpu baseline (rank 0) ------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    us, algo = time_dominant_kernel(eng)
+    achieved = algo / (us * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "conv3x3_kernel<16,16,32,...> (stage-1 3x3 conv fwd/dgrad, fp32 CUDA-core)", "us_per_launch": us,
+                "algorithmic_bytes_per_launch": algo, "peak_source": peak_src}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ips, ms, cores = time_oracle(args.workload, args.cpu_steps, 1)
+        cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "ms_per_step": ms,
+               "sample": f"{args.cpu_steps} full training steps of batch {BATCH} after 1 warm-up (oracle/port.py, PyTorch CPU fp32, {cores} threads)"}
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "global_batch": BATCH * world, "per_gpu_batch": BATCH, "parallelism": f"dp{world}",
+                       "l2": "per-step working set ~330 MB of fp32 activations + 8 rotating input batches > 126 MB L2 (no explicit flush)",
+                       "precision": "fp32 storage, fp32 FMA (exact mode)", "final_loss": final_loss},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

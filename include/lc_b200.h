@@ -75,6 +75,9 @@ int lc_loss_ce_kd(const float* logits, int ldl, const float* teacher, int ldt, c
                   int kd_n, float kd_w, float T, int pred_n, float* dlogits, int64_t* pred, float* scal, lc_stream_t stream);
 int lc_head_backward(const float* dlogits, int ldl, const float* feat, const float* W, int ncls, int batch, int feat_dim, float* dW,
                      float* db, float* dfeat, float* gact, int hw, lc_stream_t stream);
+/* Stand-alone nn.AvgPool2d(8)+flatten and its backward, for callers that keep their own head on backbone(x)['features']. */
+int lc_avgpool_forward(const float* act_nhwc, int batch, int hw, int feat_dim, float* feat, lc_stream_t stream);
+int lc_avgpool_backward(const float* dfeat, int batch, int hw, int feat_dim, float* gact_nhwc, lc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------------
  * Flat-arena kernels.  `hp` arrays live in DEVICE memory (CUDA-graph friendly).

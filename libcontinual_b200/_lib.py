@@ -33,6 +33,8 @@ SIGNATURES = {
     "lc_head_forward": (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, P, c_int, P]),
     "lc_loss_ce_kd": (c_int, [P, c_int, P, c_int, P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P]),
     "lc_head_backward": (c_int, [P, c_int, P, P, c_int, c_int, c_int, P, P, P, P, c_int, P]),
+    "lc_avgpool_forward": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "lc_avgpool_backward": (c_int, [P, c_int, c_int, c_int, P, P]),
     "lc_ewc_penalty_grad": (c_int, [P, P, P, P, c_longlong, P, P, P, P, P]),
     "lc_fisher_accumulate": (c_int, [P, P, c_longlong, c_float, P]),
     "lc_fisher_merge": (c_int, [P, P, c_longlong, c_float, c_float, P]),

@@ -137,4 +137,22 @@ __global__ void __launch_bounds__(C) head_bwd_kernel(const float* dlogits, int l
     }
 }
 
+// stand-alone global average pool (nn.AvgPool2d(8) + flatten, resnet.py:389-390) and its backward, for callers that put
+// their own head on top of backbone(x)['features']
+template <int C>
+__global__ void __launch_bounds__(C) avgpool_fwd_kernel(const float* act, int HW, float* feat) {
+    const int n = blockIdx.x, c = threadIdx.x;
+    const float* src = act + (size_t)n * HW * C + c;
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += __ldg(src + (size_t)p * C);
+    feat[(size_t)n * C + c] = s / (float)HW;
+}
+template <int C>
+__global__ void __launch_bounds__(C) avgpool_bwd_kernel(const float* dfeat, int HW, float* gact) {
+    const int n = blockIdx.x, c = threadIdx.x;
+    const float g = dfeat[(size_t)n * C + c] / (float)HW;
+    float* dst = gact + (size_t)n * HW * C + c;
+    for (int p = 0; p < HW; ++p) dst[(size_t)p * C] = g;
+}
+
 }  // namespace lc

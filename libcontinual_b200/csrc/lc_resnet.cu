@@ -493,6 +493,17 @@ int lc_head_backward(const float* dlogits, int ldl, const float* feat, const flo
     return lc_launch_status();
 }
 
+int lc_avgpool_forward(const float* act, int batch, int hw, int feat_dim, float* feat, lc_stream_t stream) {
+    LC_CHECK_ARG(act && feat && batch >= 1 && hw >= 1 && feat_dim == 64);
+    avgpool_fwd_kernel<64><<<batch, 64, 0, (cudaStream_t)stream>>>(act, hw, feat);
+    return lc_launch_status();
+}
+int lc_avgpool_backward(const float* dfeat, int batch, int hw, int feat_dim, float* gact, lc_stream_t stream) {
+    LC_CHECK_ARG(dfeat && gact && batch >= 1 && hw >= 1 && feat_dim == 64);
+    avgpool_bwd_kernel<64><<<batch, 64, 0, (cudaStream_t)stream>>>(dfeat, hw, gact);
+    return lc_launch_status();
+}
+
 // ---- flat arena ops ---------------------------------------------------------------------------------------------------
 int lc_ewc_penalty_grad(const float* theta, const float* theta_ref, const float* fisher, float* grad, long long n, const float* hp_lamda,
                         float* scratch, uint32_t* counter, float* scal, lc_stream_t stream) {

@@ -92,6 +92,7 @@ class ResNetEngine:
         self.flat_counter = torch.zeros(4, dtype=torch.int32, device=dev)
         self.hp = torch.zeros(16, device=dev)              # [0..2] sgd lr/mu/wd  [8] ewc lamda
         self._lamda_dev = None
+        self.autograd_grads = None                         # per-step copy of `grads` handed to autograd (p.grad are views of it)
         self.ncls = 0                                      # live rows of the head
         self.layout, self.bn_names = cifar_resnet_param_layout(depth, in_ch)
         # offsets of every named parameter and BN layer, cross-checked against the C plan
@@ -168,6 +169,19 @@ class ResNetEngine:
                                          ptr(self.ws if ws is None else ws), int(train), int(update_running), stream_ptr()), "lc_resnet_forward")
         self.launches += int(self.lib.lc_resnet_num_launches(self.h, 0))
 
+    def pool_forward(self, batch: int, ws=None):
+        w = self.ws if ws is None else ws
+        check(self.lib.lc_avgpool_forward(w.data_ptr() + 4 * self._off[LC_WS_FMAP3], batch, 64, self.feat_dim, w.data_ptr() + 4 * self._off[LC_WS_FEAT],
+                                          stream_ptr()), "lc_avgpool_forward")
+        self.launches += 1
+
+    def pool_backward(self, gfeat: torch.Tensor):
+        """d(features) [B][64] -> gradient of the last feature map (the slot lc_resnet_backward consumes)."""
+        assert gfeat.is_cuda and gfeat.dtype == torch.float32 and gfeat.is_contiguous()
+        check(self.lib.lc_avgpool_backward(ptr(gfeat), gfeat.shape[0], 64, self.feat_dim, self.ws.data_ptr() + 4 * self._off[LC_WS_GRAD_LAST], stream_ptr()),
+              "lc_avgpool_backward")
+        self.launches += 1
+
     def head_forward(self, batch: int, ncls: int, params=None, ws=None, logits=None):
         p = self.params if params is None else params
         w = self.ws if ws is None else ws
@@ -207,8 +221,9 @@ class ResNetEngine:
         check(self.lib.lc_fisher_accumulate(ptr(fisher), ptr(self.grads), self.n_total, float(weight), stream_ptr()), "lc_fisher_accumulate")
         self.launches += 1
 
-    def sgd_step(self, momentum_buf: torch.Tensor, hp: torch.Tensor):
-        check(self.lib.lc_sgd_momentum(ptr(self.params), ptr(self.grads), ptr(momentum_buf), self.n_total, ptr(hp), stream_ptr()), "lc_sgd_momentum")
+    def sgd_step(self, momentum_buf: torch.Tensor, hp: torch.Tensor, grads: Optional[torch.Tensor] = None):
+        g = self.grads if grads is None else grads
+        check(self.lib.lc_sgd_momentum(ptr(self.params), ptr(g), ptr(momentum_buf), self.n_total, ptr(hp), stream_ptr()), "lc_sgd_momentum")
         self.launches += 1
 
     # ---- composite: logits of a frozen teacher on the same batch -------------------------------------------------------

@@ -23,6 +23,7 @@ class _BackboneFn(torch.autograd.Function):
         eng: ResNetEngine = module.engine
         train = module.training
         eng.forward(x, train=train, update_running=train)
+        eng.pool_forward(x.shape[0])
         if train:
             module._bump_num_batches_tracked()
         B = x.shape[0]
@@ -38,13 +39,10 @@ class _BackboneFn(torch.autograd.Function):
         if not ctx.train:
             raise RuntimeError("backward through the backbone is only supported in train() mode (batch-statistics BN)")
         eng: ResNetEngine = module.engine
-        B = x.shape[0]
-        # avg-pool backward: broadcast dfeat / 64 over the 8x8 map into the plan's LC_WS_GRAD_LAST slot
-        from ...engine import LC_WS_GRAD_LAST
-        o = eng._off[LC_WS_GRAD_LAST]
-        eng.ws[o:o + B * 64 * 64].view(B, 64, 64).copy_((gfeat.contiguous() / 64.0).unsqueeze(1).expand(B, 64, 64))
+        eng.pool_backward(gfeat.contiguous())
         eng.backward(x)
-        grads = tuple(eng.param_view(n, eng.grads) for n, _ in eng.layout)
+        eng.autograd_grads = eng.grads.clone()      # see _ArenaLoss.backward: autograd never aliases the live arena
+        grads = tuple(eng.param_view(n, eng.autograd_grads) for n, _ in eng.layout)
         return (None, None, *grads)
 
 
@@ -53,6 +51,7 @@ class CifarResNet(nn.Module):
         super().__init__()
         self.engine = ResNetEngine(depth=depth, max_batch=max_batch, num_class_cap=num_class_cap, device=device, in_ch=channels)
         self.out_dim = 64
+        self.num_batches_pending = 0
         self._names = []
         eng = self.engine
         # same init distributions and the same RNG draw order as resnet.py:345-352
@@ -93,6 +92,7 @@ class CifarResNet(nn.Module):
             yield (prefix + ("." if prefix else "") + k.replace("__", ".")), b
 
     def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        self._flush_num_batches()
         sd = super().state_dict(*args, destination=None, prefix="", keep_vars=keep_vars)
         out = destination if destination is not None else type(sd)()
         for k, v in sd.items():
@@ -118,9 +118,14 @@ class CifarResNet(nn.Module):
             raise RuntimeError("libcontinual_b200 backbones live on the device they were built on, in fp32")
         return self
 
-    def _bump_num_batches_tracked(self):
-        for bn in self.engine.bn_names:
-            getattr(self, self._key(bn + ".num_batches_tracked")).add_(1)
+    def _bump_num_batches_tracked(self, k: int = 1):
+        self.num_batches_pending += k
+
+    def _flush_num_batches(self):
+        if self.num_batches_pending:
+            for bn in self.engine.bn_names:
+                getattr(self, self._key(bn + ".num_batches_tracked")).add_(self.num_batches_pending)
+            self.num_batches_pending = 0
 
     # reference interface -------------------------------------------------------------------------------------------------
     def forward(self, x):

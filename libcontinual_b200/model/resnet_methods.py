@@ -28,8 +28,11 @@ class _ArenaLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         owner = ctx.owner
-        owner.engine.grads.mul_(g)        # identity for the usual g == 1
-        return (None, None, *owner._grad_views())
+        eng = owner.engine
+        # autograd gets its own copy (one 1.9 MB kernel): p.grad must never alias the live arena, which the next fused step
+        # overwrites, or gradient accumulation / in-place clipping on p.grad would corrupt either side
+        eng.autograd_grads = eng.grads * g
+        return (None, None, *owner._grad_views(eng.autograd_grads))
 
 
 class _Head(nn.Module):
@@ -109,10 +112,11 @@ class _ResNetMethod(nn.Module):
     def _params(self):
         return [p for _, p in self.backbone.named_parameters()] + [self.network.classifier.weight, self.network.classifier.bias]
 
-    def _grad_views(self):
+    def _grad_views(self, arena=None):
         eng = self.engine
-        gw, gb = eng.fc_views(eng.ncls, eng.grads)
-        return tuple(eng.param_view(n, eng.grads) for n, _ in eng.layout) + (gw, gb)
+        arena = eng.grads if arena is None else arena
+        gw, gb = eng.fc_views(eng.ncls, arena)
+        return tuple(eng.param_view(n, arena) for n, _ in eng.layout) + (gw, gb)
 
     def get_parameters(self, config):
         return [{"params": self._params()}]
@@ -136,7 +140,7 @@ class _ResNetMethod(nn.Module):
         n = eng.ncls
         tl = eng.teacher_logits(teacher, x) if (teacher is not None and kd_n > 0) else None
         eng.forward(x, train=True, update_running=True)
-        self.backbone._bump_num_batches_tracked()
+        self.backbone.num_batches_pending += 1      # host bookkeeping of BN.num_batches_tracked (never read by the kernels)
         eng.head_forward(B, n)
         eng.loss(y, B, ce_lo, ce_hi, pred_n, teacher_logits=tl, kd_n=kd_n, kd_w=kd_w, T=2.0)
         eng.head_backward(B, n)
@@ -175,10 +179,13 @@ class Finetune(_ResNetMethod):
         super().__init__(backbone, feat_dim, num_class, **kwargs)
         self._set_head(*_draw_linear(feat_dim, num_class))
 
-    def observe(self, data):
-        x, y = self._to_device(data)
+    def _launch_step(self, x, y):
         n = self.engine.ncls
         self._fused_step(x, y, ce_lo=0, ce_hi=n, pred_n=n)
+
+    def observe(self, data):
+        x, y = self._to_device(data)
+        self._launch_step(x, y)
         return self._finish(x.shape[0], y)
 
 
@@ -198,8 +205,7 @@ class EWC(_ResNetMethod):
         self.task_idx = task_idx
         self._grow_head(self.kwargs["init_cls_num"] + task_idx * self.kwargs["inc_cls_num"])
 
-    def observe(self, data):
-        x, y = self._to_device(data)
+    def _launch_step(self, x, y):
         eng = self.engine
         n = eng.ncls
         if self.task_idx == 0:
@@ -208,6 +214,10 @@ class EWC(_ResNetMethod):
             old = n - self.kwargs["inc_cls_num"]
             self._fused_step(x, y, ce_lo=old, ce_hi=n, pred_n=n)
             eng.ewc_penalty(self.ref_param, self.fisher, float(self.lamda))
+
+    def observe(self, data):
+        x, y = self._to_device(data)
+        self._launch_step(x, y)
         return self._finish(x.shape[0], y)
 
     def after_task(self, task_idx, buffer, train_loader, test_loaders):
@@ -271,11 +281,14 @@ class ICarl(_ResNetMethod):
             buffer.update(self.network, train_loader, val_transform, self.cur_task_id, self.accu_cls_num, self.cur_cls_indexes, self.device)
         self.cur_task_id += 1
 
-    def observe(self, data):
-        x, y = self._to_device(data)
+    def _launch_step(self, x, y):
         kd = self.cur_task_id > 0 and self.old_network is not None
         self._fused_step(x, y, ce_lo=0, ce_hi=self.accu_cls_num, pred_n=self.accu_cls_num, teacher=self.old_network if kd else None,
                          kd_n=self.prev_cls_num if kd else 0, kd_w=1.0)
+
+    def observe(self, data):
+        x, y = self._to_device(data)
+        self._launch_step(x, y)
         return self._finish(x.shape[0], y)
 
     def inference(self, data):
@@ -313,11 +326,14 @@ class LWF(_ResNetMethod):
         eng.ncls = self.total_cls_num
         self.network = _Network(self.backbone, _Head(eng, self.total_cls_num))
 
-    def observe(self, data):
-        x, y = self._to_device(data)
+    def _launch_step(self, x, y):
         n = self.engine.ncls
         if self.task_idx == 0:
             self._fused_step(x, y, ce_lo=0, ce_hi=n, pred_n=n)
         else:
             self._fused_step(x, y, ce_lo=self.known_cls_num, ce_hi=n, pred_n=n, teacher=self.old, kd_n=self.known_cls_num, kd_w=3.0)
+
+    def observe(self, data):
+        x, y = self._to_device(data)
+        self._launch_step(x, y)
         return self._finish(x.shape[0], y)

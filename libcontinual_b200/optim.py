@@ -22,10 +22,6 @@ class SGD(torch.optim.Optimizer):
         self._hp_host = None
         self._check_views = True
 
-    def zero_grad(self, set_to_none: bool = True):
-        # every gradient element is overwritten by the next fused step; nothing to clear
-        return None
-
     @torch.no_grad()
     def step(self, closure=None):
         g = self.param_groups[0]
@@ -34,13 +30,20 @@ class SGD(torch.optim.Optimizer):
             self.hp[:3] = torch.tensor(hp, device=self.hp.device)
             self._hp_host = hp
         eng = self.engine
-        if self._check_views:
-            # gradients must still live in the arena (autograd keeps the views the fused step hands it)
-            lo, hi = eng.grads.data_ptr(), eng.grads.data_ptr() + 4 * eng.grads.numel()
+        ag = eng.autograd_grads
+        p0 = g["params"][0]
+        if ag is not None and p0.grad is not None and p0.grad.data_ptr() == ag.data_ptr():
+            src = ag          # fast path: p.grad are the views of the flat copy that backward() produced (clipping included)
+        else:
+            # generic path: gather whatever autograd left in p.grad back into the arena layout
+            src = eng.grads
+            base = eng.params.data_ptr()
             for grp in self.param_groups:
                 for p in grp["params"]:
-                    if p.grad is not None and not (lo <= p.grad.data_ptr() < hi):
-                        off = (p.data_ptr() - eng.params.data_ptr()) // 4
-                        eng.grads[off:off + p.numel()].copy_(p.grad.reshape(-1))
-        eng.sgd_step(self.buf, self.hp)
+                    off = (p.data_ptr() - base) // 4
+                    if p.grad is None:
+                        src[off:off + p.numel()].zero_()
+                    else:
+                        src[off:off + p.numel()].copy_(p.grad.reshape(-1))
+        eng.sgd_step(self.buf, self.hp, grads=src)
         return None

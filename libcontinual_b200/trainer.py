@@ -1,0 +1,99 @@
+"""Step loop of the reference `Trainer._train` (core/trainer.py:563-614) on top of the fused kernels.
+
+Two ways to run one training step of a method plugin:
+
+* `train_step_eager(model, optimizer, batch)` — literally the reference order (`observe` -> `zero_grad` -> `loss.backward()` ->
+  `optimizer.step()` -> `loss.item()`), usable with torch.optim or `libcontinual_b200.optim`.
+* `GraphedStep` — the same kernel sequence (teacher forward, backbone forward, head, loss, backward, regulariser, fused SGD)
+  captured once into a CUDA graph and replayed per batch: no per-launch host work, no autograd bookkeeping, metrics stay on the
+  device until asked for.  With `world_size > 1` the flat gradient arena is all-reduced (NCCL, average) between backward and
+  the optimizer kernel — one bucket, the only collective on the data path.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .optim import SGD
+
+
+def train_step_eager(model, optimizer, batch):
+    """trainer.py:601-612, default branch."""
+    pred, acc, loss = model.observe(batch)
+    optimizer.zero_grad()
+    loss.backward()
+    optimizer.step()
+    return pred, acc, loss.item()
+
+
+class GraphedStep:
+    def __init__(self, model, optimizer: SGD, batch_size: int, process_group=None, warmup: int = 3):
+        eng = model.engine
+        assert isinstance(optimizer, SGD), "GraphedStep drives the fused flat optimizer"
+        self.model, self.opt, self.eng, self.B = model, optimizer, eng, batch_size
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if (process_group is not None or (
+            torch.distributed.is_available() and torch.distributed.is_initialized())) else 1
+        dev = eng.device
+        self.x = torch.zeros(batch_size, eng.in_ch, eng.img, eng.img, device=dev)
+        self.y = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+        self._sync_hp()
+        # warm-up on a side stream (sets func attributes, primes the allocator), then capture
+        pending0 = model.backbone.num_batches_pending
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        saved = (eng.params.clone(), eng.rstat.clone(), optimizer.buf.clone())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._fwd_bwd()
+                self._update()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        eng.params.copy_(saved[0]); eng.rstat.copy_(saved[1]); optimizer.buf.copy_(saved[2])
+        l0 = eng.launches
+        self.g_main = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_main):
+            self._fwd_bwd()
+            if self.world == 1:
+                self._update()
+        self.g_upd = None
+        if self.world > 1:
+            self.g_upd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_upd):
+                self._update()
+        self.launches_per_step = eng.launches - l0
+        model.backbone.num_batches_pending = pending0      # warm-up / capture launches restored above do not count
+        self.steps = 0
+
+    def _sync_hp(self):
+        g = self.opt.param_groups[0]
+        hp = (float(g["lr"]), float(g["momentum"]), float(g["weight_decay"]))
+        if hp != self.opt._hp_host:
+            self.opt.hp[:3] = torch.tensor(hp, device=self.opt.hp.device)
+            self.opt._hp_host = hp
+
+    def _fwd_bwd(self):
+        self.model._launch_step(self.x, self.y)
+
+    def _update(self):
+        self.eng.sgd_step(self.opt.buf, self.opt.hp)
+
+    def run(self, x: torch.Tensor, y: torch.Tensor, non_blocking: bool = True):
+        """One step on a batch that is either device-resident or in (pinned) host memory.  Returns nothing: read
+        `loss()` / `correct()` when needed (device scalars)."""
+        self._sync_hp()
+        self.x.copy_(x, non_blocking=non_blocking)
+        self.y.copy_(y, non_blocking=non_blocking)
+        self.g_main.replay()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.eng.grads, op=torch.distributed.ReduceOp.AVG, group=self.pg)
+            self.g_upd.replay()
+        self.steps += 1
+        self.model.backbone.num_batches_pending += 1
+
+    def loss(self) -> torch.Tensor:
+        return self.eng.scal[0]
+
+    def correct(self) -> torch.Tensor:
+        return self.eng.scal[1]

@@ -167,7 +167,7 @@ def lwf_loss(logits: Tensor, y: Tensor, known: int, teacher_logits: Optional[Ten
     """`LWF.observe`, lwf.py:52-70 (lamda=3 and T=2 are hard-coded at :63-65)."""
     if teacher_logits is None:
         return F.cross_entropy(logits, y)
-    return 3 * kd_loss(logits[:, :known], teacher_logits, 2.0) + F.cross_entropy(logits[:, known:], y - known)
+    return 3 * kd_loss(logits[:, :known], teacher_logits[:, :known], 2.0) + F.cross_entropy(logits[:, known:], y - known)
 
 
 def lucir_loss(feat: Tensor, ref_feat: Tensor, logits: Tensor, scores_bs: Tensor, y: Tensor, num_old: int,

@@ -18,8 +18,22 @@ def lib():
     return _lib.load()
 
 
+_KEEP = []
+
+
+@pytest.fixture(autouse=True)
+def _keepalive():
+    """Raw pointers are handed to the C ABI: every device temporary must outlive the (asynchronous) call."""
+    _KEEP.clear()
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
+
+
 def dev(t):
-    return t.cuda().contiguous()
+    d = t.cuda().contiguous()
+    _KEEP.append(d)
+    return d
 
 
 def nhwc(t):

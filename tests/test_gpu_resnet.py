@@ -3,10 +3,14 @@ against the CPU oracle on the same seeded inputs, and against the golden vectors
 
 Tolerances (fp32 kernels, different summation order than ATen-CPU):
   loss / logits / features          rtol 1e-4
-  gradients                         relative L2 per tensor <= 2e-2 and median <= 2e-3.  Gradients of a randomly initialised
-                                    BN+ReLU ResNet are discontinuous in the activations: an fp32-rounding-sized change flips
-                                    ReLU masks of near-zero pre-activations, each flip moving a weight gradient by ~1/sqrt(#terms)
-                                    (the fp32 CPU oracle differs from an fp64 run of itself by the same amount).
+  gradients, first step from the    relative L2 per tensor <= 1e-4 (measured 7e-6): no ReLU mask differs from the oracle's on these
+  golden state ("tight")            fixed seeded inputs, so only summation order differs.
+  gradients, later steps            relative L2 per tensor <= 5e-2 and median <= 2e-2.  Gradients of a BN+ReLU ResNet are
+                                    discontinuous in the activations: an fp32-rounding-sized change flips the ReLU mask of a
+                                    near-zero pre-activation, and one flip moves every upstream gradient by ~1/sqrt(#terms)
+                                    (~5e-3 at batch 8).  The fp32 CPU oracle differs from an fp64 run of ITSELF by the same
+                                    amount (measured: median 5e-3, max 4e-2 at batch 32; DESIGN.md "Parity").  The per-kernel
+                                    tests (tests/test_gpu_kernels.py) carry the tight per-op tolerances.
   integer outputs (pred, #correct)  exact
 """
 import numpy as np
@@ -46,7 +50,7 @@ def grads_of(method):
     return d
 
 
-def check_step(method, orc, x, y, g=None, tag=None, opt=None):
+def check_step(method, orc, x, y, g=None, tag=None, opt=None, tight=False):
     pred, acc, loss = method.observe({"image": x, "label": y})
     if opt is not None:
         opt.zero_grad()
@@ -57,8 +61,10 @@ def check_step(method, orc, x, y, g=None, tag=None, opt=None):
     assert torch.equal(pred.cpu(), po) and abs(acc - ao) < 1e-9
     errs = {n: rel_l2(got[n], go[n]) for n in go}
     worst = max(errs, key=errs.get)
-    assert errs[worst] <= 2e-2, (worst, errs[worst])
-    assert float(np.median(list(errs.values()))) <= 2e-3
+    if tight:
+        assert errs[worst] <= 1e-4, (worst, errs[worst])
+    assert errs[worst] <= 5e-2, (worst, errs[worst])
+    assert float(np.median(list(errs.values()))) <= 2e-2
     if g is not None:       # the reference's own numbers
         assert abs(float(loss) - float(g[tag + "/loss"])) <= 1e-4 * abs(float(g[tag + "/loss"])) + 1e-5
         assert np.array_equal(pred.cpu().numpy(), g[tag + "/pred"])
@@ -121,8 +127,8 @@ def test_backbone_autograd_function_matches_oracle():
     _, _, lo, go = orc.step(x, y, apply_update=False)
     assert abs(float(loss) - float(lo)) < 1e-4
     errs = [rel_l2(q.grad, go["backbone." + n]) for n, q in bb.named_parameters()]
-    assert max(errs) < 2e-2 and float(np.median(errs)) < 2e-3
-    assert rel_l2(w.grad, go["classifier.weight"]) < 1e-3
+    assert max(errs) < 1e-4, max(errs)
+    assert rel_l2(w.grad, go["classifier.weight"]) < 1e-4
 
 
 def test_ewc_trajectory_vs_oracle_and_reference_golden():
@@ -139,7 +145,7 @@ def test_ewc_trajectory_vs_oracle_and_reference_golden():
     orc = port.ResNetMethodOracle("ewc", p, b, fc_w[:10], fc_b[:10], init_cls=10, inc_cls=10, lamda=1000.0)
     # step 0 starts from exactly the reference's state: compare with the golden too
     x, y = synth_batch(1000, B, 0, 10)
-    check_step(m, orc, x, y, g, "t0s0", opt)
+    check_step(m, orc, x, y, g, "t0s0", opt, tight=True)
     opt.step(); orc.step(x, y)                               # both advance
     # SGD step parity (momentum buffer = grad on the first step)
     for n in ("conv_1_3x3.weight", "stage_3.4.conv_b.weight"):
