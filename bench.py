@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--workload", default="icarl", choices=["icarl", "ewc"])
     ap.add_argument("--cpu-steps", type=int, default=12, help="timed oracle steps for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
+                    help="conv arithmetic: tf32 = tcgen05 tensor cores (cuDNN's default class for the reference), fp32 = exact CUDA-core path")
     return ap.parse_args()
 
 
@@ -158,13 +160,13 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_model(workload, device):
+def build_model(workload, device, precision="tf32"):
     import numpy as np
     import torch
     import libcontinual_b200.model as M
     from libcontinual_b200.engine import TeacherState
     torch.manual_seed(1993)
-    bb = M.cifar_resnet32(max_batch=BATCH, num_classes=100)
+    bb = M.cifar_resnet32(max_batch=BATCH, num_classes=100, precision=precision)
     if workload == "icarl":
         m = M.ICarl(bb, 64, 100, device=device, init_cls_num=50, inc_cls_num=5, task_num=11)
         m.before_task(0, None, None, None)
@@ -200,7 +202,7 @@ def time_dominant_kernel(eng, reps=40):
     scratch = torch.zeros(int(lib.lc_conv_scratch_floats(B, C, C, W)), device=eng.device)
     st = torch.cuda.current_stream().cuda_stream
     check(lib.lc_conv3x3(xs[0].data_ptr(), w.data_ptr(), ys[0].data_ptr(), B, C, C, W, 1, 0, 0, None, None, None, None, None, None, None, scratch.data_ptr(), st))
-    wpack = scratch.data_ptr() + 4 * 80
+    wpack = scratch.data_ptr() + 4 * 96
     for i in range(pairs):
         check(lib.lc_conv3x3_packed(xs[i].data_ptr(), wpack, ys[i].data_ptr(), B, C, C, W, 1, None, None, st))
     torch.cuda.synchronize()
@@ -228,7 +230,7 @@ def run_ours(args):
     from libcontinual_b200.optim import SGD
     from libcontinual_b200.trainer import GraphedStep, train_step_eager
 
-    m, lo, hi = build_model(args.workload, device)
+    m, lo, hi = build_model(args.workload, device, args.precision)
     opt = SGD(m.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4, engine=m.engine)
     eng = m.engine
     host = synth_batches(8, hi, lo, seed=7 + rank)
@@ -322,10 +324,12 @@ def run_ours(args):
         cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "ms_per_step": ms,
                "sample": f"{args.cpu_steps} full training steps of batch {BATCH} after 1 warm-up (oracle/port.py, PyTorch CPU fp32, {cores} threads)"}
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision.replace("fp32", "f32"), "data": "synthetic",
             "config": {"workload": workload_name(args.workload), "global_batch": BATCH * world, "per_gpu_batch": BATCH, "parallelism": f"dp{world}",
                        "l2": "per-step working set ~330 MB of fp32 activations + 8 rotating input batches > 126 MB L2 (no explicit flush)",
-                       "precision": "fp32 storage, fp32 FMA (exact mode)", "final_loss": final_loss},
+                       "precision": ("fp32 storage; 3x3 stride-1 conv fwd/dgrad on tcgen05 TF32 (fp32 accumulate in TMEM); everything else fp32 FMA"
+                                     if args.precision == "tf32" else "fp32 storage, fp32 FMA (exact mode)"),
+                       "final_loss": final_loss, "tensor_core_error": eng.tensor_core_error()},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -39,6 +39,11 @@ typedef struct lc_resnet lc_resnet;
 
 int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** out);
 void lc_resnet_destroy(lc_resnet* net);
+/* Arithmetic mode of the 3x3 stride-1 convolutions (forward + data gradient): 0 = exact fp32 FMA on CUDA cores (default),
+ * 1 = TF32 on the tcgen05 tensor cores, fp32 accumulation in TMEM (the arithmetic class cuDNN uses for the reference's convs
+ * under PyTorch's default allow_tf32).  workspace word 8 (int) is set to 1 if a tensor-core barrier ever timed out. */
+int lc_resnet_set_mode(lc_resnet* net, int mode);
+int lc_resnet_get_mode(const lc_resnet* net);
 long long lc_resnet_param_count(const lc_resnet* net);
 long long lc_resnet_rstat_count(const lc_resnet* net);
 long long lc_resnet_workspace_floats(const lc_resnet* net);
@@ -108,9 +113,16 @@ long long lc_conv_scratch_floats(int batch, int cin, int cout, int width_out);
 int lc_conv3x3(const float* in, const float* w_oihw, float* out, int batch, int cin, int cout, int width_out, int stride, int mode,
                int in_nchw, const float* pro_scale, const float* pro_shift, const float* addend, const float* gamma,
                const float* beta, float* rstat, float* stat_out, float* scratch, lc_stream_t stream);
-/* One launch of the forward conv kernel on pre-packed weights [cin][9][cout] (lc_conv3x3 leaves them at scratch+80). */
+/* One launch of the forward conv kernel on pre-packed weights [cin][9][cout] (lc_conv3x3 leaves them at scratch+96). */
 int lc_conv3x3_packed(const float* in, const float* wpack, float* out, int batch, int cin, int cout, int width_out, int stride,
                       const float* pro_scale, const float* pro_shift, lc_stream_t stream);
+/* tcgen05 (kind::tf32, TMEM accumulators) version for the square stride-1 layers (c, width) in {(16,32),(32,16),(64,8)};
+ * same prologue / addend / statistics options; scratch >= lc_conv_tc_scratch_floats, first 64 words zero; scratch word 8 (int)
+ * is set to 1 if the MMA completion barrier timed out. */
+long long lc_conv_tc_scratch_floats(int batch, int c, int width);
+int lc_conv3x3_tc(const float* in, const float* w_oihw, float* out, int batch, int c, int width, int mode, const float* pro_scale,
+                  const float* pro_shift, const float* addend, const float* gamma, const float* beta, float* rstat, float* stat_out,
+                  float* scratch, lc_stream_t stream);
 int lc_conv3x3_wgrad(const float* in, const float* dy, float* dw_oihw, int batch, int cin, int cout, int width_out, int stride,
                      int in_nchw, const float* pro_scale, const float* pro_shift, float* scratch, lc_stream_t stream);
 /* 1x1 stride-2 shortcut conv: mode 0 forward (+stats as above), 1 data gradient ACCUMULATED into `out` (shape of the conv

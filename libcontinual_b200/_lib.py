@@ -20,6 +20,8 @@ SIGNATURES = {
     "lc_device_check": (c_int, []),
     "lc_resnet_create": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
     "lc_resnet_destroy": (None, [P]),
+    "lc_resnet_set_mode": (c_int, [P, c_int]),
+    "lc_resnet_get_mode": (c_int, [P]),
     "lc_resnet_param_count": (c_longlong, [P]),
     "lc_resnet_rstat_count": (c_longlong, [P]),
     "lc_resnet_workspace_floats": (c_longlong, [P]),
@@ -44,6 +46,8 @@ SIGNATURES = {
     "lc_conv_scratch_floats": (c_longlong, [c_int, c_int, c_int, c_int]),
     "lc_conv3x3": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P]),
     "lc_conv3x3_packed": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "lc_conv_tc_scratch_floats": (c_longlong, [c_int, c_int, c_int]),
+    "lc_conv3x3_tc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P]),
     "lc_conv3x3_wgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "lc_conv1x1s2": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "lc_bn_act_forward": (c_int, [P, P, P, P, P, P, P, c_longlong, c_int, P]),

@@ -174,6 +174,8 @@ struct ConvTabEntry {
     long long wf_off;     // packed forward weights  [ci][tap][co]
     long long wd_off;     // packed dgrad weights    [co][ntap-1-tap][ci]   (-1: not needed)
     long long part_off;   // weight-gradient partials [nsplit][n]
+    long long wtf_off;    // tensor-core forward packing  [tap][ci/4][co][ci%4]   (-1: layer not on the tensor-core path)
+    long long wtd_off;    // tensor-core dgrad packing    [8-tap][co/4][ci][co%4]
     int cout, cin, ntap, nsplit;
     int blk_begin;        // first block of this layer in the table kernels
     int pad;
@@ -195,6 +197,13 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const ConvTabEntry* t
     const float w = params[t.w_off + e];
     packed[t.wf_off + ((size_t)ci * t.ntap + tap) * t.cout + co] = w;
     if (t.wd_off >= 0) packed[t.wd_off + ((size_t)co * t.ntap + (t.ntap - 1 - tap)) * t.cin + ci] = w;
+    if (t.wtf_off >= 0) {      // tensor-core operands are pre-rounded to TF32 (round-to-nearest-away) once per step
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(w));
+        const float wr = __uint_as_float(r);
+        packed[t.wtf_off + (((size_t)tap * (t.cin >> 2) + (ci >> 2)) * t.cout + co) * 4 + (ci & 3)] = wr;
+        packed[t.wtd_off + (((size_t)(t.ntap - 1 - tap) * (t.cout >> 2) + (co >> 2)) * t.cin + ci) * 4 + (co & 3)] = wr;
+    }
 }
 
 // grad[w_off + e] = sum_{s < nsplit} partial[part_off + s*n + e]   (fixed order => deterministic)

@@ -32,22 +32,37 @@ struct BnStatArgs {
 };
 
 template <int C, int NT>
-__device__ __forceinline__ void bn_finalize_last_block(const BnStatArgs& s, int nparts, double count, float* s_red /* >= NT floats*2 as double */) {
-    // every thread: one (stat, channel) column j = tid % (2C), slice = tid / (2C)
+__device__ __forceinline__ void bn_finalize_last_block(const BnStatArgs& s, int nparts, double count, float* s_red /* >= max(2*NT, 4*C) floats, 8B aligned */) {
+    // thread -> one float4 column group (COLS/4 of them) and one of NSL slices of the partial rows; independent float4 loads
+    // (4 accumulators, unrolled) keep enough requests in flight that the last block's tail is a few microseconds, not tens
     constexpr int COLS = 2 * C;
-    static_assert(NT % COLS == 0 || COLS % NT == 0, "thread count vs channel count");
+    constexpr int CQ = COLS / 4;
     double* red = reinterpret_cast<double*>(s_red);
-    if (NT >= COLS) {
-        constexpr int NSL = NT >= COLS ? NT / COLS : 1;
-        const int j = threadIdx.x % COLS, sl = threadIdx.x / COLS;
-        double acc = 0.0;
-        for (int p = sl; p < nparts; p += NSL) acc += (double)__ldcg(s.partial + (size_t)p * COLS + j);
-        red[threadIdx.x] = acc;
+    if (NT >= CQ) {
+        constexpr int NSL = NT >= CQ ? NT / CQ : 1;
+        static_assert(NT % CQ == 0 || NT < CQ, "thread count vs channel count");
+        const int cq = threadIdx.x % CQ, sl = threadIdx.x / CQ;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const float4* base = reinterpret_cast<const float4*>(s.partial) + cq;
+#pragma unroll 4
+        for (int p = sl; p < nparts; p += NSL) {
+            const float4 v = __ldcg(base + (size_t)p * CQ);
+            a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+        }
+        // fixed-order combine over the slices, 4 columns at a time (smem holds NT doubles)
+        for (int k = 0; k < 4; ++k) {
+            __syncthreads();
+            red[threadIdx.x] = k == 0 ? a0 : (k == 1 ? a1 : (k == 2 ? a2 : a3));
+            __syncthreads();
+            if (threadIdx.x < CQ) {
+                double t = 0.0;
+                for (int q = 0; q < NSL; ++q) t += red[q * CQ + threadIdx.x];
+                a0 = k == 0 ? t : a0; a1 = k == 1 ? t : a1; a2 = k == 2 ? t : a2; a3 = k == 3 ? t : a3;
+            }
+        }
         __syncthreads();
-        if (threadIdx.x < COLS) {
-            double t = 0.0;
-            for (int q = 0; q < NSL; ++q) t += red[q * COLS + threadIdx.x];
-            red[threadIdx.x] = t;
+        if (threadIdx.x < CQ) {
+            red[threadIdx.x * 4 + 0] = a0; red[threadIdx.x * 4 + 1] = a1; red[threadIdx.x * 4 + 2] = a2; red[threadIdx.x * 4 + 3] = a3;
         }
         __syncthreads();
     } else {

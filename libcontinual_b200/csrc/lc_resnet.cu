@@ -4,6 +4,7 @@
 #include "bn_elem.cuh"
 #include "conv_aux.cuh"
 #include "conv_simt.cuh"
+#include "conv_tc.cuh"
 #include "flat_ops.cuh"
 #include "head_loss.cuh"
 
@@ -69,6 +70,16 @@ int launch_wgrad3x3(int cin, int cout, int wo, int stride, bool nchw, const Wgra
     return LC_ERR_INVALID;
 }
 
+bool tc_eligible(int cin, int cout, int wo, int stride, int ksize) {
+    return ksize == 3 && stride == 1 && cin == cout && ((cin == 16 && wo == 32) || (cin == 32 && wo == 16) || (cin == 64 && wo == 8));
+}
+int launch_conv3x3_tc(int c, int wo, const tc::ConvTcArgs& a, cudaStream_t st) {
+    if (c == 16 && wo == 32) return tc::conv_tc_launch<16, 32>(a, st);
+    if (c == 32 && wo == 16) return tc::conv_tc_launch<32, 16>(a, st);
+    if (c == 64 && wo == 8) return tc::conv_tc_launch<64, 8>(a, st);
+    return LC_ERR_INVALID;
+}
+
 int wgrad_nsplit(int cin, int cout) {
     if (cout == 16) return 256;
     if (cout == 32) return 128;
@@ -125,6 +136,7 @@ struct ConvL {
     long long aff_off;                    // workspace: scale, shift, mean, invstd (4*C)
     long long y_off;                      // workspace: raw conv output
     long long wf_off, wd_off, part_off;   // workspace-relative (packed weights / partials)
+    long long wtf_off, wtd_off;           // tensor-core packings (-1 when the layer stays on the CUDA-core path)
     int nsplit;
 };
 struct BlockL {
@@ -147,6 +159,7 @@ struct lc_resnet {
     BnEvalEntry* d_bntab = nullptr;
     int tab_blocks = 0;
     int launches_fwd = 0, launches_bwd = 0;
+    int mode = 0;     // 0: exact fp32 CUDA-core convs; 1: TF32 tcgen05 convs (fwd + dgrad of the stride-1 3x3 layers)
 };
 
 extern "C" {
@@ -204,6 +217,7 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
     long long fpart = 0;
     for (auto& c : n->convs) {
         long long parts = c.ksize == 3 ? B * 8 : (B * c.wo * c.wo + 127) / 128;   // >= tiles per image of every 3x3 config
+        if (c.ksize == 3) parts = std::max(parts, tc::conv_tc_tiles((int)B, c.wo));
         fpart = std::max(fpart, parts * 2 * c.cout);
     }
     n->off_fpart = take(fpart);
@@ -214,6 +228,7 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
         const long long ne = (long long)c.cout * c.cin * c.ksize * c.ksize;
         c.wf_off = pk; pk += ne;
         if (c.ksize == 3) { c.wd_off = pk; pk += ne; } else c.wd_off = -1;
+        if (tc_eligible(c.cin, c.cout, c.wo, c.stride, c.ksize)) { c.wtf_off = pk; pk += ne; c.wtd_off = pk; pk += ne; } else { c.wtf_off = c.wtd_off = -1; }
         c.nsplit = c.ksize == 3 ? wgrad_nsplit(c.cin, c.cout) : k1x1Split;
         c.part_off = wp; wp += ne * c.nsplit;
     }
@@ -248,7 +263,7 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
     int blk = 0;
     for (auto& c : n->convs) {
         ConvTabEntry t{};
-        t.w_off = c.w_off; t.wf_off = c.wf_off; t.wd_off = c.wd_off; t.part_off = c.part_off;
+        t.w_off = c.w_off; t.wf_off = c.wf_off; t.wd_off = c.wd_off; t.part_off = c.part_off; t.wtf_off = c.wtf_off; t.wtd_off = c.wtd_off;
         t.cout = c.cout; t.cin = c.cin; t.ntap = c.ksize * c.ksize; t.nsplit = c.nsplit; t.blk_begin = blk;
         blk += (c.cout * c.cin * t.ntap + 255) / 256;
         tab.push_back(t);
@@ -276,6 +291,13 @@ void lc_resnet_destroy(lc_resnet* n) {
     if (n->d_bntab) cudaFree(n->d_bntab);
     delete n;
 }
+
+int lc_resnet_set_mode(lc_resnet* n, int mode) {
+    LC_CHECK_ARG(n && (mode == 0 || mode == 1));
+    n->mode = mode;
+    return LC_OK;
+}
+int lc_resnet_get_mode(const lc_resnet* n) { return n ? n->mode : LC_ERR_INVALID; }
 
 long long lc_resnet_param_count(const lc_resnet* n) { return n ? n->n_params : LC_ERR_INVALID; }
 long long lc_resnet_rstat_count(const lc_resnet* n) { return n ? n->n_rstat : LC_ERR_INVALID; }
@@ -324,6 +346,7 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
     cudaStream_t st = (cudaStream_t)stream;
     int launches = 0;
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws + n->off_counters);
+    int* err_flag = reinterpret_cast<int*>(counters) + 8;
     float* packed = ws + n->off_packed;
     pack_weights_kernel<<<n->tab_blocks, 256, 0, st>>>(n->d_tab, (int)n->convs.size(), params, packed);
     LC_TRY(lc_launch_status());
@@ -357,12 +380,21 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
     for (const BlockL& bl : n->blocks) {
         const ConvL& ca = n->convs[bl.conv_a];
         const ConvL& cb = n->convs[bl.conv_b];
-        {
+        if (n->mode == 1 && ca.wtf_off >= 0) {
+            tc::ConvTcArgs a{};
+            a.in = cur; a.wtc = packed + ca.wtf_off; a.out = ws + ca.y_off; a.stat = stat_for(ca); a.B = batch; a.error_flag = err_flag;
+            LC_TRY(launch_conv3x3_tc(ca.cin, ca.wo, a, st));
+        } else {
             Conv3x3Args a{};
             a.in = cur; a.wpack = packed + ca.wf_off; a.out = ws + ca.y_off; a.stat = stat_for(ca); a.B = batch;
             LC_TRY(launch_conv3x3(ca.cin, ca.cout, ca.wo, ca.stride, false, false, a, st));
         }
-        {
+        if (n->mode == 1 && cb.wtf_off >= 0) {
+            tc::ConvTcArgs a{};
+            a.in = ws + ca.y_off; a.wtc = packed + cb.wtf_off; a.out = ws + cb.y_off; a.stat = stat_for(cb); a.B = batch; a.error_flag = err_flag;
+            a.pro_scale = ws + ca.aff_off; a.pro_shift = ws + ca.aff_off + ca.cout;
+            LC_TRY(launch_conv3x3_tc(cb.cin, cb.wo, a, st));
+        } else {
             Conv3x3Args a{};
             a.in = ws + ca.y_off; a.wpack = packed + cb.wf_off; a.out = ws + cb.y_off; a.stat = stat_for(cb); a.B = batch;
             a.pro_scale = ws + ca.aff_off; a.pro_shift = ws + ca.aff_off + ca.cout;
@@ -392,6 +424,7 @@ int lc_resnet_backward(lc_resnet* n, const float* x, int batch, const float* par
     cudaStream_t st = (cudaStream_t)stream;
     int launches = 0;
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws + n->off_counters);
+    int* err_flag = reinterpret_cast<int*>(counters) + 8;
     float* packed = ws + n->off_packed;
     float* wpart = ws + n->off_wpart;
     float* T1 = ws + n->off_T1;
@@ -428,9 +461,15 @@ int lc_resnet_backward(lc_resnet* n, const float* x, int batch, const float* par
             w.in = ws + ca.y_off; w.dy = T1; w.partial = wpart + cb.part_off; w.B = batch; w.nsplit = cb.nsplit;
             w.pro_scale = ws + ca.aff_off; w.pro_shift = ws + ca.aff_off + ca.cout;
             LC_TRY(launch_wgrad3x3(cb.cin, cb.cout, cb.wo, 1, false, w, st));
-            Conv3x3Args a{};
-            a.in = T1; a.wpack = packed + cb.wd_off; a.out = T2; a.B = batch;
-            LC_TRY(launch_conv3x3(cb.cout, cb.cin, cb.wo, 1, false, false, a, st));
+            if (n->mode == 1 && cb.wtd_off >= 0) {
+                tc::ConvTcArgs a{};
+                a.in = T1; a.wtc = packed + cb.wtd_off; a.out = T2; a.B = batch; a.error_flag = err_flag;
+                LC_TRY(launch_conv3x3_tc(cb.cin, cb.wo, a, st));
+            } else {
+                Conv3x3Args a{};
+                a.in = T1; a.wpack = packed + cb.wd_off; a.out = T2; a.B = batch;
+                LC_TRY(launch_conv3x3(cb.cout, cb.cin, cb.wo, 1, false, false, a, st));
+            }
         }
         // bn_a (+ ReLU): T1 = d(y1)
         LC_TRY(bn_bwd(ca, T2, nullptr, LC_MASK_FROM_BN, T1, nullptr)); ++launches;
@@ -440,7 +479,11 @@ int lc_resnet_backward(lc_resnet* n, const float* x, int batch, const float* par
             LC_TRY(launch_wgrad3x3(ca.cin, ca.cout, ca.wo, ca.stride, false, w, st));
             Conv3x3Args a{};
             a.in = T1; a.wpack = packed + ca.wd_off; a.B = batch;
-            if (ca.stride == 1) {
+            if (ca.stride == 1 && n->mode == 1 && ca.wtd_off >= 0) {
+                tc::ConvTcArgs t{};
+                t.in = T1; t.wtc = packed + ca.wtd_off; t.out = G; t.addend = G; t.B = batch; t.error_flag = err_flag;
+                LC_TRY(launch_conv3x3_tc(ca.cin, ca.wo, t, st));
+            } else if (ca.stride == 1) {
                 a.out = G; a.addend = G;     // identity shortcut: dX = dgrad + masked G (in place)
                 LC_TRY(launch_conv3x3(ca.cout, ca.cin, ca.wo, 1, false, false, a, st));
             } else {
@@ -542,8 +585,10 @@ int lc_clip_grad_norm(float* g, long long n, float max_norm, float* scratch, flo
 }
 
 // ---- per-kernel entry points ------------------------------------------------------------------------------------------
-// scratch layout of the per-kernel entry points (floats): [0,64) election counters (caller-zeroed) | [64,80) one table
-// entry | [80, ...) packed weights / partial sums
+// scratch layout of the per-kernel entry points (floats): [0,64) election counters (caller-zeroed) | [64,96) one table
+// entry | [96, ...) packed weights / partial sums
+static_assert(sizeof(ConvTabEntry) <= 32 * sizeof(float), "table slot");
+constexpr int kOpData = 96;
 static inline long long round4(long long v) { return (v + 3) / 4 * 4; }
 
 long long lc_conv_scratch_floats(int batch, int cin, int cout, int width_out) {
@@ -552,7 +597,7 @@ long long lc_conv_scratch_floats(int batch, int cin, int cout, int width_out) {
     long long parts = (long long)batch * 8 * 2 * cm;
     const long long p1 = ((long long)batch * width_out * width_out + 127) / 128 * 2 * cm;
     if (p1 > parts) parts = p1;
-    return 80 + round4(2 * ne) + round4(parts) + ne * 256 + 64;
+    return kOpData + round4(2 * ne) + round4(parts) + ne * 256 + 64;
 }
 
 static void fill_stat(BnStatArgs& s, const float* gamma, const float* beta, float* rstat, float* stat_out, int C, float* partial, unsigned int* counter) {
@@ -569,9 +614,9 @@ int lc_conv3x3(const float* in, const float* w_oihw, float* out, int batch, int 
     cudaStream_t st = (cudaStream_t)stream;
     const long long ne = (long long)cout * cin * 9;
     ConvTabEntry t{};
-    t.w_off = 0; t.wf_off = 0; t.wd_off = ne; t.cout = cout; t.cin = cin; t.ntap = 9; t.nsplit = 0; t.blk_begin = 0;
+    t.w_off = 0; t.wf_off = 0; t.wd_off = ne; t.wtf_off = -1; t.wtd_off = -1; t.cout = cout; t.cin = cin; t.ntap = 9; t.nsplit = 0; t.blk_begin = 0;
     ConvTabEntry* d_t = reinterpret_cast<ConvTabEntry*>(scratch + 64);
-    float* packed = scratch + 80;
+    float* packed = scratch + kOpData;
     float* partial = packed + round4(2 * ne);
     if (cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, st) != cudaSuccess) return LC_ERR_CUDA;
     pack_weights_kernel<<<(int)((ne + 255) / 256), 256, 0, st>>>(d_t, 1, w_oihw, packed);
@@ -588,7 +633,7 @@ int lc_conv3x3(const float* in, const float* w_oihw, float* out, int batch, int 
     return launch_conv3x3(cout, cin, width_out * stride, 1, stride == 2, false, a, st);
 }
 
-// Single launch of the conv kernel on pre-packed weights ([cin][9][cout], as left at scratch+80 by lc_conv3x3): no packing,
+// Single launch of the conv kernel on pre-packed weights ([cin][9][cout], as left at scratch+96 by lc_conv3x3): no packing,
 // no statistics.  Used by bench.py to time the dominant kernel in isolation.
 int lc_conv3x3_packed(const float* in, const float* wpack, float* out, int batch, int cin, int cout, int width_out, int stride,
                       const float* pro_scale, const float* pro_shift, lc_stream_t stream) {
@@ -598,6 +643,35 @@ int lc_conv3x3_packed(const float* in, const float* wpack, float* out, int batch
     return launch_conv3x3(cin, cout, width_out, stride, false, false, a, (cudaStream_t)stream);
 }
 
+// Tensor-core (tcgen05 kind::tf32) version of lc_conv3x3 for the square stride-1 layers: (c, width) in {(16,32),(32,16),(64,8)}.
+// mode 0 forward, 1 data gradient.  scratch as for lc_conv3x3; scratch[8] (int) receives 1 if the MMA barrier timed out.
+int lc_conv3x3_tc(const float* in, const float* w_oihw, float* out, int batch, int c, int width, int mode, const float* pro_scale,
+                  const float* pro_shift, const float* addend, const float* gamma, const float* beta, float* rstat, float* stat_out,
+                  float* scratch, lc_stream_t stream) {
+    LC_CHECK_ARG(in && w_oihw && out && scratch && batch >= 1 && (mode == 0 || mode == 1) && ((uintptr_t)scratch % 16 == 0));
+    LC_CHECK_ARG(tc_eligible(c, c, width, 1, 3));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long ne = (long long)c * c * 9;
+    ConvTabEntry t{};
+    t.w_off = 0; t.wf_off = 0; t.wd_off = ne; t.wtf_off = 2 * ne; t.wtd_off = 3 * ne; t.cout = c; t.cin = c; t.ntap = 9; t.blk_begin = 0;
+    ConvTabEntry* d_t = reinterpret_cast<ConvTabEntry*>(scratch + 64);
+    float* packed = scratch + kOpData;
+    float* partial = packed + round4(4 * ne);
+    if (cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, st) != cudaSuccess) return LC_ERR_CUDA;
+    pack_weights_kernel<<<(int)((ne + 255) / 256), 256, 0, st>>>(d_t, 1, w_oihw, packed);
+    if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
+    tc::ConvTcArgs a{};
+    a.in = in; a.out = out; a.pro_scale = pro_scale; a.pro_shift = pro_shift; a.addend = addend; a.B = batch;
+    a.error_flag = reinterpret_cast<int*>(scratch) + 8;
+    a.wtc = packed + (mode == 0 ? 2 * ne : 3 * ne);
+    if (mode == 0 && stat_out) { LC_CHECK_ARG(gamma && beta); fill_stat(a.stat, gamma, beta, rstat, stat_out, c, partial, reinterpret_cast<unsigned int*>(scratch)); }
+    return launch_conv3x3_tc(c, width, a, st);
+}
+long long lc_conv_tc_scratch_floats(int batch, int c, int width) {
+    const long long ne = (long long)c * c * 9;
+    return kOpData + round4(4 * ne) + tc::conv_tc_tiles(batch, width) * 2 * c + 64;
+}
+
 int lc_conv3x3_wgrad(const float* in, const float* dy, float* dw, int batch, int cin, int cout, int width_out, int stride, int in_nchw,
                      const float* pro_scale, const float* pro_shift, float* scratch, lc_stream_t stream) {
     LC_CHECK_ARG(in && dy && dw && scratch && batch >= 1 && ((uintptr_t)scratch % 16 == 0));
@@ -605,9 +679,9 @@ int lc_conv3x3_wgrad(const float* in, const float* dy, float* dw, int batch, int
     const long long ne = (long long)cout * cin * 9;
     const int nsplit = wgrad_nsplit(cin, cout);
     ConvTabEntry t{};
-    t.w_off = 0; t.part_off = 0; t.cout = cout; t.cin = cin; t.ntap = 9; t.nsplit = nsplit; t.blk_begin = 0; t.wd_off = -1;
+    t.w_off = 0; t.part_off = 0; t.cout = cout; t.cin = cin; t.ntap = 9; t.nsplit = nsplit; t.blk_begin = 0; t.wd_off = -1; t.wtf_off = -1; t.wtd_off = -1;
     ConvTabEntry* d_t = reinterpret_cast<ConvTabEntry*>(scratch + 64);
-    float* partial = scratch + 80;
+    float* partial = scratch + kOpData;
     if (cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, st) != cudaSuccess) return LC_ERR_CUDA;
     WgradArgs w{};
     w.in = in; w.dy = dy; w.partial = partial; w.pro_scale = pro_scale; w.pro_shift = pro_shift; w.B = batch; w.nsplit = nsplit;
@@ -623,10 +697,10 @@ int lc_conv1x1s2(const float* a_, const float* b_, float* out, int batch, int ci
     cudaStream_t st = (cudaStream_t)stream;
     const long long ne = (long long)cout * cin;
     ConvTabEntry t{};
-    t.w_off = 0; t.wf_off = 0; t.wd_off = -1; t.part_off = 0; t.cout = cout; t.cin = cin; t.ntap = 1; t.nsplit = k1x1Split; t.blk_begin = 0;
+    t.w_off = 0; t.wf_off = 0; t.wd_off = -1; t.wtf_off = -1; t.wtd_off = -1; t.part_off = 0; t.cout = cout; t.cin = cin; t.ntap = 1; t.nsplit = k1x1Split; t.blk_begin = 0;
     ConvTabEntry* d_t = reinterpret_cast<ConvTabEntry*>(scratch + 64);
     if (cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, st) != cudaSuccess) return LC_ERR_CUDA;
-    float* buf = scratch + 80;
+    float* buf = scratch + kOpData;
     if (mode == 0) {          // a_ = in, b_ = W [cout][cin]
         pack_weights_kernel<<<(int)((ne + 255) / 256), 256, 0, st>>>(d_t, 1, b_, buf);
         if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;

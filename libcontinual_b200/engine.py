@@ -117,6 +117,17 @@ class ResNetEngine:
         self.reset_running_stats()
         self._off = {k: int(self.lib.lc_resnet_ws_offset(h, k)) for k in range(6)}
         self.launches = 0
+        self.precision = "fp32"
+
+    def set_precision(self, precision: str):
+        """'fp32': exact CUDA-core convolutions; 'tf32': tcgen05 tensor-core convolutions (TF32 operands, fp32 accumulate)."""
+        mode = {"fp32": 0, "tf32": 1}[precision]
+        check(self.lib.lc_resnet_set_mode(self.h, mode), "lc_resnet_set_mode")
+        self.precision = precision
+
+    def tensor_core_error(self) -> bool:
+        """True if any tensor-core completion barrier ever timed out (results would be garbage)."""
+        return bool(int(self.ws[:16].view(torch.int32)[8]) != 0)
 
     def __del__(self):
         try:

@@ -47,9 +47,10 @@ class _BackboneFn(torch.autograd.Function):
 
 
 class CifarResNet(nn.Module):
-    def __init__(self, depth: int = 32, channels: int = 3, device=None, max_batch: int = 128, num_class_cap: int = 100):
+    def __init__(self, depth: int = 32, channels: int = 3, device=None, max_batch: int = 128, num_class_cap: int = 100, precision: str = "fp32"):
         super().__init__()
         self.engine = ResNetEngine(depth=depth, max_batch=max_batch, num_class_cap=num_class_cap, device=device, in_ch=channels)
+        self.engine.set_precision(precision)
         self.out_dim = 64
         self.num_batches_pending = 0
         self._names = []
@@ -149,8 +150,10 @@ class _NoCtx:
 def cifar_resnet32(pretrained: bool = False, **kwargs):
     """Factory named in the YAML recipes (`backbone.name: cifar_resnet32`, resnet.py:760-763).  Reference kwargs
     (`num_classes`, `args`) are accepted and ignored exactly as the reference ignores them."""
-    return CifarResNet(32, device=kwargs.get("device"), max_batch=kwargs.get("max_batch", 128), num_class_cap=kwargs.get("num_classes", 100))
+    return CifarResNet(32, device=kwargs.get("device"), max_batch=kwargs.get("max_batch", 128), num_class_cap=kwargs.get("num_classes", 100),
+                       precision=kwargs.get("precision", "fp32"))
 
 
 def cifar_resnet20(pretrained: bool = False, **kwargs):
-    return CifarResNet(20, device=kwargs.get("device"), max_batch=kwargs.get("max_batch", 128), num_class_cap=kwargs.get("num_classes", 100))
+    return CifarResNet(20, device=kwargs.get("device"), max_batch=kwargs.get("max_batch", 128), num_class_cap=kwargs.get("num_classes", 100),
+                       precision=kwargs.get("precision", "fp32"))

@@ -93,8 +93,39 @@ def _bn(x: Tensor, p: Dict[str, Tensor], b: Dict[str, Tensor], prefix: str, trai
                         p[prefix + ".bias"], training=train, momentum=BN_MOMENTUM, eps=BN_EPS)
 
 
-def cifar_resnet_forward(p: Dict[str, Tensor], b: Dict[str, Tensor], x: Tensor, train: bool, depth: int = 32) -> Dict[str, object]:
-    """resnet.py:381-395 (network) and :303-316 (basic block).  Returns {'fmaps': [x1, x2, x3], 'features': [B, 64]}."""
+def _tf32_rna(t: Tensor) -> Tensor:
+    """Round fp32 to TF32 (10 mantissa bits), round-to-nearest with ties away from zero — PTX `cvt.rna.tf32.f32`."""
+    i = t.detach().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class _TF32Conv3x3(torch.autograd.Function):
+    """Arithmetic class of the product's `precision='tf32'` mode for the stride-1 3x3 convolutions: forward and data gradient
+    multiply TF32-rounded operands with fp32 accumulation (what cuDNN does for the reference's nn.Conv2d under PyTorch's default
+    `torch.backends.cudnn.allow_tf32 = True`); the weight gradient stays fp32."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return F.conv2d(_tf32_rna(x), _tf32_rna(w), None, 1, 1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = torch.nn.grad.conv2d_input(x.shape, _tf32_rna(w), _tf32_rna(dy), stride=1, padding=1)
+        dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=1, padding=1)
+        return dx, dw
+
+
+def _conv3x3(x: Tensor, w: Tensor, stride: int, conv_mode: str) -> Tensor:
+    if conv_mode == "tf32" and stride == 1 and w.shape[0] == w.shape[1]:
+        return _TF32Conv3x3.apply(x, w)
+    return F.conv2d(x, w, None, stride, 1)
+
+
+def cifar_resnet_forward(p: Dict[str, Tensor], b: Dict[str, Tensor], x: Tensor, train: bool, depth: int = 32, conv_mode: str = "fp32") -> Dict[str, object]:
+    """resnet.py:381-395 (network) and :303-316 (basic block).  Returns {'fmaps': [x1, x2, x3], 'features': [B, 64]}.
+    conv_mode 'tf32' restates the TF32 tensor-core arithmetic class for the square stride-1 3x3 layers (see _TF32Conv3x3)."""
     nblk = (depth - 2) // 6
     h = F.conv2d(x, p["conv_1_3x3.weight"], None, 1, 1)
     h = F.relu(_bn(h, p, b, "bn_1", train))
@@ -104,9 +135,9 @@ def cifar_resnet_forward(p: Dict[str, Tensor], b: Dict[str, Tensor], x: Tensor, 
             pre = f"stage_{s}.{k}"
             stride = 2 if (k == 0 and s > 1) else 1
             r = h
-            y = F.conv2d(h, p[pre + ".conv_a.weight"], None, stride, 1)
+            y = _conv3x3(h, p[pre + ".conv_a.weight"], stride, conv_mode)
             y = F.relu(_bn(y, p, b, pre + ".bn_a", train))
-            y = F.conv2d(y, p[pre + ".conv_b.weight"], None, 1, 1)
+            y = _conv3x3(y, p[pre + ".conv_b.weight"], 1, conv_mode)
             y = _bn(y, p, b, pre + ".bn_b", train)
             if (pre + ".downsample.0.weight") in p:
                 r = F.conv2d(h, p[pre + ".downsample.0.weight"], None, stride, 0)
@@ -281,9 +312,9 @@ class ResNetMethodOracle:
 
     def __init__(self, method: str, p: Dict[str, Tensor], b: Dict[str, Tensor], fc_w: Tensor, fc_b: Tensor, *,
                  init_cls: int, inc_cls: int, lamda: float = 1000.0, lr: float = 0.1, momentum: float = 0.9, wd: float = 5e-4,
-                 depth: int = 32):
+                 depth: int = 32, conv_mode: str = "fp32"):
         assert method in ("finetune", "ewc", "icarl", "lwf")
-        self.method, self.depth = method, depth
+        self.method, self.depth, self.conv_mode = method, depth, conv_mode
         self.p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
         self.b = {k: v.clone() for k, v in b.items()}
         self.fc_w = fc_w.clone().requires_grad_(True)
@@ -306,13 +337,13 @@ class ResNetMethodOracle:
         return d
 
     def logits(self, x: Tensor, train: bool) -> Tensor:
-        feat = cifar_resnet_forward(self.p, self.b, x, train, self.depth)["features"]
+        feat = cifar_resnet_forward(self.p, self.b, x, train, self.depth, self.conv_mode)["features"]
         return linear_head(feat, self.fc_w, self.fc_b)
 
     def teacher_logits(self, x: Tensor) -> Tensor:
         tp, tb, tw, tbias = self.teacher
         with torch.no_grad():
-            feat = cifar_resnet_forward(tp, tb, x, False, self.depth)["features"]
+            feat = cifar_resnet_forward(tp, tb, x, False, self.depth, self.conv_mode)["features"]
             return linear_head(feat, tw, tbias)
 
     def snapshot_teacher(self):
