@@ -187,9 +187,9 @@ def build_model(workload, device, precision="tf32"):
     return m, lo, hi
 
 
-def time_dominant_kernel(eng, reps=40):
-    """conv3x3 16->16 @32x32 (stage-1 forward/dgrad kernel) timed alone with CUDA events on its launch stream, rotating over
-    enough distinct (input, output) pairs that every launch reads cold HBM (set > L2)."""
+def time_dominant_kernel(eng, precision, reps=48):
+    """The stage-1 3x3 convolution (16->16 @32x32, the largest share of the step) timed alone with CUDA events on its launch
+    stream, rotating over enough distinct (input, output) pairs that every launch reads cold HBM (set > L2)."""
     import torch
     from libcontinual_b200._lib import check
     lib = eng.lib
@@ -199,22 +199,32 @@ def time_dominant_kernel(eng, reps=40):
     xs = [torch.randn(n, device=eng.device) for _ in range(pairs)]
     ys = [torch.empty(n, device=eng.device) for _ in range(pairs)]
     w = torch.randn(C, C, 3, 3, device=eng.device) * 0.1
-    scratch = torch.zeros(int(lib.lc_conv_scratch_floats(B, C, C, W)), device=eng.device)
     st = torch.cuda.current_stream().cuda_stream
-    check(lib.lc_conv3x3(xs[0].data_ptr(), w.data_ptr(), ys[0].data_ptr(), B, C, C, W, 1, 0, 0, None, None, None, None, None, None, None, scratch.data_ptr(), st))
-    wpack = scratch.data_ptr() + 4 * 96
+    if precision == "tf32":
+        scratch = torch.zeros(int(lib.lc_conv_tc_scratch_floats(B, C, W)), device=eng.device)
+        check(lib.lc_conv3x3_tc(xs[0].data_ptr(), w.data_ptr(), ys[0].data_ptr(), B, C, W, 0, None, None, None, None, None, None, None, scratch.data_ptr(), st))
+        wpack = scratch.data_ptr() + 4 * (96 + 2 * 9 * C * C)
+        err = scratch.data_ptr() + 4 * 8
+        launch = lambda i: check(lib.lc_conv3x3_tc_packed(xs[i].data_ptr(), wpack, ys[i].data_ptr(), B, C, W, None, None, err, st))
+        name = "conv3x3_tc_kernel<16,32> (stage-1 3x3 conv fwd/dgrad, tcgen05 kind::tf32, TMEM accumulators)"
+    else:
+        scratch = torch.zeros(int(lib.lc_conv_scratch_floats(B, C, C, W)), device=eng.device)
+        check(lib.lc_conv3x3(xs[0].data_ptr(), w.data_ptr(), ys[0].data_ptr(), B, C, C, W, 1, 0, 0, None, None, None, None, None, None, None, scratch.data_ptr(), st))
+        wpack = scratch.data_ptr() + 4 * 96
+        launch = lambda i: check(lib.lc_conv3x3_packed(xs[i].data_ptr(), wpack, ys[i].data_ptr(), B, C, C, W, 1, None, None, st))
+        name = "conv3x3_kernel<16,16,32,...> (stage-1 3x3 conv fwd/dgrad, fp32 CUDA-core)"
     for i in range(pairs):
-        check(lib.lc_conv3x3_packed(xs[i].data_ptr(), wpack, ys[i].data_ptr(), B, C, C, W, 1, None, None, st))
+        launch(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(reps):
-        check(lib.lc_conv3x3_packed(xs[i % pairs].data_ptr(), wpack, ys[i % pairs].data_ptr(), B, C, C, W, 1, None, None, st))
+        launch(i % pairs)
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
     algo_bytes = 2 * n * 4 + C * C * 9 * 4          # read X, write Y, read W   (|X|+|Y| per conv)
-    return us, algo_bytes
+    return us, algo_bytes, name
 
 
 def run_ours(args):
@@ -313,10 +323,10 @@ def run_ours(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    us, algo = time_dominant_kernel(eng)
+    us, algo, kname = time_dominant_kernel(eng, args.precision)
     achieved = algo / (us * 1e-6) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "conv3x3_kernel<16,16,32,...> (stage-1 3x3 conv fwd/dgrad, fp32 CUDA-core)", "us_per_launch": us,
+                "kernel": kname, "us_per_launch": us,
                 "algorithmic_bytes_per_launch": algo, "peak_source": peak_src}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

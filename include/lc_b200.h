@@ -123,6 +123,9 @@ long long lc_conv_tc_scratch_floats(int batch, int c, int width);
 int lc_conv3x3_tc(const float* in, const float* w_oihw, float* out, int batch, int c, int width, int mode, const float* pro_scale,
                   const float* pro_shift, const float* addend, const float* gamma, const float* beta, float* rstat, float* stat_out,
                   float* scratch, lc_stream_t stream);
+/* One launch of the tensor-core conv on pre-packed weights (lc_conv3x3_tc leaves the forward packing at scratch+96+2*9*c*c). */
+int lc_conv3x3_tc_packed(const float* in, const float* wtc, float* out, int batch, int c, int width, const float* pro_scale,
+                         const float* pro_shift, int* error_flag, lc_stream_t stream);
 int lc_conv3x3_wgrad(const float* in, const float* dy, float* dw_oihw, int batch, int cin, int cout, int width_out, int stride,
                      int in_nchw, const float* pro_scale, const float* pro_shift, float* scratch, lc_stream_t stream);
 /* 1x1 stride-2 shortcut conv: mode 0 forward (+stats as above), 1 data gradient ACCUMULATED into `out` (shape of the conv
@@ -133,7 +136,7 @@ int lc_conv1x1s2(const float* a, const float* b, float* out, int batch, int cin,
 int lc_bn_act_forward(const float* y, const float* scale, const float* shift, const float* res, const float* res_scale,
                       const float* res_shift, float* out, long long npix, int C, lc_stream_t stream);
 /* BatchNorm(+ReLU) backward. mask_mode 0: none, 1: g *= (mask_src > 0), 2: g *= (y*scale+shift > 0).  stat = {scale, shift,
- * mean, invstd}.  Writes dy, dgamma[C], dbeta[C]; g_out (nullable) receives the masked g.  scratch >= 296*2*C + 3*C + 64. */
+ * mean, invstd}.  Writes dy, dgamma[C], dbeta[C]; g_out (nullable) receives the masked g.  scratch >= 592*2*C + 3*C + 64. */
 int lc_bn_backward(const float* g, const float* mask_src, int mask_mode, const float* y, const float* stat, float* dy, float* g_out,
                    float* dgamma, float* dbeta, long long npix, int C, float* scratch, lc_stream_t stream);
 

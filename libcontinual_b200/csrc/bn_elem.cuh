@@ -118,19 +118,32 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
         *reinterpret_cast<float4*>(a.partial + ((size_t)blockIdx.x * 2 + 1) * C + c) = r2[threadIdx.x];
     }
     if (last_block_done(a.counter, gridDim.x)) {
+        // float4 column groups x slices of the partial rows: few, wide, independent loads (see bn_finalize_last_block)
         double* red = reinterpret_cast<double*>(s_red);
         constexpr int COLS = 2 * C;
-        constexpr int NSL = 256 / COLS;                // C <= 64 -> NSL >= 2
-        const int j = threadIdx.x % COLS, sl = threadIdx.x / COLS;
-        double acc = 0.0;
-        for (int p = sl; p < (int)gridDim.x; p += NSL) acc += (double)__ldcg(a.partial + (size_t)p * COLS + j);
+        constexpr int CQ = COLS / 4;
+        constexpr int NSL = 256 / CQ;
+        const int cq2 = threadIdx.x % CQ, sl = threadIdx.x / CQ;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const float4* base = reinterpret_cast<const float4*>(a.partial) + cq2;
+#pragma unroll 4
+        for (int p = sl; p < (int)gridDim.x; p += NSL) {
+            const float4 v = __ldcg(base + (size_t)p * CQ);
+            a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+        }
+        for (int k = 0; k < 4; ++k) {
+            __syncthreads();
+            red[threadIdx.x] = k == 0 ? a0 : (k == 1 ? a1 : (k == 2 ? a2 : a3));
+            __syncthreads();
+            if (threadIdx.x < CQ) {
+                double t = 0.0;
+                for (int q = 0; q < NSL; ++q) t += red[q * CQ + threadIdx.x];
+                a0 = k == 0 ? t : a0; a1 = k == 1 ? t : a1; a2 = k == 2 ? t : a2; a3 = k == 3 ? t : a3;
+            }
+        }
         __syncthreads();
-        red[threadIdx.x] = acc;
-        __syncthreads();
-        if (threadIdx.x < COLS) {
-            double t = 0.0;
-            for (int q = 0; q < NSL; ++q) t += red[q * COLS + threadIdx.x];
-            red[threadIdx.x] = t;
+        if (threadIdx.x < CQ) {
+            red[threadIdx.x * 4 + 0] = a0; red[threadIdx.x * 4 + 1] = a1; red[threadIdx.x * 4 + 2] = a2; red[threadIdx.x * 4 + 3] = a3;
         }
         __syncthreads();
         if (threadIdx.x < C) {

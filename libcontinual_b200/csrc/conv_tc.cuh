@@ -61,6 +61,19 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 16-byte asynchronous global->shared copy; src_bytes == 0 zero-fills the destination (border rows)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// one bulk (TMA, 1-D) copy global->shared, completion reported on an mbarrier as transaction bytes
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor, version 1):
 //   [0,14) start>>4   [16,30) LBO>>4 (16-byte chunk to the next chunk along K)   [32,46) SBO>>4 (8-row group to the next)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -96,6 +109,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+#ifdef LC_TC_TIMING
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define LC_TSTAMP(slot) do { if (a.timing != nullptr && threadIdx.x == 0) a.timing[(size_t)blockIdx.x * 8 + (slot)] = gtimer(); } while (0)
+#else
+#define LC_TSTAMP(slot) do { } while (0)
+#endif
+
 struct ConvTcArgs {
     const float* in;         // NHWC [B][W][W][C]
     const float* wtc;        // packed [9][C/4][COUT][4]  (tap, 16-byte K chunk, output channel, 4 input channels)
@@ -106,109 +126,115 @@ struct ConvTcArgs {
     BnStatArgs stat;         // stat.partial nullable: [ntiles][2][COUT]
     int* error_flag;         // set to 1 if the MMA completion barrier timed out
     int B;
+    unsigned long long* timing;   // debug builds (-DLC_TC_TIMING): [grid][8] globaltimer stamps per phase
 };
 
 template <int C, int W>
 struct ConvTcCfg {
     static constexpr int N = C;                    // square layers: COUT == CIN == C
+    static constexpr int T = C == 16 ? 4 : (C == 32 ? 2 : 1);   // 128-row MMA tiles per CTA (halo + weight loads amortised)
+    static constexpr int NT = 256;
     static constexpr int WP = W + 2;
     static constexpr int PP = (W + 2) * WP;        // padded positions per image
     static constexpr int HALO = WP + 1;
-    static constexpr int ROWS = 128 + 2 * HALO;
+    static constexpr int MROWS = T * 128;          // output rows per CTA
+    static constexpr int ROWS = MROWS + 2 * HALO;
     static constexpr int CH = C / 4;               // 16-byte chunks per row
+    static constexpr int RSTEP = NT / CH;          // rows advanced per staging iteration
+    static constexpr int NE = (ROWS + RSTEP - 1) / RSTEP;
     static constexpr int PLANE = ROWS * 16;        // bytes
     static constexpr int A_BYTES = CH * PLANE;
     static constexpr int BTAP = CH * N * 16;       // bytes per tap
     static constexpr int B_BYTES = 9 * BTAP;
-    static constexpr int T_FLOATS = 128 * (N + 1) + 256;               // epilogue transpose + column partials (aliases A/B)
-    static constexpr int MAIN_BYTES = A_BYTES + B_BYTES > T_FLOATS * 4 ? A_BYTES + B_BYTES : T_FLOATS * 4;
-    static constexpr int RED_FLOATS = 2 * 128 > 4 * N ? 2 * 128 : 4 * N;
-    static constexpr size_t SMEM_BYTES = MAIN_BYTES + RED_FLOATS * 4 + 64;
-    static_assert((ROWS * CH + 127) / 128 <= 32, "valid-mask width");
-    static constexpr uint32_t TMEM_COLS = N <= 32 ? 32 : 64;
+    static constexpr int ROWTAB_BYTES = ((ROWS * 4 + 15) / 16) * 16;
+    static constexpr int PART_FLOATS = 8 * 16 * 2 * 2;                 // [warp][16 cols][sum,sq] x 2 items
+    static constexpr int RED_FLOATS = 2 * NT > 4 * N ? 2 * NT : 4 * N;
+    static constexpr int OFF_B = A_BYTES;
+    static constexpr int OFF_ROWTAB = OFF_B + B_BYTES;
+    static constexpr int OFF_PART = OFF_ROWTAB + ROWTAB_BYTES;
+    static constexpr int OFF_RED = OFF_PART + PART_FLOATS * 4;
+    static constexpr int OFF_BAR = OFF_RED + RED_FLOATS * 4;
+    static constexpr size_t SMEM_BYTES = OFF_BAR + 64;
+    static constexpr uint32_t TMEM_COLS = 64;
+    static constexpr int ITEMS = T * (N / 16);     // (tile, 16-column block) epilogue work items: always 4
     static_assert(C % 8 == 0 && (C == 16 || C == 32 || C == 64), "tensor-core conv: C in {16,32,64}");
+    static_assert(NT % CH == 0 && NE <= 32 && T * N == 64 && ITEMS == 4, "tiling");
 };
 
-// 16-byte asynchronous global->shared copy; src_bytes == 0 zero-fills the destination (border rows)
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-// one bulk (TMA, 1-D) copy global->shared, completion reported on an mbarrier as transaction bytes
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-                 "r"(smem_u32(bar))
-                 : "memory");
-}
-
 template <int C, int W>
-__global__ void __launch_bounds__(128) conv3x3_tc_kernel(ConvTcArgs a) {
+__global__ void __launch_bounds__(256) conv3x3_tc_kernel(ConvTcArgs a) {
     using K = ConvTcCfg<C, W>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* sA = smem_raw;
-    unsigned char* sB = smem_raw + K::A_BYTES;
-    float* s_red = reinterpret_cast<float*>(smem_raw + K::MAIN_BYTES);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + K::MAIN_BYTES + K::RED_FLOATS * 4);     // [0] MMA done, [1] weights landed
+    unsigned char* sB = smem_raw + K::OFF_B;
+    int* s_rowsrc = reinterpret_cast<int*>(smem_raw + K::OFF_ROWTAB);     // per staged row: source pixel index, or -1 (border)
+    float* s_part = reinterpret_cast<float*>(smem_raw + K::OFF_PART);
+    float* s_red = reinterpret_cast<float*>(smem_raw + K::OFF_RED);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + K::OFF_BAR);   // [0] MMA done, [1] weights landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int total = a.B * K::PP;
-    const int q0 = (int)blockIdx.x * 128;
+    const int q0 = (int)blockIdx.x * K::MROWS;
+    LC_TSTAMP(0);
 
     if (tid == 32) {
-        mbar_init(bar, 1);
+        mbar_init(bar, K::T);
         mbar_init(bar + 1, 1);
         // weights are already in UMMA order in global memory: one bulk copy, tracked by bar[1]
         bulk_load(smem_u32(sB), a.wtc, (uint32_t)K::B_BYTES, bar + 1);
     }
     if (warp == 0) tmem_alloc(tmem_slot, K::TMEM_COLS);
 
-    // ---- stage A: rows Q in [q0-HALO, q0+128+HALO), 16-byte chunks, channel-chunk-planar.  All copies are issued before any
-    //      is waited for (cp.async), then each thread transforms the chunks it copied itself (BN+ReLU prologue, TF32 rounding).
-    constexpr int NE = (K::ROWS * K::CH + 127) / 128;
+    // ---- row table: the only place that divides.  Row r of the staged tile <-> padded position Q = q0 - HALO + r ----------
+    for (int r = tid; r < K::ROWS; r += K::NT) {
+        const int Q = q0 - K::HALO + r;
+        int src = -1;
+        if (Q >= 0 && Q < total) {
+            const int n = Q / K::PP, rem = Q - n * K::PP;
+            const int hp = rem / K::WP, wp = rem - hp * K::WP;
+            if (hp >= 1 && hp <= W && wp >= 1 && wp <= W) src = (n * W + (hp - 1)) * W + (wp - 1);
+        }
+        s_rowsrc[r] = src;
+    }
+    __syncthreads();
+    LC_TSTAMP(7);
+
+    // ---- stage A: thread -> fixed 16-byte channel chunk j, rows r0, r0+RSTEP, ...  All copies are issued before any wait ---
+    const int j = tid % K::CH, r0 = tid / K::CH;
+    const uint32_t sA_col = smem_u32(sA) + (uint32_t)j * K::PLANE;
+    const float* in_col = a.in + j * 4;
     uint32_t validmask = 0;
-    const uint32_t sA_u = smem_u32(sA);
 #pragma unroll
-    for (int i = 0; i < NE; ++i) {
-        const int e = tid + i * 128;
-        if (e < K::ROWS * K::CH) {
-            const int j = e % K::CH, r = e / K::CH;
-            const int Q = q0 - K::HALO + r;
-            const float* src = a.in;
-            uint32_t nbytes = 0;
-            if (Q >= 0 && Q < total) {
-                const int n = Q / K::PP, rem = Q % K::PP;
-                const int hp = rem / K::WP, wp = rem % K::WP;
-                if (hp >= 1 && hp <= W && wp >= 1 && wp <= W) {
-                    src = a.in + (((size_t)n * W + (hp - 1)) * W + (wp - 1)) * C + j * 4;
-                    nbytes = 16;
-                    validmask |= 1u << i;
-                }
-            }
-            cp_async16(sA_u + (uint32_t)j * K::PLANE + (uint32_t)r * 16, src, nbytes);
+    for (int i = 0; i < K::NE; ++i) {
+        const int r = r0 + i * K::RSTEP;
+        if (r < K::ROWS) {
+            const int src = s_rowsrc[r];
+            const bool ok = src >= 0;
+            cp_async16(sA_col + (uint32_t)r * 16, ok ? in_col + (size_t)src * C : a.in, ok ? 16u : 0u);
+            validmask |= (ok ? 1u : 0u) << i;
         }
     }
+    LC_TSTAMP(1);
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool pro = a.pro_scale != nullptr;
+    if (pro) { sc = ldg4(a.pro_scale + j * 4); sh = ldg4(a.pro_shift + j * 4); }
     cp_async_wait_all();
-    {
-        const bool pro = a.pro_scale != nullptr;
+    LC_TSTAMP(2);
+    // each thread transforms the chunks it copied itself: producer BN + ReLU (prologue) and round-to-nearest TF32
 #pragma unroll
-        for (int i = 0; i < NE; ++i) {
-            if (validmask & (1u << i)) {
-                const int e = tid + i * 128;
-                const int j = e % K::CH, r = e / K::CH;
-                float4* p4 = reinterpret_cast<float4*>(sA + (size_t)j * K::PLANE + (size_t)r * 16);
-                float4 v = *p4;
-                if (pro) {
-                    const float4 sc = ldg4(a.pro_scale + j * 4), sh = ldg4(a.pro_shift + j * 4);
-                    v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
-                    v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
-                    v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
-                    v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
-                }
-                v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-                *p4 = v;
+    for (int i = 0; i < K::NE; ++i) {
+        if (validmask & (1u << i)) {
+            float4* p4 = reinterpret_cast<float4*>(sA + (size_t)j * K::PLANE + (size_t)(r0 + i * K::RSTEP) * 16);
+            float4 v = *p4;
+            if (pro) {
+                v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
+                v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+                v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
+                v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
             }
+            v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+            *p4 = v;
         }
     }
     fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
@@ -216,94 +242,91 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(ConvTcArgs a) {
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    LC_TSTAMP(3);
 
-    // ---- MMA issue: one thread, 9 taps x C/8 K-steps ---------------------------------------------------------------------
-    if (tid == 0) {
-        mbar_wait(bar + 1, 0);     // weights landed (async proxy write, ordered by the mbarrier)
+    // ---- MMA issue: lane 0 of warp t issues tile t (T issuing threads -> the per-instruction issue latency of a single thread
+    //      overlaps across tiles); fully unrolled so that every descriptor is base + immediate.  All commit to bar[0] (count T).
+    if (warp < K::T && lane == 0) {
+        mbar_wait(bar + 1, 0);     // weights landed (async-proxy write, ordered by the mbarrier)
         constexpr uint32_t idesc = make_idesc_tf32(K::N);
-        const uint32_t aBase = smem_u32(sA), bBase = smem_u32(sB);
-        uint32_t acc = 0;
-#pragma unroll 1
+        const uint64_t a_hi = make_desc(0, K::PLANE, 128), b_hi = make_desc(0, K::N * 16, 128);
+        const uint32_t aBase = (smem_u32(sA) >> 4) + (uint32_t)(warp * 128 + K::HALO);     // 16-byte units: one row each
+        const uint32_t bBase = smem_u32(sB) >> 4;
+        const uint32_t dcol = tmem_base + (uint32_t)(warp * K::N);
+#pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-            const int dr = tap / 3 - 1, dc = tap % 3 - 1;
-            const uint32_t shift = (uint32_t)(K::HALO + dr * K::WP + dc);
 #pragma unroll
             for (int kc = 0; kc < C / 8; ++kc) {
-                const uint64_t ad = make_desc(aBase + (uint32_t)(2 * kc) * K::PLANE + shift * 16, K::PLANE, 128);
-                const uint64_t bd = make_desc(bBase + (uint32_t)tap * K::BTAP + (uint32_t)(2 * kc) * (K::N * 16), K::N * 16, 128);
-                mma_tf32(tmem_base, ad, bd, idesc, acc);
-                acc = 1;
+                constexpr int dummy = 0; (void)dummy;
+                const int shift = (tap / 3 - 1) * K::WP + (tap % 3 - 1);
+                const uint64_t ad = a_hi | (uint64_t)((aBase + (uint32_t)(shift + 2 * kc * (K::PLANE >> 4))) & 0x3FFF);
+                const uint64_t bd = b_hi | (uint64_t)((bBase + (uint32_t)(tap * (K::BTAP >> 4) + 2 * kc * K::N)) & 0x3FFF);
+                mma_tf32(dcol, ad, bd, idesc, (tap | kc) != 0 ? 1u : 0u);
             }
         }
         mma_commit(bar);           // implies tcgen05.fence::before_thread_sync
+        LC_TSTAMP(4);
     }
     const bool done = mbar_wait(bar, 0);
     fence_after_sync();
+    LC_TSTAMP(5);
     if (!done && tid == 0 && a.error_flag != nullptr) atomicExch(a.error_flag, 1);
 
-    // ---- epilogue ------------------------------------------------------------------------------------------------------------
-    const int m = tid;                                   // accumulator row == TMEM lane
-    const int Q = q0 + m;
-    bool valid = false;
-    size_t obase = 0;
-    if (Q < total) {
-        const int n = Q / K::PP, rem = Q % K::PP;
-        const int hp = rem / K::WP, wp = rem % K::WP;
-        valid = hp >= 1 && hp <= W && wp >= 1 && wp <= W;
-        obase = (((size_t)n * W + (hp - 1)) * W + (wp - 1)) * K::N;
-    }
-    float* sT = reinterpret_cast<float*>(smem_raw);     // [128][N+1] transpose buffer (A/B tiles are dead now)
+    // ---- epilogue: 4 work items (tile, 16-column block); warp w reads TMEM lanes 32*(w%4).., warp group w/4 takes 2 items ------
     const bool stats = a.stat.partial != nullptr;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int quarter = warp & 3, grp = warp >> 2;
 #pragma unroll
-    for (int c0 = 0; c0 < K::N; c0 += 16) {
+    for (int it = 0; it < 2; ++it) {
+        const int item = grp * 2 + it;
+        const int t = item / (K::N / 16), c0 = (item % (K::N / 16)) * 16;
+        const int m = quarter * 32 + lane;                                  // accumulator row == TMEM lane
+        const int src = s_rowsrc[K::HALO + t * 128 + m];
+        const bool valid = src >= 0;
         float v[16];
-        tmem_ld16(trow + (uint32_t)c0, v);
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * K::N + c0), v);
         if (valid) {
+            const size_t obase = (size_t)src * K::N + c0;
             if (a.addend != nullptr) {
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
-                    const float4 t = *reinterpret_cast<const float4*>(a.addend + obase + c0 + k4 * 4);
-                    v[k4 * 4] += t.x; v[k4 * 4 + 1] += t.y; v[k4 * 4 + 2] += t.z; v[k4 * 4 + 3] += t.w;
+                    const float4 x4 = *reinterpret_cast<const float4*>(a.addend + obase + k4 * 4);
+                    v[k4 * 4] += x4.x; v[k4 * 4 + 1] += x4.y; v[k4 * 4 + 2] += x4.z; v[k4 * 4 + 3] += x4.w;
                 }
             }
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)
-                *reinterpret_cast<float4*>(a.out + obase + c0 + k4 * 4) = make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
+                *reinterpret_cast<float4*>(a.out + obase + k4 * 4) = make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
         }
         if (stats) {
+            // per-warp column sums over its 32 rows (butterfly: fixed order), lane 0 publishes
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sT[m * (K::N + 1) + c0 + i] = valid ? v[i] : 0.f;
+            for (int i = 0; i < 16; ++i) {
+                const float x = valid ? v[i] : 0.f;
+                const float sm = warp_sum(x), sq = warp_sum(x * x);
+                if (lane == 0) { s_part[((warp * 2 + it) * 16 + i) * 2] = sm; s_part[((warp * 2 + it) * 16 + i) * 2 + 1] = sq; }
+            }
         }
     }
     fence_before_sync();
     __syncthreads();
+    LC_TSTAMP(6);
     if (warp == 0) tmem_dealloc(tmem_base, K::TMEM_COLS);
 
     if (stats) {
-        // column sums in fixed order: thread t -> channel t % N, row slice t / N
-        constexpr int SL = 128 / K::N;                  // slices per channel (8 / 4 / 2)
-        constexpr int RPS = 128 / SL;                   // rows per slice
-        float* sP = sT + 128 * (K::N + 1);              // [2][SL][N]
-        const int ch = tid % K::N, sl = tid / K::N;
-        float sm = 0.f, sq = 0.f;
-#pragma unroll 4
-        for (int r = sl * RPS; r < (sl + 1) * RPS; ++r) {
-            const float x = sT[r * (K::N + 1) + ch];
-            sm += x; sq = fmaf(x, x, sq);
-        }
-        sP[sl * K::N + ch] = sm;
-        sP[(SL + sl) * K::N + ch] = sq;
-        __syncthreads();
+        // channel c of tile t lives in item (t, c/16): sum the 4 warp quarters of every tile in fixed order
         if (tid < 2 * K::N) {
             const int stat = tid / K::N, c = tid % K::N;
-            float t = 0.f;
+            float tsum = 0.f;
 #pragma unroll
-            for (int s = 0; s < SL; ++s) t += sP[(stat * SL + s) * K::N + c];
-            a.stat.partial[((size_t)blockIdx.x * 2 + stat) * K::N + c] = t;
+            for (int t = 0; t < K::T; ++t) {
+                const int item = t * (K::N / 16) + c / 16, g = item >> 1, it = item & 1;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tsum += s_part[(((g * 4 + q) * 2 + it) * 16 + (c & 15)) * 2 + stat];
+            }
+            a.stat.partial[((size_t)blockIdx.x * 2 + stat) * K::N + c] = tsum;
         }
         if (last_block_done(a.stat.counter, gridDim.x)) {
-            bn_finalize_last_block<K::N, 128>(a.stat, (int)gridDim.x, (double)a.B * W * W, s_red);
+            bn_finalize_last_block<K::N, K::NT>(a.stat, (int)gridDim.x, (double)a.B * W * W, s_red);
         }
     }
 }
@@ -317,11 +340,12 @@ static inline int conv_tc_launch(const ConvTcArgs& a, cudaStream_t st) {
         attr_done = true;
     }
     const long long total = (long long)a.B * K::PP;
-    const int grid = (int)((total + 127) / 128);
-    conv3x3_tc_kernel<C, W><<<grid, 128, K::SMEM_BYTES, st>>>(a);
+    const int grid = (int)((total + K::MROWS - 1) / K::MROWS);
+    conv3x3_tc_kernel<C, W><<<grid, K::NT, K::SMEM_BYTES, st>>>(a);
     return lc_launch_status();
 }
 
+// upper bound on the CTA count (statistics partial rows) for any supported shape
 static inline long long conv_tc_tiles(int B, int W) { return ((long long)B * (W + 2) * (W + 2) + 127) / 128; }
 
 }  // namespace tc

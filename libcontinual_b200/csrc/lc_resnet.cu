@@ -19,7 +19,7 @@ namespace {
 
 constexpr float kBnEps = 1e-5f;       // nn.BatchNorm2d defaults (resnet.py:296)
 constexpr float kBnMomentum = 0.1f;
-constexpr int kBnBwdBlocks = 296;
+constexpr int kBnBwdBlocks = 592;
 
 // ---- kernel configurations for the CifarResNet layer shapes ------------------------------------------------------
 //                      CIN COUT WO PT CT RS COUT_CTA CHUNK STRIDE DILATE NCHW
@@ -112,7 +112,7 @@ int launch_conv1x1_wgrad(int cin, int cout, int wo, const float* in, const float
 
 int launch_bn_bwd(const BnBwdArgs& a0, cudaStream_t st) {
     BnBwdArgs a = a0;
-    long long blocks = (a.npix + 63) / 64;
+    long long blocks = (a.npix + 127) / 128;
     const int grid = (int)(blocks < kBnBwdBlocks ? blocks : kBnBwdBlocks);
     if (a.C == 16) bn_bwd_reduce_kernel<16><<<grid, 256, 0, st>>>(a);
     else if (a.C == 32) bn_bwd_reduce_kernel<32><<<grid, 256, 0, st>>>(a);
@@ -666,6 +666,15 @@ int lc_conv3x3_tc(const float* in, const float* w_oihw, float* out, int batch, i
     a.wtc = packed + (mode == 0 ? 2 * ne : 3 * ne);
     if (mode == 0 && stat_out) { LC_CHECK_ARG(gamma && beta); fill_stat(a.stat, gamma, beta, rstat, stat_out, c, partial, reinterpret_cast<unsigned int*>(scratch)); }
     return launch_conv3x3_tc(c, width, a, st);
+}
+// One launch of the tensor-core conv on pre-packed TF32 weights ([9][c/4][c][4], as left at scratch+96+2*9*c*c by lc_conv3x3_tc):
+// no packing, no statistics.  Used by bench.py to time the dominant kernel in isolation.
+int lc_conv3x3_tc_packed(const float* in, const float* wtc, float* out, int batch, int c, int width, const float* pro_scale,
+                         const float* pro_shift, int* error_flag, lc_stream_t stream) {
+    LC_CHECK_ARG(in && wtc && out && batch >= 1 && tc_eligible(c, c, width, 1, 3));
+    tc::ConvTcArgs a{};
+    a.in = in; a.wtc = wtc; a.out = out; a.pro_scale = pro_scale; a.pro_shift = pro_shift; a.B = batch; a.error_flag = error_flag;
+    return launch_conv3x3_tc(c, width, a, (cudaStream_t)stream);
 }
 long long lc_conv_tc_scratch_floats(int batch, int c, int width) {
     const long long ne = (long long)c * c * 9;

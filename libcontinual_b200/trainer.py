@@ -16,6 +16,7 @@ from typing import Optional
 import torch
 
 from .optim import SGD
+from .parallel import allreduce_mean_
 
 
 def train_step_eager(model, optimizer, batch):
@@ -87,7 +88,7 @@ class GraphedStep:
         self.y.copy_(y, non_blocking=non_blocking)
         self.g_main.replay()
         if self.world > 1:
-            torch.distributed.all_reduce(self.eng.grads, op=torch.distributed.ReduceOp.AVG, group=self.pg)
+            allreduce_mean_(self.eng.grads, self.pg)
             self.g_upd.replay()
         self.steps += 1
         self.model.backbone.num_batches_pending += 1

@@ -206,7 +206,7 @@ def test_bn_act_forward_backward(lib, C, wo, mask_mode):
     dy = torch.empty(B, wo, wo, C, device="cuda")
     gout = torch.empty(B, wo, wo, C, device="cuda")
     dgam, dbet = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
-    scratch = torch.zeros(296 * 2 * C + 3 * C + 128, device="cuda")
+    scratch = torch.zeros(592 * 2 * C + 3 * C + 128, device="cuda")
     mask_src = o if mask_mode == 1 else None
     assert lib.lc_bn_backward(P(dev(nhwc(gin))), P(mask_src), mask_mode, P(yd), P(stat), P(dy), P(gout), P(dgam), P(dbet), npix, C, P(scratch), st()) == 0
     close(nchw(dy), dy_ref, 1e-4, 1e-4, "bn bwd dy")
