@@ -39,8 +39,8 @@ def parse():
     ap.add_argument("--workload", default="icarl", choices=["icarl", "ewc"])
     ap.add_argument("--cpu-steps", type=int, default=12, help="timed oracle steps for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
-                    help="conv arithmetic: tf32 = tcgen05 tensor cores (cuDNN's default class for the reference), fp32 = exact CUDA-core path")
+    ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
+                    help="conv arithmetic: tc = tcgen05 tensor cores (TF32 fwd/dgrad, BF16-operand wgrad, fp32 accumulate), fp32 = exact CUDA-core path")
     return ap.parse_args()
 
 
@@ -160,7 +160,7 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_model(workload, device, precision="tf32"):
+def build_model(workload, device, precision="tc"):
     import numpy as np
     import torch
     import libcontinual_b200.model as M
@@ -200,7 +200,7 @@ def time_dominant_kernel(eng, precision, reps=48):
     ys = [torch.empty(n, device=eng.device) for _ in range(pairs)]
     w = torch.randn(C, C, 3, 3, device=eng.device) * 0.1
     st = torch.cuda.current_stream().cuda_stream
-    if precision == "tf32":
+    if precision == "tc":
         scratch = torch.zeros(int(lib.lc_conv_tc_scratch_floats(B, C, W)), device=eng.device)
         check(lib.lc_conv3x3_tc(xs[0].data_ptr(), w.data_ptr(), ys[0].data_ptr(), B, C, W, 0, None, None, None, None, None, None, None, scratch.data_ptr(), st))
         wpack = scratch.data_ptr() + 4 * (96 + 2 * 9 * C * C)
@@ -334,11 +334,11 @@ def run_ours(args):
         cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "ms_per_step": ms,
                "sample": f"{args.cpu_steps} full training steps of batch {BATCH} after 1 warm-up (oracle/port.py, PyTorch CPU fp32, {cores} threads)"}
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision.replace("fp32", "f32"), "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.precision == "tc" else "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.workload), "global_batch": BATCH * world, "per_gpu_batch": BATCH, "parallelism": f"dp{world}",
                        "l2": "per-step working set ~330 MB of fp32 activations + 8 rotating input batches > 126 MB L2 (no explicit flush)",
-                       "precision": ("fp32 storage; 3x3 stride-1 conv fwd/dgrad on tcgen05 TF32 (fp32 accumulate in TMEM); everything else fp32 FMA"
-                                     if args.precision == "tf32" else "fp32 storage, fp32 FMA (exact mode)"),
+                       "precision": ("fp32 storage; 3x3 stride-1 convs on tcgen05: TF32 operands fwd/dgrad, BF16 operands wgrad, fp32 accumulate in TMEM; "
+                                      "everything else fp32 FMA" if args.precision == "tc" else "fp32 storage, fp32 FMA (exact mode)"),
                        "final_loss": final_loss, "tensor_core_error": eng.tensor_core_error()},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

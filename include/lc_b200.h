@@ -40,8 +40,8 @@ typedef struct lc_resnet lc_resnet;
 int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** out);
 void lc_resnet_destroy(lc_resnet* net);
 /* Arithmetic mode of the 3x3 stride-1 convolutions (forward + data gradient): 0 = exact fp32 FMA on CUDA cores (default),
- * 1 = TF32 on the tcgen05 tensor cores, fp32 accumulation in TMEM (the arithmetic class cuDNN uses for the reference's convs
- * under PyTorch's default allow_tf32).  workspace word 8 (int) is set to 1 if a tensor-core barrier ever timed out. */
+ * 1 = tcgen05 tensor cores, fp32 accumulation in TMEM: TF32 operands for forward / data gradient (the arithmetic class cuDNN uses
+ * for the reference's convs under PyTorch's default allow_tf32), BF16 operands for the weight gradient.  workspace word 8 (int) is set to 1 if a tensor-core barrier ever timed out. */
 int lc_resnet_set_mode(lc_resnet* net, int mode);
 int lc_resnet_get_mode(const lc_resnet* net);
 long long lc_resnet_param_count(const lc_resnet* net);
@@ -128,6 +128,9 @@ int lc_conv3x3_tc_packed(const float* in, const float* wtc, float* out, int batc
                          const float* pro_shift, int* error_flag, lc_stream_t stream);
 int lc_conv3x3_wgrad(const float* in, const float* dy, float* dw_oihw, int batch, int cin, int cout, int width_out, int stride,
                      int in_nchw, const float* pro_scale, const float* pro_shift, float* scratch, lc_stream_t stream);
+/* tcgen05 (kind::tf32, MN-major operands, TMEM accumulators) weight gradient for (c, width) in {(16,32),(32,16),(64,8)}. */
+int lc_conv3x3_wgrad_tc(const float* in, const float* dy, float* dw_oihw, int batch, int c, int width, const float* pro_scale,
+                        const float* pro_shift, float* scratch, lc_stream_t stream);
 /* 1x1 stride-2 shortcut conv: mode 0 forward (+stats as above), 1 data gradient ACCUMULATED into `out` (shape of the conv
  * input), 2 weight gradient into `out` ([cout][cin]). */
 int lc_conv1x1s2(const float* a, const float* b, float* out, int batch, int cin, int cout, int width_out, int mode, const float* gamma,

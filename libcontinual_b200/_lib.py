@@ -50,6 +50,7 @@ SIGNATURES = {
     "lc_conv3x3_tc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P]),
     "lc_conv3x3_tc_packed": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P]),
     "lc_conv3x3_wgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "lc_conv3x3_wgrad_tc": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P]),
     "lc_conv1x1s2": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "lc_bn_act_forward": (c_int, [P, P, P, P, P, P, P, c_longlong, c_int, P]),
     "lc_bn_backward": (c_int, [P, P, c_int, P, P, P, P, P, P, c_longlong, c_int, P, P]),

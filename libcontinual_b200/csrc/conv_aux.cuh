@@ -178,7 +178,7 @@ struct ConvTabEntry {
     long long wtd_off;    // tensor-core dgrad packing    [8-tap][co/4][ci][co%4]
     int cout, cin, ntap, nsplit;
     int blk_begin;        // first block of this layer in the table kernels
-    int pad;
+    int nsplit_tc;        // split count used by the tensor-core weight-gradient kernel (<= nsplit)
 };
 
 __device__ __forceinline__ int tab_find_layer(const ConvTabEntry* tab, int nlayers, int blk) {
@@ -206,17 +206,33 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const ConvTabEntry* t
     }
 }
 
-// grad[w_off + e] = sum_{s < nsplit} partial[part_off + s*n + e]   (fixed order => deterministic)
-__global__ void __launch_bounds__(256) wgrad_reduce_all_kernel(const ConvTabEntry* tab, int nlayers, const float* partial, float* grad) {
+// grad[w_off + e] = sum_{s < nsplit} partial[part_off + s*n + e]   (fixed order => deterministic).
+// tc_mode != 0: layers on the tensor-core path wrote their partials as [tap][ci][co]; read them in that (coalesced) order and
+// scatter the sums to OIHW.
+__global__ void __launch_bounds__(256) wgrad_reduce_all_kernel(const ConvTabEntry* tab, int nlayers, const float* partial, float* grad, int tc_mode) {
     const int l = tab_find_layer(tab, nlayers, blockIdx.x);
     const ConvTabEntry t = tab[l];
     const int n = t.cout * t.cin * t.ntap;
     const int e = (blockIdx.x - t.blk_begin) * 256 + threadIdx.x;
     if (e >= n) return;
     const float* p = partial + t.part_off + e;
-    float acc = 0.f;
-    for (int s = 0; s < t.nsplit; ++s) acc += __ldg(p + (size_t)s * n);
-    grad[t.w_off + e] = acc;
+    const bool tc_layer = tc_mode != 0 && t.wtf_off >= 0;
+    const int ns = tc_layer ? t.nsplit_tc : t.nsplit;
+    // 8 independent partial sums (8 loads in flight), combined in a fixed order
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int s = 0;
+    for (; s + 8 <= ns; s += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += __ldg(p + (size_t)(s + k) * n);
+    }
+    for (int k = 0; s < ns; ++s, ++k) a[k] += __ldg(p + (size_t)s * n);
+    const float acc = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    int out = e;
+    if (tc_layer) {
+        const int co = e % t.cout, ci = (e / t.cout) % t.cin, tap = e / (t.cout * t.cin);
+        out = (co * t.cin + ci) * t.ntap + tap;
+    }
+    grad[t.w_off + out] = acc;
 }
 
 }  // namespace lc

@@ -5,6 +5,7 @@
 #include "conv_aux.cuh"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
+#include "wgrad_tc.cuh"
 #include "flat_ops.cuh"
 #include "head_loss.cuh"
 
@@ -83,7 +84,14 @@ int launch_conv3x3_tc(int c, int wo, const tc::ConvTcArgs& a, cudaStream_t st) {
 int wgrad_nsplit(int cin, int cout) {
     if (cout == 16) return 256;
     if (cout == 32) return 128;
-    return 32;      // cout 64 (x CIN_SPLIT CTAs)
+    return 64;      // cout 64 (CUDA-core kernel: x CIN_SPLIT CTAs)
+}
+int wgrad_nsplit_tc(int c) { return c == 64 ? 50 : (c == 32 ? 148 : 296); }
+int launch_wgrad3x3_tc(int c, int wo, const tc::WgradTcArgs& a, int nsplit, cudaStream_t st) {
+    if (c == 16 && wo == 32) return tc::wgrad_tc_launch<16, 32>(a, nsplit, st);
+    if (c == 32 && wo == 16) return tc::wgrad_tc_launch<32, 16>(a, nsplit, st);
+    if (c == 64 && wo == 8) return tc::wgrad_tc_launch<64, 8>(a, nsplit, st);
+    return LC_ERR_INVALID;
 }
 
 int launch_conv1x1_fwd(int cin, int cout, int wo, const Conv1x1Args& a, cudaStream_t st) {
@@ -230,7 +238,7 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
         if (c.ksize == 3) { c.wd_off = pk; pk += ne; } else c.wd_off = -1;
         if (tc_eligible(c.cin, c.cout, c.wo, c.stride, c.ksize)) { c.wtf_off = pk; pk += ne; c.wtd_off = pk; pk += ne; } else { c.wtf_off = c.wtd_off = -1; }
         c.nsplit = c.ksize == 3 ? wgrad_nsplit(c.cin, c.cout) : k1x1Split;
-        c.part_off = wp; wp += ne * c.nsplit;
+        c.part_off = wp; wp += ne * std::max(c.nsplit, c.wtf_off >= 0 ? wgrad_nsplit_tc(c.cout) : 0);
     }
     n->packed_floats = pk; n->wpart_floats = wp;
     n->off_packed = take(pk);
@@ -265,6 +273,7 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
         ConvTabEntry t{};
         t.w_off = c.w_off; t.wf_off = c.wf_off; t.wd_off = c.wd_off; t.part_off = c.part_off; t.wtf_off = c.wtf_off; t.wtd_off = c.wtd_off;
         t.cout = c.cout; t.cin = c.cin; t.ntap = c.ksize * c.ksize; t.nsplit = c.nsplit; t.blk_begin = blk;
+        t.nsplit_tc = c.wtf_off >= 0 ? wgrad_nsplit_tc(c.cout) : c.nsplit;
         blk += (c.cout * c.cin * t.ntap + 255) / 256;
         tab.push_back(t);
     }
@@ -457,10 +466,17 @@ int lc_resnet_backward(lc_resnet* n, const float* x, int batch, const float* par
             LC_TRY(launch_conv1x1_wgrad(cd.cin, cd.cout, cd.wo, blk_in, T3, wpart + cd.part_off, batch, st));
         }
         {   // conv_b: weight gradient (input = relu(bn_a(y1)) recomputed on load) and data gradient
-            WgradArgs w{};
-            w.in = ws + ca.y_off; w.dy = T1; w.partial = wpart + cb.part_off; w.B = batch; w.nsplit = cb.nsplit;
-            w.pro_scale = ws + ca.aff_off; w.pro_shift = ws + ca.aff_off + ca.cout;
-            LC_TRY(launch_wgrad3x3(cb.cin, cb.cout, cb.wo, 1, false, w, st));
+            if (n->mode == 1 && cb.wtf_off >= 0) {
+                tc::WgradTcArgs w{};
+                w.in = ws + ca.y_off; w.dy = T1; w.partial = wpart + cb.part_off; w.B = batch; w.error_flag = err_flag;
+                w.pro_scale = ws + ca.aff_off; w.pro_shift = ws + ca.aff_off + ca.cout;
+                LC_TRY(launch_wgrad3x3_tc(cb.cin, cb.wo, w, wgrad_nsplit_tc(cb.cin), st));
+            } else {
+                WgradArgs w{};
+                w.in = ws + ca.y_off; w.dy = T1; w.partial = wpart + cb.part_off; w.B = batch; w.nsplit = cb.nsplit;
+                w.pro_scale = ws + ca.aff_off; w.pro_shift = ws + ca.aff_off + ca.cout;
+                LC_TRY(launch_wgrad3x3(cb.cin, cb.cout, cb.wo, 1, false, w, st));
+            }
             if (n->mode == 1 && cb.wtd_off >= 0) {
                 tc::ConvTcArgs a{};
                 a.in = T1; a.wtc = packed + cb.wtd_off; a.out = T2; a.B = batch; a.error_flag = err_flag;
@@ -474,9 +490,15 @@ int lc_resnet_backward(lc_resnet* n, const float* x, int batch, const float* par
         // bn_a (+ ReLU): T1 = d(y1)
         LC_TRY(bn_bwd(ca, T2, nullptr, LC_MASK_FROM_BN, T1, nullptr)); ++launches;
         {
-            WgradArgs w{};
-            w.in = blk_in; w.dy = T1; w.partial = wpart + ca.part_off; w.B = batch; w.nsplit = ca.nsplit;
-            LC_TRY(launch_wgrad3x3(ca.cin, ca.cout, ca.wo, ca.stride, false, w, st));
+            if (n->mode == 1 && ca.wtf_off >= 0) {
+                tc::WgradTcArgs w{};
+                w.in = blk_in; w.dy = T1; w.partial = wpart + ca.part_off; w.B = batch; w.error_flag = err_flag;
+                LC_TRY(launch_wgrad3x3_tc(ca.cin, ca.wo, w, wgrad_nsplit_tc(ca.cin), st));
+            } else {
+                WgradArgs w{};
+                w.in = blk_in; w.dy = T1; w.partial = wpart + ca.part_off; w.B = batch; w.nsplit = ca.nsplit;
+                LC_TRY(launch_wgrad3x3(ca.cin, ca.cout, ca.wo, ca.stride, false, w, st));
+            }
             Conv3x3Args a{};
             a.in = T1; a.wpack = packed + ca.wd_off; a.B = batch;
             if (ca.stride == 1 && n->mode == 1 && ca.wtd_off >= 0) {
@@ -503,7 +525,7 @@ int lc_resnet_backward(lc_resnet* n, const float* x, int batch, const float* par
         w.in = x; w.dy = T1; w.partial = wpart + c.part_off; w.B = batch; w.nsplit = c.nsplit;
         LC_TRY(launch_wgrad3x3(c.cin, c.cout, c.wo, 1, true, w, st));
     }
-    wgrad_reduce_all_kernel<<<n->tab_blocks, 256, 0, st>>>(n->d_tab, (int)n->convs.size(), wpart, grads);
+    wgrad_reduce_all_kernel<<<n->tab_blocks, 256, 0, st>>>(n->d_tab, (int)n->convs.size(), wpart, grads, n->mode);
     LC_TRY(lc_launch_status());
     n->launches_bwd = launches;
     return LC_OK;
@@ -696,7 +718,29 @@ int lc_conv3x3_wgrad(const float* in, const float* dy, float* dw, int batch, int
     w.in = in; w.dy = dy; w.partial = partial; w.pro_scale = pro_scale; w.pro_shift = pro_shift; w.B = batch; w.nsplit = nsplit;
     int e = launch_wgrad3x3(cin, cout, width_out, stride, in_nchw != 0, w, st);
     if (e != LC_OK) return e;
-    wgrad_reduce_all_kernel<<<(int)((ne + 255) / 256), 256, 0, st>>>(d_t, 1, partial, dw);
+    wgrad_reduce_all_kernel<<<(int)((ne + 255) / 256), 256, 0, st>>>(d_t, 1, partial, dw, 0);
+    return lc_launch_status();
+}
+
+// Tensor-core (tcgen05 kind::tf32, MN-major operands) weight gradient of the square stride-1 layers; same contract as
+// lc_conv3x3_wgrad.  scratch word 8 (int) receives 1 if an MMA barrier timed out.
+int lc_conv3x3_wgrad_tc(const float* in, const float* dy, float* dw, int batch, int c, int width, const float* pro_scale,
+                        const float* pro_shift, float* scratch, lc_stream_t stream) {
+    LC_CHECK_ARG(in && dy && dw && scratch && batch >= 1 && ((uintptr_t)scratch % 16 == 0) && tc_eligible(c, c, width, 1, 3));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long ne = (long long)c * c * 9;
+    const int nsplit = wgrad_nsplit_tc(c);
+    ConvTabEntry t{};
+    t.w_off = 0; t.part_off = 0; t.cout = c; t.cin = c; t.ntap = 9; t.nsplit = nsplit; t.nsplit_tc = nsplit; t.blk_begin = 0; t.wd_off = -1; t.wtf_off = 0; t.wtd_off = -1;
+    ConvTabEntry* d_t = reinterpret_cast<ConvTabEntry*>(scratch + 64);
+    float* partial = scratch + kOpData;
+    if (cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, st) != cudaSuccess) return LC_ERR_CUDA;
+    tc::WgradTcArgs w{};
+    w.in = in; w.dy = dy; w.partial = partial; w.pro_scale = pro_scale; w.pro_shift = pro_shift; w.B = batch;
+    w.error_flag = reinterpret_cast<int*>(scratch) + 8;
+    int e = launch_wgrad3x3_tc(c, width, w, nsplit, st);
+    if (e != LC_OK) return e;
+    wgrad_reduce_all_kernel<<<(int)((ne + 255) / 256), 256, 0, st>>>(d_t, 1, partial, dw, 1);
     return lc_launch_status();
 }
 
@@ -723,7 +767,7 @@ int lc_conv1x1s2(const float* a_, const float* b_, float* out, int batch, int ci
     // mode 2: a_ = in, b_ = dy -> out = dW
     int e = launch_conv1x1_wgrad(cin, cout, width_out, a_, b_, buf, batch, st);
     if (e != LC_OK) return e;
-    wgrad_reduce_all_kernel<<<(int)((ne + 255) / 256), 256, 0, st>>>(d_t, 1, buf, out);
+    wgrad_reduce_all_kernel<<<(int)((ne + 255) / 256), 256, 0, st>>>(d_t, 1, buf, out, 0);
     return lc_launch_status();
 }
 

@@ -120,8 +120,9 @@ class ResNetEngine:
         self.precision = "fp32"
 
     def set_precision(self, precision: str):
-        """'fp32': exact CUDA-core convolutions; 'tf32': tcgen05 tensor-core convolutions (TF32 operands, fp32 accumulate)."""
-        mode = {"fp32": 0, "tf32": 1}[precision]
+        """'fp32': exact CUDA-core convolutions; 'tc': tcgen05 tensor-core convolutions for the stride-1 3x3 layers (TF32 operands
+        for forward / data gradient, BF16 operands for the weight gradient, fp32 accumulation in TMEM)."""
+        mode = {"fp32": 0, "tc": 1}[precision]
         check(self.lib.lc_resnet_set_mode(self.h, mode), "lc_resnet_set_mode")
         self.precision = precision
 

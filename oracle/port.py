@@ -100,9 +100,10 @@ def _tf32_rna(t: Tensor) -> Tensor:
 
 
 class _TF32Conv3x3(torch.autograd.Function):
-    """Arithmetic class of the product's `precision='tf32'` mode for the stride-1 3x3 convolutions: forward and data gradient
-    multiply TF32-rounded operands with fp32 accumulation (what cuDNN does for the reference's nn.Conv2d under PyTorch's default
-    `torch.backends.cudnn.allow_tf32 = True`); the weight gradient stays fp32."""
+    """Arithmetic class of the product's tensor-core mode (`precision='tc'`) for the stride-1 3x3 convolutions: forward and data
+    gradient multiply TF32-rounded operands (cvt.rna) with fp32 accumulation — what cuDNN does for the reference's nn.Conv2d under
+    PyTorch's default `torch.backends.cudnn.allow_tf32 = True`; the weight gradient multiplies BF16-rounded operands
+    (round-to-nearest-even) with fp32 accumulation."""
 
     @staticmethod
     def forward(ctx, x, w):
@@ -113,19 +114,19 @@ class _TF32Conv3x3(torch.autograd.Function):
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         dx = torch.nn.grad.conv2d_input(x.shape, _tf32_rna(w), _tf32_rna(dy), stride=1, padding=1)
-        dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=1, padding=1)
+        dw = torch.nn.grad.conv2d_weight(x.bfloat16().float(), w.shape, dy.bfloat16().float(), stride=1, padding=1)
         return dx, dw
 
 
 def _conv3x3(x: Tensor, w: Tensor, stride: int, conv_mode: str) -> Tensor:
-    if conv_mode == "tf32" and stride == 1 and w.shape[0] == w.shape[1]:
+    if conv_mode == "tc" and stride == 1 and w.shape[0] == w.shape[1]:
         return _TF32Conv3x3.apply(x, w)
     return F.conv2d(x, w, None, stride, 1)
 
 
 def cifar_resnet_forward(p: Dict[str, Tensor], b: Dict[str, Tensor], x: Tensor, train: bool, depth: int = 32, conv_mode: str = "fp32") -> Dict[str, object]:
     """resnet.py:381-395 (network) and :303-316 (basic block).  Returns {'fmaps': [x1, x2, x3], 'features': [B, 64]}.
-    conv_mode 'tf32' restates the TF32 tensor-core arithmetic class for the square stride-1 3x3 layers (see _TF32Conv3x3)."""
+    conv_mode 'tc' restates the tensor-core arithmetic class for the square stride-1 3x3 layers (see _TF32Conv3x3)."""
     nblk = (depth - 2) // 6
     h = F.conv2d(x, p["conv_1_3x3.weight"], None, 1, 1)
     h = F.relu(_bn(h, p, b, "bn_1", train))

@@ -289,8 +289,8 @@ def test_full_batch_128_properties():
 
 
 def test_tf32_tensor_core_mode_vs_oracle():
-    """precision='tf32': tcgen05 convolutions (TF32 operands, fp32 accumulation), compared with the oracle restating the SAME
-    arithmetic class (conv_mode='tf32': operands rounded to TF32 by cvt.rna semantics, fp32 accumulate) and with the fp32 oracle.
+    """precision='tc': tcgen05 convolutions (TF32 operands for forward / data gradient, BF16 operands for the weight gradient, fp32
+    accumulation), compared with the oracle restating the SAME arithmetic class (conv_mode='tc') and with the fp32 oracle.
 
     Rounding to TF32 is discontinuous: an fp32-ulp difference ahead of a rounding point moves that operand by a whole TF32 ulp
     (2^-11), so two faithful TF32 implementations that differ only in summation order drift apart.  The tolerance is therefore
@@ -300,7 +300,7 @@ def test_tf32_tensor_core_mode_vs_oracle():
     held to 1e-4 above).  Absolute bounds from SURVEY.md §8c against the fp32 oracle: loss |d| <= 1e-2, features rel-L2 <= 2e-2."""
     import libcontinual_b200.model as M
     p, b, fc_w, fc_b = synth_resnet_state(101, 20)
-    bb = M.cifar_resnet32(max_batch=B, precision="tf32")
+    bb = M.cifar_resnet32(max_batch=B, precision="tc")
     bb.load_state_dict({**p, **b}, strict=True)
     m = M.EWC(bb, 64, 100, device=torch.device("cuda"), init_cls_num=10, inc_cls_num=10, lamda=1000.0)
     m.before_task(0, None, None, None)
@@ -319,10 +319,10 @@ def test_tf32_tensor_core_mode_vs_oracle():
         return pr, float(l), g, f
 
     _, l32, _, f32 = oracle(p, "fp32")
-    ptf, ltf, gtf, ftf = oracle(p, "tf32")
+    ptf, ltf, gtf, ftf = oracle(p, "tc")
     rng = np.random.default_rng(5)
     p_eps = {k: v * torch.from_numpy(1 + 1e-7 * rng.standard_normal(tuple(v.shape))).float() for k, v in p.items()}
-    _, l_eps, g_eps, f_eps = oracle(p_eps, "tf32")
+    _, l_eps, g_eps, f_eps = oracle(p_eps, "tc")
     self_loss, self_feat = abs(ltf - l_eps), rel_l2(f_eps, ftf)
     self_grad = {n: rel_l2(g_eps[n], gtf[n]) for n in gtf}
     errs = {n: rel_l2(got[n], gtf[n]) for n in gtf}

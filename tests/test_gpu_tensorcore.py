@@ -70,3 +70,32 @@ def test_conv3x3_tc_dgrad_with_addend(lib, c, w):
     ref = dx_ref + addend
     err = (nchw(dx).cpu() - ref).abs().max().item()
     assert err <= 4e-3 * dx_ref.abs().max().item(), err
+
+
+@pytest.mark.parametrize("c,w", [(16, 32), (32, 16), (64, 8)])
+@pytest.mark.parametrize("B", [2, 9])
+def test_conv3x3_tc_wgrad(lib, c, w, B):
+    g = torch.Generator().manual_seed(7 * c + B)
+    x = torch.randn(B, c, w, w, generator=g)
+    dy = torch.randn(B, c, w, w, generator=g)
+    ps, psh = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.3
+    for prologue in (False, True):
+        xin = F.relu(x * ps.view(1, -1, 1, 1) + psh.view(1, -1, 1, 1)) if prologue else x
+        ref = torch.nn.grad.conv2d_weight(xin, (c, c, 3, 3), dy, stride=1, padding=1)
+        ref_tf = torch.nn.grad.conv2d_weight(xin.bfloat16().float(), (c, c, 3, 3), dy.bfloat16().float(), stride=1, padding=1)
+        dw = torch.full((c, c, 3, 3), float("nan"), device="cuda")
+        scratch = torch.zeros(int(lib.lc_conv_scratch_floats(B, c, c, w)), device="cuda")
+        rc = lib.lc_conv3x3_wgrad_tc(P(dev(nhwc(x))), P(dev(nhwc(dy))), P(dw), B, c, w, P(dev(ps)) if prologue else None, P(dev(psh)) if prologue else None,
+                                     P(scratch), st())
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert int(scratch.view(torch.int32)[8]) == 0, "tensor-core barrier timed out"
+        got = dw.cpu()
+        assert torch.isfinite(got).all()
+        scale = ref.abs().max().item()
+        err, err_tf = (got - ref).abs().max().item(), (got - ref_tf).abs().max().item()
+        print(f"wgrad c={c} w={w} B={B} pro={prologue}: max|err| {err:.3e} (ref max {scale:.2f}); vs bf16-rounded operands {err_tf:.3e}")
+        # BF16 operands (8 mantissa bits, round-to-nearest-even), fp32 accumulation: |err| <= 1e-2 * max|ref|; against an fp32
+        # contraction of the same BF16-rounded operands only the summation order differs
+        assert err <= 1e-2 * scale, (err, scale)
+        assert err_tf <= 2e-4 * scale, (err_tf, scale)
