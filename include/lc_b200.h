@@ -102,6 +102,35 @@ int lc_adam(float* p, const float* g, float* m, float* v, long long n, const flo
 int lc_clip_grad_norm(float* g, long long n, float max_norm, float* scratch, float* norm_out, lc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------------
+ * Continual-learning specific kernels.
+ * lc_cosine_head_forward : `CosineLinear` / `SplitCosineLinear` (resnet.py:418-463): scores = normalize(feat) . normalize(W)^T,
+ *                          logits = sigma * scores.  inv_norm: [batch + ncls] floats (kept for the backward).
+ * lc_cosine_head_backward: autograd of the above given gscores = d(loss)/d(scores) (caller folds sigma: sigma*dlogits + dscores).
+ * lc_lucir_loss          : `LUCIR.observe` task>0 (lucir.py:184-205): cur_lamda * CosineEmbeddingLoss(feat, ref_feat, +1) + CE(logits, y) +
+ *                          lw_mr * MarginRankingLoss(gt score, top-K novel scores of old-class samples, margin); gradients w.r.t. logits,
+ *                          pre-scale scores and features; argmax / #correct.  scal: [0] loss [1] #correct [2] ce [3] less-forget [5] mr.
+ * lc_l2p_select          : `L2P.forward` (prompt.py:369-406): cosine similarity, per-sample top-k, batch-wide majority vote (ties: count
+ *                          desc then id asc), pull-constraint `reduce_sim` and its gradient w.r.t. prompt_key.  scratch >= dim floats.
+ * lc_l2p_gather          : batched_prompt[b][t*len + l][:] = prompt[ids[t]][l][:].
+ * lc_gpm_project         : grad <- grad - (grad.view(rows, dim) @ proj)  (gpm.py:78-81; proj = U U^T, [dim][dim]), in place.
+ * lc_lora_merge_qkv      : W' = cat(W_q, W_k + B_k A_k, W_v + B_v A_v)  (transformer.py:246-254).  lc_lora_bgrad: dB = dW' A^T.
+ * ------------------------------------------------------------------------------------------------------------------- */
+int lc_cosine_head_forward(const float* feat, const float* W, const float* sigma, int batch, int ncls, int feat_dim, float* inv_norm,
+                           float* scores, float* logits, int ld, lc_stream_t stream);
+int lc_cosine_head_backward(const float* gscores, int ld, const float* feat, const float* W, const float* inv_norm, int batch, int ncls,
+                            int feat_dim, float* dfeat, float* dW, lc_stream_t stream);
+int lc_lucir_loss(const float* logits, const float* scores, int ld, const float* feat, const float* ref_feat, int feat_dim, const int64_t* y,
+                  int batch, int ncls, int num_old, int K, float cur_lamda, float margin, float lw_mr, float* dlogits, float* dscores,
+                  float* dfeat, int64_t* pred, float* scal, lc_stream_t stream);
+int lc_l2p_select(const float* query, const float* key, int batch, int pool, int dim, int top_k, float* sim, int64_t* ids, int* hist,
+                  float* reduce_sim, float* dkey, float* scratch, lc_stream_t stream);
+int lc_l2p_gather(const float* prompt, const int64_t* ids, float* out, int batch, int top_k, int length, int dim, lc_stream_t stream);
+int lc_gpm_project(float* grad, const float* proj, int rows, int dim, lc_stream_t stream);
+int lc_lora_merge_qkv(const float* qkv_w, const float* A_k, const float* B_k, const float* A_v, const float* B_v, float* out, int dim, int rank,
+                      lc_stream_t stream);
+int lc_lora_bgrad(const float* dW, const float* A, float* dB, int dim, int rank, lc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------------
  * Per-kernel entry points (unit-tested individually; the network-level calls above are compositions of these).
  * conv3x3: NHWC fp32, pad 1.  `w_oihw` is the native nn.Conv2d weight; mode 0 = forward, 1 = data gradient (input is dy).
  * Supported (cin, cout, width_out, stride): the CifarResNet layer shapes.  `in_nchw` != 0: input is NCHW (network stem).

@@ -43,6 +43,14 @@ SIGNATURES = {
     "lc_sgd_momentum": (c_int, [P, P, P, c_longlong, P, P]),
     "lc_adam": (c_int, [P, P, P, P, c_longlong, P, P]),
     "lc_clip_grad_norm": (c_int, [P, c_longlong, c_float, P, P, P]),
+    "lc_cosine_head_forward": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, c_int, P]),
+    "lc_cosine_head_backward": (c_int, [P, c_int, P, P, P, c_int, c_int, c_int, P, P, P]),
+    "lc_lucir_loss": (c_int, [P, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P, P, P, P]),
+    "lc_l2p_select": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "lc_l2p_gather": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+    "lc_gpm_project": (c_int, [P, P, c_int, c_int, P]),
+    "lc_lora_merge_qkv": (c_int, [P, P, P, P, P, P, c_int, c_int, P]),
+    "lc_lora_bgrad": (c_int, [P, P, P, c_int, c_int, P]),
     "lc_conv_scratch_floats": (c_longlong, [c_int, c_int, c_int, c_int]),
     "lc_conv3x3": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P]),
     "lc_conv3x3_packed": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),

@@ -1,0 +1,84 @@
+// C entry points of the continual-learning specific kernels (cl_ops.cuh).  See include/lc_b200.h.
+#include "../../include/lc_b200.h"
+#include "cl_ops.cuh"
+
+using namespace lc;
+
+extern "C" {
+
+int lc_cosine_head_forward(const float* feat, const float* W, const float* sigma, int batch, int ncls, int feat_dim, float* inv_norm,
+                           float* scores, float* logits, int ld, lc_stream_t stream) {
+    LC_CHECK_ARG(feat && W && inv_norm && scores && logits && batch >= 1 && ncls >= 1 && ld >= ncls && feat_dim == 64);
+    cudaStream_t st = (cudaStream_t)stream;
+    row_inv_norm_kernel<64><<<(batch + ncls + 3) / 4, 128, 0, st>>>(feat, batch, W, ncls, inv_norm);
+    if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
+    cosine_head_fwd_kernel<64><<<(batch * ncls + 127) / 128, 128, 0, st>>>(feat, W, inv_norm, sigma, batch, ncls, scores, logits, ld);
+    return lc_launch_status();
+}
+
+int lc_cosine_head_backward(const float* gscores, int ld, const float* feat, const float* W, const float* inv_norm, int batch, int ncls,
+                            int feat_dim, float* dfeat, float* dW, lc_stream_t stream) {
+    LC_CHECK_ARG(gscores && feat && W && inv_norm && dfeat && dW && batch >= 1 && ncls >= 1 && feat_dim == 64);
+    cosine_head_bwd_kernel<64><<<batch + ncls, 64, 0, (cudaStream_t)stream>>>(gscores, ld, feat, W, inv_norm, batch, ncls, dfeat, dW);
+    return lc_launch_status();
+}
+
+int lc_lucir_loss(const float* logits, const float* scores, int ld, const float* feat, const float* ref_feat, int feat_dim, const int64_t* y,
+                  int batch, int ncls, int num_old, int K, float cur_lamda, float margin, float lw_mr, float* dlogits, float* dscores,
+                  float* dfeat, int64_t* pred, float* scal, lc_stream_t stream) {
+    LC_CHECK_ARG(logits && scores && feat && ref_feat && y && dlogits && dscores && dfeat && pred && scal);
+    LC_CHECK_ARG(batch >= 1 && ncls >= 1 && ld >= ncls && num_old >= 0 && num_old <= ncls && K >= 1 && feat_dim >= 1);
+    LucirArgs a{};
+    a.logits = logits; a.scores = scores; a.feat = feat; a.ref_feat = ref_feat; a.y = reinterpret_cast<const long long*>(y);
+    a.dlogits = dlogits; a.dscores = dscores; a.dfeat = dfeat; a.pred = reinterpret_cast<long long*>(pred); a.scal = scal;
+    a.B = batch; a.C = ncls; a.ld = ld; a.D = feat_dim; a.num_old = num_old; a.K = K; a.cur_lamda = cur_lamda; a.margin = margin; a.lw_mr = lw_mr;
+    lucir_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
+    return lc_launch_status();
+}
+
+int lc_l2p_select(const float* query, const float* key, int batch, int pool, int dim, int top_k, float* sim, int64_t* ids, int* hist,
+                  float* reduce_sim, float* dkey, float* scratch, lc_stream_t stream) {
+    LC_CHECK_ARG(query && key && sim && ids && hist && reduce_sim && scratch && batch >= 1 && batch <= 4096 && pool >= 1 && pool <= 32 && top_k >= 1 &&
+                 top_k <= pool && dim >= 1);
+    L2pArgs a{};
+    a.query = query; a.key = key; a.sim = sim; a.ids = reinterpret_cast<long long*>(ids); a.hist = hist; a.reduce_sim = reduce_sim; a.dkey = dkey;
+    a.qsum = scratch; a.B = batch; a.P = pool; a.D = dim; a.top_k = top_k;
+    const size_t smem = (32 + batch) * sizeof(float) + 64 * sizeof(int) + 8 * sizeof(float);
+    l2p_select_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(a);
+    return lc_launch_status();
+}
+
+int lc_l2p_gather(const float* prompt, const int64_t* ids, float* out, int batch, int top_k, int length, int dim, lc_stream_t stream) {
+    LC_CHECK_ARG(prompt && ids && out && batch >= 1 && top_k >= 1 && length >= 1 && dim % 4 == 0);
+    const long long n4 = (long long)batch * top_k * length * dim / 4;
+    const int grid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+    l2p_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prompt, reinterpret_cast<const long long*>(ids), out, batch, top_k, length, dim);
+    return lc_launch_status();
+}
+
+int lc_gpm_project(float* grad, const float* proj, int rows, int dim, lc_stream_t stream) {
+    LC_CHECK_ARG(grad && proj && rows >= 1 && dim >= 4 && dim % 4 == 0 && dim <= 4096);
+    constexpr int RT = 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(gpm_project_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT * 4096 * 4) != cudaSuccess) return LC_ERR_CUDA;
+        attr_done = true;
+    }
+    gpm_project_kernel<RT><<<(rows + RT - 1) / RT, 256, (size_t)RT * dim * sizeof(float), (cudaStream_t)stream>>>(grad, proj, rows, dim);
+    return lc_launch_status();
+}
+
+int lc_lora_merge_qkv(const float* qkv_w, const float* A_k, const float* B_k, const float* A_v, const float* B_v, float* out, int dim, int rank,
+                      lc_stream_t stream) {
+    LC_CHECK_ARG(qkv_w && A_k && B_k && A_v && B_v && out && dim % 4 == 0 && rank >= 1 && rank <= 64);
+    lora_merge_qkv_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(qkv_w, A_k, B_k, A_v, B_v, out, dim, rank);
+    return lc_launch_status();
+}
+
+int lc_lora_bgrad(const float* dW, const float* A, float* dB, int dim, int rank, lc_stream_t stream) {
+    LC_CHECK_ARG(dW && A && dB && dim >= 1 && rank >= 1);
+    lora_bgrad_kernel<<<(dim + 3) / 4, 128, 0, (cudaStream_t)stream>>>(dW, A, dB, dim, rank);
+    return lc_launch_status();
+}
+
+}  // extern "C"
