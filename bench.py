@@ -33,7 +33,7 @@ BATCH = 128
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="icarl", choices=["icarl", "ewc"])
@@ -325,7 +325,11 @@ def run_ours(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     us, algo, kname = time_dominant_kernel(eng, args.precision)
     achieved = algo / (us * 1e-6) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
+    # (profiles/r1e_ncu_conv3x3_tc.txt: 8.45 MB read = the input tensor once, 0 B written: the 8.4 MB output was still in the
+    # 126 MB L2 when the capture ended); null for the CUDA-core kernel (not captured)
+    traffic = 8448256 if args.precision == "tc" else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": kname, "us_per_launch": us,
                 "algorithmic_bytes_per_launch": algo, "peak_source": peak_src}
     cpu = None
