@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--workload", default="icarl", choices=["icarl", "ewc"])
     ap.add_argument("--cpu-steps", type=int, default=12, help="timed oracle steps for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: run the oracle port (plain PyTorch eager ops) on the host cores (default, the contract's "
+                         "reference arm) or on cuda:0 (PyTorch/cuDNN eager: the denominator of north_star's >=1.3x single-GPU target)")
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
                     help="conv arithmetic: tc = tcgen05 tensor cores (TF32 fwd/dgrad, BF16-operand wgrad, fp32 accumulate), fp32 = exact CUDA-core path")
     return ap.parse_args()
@@ -86,18 +89,33 @@ def synth_batches(n, hi, lo=0, seed=7):
              torch.from_numpy(rng.integers(lo, hi, (BATCH,)).astype(np.int64))) for _ in range(n)]
 
 
-def time_oracle(workload, steps, warmup):
+def time_oracle(workload, steps, warmup, device="cpu"):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     orc, hi = make_oracle(workload)
     lo = 10 if workload == "ewc" else 0
     batches = synth_batches(2, hi, lo)
+    if device == "cuda":
+        # the reference's own device semantics: eager PyTorch on the GPU, cuDNN convs (TF32 allowed, PyTorch default), fp32 elsewhere
+        dev = torch.device("cuda", 0)
+        mv = lambda d: {k: v.to(dev) for k, v in d.items()}
+        orc.p = {k: v.detach().to(dev).requires_grad_(True) for k, v in orc.p.items()}
+        orc.b = mv(orc.b)
+        orc.fc_w = orc.fc_w.detach().to(dev).requires_grad_(True); orc.fc_b = orc.fc_b.detach().to(dev).requires_grad_(True)
+        if orc.teacher is not None:
+            tp, tb, tw, tbias = orc.teacher
+            orc.teacher = (mv(tp), mv(tb), tw.to(dev), tbias.to(dev))
+        orc.ref, orc.fisher = mv(orc.ref), mv(orc.fisher)
+        batches = [(x.to(dev), y.to(dev)) for x, y in batches]
+    sync = (lambda: torch.cuda.synchronize()) if device == "cuda" else (lambda: None)
     for i in range(warmup):
         orc.step(*batches[i % 2])
+    sync()
     t0 = time.perf_counter()
     for i in range(steps):
         orc.step(*batches[i % 2])
+    sync()
     dt = time.perf_counter() - t0
     return BATCH * steps / dt, dt / steps * 1e3, cores
 
@@ -106,13 +124,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warm = max(1, min(args.steps, 40)), max(1, min(args.warmup, 3))
-    ips, ms, cores = time_oracle(args.workload, steps, warm)
+    on_gpu = args.ref_device == "cuda"
+    steps, warm = (max(1, min(args.steps, 200)), max(3, min(args.warmup, 20))) if on_gpu else (max(1, min(args.steps, 40)), max(1, min(args.warmup, 3)))
+    ips, ms, cores = time_oracle(args.workload, steps, warm, args.ref_device)
     line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name(args.workload), "global_batch": BATCH, "device": "cpu"},
+            "config": {"workload": workload_name(args.workload), "global_batch": BATCH,
+                       "device": "cuda:0 (PyTorch eager + cuDNN, context only)" if on_gpu else "cpu"},
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} full training steps of batch {BATCH} (oracle/port.py, PyTorch CPU fp32, {cores} threads)"},
+                             "sample": f"{steps} full training steps of batch {BATCH} (oracle/port.py, PyTorch "
+                                       + ("eager on cuda:0)" if on_gpu else f"CPU fp32, {cores} threads)")},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 

@@ -170,7 +170,7 @@ def kd_loss(student: Tensor, teacher: Tensor, T: float = 2.0) -> Tensor:
 
 def ewc_penalty(named_params: Dict[str, Tensor], ref: Dict[str, Tensor], fisher: Dict[str, Tensor]) -> Tensor:
     """`EWC.compute_ewc`, ewc.py:207-225: sum_n sum(F_n * (p_n[:len(ref_n)] - ref_n)^2) / 2."""
-    total = torch.zeros(())
+    total = 0.0
     for n, prm in named_params.items():
         if n in fisher:
             total = total + (fisher[n] * (prm[: len(ref[n])] - ref[n]).pow(2)).sum() / 2
@@ -207,7 +207,7 @@ def lucir_loss(feat: Tensor, ref_feat: Tensor, logits: Tensor, scores_bs: Tensor
     """`LUCIR.observe` task>0 branch, lucir.py:184-205.
     feat/ref_feat: inputs of the cosine classifiers (student / frozen ref); logits = sigma*scores_bs."""
     B = y.shape[0]
-    loss = F.cosine_embedding_loss(feat, ref_feat.detach(), torch.ones(B)) * cur_lamda
+    loss = F.cosine_embedding_loss(feat, ref_feat.detach(), torch.ones(B, device=feat.device)) * cur_lamda
     loss = loss + F.cross_entropy(logits, y)
     gt = scores_bs.gather(1, y.view(-1, 1)).squeeze(1)
     max_novel = scores_bs[:, num_old:].topk(K, dim=1)[0]
