@@ -44,6 +44,8 @@ void lc_resnet_destroy(lc_resnet* net);
  * for the reference's convs under PyTorch's default allow_tf32), BF16 operands for the weight gradient.  workspace word 8 (int) is set to 1 if a tensor-core barrier ever timed out. */
 int lc_resnet_set_mode(lc_resnet* net, int mode);
 int lc_resnet_get_mode(const lc_resnet* net);
+/* last_relu = 0: the last residual block omits its final ReLU (LUCIR's `modified_ResNet`, resnet.py:472-502, factory `resnet32_V2`). */
+int lc_resnet_set_last_relu(lc_resnet* net, int last_relu);
 long long lc_resnet_param_count(const lc_resnet* net);
 long long lc_resnet_rstat_count(const lc_resnet* net);
 long long lc_resnet_workspace_floats(const lc_resnet* net);
@@ -98,6 +100,9 @@ int lc_ewc_penalty_grad(const float* theta, const float* theta_ref, const float*
 int lc_fisher_accumulate(float* fisher, const float* grad, long long n, float weight, lc_stream_t stream);
 int lc_fisher_merge(float* f_new, const float* f_old, long long n, float num_samples, float alpha, lc_stream_t stream);
 int lc_sgd_momentum(float* p, const float* g, float* m, long long n, const float* hp, lc_stream_t stream);
+/* lc_sgd_momentum with the elements [freeze_lo, freeze_hi) left untouched (a param group with lr = 0, weight_decay = 0: lucir.py:229-240). */
+int lc_sgd_momentum_frozen(float* p, const float* g, float* m, long long n, const float* hp, long long freeze_lo, long long freeze_hi,
+                           lc_stream_t stream);
 int lc_adam(float* p, const float* g, float* m, float* v, long long n, const float* hp, lc_stream_t stream);
 int lc_clip_grad_norm(float* g, long long n, float max_norm, float* scratch, float* norm_out, lc_stream_t stream);
 
@@ -121,7 +126,7 @@ int lc_cosine_head_backward(const float* gscores, int ld, const float* feat, con
                             int feat_dim, float* dfeat, float* dW, lc_stream_t stream);
 int lc_lucir_loss(const float* logits, const float* scores, int ld, const float* feat, const float* ref_feat, int feat_dim, const int64_t* y,
                   int batch, int ncls, int num_old, int K, float cur_lamda, float margin, float lw_mr, float* dlogits, float* dscores,
-                  float* dfeat, int64_t* pred, float* scal, lc_stream_t stream);
+                  float* dfeat, int64_t* pred, float* scal, float* dsigma /* nullable: sum(dlogits*scores) */, lc_stream_t stream);
 int lc_l2p_select(const float* query, const float* key, int batch, int pool, int dim, int top_k, float* sim, int64_t* ids, int* hist,
                   float* reduce_sim, float* dkey, float* scratch, lc_stream_t stream);
 int lc_l2p_gather(const float* prompt, const int64_t* ids, float* out, int batch, int top_k, int length, int dim, lc_stream_t stream);

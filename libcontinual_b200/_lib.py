@@ -22,6 +22,7 @@ SIGNATURES = {
     "lc_resnet_destroy": (None, [P]),
     "lc_resnet_set_mode": (c_int, [P, c_int]),
     "lc_resnet_get_mode": (c_int, [P]),
+    "lc_resnet_set_last_relu": (c_int, [P, c_int]),
     "lc_resnet_param_count": (c_longlong, [P]),
     "lc_resnet_rstat_count": (c_longlong, [P]),
     "lc_resnet_workspace_floats": (c_longlong, [P]),
@@ -41,11 +42,12 @@ SIGNATURES = {
     "lc_fisher_accumulate": (c_int, [P, P, c_longlong, c_float, P]),
     "lc_fisher_merge": (c_int, [P, P, c_longlong, c_float, c_float, P]),
     "lc_sgd_momentum": (c_int, [P, P, P, c_longlong, P, P]),
+    "lc_sgd_momentum_frozen": (c_int, [P, P, P, c_longlong, P, c_longlong, c_longlong, P]),
     "lc_adam": (c_int, [P, P, P, P, c_longlong, P, P]),
     "lc_clip_grad_norm": (c_int, [P, c_longlong, c_float, P, P, P]),
     "lc_cosine_head_forward": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, c_int, P]),
     "lc_cosine_head_backward": (c_int, [P, c_int, P, P, P, c_int, c_int, c_int, P, P, P]),
-    "lc_lucir_loss": (c_int, [P, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P, P, P, P]),
+    "lc_lucir_loss": (c_int, [P, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P, P, P, P, P]),
     "lc_l2p_select": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "lc_l2p_gather": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     "lc_gpm_project": (c_int, [P, P, c_int, c_int, P]),

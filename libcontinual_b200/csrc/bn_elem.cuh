@@ -18,6 +18,7 @@ struct BnActArgs {
     float* out;
     long long n4;             // number of float4 elements
     int C;
+    int no_relu;              // 1: skip the final ReLU (last block of LUCIR's modified_ResNet, resnet.py:501-502)
 };
 
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(BnActArgs a) {
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(BnActArgs a) {
             }
             v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
         }
-        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        if (!a.no_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         *reinterpret_cast<float4*>(a.out + i * 4) = v;
     }
 }

@@ -87,6 +87,7 @@ struct LucirArgs {
     float* dfeat;            // [B][D]   out: d(loss)/d(feat) from the less-forget term
     long long* pred;
     float* scal;             // [0] loss [1] #correct [2] ce [3] less-forget (x lamda) [5] margin ranking (x lw_mr)
+    float* dsigma;           // nullable: d(loss)/d(sigma) = sum(dlogits * scores)   (logits = sigma * scores)
     int B, C, ld, D, num_old, K;
     float cur_lamda, margin, lw_mr;
 };
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(256) lucir_loss_kernel(LucirArgs a) {
     const int hard_num = s_h[0];
     const float invB = 1.f / (float)a.B;
     const float mr_w = hard_num > 0 ? a.lw_mr / (float)(hard_num * a.K) : 0.f;
-    float ce_acc = 0.f, lf_acc = 0.f, mr_acc = 0.f;
+    float ce_acc = 0.f, lf_acc = 0.f, mr_acc = 0.f, dsig_acc = 0.f;
     int ok = 0;
     for (int n = threadIdx.x; n < a.B; n += 256) {
         const float* lg = a.logits + (size_t)n * a.ld;
@@ -119,7 +120,11 @@ __global__ void __launch_bounds__(256) lucir_loss_kernel(LucirArgs a) {
         for (int k = 0; k < a.C; ++k) se += expf(lg[k] - m);
         ce_acc += m + logf(se) - lg[y];
         const float inv_se = 1.f / se;
-        for (int k = 0; k < a.C; ++k) { dl[k] = (expf(lg[k] - m) * inv_se - (k == y ? 1.f : 0.f)) * invB; ds[k] = 0.f; }
+        for (int k = 0; k < a.C; ++k) {
+            const float d = (expf(lg[k] - m) * inv_se - (k == y ? 1.f : 0.f)) * invB;
+            dl[k] = d; ds[k] = 0.f;
+            dsig_acc = fmaf(d, sc[k], dsig_acc);
+        }
         // less-forget: lamda * mean_b (1 - cos(f, f_ref))   (CosineEmbeddingLoss, target +1; eps 1e-8 on the squared norms as ATen)
         const float* f = a.feat + (size_t)n * a.D;
         const float* r = a.ref_feat + (size_t)n * a.D;
@@ -164,6 +169,13 @@ __global__ void __launch_bounds__(256) lucir_loss_kernel(LucirArgs a) {
     if (threadIdx.x == 0) {
         const float ce = s_a[0] * invB, lf = a.cur_lamda * s_b[0] * invB, mr = hard_num > 0 ? a.lw_mr * s_c[0] / (float)(hard_num * a.K) : 0.f;
         a.scal[0] = lf + ce + mr; a.scal[1] = (float)s_i[0]; a.scal[2] = ce; a.scal[3] = lf; a.scal[5] = mr;
+    }
+    if (a.dsigma != nullptr) {        // second fixed-order block reduction (uniform branch)
+        __syncthreads();
+        s_a[threadIdx.x] = dsig_acc;
+        __syncthreads();
+        for (int off = 128; off > 0; off >>= 1) { if (threadIdx.x < off) s_a[threadIdx.x] += s_a[threadIdx.x + off]; __syncthreads(); }
+        if (threadIdx.x == 0) *a.dsigma = s_a[0];
     }
 }
 

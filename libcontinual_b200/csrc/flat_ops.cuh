@@ -96,6 +96,19 @@ __global__ void __launch_bounds__(256) sgd_momentum_kernel(float* p, const float
     }
 }
 
+// same update, but elements in [freeze_lo, freeze_hi) belong to a param group with lr = 0 and weight_decay = 0 (LUCIR keeps the old
+// classes' embedding fixed: lucir.py:229-240) and are left untouched
+__global__ void __launch_bounds__(256) sgd_momentum_frozen_kernel(float* p, const float* g, float* m, long long n, const float* hp, long long freeze_lo,
+                                                                   long long freeze_hi) {
+    const float lr = hp[0], mu = hp[1], wd = hp[2];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (i >= freeze_lo && i < freeze_hi) continue;
+        const float mm = __fadd_rn(__fmul_rn(mu, m[i]), fmaf(wd, p[i], g[i]));
+        m[i] = mm;
+        p[i] = fmaf(-lr, mm, p[i]);
+    }
+}
+
 // hp = {lr, beta1, beta2, eps, weight_decay, bias_corr1 (1-b1^t), bias_corr2 (1-b2^t)}
 __global__ void __launch_bounds__(256) adam_kernel(float* p, const float* g, float* m, float* v, long long n, const float* hp) {
     const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], bc1 = hp[5], bc2 = hp[6];

@@ -25,12 +25,12 @@ int lc_cosine_head_backward(const float* gscores, int ld, const float* feat, con
 
 int lc_lucir_loss(const float* logits, const float* scores, int ld, const float* feat, const float* ref_feat, int feat_dim, const int64_t* y,
                   int batch, int ncls, int num_old, int K, float cur_lamda, float margin, float lw_mr, float* dlogits, float* dscores,
-                  float* dfeat, int64_t* pred, float* scal, lc_stream_t stream) {
+                  float* dfeat, int64_t* pred, float* scal, float* dsigma, lc_stream_t stream) {
     LC_CHECK_ARG(logits && scores && feat && ref_feat && y && dlogits && dscores && dfeat && pred && scal);
     LC_CHECK_ARG(batch >= 1 && ncls >= 1 && ld >= ncls && num_old >= 0 && num_old <= ncls && K >= 1 && feat_dim >= 1);
     LucirArgs a{};
     a.logits = logits; a.scores = scores; a.feat = feat; a.ref_feat = ref_feat; a.y = reinterpret_cast<const long long*>(y);
-    a.dlogits = dlogits; a.dscores = dscores; a.dfeat = dfeat; a.pred = reinterpret_cast<long long*>(pred); a.scal = scal;
+    a.dlogits = dlogits; a.dscores = dscores; a.dfeat = dfeat; a.pred = reinterpret_cast<long long*>(pred); a.scal = scal; a.dsigma = dsigma;
     a.B = batch; a.C = ncls; a.ld = ld; a.D = feat_dim; a.num_old = num_old; a.K = K; a.cur_lamda = cur_lamda; a.margin = margin; a.lw_mr = lw_mr;
     lucir_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
     return lc_launch_status();

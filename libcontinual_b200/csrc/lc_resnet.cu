@@ -168,6 +168,7 @@ struct lc_resnet {
     int tab_blocks = 0;
     int launches_fwd = 0, launches_bwd = 0;
     int mode = 0;     // 0: exact fp32 CUDA-core convs; 1: TF32 tcgen05 convs (fwd + dgrad of the stride-1 3x3 layers)
+    int last_relu = 1; // 0: the last residual block has no final ReLU (LUCIR's modified_ResNet, resnet.py:472-502)
 };
 
 extern "C" {
@@ -307,6 +308,11 @@ int lc_resnet_set_mode(lc_resnet* n, int mode) {
     return LC_OK;
 }
 int lc_resnet_get_mode(const lc_resnet* n) { return n ? n->mode : LC_ERR_INVALID; }
+int lc_resnet_set_last_relu(lc_resnet* n, int last_relu) {
+    LC_CHECK_ARG(n && (last_relu == 0 || last_relu == 1));
+    n->last_relu = last_relu;
+    return LC_OK;
+}
 
 long long lc_resnet_param_count(const lc_resnet* n) { return n ? n->n_params : LC_ERR_INVALID; }
 long long lc_resnet_rstat_count(const lc_resnet* n) { return n ? n->n_rstat : LC_ERR_INVALID; }
@@ -421,6 +427,7 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
         } else {
             e.res = cur;
         }
+        e.no_relu = (!n->last_relu && &bl == &n->blocks.back()) ? 1 : 0;
         LC_TRY(launch_bn_act(e, st));
         cur = ws + bl.out_off;
     }
@@ -459,7 +466,8 @@ int lc_resnet_backward(lc_resnet* n, const float* x, int batch, const float* par
         const float* blk_in = bi == 0 ? ws + n->off_a0 : ws + n->blocks[bi - 1].out_off;
         const float* blk_out = ws + bl.out_off;
         // bn_b (+ ReLU of the block output): T1 = d(y2), G <- masked gradient (the residual-branch gradient)
-        LC_TRY(bn_bwd(cb, G, blk_out, LC_MASK_FROM_OUT, T1, G)); ++launches;
+        const bool no_relu = !n->last_relu && bi == (int)n->blocks.size() - 1;
+        LC_TRY(bn_bwd(cb, G, blk_out, no_relu ? LC_MASK_NONE : LC_MASK_FROM_OUT, T1, no_relu ? nullptr : G)); ++launches;
         if (bl.conv_d >= 0) {
             const ConvL& cd = n->convs[bl.conv_d];
             LC_TRY(bn_bwd(cd, G, nullptr, LC_MASK_NONE, T3, nullptr)); ++launches;
@@ -590,6 +598,12 @@ int lc_fisher_merge(float* f_new, const float* f_old, long long n, float num_sam
 int lc_sgd_momentum(float* p, const float* g, float* m, long long n, const float* hp, lc_stream_t stream) {
     LC_CHECK_ARG(p && g && m && hp && n > 0 && ((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0));
     sgd_momentum_kernel<<<kFlatBlocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, n, hp);
+    return lc_launch_status();
+}
+int lc_sgd_momentum_frozen(float* p, const float* g, float* m, long long n, const float* hp, long long freeze_lo, long long freeze_hi,
+                           lc_stream_t stream) {
+    LC_CHECK_ARG(p && g && m && hp && n > 0 && freeze_lo >= 0 && freeze_hi >= freeze_lo && freeze_hi <= n);
+    sgd_momentum_frozen_kernel<<<kFlatBlocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, n, hp, freeze_lo, freeze_hi);
     return lc_launch_status();
 }
 int lc_adam(float* p, const float* g, float* m, float* v, long long n, const float* hp, lc_stream_t stream) {

@@ -29,20 +29,24 @@ def _round4(v: int) -> int:
     return (v + 3) // 4 * 4
 
 
-def cifar_resnet_param_layout(depth: int = 32, in_ch: int = 3) -> Tuple[List[Tuple[str, Tuple[int, ...]]], List[str]]:
-    """(name, shape) of every backbone parameter in the registration order of `CifarResNet`
-    (core/model/backbone/resnet.py:334-340,294-301,361-376), and the BN layer prefixes in buffer order."""
+def cifar_resnet_param_layout(depth: int = 32, in_ch: int = 3, style: str = "cifar") -> Tuple[List[Tuple[str, Tuple[int, ...]]], List[str]]:
+    """(name, shape) of every backbone parameter in module registration order, and the BN layer prefixes in buffer order.
+    style 'cifar': `CifarResNet` (core/model/backbone/resnet.py:334-340,294-301,361-376);
+    style 'lucir': `modified_ResNet` / `modified_BasicBlock` (resnet.py:472-547) — same topology and registration order, other names."""
     nblk = (depth - 2) // 6
-    params: List[Tuple[str, Tuple[int, ...]]] = [("conv_1_3x3.weight", (16, in_ch, 3, 3)), ("bn_1.weight", (16,)), ("bn_1.bias", (16,))]
-    bns = ["bn_1"]
+    lucir = style == "lucir"
+    stem_c, stem_bn = ("conv1", "bn1") if lucir else ("conv_1_3x3", "bn_1")
+    ca, ba, cb, bb = ("conv1", "bn1", "conv2", "bn2") if lucir else ("conv_a", "bn_a", "conv_b", "bn_b")
+    params: List[Tuple[str, Tuple[int, ...]]] = [(stem_c + ".weight", (16, in_ch, 3, 3)), (stem_bn + ".weight", (16,)), (stem_bn + ".bias", (16,))]
+    bns = [stem_bn]
     inpl = 16
     for s, planes in enumerate((16, 32, 64), start=1):
         for b in range(nblk):
-            pre = f"stage_{s}.{b}"
+            pre = f"layer{s}.{b}" if lucir else f"stage_{s}.{b}"
             cin = inpl if b == 0 else planes
-            params += [(pre + ".conv_a.weight", (planes, cin, 3, 3)), (pre + ".bn_a.weight", (planes,)), (pre + ".bn_a.bias", (planes,)),
-                       (pre + ".conv_b.weight", (planes, planes, 3, 3)), (pre + ".bn_b.weight", (planes,)), (pre + ".bn_b.bias", (planes,))]
-            bns += [pre + ".bn_a", pre + ".bn_b"]
+            params += [(pre + f".{ca}.weight", (planes, cin, 3, 3)), (pre + f".{ba}.weight", (planes,)), (pre + f".{ba}.bias", (planes,)),
+                       (pre + f".{cb}.weight", (planes, planes, 3, 3)), (pre + f".{bb}.weight", (planes,)), (pre + f".{bb}.bias", (planes,))]
+            bns += [pre + "." + ba, pre + "." + bb]
             if b == 0 and s > 1:
                 params += [(pre + ".downsample.0.weight", (planes, cin, 1, 1)), (pre + ".downsample.1.weight", (planes,)),
                            (pre + ".downsample.1.bias", (planes,))]
@@ -64,7 +68,8 @@ class TeacherState:
 
 
 class ResNetEngine:
-    def __init__(self, depth: int = 32, max_batch: int = 128, num_class_cap: int = 100, device=None, in_ch: int = 3, img: int = 32):
+    def __init__(self, depth: int = 32, max_batch: int = 128, num_class_cap: int = 100, device=None, in_ch: int = 3, img: int = 32,
+                 style: str = "cifar", last_relu: bool = True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.LcError("libcontinual_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -94,7 +99,12 @@ class ResNetEngine:
         self._lamda_dev = None
         self.autograd_grads = None                         # per-step copy of `grads` handed to autograd (p.grad are views of it)
         self.ncls = 0                                      # live rows of the head
-        self.layout, self.bn_names = cifar_resnet_param_layout(depth, in_ch)
+        self.layout, self.bn_names = cifar_resnet_param_layout(depth, in_ch, style)
+        check(self.lib.lc_resnet_set_last_relu(h, int(last_relu)), "lc_resnet_set_last_relu")
+        self.cos_inv_norm = torch.zeros(max_batch + self.cap, device=dev)      # cosine head: 1/||feat_b||, 1/||w_c||
+        self.scores = torch.zeros(max_batch, self.cap, device=dev)             # cosine head: scores before the sigma scale
+        self.dscores = torch.zeros(max_batch, self.cap, device=dev)
+        self.dfeat_extra = torch.zeros(max_batch, self.feat_dim, device=dev)   # loss terms acting directly on the features
         # offsets of every named parameter and BN layer, cross-checked against the C plan
         self.param_off: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
         off = 0
@@ -233,8 +243,13 @@ class ResNetEngine:
         check(self.lib.lc_fisher_accumulate(ptr(fisher), ptr(self.grads), self.n_total, float(weight), stream_ptr()), "lc_fisher_accumulate")
         self.launches += 1
 
-    def sgd_step(self, momentum_buf: torch.Tensor, hp: torch.Tensor, grads: Optional[torch.Tensor] = None):
+    def sgd_step(self, momentum_buf: torch.Tensor, hp: torch.Tensor, grads: Optional[torch.Tensor] = None, frozen: Optional[Tuple[int, int]] = None):
         g = self.grads if grads is None else grads
+        if frozen is not None:
+            check(self.lib.lc_sgd_momentum_frozen(ptr(self.params), ptr(g), ptr(momentum_buf), self.n_total, ptr(hp), frozen[0], frozen[1], stream_ptr()),
+                  "lc_sgd_momentum_frozen")
+            self.launches += 1
+            return
         check(self.lib.lc_sgd_momentum(ptr(self.params), ptr(g), ptr(momentum_buf), self.n_total, ptr(hp), stream_ptr()), "lc_sgd_momentum")
         self.launches += 1
 

@@ -1,3 +1,3 @@
 """Method plugins (mirror of core/model/__init__.py for the hot-path methods) and backbone factories."""
-from .backbone import CifarResNet, cifar_resnet20, cifar_resnet32  # noqa: F401
-from .resnet_methods import EWC, LWF, Finetune, ICarl  # noqa: F401
+from .backbone import CifarResNet, cifar_resnet20, cifar_resnet32, resnet32_V2  # noqa: F401
+from .resnet_methods import EWC, LUCIR, LWF, Finetune, ICarl  # noqa: F401

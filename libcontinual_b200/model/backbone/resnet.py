@@ -47,9 +47,11 @@ class _BackboneFn(torch.autograd.Function):
 
 
 class CifarResNet(nn.Module):
-    def __init__(self, depth: int = 32, channels: int = 3, device=None, max_batch: int = 128, num_class_cap: int = 100, precision: str = "fp32"):
+    def __init__(self, depth: int = 32, channels: int = 3, device=None, max_batch: int = 128, num_class_cap: int = 100, precision: str = "fp32",
+                 style: str = "cifar", last_relu: bool = True):
         super().__init__()
-        self.engine = ResNetEngine(depth=depth, max_batch=max_batch, num_class_cap=num_class_cap, device=device, in_ch=channels)
+        self.engine = ResNetEngine(depth=depth, max_batch=max_batch, num_class_cap=num_class_cap, device=device, in_ch=channels, style=style,
+                                   last_relu=last_relu)
         self.engine.set_precision(precision)
         self.out_dim = 64
         self.num_batches_pending = 0
@@ -157,3 +159,10 @@ def cifar_resnet32(pretrained: bool = False, **kwargs):
 def cifar_resnet20(pretrained: bool = False, **kwargs):
     return CifarResNet(20, device=kwargs.get("device"), max_batch=kwargs.get("max_batch", 128), num_class_cap=kwargs.get("num_classes", 100),
                        precision=kwargs.get("precision", "fp32"))
+
+
+def resnet32_V2(pretrained: bool = False, **kwargs):
+    """LUCIR's backbone (`modified_ResNet(modified_BasicBlock, [5, 5, 5])`, resnet.py:472-547, factory :770-774): the same topology
+    as cifar_resnet32 with `layerN.M.conv1/bn1/conv2/bn2` names and NO ReLU after the last residual block."""
+    return CifarResNet(32, device=kwargs.get("device"), max_batch=kwargs.get("max_batch", 128), num_class_cap=kwargs.get("num_classes", 100),
+                       precision=kwargs.get("precision", "fp32"), style="lucir", last_relu=False)

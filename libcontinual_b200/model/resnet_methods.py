@@ -337,3 +337,180 @@ class LWF(_ResNetMethod):
         x, y = self._to_device(data)
         self._launch_step(x, y)
         return self._finish(x.shape[0], y)
+
+
+class _CosineHead(nn.Module):
+    """`CosineLinear` / `SplitCosineLinear` look-alike (resnet.py:418-463) over the engine's head arena: weight rows [0, n_old) are
+    `fc1.weight`, rows [n_old, n) `fc2.weight`, `sigma` lives in the first slot of the bias region."""
+
+    class _Part(nn.Module):
+        def __init__(self, w):
+            super().__init__()
+            self.weight = nn.Parameter(w)
+            self.out_features, self.in_features = w.shape
+
+        def _apply(self, fn, recurse=True):
+            return self
+
+    def __init__(self, eng: ResNetEngine, n_old: int, n_new: int):
+        super().__init__()
+        n = n_old + n_new
+        self.in_features, self.out_features = eng.feat_dim, n
+        w, b = eng.fc_views(n)
+        self.sigma = nn.Parameter(eng.params[eng.off_fc_b:eng.off_fc_b + 1])
+        if n_new == 0:
+            self.weight = nn.Parameter(w)
+        else:
+            self.fc1 = _CosineHead._Part(w[:n_old])
+            self.fc2 = _CosineHead._Part(w[n_old:])
+
+    def _apply(self, fn, recurse=True):
+        return self
+
+
+class LUCIR(_ResNetMethod):
+    """core/model/lucir.py:72-240 on the `resnet32_V2` backbone: cosine head, less-forget + CE + margin-ranking losses, frozen
+    reference model, old-class embedding excluded from the update (param group with lr 0)."""
+
+    def __init__(self, backbone, feat_dim, num_class, **kwargs):
+        super().__init__(backbone, feat_dim, num_class, **kwargs)
+        _draw_linear(feat_dim, num_class)                           # Finetune.classifier (finetune.py:10): unused, draws RNG
+        stdv = 1.0 / (feat_dim ** 0.5)                              # CosineLinear.reset_parameters (resnet.py:431-435)
+        w0 = torch.empty(kwargs["init_cls_num"], feat_dim).uniform_(-stdv, stdv)
+        eng = self.engine
+        self._set_cos_head(w0, 1.0, 0)
+        self.K, self.lw_mr, self.dist, self.lamda = kwargs["K"], kwargs["lw_mr"], kwargs["dist"], kwargs["lamda"]
+        self.ref_model = None
+        self.cur_lamda = self.lamda
+        self.num_old_classes = 0
+
+    def _set_cos_head(self, weight, sigma, n_old):
+        eng = self.engine
+        n = weight.shape[0]
+        w, _ = eng.fc_views(n)
+        w.copy_(weight)
+        eng.params[eng.off_fc_b] = float(sigma)
+        eng.ncls = n
+        self.n_old_rows = n_old
+        self.network = _Network.__new__(_Network)
+        nn.Module.__init__(self.network)
+        self.network.backbone = self.backbone
+        self.network.classifier = _CosineHead(eng, n_old, n - n_old)
+        self.network.feat_dim, self.network.num_class = self.feat_dim, n
+
+    def _class_mean_embeddings(self, train_loader, first_cls, n_new):
+        """`_init_new_fc` (lucir.py:130-158): eval-mode features of every sample of each new class, L2-normalised, averaged and
+        re-normalised in float64 on the host exactly as the reference does with its numpy feature matrix."""
+        eng = self.engine
+        was_training = self.backbone.training
+        self.backbone.eval()
+        sums = torch.zeros(n_new, self.feat_dim, dtype=torch.float64)
+        counts = torch.zeros(n_new, dtype=torch.float64)
+        with torch.no_grad():
+            for data in train_loader:
+                x, y = self._to_device(data)
+                f = self.backbone.feature(x).double().cpu()
+                f = torch.nn.functional.normalize(f, p=2, dim=1)
+                yl = y.cpu()
+                for c in range(n_new):
+                    m = yl == first_cls + c
+                    if m.any():
+                        sums[c] += f[m].sum(0); counts[c] += float(m.sum())
+        self.backbone.train(was_training)
+        mean = sums / counts.clamp_min(1.0).unsqueeze(1)
+        return torch.nn.functional.normalize(mean, p=2, dim=1)
+
+    def before_task(self, task_idx, buffer, train_loader, test_loaders):
+        self.task_idx = task_idx
+        eng = self.engine
+        inc = self.kwargs["inc_cls_num"]
+        if task_idx >= 1:
+            n_prev = eng.ncls
+            self.ref_model = TeacherState(eng)                     # copy.deepcopy(self.network), eval (lucir.py:88,99,121)
+            self.num_old_classes = n_prev
+            stdv = 1.0 / (self.feat_dim ** 0.5)
+            # SplitCosineLinear(in, n_prev, inc): both parts draw their uniform init, fc1 is then overwritten by the old embedding
+            torch.empty(n_prev, self.feat_dim).uniform_(-stdv, stdv)
+            w2 = torch.empty(inc, self.feat_dim).uniform_(-stdv, stdv)
+            old_w, _ = eng.fc_views(n_prev)
+            old_w = old_w.clone()
+            if train_loader is not None:                           # _init_new_fc: class-mean embedding scaled to the old average norm
+                avg_norm = old_w.norm(dim=1, keepdim=True).mean(dim=0).double().cpu()
+                emb = self._class_mean_embeddings(train_loader, n_prev, inc)
+                w2 = (emb * avg_norm).float()
+            sigma = float(eng.params[eng.off_fc_b])
+            self._set_cos_head(torch.cat([old_w, w2.to(old_w.device)]), sigma, n_prev)
+            self.cur_lamda = self.lamda * ((n_prev * 1.0 / inc) ** 0.5)
+        else:
+            self.cur_lamda = self.lamda
+
+    def _params(self):
+        c = self.network.classifier
+        head = [c.weight] if hasattr(c, "weight") else [c.fc1.weight, c.fc2.weight]
+        return [p for _, p in self.backbone.named_parameters()] + head + [c.sigma]
+
+    def _grad_views(self, arena=None):
+        eng = self.engine
+        arena = eng.grads if arena is None else arena
+        gw, _ = eng.fc_views(eng.ncls, arena)
+        heads = (gw,) if self.n_old_rows == 0 else (gw[:self.n_old_rows], gw[self.n_old_rows:])
+        return tuple(eng.param_view(n, arena) for n, _ in eng.layout) + heads + (arena[eng.off_fc_b:eng.off_fc_b + 1],)
+
+    def get_parameters(self, config):
+        if self.task_idx > 0:       # lucir.py:229-240 (the lr 0.1 / wd 5e-4 literals are the reference's)
+            c = self.network.classifier
+            base = [p for _, p in self.backbone.named_parameters()] + [c.fc2.weight, c.sigma]
+            return [{"params": base, "lr": 0.1, "weight_decay": 5e-4}, {"params": [c.fc1.weight], "lr": 0, "weight_decay": 0}]
+        return self._params()
+
+    def _launch_step(self, x, y):
+        eng = self.engine
+        lib, st = eng.lib, torch.cuda.current_stream().cuda_stream
+        from .._lib import check
+        B, n = x.shape[0], eng.ncls
+        kd = self.task_idx > 0 and self.ref_model is not None
+        ref_feat = eng.features(B)
+        if kd:
+            t = self.ref_model
+            eng.forward(x, train=False, update_running=False, params=t.params, rstat=t.rstat, ws=t.ws)
+            eng.pool_forward(B, ws=t.ws)
+            ref_feat = eng.features(B, ws=t.ws)
+        eng.forward(x, train=True, update_running=True)
+        self.backbone.num_batches_pending += 1
+        eng.pool_forward(B)
+        feat = eng.features(B)
+        P = eng.params.data_ptr()
+        w_ptr, sig_ptr = P + 4 * eng.off_fc_w, P + 4 * eng.off_fc_b
+        check(lib.lc_cosine_head_forward(feat.data_ptr(), w_ptr, sig_ptr, B, n, eng.feat_dim, eng.cos_inv_norm.data_ptr(), eng.scores.data_ptr(),
+                                         eng.logits.data_ptr(), eng.cap, st), "lc_cosine_head_forward")
+        G = eng.grads.data_ptr()
+        check(lib.lc_lucir_loss(eng.logits.data_ptr(), eng.scores.data_ptr(), eng.cap, feat.data_ptr(), ref_feat.data_ptr(), eng.feat_dim, y.data_ptr(), B, n,
+                                self.num_old_classes if kd else 0, int(self.K), float(self.cur_lamda if kd else 0.0), float(self.dist),
+                                float(self.lw_mr if kd else 0.0), eng.dlogits.data_ptr(), eng.dscores.data_ptr(), eng.dfeat_extra.data_ptr(), eng.pred.data_ptr(),
+                                eng.scal.data_ptr(), G + 4 * eng.off_fc_b, st), "lc_lucir_loss")
+        # gscores = sigma * dlogits + dscores  (one fused elementwise over [B, cap])
+        gs = torch.addcmul(eng.dscores, eng.dlogits, eng.params[eng.off_fc_b:eng.off_fc_b + 1])
+        dfeat = eng.ws[eng._off[5]:eng._off[5] + B * eng.feat_dim]
+        check(lib.lc_cosine_head_backward(gs.data_ptr(), eng.cap, feat.data_ptr(), w_ptr, eng.cos_inv_norm.data_ptr(), B, n, eng.feat_dim, dfeat.data_ptr(),
+                                          G + 4 * eng.off_fc_w, st), "lc_cosine_head_backward")
+        dfeat.view(B, eng.feat_dim).add_(eng.dfeat_extra[:B])
+        eng.pool_backward(dfeat.view(B, eng.feat_dim))
+        eng.backward(x)
+        eng.launches += 6
+
+    def observe(self, data):
+        x, y = self._to_device(data)
+        self._launch_step(x, y)
+        return self._finish(x.shape[0], y)
+
+    def _infer_logits(self, x):
+        eng = self.engine
+        B = x.shape[0]
+        eng.forward(x, train=self.training, update_running=self.training)
+        eng.pool_forward(B)
+        P = eng.params.data_ptr()
+        from .._lib import check
+        check(eng.lib.lc_cosine_head_forward(eng.features(B).data_ptr(), P + 4 * eng.off_fc_w, P + 4 * eng.off_fc_b, B, eng.ncls, eng.feat_dim,
+                                             eng.cos_inv_norm.data_ptr(), eng.scores.data_ptr(), eng.logits.data_ptr(), eng.cap,
+                                             torch.cuda.current_stream().cuda_stream), "lc_cosine_head_forward")
+        return eng.logits[:B, :eng.ncls]

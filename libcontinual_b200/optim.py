@@ -45,5 +45,20 @@ class SGD(torch.optim.Optimizer):
                         src[off:off + p.numel()].zero_()
                     else:
                         src[off:off + p.numel()].copy_(p.grad.reshape(-1))
-        eng.sgd_step(self.buf, self.hp, grads=src)
+        eng.sgd_step(self.buf, self.hp, grads=src, frozen=self._frozen_range())
         return None
+
+    def _frozen_range(self):
+        """A param group with lr == 0 and weight_decay == 0 (LUCIR's old-class embedding, lucir.py:229-240) maps to one contiguous
+        arena range that the fused kernel skips."""
+        lo = hi = None
+        base = self.engine.params.data_ptr()
+        for grp in self.param_groups[1:]:
+            if float(grp["lr"]) == 0.0 and float(grp["weight_decay"]) == 0.0:
+                for p in grp["params"]:
+                    off = (p.data_ptr() - base) // 4
+                    lo = off if lo is None else min(lo, off)
+                    hi = off + p.numel() if hi is None else max(hi, off + p.numel())
+            else:
+                raise ValueError("libcontinual_b200.optim.SGD: extra param groups must be frozen (lr = 0, weight_decay = 0)")
+        return None if lo is None else (int(lo), int(hi))

@@ -261,6 +261,75 @@ def golden_lwf(core):
     np.savez_compressed(os.path.join(OUT, "lwf_resnet32.npz"), **out)
 
 
+# ---- LUCIR --------------------------------------------------------------------------------------
+def cifar_to_lucir_name(n: str) -> str:
+    """cifar_resnet32 parameter name -> modified_ResNet (resnet32_V2) name: same topology / order, other names."""
+    n = n.replace("conv_1_3x3", "conv1").replace("bn_1.", "bn1.")
+    for s in (1, 2, 3):
+        n = n.replace(f"stage_{s}.", f"layer{s}.")
+    return n.replace("conv_a", "conv1").replace("bn_a", "bn1").replace("conv_b", "conv2").replace("bn_b", "bn2")
+
+
+def golden_lucir(core):
+    import core.model as M
+    print("LUCIR / resnet32_V2")
+    B, init_cls, inc_cls = 8, 10, 5
+    p, b, fc_w, fc_b = synth_resnet_state(404, 15)
+    rng = np.random.default_rng(4040)
+    out = {}
+    bb = M.resnet32_V2()
+    bb.load_state_dict({cifar_to_lucir_name(k): v for k, v in {**p, **b}.items()}, strict=True)
+    ref = M.LUCIR(bb, 64, 100, device=torch.device("cpu"), init_cls_num=init_cls, inc_cls_num=inc_cls, K=2, lw_mr=1, lamda=5, dist=0.5)
+    w0 = fc_w[:10].clone()
+    with torch.no_grad():
+        ref.network.classifier.weight.copy_(w0); ref.network.classifier.sigma.fill_(1.5)
+    ref.before_task(0, None, None, None)
+    ref.train()
+    x, y = synth_batch(4100, B, 0, 10)
+    pred, acc, loss = ref.observe({"image": x, "label": y})
+    grads = torch.autograd.grad(loss, list(ref.network.parameters()))
+    names = [n for n, _ in ref.network.named_parameters()]
+    out["t0/loss"] = np.float64(loss.item()); out["t0/pred"] = pred.numpy().copy()
+    summarize("t0/grad", dict(zip(names, grads)), out)
+    # oracle check (task 0 = plain CE on the cosine logits)
+    op = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    ob = {k: v.clone() for k, v in b.items()}
+    ow, osig = w0.clone().requires_grad_(True), torch.tensor([1.5], requires_grad=True)
+    feat = port.cifar_resnet_forward(op, ob, x, True, last_relu=False)["features"]
+    l0 = F.cross_entropy(port.cosine_head(feat, ow, osig), y)
+    close(l0, loss.detach(), 1e-6, 1e-7, "lucir t0 loss")
+    # task 1: reference before_task with the dataset-backed embedding init bypassed (weights set explicitly afterwards)
+    ref._init_new_fc = lambda *a, **k: None
+    ref.before_task(1, None, None, None)
+    w2 = fc_w[10:15].clone()
+    with torch.no_grad():
+        ref.network.classifier.fc2.weight.copy_(w2)
+    ref.train(); ref.ref_model.eval()
+    x, y = synth_batch(4101, B, 0, 15)
+    y[0], y[1] = 3, 12          # make sure old-class (hard) and new-class samples are both present
+    pred, acc, loss = ref.observe({"image": x, "label": y})
+    params = dict(ref.network.named_parameters())
+    grads = torch.autograd.grad(loss, list(params.values()))
+    out["t1/loss"] = np.float64(loss.item()); out["t1/pred"] = pred.numpy().copy(); out["t1/y"] = y.numpy().copy()
+    out["t1/cur_lamda"] = np.float64(ref.cur_lamda)
+    summarize("t1/grad", dict(zip(params.keys(), grads)), out)
+    for n, g in zip(params.keys(), grads):
+        if "classifier" in n:
+            out["t1/full/" + n] = g.numpy().copy()
+    # oracle check of the task-1 loss and head gradients
+    W = torch.cat([w0, w2]).requires_grad_(True)
+    with torch.no_grad():      # frozen copy taken at before_task(1): its BN statistics are those BEFORE this step's update
+        rfeat = port.cifar_resnet_forward({k: v.detach() for k, v in p.items()}, {k: v.clone() for k, v in ob.items()}, x, False, last_relu=False)["features"]
+    feat = port.cifar_resnet_forward(op, ob, x, True, last_relu=False)["features"]
+    scores = port.cosine_head(feat, W, None)
+    l1 = port.lucir_loss(feat, rfeat, osig * scores, scores, y, 10, ref.cur_lamda, 2, 0.5, 1)
+    close(l1, loss.detach(), 1e-5, 1e-6, "lucir t1 loss")
+    gW, = torch.autograd.grad(l1, [W])
+    close(gW[:10], dict(zip(params.keys(), grads))["classifier.fc1.weight"], 1e-4, 1e-7, "lucir d fc1")
+    close(gW[10:], dict(zip(params.keys(), grads))["classifier.fc2.weight"], 1e-4, 1e-7, "lucir d fc2")
+    np.savez_compressed(os.path.join(OUT, "lucir_resnet32.npz"), **out)
+
+
 # ---- small op-level goldens -----------------------------------------------------------------------
 def golden_ops(core):
     from core.model.backbone.prompt import L2P as RefL2PPool
@@ -332,6 +401,7 @@ def main():
     golden_ewc(core)
     golden_icarl(core)
     golden_lwf(core)
+    golden_lucir(core)
     golden_ops(core)
     print("golden vectors written to", OUT)
 

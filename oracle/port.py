@@ -124,7 +124,8 @@ def _conv3x3(x: Tensor, w: Tensor, stride: int, conv_mode: str) -> Tensor:
     return F.conv2d(x, w, None, stride, 1)
 
 
-def cifar_resnet_forward(p: Dict[str, Tensor], b: Dict[str, Tensor], x: Tensor, train: bool, depth: int = 32, conv_mode: str = "fp32") -> Dict[str, object]:
+def cifar_resnet_forward(p: Dict[str, Tensor], b: Dict[str, Tensor], x: Tensor, train: bool, depth: int = 32, conv_mode: str = "fp32",
+                         last_relu: bool = True) -> Dict[str, object]:
     """resnet.py:381-395 (network) and :303-316 (basic block).  Returns {'fmaps': [x1, x2, x3], 'features': [B, 64]}.
     conv_mode 'tc' restates the tensor-core arithmetic class for the square stride-1 3x3 layers (see _TF32Conv3x3)."""
     nblk = (depth - 2) // 6
@@ -143,7 +144,8 @@ def cifar_resnet_forward(p: Dict[str, Tensor], b: Dict[str, Tensor], x: Tensor, 
             if (pre + ".downsample.0.weight") in p:
                 r = F.conv2d(h, p[pre + ".downsample.0.weight"], None, stride, 0)
                 r = _bn(r, p, b, pre + ".downsample.1", train)
-            h = F.relu(r + y)
+            # LUCIR's modified_BasicBlock(last=True) drops the final ReLU of the network (resnet.py:497-502)
+            h = (r + y) if (not last_relu and s == 3 and k == nblk - 1) else F.relu(r + y)
         fmaps.append(h)
     feats = F.avg_pool2d(h, 8).flatten(1)          # nn.AvgPool2d(8), resnet.py:340,389-390
     return {"fmaps": fmaps, "features": feats}

@@ -78,9 +78,9 @@ def test_cosine_head_and_lucir_loss_vs_oracle(lib):
     close(l2[:, :15], torch.from_numpy(g["cos/split_out"]), 1e-5, 1e-6, "SplitCosineLinear golden")
     # loss
     dl = torch.zeros(B, ld, device="cuda"); ds = torch.zeros(B, ld, device="cuda"); dfe = torch.zeros(B, D, device="cuda")
-    pred = torch.zeros(B, dtype=torch.int64, device="cuda"); scal = torch.zeros(8, device="cuda")
+    pred = torch.zeros(B, dtype=torch.int64, device="cuda"); scal = torch.zeros(8, device="cuda"); dsg = torch.zeros(1, device="cuda")
     assert lib.lc_lucir_loss(P(logits), P(scores), ld, P(fd), P(dev(ref_feat)), D, P(dev(y)), B, C, n_old, K, float(cur_lamda), margin, lw_mr,
-                             P(dl), P(ds), P(dfe), P(pred), P(scal), st()) == 0
+                             P(dl), P(ds), P(dfe), P(pred), P(scal), P(dsg), st()) == 0
     assert abs(float(scal[0]) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref)) + 1e-6, (float(scal[0]), float(loss_ref))
     assert torch.equal(pred.cpu(), logits_ref.argmax(1))
     # backward through the head: gscores = sigma*dlogits + dscores ; dsigma = sum(dlogits * scores)
@@ -88,7 +88,7 @@ def test_cosine_head_and_lucir_loss_vs_oracle(lib):
     dfeat = torch.zeros(B, D, device="cuda"); dW = torch.zeros(C, D, device="cuda")
     assert lib.lc_cosine_head_backward(P(gs), ld, P(fd), P(Wd), P(inv), B, C, D, P(dfeat), P(dW), st()) == 0
     close(dfeat + dfe, dfeat_ref, 1e-4, 1e-6, "d feat"); close(dW, dW_ref, 1e-4, 1e-6, "d W")
-    assert abs(float((dl[:, :C] * scores[:, :C]).sum()) - float(dsig_ref)) < 1e-5
+    assert abs(float((dl[:, :C] * scores[:, :C]).sum()) - float(dsig_ref)) < 1e-5 and abs(float(dsg) - float(dsig_ref)) < 1e-5
 
 
 def test_gpm_project_and_lora(lib):

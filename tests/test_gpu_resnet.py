@@ -334,3 +334,63 @@ def test_tf32_tensor_core_mode_vs_oracle():
     assert rel_l2(feat, ftf) <= 2 * self_feat + 1e-5
     assert med_err <= 2 * med_self + 1e-4
     assert max(errs.values()) <= 2 * max(self_grad.values()) + 1e-4
+
+
+def test_lucir_step_vs_oracle_and_reference_golden():
+    """LUCIR on resnet32_V2 (last block without ReLU): task 0 (CE on cosine logits) and task 1 (less-forget + CE + margin ranking
+    against the frozen reference model), fp32 path; then the frozen-range SGD step (old-class embedding excluded, lucir.py:229-240)."""
+    import libcontinual_b200.model as M
+    from libcontinual_b200.optim import SGD
+    from tests.test_oracle_golden import lucir_oracle_step
+    g = load("lucir_resnet32.npz")
+    p, b, fc_w, fc_b = synth_resnet_state(404, 15)
+    from oracle.make_golden import cifar_to_lucir_name
+    bb = M.resnet32_V2(max_batch=B)
+    bb.load_state_dict({cifar_to_lucir_name(k): v for k, v in {**p, **b}.items()}, strict=True)
+    m = M.LUCIR(bb, 64, 100, device=torch.device("cuda"), init_cls_num=10, inc_cls_num=5, K=2, lw_mr=1, lamda=5, dist=0.5)
+    eng = m.engine
+    m._set_cos_head(fc_w[:10].cuda(), 1.5, 0)
+    m.before_task(0, None, None, None)
+    m.train()
+
+    def compare(loss, pred, ref_loss, ref_pred, ref_grads, tight):
+        assert abs(float(loss) - float(ref_loss)) <= 1e-4 * abs(float(ref_loss)) + 1e-5, (float(loss), float(ref_loss))
+        assert torch.equal(pred.cpu(), ref_pred)
+        lay = [n for n, _ in port.cifar_resnet_layout()[0]]
+        errs = {}
+        for (name, _), cname in zip(eng.layout, lay):
+            errs[name] = rel_l2(eng.param_view(name, eng.grads), ref_grads["backbone." + cname])
+        gw, _ = eng.fc_views(eng.ncls, eng.grads)
+        errs["head"] = rel_l2(gw, ref_grads["head"])
+        errs["sigma"] = rel_l2(eng.grads[eng.off_fc_b:eng.off_fc_b + 1], ref_grads["sigma"])
+        worst = max(errs, key=errs.get)
+        assert errs[worst] <= (1e-4 if tight else 5e-2), (worst, errs[worst])
+        return errs
+
+    ob = {k: v.clone() for k, v in b.items()}
+    x, y = synth_batch(4100, B, 0, 10)
+    pred, acc, loss = m.observe({"image": x, "label": y})
+    rl, rp, rg = lucir_oracle_step(p, ob, fc_w[:10], torch.tensor([1.5]), x, y, None, 0, 5.0)
+    compare(loss, pred, rl, rp, rg, tight=True)
+    assert abs(float(loss) - float(g["t0/loss"])) < 1e-4 and np.array_equal(pred.cpu().numpy(), g["t0/pred"])
+    # task 1 (no parameter update in between, exactly as the golden was recorded)
+    m.before_task(1, None, None, None)
+    w15, _ = eng.fc_views(15)
+    w15[10:].copy_(fc_w[10:15].cuda())
+    teacher = (p, {k: v.clone() for k, v in ob.items()})
+    x, y = synth_batch(4101, B, 0, 15)
+    y[0], y[1] = 3, 12
+    pred, acc, loss = m.observe({"image": x, "label": y})
+    rl, rp, rg = lucir_oracle_step(p, ob, fc_w[:15], torch.tensor([1.5]), x, y, teacher, 10, m.cur_lamda)
+    assert abs(m.cur_lamda - float(g["t1/cur_lamda"])) < 1e-9
+    compare(loss, pred, rl, rp, rg, tight=False)
+    assert abs(float(loss) - float(g["t1/loss"])) < 1e-4 and np.array_equal(pred.cpu().numpy(), g["t1/pred"])
+    assert float(eng.scal[3]) > 0 and float(eng.scal[5]) >= 0                # less-forget live, margin ranking evaluated
+    # optimizer: fc1 rows frozen, everything else moves
+    opt = SGD(m.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4, engine=eng)
+    before = eng.params.clone()
+    opt.zero_grad(); loss.backward(); opt.step()
+    w_after, _ = eng.fc_views(15)
+    w_before, _ = eng.fc_views(15, before)
+    assert torch.equal(w_after[:10], w_before[:10]) and not torch.equal(w_after[10:], w_before[10:])
+    assert not torch.equal(eng.param_view("conv1.weight"), eng.param_view("conv1.weight", before))

@@ -110,3 +110,41 @@ def test_known_answer_properties():
     qkv = torch.from_numpy(rng.standard_normal((12, 4)).astype(np.float32))
     A = torch.from_numpy(rng.standard_normal((2, 4)).astype(np.float32))
     assert torch.equal(port.lora_merge_qkv(qkv, A, torch.zeros(4, 2), A, torch.zeros(4, 2)), qkv)   # B = 0 -> frozen model
+
+
+def lucir_oracle_step(p, b, W, sigma, x, y, teacher, n_old, cur_lamda, K=2, dist=0.5, lw_mr=1.0):
+    """One LUCIR loss evaluation with the oracle pieces (lucir.py:175-205).  `teacher` = (params, buffers) of the frozen copy or
+    None (task 0: CE only).  Returns (loss, pred, grads dict keyed like the product's arena: backbone.<n>, head, sigma)."""
+    op = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    Wv, sv = W.clone().requires_grad_(True), sigma.clone().requires_grad_(True)
+    rfeat = None
+    if teacher is not None:
+        with torch.no_grad():
+            rfeat = port.cifar_resnet_forward(teacher[0], {k: v.clone() for k, v in teacher[1].items()}, x, False, last_relu=False)["features"]
+    feat = port.cifar_resnet_forward(op, b, x, True, last_relu=False)["features"]
+    scores = port.cosine_head(feat, Wv, None)
+    logits = sv * scores
+    loss = F.cross_entropy(logits, y) if teacher is None else port.lucir_loss(feat, rfeat, logits, scores, y, n_old, cur_lamda, K, dist, lw_mr)
+    gs = torch.autograd.grad(loss, list(op.values()) + [Wv, sv])
+    grads = {"backbone." + k: g for k, g in zip(op.keys(), gs)}
+    grads["head"], grads["sigma"] = gs[-2], gs[-1]
+    return loss.detach(), logits.argmax(1), grads
+
+
+def test_lucir_matches_reference():
+    from tests.golden_util import synth_resnet_state
+    g = load("lucir_resnet32.npz")
+    p, b, fc_w, fc_b = synth_resnet_state(404, 15)
+    bb = {k: v.clone() for k, v in b.items()}
+    x, y = synth_batch(4100, 8, 0, 10)
+    loss, pred, grads = lucir_oracle_step(p, bb, fc_w[:10], torch.tensor([1.5]), x, y, None, 0, 5.0)
+    assert abs(float(loss) - float(g["t0/loss"])) < 1e-6 and np.array_equal(pred.numpy(), g["t0/pred"])
+    teacher = (p, {k: v.clone() for k, v in bb.items()})
+    x, y = synth_batch(4101, 8, 0, 15)
+    y[0], y[1] = 3, 12
+    assert np.array_equal(y.numpy(), g["t1/y"])
+    loss, pred, grads = lucir_oracle_step(p, bb, fc_w[:15], torch.tensor([1.5]), x, y, teacher, 10, float(g["t1/cur_lamda"]))
+    assert abs(float(loss) - float(g["t1/loss"])) < 1e-5 and np.array_equal(pred.numpy(), g["t1/pred"])
+    assert np.allclose(grads["head"][:10].numpy(), g["t1/full/classifier.fc1.weight"], rtol=1e-4, atol=1e-7)
+    assert np.allclose(grads["head"][10:].numpy(), g["t1/full/classifier.fc2.weight"], rtol=1e-4, atol=1e-7)
+    assert np.allclose(grads["sigma"].numpy(), g["t1/full/classifier.sigma"], rtol=1e-4, atol=1e-7)
