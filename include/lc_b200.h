@@ -134,6 +134,14 @@ int lc_gpm_project(float* grad, const float* proj, int rows, int dim, lc_stream_
 int lc_lora_merge_qkv(const float* qkv_w, const float* A_k, const float* B_k, const float* A_v, const float* B_v, float* out, int dim, int rank,
                       lc_stream_t stream);
 int lc_lora_bgrad(const float* dW, const float* A, float* dB, int dim, int rank, lc_stream_t stream);
+/* iCaRL exemplar management.
+ * lc_herding_select : greedy herding of `LinearHerdingBuffer.herding_select` (linearherdingbuffer.py:133-163) over L2-normalised
+ *                     features sorted by class (class c = rows [cls_begin[c], cls_begin[c+1])): per class `per_class` picks of
+ *                     argmin || mean - (f + running_sum)/(i+1) ||, the picked row pushed away by +1e6; out[c][i] = global row
+ *                     index (-1 if the class is smaller).  work: scratch of the same size as feats.
+ * lc_ncm_classify   : `ICarl.NCM_classify` (icarl.py:122-152): argmin_c ||feat - mean_c||^2 (first minimum). */
+int lc_herding_select(const float* feats, const int* cls_begin, int ncls, int dim, int per_class, float* work, int64_t* out, lc_stream_t stream);
+int lc_ncm_classify(const float* feat, const float* means, int batch, int ncls, int dim, int64_t* pred, lc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------------
  * Per-kernel entry points (unit-tested individually; the network-level calls above are compositions of these).

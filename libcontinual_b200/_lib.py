@@ -53,6 +53,8 @@ SIGNATURES = {
     "lc_gpm_project": (c_int, [P, P, c_int, c_int, P]),
     "lc_lora_merge_qkv": (c_int, [P, P, P, P, P, P, c_int, c_int, P]),
     "lc_lora_bgrad": (c_int, [P, P, P, c_int, c_int, P]),
+    "lc_herding_select": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
+    "lc_ncm_classify": (c_int, [P, P, c_int, c_int, c_int, P, P]),
     "lc_conv_scratch_floats": (c_longlong, [c_int, c_int, c_int, c_int]),
     "lc_conv3x3": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P]),
     "lc_conv3x3_packed": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),

@@ -385,3 +385,86 @@ __global__ void __launch_bounds__(128) lora_bgrad_kernel(const float* dW, const 
 }
 
 }  // namespace lc
+
+namespace lc {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// iCaRL exemplar management (core/model/buffer/linearherdingbuffer.py:133-163, core/model/icarl.py:122-152)
+// ---------------------------------------------------------------------------------------------------------------------
+// Herding: one CTA per class over its (already L2-normalised) feature rows [begin, end).  Mirrors the reference's fp32 op order:
+//   cost_j = || mean - (f_j + running_sum) / (i + 1) ||_2 ,  idx = first argmin,  running_sum += f_idx,  f_idx += 1e6
+// `work` is a scratch copy of the features (the algorithm mutates them).  out[c][i] = global row index, -1 when the class has
+// fewer than `per_class` rows.
+template <int D>
+__global__ void __launch_bounds__(256) herding_select_kernel(const float* feats, float* work, const int* cls_begin, int per_class, long long* out) {
+    __shared__ float s_mean[D], s_rs[D];
+    __shared__ float s_cost[256];
+    __shared__ int s_arg[256];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const int begin = cls_begin[c], end = cls_begin[c + 1], n = end - begin;
+    for (int e = tid; e < n * D; e += 256) work[(size_t)begin * D + e] = feats[(size_t)begin * D + e];
+    if (tid < D) {      // torch's mean over dim 0: sum of the column, divided by n
+        float s = 0.f;
+        for (int j = 0; j < n; ++j) s += feats[(size_t)(begin + j) * D + tid];
+        s_mean[tid] = s / (float)n;
+        s_rs[tid] = 0.f;
+    }
+    __syncthreads();
+    for (int i = 0; i < per_class; ++i) {
+        if (i >= n) { if (tid == 0) out[(size_t)c * per_class + i] = -1; continue; }
+        const float inv = (float)(i + 1);
+        float best = CUDART_INF_F; int barg = 0x7fffffff;
+        for (int j = tid; j < n; j += 256) {
+            const float* f = work + (size_t)(begin + j) * D;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int d = 0; d < D; ++d) {
+                const float t = s_mean[d] - (f[d] + s_rs[d]) / inv;
+                acc = fmaf(t, t, acc);
+            }
+            const float cost = sqrtf(acc);
+            if (cost < best) { best = cost; barg = j; }
+        }
+        s_cost[tid] = best; s_arg[tid] = barg;
+        __syncthreads();
+        for (int off = 128; off > 0; off >>= 1) {
+            if (tid < off) {
+                const float oc = s_cost[tid + off]; const int oa = s_arg[tid + off];
+                if (oc < s_cost[tid] || (oc == s_cost[tid] && oa < s_arg[tid])) { s_cost[tid] = oc; s_arg[tid] = oa; }
+            }
+            __syncthreads();
+        }
+        const int pick = s_arg[0];
+        if (tid == 0) out[(size_t)c * per_class + i] = begin + pick;
+        if (tid < D) {
+            float* f = work + (size_t)(begin + pick) * D;
+            s_rs[tid] += f[tid];
+            f[tid] = f[tid] + 1e6f;
+        }
+        __syncthreads();
+    }
+}
+
+// nearest-class-mean: pred[b] = argmin_c sum_d (feat[b][d] - mean[c][d])^2   (first minimum), one warp per sample
+template <int D>
+__global__ void __launch_bounds__(128) ncm_classify_kernel(const float* feat, const float* means, int B, int C, long long* pred) {
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const float* f = feat + (size_t)b * D;
+    float best = CUDART_INF_F; int barg = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {
+        const float* m = means + (size_t)c * D;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < D; ++d) { const float t = f[d] - __ldg(m + d); acc = fmaf(t, t, acc); }
+        if (acc < best) { best = acc; barg = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o); const int oa = __shfl_xor_sync(0xffffffffu, barg, o);
+        if (ob < best || (ob == best && oa < barg)) { best = ob; barg = oa; }
+    }
+    if (lane == 0) pred[b] = barg;
+}
+
+}  // namespace lc

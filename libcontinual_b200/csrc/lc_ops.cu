@@ -81,4 +81,16 @@ int lc_lora_bgrad(const float* dW, const float* A, float* dB, int dim, int rank,
     return lc_launch_status();
 }
 
+int lc_herding_select(const float* feats, const int* cls_begin, int ncls, int dim, int per_class, float* work, int64_t* out, lc_stream_t stream) {
+    LC_CHECK_ARG(feats && cls_begin && work && out && ncls >= 1 && per_class >= 1 && dim == 64);
+    herding_select_kernel<64><<<ncls, 256, 0, (cudaStream_t)stream>>>(feats, work, cls_begin, per_class, reinterpret_cast<long long*>(out));
+    return lc_launch_status();
+}
+
+int lc_ncm_classify(const float* feat, const float* means, int batch, int ncls, int dim, int64_t* pred, lc_stream_t stream) {
+    LC_CHECK_ARG(feat && means && pred && batch >= 1 && ncls >= 1 && dim == 64);
+    ncm_classify_kernel<64><<<(batch + 3) / 4, 128, 0, (cudaStream_t)stream>>>(feat, means, batch, ncls, reinterpret_cast<long long*>(pred));
+    return lc_launch_status();
+}
+
 }  // extern "C"

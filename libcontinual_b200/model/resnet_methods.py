@@ -274,8 +274,21 @@ class ICarl(_ResNetMethod):
         self.prev_cls_num = self.accu_cls_num
 
     def after_task(self, task_idx, buffer, train_loader, test_loaders):
+        """icarl.py:169-191: freeze the teacher, shrink + refill the exemplar memory by herding, recompute the class means."""
         self.snapshot_teacher()
-        if buffer is not None and hasattr(buffer, "reduce_old_data"):
+        if buffer is not None and hasattr(buffer, "herding_indices") and train_loader is not None:
+            # tensor-backed memory (libcontinual_b200.buffer.HerdingBuffer): current-task samples, class-sorted
+            xs, ys = [], []
+            for data in train_loader:
+                xs.append(data["image"]); ys.append(data["label"])
+            x, y = torch.cat(xs), torch.cat(ys)
+            keep = (y >= int(self.cur_cls_indexes[0])) & (y <= int(self.cur_cls_indexes[-1]))     # drop replayed exemplars
+            x, y = x[keep], y[keep]
+            order = torch.sort(y, stable=True)[1]
+            buffer.reduce_old_data(self.cur_task_id, self.accu_cls_num)
+            buffer.update(self, x[order], y[order], self.accu_cls_num)
+            self.class_means = buffer.class_means(self).to(self.engine.device).contiguous()
+        elif buffer is not None and hasattr(buffer, "reduce_old_data"):
             buffer.reduce_old_data(self.cur_task_id, self.accu_cls_num)
             val_transform = test_loaders[0].dataset.trfms
             buffer.update(self.network, train_loader, val_transform, self.cur_task_id, self.accu_cls_num, self.cur_cls_indexes, self.device)
@@ -292,9 +305,20 @@ class ICarl(_ResNetMethod):
         return self._finish(x.shape[0], y)
 
     def inference(self, data):
+        """icarl.py:96-152: nearest-class-mean once the class means of every seen class exist, else the linear head."""
         x, y = self._to_device(data)
-        logits = self._infer_logits(x)[:, :self.accu_cls_num]
-        pred = torch.argmax(logits, dim=1)
+        eng = self.engine
+        if self.class_means is not None and len(self.class_means) == self.accu_cls_num:
+            B = x.shape[0]
+            eng.forward(x, train=self.training, update_running=self.training)
+            eng.pool_forward(B)
+            from .._lib import check
+            check(eng.lib.lc_ncm_classify(eng.features(B).data_ptr(), self.class_means.data_ptr(), B, self.accu_cls_num, eng.feat_dim, eng.pred.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream), "lc_ncm_classify")
+            pred = eng.pred[:B].clone()
+        else:
+            logits = self._infer_logits(x)[:, :self.accu_cls_num]
+            pred = torch.argmax(logits, dim=1)
         return pred, torch.sum(pred == y).item() / x.size(0)
 
 

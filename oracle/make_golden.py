@@ -330,6 +330,47 @@ def golden_lucir(core):
     np.savez_compressed(os.path.join(OUT, "lucir_resnet32.npz"), **out)
 
 
+# ---- herding (exemplar selection) ------------------------------------------------------------------
+def herding_inputs(seed=2121, ncls=4, n_per=90, D=64):
+    rng = np.random.default_rng(seed)
+    sizes = [n_per - 7 * (c % 3) for c in range(ncls)]
+    feats = np.abs(rng.standard_normal((sum(sizes), D))).astype(np.float32)
+    labels = np.concatenate([np.full(s, c, dtype=np.int64) for c, s in enumerate(sizes)])
+    return torch.from_numpy(feats), torch.from_numpy(labels)
+
+
+def golden_herding(core):
+    """Drives the REAL `LinearHerdingBuffer.herding_select` with an identity 'backbone' over a tensor-backed dataset, so that the
+    recorded index list is the reference's own."""
+    from core.model.buffer.linearherdingbuffer import LinearHerdingBuffer
+    print("herding_select (LinearHerdingBuffer)")
+    raw, labels = herding_inputs()
+
+    class DS(torch.utils.data.Dataset):
+        def __init__(self):
+            self.images = list(range(raw.shape[0])); self.labels = [int(v) for v in labels]; self.trfms = None
+        def __getitem__(self, i):
+            return {"image": raw[self.images[i]], "label": self.labels[i]}
+        def __len__(self):
+            return len(self.labels)
+
+    class Loader:
+        dataset = DS()
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.backbone = lambda x: {"features": x}
+
+    buf = LinearHerdingBuffer(buffer_size=100, batch_size=32)
+    idx = buf.herding_select(Net(), Loader(), None, 0, 4, np.arange(4), torch.device("cpu"))
+    feats = raw / raw.norm(dim=1).view(-1, 1)
+    mine = port.herding_select(feats, labels, 100 // 4)
+    assert [int(i) for i in idx] == mine, "oracle herding differs from the reference"
+    print(f"   [ok] {len(mine)} exemplar indices identical")
+    np.savez_compressed(os.path.join(OUT, "herding.npz"), idx=np.array(mine, dtype=np.int64))
+
+
 # ---- small op-level goldens -----------------------------------------------------------------------
 def golden_ops(core):
     from core.model.backbone.prompt import L2P as RefL2PPool
@@ -402,6 +443,7 @@ def main():
     golden_icarl(core)
     golden_lwf(core)
     golden_lucir(core)
+    golden_herding(core)
     golden_ops(core)
     print("golden vectors written to", OUT)
 

@@ -286,6 +286,37 @@ def l2p_majority_ids_numpy(sim: np.ndarray, top_k: int) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------------------------
+# iCaRL exemplar management
+# ----------------------------------------------------------------------------------------------
+def herding_select(features: Tensor, targets: Tensor, per_class: int) -> List[int]:
+    """Greedy herding of `LinearHerdingBuffer.herding_select` (core/model/buffer/linearherdingbuffer.py:133-163) on features that
+    are already L2-normalised and ordered by class.  Returns global row indices."""
+    feats = features.clone()
+    result: List[int] = []
+    for c in np.unique(targets.numpy()):
+        ind = np.where(targets.numpy() == c)[0]
+        cf = feats[ind]
+        mean = cf.mean(0, keepdim=True)
+        rs = torch.zeros_like(mean)
+        i = 0
+        while i < per_class and i < cf.shape[0]:
+            cost = (mean - (cf + rs) / (i + 1)).norm(2, 1)
+            j = int(cost.argmin())
+            result.append(j + int(ind[0]))
+            rs += cf[j:j + 1]
+            cf[j] = cf[j] + 1e6
+            i += 1
+    return result
+
+
+def ncm_classify(feats: Tensor, class_means: Tensor) -> Tensor:
+    """`ICarl.NCM_classify` (core/model/icarl.py:122-152)."""
+    n, m = feats.shape[0], class_means.shape[0]
+    d = torch.pow(feats.unsqueeze(1).expand(n, m, -1) - class_means.unsqueeze(0).expand(n, m, -1), 2).sum(2)
+    return torch.argmin(d, dim=1)
+
+
+# ----------------------------------------------------------------------------------------------
 # GPM gradient projection  (core/model/gpm.py:78-81, M = U U^T from gpm.py:124)
 # ----------------------------------------------------------------------------------------------
 def gpm_project(grad: Tensor, feature_mat: Tensor) -> Tensor:

@@ -116,3 +116,37 @@ def test_gpm_project_and_lora(lib):
     dB = torch.empty(D, r, device="cuda")
     assert lib.lc_lora_bgrad(P(dev(dWk)), P(dev(Ak)), P(dB), D, r, st()) == 0
     close(dB, dWk @ Ak.T, 1e-4, 1e-4, "lora dB")
+
+
+def test_herding_and_ncm_bit_exact_indices(lib):
+    """Exemplar selection and nearest-class-mean classification: integer outputs must equal the oracle's exactly."""
+    rng = np.random.default_rng(21)
+    for ncls, per_cls_n, pick in [(5, 500, 20), (10, 37, 40), (3, 64, 64)]:
+        sizes = [per_cls_n - (c % 3) for c in range(ncls)]
+        feats = torch.from_numpy(rng.standard_normal((sum(sizes), 64)).astype(np.float32)).abs()
+        feats = feats / feats.norm(dim=1).view(-1, 1)
+        targets = torch.cat([torch.full((s,), c, dtype=torch.int64) for c, s in enumerate(sizes)])
+        ref = port.herding_select(feats, targets, pick)
+        begins = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int32)
+        out = torch.zeros(ncls, pick, dtype=torch.int64, device="cuda")
+        work = torch.empty_like(feats, device="cuda")
+        assert lib.lc_herding_select(P(dev(feats)), P(dev(begins)), ncls, 64, pick, P(work), P(out), st()) == 0
+        got = [int(v) for v in out.cpu().flatten() if v >= 0]
+        assert got == ref, (ncls, per_cls_n, pick)
+    feats = torch.from_numpy(rng.standard_normal((200, 64)).astype(np.float32))
+    means = torch.from_numpy(rng.standard_normal((55, 64)).astype(np.float32))
+    pred = torch.zeros(200, dtype=torch.int64, device="cuda")
+    assert lib.lc_ncm_classify(P(dev(feats)), P(dev(means)), 200, 55, 64, P(pred), st()) == 0
+    assert torch.equal(pred.cpu(), port.ncm_classify(feats, means))
+
+
+def test_herding_matches_reference_golden(lib):
+    from oracle.make_golden import herding_inputs
+    raw, labels = herding_inputs()
+    feats = raw / raw.norm(dim=1).view(-1, 1)
+    sizes = np.bincount(labels.numpy())
+    begins = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int32)
+    out = torch.zeros(len(sizes), 25, dtype=torch.int64, device="cuda")
+    work = torch.empty_like(feats, device="cuda")
+    assert lib.lc_herding_select(P(dev(feats)), P(dev(begins)), len(sizes), 64, 25, P(work), P(out), st()) == 0
+    assert [int(v) for v in out.cpu().flatten()] == [int(i) for i in load("herding.npz")["idx"]]

@@ -148,3 +148,10 @@ def test_lucir_matches_reference():
     assert np.allclose(grads["head"][:10].numpy(), g["t1/full/classifier.fc1.weight"], rtol=1e-4, atol=1e-7)
     assert np.allclose(grads["head"][10:].numpy(), g["t1/full/classifier.fc2.weight"], rtol=1e-4, atol=1e-7)
     assert np.allclose(grads["sigma"].numpy(), g["t1/full/classifier.sigma"], rtol=1e-4, atol=1e-7)
+
+
+def test_herding_matches_reference():
+    from oracle.make_golden import herding_inputs
+    raw, labels = herding_inputs()
+    feats = raw / raw.norm(dim=1).view(-1, 1)
+    assert port.herding_select(feats, labels, 25) == [int(i) for i in load("herding.npz")["idx"]]
