@@ -144,6 +144,17 @@ int lc_herding_select(const float* feats, const int* cls_begin, int ncls, int di
 int lc_ncm_classify(const float* feat, const float* means, int batch, int ncls, int dim, int64_t* pred, lc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------------
+ * ViT-B/16 building blocks (core/model/backbone/transformer.py:169-197 MultiHeadAttention, :1255-1273 Mlp, :1331-1336 block).
+ * lc_gemm_bf16 : C[b][M][N] = alpha * A[b][M][K] . B[b][N][K]^T (+ bias[N]) (+ residual fp32) on tcgen05 (BF16 operands fetched by TMA
+ *                into 128B-swizzled smem, fp32 accumulation in TMEM).  A/B/C are bf16 unless out_f32; lda/ldb/ldc/ldr and the batch
+ *                strides are in elements (row strides of A and B must be multiples of 8).  out2 (nullable, bf16): GELU(C), exact erf
+ *                form (nn.GELU), in which case C keeps the pre-activation.  Replaces nn.Linear / F.linear / torch.matmul.
+ * ------------------------------------------------------------------------------------------------------------------- */
+int lc_gemm_bf16(const void* A, int lda, long long strideA, const void* B, int ldb, long long strideB, void* C, int ldc, long long strideC, int M, int N,
+                 int K, int batch, const float* bias, const float* residual, int ldr, long long strideR, void* out2, int out_f32, float alpha,
+                 int* error_flag, lc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------------
  * Per-kernel entry points (unit-tested individually; the network-level calls above are compositions of these).
  * conv3x3: NHWC fp32, pad 1.  `w_oihw` is the native nn.Conv2d weight; mode 0 = forward, 1 = data gradient (input is dy).
  * Supported (cin, cout, width_out, stride): the CifarResNet layer shapes.  `in_nchw` != 0: input is NCHW (network stem).

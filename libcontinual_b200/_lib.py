@@ -55,6 +55,8 @@ SIGNATURES = {
     "lc_lora_bgrad": (c_int, [P, P, P, c_int, c_int, P]),
     "lc_herding_select": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
     "lc_ncm_classify": (c_int, [P, P, c_int, c_int, c_int, P, P]),
+    "lc_gemm_bf16": (c_int, [P, c_int, c_longlong, P, c_int, c_longlong, P, c_int, c_longlong, c_int, c_int, c_int, c_int, P, P, c_int, c_longlong, P, c_int,
+                             c_float, P, P]),
     "lc_conv_scratch_floats": (c_longlong, [c_int, c_int, c_int, c_int]),
     "lc_conv3x3": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P]),
     "lc_conv3x3_packed": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
