@@ -153,6 +153,31 @@ int lc_ncm_classify(const float* feat, const float* means, int batch, int ncls, 
 int lc_gemm_bf16(const void* A, int lda, long long strideA, const void* B, int ldb, long long strideB, void* C, int ldc, long long strideC, int M, int N,
                  int K, int batch, const float* bias, const float* residual, int ldr, long long strideR, void* out2, int out_f32, float alpha,
                  int* error_flag, lc_stream_t stream);
+/* Same GEMM with a two-level batch (z = z_out * batch_in + z_in; every operand has an inner and an outer batch stride): the per-head
+ * attention GEMMs (Q K^T, P V) read strided views of the fused QKV buffer [B][T][3][H][64] and write [B][T][H*64] without copies. */
+typedef struct lc_gemm_desc {
+    const void* A; long long lda, strideA_in, strideA_out;
+    const void* B; long long ldb, strideB_in, strideB_out;
+    void* C; long long ldc, strideC_in, strideC_out;
+    const float* bias; const float* residual; long long ldr, strideR_in, strideR_out;
+    void* out2;
+    int M, N, K, batch_in, batch_out, out_f32;
+    float alpha;
+} lc_gemm_desc;
+int lc_gemm_bf16_ex(const lc_gemm_desc* desc, int* error_flag, lc_stream_t stream);
+/* Row-wise / layout kernels of the ViT forward (transformer.py:2222-2261): im2col of the 16x16 patches (timm PatchEmbed as a GEMM), cls-row
+ * assembly, LayerNorm (fp32 in -> bf16 and/or fp32 out, optional (mean, rstd) per row), row softmax (fp32 scores -> bf16 probabilities,
+ * padding columns zeroed), V -> V^T per head, mean over a row range (L2P: the prompt positions, transformer.py:2256-2259), fp32 linear head,
+ * fp32 -> bf16 cast. */
+int lc_vit_patchify(const float* img_nchw, void* out_bf16, int batch, lc_stream_t stream);
+int lc_vit_set_row(float* x, long long batch_stride, int batch, int row, const float* src, const float* add, int dim, lc_stream_t stream);
+int lc_layernorm_forward(const float* x, const float* gamma, const float* beta, float eps, long long rows, int dim, void* out_bf16, float* out_f32,
+                         float* stat, lc_stream_t stream);
+int lc_softmax_rows(const float* S, void* P_bf16, long long rows, int T, int ld, lc_stream_t stream);
+int lc_vit_transpose_v(const void* qkv_bf16, void* vt_bf16, int batch, int T, int heads, int ld, lc_stream_t stream);
+int lc_vit_pool_rows(const float* y, long long batch_stride, int batch, int r0, int nr, int dim, float* feat, lc_stream_t stream);
+int lc_linear_head(const float* feat, const float* W, const float* bias, int batch, int ncls, int dim, float* logits, int ld, lc_stream_t stream);
+int lc_cast_bf16(const float* in, void* out_bf16, long long n, lc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------------
  * Per-kernel entry points (unit-tested individually; the network-level calls above are compositions of these).

@@ -3,7 +3,7 @@
 // fused epilogues (bias, exact GELU, fp32 residual add, BF16 / fp32 output, optional transposed per-head store).
 //
 // Structure (one 128 x BN output tile per CTA, warp specialised, mbarrier pipelines):
-//   warp 0 : TMA producer — cp.async.bulk.tensor 2-D/3-D loads of A (128 x 64) and B (BN x 64) K-blocks into a STAGES-deep ring of
+//   warp 0 : TMA producer — cp.async.bulk.tensor (rank-4 maps: K, rows, inner batch, outer batch) loads of A (128 x 64) and B (BN x 64) K-blocks into a STAGES-deep ring of
 //            128-byte-swizzled shared-memory tiles (CU_TENSOR_MAP_SWIZZLE_128B), arriving on full[stage] with expect_tx bytes
 //   warp 1 : MMA issuer — one elected thread issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M128 x BN x K16) per K-block with
 //            SWIZZLE_128B K-major shared-memory descriptors (SBO = 1024 B, start advanced by 32 B per K16 step), commits the stage back
@@ -28,15 +28,16 @@ struct GemmArgs {
     void* out2;                // nullable bf16: GELU(out) (out then holds the pre-activation, needed by the backward)
     int M, N, K;
     int ldc, ldr;
-    long long batch_stride_c, batch_stride_r;   // elements
+    long long c_stride_in, c_stride_out, r_stride_in, r_stride_out;   // elements; batch index z = z_out * batch_in + z_in
+    int batch_in;
     int out_dtype;
     float alpha;               // scale applied to the accumulator before bias (attention: 1/sqrt(d))
     int* error_flag;
 };
 
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(tmap),
-                 "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(tmap),
+                 "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -75,7 +76,8 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_kernel(const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * K::BM, batch = blockIdx.z;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * K::BM;
+    const int z_in = (int)blockIdx.z % a.batch_in, z_out = (int)blockIdx.z / a.batch_in;
     const int nkb = (a.K + K::BK - 1) / K::BK;
 
     if (threadIdx.x == 0) {
@@ -96,8 +98,8 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_kernel(const __grid_constant
                 mbar_wait(empty + s, ph ^ 1u);                                     // slot free (first lap passes immediately)
                 mbar_expect_tx(full + s, (uint32_t)K::STAGE_BYTES);
                 const uint32_t sa = base_u + (uint32_t)s * K::STAGE_BYTES;
-                tma_load_3d(sa, &tmA, full + s, kb * K::BK, m0, batch);
-                tma_load_3d(sa + K::A_BYTES, &tmB, full + s, kb * K::BK, n0, batch);
+                tma_load_4d(sa, &tmA, full + s, kb * K::BK, m0, z_in, z_out);
+                tma_load_4d(sa + K::A_BYTES, &tmB, full + s, kb * K::BK, n0, z_in, z_out);
             }
         }
     } else if (warp == 1) {
@@ -125,8 +127,8 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_kernel(const __grid_constant
         const int quarter = warp & 3;
         const int m = m0 + quarter * 32 + lane;
         const bool row_ok = m < a.M;
-        const size_t crow = (size_t)batch * a.batch_stride_c + (size_t)m * a.ldc;
-        const size_t rrow = (size_t)batch * a.batch_stride_r + (size_t)m * a.ldr;
+        const size_t crow = (size_t)z_out * a.c_stride_out + (size_t)z_in * a.c_stride_in + (size_t)m * a.ldc;
+        const size_t rrow = (size_t)z_out * a.r_stride_out + (size_t)z_in * a.r_stride_in + (size_t)m * a.ldr;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
             float v[16];

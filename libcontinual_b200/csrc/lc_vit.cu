@@ -1,8 +1,7 @@
-// C entry points of the ViT-B/16 building blocks: tcgen05 GEMM (gemm_tc.cuh) and the row-wise kernels around it.
+// C entry points of the ViT-B/16 building blocks: tcgen05 GEMM (gemm_tc.cuh) and the row-wise kernels around it (vit_ops.cuh).
 #include "../../include/lc_b200.h"
 #include "gemm_tc.cuh"
-
-#include <cstdio>
+#include "vit_ops.cuh"
 
 using namespace lc;
 
@@ -22,16 +21,18 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// rank-3 bf16 tensor map {K (contiguous), rows, batch}, box {64, box_rows, 1}, 128-byte swizzle, zero fill out of bounds
-int make_tmap(CUtensorMap* m, const void* ptr, int K, int rows, int batch, long long ld, long long batch_stride, int box_rows) {
+// rank-4 bf16 tensor map {K (contiguous), rows, inner batch, outer batch}, box {64, box_rows, 1, 1}, 128-byte swizzle, zero fill out of bounds
+int make_tmap(CUtensorMap* m, const void* ptr, int K, int rows, int b_in, int b_out, long long ld, long long s_in, long long s_out, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (enc == nullptr) return LC_ERR_CUDA;
-    cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
-    cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? batch_stride : (long long)rows * ld) * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    if ((gstr[0] % 16) != 0 || (gstr[1] % 16) != 0 || ((uintptr_t)ptr % 16) != 0) return LC_ERR_INVALID;
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    if (b_in <= 1) s_in = (long long)rows * ld;
+    if (b_out <= 1) s_out = (b_in <= 1 ? (long long)rows * ld : s_in * b_in);
+    cuuint64_t gdim[4] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(b_in < 1 ? 1 : b_in), (cuuint64_t)(b_out < 1 ? 1 : b_out)};
+    cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)s_in * 2, (cuuint64_t)s_out * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if ((gstr[0] % 16) != 0 || (gstr[1] % 16) != 0 || (gstr[2] % 16) != 0 || ((uintptr_t)ptr % 16) != 0) return LC_ERR_INVALID;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? LC_OK : LC_ERR_INVALID;
 }
@@ -49,27 +50,89 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmArgs
     return lc_launch_status();
 }
 
+int grid_for(long long n, int per_block) {
+    long long b = (n + per_block - 1) / per_block;
+    const long long cap = 148 * 16;
+    return (int)(b < 1 ? 1 : (b < cap ? b : cap));
+}
+
 }  // namespace
 
 extern "C" {
 
+int lc_gemm_bf16_ex(const lc_gemm_desc* d, int* error_flag, lc_stream_t stream) {
+    LC_CHECK_ARG(d && d->A && d->B && d->C && d->M >= 1 && d->N >= 1 && d->K >= 8 && d->K % 8 == 0 && d->batch_in >= 1 && d->batch_out >= 1);
+    LC_CHECK_ARG(d->lda >= d->K && d->ldb >= d->K && d->ldc >= d->N);
+    const int cal = d->out_f32 ? 4 : 8;      // vectorised epilogue stores: rows of C / residual start on 16-byte boundaries
+    LC_CHECK_ARG(d->ldc % cal == 0 && d->strideC_in % cal == 0 && d->strideC_out % cal == 0);
+    LC_CHECK_ARG(d->residual == nullptr || (d->ldr % 4 == 0 && d->strideR_in % 4 == 0 && d->strideR_out % 4 == 0));
+    CUtensorMap ta, tb;
+    const int bn = d->N > 128 ? 256 : 128;
+    int e = make_tmap(&ta, d->A, d->K, d->M, d->batch_in, d->batch_out, d->lda, d->strideA_in, d->strideA_out, 128);
+    if (e != LC_OK) return e;
+    e = make_tmap(&tb, d->B, d->K, d->N, d->batch_in, d->batch_out, d->ldb, d->strideB_in, d->strideB_out, bn);
+    if (e != LC_OK) return e;
+    tc::GemmArgs a{};
+    a.out = d->C; a.bias = d->bias; a.residual = d->residual; a.out2 = d->out2; a.M = d->M; a.N = d->N; a.K = d->K; a.ldc = (int)d->ldc; a.ldr = (int)d->ldr;
+    a.c_stride_in = d->strideC_in; a.c_stride_out = d->strideC_out; a.r_stride_in = d->strideR_in; a.r_stride_out = d->strideR_out;
+    a.batch_in = d->batch_in; a.out_dtype = d->out_f32 ? tc::GEMM_OUT_F32 : tc::GEMM_OUT_BF16; a.alpha = d->alpha; a.error_flag = error_flag;
+    const int batch = d->batch_in * d->batch_out;
+    return bn == 256 ? launch_gemm<256>(ta, tb, a, batch, (cudaStream_t)stream) : launch_gemm<128>(ta, tb, a, batch, (cudaStream_t)stream);
+}
+
 int lc_gemm_bf16(const void* A, int lda, long long strideA, const void* B, int ldb, long long strideB, void* C, int ldc, long long strideC, int M, int N,
                  int K, int batch, const float* bias, const float* residual, int ldr, long long strideR, void* out2, int out_f32, float alpha,
                  int* error_flag, lc_stream_t stream) {
-    LC_CHECK_ARG(A && B && C && M >= 1 && N >= 1 && K >= 8 && K % 8 == 0 && batch >= 1 && lda >= K && ldb >= K && ldc >= N);
-    // vectorised epilogue stores: rows of C (and of the residual) must start on 16-byte boundaries
-    LC_CHECK_ARG(ldc % (out_f32 ? 4 : 8) == 0 && strideC % (out_f32 ? 4 : 8) == 0 && (residual == nullptr || (ldr % 4 == 0 && strideR % 4 == 0)));
-    CUtensorMap ta, tb;
-    const int bn = (N % 256 == 0 || N > 128) ? 256 : 128;
-    int e = make_tmap(&ta, A, K, M, batch, lda, strideA, 128);
-    if (e != LC_OK) return e;
-    e = make_tmap(&tb, B, K, N, batch, ldb, strideB, bn);
-    if (e != LC_OK) return e;
-    tc::GemmArgs a{};
-    a.out = C; a.bias = bias; a.residual = residual; a.out2 = out2; a.M = M; a.N = N; a.K = K; a.ldc = ldc; a.ldr = ldr;
-    a.batch_stride_c = strideC; a.batch_stride_r = strideR; a.out_dtype = out_f32 ? tc::GEMM_OUT_F32 : tc::GEMM_OUT_BF16; a.alpha = alpha;
-    a.error_flag = error_flag;
-    return bn == 256 ? launch_gemm<256>(ta, tb, a, batch, (cudaStream_t)stream) : launch_gemm<128>(ta, tb, a, batch, (cudaStream_t)stream);
+    lc_gemm_desc d{};
+    d.A = A; d.lda = lda; d.strideA_in = strideA; d.B = B; d.ldb = ldb; d.strideB_in = strideB; d.C = C; d.ldc = ldc; d.strideC_in = strideC;
+    d.bias = bias; d.residual = residual; d.ldr = ldr; d.strideR_in = strideR; d.out2 = out2; d.M = M; d.N = N; d.K = K; d.batch_in = batch;
+    d.batch_out = 1; d.out_f32 = out_f32; d.alpha = alpha;
+    return lc_gemm_bf16_ex(&d, error_flag, stream);
+}
+
+int lc_vit_patchify(const float* img, void* out_bf16, int batch, lc_stream_t stream) {
+    LC_CHECK_ARG(img && out_bf16 && batch >= 1);
+    patchify_kernel<<<grid_for((long long)batch * 196 * 96, 256), 256, 0, (cudaStream_t)stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out_bf16), batch);
+    return lc_launch_status();
+}
+int lc_vit_set_row(float* x, long long batch_stride, int batch, int row, const float* src, const float* add, int dim, lc_stream_t stream) {
+    LC_CHECK_ARG(x && src && batch >= 1 && dim % 4 == 0);
+    set_row_kernel<<<batch, 192, 0, (cudaStream_t)stream>>>(x, batch_stride, row, src, add, dim);
+    return lc_launch_status();
+}
+int lc_layernorm_forward(const float* x, const float* gamma, const float* beta, float eps, long long rows, int dim, void* out_bf16, float* out_f32,
+                         float* stat, lc_stream_t stream) {
+    LC_CHECK_ARG(x && gamma && beta && rows >= 1 && dim == 768 && (out_bf16 || out_f32));
+    layernorm_fwd_kernel<768><<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, rows, reinterpret_cast<__nv_bfloat16*>(out_bf16),
+                                                                                       out_f32, stat);
+    return lc_launch_status();
+}
+int lc_softmax_rows(const float* S, void* P_bf16, long long rows, int T, int ld, lc_stream_t stream) {
+    LC_CHECK_ARG(S && P_bf16 && rows >= 1 && T >= 1 && ld >= T);
+    softmax_rows_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(S, reinterpret_cast<__nv_bfloat16*>(P_bf16), rows, T, ld);
+    return lc_launch_status();
+}
+int lc_vit_transpose_v(const void* qkv_bf16, void* vt_bf16, int batch, int T, int heads, int ld, lc_stream_t stream) {
+    LC_CHECK_ARG(qkv_bf16 && vt_bf16 && batch >= 1 && T >= 1 && heads >= 1 && ld >= T);
+    dim3 grid((ld + 63) / 64, batch * heads);
+    transpose_v_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(vt_bf16), batch, T,
+                                                              heads, ld);
+    return lc_launch_status();
+}
+int lc_vit_pool_rows(const float* y, long long batch_stride, int batch, int r0, int nr, int dim, float* feat, lc_stream_t stream) {
+    LC_CHECK_ARG(y && feat && batch >= 1 && nr >= 1 && dim % 4 == 0);
+    pool_rows_kernel<<<batch, 192, 0, (cudaStream_t)stream>>>(y, batch_stride, r0, nr, dim, feat);
+    return lc_launch_status();
+}
+int lc_linear_head(const float* feat, const float* W, const float* bias, int batch, int ncls, int dim, float* logits, int ld, lc_stream_t stream) {
+    LC_CHECK_ARG(feat && W && logits && batch >= 1 && ncls >= 1 && ld >= ncls);
+    linear_head_kernel<<<(batch * ncls + 3) / 4, 128, 0, (cudaStream_t)stream>>>(feat, W, bias, batch, ncls, dim, logits, ld);
+    return lc_launch_status();
+}
+int lc_cast_bf16(const float* in, void* out_bf16, long long n, lc_stream_t stream) {
+    LC_CHECK_ARG(in && out_bf16 && n >= 1);
+    cast_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n);
+    return lc_launch_status();
 }
 
 }  // extern "C"

@@ -435,6 +435,72 @@ def golden_ops(core):
     np.savez_compressed(os.path.join(OUT, "ops_small.npz"), **out)
 
 
+def synth_vit_state(seed: int, total_cls: int = 100, pool: int = 10, length: int = 5, depth: int = 12):
+    """ViT-B/16 weights + L2P pool (uniform(0,1) like `nn.init.uniform_`, l2p.py:60) + classifier, all from one numpy Generator."""
+    rng = np.random.default_rng(seed)
+    p = port.vit_init(rng, depth=depth)
+    prm = torch.from_numpy(rng.uniform(0, 1, (1, pool, length, 768)).astype(np.float32))
+    key = torch.from_numpy(rng.uniform(0, 1, (pool, 768)).astype(np.float32))
+    bound = 1.0 / np.sqrt(768)
+    fc_w = torch.from_numpy(rng.uniform(-bound, bound, (total_cls, 768)).astype(np.float32))
+    fc_b = torch.from_numpy(rng.uniform(-bound, bound, (total_cls,)).astype(np.float32))
+    return p, prm, key, fc_w, fc_b
+
+
+def synth_images(seed: int, B: int, lo: int, hi: int):
+    rng = np.random.default_rng(seed)
+    x = torch.from_numpy(rng.uniform(0, 1, (B, 3, 224, 224)).astype(np.float32))        # ToTensor() range, no Normalize in the l2p yaml
+    y = torch.from_numpy(rng.integers(lo, hi, (B,)).astype(np.int64))
+    return x, y
+
+
+def golden_l2p(core):
+    """The real `core.model.l2p.L2P` on `vit_pt_imnet` (ViTZoo, 12 x 768): observe() on task 0 and on task 1."""
+    from core.model.backbone.vit import vit_pt_imnet
+    from core.model.l2p import L2P as RefL2P
+    print("L2P / ViT-B/16: reference observe() vs oracle")
+    out = {}
+    p, prm, key, fc_w, fc_b = synth_vit_state(5150)
+    bb = vit_pt_imnet(pretrained=False)
+    ref = RefL2P(bb, torch.device("cpu"), init_cls_num=10, inc_cls_num=10, num_class=100, task_num=10, feat_dim=768, prompt_length=5,
+                 pool_size=10, top_k=5, pull_constraint_coeff=1.0)
+    missing = ref.network.backbone.feat.load_state_dict(p, strict=True)
+    with torch.no_grad():
+        ref.network.backbone.prompt.prompt.copy_(prm); ref.network.backbone.prompt.prompt_key.copy_(key)
+        ref.network.classifier.weight.copy_(fc_w); ref.network.classifier.bias.copy_(fc_b)
+    for task, (lo, hi) in enumerate([(0, 10), (10, 20)]):
+        if task == 1:
+            ref.after_task(0, None, None, None); ref.before_task(1, None, None, None)
+        x, y = synth_images(600 + task, 4, lo, hi)
+        for q in ref.unfrezeed_params:
+            q.grad = None
+        pred, acc, loss = ref.observe({"image": x, "label": y})
+        # oracle (clip_grad_norm_ is applied by observe() itself: l2p.py:104)
+        oprm = prm.clone().requires_grad_(True); okey = key.clone().requires_grad_(True)
+        ow = fc_w.clone().requires_grad_(True); ob = fc_b.clone().requires_grad_(True)
+        feat, rs, major, cls_f = port.l2p_forward(p, oprm, okey, x, 5)
+        ologits = port.linear_head(feat, ow, ob)
+        oloss, _ = port.l2p_loss(ologits, y, lo, hi, rs, 1.0)
+        oloss.backward()
+        torch.nn.utils.clip_grad_norm_([oprm, okey, ow, ob], 1.0)
+        close(oloss, loss, 1e-6, 1e-7, f"l2p task{task} loss")
+        rp = ref.network.backbone.prompt
+        close(oprm.grad, rp.prompt.grad, 1e-5, 1e-8, f"l2p task{task} dprompt")
+        close(okey.grad, rp.prompt_key.grad, 1e-5, 1e-8, f"l2p task{task} dkey")
+        close(ow.grad, ref.network.classifier.weight.grad, 1e-5, 1e-8, f"l2p task{task} dW")
+        close(ob.grad, ref.network.classifier.bias.grad, 1e-5, 1e-8, f"l2p task{task} db")
+        with torch.no_grad():
+            rlogits, _ = ref.network(x, train=False)
+        close(ologits, rlogits, 1e-5, 1e-6, f"l2p task{task} logits")
+        out[f"t{task}/loss"] = np.float64(loss.item()); out[f"t{task}/logits"] = rlogits.numpy().copy()
+        out[f"t{task}/major"] = major.numpy().copy(); out[f"t{task}/cls_features"] = cls_f.numpy().copy()
+        out[f"t{task}/feat"] = feat.detach().numpy().copy()
+        out[f"t{task}/dprompt"] = rp.prompt.grad.numpy().copy(); out[f"t{task}/dkey"] = rp.prompt_key.grad.numpy().copy()
+        out[f"t{task}/dW"] = ref.network.classifier.weight.grad.numpy().copy(); out[f"t{task}/db"] = ref.network.classifier.bias.grad.numpy().copy()
+        out[f"t{task}/pred"] = pred.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "l2p_vit.npz"), **out)
+
+
 def main():
     torch.set_num_threads(8)
     os.makedirs(OUT, exist_ok=True)
@@ -445,6 +511,7 @@ def main():
     golden_lucir(core)
     golden_herding(core)
     golden_ops(core)
+    golden_l2p(core)
     print("golden vectors written to", OUT)
 
 

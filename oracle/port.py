@@ -286,6 +286,104 @@ def l2p_majority_ids_numpy(sim: np.ndarray, top_k: int) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------------------------
+# ViT-B/16 backbone + L2P  (core/model/backbone/transformer.py:2222-2261 VisionTransformer.forward, :2006-2017 Transformer.forward,
+# :1331-1336 ResidualAttentionBlock.forward, :169-197 MultiHeadAttention.forward, :1267-1273 Mlp; core/model/backbone/vit.py:100-121
+# ViTZoo.forward (l2p branch); core/model/l2p.py:84-107 observe)
+# ----------------------------------------------------------------------------------------------
+def vit_layout(depth: int = 12, dim: int = 768, mlp: int = 3072, patch: int = 16, tokens: int = 197) -> List[Tuple[str, Tuple[int, ...]]]:
+    """Parameter names (state-dict keys of the reference `VisionTransformer`) and shapes, in registration order."""
+    out: List[Tuple[str, Tuple[int, ...]]] = [("cls_token", (1, 1, dim)), ("pos_embed", (1, tokens, dim)),
+                                             ("patch_embed.proj.weight", (dim, 3, patch, patch)), ("patch_embed.proj.bias", (dim,))]
+    for i in range(depth):
+        b = f"transformer.blocks.{i}."
+        out += [(b + "attn.qkv.weight", (3 * dim, dim)), (b + "attn.qkv.bias", (3 * dim,)), (b + "attn.proj.weight", (dim, dim)),
+                (b + "attn.proj.bias", (dim,)), (b + "ln_1.weight", (dim,)), (b + "ln_1.bias", (dim,)), (b + "mlp.fc1.weight", (mlp, dim)),
+                (b + "mlp.fc1.bias", (mlp,)), (b + "mlp.fc2.weight", (dim, mlp)), (b + "mlp.fc2.bias", (dim,)), (b + "ln_2.weight", (dim,)),
+                (b + "ln_2.bias", (dim,))]
+    out += [("norm.weight", (dim,)), ("norm.bias", (dim,))]
+    return out
+
+
+def vit_init(rng: np.random.Generator, depth: int = 12, dim: int = 768, mlp: int = 3072) -> Dict[str, Tensor]:
+    """Synthetic 'pretrained' weights from a numpy Generator (there is no checkpoint offline): matrices N(0, 0.02^2) like
+    `_init_weights` (transformer.py:2207-2214) but with non-zero biases / non-unit LayerNorm affine so that every term is exercised."""
+    p: Dict[str, Tensor] = {}
+    for name, shape in vit_layout(depth, dim, mlp):
+        if name.endswith("ln_1.weight") or name.endswith("ln_2.weight") or name == "norm.weight":
+            a = 1.0 + 0.1 * rng.standard_normal(shape)
+        elif name.endswith(".bias"):
+            a = 0.02 * rng.standard_normal(shape)
+        elif name == "patch_embed.proj.weight":
+            a = rng.uniform(-1.0, 1.0, shape) / math.sqrt(shape[1] * shape[2] * shape[3])
+        else:
+            a = 0.02 * rng.standard_normal(shape)
+        p[name] = torch.from_numpy(a.astype(np.float32))
+    return p
+
+
+def _bf16_round(t: Tensor) -> Tensor:
+    """Round-to-nearest-even to BF16 with a straight-through gradient (the CUDA path's GEMM operands are BF16)."""
+    return t + (t.detach().bfloat16().float() - t.detach())
+
+
+def vit_tokens(p: Dict[str, Tensor], x: Tensor, prompts: Optional[Tensor] = None, depth: int = 12, heads: int = 12, gemm_mode: str = "fp32",
+               taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    """`VisionTransformer.forward(prompt_flag='l2p')` up to and including the final LayerNorm: [B, (P +) 197, D].
+    `prompts` [B, P, D] are prepended in front of [cls, patches] AFTER the position embedding was added (transformer.py:2240-2251,
+    :2010-2014).  gemm_mode 'bf16' rounds every GEMM operand (and the stored qkv / probabilities / GELU output) to BF16 exactly where
+    the CUDA path does; accumulation stays fp32."""
+    r = _bf16_round if gemm_mode == "bf16" else (lambda t: t)
+    B = x.shape[0]
+    D = p["cls_token"].shape[-1]
+    w_pe = p["patch_embed.proj.weight"]
+    ps = w_pe.shape[-1]
+    g = x.shape[-1] // ps
+    # conv k=16 s=16 == GEMM over im2col patches (column order c, py, px)
+    cols = x.reshape(B, 3, g, ps, g, ps).permute(0, 2, 4, 1, 3, 5).reshape(B, g * g, 3 * ps * ps)
+    tok = F.linear(r(cols), r(w_pe.reshape(D, -1)), p["patch_embed.proj.bias"])
+    xs = torch.cat([p["cls_token"].expand(B, -1, -1), tok], dim=1) + p["pos_embed"][:, : g * g + 1]
+    if prompts is not None:
+        xs = torch.cat([prompts, xs], dim=1)
+    T = xs.shape[1]
+    hd = D // heads
+    for i in range(depth):
+        b = f"transformer.blocks.{i}."
+        h = F.layer_norm(xs, (D,), p[b + "ln_1.weight"], p[b + "ln_1.bias"], 1e-5)
+        qkv = r(F.linear(r(h), r(p[b + "attn.qkv.weight"]), p[b + "attn.qkv.bias"]))
+        qkv = qkv.reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv[0], qkv[1], qkv[2]
+        attn = r(((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(dim=-1))
+        o = r((attn @ v).transpose(1, 2).reshape(B, T, D))
+        xs = xs + F.linear(o, r(p[b + "attn.proj.weight"]), p[b + "attn.proj.bias"])
+        h = F.layer_norm(xs, (D,), p[b + "ln_2.weight"], p[b + "ln_2.bias"], 1e-5)
+        u = r(F.gelu(F.linear(r(h), r(p[b + "mlp.fc1.weight"]), p[b + "mlp.fc1.bias"])))
+        xs = xs + F.linear(u, r(p[b + "mlp.fc2.weight"]), p[b + "mlp.fc2.bias"])
+        if taps is not None:
+            taps[f"block{i}"] = xs.detach()
+    return F.layer_norm(xs, (D,), p["norm.weight"], p["norm.bias"], 1e-6)
+
+
+def l2p_forward(p: Dict[str, Tensor], pool_prompt: Tensor, pool_key: Tensor, x: Tensor, top_k: int, depth: int = 12, heads: int = 12,
+                gemm_mode: str = "fp32") -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """`ViTZoo.forward` l2p branch (vit.py:102-119): query pass without prompts (no grad) -> pool selection -> prompted pass; the feature is
+    the mean over the prompt positions of the normalised tokens (transformer.py:2255-2258).
+    Returns (feat [B, D], reduce_sim, major ids [top_k], cls_features [B, D])."""
+    with torch.no_grad():
+        cls_features = vit_tokens(p, x, None, depth, heads, gemm_mode)[:, 0]
+    batched, reduce_sim, major = l2p_select(pool_prompt, pool_key, cls_features, top_k)
+    prompts = batched[0]
+    y = vit_tokens(p, x, prompts, depth, heads, gemm_mode)
+    return y[:, : prompts.shape[1]].mean(dim=1), reduce_sim, major, cls_features
+
+
+def l2p_loss(logits: Tensor, y: Tensor, lo: int, hi: int, reduce_sim: Tensor, coeff: float) -> Tuple[Tensor, Tensor]:
+    """l2p.py:89-99: logits outside the current task's classes [lo, hi) are set to -inf, CE, minus coeff * reduce_sim."""
+    masked = torch.full_like(logits, float("-inf"))
+    masked[:, lo:hi] = logits[:, lo:hi]
+    return F.cross_entropy(masked, y) - coeff * reduce_sim, masked
+
+
+# ----------------------------------------------------------------------------------------------
 # iCaRL exemplar management
 # ----------------------------------------------------------------------------------------------
 def herding_select(features: Tensor, targets: Tensor, per_class: int) -> List[int]:

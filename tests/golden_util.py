@@ -44,3 +44,35 @@ def check_summary(g, prefix, named, rtol=1e-4, atol=1e-6, full_rtol=None):
             scale = float(ref.abs().max()) + 1e-12
             err = float((t - ref).abs().max()) / scale
             assert err <= (full_rtol or rtol) , (prefix, n, err)
+
+
+def synth_vit_state(seed, total_cls=100, pool=10, length=5, depth=12):
+    rng = np.random.default_rng(seed)
+    p = port.vit_init(rng, depth=depth)
+    prm = torch.from_numpy(rng.uniform(0, 1, (1, pool, length, 768)).astype(np.float32))
+    key = torch.from_numpy(rng.uniform(0, 1, (pool, 768)).astype(np.float32))
+    bound = 1.0 / np.sqrt(768)
+    fc_w = torch.from_numpy(rng.uniform(-bound, bound, (total_cls, 768)).astype(np.float32))
+    fc_b = torch.from_numpy(rng.uniform(-bound, bound, (total_cls,)).astype(np.float32))
+    return p, prm, key, fc_w, fc_b
+
+
+def synth_images(seed, B, lo, hi):
+    rng = np.random.default_rng(seed)
+    x = torch.from_numpy(rng.uniform(0, 1, (B, 3, 224, 224)).astype(np.float32))
+    y = torch.from_numpy(rng.integers(lo, hi, (B,)).astype(np.int64))
+    return x, y
+
+
+def l2p_oracle_step(p, prm, key, fc_w, fc_b, x, y, lo, hi, top_k=5, coeff=1.0, gemm_mode="fp32", clip=1.0):
+    """One L2P observe() through the oracle (l2p.py:84-107): returns a dict with loss, logits, feat, major ids and the clipped grads."""
+    oprm = prm.clone().requires_grad_(True); okey = key.clone().requires_grad_(True)
+    ow = fc_w.clone().requires_grad_(True); ob = fc_b.clone().requires_grad_(True)
+    feat, rs, major, cls_f = port.l2p_forward(p, oprm, okey, x, top_k, gemm_mode=gemm_mode)
+    logits = port.linear_head(feat, ow, ob)
+    loss, masked = port.l2p_loss(logits, y, lo, hi, rs, coeff)
+    loss.backward()
+    if clip is not None:
+        torch.nn.utils.clip_grad_norm_([oprm, okey, ow, ob], clip)
+    return {"loss": loss.detach(), "logits": logits.detach(), "feat": feat.detach(), "major": major, "cls_features": cls_f, "reduce_sim": rs.detach(),
+            "dprompt": oprm.grad, "dkey": okey.grad, "dW": ow.grad, "db": ob.grad}

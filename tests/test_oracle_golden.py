@@ -155,3 +155,20 @@ def test_herding_matches_reference():
     raw, labels = herding_inputs()
     feats = raw / raw.norm(dim=1).view(-1, 1)
     assert port.herding_select(feats, labels, 25) == [int(i) for i in load("herding.npz")["idx"]]
+
+
+def test_l2p_vit_observe_matches_reference():
+    """Oracle ViT-B/16 + L2P observe() vs the real `core.model.l2p.L2P` on `vit_pt_imnet` (fixture: tests/golden/l2p_vit.npz).
+    One task only here (the generator checked both) to keep the CPU suite short."""
+    from tests.golden_util import l2p_oracle_step, synth_images, synth_vit_state
+    g = load("l2p_vit.npz")
+    torch.set_num_threads(8)
+    p, prm, key, fc_w, fc_b = synth_vit_state(5150)
+    x, y = synth_images(601, 4, 10, 20)
+    o = l2p_oracle_step(p, prm, key, fc_w, fc_b, x, y, 10, 20)
+    assert np.array_equal(o["major"].numpy(), g["t1/major"])
+    assert abs(float(o["loss"]) - float(g["t1/loss"])) < 1e-5
+    for k in ("logits", "dprompt", "dkey", "dW", "db", "cls_features", "feat"):
+        ref = torch.from_numpy(g["t1/" + k])
+        err = float((o[k] - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
+        assert err < 1e-4, (k, err)
