@@ -153,7 +153,7 @@ int lc_ncm_classify(const float* feat, const float* means, int batch, int ncls, 
 int lc_gemm_bf16(const void* A, int lda, long long strideA, const void* B, int ldb, long long strideB, void* C, int ldc, long long strideC, int M, int N,
                  int K, int batch, const float* bias, const float* residual, int ldr, long long strideR, void* out2, int out_f32, float alpha,
                  int* error_flag, lc_stream_t stream);
-/* Same GEMM with a two-level batch (z = z_out * batch_in + z_in; every operand has an inner and an outer batch stride): the per-head
+/* Same GEMM with a two-level batch (z = z_out * batch_in + z_in; every operand has an inner and an outer batch stride; a stride of 0 shares the operand across that batch level): the per-head
  * attention GEMMs (Q K^T, P V) read strided views of the fused QKV buffer [B][T][3][H][64] and write [B][T][H*64] without copies. */
 typedef struct lc_gemm_desc {
     const void* A; long long lda, strideA_in, strideA_out;
@@ -170,7 +170,7 @@ int lc_gemm_bf16_ex(const lc_gemm_desc* desc, int* error_flag, lc_stream_t strea
  * padding columns zeroed), V -> V^T per head, mean over a row range (L2P: the prompt positions, transformer.py:2256-2259), fp32 linear head,
  * fp32 -> bf16 cast. */
 int lc_vit_patchify(const float* img_nchw, void* out_bf16, int batch, lc_stream_t stream);
-int lc_vit_set_row(float* x, long long batch_stride, int batch, int row, const float* src, const float* add, int dim, lc_stream_t stream);
+int lc_vit_set_rows(float* x, long long batch_stride, int batch, int row0, int nrows, const float* src, const float* add, int dim, lc_stream_t stream);
 int lc_layernorm_forward(const float* x, const float* gamma, const float* beta, float eps, long long rows, int dim, void* out_bf16, float* out_f32,
                          float* stat, lc_stream_t stream);
 int lc_softmax_rows(const float* S, void* P_bf16, long long rows, int T, int ld, lc_stream_t stream);

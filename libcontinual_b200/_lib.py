@@ -59,7 +59,7 @@ SIGNATURES = {
                              c_float, P, P]),
     "lc_gemm_bf16_ex": (c_int, [P, P, P]),
     "lc_vit_patchify": (c_int, [P, P, c_int, P]),
-    "lc_vit_set_row": (c_int, [P, c_longlong, c_int, c_int, P, P, c_int, P]),
+    "lc_vit_set_rows": (c_int, [P, c_longlong, c_int, c_int, c_int, P, P, c_int, P]),
     "lc_layernorm_forward": (c_int, [P, P, P, c_float, c_longlong, c_int, P, P, P, P]),
     "lc_softmax_rows": (c_int, [P, P, c_longlong, c_int, c_int, P]),
     "lc_vit_transpose_v": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),

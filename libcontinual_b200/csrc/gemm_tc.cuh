@@ -30,6 +30,7 @@ struct GemmArgs {
     int ldc, ldr;
     long long c_stride_in, c_stride_out, r_stride_in, r_stride_out;   // elements; batch index z = z_out * batch_in + z_in
     int batch_in;
+    int a_bcast, b_bcast;      // bit 0 / bit 1: the operand is shared across the inner / outer batch (its tensor map has extent 1 there)
     int out_dtype;
     float alpha;               // scale applied to the accumulator before bias (attention: 1/sqrt(d))
     int* error_flag;
@@ -98,8 +99,8 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_kernel(const __grid_constant
                 mbar_wait(empty + s, ph ^ 1u);                                     // slot free (first lap passes immediately)
                 mbar_expect_tx(full + s, (uint32_t)K::STAGE_BYTES);
                 const uint32_t sa = base_u + (uint32_t)s * K::STAGE_BYTES;
-                tma_load_4d(sa, &tmA, full + s, kb * K::BK, m0, z_in, z_out);
-                tma_load_4d(sa + K::A_BYTES, &tmB, full + s, kb * K::BK, n0, z_in, z_out);
+                tma_load_4d(sa, &tmA, full + s, kb * K::BK, m0, (a.a_bcast & 1) ? 0 : z_in, (a.a_bcast & 2) ? 0 : z_out);
+                tma_load_4d(sa + K::A_BYTES, &tmB, full + s, kb * K::BK, n0, (a.b_bcast & 1) ? 0 : z_in, (a.b_bcast & 2) ? 0 : z_out);
             }
         }
     } else if (warp == 1) {

@@ -22,11 +22,15 @@ EncodeTiledFn get_encode() {
 }
 
 // rank-4 bf16 tensor map {K (contiguous), rows, inner batch, outer batch}, box {64, box_rows, 1, 1}, 128-byte swizzle, zero fill out of bounds
-int make_tmap(CUtensorMap* m, const void* ptr, int K, int rows, int b_in, int b_out, long long ld, long long s_in, long long s_out, int box_rows) {
+int make_tmap(CUtensorMap* m, const void* ptr, int K, int rows, int b_in, int b_out, long long ld, long long s_in, long long s_out, int box_rows,
+              int* bcast) {
     EncodeTiledFn enc = get_encode();
     if (enc == nullptr) return LC_ERR_CUDA;
+    *bcast = 0;
+    if (b_in > 1 && s_in == 0) { *bcast |= 1; b_in = 1; }       // operand shared across the batch: extent 1, the kernel passes coordinate 0
+    if (b_out > 1 && s_out == 0) { *bcast |= 2; b_out = 1; }
     if (b_in <= 1) s_in = (long long)rows * ld;
-    if (b_out <= 1) s_out = (b_in <= 1 ? (long long)rows * ld : s_in * b_in);
+    if (b_out <= 1) s_out = s_in * (b_in < 1 ? 1 : b_in);
     cuuint64_t gdim[4] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(b_in < 1 ? 1 : b_in), (cuuint64_t)(b_out < 1 ? 1 : b_out)};
     cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)s_in * 2, (cuuint64_t)s_out * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
@@ -68,11 +72,11 @@ int lc_gemm_bf16_ex(const lc_gemm_desc* d, int* error_flag, lc_stream_t stream) 
     LC_CHECK_ARG(d->residual == nullptr || (d->ldr % 4 == 0 && d->strideR_in % 4 == 0 && d->strideR_out % 4 == 0));
     CUtensorMap ta, tb;
     const int bn = d->N > 128 ? 256 : 128;
-    int e = make_tmap(&ta, d->A, d->K, d->M, d->batch_in, d->batch_out, d->lda, d->strideA_in, d->strideA_out, 128);
-    if (e != LC_OK) return e;
-    e = make_tmap(&tb, d->B, d->K, d->N, d->batch_in, d->batch_out, d->ldb, d->strideB_in, d->strideB_out, bn);
-    if (e != LC_OK) return e;
     tc::GemmArgs a{};
+    int e = make_tmap(&ta, d->A, d->K, d->M, d->batch_in, d->batch_out, d->lda, d->strideA_in, d->strideA_out, 128, &a.a_bcast);
+    if (e != LC_OK) return e;
+    e = make_tmap(&tb, d->B, d->K, d->N, d->batch_in, d->batch_out, d->ldb, d->strideB_in, d->strideB_out, bn, &a.b_bcast);
+    if (e != LC_OK) return e;
     a.out = d->C; a.bias = d->bias; a.residual = d->residual; a.out2 = d->out2; a.M = d->M; a.N = d->N; a.K = d->K; a.ldc = (int)d->ldc; a.ldr = (int)d->ldr;
     a.c_stride_in = d->strideC_in; a.c_stride_out = d->strideC_out; a.r_stride_in = d->strideR_in; a.r_stride_out = d->strideR_out;
     a.batch_in = d->batch_in; a.out_dtype = d->out_f32 ? tc::GEMM_OUT_F32 : tc::GEMM_OUT_BF16; a.alpha = d->alpha; a.error_flag = error_flag;
@@ -95,9 +99,9 @@ int lc_vit_patchify(const float* img, void* out_bf16, int batch, lc_stream_t str
     patchify_kernel<<<grid_for((long long)batch * 196 * 96, 256), 256, 0, (cudaStream_t)stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out_bf16), batch);
     return lc_launch_status();
 }
-int lc_vit_set_row(float* x, long long batch_stride, int batch, int row, const float* src, const float* add, int dim, lc_stream_t stream) {
-    LC_CHECK_ARG(x && src && batch >= 1 && dim % 4 == 0);
-    set_row_kernel<<<batch, 192, 0, (cudaStream_t)stream>>>(x, batch_stride, row, src, add, dim);
+int lc_vit_set_rows(float* x, long long batch_stride, int batch, int row0, int nrows, const float* src, const float* add, int dim, lc_stream_t stream) {
+    LC_CHECK_ARG(x && src && batch >= 1 && nrows >= 1 && dim % 4 == 0);
+    set_rows_kernel<<<dim3(batch, nrows), 192, 0, (cudaStream_t)stream>>>(x, batch_stride, row0, src, add, dim);
     return lc_launch_status();
 }
 int lc_layernorm_forward(const float* x, const float* gamma, const float* beta, float eps, long long rows, int dim, void* out_bf16, float* out_f32,

@@ -26,13 +26,14 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* img, __nv_bf
     }
 }
 
-// x[b][row][:] = src[:] (+ add[:])   for every batch element: the cls token row (cls_token + pos_embed[0])
-__global__ void __launch_bounds__(192) set_row_kernel(float* x, long long batch_stride, int row, const float* src, const float* add, int D) {
-    const int b = blockIdx.x;
+// x[b][row0 + r][:] = src[r][:] (+ add[r][:])   for every batch element: the cls token row (cls_token + pos_embed[0]) and the shared
+// L2P prompt rows in front of it
+__global__ void __launch_bounds__(192) set_rows_kernel(float* x, long long batch_stride, int row0, const float* src, const float* add, int D) {
+    const int b = blockIdx.x, r = blockIdx.y;
     for (int j = threadIdx.x * 4; j < D; j += 192 * 4) {
-        float4 v = ldg4(src + j);
-        if (add != nullptr) { const float4 a = ldg4(add + j); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
-        *reinterpret_cast<float4*>(x + (size_t)b * batch_stride + (size_t)row * D + j) = v;
+        float4 v = ldg4(src + (size_t)r * D + j);
+        if (add != nullptr) { const float4 a = ldg4(add + (size_t)r * D + j); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+        *reinterpret_cast<float4*>(x + (size_t)b * batch_stride + (size_t)(row0 + r) * D + j) = v;
     }
 }
 

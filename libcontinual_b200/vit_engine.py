@@ -1,0 +1,219 @@
+"""Device-side state and kernel sequencing for the ViT-B/16 hot path (L2P / prompt methods: frozen backbone, trainable prompts + head).
+
+`ViTEngine` owns the frozen backbone weights (fp32 master copy for the row-wise kernels, BF16 copies in both orientations for the
+tcgen05 GEMMs), per-(batch, tokens) activation workspaces and the launch sequence of
+`VisionTransformer.forward(prompt_flag='l2p')` (core/model/backbone/transformer.py:2222-2261):
+
+    patchify -> patch-embed GEMM (+bias +pos_embed) -> [prompts | cls | patches]
+    12 x { LN1 -> QKV GEMM -> S = QK^T/8 -> softmax -> P V -> proj GEMM (+residual) -> LN2 -> fc1 GEMM (+GELU) -> fc2 GEMM (+residual) }
+    final LN (eps 1e-6)
+
+and of its backward with respect to the INPUT tokens only (the backbone is frozen: l2p.py:66-71), which is what carries the loss
+gradient back to the prompt rows.  The residual stream is fp32; GEMM operands, the stored QKV / probabilities / GELU outputs are BF16;
+accumulation is fp32 in TMEM.  Everything here is launch plumbing: torch supplies device memory and streams, every FLOP runs in
+`liblc_b200.so`.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, check, stream_ptr
+
+DIM, HEADS, HDIM, MLP, GRID, PATCHES = 768, 12, 64, 3072, 14, 196
+
+
+def vit_param_layout(depth: int = 12):
+    """(name, shape) in the reference `VisionTransformer` registration order (transformer.py:2186-2205, block: :1320-1326)."""
+    out = [("cls_token", (1, 1, DIM)), ("pos_embed", (1, PATCHES + 1, DIM)), ("patch_embed.proj.weight", (DIM, 3, 16, 16)),
+           ("patch_embed.proj.bias", (DIM,))]
+    for i in range(depth):
+        b = f"transformer.blocks.{i}."
+        out += [(b + "attn.qkv.weight", (3 * DIM, DIM)), (b + "attn.qkv.bias", (3 * DIM,)), (b + "attn.proj.weight", (DIM, DIM)),
+                (b + "attn.proj.bias", (DIM,)), (b + "ln_1.weight", (DIM,)), (b + "ln_1.bias", (DIM,)), (b + "mlp.fc1.weight", (MLP, DIM)),
+                (b + "mlp.fc1.bias", (MLP,)), (b + "mlp.fc2.weight", (DIM, MLP)), (b + "mlp.fc2.bias", (DIM,)), (b + "ln_2.weight", (DIM,)),
+                (b + "ln_2.bias", (DIM,))]
+    out += [("norm.weight", (DIM,)), ("norm.bias", (DIM,))]
+    return out
+
+
+def _up8(v: int) -> int:
+    return (v + 7) // 8 * 8
+
+
+class _Workspace:
+    """Activation buffers of one (batch, tokens) shape.  With `save` every block keeps what its backward needs:
+    x_in / x_mid (LayerNorm inputs), qkv, P (probabilities), pre-GELU fc1 output."""
+
+    def __init__(self, B: int, T: int, depth: int, save: bool, dev):
+        self.B, self.T, self.Tp, self.save = B, T, _up8(T), save
+        bf, f32 = torch.bfloat16, torch.float32
+        n = B * T
+        nx = depth + 1 if save else 2
+        self.x = [torch.empty(B, T, DIM, device=dev, dtype=f32) for _ in range(nx)]          # block inputs (x[depth] = last block's output)
+        self.xmid = [torch.empty(B, T, DIM, device=dev, dtype=f32) for _ in range(depth if save else 1)]
+        self.qkv = [torch.empty(n, 3 * DIM, device=dev, dtype=bf) for _ in range(depth if save else 1)]
+        self.P = [torch.empty(B * HEADS, T, self.Tp, device=dev, dtype=bf) for _ in range(depth if save else 1)]
+        self.upre = [torch.empty(n, MLP, device=dev, dtype=bf) for _ in range(depth if save else 1)]
+        self.patches = torch.empty(B * PATCHES, DIM, device=dev, dtype=bf)
+        self.h = torch.empty(n, DIM, device=dev, dtype=bf)
+        self.S = torch.empty(B * HEADS, T, self.Tp, device=dev, dtype=f32)
+        self.vt = torch.empty(B * HEADS, HDIM, self.Tp, device=dev, dtype=bf)
+        self.o = torch.empty(n, DIM, device=dev, dtype=bf)
+        self.u = torch.empty(n, MLP, device=dev, dtype=bf)
+        self.y = torch.empty(B, T, DIM, device=dev, dtype=f32)
+        self.ystat = torch.empty(n, 2, device=dev, dtype=f32)
+        self.feat = torch.empty(B, DIM, device=dev, dtype=f32)
+
+    def idx(self, layer: int) -> int:
+        return layer if self.save else 0
+
+
+class ViTEngine:
+    def __init__(self, depth: int = 12, device=None):
+        self.lib = _lib.load()
+        self.dev = torch.device(device if device is not None else "cuda:0")
+        if self.dev.type != "cuda":
+            raise _lib.LcError("ViTEngine needs a CUDA device: there is no CPU path")
+        self.depth = depth
+        self.layout = vit_param_layout(depth)
+        self.w: Dict[str, torch.Tensor] = {}          # fp32 master (frozen)
+        self.wb: Dict[str, torch.Tensor] = {}         # bf16 [N, K]   (forward B operand)
+        self.wbt: Dict[str, torch.Tensor] = {}        # bf16 [K, N]   (backward-data B operand)
+        self.err = torch.zeros(1, device=self.dev, dtype=torch.int32)
+        self._ws: Dict[tuple, _Workspace] = {}
+        self.launches = 0
+
+    # ---- weights -------------------------------------------------------------------------------
+    def load_state(self, state: Dict[str, torch.Tensor]):
+        """`state`: the reference `VisionTransformer.state_dict()` (keys as in `vit_param_layout`; `ViTZoo` maps timm names onto them:
+        vit.py:70-84)."""
+        for name, shape in self.layout:
+            t = state[name].detach().to(self.dev, torch.float32).contiguous()
+            assert tuple(t.shape) == tuple(shape), (name, t.shape, shape)
+            self.w[name] = t
+        gemm_w = ["patch_embed.proj.weight"] + [f"transformer.blocks.{i}.{n}.weight" for i in range(self.depth)
+                                                 for n in ("attn.qkv", "attn.proj", "mlp.fc1", "mlp.fc2")]
+        for name in gemm_w:
+            w2 = self.w[name].reshape(self.w[name].shape[0], -1)
+            self.wb[name] = self._cast(w2)
+            if name != "patch_embed.proj.weight":
+                self.wbt[name] = self._cast(w2.t().contiguous())
+        self.pos_rest = self.w["pos_embed"][0, 1:].contiguous()
+        self.pos_cls = self.w["pos_embed"][0, 0].contiguous()
+        self.cls = self.w["cls_token"].reshape(DIM).contiguous()
+
+    def _cast(self, t: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(t.shape, device=self.dev, dtype=torch.bfloat16)
+        check(self.lib.lc_cast_bf16(t.data_ptr(), out.data_ptr(), t.numel(), stream_ptr()), "cast_bf16")
+        return out
+
+    def workspace(self, B: int, T: int, save: bool) -> _Workspace:
+        key = (B, T, save)
+        if key not in self._ws:
+            self._ws[key] = _Workspace(B, T, self.depth, save, self.dev)
+        return self._ws[key]
+
+    def tensor_core_error(self) -> bool:
+        """True if any tcgen05 kernel hit an mbarrier timeout (it then wrote nothing useful)."""
+        return bool(self.err.item())
+
+    # ---- GEMM plumbing -------------------------------------------------------------------------
+    def gemm(self, A, lda, B, ldb, C, ldc, M, N, K, *, sA=(0, 0), sB=(0, 0), sC=(0, 0), batch=(1, 1), bias=None, residual=None, ldr=0, sR=(0, 0),
+             out2=None, out_f32=False, alpha=1.0):
+        """C[z] = alpha * A[z] @ B[z]^T (+bias +residual); A/B/C/residual/out2 are raw device addresses (ints), strides in elements."""
+        d = GemmDesc()
+        d.A, d.lda, d.strideA_in, d.strideA_out = A, lda, sA[0], sA[1]
+        d.B, d.ldb, d.strideB_in, d.strideB_out = B, ldb, sB[0], sB[1]
+        d.C, d.ldc, d.strideC_in, d.strideC_out = C, ldc, sC[0], sC[1]
+        d.bias, d.residual, d.ldr, d.strideR_in, d.strideR_out = bias, residual, ldr, sR[0], sR[1]
+        d.out2 = out2
+        d.M, d.N, d.K, d.batch_in, d.batch_out, d.out_f32, d.alpha = M, N, K, batch[0], batch[1], int(out_f32), alpha
+        check(self.lib.lc_gemm_bf16_ex(ctypes.byref(d), self.err.data_ptr(), stream_ptr()), f"gemm {M}x{N}x{K}")
+        self.launches += 1
+
+    def _linear(self, a_bf16: torch.Tensor, wname: str, out: torch.Tensor, *, bias=None, residual=None, out2=None, rows=None):
+        w = self.wb[wname]
+        N, K = w.shape
+        M = a_bf16.shape[0] if rows is None else rows
+        self.gemm(a_bf16.data_ptr(), K, w.data_ptr(), K, out.data_ptr(), N, M, N, K, bias=None if bias is None else self.w[bias].data_ptr(),
+                  residual=None if residual is None else residual.data_ptr(), ldr=N, out2=None if out2 is None else out2.data_ptr(),
+                  out_f32=out.dtype == torch.float32)
+
+    def _ln(self, x: torch.Tensor, wname: str, eps: float, out_bf16=None, out_f32=None, stat=None):
+        rows = x.numel() // DIM
+        check(self.lib.lc_layernorm_forward(x.data_ptr(), self.w[wname + ".weight"].data_ptr(), self.w[wname + ".bias"].data_ptr(), eps, rows, DIM,
+                                            None if out_bf16 is None else out_bf16.data_ptr(), None if out_f32 is None else out_f32.data_ptr(),
+                                            None if stat is None else stat.data_ptr(), stream_ptr()), "layernorm")
+        self.launches += 1
+
+    # ---- forward -------------------------------------------------------------------------------
+    def embed(self, img: torch.Tensor, prompts: Optional[torch.Tensor], ws: _Workspace):
+        """Tokens [prompts (shared by the batch) | cls + pos[0] | patches + pos[1:]] into ws.x[0]."""
+        B, T = ws.B, ws.T
+        Pn = 0 if prompts is None else prompts.shape[0]
+        assert T == Pn + PATCHES + 1 and img.shape == (B, 3, 224, 224) and img.is_contiguous() and img.dtype == torch.float32
+        st = stream_ptr()
+        x0 = ws.x[0]
+        check(self.lib.lc_vit_patchify(img.data_ptr(), ws.patches.data_ptr(), B, st), "patchify")
+        w = self.wb["patch_embed.proj.weight"]
+        self.gemm(ws.patches.data_ptr(), DIM, w.data_ptr(), DIM, x0.data_ptr() + (Pn + 1) * DIM * 4, DIM, PATCHES, DIM, DIM, sA=(PATCHES * DIM, 0),
+                  sC=(T * DIM, 0), batch=(B, 1), bias=self.w["patch_embed.proj.bias"].data_ptr(), residual=self.pos_rest.data_ptr(), ldr=DIM, out_f32=True)
+        check(self.lib.lc_vit_set_rows(x0.data_ptr(), T * DIM, B, Pn, 1, self.cls.data_ptr(), self.pos_cls.data_ptr(), DIM, st), "cls row")
+        if Pn:
+            assert prompts.is_contiguous() and prompts.dtype == torch.float32 and prompts.shape[1] == DIM
+            check(self.lib.lc_vit_set_rows(x0.data_ptr(), T * DIM, B, 0, Pn, prompts.data_ptr(), None, DIM, st), "prompt rows")
+        self.launches += 3 + (1 if Pn else 0)
+
+    def block_forward(self, i: int, ws: _Workspace):
+        B, T, Tp = ws.B, ws.T, ws.Tp
+        st = stream_ptr()
+        pre = f"transformer.blocks.{i}."
+        k = ws.idx(i)
+        xin = ws.x[i] if ws.save else ws.x[i % 2]
+        xout = ws.x[i + 1] if ws.save else ws.x[(i + 1) % 2]
+        xmid, qkv, P, upre = ws.xmid[k], ws.qkv[k], ws.P[k], ws.upre[k]
+        self._ln(xin, pre + "ln_1", 1e-5, out_bf16=ws.h)
+        self._linear(ws.h, pre + "attn.qkv.weight", qkv, bias=pre + "attn.qkv.bias")
+        q = qkv.data_ptr()
+        # S[b,h] = Q K^T / 8 : strided views of the fused QKV buffer [B][T][3][H][64]
+        self.gemm(q, 3 * DIM, q + DIM * 2, 3 * DIM, ws.S.data_ptr(), Tp, T, T, HDIM, sA=(HDIM, T * 3 * DIM), sB=(HDIM, T * 3 * DIM),
+                  sC=(T * Tp, HEADS * T * Tp), batch=(HEADS, B), out_f32=True, alpha=HDIM ** -0.5)
+        check(self.lib.lc_softmax_rows(ws.S.data_ptr(), P.data_ptr(), B * HEADS * T, T, Tp, st), "softmax")
+        check(self.lib.lc_vit_transpose_v(q, ws.vt.data_ptr(), B, T, HEADS, Tp, st), "transpose_v")
+        # O[b,:,h*64:(h+1)*64] = P[b,h] V[b,h]
+        self.gemm(P.data_ptr(), Tp, ws.vt.data_ptr(), Tp, ws.o.data_ptr(), DIM, T, HDIM, Tp, sA=(T * Tp, HEADS * T * Tp), sB=(HDIM * Tp, HEADS * HDIM * Tp),
+                  sC=(HDIM, T * DIM), batch=(HEADS, B))
+        self._linear(ws.o, pre + "attn.proj.weight", xmid, bias=pre + "attn.proj.bias", residual=xin)
+        self._ln(xmid, pre + "ln_2", 1e-5, out_bf16=ws.h)
+        self._linear(ws.h, pre + "mlp.fc1.weight", upre, bias=pre + "mlp.fc1.bias", out2=ws.u)
+        self._linear(ws.u, pre + "mlp.fc2.weight", xout, bias=pre + "mlp.fc2.bias", residual=xmid)
+        self.launches += 2
+
+    def forward(self, img: torch.Tensor, prompts: Optional[torch.Tensor] = None, save: bool = False) -> _Workspace:
+        """Runs the backbone; returns the workspace (ws.y = final-LayerNorm tokens fp32 [B, T, 768])."""
+        B = img.shape[0]
+        T = PATCHES + 1 + (0 if prompts is None else prompts.shape[0])
+        ws = self.workspace(B, T, save)
+        self.embed(img, prompts, ws)
+        for i in range(self.depth):
+            self.block_forward(i, ws)
+        last = ws.x[self.depth] if save else ws.x[self.depth % 2]
+        self._ln(last, "norm", 1e-6, out_f32=ws.y, stat=ws.ystat if save else None)
+        return ws
+
+    def pooled(self, ws: _Workspace, n_prompt: int) -> torch.Tensor:
+        """Mean over the prompt positions of the normalised tokens (transformer.py:2255-2258), or the cls row without prompts (:2260)."""
+        check(self.lib.lc_vit_pool_rows(ws.y.data_ptr(), ws.T * DIM, ws.B, 0, max(n_prompt, 1), DIM, ws.feat.data_ptr(), stream_ptr()), "pool_rows")
+        self.launches += 1
+        return ws.feat
+
+    def linear_head(self, feat: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], logits: torch.Tensor):
+        B, C = feat.shape[0], W.shape[0]
+        check(self.lib.lc_linear_head(feat.data_ptr(), W.data_ptr(), None if bias is None else bias.data_ptr(), B, C, DIM, logits.data_ptr(),
+                                      logits.stride(0), stream_ptr()), "linear_head")
+        self.launches += 1
+        return logits
