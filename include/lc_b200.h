@@ -80,6 +80,10 @@ int lc_head_forward(const float* act_nhwc, int batch, int hw, int feat_dim, cons
                     float* feat, float* logits, int ldl, lc_stream_t stream);
 int lc_loss_ce_kd(const float* logits, int ldl, const float* teacher, int ldt, const int64_t* y, int batch, int ce_lo, int ce_hi,
                   int kd_n, float kd_w, float T, int pred_n, float* dlogits, int64_t* pred, float* scal, lc_stream_t stream);
+/* L2P's masked loss (l2p.py:89-106): logits outside [lo, hi) are -inf, so CE and argmax run over the slice; scal[0] = CE + extra_coeff * *extra
+ * (the pull-constraint term, extra = reduce_sim of lc_l2p_select, extra_coeff = -pull_constraint_coeff). */
+int lc_loss_ce_masked(const float* logits, int ldl, const int64_t* y, int batch, int lo, int hi, const float* extra, float extra_coeff, float* dlogits,
+                      int64_t* pred, float* scal, lc_stream_t stream);
 int lc_head_backward(const float* dlogits, int ldl, const float* feat, const float* W, int ncls, int batch, int feat_dim, float* dW,
                      float* db, float* dfeat, float* gact, int hw, lc_stream_t stream);
 /* Stand-alone nn.AvgPool2d(8)+flatten and its backward, for callers that keep their own head on backbone(x)['features']. */
@@ -161,23 +165,39 @@ typedef struct lc_gemm_desc {
     void* C; long long ldc, strideC_in, strideC_out;
     const float* bias; const float* residual; long long ldr, strideR_in, strideR_out;
     void* out2;
+    const void* gelu_bwd_aux;   /* nullable bf16 indexed like C: result *= GELU'(aux) */
     int M, N, K, batch_in, batch_out, out_f32;
     float alpha;
 } lc_gemm_desc;
 int lc_gemm_bf16_ex(const lc_gemm_desc* desc, int* error_flag, lc_stream_t stream);
 /* Row-wise / layout kernels of the ViT forward (transformer.py:2222-2261): im2col of the 16x16 patches (timm PatchEmbed as a GEMM), cls-row
  * assembly, LayerNorm (fp32 in -> bf16 and/or fp32 out, optional (mean, rstd) per row), row softmax (fp32 scores -> bf16 probabilities,
- * padding columns zeroed), V -> V^T per head, mean over a row range (L2P: the prompt positions, transformer.py:2256-2259), fp32 linear head,
+ * padding columns zeroed), one head slice of a token-major buffer -> [B*H][64][tokens] (V^T, K^T, Q^T, dO^T), mean over a row range (L2P: the prompt positions, transformer.py:2256-2259), fp32 linear head,
  * fp32 -> bf16 cast. */
 int lc_vit_patchify(const float* img_nchw, void* out_bf16, int batch, lc_stream_t stream);
 int lc_vit_set_rows(float* x, long long batch_stride, int batch, int row0, int nrows, const float* src, const float* add, int dim, lc_stream_t stream);
 int lc_layernorm_forward(const float* x, const float* gamma, const float* beta, float eps, long long rows, int dim, void* out_bf16, float* out_f32,
                          float* stat, lc_stream_t stream);
 int lc_softmax_rows(const float* S, void* P_bf16, long long rows, int T, int ld, lc_stream_t stream);
-int lc_vit_transpose_v(const void* qkv_bf16, void* vt_bf16, int batch, int T, int heads, int ld, lc_stream_t stream);
+int lc_vit_transpose_heads(const void* in_bf16, long long row_stride, int col0, void* out_bf16, int batch, int T, int heads, int ld, lc_stream_t stream);
+/* Backward of the frozen backbone wrt its input tokens (what carries the loss to the L2P prompt rows; the backbone itself has
+ * requires_grad=False: l2p.py:66-71): LayerNorm backward fused with the residual-path gradient (dh either dense fp32 or the pooled-feature
+ * gradient broadcast over the first n_active rows of every image), softmax backward per row, T x T batched transpose (P^T, dS^T are the
+ * A operands of dV / dK), and the batch sum of the shared prompt rows. */
+int lc_layernorm_backward(const float* dh, const float* dh_pool, int T, int n_active, const float* x, const float* gamma, float eps, long long rows, int dim,
+                          const float* res, float* out_f32, void* out_bf16, lc_stream_t stream);
+int lc_softmax_backward_rows(const void* P_bf16, const float* dP, void* dS_bf16, long long rows, int T, int ld, lc_stream_t stream);
+int lc_transpose_tt(const void* in_bf16, void* out_bf16, long long nmat, int T, int ld, lc_stream_t stream);
+int lc_sum_batch_rows(const float* x, long long batch_stride, int batch, int nrows, int dim, float* out, lc_stream_t stream);
 int lc_vit_pool_rows(const float* y, long long batch_stride, int batch, int r0, int nr, int dim, float* feat, lc_stream_t stream);
 int lc_linear_head(const float* feat, const float* W, const float* bias, int batch, int ncls, int dim, float* logits, int ld, lc_stream_t stream);
 int lc_cast_bf16(const float* in, void* out_bf16, long long n, lc_stream_t stream);
+/* nn.Linear classifier backward on a wide feature (l2p.py:31-40), and the L2P parameter gradients: the prompt-row gradient scattered into the
+ * pool layout [pool][length][dim] (zero elsewhere) and dkey_out = coeff * dkey_in. */
+int lc_linear_head_backward(const float* dlogits, int ldl, const float* feat, const float* W, int ncls, int batch, int dim, float* dW, float* db,
+                            float* dfeat, lc_stream_t stream);
+int lc_l2p_backward(const float* dprompts, const int64_t* ids, int pool, int top_k, int length, int dim, float* dpool, const float* dkey_in, float coeff,
+                    float* dkey_out, lc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------------
  * Per-kernel entry points (unit-tested individually; the network-level calls above are compositions of these).

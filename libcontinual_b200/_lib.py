@@ -62,10 +62,17 @@ SIGNATURES = {
     "lc_vit_set_rows": (c_int, [P, c_longlong, c_int, c_int, c_int, P, P, c_int, P]),
     "lc_layernorm_forward": (c_int, [P, P, P, c_float, c_longlong, c_int, P, P, P, P]),
     "lc_softmax_rows": (c_int, [P, P, c_longlong, c_int, c_int, P]),
-    "lc_vit_transpose_v": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "lc_vit_transpose_heads": (c_int, [P, c_longlong, c_int, P, c_int, c_int, c_int, c_int, P]),
+    "lc_layernorm_backward": (c_int, [P, P, c_int, c_int, P, P, c_float, c_longlong, c_int, P, P, P, P]),
+    "lc_softmax_backward_rows": (c_int, [P, P, P, c_longlong, c_int, c_int, P]),
+    "lc_transpose_tt": (c_int, [P, P, c_longlong, c_int, c_int, P]),
+    "lc_sum_batch_rows": (c_int, [P, c_longlong, c_int, c_int, c_int, P, P]),
     "lc_vit_pool_rows": (c_int, [P, c_longlong, c_int, c_int, c_int, c_int, P, P]),
     "lc_linear_head": (c_int, [P, P, P, c_int, c_int, c_int, P, c_int, P]),
     "lc_cast_bf16": (c_int, [P, P, c_longlong, P]),
+    "lc_linear_head_backward": (c_int, [P, c_int, P, P, c_int, c_int, c_int, P, P, P, P]),
+    "lc_l2p_backward": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, P]),
+    "lc_loss_ce_masked": (c_int, [P, c_int, P, c_int, c_int, c_int, P, c_float, P, P, P, P]),
     "lc_conv_scratch_floats": (c_longlong, [c_int, c_int, c_int, c_int]),
     "lc_conv3x3": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P]),
     "lc_conv3x3_packed": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
@@ -86,7 +93,7 @@ class GemmDesc(ctypes.Structure):
                 ("B", c_void_p), ("ldb", c_longlong), ("strideB_in", c_longlong), ("strideB_out", c_longlong),
                 ("C", c_void_p), ("ldc", c_longlong), ("strideC_in", c_longlong), ("strideC_out", c_longlong),
                 ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_longlong), ("strideR_in", c_longlong), ("strideR_out", c_longlong),
-                ("out2", c_void_p),
+                ("out2", c_void_p), ("gelu_bwd_aux", c_void_p),
                 ("M", c_int), ("N", c_int), ("K", c_int), ("batch_in", c_int), ("batch_out", c_int), ("out_f32", c_int),
                 ("alpha", c_float)]
 

@@ -26,6 +26,7 @@ struct GemmArgs {
     const float* bias;         // nullable [N]
     const float* residual;     // nullable fp32 [batch][M][ldr], added before the store
     void* out2;                // nullable bf16: GELU(out) (out then holds the pre-activation, needed by the backward)
+    const void* gelu_aux;      // nullable bf16, indexed like out: the result is multiplied by GELU'(gelu_aux) (fc2 backward-data -> d pre-activation)
     int M, N, K;
     int ldc, ldr;
     long long c_stride_in, c_stride_out, r_stride_in, r_stride_out;   // elements; batch index z = z_out * batch_in + z_in
@@ -52,6 +53,9 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float dgelu_erf(float x) {
+    return 0.5f * (1.f + erff(x * 0.70710678118654752440f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
 
 template <int BN>
 struct GemmCfg {
@@ -139,6 +143,7 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_kernel(const __grid_constant
                 for (int i = 0; i < 16 && n + i < a.N; ++i) {
                     float x = v[i] * a.alpha + (a.bias != nullptr ? a.bias[n + i] : 0.f);
                     if (a.residual != nullptr) x += a.residual[rrow + n + i];
+                    if (a.gelu_aux != nullptr) x *= dgelu_erf(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.gelu_aux)[crow + n + i]));
                     if (a.out_dtype == GEMM_OUT_F32) reinterpret_cast<float*>(a.out)[crow + n + i] = x;
                     else reinterpret_cast<__nv_bfloat16*>(a.out)[crow + n + i] = __float2bfloat16_rn(x);
                     if (a.out2 != nullptr) reinterpret_cast<__nv_bfloat16*>(a.out2)[crow + n + i] = __float2bfloat16_rn(gelu_erf(x));
@@ -158,6 +163,16 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_kernel(const __grid_constant
                     for (int k4 = 0; k4 < 4; ++k4) {
                         const float4 r4 = *reinterpret_cast<const float4*>(a.residual + rrow + n + k4 * 4);
                         v[k4 * 4] += r4.x; v[k4 * 4 + 1] += r4.y; v[k4 * 4 + 2] += r4.z; v[k4 * 4 + 3] += r4.w;
+                    }
+                }
+                if (a.gelu_aux != nullptr) {
+                    const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.gelu_aux) + crow + n);
+                    const uint4 a0 = ap[0], a1 = ap[1];
+                    const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        v[2 * i] *= dgelu_erf(__uint_as_float(aw[i] << 16));
+                        v[2 * i + 1] *= dgelu_erf(__uint_as_float(aw[i] & 0xffff0000u));
                     }
                 }
                 if (a.out_dtype == GEMM_OUT_F32) {

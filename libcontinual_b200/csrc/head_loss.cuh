@@ -42,7 +42,10 @@ struct LossArgs {
     int B, ldl, ldt, ncols;
     int ce_lo, ce_hi;       // CE over logits[:, ce_lo:ce_hi) with target y - ce_lo
     int kd_n;               // KD over logits[:, 0:kd_n) vs teacher[:, 0:kd_n)   (0 = off)
-    int pred_n;             // argmax over logits[:, 0:pred_n)
+    int pred_n;             // argmax over logits[:, pred_lo:pred_n)
+    int pred_lo;
+    const float* extra;     // nullable device scalar: scal[0] += extra_coeff * *extra (L2P pull constraint, l2p.py:99)
+    float extra_coeff;
     float kd_w, T;
 };
 
@@ -57,8 +60,8 @@ __global__ void __launch_bounds__(256) ce_kd_loss_kernel(LossArgs a) {
         float* dl = a.dlogits + (size_t)n * a.ldl;
         const int y = (int)a.y[n];
         // prediction (first maximal index)
-        float best = -CUDART_INF_F; int bi = 0;
-        for (int k = 0; k < a.pred_n; ++k) { const float v = lg[k]; if (v > best) { best = v; bi = k; } }
+        float best = -CUDART_INF_F; int bi = a.pred_lo;
+        for (int k = a.pred_lo; k < a.pred_n; ++k) { const float v = lg[k]; if (v > best) { best = v; bi = k; } }
         a.pred[n] = bi;
         ok_acc += (bi == y);
         for (int k = 0; k < a.ncols; ++k) dl[k] = 0.f;
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(256) ce_kd_loss_kernel(LossArgs a) {
     }
     if (threadIdx.x == 0) {
         const float ce = s_ce[0] * invB, kd = s_kd[0] * invB;
-        a.scal[0] = ce + a.kd_w * kd;
+        a.scal[0] = ce + a.kd_w * kd + (a.extra != nullptr ? a.extra_coeff * *a.extra : 0.f);
         a.scal[1] = (float)s_ok[0];
         a.scal[2] = ce;
         a.scal[3] = kd;

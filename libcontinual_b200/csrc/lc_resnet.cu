@@ -559,6 +559,16 @@ int lc_loss_ce_kd(const float* logits, int ldl, const float* teacher, int ldt, c
     return lc_launch_status();
 }
 
+int lc_loss_ce_masked(const float* logits, int ldl, const int64_t* y, int batch, int lo, int hi, const float* extra, float extra_coeff, float* dlogits,
+                      int64_t* pred, float* scal, lc_stream_t stream) {
+    LC_CHECK_ARG(logits && y && dlogits && pred && scal && batch >= 1 && lo >= 0 && hi > lo && hi <= ldl);
+    LossArgs a{};
+    a.logits = logits; a.y = reinterpret_cast<const long long*>(y); a.dlogits = dlogits; a.pred = reinterpret_cast<long long*>(pred); a.scal = scal;
+    a.B = batch; a.ldl = ldl; a.ncols = ldl; a.ce_lo = lo; a.ce_hi = hi; a.pred_lo = lo; a.pred_n = hi; a.extra = extra; a.extra_coeff = extra_coeff;
+    ce_kd_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
+    return lc_launch_status();
+}
+
 int lc_head_backward(const float* dlogits, int ldl, const float* feat, const float* W, int ncls, int batch, int feat_dim, float* dW, float* db,
                      float* dfeat, float* gact, int hw, lc_stream_t stream) {
     LC_CHECK_ARG(dlogits && feat && W && dW && dfeat && ncls >= 1 && batch >= 1 && feat_dim == 64 && ldl >= ncls);

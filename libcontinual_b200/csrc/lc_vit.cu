@@ -77,7 +77,7 @@ int lc_gemm_bf16_ex(const lc_gemm_desc* d, int* error_flag, lc_stream_t stream) 
     if (e != LC_OK) return e;
     e = make_tmap(&tb, d->B, d->K, d->N, d->batch_in, d->batch_out, d->ldb, d->strideB_in, d->strideB_out, bn, &a.b_bcast);
     if (e != LC_OK) return e;
-    a.out = d->C; a.bias = d->bias; a.residual = d->residual; a.out2 = d->out2; a.M = d->M; a.N = d->N; a.K = d->K; a.ldc = (int)d->ldc; a.ldr = (int)d->ldr;
+    a.out = d->C; a.bias = d->bias; a.residual = d->residual; a.out2 = d->out2; a.gelu_aux = d->gelu_bwd_aux; a.M = d->M; a.N = d->N; a.K = d->K; a.ldc = (int)d->ldc; a.ldr = (int)d->ldr;
     a.c_stride_in = d->strideC_in; a.c_stride_out = d->strideC_out; a.r_stride_in = d->strideR_in; a.r_stride_out = d->strideR_out;
     a.batch_in = d->batch_in; a.out_dtype = d->out_f32 ? tc::GEMM_OUT_F32 : tc::GEMM_OUT_BF16; a.alpha = d->alpha; a.error_flag = error_flag;
     const int batch = d->batch_in * d->batch_out;
@@ -116,11 +116,36 @@ int lc_softmax_rows(const float* S, void* P_bf16, long long rows, int T, int ld,
     softmax_rows_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(S, reinterpret_cast<__nv_bfloat16*>(P_bf16), rows, T, ld);
     return lc_launch_status();
 }
-int lc_vit_transpose_v(const void* qkv_bf16, void* vt_bf16, int batch, int T, int heads, int ld, lc_stream_t stream) {
-    LC_CHECK_ARG(qkv_bf16 && vt_bf16 && batch >= 1 && T >= 1 && heads >= 1 && ld >= T);
+int lc_vit_transpose_heads(const void* in_bf16, long long row_stride, int col0, void* out_bf16, int batch, int T, int heads, int ld, lc_stream_t stream) {
+    LC_CHECK_ARG(in_bf16 && out_bf16 && batch >= 1 && T >= 1 && heads >= 1 && ld >= T && col0 >= 0);
     dim3 grid((ld + 63) / 64, batch * heads);
-    transpose_v_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(vt_bf16), batch, T,
-                                                              heads, ld);
+    transpose_heads_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(in_bf16), row_stride, col0,
+                                                                  reinterpret_cast<__nv_bfloat16*>(out_bf16), batch, T, heads, ld);
+    return lc_launch_status();
+}
+int lc_transpose_tt(const void* in_bf16, void* out_bf16, long long nmat, int T, int ld, lc_stream_t stream) {
+    LC_CHECK_ARG(in_bf16 && out_bf16 && nmat >= 1 && nmat <= 65535 && T >= 1 && ld >= T);
+    dim3 grid((ld + 63) / 64, (T + 63) / 64, (unsigned)nmat);
+    transpose_tt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(in_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), T, ld);
+    return lc_launch_status();
+}
+int lc_layernorm_backward(const float* dh, const float* dh_pool, int T, int n_active, const float* x, const float* gamma, float eps, long long rows, int dim,
+                          const float* res, float* out_f32, void* out_bf16, lc_stream_t stream) {
+    LC_CHECK_ARG((dh != nullptr) != (dh_pool != nullptr) && x && gamma && rows >= 1 && dim == 768 && (out_f32 || out_bf16));
+    LC_CHECK_ARG(dh_pool == nullptr || (T >= 1 && n_active >= 1 && n_active <= T && rows % T == 0));
+    layernorm_bwd_kernel<768><<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(dh, dh_pool, T, n_active, x, gamma, eps, rows, res, out_f32,
+                                                                                       reinterpret_cast<__nv_bfloat16*>(out_bf16));
+    return lc_launch_status();
+}
+int lc_softmax_backward_rows(const void* P_bf16, const float* dP, void* dS_bf16, long long rows, int T, int ld, lc_stream_t stream) {
+    LC_CHECK_ARG(P_bf16 && dP && dS_bf16 && rows >= 1 && T >= 1 && ld >= T);
+    softmax_bwd_rows_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(P_bf16), dP,
+                                                                                         reinterpret_cast<__nv_bfloat16*>(dS_bf16), rows, T, ld);
+    return lc_launch_status();
+}
+int lc_sum_batch_rows(const float* x, long long batch_stride, int batch, int nrows, int dim, float* out, lc_stream_t stream) {
+    LC_CHECK_ARG(x && out && batch >= 1 && nrows >= 1 && dim % 4 == 0);
+    sum_batch_rows_kernel<<<nrows, 192, 0, (cudaStream_t)stream>>>(x, batch_stride, batch, dim, out);
     return lc_launch_status();
 }
 int lc_vit_pool_rows(const float* y, long long batch_stride, int batch, int r0, int nr, int dim, float* feat, lc_stream_t stream) {
@@ -131,6 +156,19 @@ int lc_vit_pool_rows(const float* y, long long batch_stride, int batch, int r0, 
 int lc_linear_head(const float* feat, const float* W, const float* bias, int batch, int ncls, int dim, float* logits, int ld, lc_stream_t stream) {
     LC_CHECK_ARG(feat && W && logits && batch >= 1 && ncls >= 1 && ld >= ncls);
     linear_head_kernel<<<(batch * ncls + 3) / 4, 128, 0, (cudaStream_t)stream>>>(feat, W, bias, batch, ncls, dim, logits, ld);
+    return lc_launch_status();
+}
+int lc_linear_head_backward(const float* dlogits, int ldl, const float* feat, const float* W, int ncls, int batch, int dim, float* dW, float* db,
+                            float* dfeat, lc_stream_t stream) {
+    LC_CHECK_ARG(dlogits && feat && W && dW && dfeat && ncls >= 1 && batch >= 1 && dim % 4 == 0 && ldl >= ncls);
+    linear_head_bwd_kernel<<<ncls + batch, 192, 0, (cudaStream_t)stream>>>(dlogits, ldl, feat, W, ncls, batch, dim, dW, db, dfeat);
+    return lc_launch_status();
+}
+int lc_l2p_backward(const float* dprompts, const int64_t* ids, int pool, int top_k, int length, int dim, float* dpool, const float* dkey_in, float coeff,
+                    float* dkey_out, lc_stream_t stream) {
+    LC_CHECK_ARG(dprompts && ids && dpool && dkey_in && dkey_out && pool >= 1 && top_k >= 1 && top_k <= pool && length >= 1 && dim % 4 == 0);
+    l2p_backward_kernel<<<pool * length + pool, 192, 0, (cudaStream_t)stream>>>(dprompts, reinterpret_cast<const long long*>(ids), pool, top_k, length, dim, dpool,
+                                                                             dkey_in, coeff, dkey_out);
     return lc_launch_status();
 }
 int lc_cast_bf16(const float* in, void* out_bf16, long long n, lc_stream_t stream) {

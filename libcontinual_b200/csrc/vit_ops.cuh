@@ -89,23 +89,6 @@ __global__ void __launch_bounds__(128) softmax_rows_kernel(const float* S, __nv_
     for (int j = lane; j < ld; j += 32) p[j] = __float2bfloat16_rn(j < T ? expf(s[j] - m) * inv : 0.f);
 }
 
-// V of the fused QKV buffer [B][T][3][H][64] (bf16) -> V^T [B*H][64][ld] (keys contiguous, padding keys zeroed): the K-major B operand of P.V
-__global__ void __launch_bounds__(256) transpose_v_kernel(const __nv_bfloat16* qkv, __nv_bfloat16* vt, int B, int T, int H, int ld) {
-    __shared__ __nv_bfloat16 tile[64][66];
-    const int bh = blockIdx.y, b = bh / H, h = bh % H;
-    const int t0 = blockIdx.x * 64;
-    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
-        const int tt = e / 64, d = e % 64;
-        const int t = t0 + tt;
-        tile[tt][d] = t < T ? qkv[((size_t)(b * T + t) * 3 + 2) * (H * 64) + h * 64 + d] : __float2bfloat16_rn(0.f);
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
-        const int d = e / 64, tt = e % 64;
-        if (t0 + tt < ld) vt[((size_t)bh * 64 + d) * ld + t0 + tt] = tile[tt][d];
-    }
-}
-
 // features[b][:] = mean over rows [r0, r0+nr) of y[b][:][:]  (L2P: the 25 prompt positions; otherwise the cls row) ; fp32
 __global__ void __launch_bounds__(192) pool_rows_kernel(const float* y, long long batch_stride, int r0, int nr, int D, float* feat) {
     const int b = blockIdx.x;
@@ -134,6 +117,185 @@ __global__ void __launch_bounds__(128) linear_head_kernel(const float* feat, con
 // fp32 -> bf16 cast (weights, once per load)
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* in, __nv_bfloat16* out, long long n) {
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+// ---- backward (input gradients only: the backbone is frozen, l2p.py:66-71) ------------------------------------------------------------
+
+// LayerNorm backward wrt its input, fused with the residual-path gradient:
+//   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dh * gamma ;   out = dx + res
+// dh is fp32 [rows][D], or — for the final LayerNorm in front of the L2P prompt-position mean (transformer.py:2253-2258) — the pooled
+// gradient broadcast: dh(row (b, t)) = t < n_active ? dfeat[b] / n_active : 0  (dh_pool = dfeat [B][D], T = tokens per image).
+// (mean, rstd) are recomputed from x (x is read anyway).  Writes fp32 and/or a BF16 copy (the A operand of the next backward GEMM).
+template <int D>
+__global__ void __launch_bounds__(128) layernorm_bwd_kernel(const float* dh, const float* dh_pool, int T, int n_active, const float* x, const float* gamma,
+                                                            float eps, long long rows, const float* res, float* out_f32, __nv_bfloat16* out_bf16) {
+    constexpr int PER = D / 32;
+    const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + (size_t)row * D;
+    float v[PER], g[PER];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < PER / 4; ++k) {
+        const float4 t = *reinterpret_cast<const float4*>(xr + (k * 32 + lane) * 4);
+        v[k * 4] = t.x; v[k * 4 + 1] = t.y; v[k * 4 + 2] = t.z; v[k * 4 + 3] = t.w;
+        s += t.x + t.y + t.z + t.w;
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] -= mean; q = fmaf(v[i], v[i], q); }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+    const float* dsrc = nullptr;
+    float dscale = 1.f;
+    if (dh != nullptr) dsrc = dh + (size_t)row * D;
+    else if ((int)(row % T) < n_active) { dsrc = dh_pool + (size_t)(row / T) * D; dscale = 1.f / (float)n_active; }
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int k = 0; k < PER / 4; ++k) {
+        const int j = (k * 32 + lane) * 4;
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dsrc != nullptr) d = *reinterpret_cast<const float4*>(dsrc + j);
+        const float4 gm = ldg4(gamma + j);
+        g[k * 4] = d.x * dscale * gm.x; g[k * 4 + 1] = d.y * dscale * gm.y; g[k * 4 + 2] = d.z * dscale * gm.z; g[k * 4 + 3] = d.w * dscale * gm.w;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[k * 4 + i] *= rstd; sg += g[k * 4 + i]; sgx = fmaf(g[k * 4 + i], v[k * 4 + i], sgx); }
+    }
+    const float mg = warp_sum(sg) / (float)D, mgx = warp_sum(sgx) / (float)D;
+#pragma unroll
+    for (int k = 0; k < PER / 4; ++k) {
+        const int j = (k * 32 + lane) * 4;
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = rstd * (g[k * 4 + i] - mg - v[k * 4 + i] * mgx);
+        if (res != nullptr) {
+            const float4 r = *reinterpret_cast<const float4*>(res + (size_t)row * D + j);
+            o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+        }
+        if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + (size_t)row * D + j) = make_float4(o[0], o[1], o[2], o[3]);
+        if (out_bf16 != nullptr) *reinterpret_cast<uint2*>(out_bf16 + (size_t)row * D + j) = make_uint2(pack2_bf16(o[0], o[1]), pack2_bf16(o[2], o[3]));
+    }
+}
+
+// softmax backward per row (the 1/sqrt(d) scale is folded into the dQ / dK GEMMs): dS = P * (dP - sum_j P_j dP_j) ; bf16, padding zeroed
+__global__ void __launch_bounds__(128) softmax_bwd_rows_kernel(const __nv_bfloat16* P, const float* dP, __nv_bfloat16* dS, long long rows, int T, int ld) {
+    const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const __nv_bfloat16* p = P + (size_t)row * ld;
+    const float* d = dP + (size_t)row * ld;
+    float s = 0.f;
+    for (int j = lane; j < T; j += 32) s = fmaf(__bfloat162float(p[j]), d[j], s);
+    s = warp_sum(s);
+    __nv_bfloat16* o = dS + (size_t)row * ld;
+    for (int j = lane; j < ld; j += 32) o[j] = __float2bfloat16_rn(j < T ? __bfloat162float(p[j]) * (d[j] - s) : 0.f);
+}
+
+// batched bf16 transpose of the T x T corner of [Z][T][ld] matrices into [Z][T][ld] (padding columns zeroed): P -> P^T, dS -> dS^T
+__global__ void __launch_bounds__(256) transpose_tt_kernel(const __nv_bfloat16* in, __nv_bfloat16* out, int T, int ld) {
+    __shared__ __nv_bfloat16 tile[64][66];
+    const size_t z = blockIdx.z;
+    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;       // input rows i0.., cols j0..
+    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+        const int r = e / 64, c = e % 64;
+        tile[r][c] = (i0 + r < T && j0 + c < T) ? in[(z * T + i0 + r) * ld + j0 + c] : __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+        const int r = e / 64, c = e % 64;                         // output row j0 + r, col i0 + c
+        if (j0 + r < T && i0 + c < ld) out[(z * T + j0 + r) * ld + i0 + c] = tile[c][r];
+    }
+}
+
+// one 64-wide head slice of a token-major bf16 buffer -> [B*H][64][ld] (tokens contiguous, padding zeroed):
+//   out[(b*H+h)][d][t] = in[(b*T+t)*row_stride + col0 + h*64 + d]        (V, K, Q of the fused QKV buffer; dO)
+__global__ void __launch_bounds__(256) transpose_heads_kernel(const __nv_bfloat16* in, long long row_stride, int col0, __nv_bfloat16* out, int B, int T, int H,
+                                                              int ld) {
+    __shared__ __nv_bfloat16 tile[64][66];
+    const int bh = blockIdx.y, b = bh / H, h = bh % H;
+    const int t0 = blockIdx.x * 64;
+    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+        const int tt = e / 64, d = e % 64;
+        const int t = t0 + tt;
+        tile[tt][d] = t < T ? in[(size_t)(b * T + t) * row_stride + col0 + h * 64 + d] : __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+        const int d = e / 64, tt = e % 64;
+        if (t0 + tt < ld) out[((size_t)bh * 64 + d) * ld + t0 + tt] = tile[tt][d];
+    }
+}
+
+// out[r][:] = sum over the batch of x[b][r][:]   (gradient of the shared prompt rows; fixed summation order)
+__global__ void __launch_bounds__(192) sum_batch_rows_kernel(const float* x, long long batch_stride, int B, int D, float* out) {
+    const int r = blockIdx.x;
+    for (int j = threadIdx.x * 4; j < D; j += 192 * 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = 0; b < B; ++b) {
+            const float4 t = *reinterpret_cast<const float4*>(x + (size_t)b * batch_stride + (size_t)r * D + j);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        *reinterpret_cast<float4*>(out + (size_t)r * D + j) = acc;
+    }
+}
+
+// nn.Linear backward for a wide feature (classifier on the 768-d pooled feature, l2p.py:31-40):
+//   blocks [0, ncls): dW[k][:] = sum_n dlogits[n][k] feat[n][:], db[k] ; blocks [ncls, ncls + B): dfeat[n][:] = sum_k dlogits[n][k] W[k][:]
+__global__ void __launch_bounds__(192) linear_head_bwd_kernel(const float* dlogits, int ldl, const float* feat, const float* W, int ncls, int B, int D,
+                                                              float* dW, float* db, float* dfeat) {
+    if ((int)blockIdx.x < ncls) {
+        const int k = blockIdx.x;
+        for (int j = threadIdx.x * 4; j < D; j += 192 * 4) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int n = 0; n < B; ++n) {
+                const float d = __ldg(dlogits + (size_t)n * ldl + k);
+                const float4 f = ldg4(feat + (size_t)n * D + j);
+                acc.x = fmaf(d, f.x, acc.x); acc.y = fmaf(d, f.y, acc.y); acc.z = fmaf(d, f.z, acc.z); acc.w = fmaf(d, f.w, acc.w);
+            }
+            *reinterpret_cast<float4*>(dW + (size_t)k * D + j) = acc;
+        }
+        if (db != nullptr && threadIdx.x == 0) {
+            float b = 0.f;
+            for (int n = 0; n < B; ++n) b += __ldg(dlogits + (size_t)n * ldl + k);
+            db[k] = b;
+        }
+    } else {
+        const int n = blockIdx.x - ncls;
+        for (int j = threadIdx.x * 4; j < D; j += 192 * 4) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < ncls; ++k) {
+                const float d = __ldg(dlogits + (size_t)n * ldl + k);
+                if (d == 0.f) continue;                      // classes outside the task mask carry exactly zero gradient
+                const float4 w = ldg4(W + (size_t)k * D + j);
+                acc.x = fmaf(d, w.x, acc.x); acc.y = fmaf(d, w.y, acc.y); acc.z = fmaf(d, w.z, acc.z); acc.w = fmaf(d, w.w, acc.w);
+            }
+            *reinterpret_cast<float4*>(dfeat + (size_t)n * D + j) = acc;
+        }
+    }
+}
+
+// L2P parameter gradients: dpool[P][L][D] = 0 except dpool[ids[t]][l][:] = dprompts[t*L + l][:] (ids are distinct);
+// dkey_out = coeff * dkey_in  (coeff = -pull_constraint_coeff: l2p.py:99).  One block per pool row (p, l) + P blocks for the keys.
+__global__ void __launch_bounds__(192) l2p_backward_kernel(const float* dprompts, const long long* ids, int pool, int top_k, int L, int D, float* dpool,
+                                                           const float* dkey_in, float coeff, float* dkey_out) {
+    const int r = blockIdx.x;
+    if (r < pool * L) {
+        const int p = r / L, l = r % L;
+        int t = -1;
+        for (int i = 0; i < top_k; ++i) if ((int)ids[i] == p) t = i;
+        for (int j = threadIdx.x * 4; j < D; j += 192 * 4) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t >= 0) v = *reinterpret_cast<const float4*>(dprompts + (size_t)(t * L + l) * D + j);
+            *reinterpret_cast<float4*>(dpool + (size_t)r * D + j) = v;
+        }
+    } else {
+        const int p = r - pool * L;
+        for (int j = threadIdx.x * 4; j < D; j += 192 * 4) {
+            const float4 v = *reinterpret_cast<const float4*>(dkey_in + (size_t)p * D + j);
+            *reinterpret_cast<float4*>(dkey_out + (size_t)p * D + j) = make_float4(coeff * v.x, coeff * v.y, coeff * v.z, coeff * v.w);
+        }
+    }
 }
 
 }  // namespace lc

@@ -62,3 +62,54 @@ class SGD(torch.optim.Optimizer):
             else:
                 raise ValueError("libcontinual_b200.optim.SGD: extra param groups must be frozen (lr = 0, weight_decay = 0)")
         return None if lo is None else (int(lo), int(hi))
+
+
+class Adam(torch.optim.Optimizer):
+    """torch.optim.Adam (config/l2p-vit-cifar100-b10-10-10.yaml:37-42) as one kernel over a model's flat trainable arena
+    (`model.theta` / `model.theta_grad`, e.g. `libcontinual_b200.model.l2p.L2P`).  State (exp_avg, exp_avg_sq, step) is rebuilt
+    with the optimizer every task, like the reference (trainer.py:294)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, *, model=None):
+        if model is None or not hasattr(model, "theta"):
+            raise ValueError("libcontinual_b200.optim.Adam needs model= with a flat .theta / .theta_grad arena")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.model = model
+        self.m = torch.zeros_like(model.theta)
+        self.v = torch.zeros_like(model.theta)
+        self.hp = torch.zeros(8, device=model.theta.device)
+        self.t = 0
+        from . import _lib
+        self.lib = _lib.load()
+
+    def hyper(self, t: int):
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        return [float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]), 1.0 - b1 ** t, 1.0 - b2 ** t, 0.0]
+
+    def zero_grad(self, set_to_none: bool = True):
+        # gradients are overwritten (not accumulated) by the model's backward kernels
+        for grp in self.param_groups:
+            for p in grp["params"]:
+                p.grad = None
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        mdl = self.model
+        self.t += 1
+        self.hp.copy_(torch.tensor(self.hyper(self.t), dtype=torch.float32), non_blocking=False)
+        base = mdl.theta.data_ptr()
+        for grp in self.param_groups:
+            for p in grp["params"]:
+                if p.grad is None:
+                    raise RuntimeError("Adam.step() before observe(): no gradient")
+                off = (p.data_ptr() - base) // 4
+                if p.grad.data_ptr() != mdl.theta_grad.data_ptr() + off * 4:         # foreign gradient: gather it into the arena layout
+                    mdl.theta_grad[off:off + p.numel()].copy_(p.grad.reshape(-1))
+        self.launch()
+        return None
+
+    def launch(self):
+        """The update kernel alone (hp already on the device): what a captured step replays."""
+        mdl = self.model
+        check(self.lib.lc_adam(mdl.theta.data_ptr(), mdl.theta_grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), mdl.theta.numel(),
+                               self.hp.data_ptr(), torch.cuda.current_stream().cuda_stream), "adam")

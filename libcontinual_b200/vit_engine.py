@@ -68,8 +68,22 @@ class _Workspace:
         self.ystat = torch.empty(n, 2, device=dev, dtype=f32)
         self.feat = torch.empty(B, DIM, device=dev, dtype=f32)
 
+        self.bwd = None
+
     def idx(self, layer: int) -> int:
         return layer if self.save else 0
+
+    def backward_buffers(self):
+        """Transient buffers of the input-gradient pass (allocated on first use)."""
+        if self.bwd is None:
+            B, T, Tp, dev = self.B, self.T, self.Tp, self.y.device
+            bf, f32 = torch.bfloat16, torch.float32
+            n = B * T
+            e = lambda *shape, dt=bf: torch.empty(*shape, device=dev, dtype=dt)
+            self.bwd = dict(g=[e(B, T, DIM, dt=f32), e(B, T, DIM, dt=f32)], gbf=e(n, DIM), dU=e(n, MLP), dh=e(n, DIM, dt=f32), dO=e(n, DIM),
+                            dS=e(B * HEADS, T, Tp), dSt=e(B * HEADS, T, Tp), Pt=e(B * HEADS, T, Tp), kt=e(B * HEADS, HDIM, Tp), qt=e(B * HEADS, HDIM, Tp),
+                            dot=e(B * HEADS, HDIM, Tp), dqkv=e(n, 3 * DIM))
+        return self.bwd
 
 
 class ViTEngine:
@@ -123,7 +137,7 @@ class ViTEngine:
 
     # ---- GEMM plumbing -------------------------------------------------------------------------
     def gemm(self, A, lda, B, ldb, C, ldc, M, N, K, *, sA=(0, 0), sB=(0, 0), sC=(0, 0), batch=(1, 1), bias=None, residual=None, ldr=0, sR=(0, 0),
-             out2=None, out_f32=False, alpha=1.0):
+             out2=None, gelu_bwd_aux=None, out_f32=False, alpha=1.0):
         """C[z] = alpha * A[z] @ B[z]^T (+bias +residual); A/B/C/residual/out2 are raw device addresses (ints), strides in elements."""
         d = GemmDesc()
         d.A, d.lda, d.strideA_in, d.strideA_out = A, lda, sA[0], sA[1]
@@ -131,6 +145,7 @@ class ViTEngine:
         d.C, d.ldc, d.strideC_in, d.strideC_out = C, ldc, sC[0], sC[1]
         d.bias, d.residual, d.ldr, d.strideR_in, d.strideR_out = bias, residual, ldr, sR[0], sR[1]
         d.out2 = out2
+        d.gelu_bwd_aux = gelu_bwd_aux
         d.M, d.N, d.K, d.batch_in, d.batch_out, d.out_f32, d.alpha = M, N, K, batch[0], batch[1], int(out_f32), alpha
         check(self.lib.lc_gemm_bf16_ex(ctypes.byref(d), self.err.data_ptr(), stream_ptr()), f"gemm {M}x{N}x{K}")
         self.launches += 1
@@ -183,7 +198,7 @@ class ViTEngine:
         self.gemm(q, 3 * DIM, q + DIM * 2, 3 * DIM, ws.S.data_ptr(), Tp, T, T, HDIM, sA=(HDIM, T * 3 * DIM), sB=(HDIM, T * 3 * DIM),
                   sC=(T * Tp, HEADS * T * Tp), batch=(HEADS, B), out_f32=True, alpha=HDIM ** -0.5)
         check(self.lib.lc_softmax_rows(ws.S.data_ptr(), P.data_ptr(), B * HEADS * T, T, Tp, st), "softmax")
-        check(self.lib.lc_vit_transpose_v(q, ws.vt.data_ptr(), B, T, HEADS, Tp, st), "transpose_v")
+        check(self.lib.lc_vit_transpose_heads(q, 3 * DIM, 2 * DIM, ws.vt.data_ptr(), B, T, HEADS, Tp, st), "transpose V")
         # O[b,:,h*64:(h+1)*64] = P[b,h] V[b,h]
         self.gemm(P.data_ptr(), Tp, ws.vt.data_ptr(), Tp, ws.o.data_ptr(), DIM, T, HDIM, Tp, sA=(T * Tp, HEADS * T * Tp), sB=(HDIM * Tp, HEADS * HDIM * Tp),
                   sC=(HDIM, T * DIM), batch=(HEADS, B))
@@ -217,3 +232,65 @@ class ViTEngine:
                                       logits.stride(0), stream_ptr()), "linear_head")
         self.launches += 1
         return logits
+
+    # ---- backward wrt the input tokens -----------------------------------------------------------
+    def _linear_t(self, a_bf16: torch.Tensor, wname: str, out: torch.Tensor, gelu_bwd_aux=None):
+        """out = a @ W  (backward-data of y = x W^T): the B operand is the pre-transposed BF16 copy [in_features][out_features]."""
+        w = self.wbt[wname]
+        N, K = w.shape
+        self.gemm(a_bf16.data_ptr(), K, w.data_ptr(), K, out.data_ptr(), N, a_bf16.shape[0], N, K, out_f32=out.dtype == torch.float32,
+                  gelu_bwd_aux=None if gelu_bwd_aux is None else gelu_bwd_aux.data_ptr())
+
+    def _ln_bwd(self, dh, x, wname, eps, res, out_f32, out_bf16, dh_pool=None, T=0, n_active=0):
+        rows = x.numel() // DIM
+        check(self.lib.lc_layernorm_backward(None if dh is None else dh.data_ptr(), None if dh_pool is None else dh_pool.data_ptr(), T, n_active, x.data_ptr(),
+                                             self.w[wname + ".weight"].data_ptr(), eps, rows, DIM, None if res is None else res.data_ptr(),
+                                             None if out_f32 is None else out_f32.data_ptr(), None if out_bf16 is None else out_bf16.data_ptr(), stream_ptr()),
+              "layernorm_backward")
+        self.launches += 1
+
+    def backward_tokens(self, ws: _Workspace, dfeat: torch.Tensor, n_prompt: int) -> torch.Tensor:
+        """Given d(loss)/d(pooled feature) [B, 768], returns d(loss)/d(input tokens) fp32 [B, T, 768] (ws must come from forward(save=True)).
+        Autograd of transformer.py:2006-2017 / :1331-1336 / :169-197 restricted to the activations: no weight gradients (frozen backbone)."""
+        assert ws.save, "backward needs the activations of forward(save=True)"
+        B, T, Tp = ws.B, ws.T, ws.Tp
+        st = stream_ptr()
+        bw = ws.backward_buffers()
+        g, g2 = bw["g"]
+        gbf, dU, dh, dO, dS, dSt, Pt, kt, qt, dot, dqkv = (bw[k] for k in ("gbf", "dU", "dh", "dO", "dS", "dSt", "Pt", "kt", "qt", "dot", "dqkv"))
+        scale = HDIM ** -0.5
+        self._ln_bwd(None, ws.x[self.depth], "norm", 1e-6, None, g, gbf, dh_pool=dfeat, T=T, n_active=max(n_prompt, 1))
+        for i in reversed(range(self.depth)):
+            pre = f"transformer.blocks.{i}."
+            qkv, P = ws.qkv[i], ws.P[i]
+            q = qkv.data_ptr()
+            # MLP branch: x_out = x_mid + fc2(GELU(fc1(LN2(x_mid))))
+            self._linear_t(gbf, pre + "mlp.fc2.weight", dU, gelu_bwd_aux=ws.upre[i])
+            self._linear_t(dU, pre + "mlp.fc1.weight", dh)
+            self._ln_bwd(dh, ws.xmid[i], pre + "ln_2", 1e-5, g, g2, gbf)
+            # attention branch: x_mid = x_in + proj(softmax(QK^T/8) V)
+            self._linear_t(gbf, pre + "attn.proj.weight", dO)
+            self.gemm(dO.data_ptr(), DIM, q + 2 * DIM * 2, 3 * DIM, ws.S.data_ptr(), Tp, T, T, HDIM, sA=(HDIM, T * DIM), sB=(HDIM, T * 3 * DIM),
+                      sC=(T * Tp, HEADS * T * Tp), batch=(HEADS, B), out_f32=True)                                  # dP = dO V^T
+            check(self.lib.lc_softmax_backward_rows(P.data_ptr(), ws.S.data_ptr(), dS.data_ptr(), B * HEADS * T, T, Tp, st), "softmax_backward")
+            check(self.lib.lc_vit_transpose_heads(q, 3 * DIM, DIM, kt.data_ptr(), B, T, HEADS, Tp, st), "K^T")
+            check(self.lib.lc_vit_transpose_heads(q, 3 * DIM, 0, qt.data_ptr(), B, T, HEADS, Tp, st), "Q^T")
+            check(self.lib.lc_vit_transpose_heads(dO.data_ptr(), DIM, 0, dot.data_ptr(), B, T, HEADS, Tp, st), "dO^T")
+            check(self.lib.lc_transpose_tt(P.data_ptr(), Pt.data_ptr(), B * HEADS, T, Tp, st), "P^T")
+            check(self.lib.lc_transpose_tt(dS.data_ptr(), dSt.data_ptr(), B * HEADS, T, Tp, st), "dS^T")
+            self.launches += 6
+            hs = dict(sA=(T * Tp, HEADS * T * Tp), sB=(HDIM * Tp, HEADS * HDIM * Tp), sC=(HDIM, T * 3 * DIM), batch=(HEADS, B))
+            dq = dqkv.data_ptr()
+            self.gemm(dS.data_ptr(), Tp, kt.data_ptr(), Tp, dq, 3 * DIM, T, HDIM, Tp, alpha=scale, **hs)                  # dQ = dS K / 8
+            self.gemm(dSt.data_ptr(), Tp, qt.data_ptr(), Tp, dq + DIM * 2, 3 * DIM, T, HDIM, Tp, alpha=scale, **hs)       # dK = dS^T Q / 8
+            self.gemm(Pt.data_ptr(), Tp, dot.data_ptr(), Tp, dq + 2 * DIM * 2, 3 * DIM, T, HDIM, Tp, **hs)                # dV = P^T dO
+            self._linear_t(dqkv, pre + "attn.qkv.weight", dh)
+            self._ln_bwd(dh, ws.x[i], pre + "ln_1", 1e-5, g2, g, gbf)
+        return g
+
+    def prompt_row_grads(self, g: torch.Tensor, n_prompt: int, out: torch.Tensor) -> torch.Tensor:
+        """Gradient of the prompt rows shared by the batch: out[r] = sum_b g[b, r]  (the `repeat(B, 1)` of prompt.py:390)."""
+        B, T = g.shape[0], g.shape[1]
+        check(self.lib.lc_sum_batch_rows(g.data_ptr(), T * DIM, B, n_prompt, DIM, out.data_ptr(), stream_ptr()), "sum_batch_rows")
+        self.launches += 1
+        return out
