@@ -5,7 +5,10 @@ Workload (default, BASELINE.json configs[1]): iCaRL, cifar_resnet32, CIFAR-100 b
 against the frozen teacher active: teacher forward + student forward/backward + CE/KD + SGD momentum step), synthetic
 N(0,1) 32x32 images, random-init weights.  `--workload ewc` runs configs[0] at bs 128 (task 1, penalty active).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload icarl|ewc]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload icarl|ewc|l2p]
+
+`--workload l2p` runs configs[2]: L2P on ViT-B/16, CIFAR-100 b10-10-10 at 224x224, batch 128 per GPU (query pass + prompted pass +
+backward to the prompt rows + clip + Adam), BF16 tcgen05 GEMMs with fp32 accumulation, synthetic U(0,1) images, random-init weights.
 
 value : whole-job images/s, inputs resident in HBM, one CUDA-graph replay per step, timed with CUDA events, max over ranks.
 e2e   : the same metric through the plugin surface a reference Trainer uses (observe -> zero_grad -> backward -> step ->
@@ -36,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="icarl", choices=["icarl", "ewc"])
+    ap.add_argument("--workload", default="icarl", choices=["icarl", "ewc", "l2p"])
     ap.add_argument("--cpu-steps", type=int, default=12, help="timed oracle steps for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
@@ -49,7 +52,8 @@ def parse():
 
 def workload_name(w):
     return {"icarl": "iCaRL ResNet32 CIFAR-100 b50-5-10 (task 1: CE + KD vs frozen teacher), bs=128, synthetic 32x32",
-            "ewc": "EWC ResNet32 CIFAR-100 b0-10-10 (task 1: CE + lamda*Fisher penalty), bs=128, synthetic 32x32"}[w]
+            "ewc": "EWC ResNet32 CIFAR-100 b0-10-10 (task 1: CE + lamda*Fisher penalty), bs=128, synthetic 32x32",
+            "l2p": "L2P ViT-B/16 CIFAR-100 b10-10-10 (task 1: query pass + prompted pass + backward to prompts, clip, Adam), bs=128, synthetic 224x224"}[w]
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -120,10 +124,85 @@ def time_oracle(workload, steps, warmup, device="cpu"):
     return BATCH * steps / dt, dt / steps * 1e3, cores
 
 
+# ---- L2P / ViT-B/16 ---------------------------------------------------------------------------------------------------
+def l2p_synth_state(seed=1993):
+    """Random-init ViT-B/16 + pool + head from one numpy Generator (no checkpoint offline)."""
+    import numpy as np
+    import torch
+    from oracle import port  # only the init helper (weights are data, not compute)
+    rng = np.random.default_rng(seed)
+    p = port.vit_init(rng)
+    prm = torch.from_numpy(rng.uniform(0, 1, (1, 10, 5, 768)).astype(np.float32))
+    key = torch.from_numpy(rng.uniform(0, 1, (10, 768)).astype(np.float32))
+    bound = 1.0 / np.sqrt(768)
+    fc_w = torch.from_numpy(rng.uniform(-bound, bound, (100, 768)).astype(np.float32))
+    fc_b = torch.from_numpy(rng.uniform(-bound, bound, (100,)).astype(np.float32))
+    return p, prm, key, fc_w, fc_b
+
+
+def l2p_batches(n, batch, lo, hi, seed=7):
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(seed)
+    return [(torch.from_numpy(rng.random((batch, 3, 224, 224), dtype=np.float32)), torch.from_numpy(rng.integers(lo, hi, (batch,)).astype(np.int64)))
+            for _ in range(n)]
+
+
+def time_oracle_l2p(steps, warmup, batch, device="cpu"):
+    """The oracle restatement of L2P.observe + Adam (pinned to the reference by tests/golden/l2p_vit.npz) on `batch` images per step."""
+    import torch
+    from oracle import port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p, prm, key, fc_w, fc_b = l2p_synth_state()
+    dev = torch.device("cuda", 0) if device == "cuda" else torch.device("cpu")
+    p = {k: v.to(dev) for k, v in p.items()}
+    tr = [t.to(dev).requires_grad_(True) for t in (prm, key, fc_w, fc_b)]
+    opt = torch.optim.Adam(tr, lr=0.001875, betas=(0.9, 0.999), weight_decay=0)
+    batches = [(x.to(dev), y.to(dev)) for x, y in l2p_batches(2, batch, 10, 20)]
+    sync = (lambda: torch.cuda.synchronize()) if device == "cuda" else (lambda: None)
+
+    def one(x, y):
+        opt.zero_grad()
+        feat, rs, _, _ = port.l2p_forward(p, tr[0], tr[1], x, 5)
+        loss, _ = port.l2p_loss(port.linear_head(feat, tr[2], tr[3]), y, 10, 20, rs, 1.0)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(tr, 1.0)
+        opt.step()
+        return loss.item()
+    for i in range(warmup):
+        one(*batches[i % 2])
+    sync()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(*batches[i % 2])
+    sync()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, cores
+
+
+def run_reference_l2p(args):
+    on_gpu = args.ref_device == "cuda"
+    batch = BATCH if on_gpu else 16
+    steps, warm = (max(1, min(args.steps, 20)), 3) if on_gpu else (max(1, min(args.steps, 6)), 1)
+    ips, ms, cores = time_oracle_l2p(steps, warm, batch, args.ref_device)
+    line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name("l2p"), "global_batch": batch,
+                       "device": "cuda:0 (PyTorch eager fp32, context only)" if on_gpu else "cpu"},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} full L2P steps of {batch} images (bounded sample of the bs-128 step; oracle/port.py, PyTorch "
+                                       + ("eager on cuda:0)" if on_gpu else f"CPU fp32, {cores} threads)")},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "l2p":
+        return run_reference_l2p(args)
     on_gpu = args.ref_device == "cuda"
     steps, warm = (max(1, min(args.steps, 200)), max(3, min(args.warmup, 20))) if on_gpu else (max(1, min(args.steps, 40)), max(1, min(args.warmup, 3)))
     ips, ms, cores = time_oracle(args.workload, steps, warm, args.ref_device)
@@ -248,7 +327,159 @@ def time_dominant_kernel(eng, precision, reps=48):
     return us, algo_bytes, name
 
 
+def time_dominant_gemm(eng, reps=40):
+    """The fc1 GEMM of one block (M = 128*222 tokens, N = 3072, K = 768, bias + GELU epilogue: the largest single share of the L2P step)
+    timed alone with CUDA events, rotating over enough distinct operand sets that every launch starts from cold HBM."""
+    import torch
+    M, N, K = BATCH * 222, 3072, 768
+    sets = 4                                       # 4 * (43.6 + 2*174.6) MB = 1.5 GB > 126 MB L2
+    a = [torch.randn(M, K, device=eng.dev).bfloat16() for _ in range(sets)]
+    c = [torch.empty(M, N, device=eng.dev, dtype=torch.bfloat16) for _ in range(sets)]
+    c2 = [torch.empty(M, N, device=eng.dev, dtype=torch.bfloat16) for _ in range(sets)]
+    w = eng.wb["transformer.blocks.0.mlp.fc1.weight"]
+    bias = eng.w["transformer.blocks.0.mlp.fc1.bias"]
+    launch = lambda i: eng.gemm(a[i].data_ptr(), K, w.data_ptr(), K, c[i].data_ptr(), N, M, N, K, bias=bias.data_ptr(), out2=c2[i].data_ptr())
+    for i in range(sets):
+        launch(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        launch(i % sets)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    return us, 2.0 * M * N * K, "gemm_bf16_kernel<256> (fc1: 28416 x 3072 x 768, bias + GELU epilogue, tcgen05 kind::f16 BF16, TMA SW128, TMEM accumulators)"
+
+
+def run_ours_l2p(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from libcontinual_b200.model.l2p import L2P, vit_pt_imnet
+    from libcontinual_b200.optim import Adam
+    from libcontinual_b200.trainer import GraphedL2PStep
+
+    p, prm, key, fc_w, fc_b = l2p_synth_state()
+    bb = vit_pt_imnet(pretrained=False, state=p, device=device)
+    m = L2P(bb, device, init_cls_num=10, inc_cls_num=10, num_class=100, task_num=10, feat_dim=768, prompt_length=5, pool_size=10, top_k=5,
+            pull_constraint_coeff=1.0)
+    with torch.no_grad():
+        bb.prompt.prompt.copy_(prm); bb.prompt.prompt_key.copy_(key)
+        m.network.classifier.weight.copy_(fc_w); m.network.classifier.bias.copy_(fc_b)
+    m.after_task(0, None, None, None); m.before_task(1, None, None, None)
+    opt = Adam(m.get_parameters(None), lr=0.001875, betas=(0.9, 0.999), weight_decay=0, model=m)
+    eng = m.engine
+    NB = 3
+    host = [(x.pin_memory(), y.pin_memory()) for x, y in l2p_batches(NB, BATCH, 10, 20, seed=7 + rank)]
+    devb = [(x.to(device), y.to(device)) for x, y in host]
+    K, W = args.steps, max(3, args.warmup)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step = GraphedL2PStep(m, opt, BATCH)
+    for i in range(W):
+        step.run(*devb[i % NB])
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(K):
+        step.run(*devb[i % NB])
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    final_loss = float(step.loss())
+    t = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t) / K
+    value = world * BATCH / (ms_step * 1e-3)
+    launches = step.launches_per_step * K + (K if world > 1 else 0)
+
+    Ke = max(5, min(K, 50))
+    for i in range(2):
+        step.run(*host[i % NB]); float(step.loss())
+    barrier()
+    e0.record()
+    for i in range(Ke):
+        step.run(*host[i % NB])
+        lossv = step.loss().item()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t) / Ke
+    e2e = {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * 4 + BATCH * 8 + 32,
+           "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
+           "path": "libcontinual_b200.trainer.GraphedL2PStep.run(pinned host batch) + loss().item() every step"}
+    plugin = None
+    if world == 1:
+        def eager(i):
+            opt.zero_grad()
+            pred, acc, loss = m.observe({"image": host[i % NB][0], "label": host[i % NB][1]})
+            opt.step()
+            return loss.item()
+        for i in range(2):
+            eager(i)
+        torch.cuda.synchronize()
+        Kp = max(5, min(K, 20))
+        e0.record()
+        for i in range(Kp):
+            eager(i)
+        e1.record()
+        torch.cuda.synchronize()
+        pm = e0.elapsed_time(e1) / Kp
+        plugin = {"value": BATCH / (pm * 1e-3), "unit": "images/s", "ms_per_step": pm,
+                  "path": "plugin zero_grad->observe (backward + clip inside)->optim.step->loss.item() (trainer.py:592-611), eager launches"}
+    e2e["plugin_eager"] = plugin
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["bf16_tflops"]), "MEASURED_PEAKS.json bf16 burst (kernel timed alone)"
+    else:
+        peak, peak_src = 1650.0, "fallback (B200_PROFILING.md)"
+    us, flops, kname = time_dominant_gemm(eng)
+    achieved = flops / (us * 1e-6) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "kernel": kname,
+                "us_per_launch": us, "algorithmic_flops_per_launch": flops, "peak_source": peak_src}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ips, ms, cores = time_oracle_l2p(2, 1, 16)
+        cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "ms_per_step": ms,
+               "sample": f"2 full L2P steps of 16 images after 1 warm-up (bounded sample of the bs-128 step; oracle/port.py, PyTorch CPU fp32, {cores} threads)"}
+    flop_step = 3 * 12 * 2 * (768 * 2304 + 768 * 768 + 2 * 768 * 3072) * BATCH * 215.0     # rough: 3 passes x 12 blocks x linear layers
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name("l2p"), "global_batch": BATCH * world, "per_gpu_batch": BATCH, "parallelism": f"dp{world}",
+                       "l2": f"per-step working set ~9 GB of saved activations + {NB} rotating 77 MB input batches > 126 MB L2 (no explicit flush)",
+                       "precision": "BF16 GEMM operands (tcgen05 kind::f16), fp32 accumulate in TMEM, fp32 residual stream / LayerNorm / softmax / loss / Adam",
+                       "final_loss": final_loss, "tensor_core_error": eng.tensor_core_error(),
+                       "approx_model_tflops": flop_step / (ms_step * 1e-3) / 1e12},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ours(args):
+    if args.workload == "l2p":
+        return run_ours_l2p(args)
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))

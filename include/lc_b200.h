@@ -174,6 +174,14 @@ int lc_gemm_bf16_ex(const lc_gemm_desc* desc, int* error_flag, lc_stream_t strea
  * assembly, LayerNorm (fp32 in -> bf16 and/or fp32 out, optional (mean, rstd) per row), row softmax (fp32 scores -> bf16 probabilities,
  * padding columns zeroed), one head slice of a token-major buffer -> [B*H][64][tokens] (V^T, K^T, Q^T, dO^T), mean over a row range (L2P: the prompt positions, transformer.py:2256-2259), fp32 linear head,
  * fp32 -> bf16 cast. */
+/* Fused multi-head self-attention, head dim 64, T <= 256 tokens (transformer.py:169-197): O = softmax(Q K^T / 8) V on strided views of the
+ * fused QKV buffer [B][T][3][H][64] (BF16) -> O [B][T][H*64] (BF16); lse2 [B][H][T] = base-2 log-sum-exp of the scaled score rows, kept for
+ * the backward.  The T x T score / probability matrices live in TMEM / shared memory only. */
+int lc_attn_forward(const void* qkv_bf16, void* out_bf16, float* lse2, int batch, int T, int heads, int* error_flag, lc_stream_t stream);
+/* Its backward: dQ, dK, dV (written into dqkv with the QKV layout) from dO, with the probabilities recomputed on chip from lse2;
+ * rowdot [B][H][T] is scratch (sum_d dO*O per row). */
+int lc_attn_backward(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2, float* rowdot, void* dqkv_bf16, int batch, int T,
+                     int heads, int* error_flag, lc_stream_t stream);
 int lc_vit_patchify(const float* img_nchw, void* out_bf16, int batch, lc_stream_t stream);
 int lc_vit_set_rows(float* x, long long batch_stride, int batch, int row0, int nrows, const float* src, const float* add, int dim, lc_stream_t stream);
 int lc_layernorm_forward(const float* x, const float* gamma, const float* beta, float eps, long long rows, int dim, void* out_bf16, float* out_f32,

@@ -1,6 +1,7 @@
 // C entry points of the ViT-B/16 building blocks: tcgen05 GEMM (gemm_tc.cuh) and the row-wise kernels around it (vit_ops.cuh).
 #include "../../include/lc_b200.h"
 #include "gemm_tc.cuh"
+#include "attn_tc.cuh"
 #include "vit_ops.cuh"
 
 using namespace lc;
@@ -92,6 +93,37 @@ int lc_gemm_bf16(const void* A, int lda, long long strideA, const void* B, int l
     d.bias = bias; d.residual = residual; d.ldr = ldr; d.strideR_in = strideR; d.out2 = out2; d.M = M; d.N = N; d.K = K; d.batch_in = batch;
     d.batch_out = 1; d.out_f32 = out_f32; d.alpha = alpha;
     return lc_gemm_bf16_ex(&d, error_flag, stream);
+}
+
+int lc_attn_forward(const void* qkv_bf16, void* out_bf16, float* lse2, int batch, int T, int heads, int* error_flag, lc_stream_t stream) {
+    LC_CHECK_ARG(qkv_bf16 && out_bf16 && lse2 && batch >= 1 && T >= 1 && T <= 256 && heads >= 1);
+    const size_t smem = tc::attn_fwd_smem(T);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        if (cudaFuncSetAttribute(tc::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return LC_ERR_CUDA;
+        attr_smem = smem;
+    }
+    tc::AttnFwdArgs a{reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), lse2, T, heads, error_flag};
+    tc::attn_fwd_kernel<<<dim3((T + 127) / 128, heads, batch), 128, smem, (cudaStream_t)stream>>>(a);
+    return lc_launch_status();
+}
+
+int lc_attn_backward(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2, float* rowdot, void* dqkv_bf16, int batch, int T,
+                     int heads, int* error_flag, lc_stream_t stream) {
+    LC_CHECK_ARG(qkv_bf16 && out_bf16 && dout_bf16 && lse2 && rowdot && dqkv_bf16 && batch >= 1 && T >= 1 && T <= 256 && heads >= 1 && batch <= 65535);
+    const size_t smem = tc::attn_bwd_smem(T);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        if (cudaFuncSetAttribute(tc::attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return LC_ERR_CUDA;
+        attr_smem = smem;
+    }
+    const long long rows = (long long)batch * T;
+    tc::attn_rowdot_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(dout_bf16),
+                                                                                        reinterpret_cast<const __nv_bfloat16*>(out_bf16), rowdot, rows, T, heads);
+    tc::AttnBwdArgs a{reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse2, rowdot,
+                      reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), T, heads, error_flag};
+    tc::attn_bwd_kernel<<<dim3(heads, batch), 256, smem, (cudaStream_t)stream>>>(a);
+    return lc_launch_status();
 }
 
 int lc_vit_patchify(const float* img, void* out_bf16, int batch, lc_stream_t stream) {

@@ -209,8 +209,10 @@ class L2P(nn.Module):
         eng.launches += 2
         return ws2, feat, bb
 
-    def _launch_step(self, x, y):
-        """Everything `observe` puts on the stream (no host synchronisation): capturable into a CUDA graph."""
+    def _launch_step(self, x, y, clip: bool = True):
+        """Everything `observe` puts on the stream (no host synchronisation): capturable into a CUDA graph.  clip=False stops before
+        `clip_grad_norm_` so that a data-parallel caller can average `theta_grad` across ranks first (DDP averages during backward,
+        the clip at l2p.py:104 then sees the averaged gradient)."""
         eng, lib, st = self.engine, self.engine.lib, stream_ptr()
         B = x.shape[0]
         lo = 0 if self.cur_task_id == 0 else self._known_classes
@@ -227,10 +229,15 @@ class L2P(nn.Module):
         check(lib.lc_l2p_backward(self.dprompts.data_ptr(), self.ids.data_ptr(), self.pool_size, self.top_k, self.length, DIM,
                                   self._view(0, self.theta_grad).data_ptr(), self.dkey_raw.data_ptr(), -float(self.pull_constraint_coeff),
                                   self._view(1, self.theta_grad).data_ptr(), st), "l2p_backward")
-        check(lib.lc_clip_grad_norm(self.theta_grad.data_ptr(), self.theta_grad.numel(), 1.0, self.clip_scratch.data_ptr(), self.grad_norm.data_ptr(), st),
-              "clip_grad_norm")
-        eng.launches += 5      # loss, head backward, l2p backward, clip (2 launches)
+        eng.launches += 3      # loss, head backward, l2p backward
+        if clip:
+            self._launch_clip()
         return bb
+
+    def _launch_clip(self):
+        check(self.engine.lib.lc_clip_grad_norm(self.theta_grad.data_ptr(), self.theta_grad.numel(), 1.0, self.clip_scratch.data_ptr(),
+                                                self.grad_norm.data_ptr(), stream_ptr()), "clip_grad_norm")
+        self.engine.launches += 2
 
     def observe(self, data):
         x, y = self._to_device(data)

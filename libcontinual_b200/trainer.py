@@ -15,7 +15,7 @@ from typing import Optional
 
 import torch
 
-from .optim import SGD
+from .optim import SGD, Adam
 from .parallel import allreduce_mean_
 
 
@@ -98,3 +98,66 @@ class GraphedStep:
 
     def correct(self) -> torch.Tensor:
         return self.eng.scal[1]
+
+
+class GraphedL2PStep:
+    """The L2P step (query pass, prompt selection, prompted pass, masked loss, backward to the prompt rows, clip, Adam) as CUDA graphs.
+    world_size > 1: graph 1 ends before the clip, the flat trainable-gradient arena (123k floats) is all-reduced (average), graph 2
+    clips and updates — the reference's DDP order (gradients averaged in backward, then l2p.py:104, then optimizer.step)."""
+
+    def __init__(self, model, optimizer: Adam, batch_size: int, process_group=None, warmup: int = 2):
+        assert isinstance(optimizer, Adam), "GraphedL2PStep drives the fused flat Adam"
+        self.model, self.opt, self.eng, self.B = model, optimizer, model.engine, batch_size
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if (process_group is not None or (
+            torch.distributed.is_available() and torch.distributed.is_initialized())) else 1
+        dev = self.eng.dev
+        self.x = torch.zeros(batch_size, 3, 224, 224, device=dev)
+        self.y = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+        self.hp_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self._stage_hp(1)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        saved = (model.theta.clone(), optimizer.m.clone(), optimizer.v.clone())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                model._launch_step(self.x, self.y, clip=True)
+                optimizer.launch()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        model.theta.copy_(saved[0]); optimizer.m.copy_(saved[1]); optimizer.v.copy_(saved[2])
+        l0 = self.eng.launches
+        self.g_main = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_main):
+            model._launch_step(self.x, self.y, clip=self.world == 1)
+            if self.world == 1:
+                optimizer.launch()
+        self.g_upd = None
+        if self.world > 1:
+            self.g_upd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_upd):
+                model._launch_clip()
+                optimizer.launch()
+        self.launches_per_step = self.eng.launches - l0 + 1
+        self.steps = 0
+
+    def _stage_hp(self, t: int):
+        self.hp_host.copy_(torch.tensor(self.opt.hyper(t), dtype=torch.float32))
+        self.opt.hp.copy_(self.hp_host, non_blocking=True)
+
+    def run(self, x: torch.Tensor, y: torch.Tensor, non_blocking: bool = True):
+        self.opt.t += 1
+        self._stage_hp(self.opt.t)
+        self.x.copy_(x, non_blocking=non_blocking)
+        self.y.copy_(y, non_blocking=non_blocking)
+        self.g_main.replay()
+        if self.world > 1:
+            allreduce_mean_(self.model.theta_grad, self.pg)
+            self.g_upd.replay()
+        self.steps += 1
+
+    def loss(self) -> torch.Tensor:
+        return self.model.scal[0]
+
+    def correct(self) -> torch.Tensor:
+        return self.model.scal[1]
