@@ -171,8 +171,7 @@ typedef struct lc_gemm_desc {
 } lc_gemm_desc;
 int lc_gemm_bf16_ex(const lc_gemm_desc* desc, int* error_flag, lc_stream_t stream);
 /* Row-wise / layout kernels of the ViT forward (transformer.py:2222-2261): im2col of the 16x16 patches (timm PatchEmbed as a GEMM), cls-row
- * assembly, LayerNorm (fp32 in -> bf16 and/or fp32 out, optional (mean, rstd) per row), row softmax (fp32 scores -> bf16 probabilities,
- * padding columns zeroed), one head slice of a token-major buffer -> [B*H][64][tokens] (V^T, K^T, Q^T, dO^T), mean over a row range (L2P: the prompt positions, transformer.py:2256-2259), fp32 linear head,
+ * assembly, LayerNorm (fp32 in -> bf16 and/or fp32 out, optional (mean, rstd) per row), mean over a row range (L2P: the prompt positions, transformer.py:2256-2259), fp32 linear head,
  * fp32 -> bf16 cast. */
 /* Fused multi-head self-attention, head dim 64, T <= 256 tokens (transformer.py:169-197): O = softmax(Q K^T / 8) V on strided views of the
  * fused QKV buffer [B][T][3][H][64] (BF16) -> O [B][T][H*64] (BF16); lse2 [B][H][T] = base-2 log-sum-exp of the scaled score rows, kept for
@@ -186,16 +185,11 @@ int lc_vit_patchify(const float* img_nchw, void* out_bf16, int batch, lc_stream_
 int lc_vit_set_rows(float* x, long long batch_stride, int batch, int row0, int nrows, const float* src, const float* add, int dim, lc_stream_t stream);
 int lc_layernorm_forward(const float* x, const float* gamma, const float* beta, float eps, long long rows, int dim, void* out_bf16, float* out_f32,
                          float* stat, lc_stream_t stream);
-int lc_softmax_rows(const float* S, void* P_bf16, long long rows, int T, int ld, lc_stream_t stream);
-int lc_vit_transpose_heads(const void* in_bf16, long long row_stride, int col0, void* out_bf16, int batch, int T, int heads, int ld, lc_stream_t stream);
 /* Backward of the frozen backbone wrt its input tokens (what carries the loss to the L2P prompt rows; the backbone itself has
  * requires_grad=False: l2p.py:66-71): LayerNorm backward fused with the residual-path gradient (dh either dense fp32 or the pooled-feature
- * gradient broadcast over the first n_active rows of every image), softmax backward per row, T x T batched transpose (P^T, dS^T are the
- * A operands of dV / dK), and the batch sum of the shared prompt rows. */
+ * gradient broadcast over the first n_active rows of every image) and the batch sum of the shared prompt rows. */
 int lc_layernorm_backward(const float* dh, const float* dh_pool, int T, int n_active, const float* x, const float* gamma, float eps, long long rows, int dim,
                           const float* res, float* out_f32, void* out_bf16, lc_stream_t stream);
-int lc_softmax_backward_rows(const void* P_bf16, const float* dP, void* dS_bf16, long long rows, int T, int ld, lc_stream_t stream);
-int lc_transpose_tt(const void* in_bf16, void* out_bf16, long long nmat, int T, int ld, lc_stream_t stream);
 int lc_sum_batch_rows(const float* x, long long batch_stride, int batch, int nrows, int dim, float* out, lc_stream_t stream);
 int lc_vit_pool_rows(const float* y, long long batch_stride, int batch, int r0, int nr, int dim, float* feat, lc_stream_t stream);
 int lc_linear_head(const float* feat, const float* W, const float* bias, int batch, int ncls, int dim, float* logits, int ld, lc_stream_t stream);

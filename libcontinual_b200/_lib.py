@@ -63,11 +63,7 @@ SIGNATURES = {
     "lc_vit_patchify": (c_int, [P, P, c_int, P]),
     "lc_vit_set_rows": (c_int, [P, c_longlong, c_int, c_int, c_int, P, P, c_int, P]),
     "lc_layernorm_forward": (c_int, [P, P, P, c_float, c_longlong, c_int, P, P, P, P]),
-    "lc_softmax_rows": (c_int, [P, P, c_longlong, c_int, c_int, P]),
-    "lc_vit_transpose_heads": (c_int, [P, c_longlong, c_int, P, c_int, c_int, c_int, c_int, P]),
     "lc_layernorm_backward": (c_int, [P, P, c_int, c_int, P, P, c_float, c_longlong, c_int, P, P, P, P]),
-    "lc_softmax_backward_rows": (c_int, [P, P, P, c_longlong, c_int, c_int, P]),
-    "lc_transpose_tt": (c_int, [P, P, c_longlong, c_int, c_int, P]),
     "lc_sum_batch_rows": (c_int, [P, c_longlong, c_int, c_int, c_int, P, P]),
     "lc_vit_pool_rows": (c_int, [P, c_longlong, c_int, c_int, c_int, c_int, P, P]),
     "lc_linear_head": (c_int, [P, P, P, c_int, c_int, c_int, P, c_int, P]),

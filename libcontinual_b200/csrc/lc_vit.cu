@@ -143,36 +143,12 @@ int lc_layernorm_forward(const float* x, const float* gamma, const float* beta, 
                                                                                        out_f32, stat);
     return lc_launch_status();
 }
-int lc_softmax_rows(const float* S, void* P_bf16, long long rows, int T, int ld, lc_stream_t stream) {
-    LC_CHECK_ARG(S && P_bf16 && rows >= 1 && T >= 1 && ld >= T);
-    softmax_rows_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(S, reinterpret_cast<__nv_bfloat16*>(P_bf16), rows, T, ld);
-    return lc_launch_status();
-}
-int lc_vit_transpose_heads(const void* in_bf16, long long row_stride, int col0, void* out_bf16, int batch, int T, int heads, int ld, lc_stream_t stream) {
-    LC_CHECK_ARG(in_bf16 && out_bf16 && batch >= 1 && T >= 1 && heads >= 1 && ld >= T && col0 >= 0);
-    dim3 grid((ld + 63) / 64, batch * heads);
-    transpose_heads_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(in_bf16), row_stride, col0,
-                                                                  reinterpret_cast<__nv_bfloat16*>(out_bf16), batch, T, heads, ld);
-    return lc_launch_status();
-}
-int lc_transpose_tt(const void* in_bf16, void* out_bf16, long long nmat, int T, int ld, lc_stream_t stream) {
-    LC_CHECK_ARG(in_bf16 && out_bf16 && nmat >= 1 && nmat <= 65535 && T >= 1 && ld >= T);
-    dim3 grid((ld + 63) / 64, (T + 63) / 64, (unsigned)nmat);
-    transpose_tt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(in_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), T, ld);
-    return lc_launch_status();
-}
 int lc_layernorm_backward(const float* dh, const float* dh_pool, int T, int n_active, const float* x, const float* gamma, float eps, long long rows, int dim,
                           const float* res, float* out_f32, void* out_bf16, lc_stream_t stream) {
     LC_CHECK_ARG((dh != nullptr) != (dh_pool != nullptr) && x && gamma && rows >= 1 && dim == 768 && (out_f32 || out_bf16));
     LC_CHECK_ARG(dh_pool == nullptr || (T >= 1 && n_active >= 1 && n_active <= T && rows % T == 0));
     layernorm_bwd_kernel<768><<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(dh, dh_pool, T, n_active, x, gamma, eps, rows, res, out_f32,
                                                                                        reinterpret_cast<__nv_bfloat16*>(out_bf16));
-    return lc_launch_status();
-}
-int lc_softmax_backward_rows(const void* P_bf16, const float* dP, void* dS_bf16, long long rows, int T, int ld, lc_stream_t stream) {
-    LC_CHECK_ARG(P_bf16 && dP && dS_bf16 && rows >= 1 && T >= 1 && ld >= T);
-    softmax_bwd_rows_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(P_bf16), dP,
-                                                                                         reinterpret_cast<__nv_bfloat16*>(dS_bf16), rows, T, ld);
     return lc_launch_status();
 }
 int lc_sum_batch_rows(const float* x, long long batch_stride, int batch, int nrows, int dim, float* out, lc_stream_t stream) {

@@ -71,24 +71,6 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const float* x, cons
     }
 }
 
-// softmax over the first T columns of every row of S (fp32, row stride ld), written as bf16 P with the padding columns [T, ld) zeroed
-// (they are the K-tail of the P.V GEMM).  One warp per row.
-__global__ void __launch_bounds__(128) softmax_rows_kernel(const float* S, __nv_bfloat16* P, long long rows, int T, int ld) {
-    const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    const float* s = S + (size_t)row * ld;
-    float m = -CUDART_INF_F;
-    for (int j = lane; j < T; j += 32) m = fmaxf(m, s[j]);
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int j = lane; j < T; j += 32) sum += expf(s[j] - m);
-    sum = warp_sum(sum);
-    const float inv = 1.f / sum;
-    __nv_bfloat16* p = P + (size_t)row * ld;
-    for (int j = lane; j < ld; j += 32) p[j] = __float2bfloat16_rn(j < T ? expf(s[j] - m) * inv : 0.f);
-}
-
 // features[b][:] = mean over rows [r0, r0+nr) of y[b][:][:]  (L2P: the 25 prompt positions; otherwise the cls row) ; fp32
 __global__ void __launch_bounds__(192) pool_rows_kernel(const float* y, long long batch_stride, int r0, int nr, int D, float* feat) {
     const int b = blockIdx.x;
@@ -175,55 +157,6 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const float* dh, con
         }
         if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + (size_t)row * D + j) = make_float4(o[0], o[1], o[2], o[3]);
         if (out_bf16 != nullptr) *reinterpret_cast<uint2*>(out_bf16 + (size_t)row * D + j) = make_uint2(pack2_bf16(o[0], o[1]), pack2_bf16(o[2], o[3]));
-    }
-}
-
-// softmax backward per row (the 1/sqrt(d) scale is folded into the dQ / dK GEMMs): dS = P * (dP - sum_j P_j dP_j) ; bf16, padding zeroed
-__global__ void __launch_bounds__(128) softmax_bwd_rows_kernel(const __nv_bfloat16* P, const float* dP, __nv_bfloat16* dS, long long rows, int T, int ld) {
-    const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    const __nv_bfloat16* p = P + (size_t)row * ld;
-    const float* d = dP + (size_t)row * ld;
-    float s = 0.f;
-    for (int j = lane; j < T; j += 32) s = fmaf(__bfloat162float(p[j]), d[j], s);
-    s = warp_sum(s);
-    __nv_bfloat16* o = dS + (size_t)row * ld;
-    for (int j = lane; j < ld; j += 32) o[j] = __float2bfloat16_rn(j < T ? __bfloat162float(p[j]) * (d[j] - s) : 0.f);
-}
-
-// batched bf16 transpose of the T x T corner of [Z][T][ld] matrices into [Z][T][ld] (padding columns zeroed): P -> P^T, dS -> dS^T
-__global__ void __launch_bounds__(256) transpose_tt_kernel(const __nv_bfloat16* in, __nv_bfloat16* out, int T, int ld) {
-    __shared__ __nv_bfloat16 tile[64][66];
-    const size_t z = blockIdx.z;
-    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;       // input rows i0.., cols j0..
-    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
-        const int r = e / 64, c = e % 64;
-        tile[r][c] = (i0 + r < T && j0 + c < T) ? in[(z * T + i0 + r) * ld + j0 + c] : __float2bfloat16_rn(0.f);
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
-        const int r = e / 64, c = e % 64;                         // output row j0 + r, col i0 + c
-        if (j0 + r < T && i0 + c < ld) out[(z * T + j0 + r) * ld + i0 + c] = tile[c][r];
-    }
-}
-
-// one 64-wide head slice of a token-major bf16 buffer -> [B*H][64][ld] (tokens contiguous, padding zeroed):
-//   out[(b*H+h)][d][t] = in[(b*T+t)*row_stride + col0 + h*64 + d]        (V, K, Q of the fused QKV buffer; dO)
-__global__ void __launch_bounds__(256) transpose_heads_kernel(const __nv_bfloat16* in, long long row_stride, int col0, __nv_bfloat16* out, int B, int T, int H,
-                                                              int ld) {
-    __shared__ __nv_bfloat16 tile[64][66];
-    const int bh = blockIdx.y, b = bh / H, h = bh % H;
-    const int t0 = blockIdx.x * 64;
-    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
-        const int tt = e / 64, d = e % 64;
-        const int t = t0 + tt;
-        tile[tt][d] = t < T ? in[(size_t)(b * T + t) * row_stride + col0 + h * 64 + d] : __float2bfloat16_rn(0.f);
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
-        const int d = e / 64, tt = e % 64;
-        if (t0 + tt < ld) out[((size_t)bh * 64 + d) * ld + t0 + tt] = tile[tt][d];
     }
 }
 

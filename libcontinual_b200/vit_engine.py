@@ -5,11 +5,11 @@ tcgen05 GEMMs), per-(batch, tokens) activation workspaces and the launch sequenc
 `VisionTransformer.forward(prompt_flag='l2p')` (core/model/backbone/transformer.py:2222-2261):
 
     patchify -> patch-embed GEMM (+bias +pos_embed) -> [prompts | cls | patches]
-    12 x { LN1 -> QKV GEMM -> S = QK^T/8 -> softmax -> P V -> proj GEMM (+residual) -> LN2 -> fc1 GEMM (+GELU) -> fc2 GEMM (+residual) }
+    12 x { LN1 -> QKV GEMM -> fused attention (S, softmax, P V on chip) -> proj GEMM (+residual) -> LN2 -> fc1 GEMM (+GELU) -> fc2 GEMM (+residual) }
     final LN (eps 1e-6)
 
 and of its backward with respect to the INPUT tokens only (the backbone is frozen: l2p.py:66-71), which is what carries the loss
-gradient back to the prompt rows.  The residual stream is fp32; GEMM operands, the stored QKV / probabilities / GELU outputs are BF16;
+gradient back to the prompt rows.  The residual stream is fp32; GEMM operands, the stored QKV / attention / GELU outputs are BF16;
 accumulation is fp32 in TMEM.  Everything here is launch plumbing: torch supplies device memory and streams, every FLOP runs in
 `liblc_b200.so`.
 """
@@ -46,7 +46,7 @@ def _up8(v: int) -> int:
 
 class _Workspace:
     """Activation buffers of one (batch, tokens) shape.  With `save` every block keeps what its backward needs:
-    x_in / x_mid (LayerNorm inputs), qkv, P (probabilities), pre-GELU fc1 output."""
+    x_in / x_mid (LayerNorm inputs), qkv, attention output + row log-sum-exp, pre-GELU fc1 output."""
 
     def __init__(self, B: int, T: int, depth: int, save: bool, dev):
         self.B, self.T, self.Tp, self.save = B, T, _up8(T), save
@@ -56,13 +56,11 @@ class _Workspace:
         self.x = [torch.empty(B, T, DIM, device=dev, dtype=f32) for _ in range(nx)]          # block inputs (x[depth] = last block's output)
         self.xmid = [torch.empty(B, T, DIM, device=dev, dtype=f32) for _ in range(depth if save else 1)]
         self.qkv = [torch.empty(n, 3 * DIM, device=dev, dtype=bf) for _ in range(depth if save else 1)]
-        self.P = [torch.empty(B * HEADS, T, self.Tp, device=dev, dtype=bf) for _ in range(depth if save else 1)]
+        self.o = [torch.empty(n, DIM, device=dev, dtype=bf) for _ in range(depth if save else 1)]          # attention output (pre-projection)
+        self.lse = [torch.empty(B, HEADS, T, device=dev, dtype=f32) for _ in range(depth if save else 1)]   # base-2 log-sum-exp of the score rows
         self.upre = [torch.empty(n, MLP, device=dev, dtype=bf) for _ in range(depth if save else 1)]
         self.patches = torch.empty(B * PATCHES, DIM, device=dev, dtype=bf)
         self.h = torch.empty(n, DIM, device=dev, dtype=bf)
-        self.S = torch.empty(B * HEADS, T, self.Tp, device=dev, dtype=f32)
-        self.vt = torch.empty(B * HEADS, HDIM, self.Tp, device=dev, dtype=bf)
-        self.o = torch.empty(n, DIM, device=dev, dtype=bf)
         self.u = torch.empty(n, MLP, device=dev, dtype=bf)
         self.y = torch.empty(B, T, DIM, device=dev, dtype=f32)
         self.ystat = torch.empty(n, 2, device=dev, dtype=f32)
@@ -81,8 +79,7 @@ class _Workspace:
             n = B * T
             e = lambda *shape, dt=bf: torch.empty(*shape, device=dev, dtype=dt)
             self.bwd = dict(g=[e(B, T, DIM, dt=f32), e(B, T, DIM, dt=f32)], gbf=e(n, DIM), dU=e(n, MLP), dh=e(n, DIM, dt=f32), dO=e(n, DIM),
-                            dS=e(B * HEADS, T, Tp), dSt=e(B * HEADS, T, Tp), Pt=e(B * HEADS, T, Tp), kt=e(B * HEADS, HDIM, Tp), qt=e(B * HEADS, HDIM, Tp),
-                            dot=e(B * HEADS, HDIM, Tp), dqkv=e(n, 3 * DIM))
+                            rowdot=e(B, HEADS, T, dt=f32), dqkv=e(n, 3 * DIM))
         return self.bwd
 
 
@@ -190,23 +187,15 @@ class ViTEngine:
         k = ws.idx(i)
         xin = ws.x[i] if ws.save else ws.x[i % 2]
         xout = ws.x[i + 1] if ws.save else ws.x[(i + 1) % 2]
-        xmid, qkv, P, upre = ws.xmid[k], ws.qkv[k], ws.P[k], ws.upre[k]
+        xmid, qkv, o, upre = ws.xmid[k], ws.qkv[k], ws.o[k], ws.upre[k]
         self._ln(xin, pre + "ln_1", 1e-5, out_bf16=ws.h)
         self._linear(ws.h, pre + "attn.qkv.weight", qkv, bias=pre + "attn.qkv.bias")
-        q = qkv.data_ptr()
-        # S[b,h] = Q K^T / 8 : strided views of the fused QKV buffer [B][T][3][H][64]
-        self.gemm(q, 3 * DIM, q + DIM * 2, 3 * DIM, ws.S.data_ptr(), Tp, T, T, HDIM, sA=(HDIM, T * 3 * DIM), sB=(HDIM, T * 3 * DIM),
-                  sC=(T * Tp, HEADS * T * Tp), batch=(HEADS, B), out_f32=True, alpha=HDIM ** -0.5)
-        check(self.lib.lc_softmax_rows(ws.S.data_ptr(), P.data_ptr(), B * HEADS * T, T, Tp, st), "softmax")
-        check(self.lib.lc_vit_transpose_heads(q, 3 * DIM, 2 * DIM, ws.vt.data_ptr(), B, T, HEADS, Tp, st), "transpose V")
-        # O[b,:,h*64:(h+1)*64] = P[b,h] V[b,h]
-        self.gemm(P.data_ptr(), Tp, ws.vt.data_ptr(), Tp, ws.o.data_ptr(), DIM, T, HDIM, Tp, sA=(T * Tp, HEADS * T * Tp), sB=(HDIM * Tp, HEADS * HDIM * Tp),
-                  sC=(HDIM, T * DIM), batch=(HEADS, B))
-        self._linear(ws.o, pre + "attn.proj.weight", xmid, bias=pre + "attn.proj.bias", residual=xin)
+        check(self.lib.lc_attn_forward(qkv.data_ptr(), o.data_ptr(), ws.lse[k].data_ptr(), B, T, HEADS, self.err.data_ptr(), st), "attn_forward")
+        self._linear(o, pre + "attn.proj.weight", xmid, bias=pre + "attn.proj.bias", residual=xin)
         self._ln(xmid, pre + "ln_2", 1e-5, out_bf16=ws.h)
         self._linear(ws.h, pre + "mlp.fc1.weight", upre, bias=pre + "mlp.fc1.bias", out2=ws.u)
         self._linear(ws.u, pre + "mlp.fc2.weight", xout, bias=pre + "mlp.fc2.bias", residual=xmid)
-        self.launches += 2
+        self.launches += 1
 
     def forward(self, img: torch.Tensor, prompts: Optional[torch.Tensor] = None, save: bool = False) -> _Workspace:
         """Runs the backbone; returns the workspace (ws.y = final-LayerNorm tokens fp32 [B, T, 768])."""
@@ -257,33 +246,19 @@ class ViTEngine:
         st = stream_ptr()
         bw = ws.backward_buffers()
         g, g2 = bw["g"]
-        gbf, dU, dh, dO, dS, dSt, Pt, kt, qt, dot, dqkv = (bw[k] for k in ("gbf", "dU", "dh", "dO", "dS", "dSt", "Pt", "kt", "qt", "dot", "dqkv"))
-        scale = HDIM ** -0.5
+        gbf, dU, dh, dO, rowdot, dqkv = (bw[k] for k in ("gbf", "dU", "dh", "dO", "rowdot", "dqkv"))
         self._ln_bwd(None, ws.x[self.depth], "norm", 1e-6, None, g, gbf, dh_pool=dfeat, T=T, n_active=max(n_prompt, 1))
         for i in reversed(range(self.depth)):
             pre = f"transformer.blocks.{i}."
-            qkv, P = ws.qkv[i], ws.P[i]
-            q = qkv.data_ptr()
             # MLP branch: x_out = x_mid + fc2(GELU(fc1(LN2(x_mid))))
             self._linear_t(gbf, pre + "mlp.fc2.weight", dU, gelu_bwd_aux=ws.upre[i])
             self._linear_t(dU, pre + "mlp.fc1.weight", dh)
             self._ln_bwd(dh, ws.xmid[i], pre + "ln_2", 1e-5, g, g2, gbf)
             # attention branch: x_mid = x_in + proj(softmax(QK^T/8) V)
             self._linear_t(gbf, pre + "attn.proj.weight", dO)
-            self.gemm(dO.data_ptr(), DIM, q + 2 * DIM * 2, 3 * DIM, ws.S.data_ptr(), Tp, T, T, HDIM, sA=(HDIM, T * DIM), sB=(HDIM, T * 3 * DIM),
-                      sC=(T * Tp, HEADS * T * Tp), batch=(HEADS, B), out_f32=True)                                  # dP = dO V^T
-            check(self.lib.lc_softmax_backward_rows(P.data_ptr(), ws.S.data_ptr(), dS.data_ptr(), B * HEADS * T, T, Tp, st), "softmax_backward")
-            check(self.lib.lc_vit_transpose_heads(q, 3 * DIM, DIM, kt.data_ptr(), B, T, HEADS, Tp, st), "K^T")
-            check(self.lib.lc_vit_transpose_heads(q, 3 * DIM, 0, qt.data_ptr(), B, T, HEADS, Tp, st), "Q^T")
-            check(self.lib.lc_vit_transpose_heads(dO.data_ptr(), DIM, 0, dot.data_ptr(), B, T, HEADS, Tp, st), "dO^T")
-            check(self.lib.lc_transpose_tt(P.data_ptr(), Pt.data_ptr(), B * HEADS, T, Tp, st), "P^T")
-            check(self.lib.lc_transpose_tt(dS.data_ptr(), dSt.data_ptr(), B * HEADS, T, Tp, st), "dS^T")
-            self.launches += 6
-            hs = dict(sA=(T * Tp, HEADS * T * Tp), sB=(HDIM * Tp, HEADS * HDIM * Tp), sC=(HDIM, T * 3 * DIM), batch=(HEADS, B))
-            dq = dqkv.data_ptr()
-            self.gemm(dS.data_ptr(), Tp, kt.data_ptr(), Tp, dq, 3 * DIM, T, HDIM, Tp, alpha=scale, **hs)                  # dQ = dS K / 8
-            self.gemm(dSt.data_ptr(), Tp, qt.data_ptr(), Tp, dq + DIM * 2, 3 * DIM, T, HDIM, Tp, alpha=scale, **hs)       # dK = dS^T Q / 8
-            self.gemm(Pt.data_ptr(), Tp, dot.data_ptr(), Tp, dq + 2 * DIM * 2, 3 * DIM, T, HDIM, Tp, **hs)                # dV = P^T dO
+            check(self.lib.lc_attn_backward(ws.qkv[i].data_ptr(), ws.o[i].data_ptr(), dO.data_ptr(), ws.lse[i].data_ptr(), rowdot.data_ptr(), dqkv.data_ptr(),
+                                            B, T, HEADS, self.err.data_ptr(), st), "attn_backward")
+            self.launches += 2
             self._linear_t(dqkv, pre + "attn.qkv.weight", dh)
             self._ln_bwd(dh, ws.x[i], pre + "ln_1", 1e-5, g2, g, gbf)
         return g
