@@ -105,10 +105,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise LcError(f"{LIB_PATH} is missing: build it with `python -m libcontinual_b200.build` (nvcc, sm_100a). "
+    path = os.environ.get("LC_B200_LIB", LIB_PATH)      # debug builds (tools/) may point at an instrumented copy
+    if not os.path.exists(path):
+        raise LcError(f"{path} is missing: build it with `python -m libcontinual_b200.build` (nvcc, sm_100a). "
                       "There is no CPU / PyTorch fallback for the hot path.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.restype = res

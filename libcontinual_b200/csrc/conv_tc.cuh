@@ -30,6 +30,7 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 // bounded wait: returns false if the phase never completed (a mis-programmed MMA must not hang the GPU)
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 22); ++it) {
         uint32_t ok;
         asm volatile(

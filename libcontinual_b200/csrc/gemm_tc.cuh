@@ -2,13 +2,15 @@
 // :1255-1273 Mlp, :1331-1336 ResidualAttentionBlock): D[M][N] = A[M][K] * B[N][K]^T, BF16 operands, fp32 accumulation in TMEM,
 // fused epilogues (bias, exact GELU, fp32 residual add, BF16 / fp32 output, optional transposed per-head store).
 //
-// Structure (one 128 x BN output tile per CTA, warp specialised, mbarrier pipelines):
+// Structure (persistent CTAs, one per SM, looping over 128 x BN output tiles; warp specialised, mbarrier pipelines; two TMEM accumulators so
+// that the epilogue of one tile overlaps the MMAs of the next):
 //   warp 0 : TMA producer — cp.async.bulk.tensor (rank-4 maps: K, rows, inner batch, outer batch) loads of A (128 x 64) and B (BN x 64) K-blocks into a STAGES-deep ring of
 //            128-byte-swizzled shared-memory tiles (CU_TENSOR_MAP_SWIZZLE_128B), arriving on full[stage] with expect_tx bytes
 //   warp 1 : MMA issuer — one elected thread issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M128 x BN x K16) per K-block with
 //            SWIZZLE_128B K-major shared-memory descriptors (SBO = 1024 B, start advanced by 32 B per K16 step), commits the stage back
 //            to the producer (empty[stage]) and, after the last K-block, the accumulator to the epilogue (tmem_full)
-//   warps 2-5 : epilogue — tcgen05.ld 32x32b (warp w owns TMEM lanes 32*(w%4)..), bias / GELU / residual, vectorised stores
+//   warps 2-9 : epilogue (two warps per TMEM lane quarter, alternating 32-column slabs) — tcgen05.ld 32x32b (warp w owns TMEM lanes 32*(w%4)..), staged through shared memory so that bias / GELU /
+//            residual and the global stores run row-wise (128-byte row segments per 8 lanes), then the accumulator is handed back (tmem_empty)
 // Operands are addressed through tensor maps (row stride and batch strides arbitrary), so the same kernel runs the per-head
 // batched attention GEMMs (Q K^T, P V) on strided views of the fused QKV buffer.
 #pragma once
@@ -30,7 +32,7 @@ struct GemmArgs {
     int M, N, K;
     int ldc, ldr;
     long long c_stride_in, c_stride_out, r_stride_in, r_stride_out;   // elements; batch index z = z_out * batch_in + z_in
-    int batch_in;
+    int batch_in, batch_total;
     int a_bcast, b_bcast;      // bit 0 / bit 1: the operand is shared across the inner / outer batch (its tensor map has extent 1 there)
     int out_dtype;
     float alpha;               // scale applied to the accumulator before bias (attention: 1/sqrt(d))
@@ -52,150 +54,224 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
-__device__ __forceinline__ float dgelu_erf(float x) {
-    return 0.5f * (1.f + erff(x * 0.70710678118654752440f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+// Exact (erf) GELU and its derivative with erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the BF16 rounding of every
+// consumer) on the MUFU approximations: one rcp, one ex2 and ~12 FMA-pipe instructions per element — the GELU epilogues were
+// instruction-issue-bound with libdevice erff (ncu: 43k warp instructions per 128x256 tile).  exp2(-x^2 log2(e)/2) serves both the erf
+// tail and the Gaussian density of the derivative.
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& gauss) {
+    const float ax = fabsf(x);
+    const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    gauss = ex2_approx(-0.72134752044448170368f * x * x);            // exp(-x^2 / 2)
+    const float erf_abs = fmaf(-p * t, gauss, 1.f);                    // erf(|x| / sqrt(2))
+    cdf = fmaf(0.5f, copysignf(erf_abs, x), 0.5f);                     // Phi(x)
 }
+__device__ __forceinline__ float gelu_erf(float x) { float c, g; gelu_parts(x, c, g); return x * c; }
+__device__ __forceinline__ float dgelu_erf(float x) { float c, g; gelu_parts(x, c, g); return fmaf(x * 0.3989422804014327f, g, c); }
 
 template <int BN>
 struct GemmCfg {
     static constexpr int BM = 128, BK = 64;
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = BN == 256 ? 4 : 6;
-    static constexpr int NT = 192;
-    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-    static constexpr uint32_t TMEM_COLS = BN;   // 128 or 256 (power of two >= 32)
-    static_assert(BN == 128 || BN == 256 || BN == 64, "BN");
+    static constexpr int STAGES = BN == 256 ? 3 : 5;
+    static constexpr int EPI_WARPS = 8;
+    static constexpr int NT = 64 + 32 * EPI_WARPS;
+    static constexpr int SLAB = 32;                                   // epilogue column slab
+    static constexpr int STG_LD = SLAB + 4;                           // staging row stride (floats): conflict-free float4 rows
+    static constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;     // per epilogue warp: 32 rows
+    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + STG_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;                     // two accumulators: the epilogue of tile i overlaps the MMAs of tile i+1
+    static_assert(BN == 128 || BN == 256, "BN");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(192, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs a) {
+#ifdef LC_GEMM_TIMING
+// debug build only (tools/gemm_timing.py): per CTA and tile, globaltimer stamps of the three roles
+__device__ unsigned long long g_gemm_tstamp[148 * 32 * 8];
+__device__ __forceinline__ unsigned long long gemm_gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define LC_GSTAMP(tile_local, slot) do { if ((tile_local) < 32 && blockIdx.x < 148) g_gemm_tstamp[((size_t)blockIdx.x * 32 + (tile_local)) * 8 + (slot)] = gemm_gtimer(); } while (0)
+#else
+#define LC_GSTAMP(tile_local, slot) do { } while (0)
+#endif
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+enum { EPI_F32 = 1, EPI_RES = 2, EPI_GELU2 = 4, EPI_DGELU = 8 };     // compile-time epilogue variants (keeps each instance's code small)
+
+// Persistent: grid = min(#tiles, #SMs); CTA c processes tiles c, c + grid, ...  Tile order: m fastest inside an n panel (the B panel
+// — weights — stays hot in L2 across the CTAs working on it), panels inside a batch element.
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GemmCfg<BN>::NT, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs a) {
     using K = GemmCfg<BN>;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base_u = (smem_u32(smem_dyn) + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char* base = smem_dyn + (base_u - smem_u32(smem_dyn));
-    uint64_t* full = reinterpret_cast<uint64_t*>(base + K::STAGES * K::STAGE_BYTES);
+    float* staging = reinterpret_cast<float*>(base + K::STAGES * K::STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + K::STAGES * K::STAGE_BYTES + K::STG_BYTES);
     uint64_t* empty = full + K::STAGES;
-    uint64_t* tmem_full = empty + K::STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty + K::STAGES;      // [2]
+    uint64_t* tmem_empty = tmem_full + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * K::BM;
-    const int z_in = (int)blockIdx.z % a.batch_in, z_out = (int)blockIdx.z / a.batch_in;
     const int nkb = (a.K + K::BK - 1) / K::BK;
+    const int m_tiles = (a.M + K::BM - 1) / K::BM, n_tiles = (a.N + BN - 1) / BN;
+    const int per_z = m_tiles * n_tiles;
+    const int total = per_z * a.batch_total;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < K::STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(tmem_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, K::EPI_WARPS); }
     }
     if (warp == 1) tmem_alloc(tmem_slot, K::TMEM_COLS);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    bool ok = true;
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % K::STAGES;
-                const uint32_t ph = (uint32_t)(kb / K::STAGES) & 1u;
-                mbar_wait(empty + s, ph ^ 1u);                                     // slot free (first lap passes immediately)
-                mbar_expect_tx(full + s, (uint32_t)K::STAGE_BYTES);
-                const uint32_t sa = base_u + (uint32_t)s * K::STAGE_BYTES;
-                tma_load_4d(sa, &tmA, full + s, kb * K::BK, m0, (a.a_bcast & 1) ? 0 : z_in, (a.a_bcast & 2) ? 0 : z_out);
-                tma_load_4d(sa + K::A_BYTES, &tmB, full + s, kb * K::BK, n0, (a.b_bcast & 1) ? 0 : z_in, (a.b_bcast & 2) ? 0 : z_out);
+            uint32_t it = 0;
+            int tl = 0; (void)tl;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int z = tile / per_z, r = tile % per_z;
+                const int n0 = (r / m_tiles) * BN, m0 = (r % m_tiles) * K::BM;
+                const int z_in = z % a.batch_in, z_out = z / a.batch_in;
+                LC_GSTAMP(tl, 0);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % K::STAGES;
+                    const uint32_t ph = (it / K::STAGES) & 1u;
+                    ok = mbar_wait(empty + s, ph ^ 1u) && ok;
+                    mbar_expect_tx(full + s, (uint32_t)K::STAGE_BYTES);
+                    const uint32_t sa = base_u + (uint32_t)s * K::STAGE_BYTES;
+                    tma_load_4d(sa, &tmA, full + s, kb * K::BK, m0, (a.a_bcast & 1) ? 0 : z_in, (a.a_bcast & 2) ? 0 : z_out);
+                    tma_load_4d(sa + K::A_BYTES, &tmB, full + s, kb * K::BK, n0, (a.b_bcast & 1) ? 0 : z_in, (a.b_bcast & 2) ? 0 : z_out);
+                }
+                LC_GSTAMP(tl, 1);
+                ++tl;
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(128, BN);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % K::STAGES;
-                const uint32_t ph = (uint32_t)(kb / K::STAGES) & 1u;
-                mbar_wait(full + s, ph);
+            uint32_t it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
+                const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+                LC_GSTAMP(t, 2);
+                ok = mbar_wait(tmem_empty + acc, aph ^ 1u) && ok;                   // the epilogue has drained this accumulator
                 fence_after_sync();
-                const uint32_t sa = base_u + (uint32_t)s * K::STAGE_BYTES;
-                const uint64_t ad = make_desc_sw128(sa), bd = make_desc_sw128(sa + K::A_BYTES);
+                LC_GSTAMP(t, 3);
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % K::STAGES;
+                    const uint32_t ph = (it / K::STAGES) & 1u;
+                    ok = mbar_wait(full + s, ph) && ok;
+                    fence_after_sync();
+                    const uint32_t sa = base_u + (uint32_t)s * K::STAGE_BYTES;
+                    const uint64_t ad = make_desc_sw128(sa), bd = make_desc_sw128(sa + K::A_BYTES);
 #pragma unroll
-                for (int k = 0; k < K::BK / 16; ++k)                               // +32 B (2 x 16-byte units) per K16 step inside the swizzle atom
-                    mma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-                mma_commit(empty + s);                                             // frees the stage when these MMAs have read it
+                    for (int k = 0; k < K::BK / 16; ++k)                           // +32 B (2 x 16-byte units) per K16 step inside the swizzle atom
+                        mma_f16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    mma_commit(empty + s);                                         // frees the stage when these MMAs have read it
+                }
+                mma_commit(tmem_full + acc);
+                LC_GSTAMP(t, 4);
             }
-            mma_commit(tmem_full);
         }
     } else {
-        // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4 --------------------------------------------------------------------
-        const bool done = mbar_wait(tmem_full, 0);
-        fence_after_sync();
-        if (!done && lane == 0 && a.error_flag != nullptr) atomicExch(a.error_flag, 2);
-        const int quarter = warp & 3;
-        const int m = m0 + quarter * 32 + lane;
-        const bool row_ok = m < a.M;
-        const size_t crow = (size_t)z_out * a.c_stride_out + (size_t)z_in * a.c_stride_in + (size_t)m * a.ldc;
-        const size_t rrow = (size_t)z_out * a.r_stride_out + (size_t)z_in * a.r_stride_in + (size_t)m * a.ldr;
+        // ---- epilogue warps 2..9: TMEM lane quarter = warp % 4, slab parity = (warp - 2) / 4.  Per 32-column slab: TMEM -> registers (thread = row) -> shared staging ->
+        //      row-wise pass (8 lanes x float4 = one 128-byte row segment, 4 rows per instruction): bias / residual / GELU, coalesced stores
+        const int quarter = warp & 3, spar = (warp - 2) >> 2;
+        float* stg = staging + (size_t)(warp - 2) * 32 * K::STG_LD;
+        const int rr = lane >> 3, c4 = (lane & 7) * 4;
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
+            const int z = tile / per_z, r = tile % per_z;
+            const int n0 = (r / m_tiles) * BN, m0 = (r % m_tiles) * K::BM;
+            const int z_in = z % a.batch_in, z_out = z / a.batch_in;
+            const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+            if (warp == 2 && lane == 0) LC_GSTAMP(t, 5);
+            ok = mbar_wait(tmem_full + acc, aph) && ok;
+            fence_after_sync();
+            if (warp == 2 && lane == 0) LC_GSTAMP(t, 6);
+            const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+            const size_t cz = (size_t)z_out * a.c_stride_out + (size_t)z_in * a.c_stride_in;
+            const size_t rz = (size_t)z_out * a.r_stride_out + (size_t)z_in * a.r_stride_in;
+            const int mrow0 = m0 + quarter * 32;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-            const int n = n0 + c0;
-            if (row_ok && n < a.N && n + 16 > a.N) {      // ragged last chunk (attention: N = #keys; head: N = #classes): scalar path
-                for (int i = 0; i < 16 && n + i < a.N; ++i) {
-                    float x = v[i] * a.alpha + (a.bias != nullptr ? a.bias[n + i] : 0.f);
-                    if (a.residual != nullptr) x += a.residual[rrow + n + i];
-                    if (a.gelu_aux != nullptr) x *= dgelu_erf(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.gelu_aux)[crow + n + i]));
-                    if (a.out_dtype == GEMM_OUT_F32) reinterpret_cast<float*>(a.out)[crow + n + i] = x;
-                    else reinterpret_cast<__nv_bfloat16*>(a.out)[crow + n + i] = __float2bfloat16_rn(x);
-                    if (a.out2 != nullptr) reinterpret_cast<__nv_bfloat16*>(a.out2)[crow + n + i] = __float2bfloat16_rn(gelu_erf(x));
-                }
-            } else if (row_ok && n < a.N) {
+            for (int c0 = spar * K::SLAB; c0 < BN && n0 + c0 < a.N; c0 += 2 * K::SLAB) {
+                const int n = n0 + c0 + c4;
+                const bool vec = n + 3 < a.N;
+                float4 res[8];
+                if constexpr ((EPI & EPI_RES) != 0) {                                // all of the slab's residual loads in flight before the TMEM read
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] *= a.alpha;
+                    for (int j = 0; j < 8; ++j) {
+                        const int m = mrow0 + j * 4 + rr;
+                        res[j] = (vec && m < a.M) ? *reinterpret_cast<const float4*>(a.residual + rz + (size_t)m * a.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                float v[32];
+                tmem_ld16(trow + (uint32_t)c0, v);
+                tmem_ld16(trow + (uint32_t)(c0 + 16), v + 16);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stg + lane * K::STG_LD + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (a.bias != nullptr) {
+                    if (vec) b4 = ldg4(a.bias + n);
+                    else { if (n < a.N) b4.x = a.bias[n]; if (n + 1 < a.N) b4.y = a.bias[n + 1]; if (n + 2 < a.N) b4.z = a.bias[n + 2]; }
+                }
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        const float4 b4 = ldg4(a.bias + n + k4 * 4);
-                        v[k4 * 4] += b4.x; v[k4 * 4 + 1] += b4.y; v[k4 * 4 + 2] += b4.z; v[k4 * 4 + 3] += b4.w;
+                for (int j = 0; j < 8; ++j) {
+                    const int r0 = j * 4;
+                    const int m = mrow0 + r0 + rr;
+                    if (m >= a.M || n >= a.N) continue;
+                    const float4 acc4 = *reinterpret_cast<const float4*>(stg + (r0 + rr) * K::STG_LD + c4);
+                    float x0 = fmaf(acc4.x, a.alpha, b4.x), x1 = fmaf(acc4.y, a.alpha, b4.y), x2 = fmaf(acc4.z, a.alpha, b4.z), x3 = fmaf(acc4.w, a.alpha, b4.w);
+                    const size_t ci = cz + (size_t)m * a.ldc + n;
+                    if (vec) {
+                        if constexpr ((EPI & EPI_RES) != 0) { x0 += res[j].x; x1 += res[j].y; x2 += res[j].z; x3 += res[j].w; }
+                        if constexpr ((EPI & EPI_DGELU) != 0) {
+                            const uint2 g = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(a.gelu_aux) + ci);
+                            x0 *= dgelu_erf(__uint_as_float(g.x << 16)); x1 *= dgelu_erf(__uint_as_float(g.x & 0xffff0000u));
+                            x2 *= dgelu_erf(__uint_as_float(g.y << 16)); x3 *= dgelu_erf(__uint_as_float(g.y & 0xffff0000u));
+                        }
+                        if constexpr ((EPI & EPI_F32) != 0) *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + ci) = make_float4(x0, x1, x2, x3);
+                        else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out) + ci) = make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
+                        if constexpr ((EPI & EPI_GELU2) != 0)
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out2) + ci) =
+                                make_uint2(pack_bf16(gelu_erf(x0), gelu_erf(x1)), pack_bf16(gelu_erf(x2), gelu_erf(x3)));
+                    } else {
+                        const float xs[4] = {x0, x1, x2, x3};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {                               // ragged last columns: scalar
+                            if (n + i >= a.N) break;
+                            float xi = xs[i];
+                            if constexpr ((EPI & EPI_RES) != 0) xi += a.residual[rz + (size_t)m * a.ldr + n + i];
+                            if constexpr ((EPI & EPI_DGELU) != 0) xi *= dgelu_erf(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.gelu_aux)[ci + i]));
+                            if constexpr ((EPI & EPI_F32) != 0) reinterpret_cast<float*>(a.out)[ci + i] = xi;
+                            else reinterpret_cast<__nv_bfloat16*>(a.out)[ci + i] = __float2bfloat16_rn(xi);
+                            if constexpr ((EPI & EPI_GELU2) != 0) reinterpret_cast<__nv_bfloat16*>(a.out2)[ci + i] = __float2bfloat16_rn(gelu_erf(xi));
+                        }
                     }
                 }
-                if (a.residual != nullptr) {
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        const float4 r4 = *reinterpret_cast<const float4*>(a.residual + rrow + n + k4 * 4);
-                        v[k4 * 4] += r4.x; v[k4 * 4 + 1] += r4.y; v[k4 * 4 + 2] += r4.z; v[k4 * 4 + 3] += r4.w;
-                    }
-                }
-                if (a.gelu_aux != nullptr) {
-                    const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.gelu_aux) + crow + n);
-                    const uint4 a0 = ap[0], a1 = ap[1];
-                    const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        v[2 * i] *= dgelu_erf(__uint_as_float(aw[i] << 16));
-                        v[2 * i + 1] *= dgelu_erf(__uint_as_float(aw[i] & 0xffff0000u));
-                    }
-                }
-                if (a.out_dtype == GEMM_OUT_F32) {
-                    float* o = reinterpret_cast<float*>(a.out) + crow + n;
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) *reinterpret_cast<float4*>(o + k4 * 4) = make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
-                } else {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + crow + n;
-                    uint4 p0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                    uint4 p1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-                    *reinterpret_cast<uint4*>(o) = p0; *reinterpret_cast<uint4*>(o + 8) = p1;
-                }
-                if (a.out2 != nullptr) {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out2) + crow + n;
-                    float g[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) g[i] = gelu_erf(v[i]);
-                    *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
-                    *reinterpret_cast<uint4*>(o + 8) = make_uint4(pack_bf16(g[8], g[9]), pack_bf16(g[10], g[11]), pack_bf16(g[12], g[13]), pack_bf16(g[14], g[15]));
-                }
+                __syncwarp();
             }
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + acc);
+            if (warp == 2 && lane == 0) LC_GSTAMP(t, 7);
         }
     }
+    if (!ok && lane == 0 && a.error_flag != nullptr) atomicExch(a.error_flag, 2);
     fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, K::TMEM_COLS);

@@ -42,17 +42,41 @@ int make_tmap(CUtensorMap* m, const void* ptr, int K, int rows, int b_in, int b_
     return r == CUDA_SUCCESS ? LC_OK : LC_ERR_INVALID;
 }
 
-template <int BN>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmArgs& a, int batch, cudaStream_t st) {
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BN, int EPI>
+int launch_gemm_epi(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmArgs& a, int batch, cudaStream_t st) {
     using K = tc::GemmCfg<BN>;
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(tc::gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES) != cudaSuccess) return LC_ERR_CUDA;
+        if (cudaFuncSetAttribute(tc::gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES) != cudaSuccess) return LC_ERR_CUDA;
         attr_done = true;
     }
-    dim3 grid((a.N + BN - 1) / BN, (a.M + 127) / 128, batch);
-    tc::gemm_bf16_kernel<BN><<<grid, K::NT, K::SMEM_BYTES, st>>>(ta, tb, a);
+    const long long tiles = (long long)((a.N + BN - 1) / BN) * ((a.M + 127) / 128) * batch;
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    tc::gemm_bf16_kernel<BN, EPI><<<grid, K::NT, K::SMEM_BYTES, st>>>(ta, tb, a);
     return lc_launch_status();
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmArgs& a, int batch, cudaStream_t st) {
+    const int epi = (a.out_dtype == tc::GEMM_OUT_F32 ? tc::EPI_F32 : 0) | (a.residual != nullptr ? tc::EPI_RES : 0) | (a.out2 != nullptr ? tc::EPI_GELU2 : 0) |
+                    (a.gelu_aux != nullptr ? tc::EPI_DGELU : 0);
+    switch (epi) {
+#define LC_EPI_CASE(E) case E: return launch_gemm_epi<BN, E>(ta, tb, a, batch, st);
+        LC_EPI_CASE(0) LC_EPI_CASE(1) LC_EPI_CASE(2) LC_EPI_CASE(3) LC_EPI_CASE(4) LC_EPI_CASE(5) LC_EPI_CASE(6) LC_EPI_CASE(7)
+        LC_EPI_CASE(8) LC_EPI_CASE(9) LC_EPI_CASE(10) LC_EPI_CASE(11) LC_EPI_CASE(12) LC_EPI_CASE(13) LC_EPI_CASE(14) LC_EPI_CASE(15)
+#undef LC_EPI_CASE
+    }
+    return LC_ERR_INVALID;
 }
 
 int grid_for(long long n, int per_block) {
@@ -62,6 +86,12 @@ int grid_for(long long n, int per_block) {
 }
 
 }  // namespace
+
+#ifdef LC_GEMM_TIMING
+extern "C" int lc_debug_gemm_timing(unsigned long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, tc::g_gemm_tstamp, sizeof(unsigned long long) * 148 * 32 * 8) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" {
 
@@ -80,7 +110,7 @@ int lc_gemm_bf16_ex(const lc_gemm_desc* d, int* error_flag, lc_stream_t stream) 
     if (e != LC_OK) return e;
     a.out = d->C; a.bias = d->bias; a.residual = d->residual; a.out2 = d->out2; a.gelu_aux = d->gelu_bwd_aux; a.M = d->M; a.N = d->N; a.K = d->K; a.ldc = (int)d->ldc; a.ldr = (int)d->ldr;
     a.c_stride_in = d->strideC_in; a.c_stride_out = d->strideC_out; a.r_stride_in = d->strideR_in; a.r_stride_out = d->strideR_out;
-    a.batch_in = d->batch_in; a.out_dtype = d->out_f32 ? tc::GEMM_OUT_F32 : tc::GEMM_OUT_BF16; a.alpha = d->alpha; a.error_flag = error_flag;
+    a.batch_in = d->batch_in; a.batch_total = d->batch_in * d->batch_out; a.out_dtype = d->out_f32 ? tc::GEMM_OUT_F32 : tc::GEMM_OUT_BF16; a.alpha = d->alpha; a.error_flag = error_flag;
     const int batch = d->batch_in * d->batch_out;
     return bn == 256 ? launch_gemm<256>(ta, tb, a, batch, (cudaStream_t)stream) : launch_gemm<128>(ta, tb, a, batch, (cudaStream_t)stream);
 }
