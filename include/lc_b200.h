@@ -201,6 +201,23 @@ int lc_linear_head_backward(const float* dlogits, int ldl, const float* feat, co
 int lc_l2p_backward(const float* dprompts, const int64_t* ids, int pool, int top_k, int length, int dim, float* dpool, const float* dkey_in, float coeff,
                     float* dkey_out, lc_stream_t stream);
 
+/* Low-rank adapters on the fused QKV projection (transformer.py:199-274 MultiHeadAttention_LoRA, :276-357 MultiHeadAttention_SDLoRA).
+ * lc_lora_merge      : for every layer l and adapted slab s (bit s of slab_mask: 0 = q, 1 = k, 2 = v; arrays hold the adapted slabs in increasing
+ *                      order): W'[l][s] = W[l][s] + B[l][s] diag(scale[l][s]) A[l][s]   (A [rank][dim], B [dim][rank], scale nullable = 1), written
+ *                      as the BF16 GEMM operands wb [l][3 dim][dim] / wbt [l][dim][3 dim] (either nullable) and/or fp32 w_out (may alias w:
+ *                      `merge_weight`, transformer.py:237-242).  Replaces the per-forward `k_weight + lora_B_k.weight @ lora_A_k.weight` (:246-254).
+ * lc_lora_bgrad_rows : out[s][c][j] = sum_n X[n][x0 + s*x_slab_stride + c] * Z[n][s*rank + j]  — the adapter gradient in rank form, e.g.
+ *                      d lora_B_k.weight = dK^T (h A_k^T) with X = d(qkv) (BF16) and Z = the saved down-projection (fp32); deterministic
+ *                      two-stage sum over `nchunk` row chunks (partial >= lc_lora_bgrad_partial_floats floats).  rank <= 16, dim % 768 == 0. */
+/* out[c][r] = in[r][c] (BF16; columns [rows, ld_out) of out zero-filled): the transposed copy that turns a contraction over token rows
+ * (InfLoRA's input matrix sum_n h_n h_n^T, transformer.py:242-244) into the K-major operands of lc_gemm_bf16. */
+int lc_transpose_bf16(const void* in_bf16, long long ld_in, long long rows, int cols, void* out_bf16, long long ld_out, lc_stream_t stream);
+int lc_lora_merge(const float* w, const float* A, const float* B, const float* scale, int slab_mask, int layers, int dim, int rank, void* wb_bf16,
+                  void* wbt_bf16, float* w_out, lc_stream_t stream);
+long long lc_lora_bgrad_partial_floats(int nslab, int dim, int rank, int nchunk);
+int lc_lora_bgrad_rows(const void* x_bf16, long long ldx, int x0, int x_slab_stride, int nslab, int dim, const float* z, int ldz, int rank, long long rows, float* partial,
+                       int nchunk, float* out, lc_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------------------
  * Per-kernel entry points (unit-tested individually; the network-level calls above are compositions of these).
  * conv3x3: NHWC fp32, pad 1.  `w_oihw` is the native nn.Conv2d weight; mode 0 = forward, 1 = data gradient (input is dy).

@@ -53,6 +53,10 @@ SIGNATURES = {
     "lc_gpm_project": (c_int, [P, P, c_int, c_int, P]),
     "lc_lora_merge_qkv": (c_int, [P, P, P, P, P, P, c_int, c_int, P]),
     "lc_lora_bgrad": (c_int, [P, P, P, c_int, c_int, P]),
+    "lc_transpose_bf16": (c_int, [P, c_longlong, c_longlong, c_int, P, c_longlong, P]),
+    "lc_lora_merge": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "lc_lora_bgrad_partial_floats": (c_longlong, [c_int, c_int, c_int, c_int]),
+    "lc_lora_bgrad_rows": (c_int, [P, c_longlong, c_int, c_int, c_int, c_int, P, c_int, c_int, c_longlong, P, c_int, P, P]),
     "lc_herding_select": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
     "lc_ncm_classify": (c_int, [P, P, c_int, c_int, c_int, P, P]),
     "lc_gemm_bf16": (c_int, [P, c_int, c_longlong, P, c_int, c_longlong, P, c_int, c_longlong, c_int, c_int, c_int, c_int, P, P, c_int, c_longlong, P, c_int,

@@ -180,7 +180,7 @@ struct AttnBwdArgs {
     const __nv_bfloat16* qkv;   // [B][T][3][H][64]
     const __nv_bfloat16* dout;  // [B][T][H*64]
     const float* lse2;          // [B][H][T]
-    const float* D;             // [B][H][T]
+    const float* D;             // unused (kept for ABI stability): the row term sum_j P_j dP_j is formed on chip
     __nv_bfloat16* dqkv;        // [B][T][3][H][64]
     int T, H;
     int* error_flag;
@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
     unsigned char* g_sdS = smem + nplanes * PQ;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * nplanes * PQ + 16 * PK + 16 * PQ);
     uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+    float* s_dpart = reinterpret_cast<float*>(smem + 2 * nplanes * PQ + 16 * PK + 16 * PQ + 64);
     const long long ld = 3LL * a.H * kAttnD;
     const int HD = a.H * kAttnD;
     const __nv_bfloat16* base = a.qkv + (size_t)b * T * ld + h * kAttnD;
@@ -241,7 +242,6 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
         const int t = q0 + row;
         const bool rv = t < T;
         const float l2 = rv ? a.lse2[((size_t)b * a.H + h) * T + t] : 0.f;
-        const float Dr = rv ? a.D[((size_t)b * a.H + h) * T + t] : 0.f;
         // ---- P = exp2(S c - lse2) for this thread's half of the key columns ------------------------------------------------------------
         for (int g0 = cbeg & ~15; g0 < cend; g0 += 16) {     // tcgen05.ld x16 granularity: aligned 16-column groups, 8-column sub-groups inside [cbeg, cend)
             float v[16];
@@ -271,6 +271,32 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
         }
         ok = mbar_wait(bar, phase & 1) && ok; ++phase;
         fence_after_sync();
+        // ---- D = sum_j P_j dP_j in fp32 from the very probabilities the dS / dV products use.  (The usual shortcut D = dO . O inherits the BF16
+        //      rounding of the stored O as a common-mode error of the whole row, which dS = P (dP - D) does not average out when the values of
+        //      a head are nearly alike; the row sum over the keys has no such term.)  Two threads share a row: partial sums meet in shared memory.
+        float Dr;
+        {
+            float dpart = 0.f;
+            for (int g0 = cbeg & ~15; g0 < cend; g0 += 16) {
+                float v[16];
+                tmem_ld16(trow + (uint32_t)g0, v);
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    const int c0 = g0 + sub * 8;
+                    if (c0 < cbeg || c0 >= cend) continue;
+                    const uint4 pv = *reinterpret_cast<const uint4*>(g_sP + (size_t)((c0 >> 3) * PQ + row * 16));
+                    const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        dpart = fmaf(__uint_as_float(pw[i] << 16), v[sub * 8 + 2 * i], dpart);
+                        dpart = fmaf(__uint_as_float(pw[i] & 0xffff0000u), v[sub * 8 + 2 * i + 1], dpart);
+                    }
+                }
+            }
+            s_dpart[tid] = dpart;
+            __syncthreads();
+            Dr = s_dpart[row] + s_dpart[row + 128];
+        }
         // ---- dS = P (dP - D) ---------------------------------------------------------------------------------------------------------
         for (int g0 = cbeg & ~15; g0 < cend; g0 += 16) {
             float v[16];
@@ -358,7 +384,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
 
 inline size_t attn_bwd_smem(int T) {
     const int NP = attn_np(T), PQ = attn_plane(128), PK = attn_plane(NP);
-    return (size_t)2 * (NP / 8) * PQ + 16 * PK + 16 * PQ + 64;
+    return (size_t)2 * (NP / 8) * PQ + 16 * PK + 16 * PQ + 64 + 256 * sizeof(float);
 }
 
 }  // namespace tc

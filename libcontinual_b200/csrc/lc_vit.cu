@@ -3,6 +3,7 @@
 #include "gemm_tc.cuh"
 #include "attn_tc.cuh"
 #include "vit_ops.cuh"
+#include "lora_ops.cuh"
 
 using namespace lc;
 
@@ -147,9 +148,7 @@ int lc_attn_backward(const void* qkv_bf16, const void* out_bf16, const void* dou
         if (cudaFuncSetAttribute(tc::attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return LC_ERR_CUDA;
         attr_smem = smem;
     }
-    const long long rows = (long long)batch * T;
-    tc::attn_rowdot_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(dout_bf16),
-                                                                                        reinterpret_cast<const __nv_bfloat16*>(out_bf16), rowdot, rows, T, heads);
+    (void)out_bf16;      // the softmax row term is formed on chip from P and dP (attn_tc.cuh); O is not read
     tc::AttnBwdArgs a{reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse2, rowdot,
                       reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), T, heads, error_flag};
     tc::attn_bwd_kernel<<<dim3(heads, batch), 256, smem, (cudaStream_t)stream>>>(a);
@@ -212,6 +211,39 @@ int lc_l2p_backward(const float* dprompts, const int64_t* ids, int pool, int top
 int lc_cast_bf16(const float* in, void* out_bf16, long long n, lc_stream_t stream) {
     LC_CHECK_ARG(in && out_bf16 && n >= 1);
     cast_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n);
+    return lc_launch_status();
+}
+
+int lc_transpose_bf16(const void* in_bf16, long long ld_in, long long rows, int cols, void* out_bf16, long long ld_out, lc_stream_t stream) {
+    LC_CHECK_ARG(in_bf16 && out_bf16 && rows >= 1 && cols >= 1 && ld_in >= cols && ld_out >= rows);
+    transpose_bf16_kernel<<<dim3((unsigned)((ld_out + 63) / 64), (cols + 63) / 64), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(in_bf16), ld_in, rows, cols, reinterpret_cast<__nv_bfloat16*>(out_bf16), ld_out);
+    return lc_launch_status();
+}
+int lc_lora_merge(const float* w, const float* A, const float* B, const float* scale, int slab_mask, int layers, int dim, int rank, void* wb_bf16,
+                  void* wbt_bf16, float* w_out, lc_stream_t stream) {
+    LC_CHECK_ARG(w && A && B && layers >= 1 && dim >= 32 && dim % 32 == 0 && rank >= 1 && rank <= kLoraMaxR && slab_mask >= 1 && slab_mask <= 7);
+    LC_CHECK_ARG(wb_bf16 || wbt_bf16 || w_out);
+    LoraMergeArgs a{};
+    a.w = w; a.A = A; a.B = B; a.scale = scale; a.wb = reinterpret_cast<__nv_bfloat16*>(wb_bf16); a.wbt = reinterpret_cast<__nv_bfloat16*>(wbt_bf16);
+    a.w_out = w_out; a.D = dim; a.R = rank; a.ns = 0;
+    for (int s = 0; s < 3; ++s) if (slab_mask & (1 << s)) a.slab[a.ns++] = s;
+    lora_merge_kernel<<<dim3(dim / 32, dim / 32, layers * a.ns), dim3(32, 8), 0, (cudaStream_t)stream>>>(a);
+    return lc_launch_status();
+}
+long long lc_lora_bgrad_partial_floats(int nslab, int dim, int rank, int nchunk) { return (long long)nslab * dim * rank * nchunk; }
+int lc_lora_bgrad_rows(const void* x_bf16, long long ldx, int x0, int x_slab_stride, int nslab, int dim, const float* z, int ldz, int rank, long long rows, float* partial,
+                       int nchunk, float* out, lc_stream_t stream) {
+    LC_CHECK_ARG(x_bf16 && z && partial && out && nslab >= 1 && dim >= 768 && dim % 768 == 0 && rank >= 1 && rank <= 16 && rows >= 1 && nchunk >= 1);
+    LC_CHECK_ARG(ldx % 4 == 0 && x0 % 4 == 0 && x_slab_stride % 4 == 0 && ldz >= nslab * rank);
+    const int rows_per = (int)((rows + nchunk - 1) / nchunk);
+    const dim3 grid(nslab * (dim / 768), nchunk);
+    const __nv_bfloat16* X = reinterpret_cast<const __nv_bfloat16*>(x_bf16);
+    if (rank <= 10) rowouter_partial_kernel<10><<<grid, 192, 0, (cudaStream_t)stream>>>(X, ldx, x0, x_slab_stride, dim, z, ldz, rank, rows, rows_per, partial);
+    else rowouter_partial_kernel<16><<<grid, 192, 0, (cudaStream_t)stream>>>(X, ldx, x0, x_slab_stride, dim, z, ldz, rank, rows, rows_per, partial);
+    if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
+    const long long per_chunk = (long long)nslab * dim * rank;
+    rowouter_reduce_kernel<<<grid_for(per_chunk, 256), 256, 0, (cudaStream_t)stream>>>(partial, per_chunk, nchunk, out);
     return lc_launch_status();
 }
 

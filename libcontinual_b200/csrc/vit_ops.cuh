@@ -231,4 +231,23 @@ __global__ void __launch_bounds__(192) l2p_backward_kernel(const float* dprompts
     }
 }
 
+// out[c][r] = in[r][c] for a bf16 matrix [rows][cols] (row stride ld_in) -> [cols][ld_out]; columns r in [rows, ld_out) of `out` are zero-filled
+// (the K padding of the token-contraction GEMM h^T h of InfLoRA's input matrix, transformer.py:242-244).  grid (ceil(ld_out/64), ceil(cols/64)), block (64, 4)... 32x32 tiles of 2-byte elements.
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* in, long long ld_in, long long rows, int cols, __nv_bfloat16* out, long long ld_out) {
+    __shared__ __nv_bfloat16 tile[64][66];
+    const long long r0 = (long long)blockIdx.x * 64;
+    const int c0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    for (int i = ty; i < 64; i += 4) {
+        const long long r = r0 + i;
+        tile[i][tx] = (r < rows && c0 + tx < cols) ? in[(size_t)r * ld_in + c0 + tx] : __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();
+    for (int i = ty; i < 64; i += 4) {
+        const int c = c0 + i;
+        const long long r = r0 + tx;
+        if (c < cols && r < ld_out) out[(size_t)c * ld_out + r] = tile[tx][i];
+    }
+}
+
 }  // namespace lc

@@ -50,6 +50,8 @@ class ViTZoo(nn.Module):
         self.task_id = None
         self.feat_dim = DIM
         self.depth = depth
+        self.attn_layer = kwargs.get("attn_layer", "MultiHeadAttention")       # vit.py:48; the adapters themselves are installed by the method plugin
+        self.lora_rank = int(kwargs.get("lora_rank", 10))
         self.engine = ViTEngine(depth=depth, device=device)
         if state is None:
             if pretrained:

@@ -113,3 +113,56 @@ class Adam(torch.optim.Optimizer):
         mdl = self.model
         check(self.lib.lc_adam(mdl.theta.data_ptr(), mdl.theta_grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), mdl.theta.numel(),
                                self.hp.data_ptr(), torch.cuda.current_stream().cuda_stream), "adam")
+
+
+class FlatSGD(torch.optim.Optimizer):
+    """torch.optim.SGD (momentum, weight decay; config/InfLoRA_opt-vit-imagenetr-b20-20-10.yaml:44-48) over the ACTIVE ranges of a model's flat
+    trainable arena (`model.theta`, `model.theta_grad`, `model.active_ranges()`), one fused kernel per range.  Momentum buffers are rebuilt
+    with the optimizer every task, like the reference (trainer.py:294)."""
+
+    def __init__(self, params, lr=1e-3, momentum=0.0, weight_decay=0.0, *, model=None):
+        if model is None or not hasattr(model, "theta") or not hasattr(model, "active_ranges"):
+            raise ValueError("libcontinual_b200.optim.FlatSGD needs model= with .theta / .theta_grad / .active_ranges()")
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+        self.model = model
+        self.buf = torch.zeros_like(model.theta)
+        self.hp = torch.zeros(4, device=model.theta.device)
+        self._hp_host = None
+        from . import _lib
+        self.lib = _lib.load()
+
+    def sync_hp(self):
+        g = self.param_groups[0]
+        hp = (float(g["lr"]), float(g["momentum"]), float(g["weight_decay"]))
+        if hp != self._hp_host:
+            self.hp[:3] = torch.tensor(hp, device=self.hp.device)
+            self._hp_host = hp
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        mdl = self.model
+        self.sync_hp()
+        ag = getattr(mdl, "autograd_grads", None)
+        base = mdl.theta.data_ptr()
+        src = None
+        for grp in self.param_groups:
+            for p in grp["params"]:
+                if p.grad is None:
+                    continue
+                off = (p.data_ptr() - base) // 4
+                if ag is not None and p.grad.data_ptr() == ag.data_ptr() + off * 4:
+                    src = ag                                                   # the copy loss.backward() produced, already in arena layout
+                elif p.grad.data_ptr() != mdl.theta_grad.data_ptr() + off * 4:
+                    mdl.theta_grad[off:off + p.numel()].copy_(p.grad.reshape(-1))     # foreign gradient: gather it
+        self.launch(mdl.theta_grad if src is None else src)
+        return None
+
+    def launch(self, grads=None):
+        """The update kernels alone (hp already on the device): what a captured step replays."""
+        mdl = self.model
+        g = mdl.theta_grad if grads is None else grads
+        st = torch.cuda.current_stream().cuda_stream
+        for lo, hi in mdl.active_ranges():
+            assert lo % 4 == 0
+            check(self.lib.lc_sgd_momentum(mdl.theta.data_ptr() + 4 * lo, g.data_ptr() + 4 * lo, self.buf.data_ptr() + 4 * lo, hi - lo, self.hp.data_ptr(), st),
+                  "sgd_momentum")

@@ -161,3 +161,60 @@ class GraphedL2PStep:
 
     def correct(self) -> torch.Tensor:
         return self.model.scal[1]
+
+
+class GraphedFlatStep:
+    """A flat-arena method (`model.theta` / `model.theta_grad` / `model._launch_step(x, y)`, e.g. `model.inflora.InfLoRA_OPT`) with
+    `optim.FlatSGD`: forward + backward captured as one CUDA graph, the optimizer kernels as a second one; with world_size > 1 the flat
+    gradient arena is all-reduced (average) in between — the only collective on the data path."""
+
+    def __init__(self, model, optimizer, batch_size: int, process_group=None, warmup: int = 2, img: int = 224):
+        from .optim import FlatSGD
+        assert isinstance(optimizer, FlatSGD), "GraphedFlatStep drives the fused flat SGD"
+        self.model, self.opt, self.eng, self.B = model, optimizer, model.engine, batch_size
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if (process_group is not None or (
+            torch.distributed.is_available() and torch.distributed.is_initialized())) else 1
+        dev = self.eng.dev
+        self.x = torch.zeros(batch_size, 3, img, img, device=dev)
+        self.y = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+        optimizer.sync_hp()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        saved = (model.theta.clone(), optimizer.buf.clone())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                model._launch_step(self.x, self.y)
+                optimizer.launch()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        model.theta.copy_(saved[0]); optimizer.buf.copy_(saved[1])
+        l0 = self.eng.launches
+        self.g_main = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_main):
+            model._launch_step(self.x, self.y)
+            if self.world == 1:
+                optimizer.launch()
+        self.g_upd = None
+        if self.world > 1:
+            self.g_upd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_upd):
+                optimizer.launch()
+        self.launches_per_step = self.eng.launches - l0 + len(model.active_ranges())
+        self.steps = 0
+
+    def run(self, x: torch.Tensor, y: torch.Tensor, non_blocking: bool = True):
+        self.opt.sync_hp()
+        self.x.copy_(x, non_blocking=non_blocking)
+        self.y.copy_(y, non_blocking=non_blocking)
+        self.g_main.replay()
+        if self.world > 1:
+            allreduce_mean_(self.model.theta_grad, self.pg)
+            self.g_upd.replay()
+        self.steps += 1
+
+    def loss(self) -> torch.Tensor:
+        return self.model.scal[0]
+
+    def correct(self) -> torch.Tensor:
+        return self.model.scal[1]

@@ -48,7 +48,7 @@ class _Workspace:
     """Activation buffers of one (batch, tokens) shape.  With `save` every block keeps what its backward needs:
     x_in / x_mid (LayerNorm inputs), qkv, attention output + row log-sum-exp, pre-GELU fc1 output."""
 
-    def __init__(self, B: int, T: int, depth: int, save: bool, dev):
+    def __init__(self, B: int, T: int, depth: int, save: bool, dev, lora_cols: int = 0):
         self.B, self.T, self.Tp, self.save = B, T, _up8(T), save
         bf, f32 = torch.bfloat16, torch.float32
         n = B * T
@@ -65,7 +65,8 @@ class _Workspace:
         self.y = torch.empty(B, T, DIM, device=dev, dtype=f32)
         self.ystat = torch.empty(n, 2, device=dev, dtype=f32)
         self.feat = torch.empty(B, DIM, device=dev, dtype=f32)
-
+        # LoRA down-projections h A^T of every block (fp32 [n, adapted slabs * rank]), kept for the adapter gradients
+        self.hA = [torch.empty(n, lora_cols, device=dev, dtype=f32) for _ in range(depth if save else 1)] if lora_cols else None
         self.bwd = None
 
     def idx(self, layer: int) -> int:
@@ -83,6 +84,32 @@ class _Workspace:
         return self.bwd
 
 
+class LoraState:
+    """Adapters on `slabs` (0 = q, 1 = k, 2 = v) of the fused QKV projection of every block: A [L][ns][r][D] (fixed during a task), B / dB
+    [L][ns][D][r] (views of the owner's flat trainable / gradient arenas)."""
+
+    def __init__(self, engine: "ViTEngine", slabs, rank: int, B: torch.Tensor, dB: torch.Tensor):
+        L = engine.depth
+        self.slabs, self.ns, self.rank = tuple(slabs), len(slabs), rank
+        assert self.ns in (1, 2) and all(0 <= s <= 2 for s in slabs) and list(slabs) == sorted(slabs)
+        self.slab_mask = sum(1 << s for s in slabs)
+        self.cols = self.ns * rank
+        assert self.cols % 4 == 0, "adapted slabs * rank must be a multiple of 4 (fp32 rows of the down-projection are stored 16-byte aligned)"
+        self.A = torch.zeros(L, self.ns, rank, DIM, device=engine.dev)
+        self.A_bf = torch.zeros(L, self.cols, DIM, device=engine.dev, dtype=torch.bfloat16)
+        assert B.shape == (L, self.ns, DIM, rank) and dB.shape == B.shape and B.is_contiguous() and dB.is_contiguous()
+        self.B, self.dB = B, dB
+        self.nchunk = 148
+        self.partial = torch.empty(engine.lib.lc_lora_bgrad_partial_floats(self.ns, DIM, rank, self.nchunk), device=engine.dev)
+        self.active = False
+        self.engine = engine
+
+    def set_A(self, A: torch.Tensor):
+        """Installs the down-projections for the coming task (and their BF16 GEMM copy)."""
+        self.A.copy_(A.reshape(self.A.shape))
+        self.engine._cast(self.A.reshape(self.A_bf.shape), self.A_bf)
+
+
 class ViTEngine:
     def __init__(self, depth: int = 12, device=None):
         self.lib = _lib.load()
@@ -97,19 +124,36 @@ class ViTEngine:
         self.err = torch.zeros(1, device=self.dev, dtype=torch.int32)
         self._ws: Dict[tuple, _Workspace] = {}
         self.launches = 0
+        self.lora: Optional[LoraState] = None
+        self.cov: Optional[torch.Tensor] = None       # [L, 768, 768] running sums of h^T h while an input-matrix pass is on (see input_matrix_begin)
+        self.cov_rows = 0
 
     # ---- weights -------------------------------------------------------------------------------
     def load_state(self, state: Dict[str, torch.Tensor]):
         """`state`: the reference `VisionTransformer.state_dict()` (keys as in `vit_param_layout`; `ViTZoo` maps timm names onto them:
         vit.py:70-84)."""
+        # the fused QKV weights of all layers share one arena per representation, so that the adapter merge (lc_lora_merge) is one launch
+        L = self.depth
+        self.qkv_w = torch.empty(L, 3 * DIM, DIM, device=self.dev, dtype=torch.float32)
+        self.qkv_wb = torch.empty(L, 3 * DIM, DIM, device=self.dev, dtype=torch.bfloat16)
+        self.qkv_wbt = torch.empty(L, DIM, 3 * DIM, device=self.dev, dtype=torch.bfloat16)
         for name, shape in self.layout:
             t = state[name].detach().to(self.dev, torch.float32).contiguous()
             assert tuple(t.shape) == tuple(shape), (name, t.shape, shape)
+            if name.endswith("attn.qkv.weight"):
+                i = int(name.split(".")[2])
+                self.qkv_w[i].copy_(t)
+                t = self.qkv_w[i]
             self.w[name] = t
         gemm_w = ["patch_embed.proj.weight"] + [f"transformer.blocks.{i}.{n}.weight" for i in range(self.depth)
                                                  for n in ("attn.qkv", "attn.proj", "mlp.fc1", "mlp.fc2")]
         for name in gemm_w:
             w2 = self.w[name].reshape(self.w[name].shape[0], -1)
+            if name.endswith("attn.qkv.weight"):
+                i = int(name.split(".")[2])
+                self.wb[name], self.wbt[name] = self.qkv_wb[i], self.qkv_wbt[i]
+                self._cast(w2, self.wb[name]); self._cast(w2.t().contiguous(), self.wbt[name])
+                continue
             self.wb[name] = self._cast(w2)
             if name != "patch_embed.proj.weight":
                 self.wbt[name] = self._cast(w2.t().contiguous())
@@ -117,15 +161,18 @@ class ViTEngine:
         self.pos_cls = self.w["pos_embed"][0, 0].contiguous()
         self.cls = self.w["cls_token"].reshape(DIM).contiguous()
 
-    def _cast(self, t: torch.Tensor) -> torch.Tensor:
-        out = torch.empty(t.shape, device=self.dev, dtype=torch.bfloat16)
+    def _cast(self, t: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty(t.shape, device=self.dev, dtype=torch.bfloat16)
+        assert t.is_contiguous() and out.is_contiguous() and out.shape == t.shape
         check(self.lib.lc_cast_bf16(t.data_ptr(), out.data_ptr(), t.numel(), stream_ptr()), "cast_bf16")
         return out
 
     def workspace(self, B: int, T: int, save: bool) -> _Workspace:
-        key = (B, T, save)
+        lc = self.lora.cols if self.lora is not None else 0
+        key = (B, T, save, lc)
         if key not in self._ws:
-            self._ws[key] = _Workspace(B, T, self.depth, save, self.dev)
+            self._ws[key] = _Workspace(B, T, self.depth, save, self.dev, lora_cols=lc)
         return self._ws[key]
 
     def tensor_core_error(self) -> bool:
@@ -189,6 +236,11 @@ class ViTEngine:
         xout = ws.x[i + 1] if ws.save else ws.x[(i + 1) % 2]
         xmid, qkv, o, upre = ws.xmid[k], ws.qkv[k], ws.o[k], ws.upre[k]
         self._ln(xin, pre + "ln_1", 1e-5, out_bf16=ws.h)
+        if self.cov is not None:
+            self._accumulate_input_matrix(i, ws)
+        if self.lora is not None and self.lora.active and ws.save:
+            lo = self.lora
+            self.gemm(ws.h.data_ptr(), DIM, lo.A_bf[i].data_ptr(), DIM, ws.hA[k].data_ptr(), lo.cols, B * T, lo.cols, DIM, out_f32=True)
         self._linear(ws.h, pre + "attn.qkv.weight", qkv, bias=pre + "attn.qkv.bias")
         check(self.lib.lc_attn_forward(qkv.data_ptr(), o.data_ptr(), ws.lse[k].data_ptr(), B, T, HEADS, self.err.data_ptr(), st), "attn_forward")
         self._linear(o, pre + "attn.proj.weight", xmid, bias=pre + "attn.proj.bias", residual=xin)
@@ -238,7 +290,7 @@ class ViTEngine:
               "layernorm_backward")
         self.launches += 1
 
-    def backward_tokens(self, ws: _Workspace, dfeat: torch.Tensor, n_prompt: int) -> torch.Tensor:
+    def backward_tokens(self, ws: _Workspace, dfeat: torch.Tensor, n_prompt: int, to_tokens: bool = True) -> Optional[torch.Tensor]:
         """Given d(loss)/d(pooled feature) [B, 768], returns d(loss)/d(input tokens) fp32 [B, T, 768] (ws must come from forward(save=True)).
         Autograd of transformer.py:2006-2017 / :1331-1336 / :169-197 restricted to the activations: no weight gradients (frozen backbone)."""
         assert ws.save, "backward needs the activations of forward(save=True)"
@@ -259,9 +311,53 @@ class ViTEngine:
             check(self.lib.lc_attn_backward(ws.qkv[i].data_ptr(), ws.o[i].data_ptr(), dO.data_ptr(), ws.lse[i].data_ptr(), rowdot.data_ptr(), dqkv.data_ptr(),
                                             B, T, HEADS, self.err.data_ptr(), st), "attn_backward")
             self.launches += 2
+            if self.lora is not None and self.lora.active:
+                self.lora_grads(i, ws, dqkv)
+            if i == 0 and not to_tokens:          # nothing trainable below the first attention (adapters only): stop here
+                return None
             self._linear_t(dqkv, pre + "attn.qkv.weight", dh)
             self._ln_bwd(dh, ws.x[i], pre + "ln_1", 1e-5, g2, g, gbf)
         return g
+
+    # ---- InfLoRA's input matrix (transformer.py:242-244, InfLoRA_opt.py:243-245) ----------------------
+    def input_matrix_begin(self):
+        self.cov = torch.zeros(self.depth, DIM, DIM, device=self.dev)
+        self.cov_rows = 0
+
+    def input_matrix_end(self) -> torch.Tensor:
+        """Mean over all tokens seen since input_matrix_begin() of h h^T, h = ln_1(x): [L, 768, 768] (the reference's `cur_matrix` per block)."""
+        out = self.cov / float(max(self.cov_rows, 1))
+        self.cov = None
+        return out
+
+    def _accumulate_input_matrix(self, i: int, ws: _Workspace):
+        n = ws.B * ws.T
+        npad = _up8(n)
+        if getattr(ws, "hT", None) is None:
+            ws.hT = torch.empty(DIM, npad, device=self.dev, dtype=torch.bfloat16)
+        check(self.lib.lc_transpose_bf16(ws.h.data_ptr(), DIM, n, DIM, ws.hT.data_ptr(), npad, stream_ptr()), "transpose_bf16")
+        c = self.cov[i]
+        self.gemm(ws.hT.data_ptr(), npad, ws.hT.data_ptr(), npad, c.data_ptr(), DIM, DIM, DIM, npad, residual=c.data_ptr(), ldr=DIM, out_f32=True)
+        self.launches += 1
+        if i == 0:
+            self.cov_rows += n
+
+    # ---- low-rank adapters on the QKV projection ----------------------------------------------------
+    def lora_merge(self, w_out: bool = False):
+        """W' = W + B A for the adapted slabs of every layer into the BF16 GEMM operands (w_out: also into the fp32 master = `merge_weight`)."""
+        lo = self.lora
+        check(self.lib.lc_lora_merge(self.qkv_w.data_ptr(), lo.A.data_ptr(), lo.B.data_ptr(), None, lo.slab_mask, self.depth, DIM, lo.rank,
+                                     self.qkv_wb.data_ptr(), self.qkv_wbt.data_ptr(), self.qkv_w.data_ptr() if w_out else None, stream_ptr()), "lora_merge")
+        self.launches += 1
+
+    def lora_grads(self, i: int, ws: _Workspace, dqkv: torch.Tensor):
+        """d lora_B[i] = d(slab)^T (h A^T): rank-form adapter gradient of block i from the token gradient of the adapted QKV slabs."""
+        lo = self.lora
+        n = ws.B * ws.T
+        check(self.lib.lc_lora_bgrad_rows(dqkv.data_ptr(), 3 * DIM, lo.slabs[0] * DIM, (lo.slabs[1] - lo.slabs[0]) * DIM if lo.ns > 1 else DIM, lo.ns, DIM,
+                                          ws.hA[i].data_ptr(), lo.cols, lo.rank, n, lo.partial.data_ptr(), lo.nchunk, lo.dB[i].data_ptr(), stream_ptr()),
+              "lora_bgrad_rows")
+        self.launches += 2
 
     def prompt_row_grads(self, g: torch.Tensor, n_prompt: int, out: torch.Tensor) -> torch.Tensor:
         """Gradient of the prompt rows shared by the batch: out[r] = sum_b g[b, r]  (the `repeat(B, 1)` of prompt.py:390)."""

@@ -10,6 +10,7 @@ torch RNG, so the tests can regenerate the inputs and initial weights bit-exactl
 """
 from __future__ import annotations
 
+import math
 import os
 import sys
 
@@ -501,10 +502,115 @@ def golden_l2p(core):
     np.savez_compressed(os.path.join(OUT, "l2p_vit.npz"), **out)
 
 
+def synth_lora_state(seed: int, depth: int = 12, rank: int = 10, n_head: int = 20, slabs: str = "kv"):
+    """Adapters for every block (A ~ orthonormal-ish rows / sqrt(3) scale, B small but non-zero so that the merge is exercised) + one head."""
+    rng = np.random.default_rng(seed)
+    lora = []
+    for _ in range(depth):
+        d = {}
+        for sn in slabs:
+            d[f"A_{sn}"] = torch.from_numpy((rng.standard_normal((rank, 768)) / np.sqrt(768 * 3)).astype(np.float32))
+            d[f"B_{sn}"] = torch.from_numpy((0.05 * rng.standard_normal((768, rank))).astype(np.float32))
+        lora.append(d)
+    bound = 1.0 / np.sqrt(768)
+    hw = torch.from_numpy(rng.uniform(-bound, bound, (n_head, 768)).astype(np.float32))
+    hb = torch.from_numpy(rng.uniform(-bound, bound, (n_head,)).astype(np.float32))
+    return lora, hw, hb
+
+
+def golden_inflora(core):
+    """The real `core.model.InfLoRA_opt.InfLoRA_OPT` on `vit_pt_imnet(attn_layer='MultiHeadAttention_LoRA', lora_rank=10)`: observe() on
+    task 0 and task 1 with given adapters, the input-matrix pass (`update_input_matrix`) and the task-0 basis (SVD)."""
+    from core.model.backbone.vit import vit_pt_imnet
+    from core.model.InfLoRA_opt import InfLoRA_OPT as RefInfLoRA
+    from core.utils import init_seed
+    print("InfLoRA_OPT / ViT-B/16: reference observe() vs oracle")
+    init_seed(42, True)                              # sets PYTHONHASHSEED, read by InfLoRA_opt.py:55
+    out = {}
+    p, _, _, _, _ = synth_vit_state(5150)
+    bb = vit_pt_imnet(pretrained=False, attn_layer="MultiHeadAttention_LoRA", lora_rank=10)
+    ref = RefInfLoRA(bb, torch.device("cpu"), init_cls_num=20, inc_cls_num=20, task_num=10, lame=1.0, lamb=0.95, embd_dim=768, use_ca=False,
+                     dataset="imagenet-r")
+    ref._network.backbone.feat.load_state_dict(p, strict=False)
+    for task in (0, 1):
+        lora, hw, hb = synth_lora_state(880 + task)
+        # what before_task does around the loader pass (InfLoRA_opt.py:207-229), with the adapters given instead of derived
+        if task == 1:
+            ref._known_classes = ref.init_cls_num
+        ref._network.update_fc(None)
+        for i, mod in enumerate(ref.attention_modules):
+            mod.init_param()
+            with torch.no_grad():
+                mod.lora_A_k.weight.copy_(lora[i]["A_k"]); mod.lora_B_k.weight.copy_(lora[i]["B_k"])
+                mod.lora_A_v.weight.copy_(lora[i]["A_v"]); mod.lora_B_v.weight.copy_(lora[i]["B_v"])
+        for name, prm in ref._network.named_parameters():
+            prm.requires_grad_(f"classifier_pool.{task}." in name or "lora_B" in name)
+            prm.grad = None
+        head = ref._network.classifier_pool[task]
+        with torch.no_grad():
+            head.weight.copy_(hw); head.bias.copy_(hb)
+        lo = 0 if task == 0 else 20
+        x, y = synth_images(700 + task, 4, lo, lo + 20)
+        ref._network.train()
+        pred, acc, loss = ref.observe({"image": x, "label": y})
+        loss.backward()
+        # oracle
+        ol = [{k: v.clone().requires_grad_(k.startswith("B_")) for k, v in d.items()} for d in lora]
+        ow = hw.clone().requires_grad_(True); ob = hb.clone().requires_grad_(True)
+        po = p if task == 0 else p1
+        ologits = port.inflora_logits(po, ol, ow, ob, x)
+        oloss = F.cross_entropy(ologits, y - lo)
+        oloss.backward()
+        close(oloss, loss, 1e-6, 1e-7, f"inflora task{task} loss")
+        close(ow.grad, head.weight.grad, 1e-4, 2e-6, f"inflora task{task} dW")
+        close(ob.grad, head.bias.grad, 1e-4, 2e-6, f"inflora task{task} db")
+        dBk = torch.stack([m.lora_B_k.weight.grad for m in ref.attention_modules]); dBv = torch.stack([m.lora_B_v.weight.grad for m in ref.attention_modules])
+        close(torch.stack([d["B_k"].grad for d in ol]), dBk, 1e-4, 2e-6, f"inflora task{task} dB_k")
+        close(torch.stack([d["B_v"].grad for d in ol]), dBv, 1e-4, 2e-6, f"inflora task{task} dB_v")
+        with torch.no_grad():
+            rlogits = ref._network(x)
+        out[f"t{task}/loss"] = np.float64(loss.item()); out[f"t{task}/logits"] = rlogits.numpy().copy(); out[f"t{task}/pred"] = pred.numpy().copy()
+        out[f"t{task}/dW"] = head.weight.grad.numpy().copy(); out[f"t{task}/db"] = head.bias.grad.numpy().copy()
+        out[f"t{task}/dB_k"] = dBk.numpy().copy(); out[f"t{task}/dB_v"] = dBv.numpy().copy()
+        if task == 0:
+            # input-matrix pass (two batches) with the adapters applied, then the task-0 basis of two blocks
+            xs = [synth_images(710 + j, 3, 0, 20)[0] for j in range(2)]
+            for mod in ref.attention_modules:
+                mod.reset_input_matrix()
+            with torch.no_grad():
+                for xb in xs:
+                    ref._network.update_input_matrix(x=xb)
+            cur = port.inflora_input_matrices(p, lora, xs)
+            proj = torch.from_numpy(np.random.default_rng(99).standard_normal((768, 8)).astype(np.float32))
+            for i, mod in enumerate(ref.attention_modules):
+                close(cur[i], mod.cur_matrix, 1e-4, 1e-6, f"inflora input matrix {i}")
+            out["cov/proj"] = torch.stack([m.cur_matrix @ proj for m in ref.attention_modules]).numpy().copy()
+            out["cov/trace"] = np.array([float(m.cur_matrix.trace()) for m in ref.attention_modules])
+            for i in (0, 11):
+                U, S, _ = torch.linalg.svd(ref.attention_modules[i].cur_matrix, full_matrices=False)
+                close(port.inflora_init_A(cur[i], 10).abs(), (U[:, :10].T / math.sqrt(3)).abs(), 1e-3, 1e-5, f"inflora basis {i}")
+                out[f"cov/S{i}"] = S[:16].numpy().copy()
+                out[f"cov/P{i}"] = (U[:, :10] @ U[:, :10].T @ proj).numpy().copy()        # projector onto the basis (sign / rotation free)
+            # merge_weight() (after_task, InfLoRA_opt.py:266-267): the merged QKV weights feed task 1
+            for mod in ref.attention_modules:
+                mod.merge_weight()
+            p1 = dict(p)
+            for i in range(12):
+                p1[f"transformer.blocks.{i}.attn.qkv.weight"] = port.lora_merge_qkv(p[f"transformer.blocks.{i}.attn.qkv.weight"], lora[i]["A_k"], lora[i]["B_k"],
+                                                                                   lora[i]["A_v"], lora[i]["B_v"])
+                close(p1[f"transformer.blocks.{i}.attn.qkv.weight"], ref.attention_modules[i].qkv.weight, 0, 0, f"merged qkv {i}")
+    np.savez_compressed(os.path.join(OUT, "inflora_vit.npz"), **out)
+
+
 def main():
     torch.set_num_threads(8)
     os.makedirs(OUT, exist_ok=True)
     core = import_reference()
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if only:                                   # python oracle/make_golden.py inflora [l2p ...]
+        for name in only:
+            globals()["golden_" + name](core)
+        return
     golden_ewc(core)
     golden_icarl(core)
     golden_lwf(core)
@@ -512,6 +618,7 @@ def main():
     golden_herding(core)
     golden_ops(core)
     golden_l2p(core)
+    golden_inflora(core)
     print("golden vectors written to", OUT)
 
 

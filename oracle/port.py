@@ -327,11 +327,15 @@ def _bf16_round(t: Tensor) -> Tensor:
 
 
 def vit_tokens(p: Dict[str, Tensor], x: Tensor, prompts: Optional[Tensor] = None, depth: int = 12, heads: int = 12, gemm_mode: str = "fp32",
-               taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
+               taps: Optional[Dict[str, Tensor]] = None, lora: Optional[Sequence[Dict[str, Tensor]]] = None,
+               prefix: Optional[Dict[int, Tuple[Tensor, Tensor]]] = None, attn_inputs: Optional[List[Tensor]] = None) -> Tensor:
     """`VisionTransformer.forward(prompt_flag='l2p')` up to and including the final LayerNorm: [B, (P +) 197, D].
     `prompts` [B, P, D] are prepended in front of [cls, patches] AFTER the position embedding was added (transformer.py:2240-2251,
     :2010-2014).  gemm_mode 'bf16' rounds every GEMM operand (and the stored qkv / probabilities / GELU output) to BF16 exactly where
-    the CUDA path does; accumulation stays fp32."""
+    the CUDA path does; accumulation stays fp32.
+    `lora[i]` = {'A_k','B_k','A_v','B_v'} (or 'A_q','B_q'): weight-side adapters of block i, W_s + B_s A_s (transformer.py:246-254).
+    `prefix[i]` = (pk, pv) [B, P, D]: prefix keys / values concatenated in front of block i's K, V (transformer.py:175-180).
+    `attn_inputs` (a list) receives ln_1(x) of every block, the matrix InfLoRA's `get_input_matrix` accumulates (transformer.py:242-244)."""
     r = _bf16_round if gemm_mode == "bf16" else (lambda t: t)
     B = x.shape[0]
     D = p["cls_token"].shape[-1]
@@ -349,9 +353,22 @@ def vit_tokens(p: Dict[str, Tensor], x: Tensor, prompts: Optional[Tensor] = None
     for i in range(depth):
         b = f"transformer.blocks.{i}."
         h = F.layer_norm(xs, (D,), p[b + "ln_1.weight"], p[b + "ln_1.bias"], 1e-5)
-        qkv = r(F.linear(r(h), r(p[b + "attn.qkv.weight"]), p[b + "attn.qkv.bias"]))
+        if attn_inputs is not None:
+            attn_inputs.append(h.detach())
+        w_qkv = p[b + "attn.qkv.weight"]
+        if lora is not None:
+            slabs = list(w_qkv.chunk(3, dim=0))
+            for si, sn in enumerate("qkv"):
+                if f"A_{sn}" in lora[i]:
+                    slabs[si] = slabs[si] + lora[i][f"B_{sn}"] @ lora[i][f"A_{sn}"]
+            w_qkv = torch.cat(slabs, dim=0)
+        qkv = r(F.linear(r(h), r(w_qkv), p[b + "attn.qkv.bias"]))
         qkv = qkv.reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
         q, k, v = qkv[0], qkv[1], qkv[2]
+        if prefix is not None and i in prefix:
+            pk, pv = prefix[i]
+            k = torch.cat([r(pk).reshape(B, -1, heads, hd).permute(0, 2, 1, 3), k], dim=2)
+            v = torch.cat([r(pv).reshape(B, -1, heads, hd).permute(0, 2, 1, 3), v], dim=2)
         attn = r(((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(dim=-1))
         o = r((attn @ v).transpose(1, 2).reshape(B, T, D))
         xs = xs + F.linear(o, r(p[b + "attn.proj.weight"]), p[b + "attn.proj.bias"])
@@ -381,6 +398,39 @@ def l2p_loss(logits: Tensor, y: Tensor, lo: int, hi: int, reduce_sim: Tensor, co
     masked = torch.full_like(logits, float("-inf"))
     masked[:, lo:hi] = logits[:, lo:hi]
     return F.cross_entropy(masked, y) - coeff * reduce_sim, masked
+
+
+# ----------------------------------------------------------------------------------------------
+# InfLoRA_OPT on ViT-B/16  (core/model/InfLoRA_opt.py:107-121 SiNet.forward, :175-189 observe; transformer.py:199-274)
+# ----------------------------------------------------------------------------------------------
+def inflora_logits(p: Dict[str, Tensor], lora: Sequence[Dict[str, Tensor]], head_w: Tensor, head_b: Tensor, x: Tensor, depth: int = 12,
+                   heads: int = 12, gemm_mode: str = "fp32") -> Tensor:
+    """features = final-LayerNorm cls token of the adapted backbone (vit.py:128-131), logits = classifier_pool[task](features)."""
+    feat = vit_tokens(p, x, None, depth, heads, gemm_mode, lora=lora)[:, 0]
+    return F.linear(feat, head_w, head_b)
+
+
+def inflora_input_matrices(p: Dict[str, Tensor], lora: Optional[Sequence[Dict[str, Tensor]]], batches: Sequence[Tensor], depth: int = 12,
+                           heads: int = 12) -> List[Tensor]:
+    """`update_input_matrix` over a loader (InfLoRA_opt.py:243-245, transformer.py:242-244): per block the running mean over tokens of
+    h h^T with h = ln_1(x) (the attention input), in the reference's update order."""
+    cur = [torch.zeros(p["cls_token"].shape[-1], p["cls_token"].shape[-1]) for _ in range(depth)]
+    n = 0
+    with torch.no_grad():
+        for x in batches:
+            hs: List[Tensor] = []
+            vit_tokens(p, x, None, depth, heads, "fp32", lora=lora, attn_inputs=hs)
+            m = hs[0].shape[0] * hs[0].shape[1]
+            for i, h in enumerate(hs):
+                cur[i] = (cur[i] * n + torch.bmm(h.permute(0, 2, 1), h).sum(dim=0)) / (n + m)
+            n += m
+    return cur
+
+
+def inflora_init_A(cur_matrix: Tensor, rank: int) -> Tensor:
+    """Task-0 adapter basis (InfLoRA_opt.py:248-254): the top-`rank` left singular vectors of the input matrix, scaled by 1/sqrt(3)."""
+    U, _, _ = torch.linalg.svd(cur_matrix, full_matrices=False)
+    return U[:, :rank].T / math.sqrt(3)
 
 
 # ----------------------------------------------------------------------------------------------

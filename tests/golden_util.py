@@ -76,3 +76,19 @@ def l2p_oracle_step(p, prm, key, fc_w, fc_b, x, y, lo, hi, top_k=5, coeff=1.0, g
         torch.nn.utils.clip_grad_norm_([oprm, okey, ow, ob], clip)
     return {"loss": loss.detach(), "logits": logits.detach(), "feat": feat.detach(), "major": major, "cls_features": cls_f, "reduce_sim": rs.detach(),
             "dprompt": oprm.grad, "dkey": okey.grad, "dW": ow.grad, "db": ob.grad}
+
+
+def synth_lora_state(seed, depth=12, rank=10, n_head=20, slabs="kv"):
+    """Same draws as oracle/make_golden.py::synth_lora_state."""
+    rng = np.random.default_rng(seed)
+    lora = []
+    for _ in range(depth):
+        d = {}
+        for sn in slabs:
+            d[f"A_{sn}"] = torch.from_numpy((rng.standard_normal((rank, 768)) / np.sqrt(768 * 3)).astype(np.float32))
+            d[f"B_{sn}"] = torch.from_numpy((0.05 * rng.standard_normal((768, rank))).astype(np.float32))
+        lora.append(d)
+    bound = 1.0 / np.sqrt(768)
+    hw = torch.from_numpy(rng.uniform(-bound, bound, (n_head, 768)).astype(np.float32))
+    hb = torch.from_numpy(rng.uniform(-bound, bound, (n_head,)).astype(np.float32))
+    return lora, hw, hb

@@ -172,3 +172,27 @@ def test_l2p_vit_observe_matches_reference():
         ref = torch.from_numpy(g["t1/" + k])
         err = float((o[k] - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
         assert err < 1e-4, (k, err)
+
+
+def test_inflora_vit_observe_matches_reference():
+    """Oracle InfLoRA_OPT step (weight-side adapters on k, v; CE over the task head) vs the real `core.model.InfLoRA_opt.InfLoRA_OPT`
+    (fixture: tests/golden/inflora_vit.npz), task 0 only here (the generator checked task 1 on the merged weights as well)."""
+    import torch.nn.functional as F
+    from tests.golden_util import synth_images, synth_lora_state, synth_vit_state
+    g = load("inflora_vit.npz")
+    torch.set_num_threads(8)
+    p = synth_vit_state(5150)[0]
+    lora, hw, hb = synth_lora_state(880)
+    x, y = synth_images(700, 4, 0, 20)
+    ol = [{k: v.clone().requires_grad_(k.startswith("B_")) for k, v in d.items()} for d in lora]
+    ow = hw.clone().requires_grad_(True); ob = hb.clone().requires_grad_(True)
+    logits = port.inflora_logits(p, ol, ow, ob, x)
+    loss = F.cross_entropy(logits, y)
+    loss.backward()
+    assert abs(float(loss) - float(g["t0/loss"])) < 1e-5
+    got = {"logits": logits.detach(), "dW": ow.grad, "db": ob.grad, "dB_k": torch.stack([d["B_k"].grad for d in ol]),
+           "dB_v": torch.stack([d["B_v"].grad for d in ol])}
+    for k, v in got.items():
+        ref = torch.from_numpy(g["t0/" + k])
+        err = float((v - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
+        assert err < 1e-4, (k, err)
