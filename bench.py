@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="icarl", choices=["icarl", "ewc", "l2p"])
+    ap.add_argument("--workload", default="icarl", choices=["icarl", "ewc", "l2p", "inflora"])
     ap.add_argument("--cpu-steps", type=int, default=12, help="timed oracle steps for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
@@ -53,7 +53,9 @@ def parse():
 def workload_name(w):
     return {"icarl": "iCaRL ResNet32 CIFAR-100 b50-5-10 (task 1: CE + KD vs frozen teacher), bs=128, synthetic 32x32",
             "ewc": "EWC ResNet32 CIFAR-100 b0-10-10 (task 1: CE + lamda*Fisher penalty), bs=128, synthetic 32x32",
-            "l2p": "L2P ViT-B/16 CIFAR-100 b10-10-10 (task 1: query pass + prompted pass + backward to prompts, clip, Adam), bs=128, synthetic 224x224"}[w]
+            "l2p": "L2P ViT-B/16 CIFAR-100 b10-10-10 (task 1: query pass + prompted pass + backward to prompts, clip, Adam), bs=128, synthetic 224x224",
+            "inflora": "InfLoRA_OPT ViT-B/16 ImageNet-R b20-20-10 (task 1: rank-10 adapters on k,v of 12 blocks + task head, CE, SGD momentum), bs=128 per GPU, "
+                       "synthetic 224x224"}[w]
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -181,17 +183,69 @@ def time_oracle_l2p(steps, warmup, batch, device="cpu"):
     return batch * steps / dt, dt / steps * 1e3, cores
 
 
+def inflora_synth_state(seed=1993, depth=12, rank=10):
+    """Random-init ViT-B/16 + adapters (A: orthonormal-scale rows / sqrt(3), B: small non-zero as after a few steps) + the 10 task heads."""
+    import numpy as np
+    import torch
+    from oracle import port  # only the init helper (weights are data, not compute)
+    rng = np.random.default_rng(seed)
+    p = port.vit_init(rng)
+    A = torch.from_numpy((rng.standard_normal((depth, 2, rank, 768)) / np.sqrt(768 * 3)).astype(np.float32))
+    B = torch.from_numpy((0.01 * rng.standard_normal((depth, 2, 768, rank))).astype(np.float32))
+    bound = 1.0 / np.sqrt(768)
+    hw = torch.from_numpy(rng.uniform(-bound, bound, (200, 768)).astype(np.float32))
+    hb = torch.from_numpy(rng.uniform(-bound, bound, (200,)).astype(np.float32))
+    return p, A, B, hw, hb
+
+
+def time_oracle_inflora(steps, warmup, batch, device="cpu"):
+    """The oracle restatement of InfLoRA_OPT.observe + backward + SGD (pinned to the reference by tests/golden/inflora_vit.npz): weight-side
+    adapters `W + B A` and autograd's dense weight gradients, as the reference computes them."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p, A, B, hw, hb = inflora_synth_state()
+    dev = torch.device("cuda", 0) if device == "cuda" else torch.device("cpu")
+    p = {k: v.to(dev) for k, v in p.items()}
+    lora = [{"A_k": A[i, 0].to(dev), "B_k": B[i, 0].to(dev).requires_grad_(True), "A_v": A[i, 1].to(dev), "B_v": B[i, 1].to(dev).requires_grad_(True)}
+            for i in range(12)]
+    w = hw[20:40].to(dev).requires_grad_(True); b = hb[20:40].to(dev).requires_grad_(True)
+    tr = [d["B_k"] for d in lora] + [d["B_v"] for d in lora] + [w, b]
+    opt = torch.optim.SGD(tr, lr=8e-3, momentum=0.9)
+    batches = [(x.to(dev), y.to(dev)) for x, y in l2p_batches(2, batch, 20, 40)]
+    sync = (lambda: torch.cuda.synchronize()) if device == "cuda" else (lambda: None)
+
+    def one(x, y):
+        loss = F.cross_entropy(port.inflora_logits(p, lora, w, b, x), y - 20)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss.item()
+    for i in range(warmup):
+        one(*batches[i % 2])
+    sync()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(*batches[i % 2])
+    sync()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, cores
+
+
 def run_reference_l2p(args):
     on_gpu = args.ref_device == "cuda"
     batch = BATCH if on_gpu else 16
     steps, warm = (max(1, min(args.steps, 20)), 3) if on_gpu else (max(1, min(args.steps, 6)), 1)
-    ips, ms, cores = time_oracle_l2p(steps, warm, batch, args.ref_device)
+    timer = time_oracle_inflora if args.workload == "inflora" else time_oracle_l2p
+    ips, ms, cores = timer(steps, warm, batch, args.ref_device)
     line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name("l2p"), "global_batch": batch,
+            "config": {"workload": workload_name(args.workload), "global_batch": batch,
                        "device": "cuda:0 (PyTorch eager fp32, context only)" if on_gpu else "cpu"},
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} full L2P steps of {batch} images (bounded sample of the bs-128 step; oracle/port.py, PyTorch "
+                             "sample": f"{steps} full {args.workload} steps of {batch} images (bounded sample of the bs-128 step; oracle/port.py, PyTorch "
                                        + ("eager on cuda:0)" if on_gpu else f"CPU fp32, {cores} threads)")},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -201,7 +255,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if args.workload == "l2p":
+    if args.workload in ("l2p", "inflora"):
         return run_reference_l2p(args)
     on_gpu = args.ref_device == "cuda"
     steps, warm = (max(1, min(args.steps, 200)), max(3, min(args.warmup, 20))) if on_gpu else (max(1, min(args.steps, 40)), max(1, min(args.warmup, 3)))
@@ -327,11 +381,11 @@ def time_dominant_kernel(eng, precision, reps=48):
     return us, algo_bytes, name
 
 
-def time_dominant_gemm(eng, reps=40):
+def time_dominant_gemm(eng, reps=40, tokens=222):
     """The fc1 GEMM of one block (M = 128*222 tokens, N = 3072, K = 768, bias + GELU epilogue: the largest single share of the L2P step)
     timed alone with CUDA events, rotating over enough distinct operand sets that every launch starts from cold HBM."""
     import torch
-    M, N, K = BATCH * 222, 3072, 768
+    M, N, K = BATCH * tokens, 3072, 768
     sets = 4                                       # 4 * (43.6 + 2*174.6) MB = 1.5 GB > 126 MB L2
     a = [torch.randn(M, K, device=eng.dev).bfloat16() for _ in range(sets)]
     c = [torch.empty(M, N, device=eng.dev, dtype=torch.bfloat16) for _ in range(sets)]
@@ -349,7 +403,7 @@ def time_dominant_gemm(eng, reps=40):
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
-    return us, 2.0 * M * N * K, "gemm_bf16_kernel<256> (fc1: 28416 x 3072 x 768, bias + GELU epilogue, tcgen05 kind::f16 BF16, TMA SW128, TMEM accumulators)"
+    return us, 2.0 * M * N * K, f"gemm_bf16_kernel<256> (fc1: {M} x 3072 x 768, bias + GELU epilogue, tcgen05 kind::f16 BF16, TMA SW128, TMEM accumulators)"
 
 
 def run_ours_l2p(args):
@@ -363,21 +417,35 @@ def run_ours_l2p(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     from libcontinual_b200.model.l2p import L2P, vit_pt_imnet
-    from libcontinual_b200.optim import Adam
-    from libcontinual_b200.trainer import GraphedL2PStep
+    from libcontinual_b200.optim import Adam, FlatSGD
+    from libcontinual_b200.trainer import GraphedFlatStep, GraphedL2PStep
 
-    p, prm, key, fc_w, fc_b = l2p_synth_state()
-    bb = vit_pt_imnet(pretrained=False, state=p, device=device)
-    m = L2P(bb, device, init_cls_num=10, inc_cls_num=10, num_class=100, task_num=10, feat_dim=768, prompt_length=5, pool_size=10, top_k=5,
-            pull_constraint_coeff=1.0)
-    with torch.no_grad():
-        bb.prompt.prompt.copy_(prm); bb.prompt.prompt_key.copy_(key)
-        m.network.classifier.weight.copy_(fc_w); m.network.classifier.bias.copy_(fc_b)
-    m.after_task(0, None, None, None); m.before_task(1, None, None, None)
-    opt = Adam(m.get_parameters(None), lr=0.001875, betas=(0.9, 0.999), weight_decay=0, model=m)
+    kind = args.workload
+    if kind == "l2p":
+        p, prm, key, fc_w, fc_b = l2p_synth_state()
+        bb = vit_pt_imnet(pretrained=False, state=p, device=device)
+        m = L2P(bb, device, init_cls_num=10, inc_cls_num=10, num_class=100, task_num=10, feat_dim=768, prompt_length=5, pool_size=10, top_k=5,
+                pull_constraint_coeff=1.0)
+        with torch.no_grad():
+            bb.prompt.prompt.copy_(prm); bb.prompt.prompt_key.copy_(key)
+            m.network.classifier.weight.copy_(fc_w); m.network.classifier.bias.copy_(fc_b)
+        m.after_task(0, None, None, None); m.before_task(1, None, None, None)
+        opt = Adam(m.get_parameters(None), lr=0.001875, betas=(0.9, 0.999), weight_decay=0, model=m)
+        lo, hi, tokens = 10, 20, 222
+    else:
+        from libcontinual_b200.model.inflora import InfLoRA_OPT
+        os.environ.setdefault("PYTHONHASHSEED", "42")
+        p, A, Bm, hw, hb = inflora_synth_state()
+        bb = vit_pt_imnet(pretrained=False, state=p, device=device, attn_layer="MultiHeadAttention_LoRA", lora_rank=10)
+        m = InfLoRA_OPT(bb, device, init_cls_num=20, inc_cls_num=20, task_num=10, lame=1.0, lamb=0.95, embd_dim=768, use_ca=False, dataset="imagenet-r")
+        m.start_task(0); m.start_task(1, A)                 # task 1: adapters installed (the loader passes of before_task are task-boundary work)
+        with torch.no_grad():
+            m.lora_B.copy_(Bm.to(device)); m.heads_W.copy_(hw.to(device)); m.heads_b.copy_(hb.to(device))
+        opt = FlatSGD(m.get_parameters(None), lr=8e-3, momentum=0.9, model=m)
+        lo, hi, tokens = 20, 40, 197
     eng = m.engine
     NB = 3
-    host = [(x.pin_memory(), y.pin_memory()) for x, y in l2p_batches(NB, BATCH, 10, 20, seed=7 + rank)]
+    host = [(x.pin_memory(), y.pin_memory()) for x, y in l2p_batches(NB, BATCH, lo, hi, seed=7 + rank)]
     devb = [(x.to(device), y.to(device)) for x, y in host]
     K, W = args.steps, max(3, args.warmup)
 
@@ -386,7 +454,7 @@ def run_ours_l2p(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    step = GraphedL2PStep(m, opt, BATCH)
+    step = GraphedL2PStep(m, opt, BATCH) if kind == "l2p" else GraphedFlatStep(m, opt, BATCH)
     for i in range(W):
         step.run(*devb[i % NB])
     barrier()
@@ -424,12 +492,17 @@ def run_ours_l2p(args):
     e2e_ms = float(t) / Ke
     e2e = {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * 4 + BATCH * 8 + 32,
            "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
-           "path": "libcontinual_b200.trainer.GraphedL2PStep.run(pinned host batch) + loss().item() every step"}
+           "path": f"libcontinual_b200.trainer.{type(step).__name__}.run(pinned host batch) + loss().item() every step"}
     plugin = None
     if world == 1:
         def eager(i):
-            opt.zero_grad()
-            pred, acc, loss = m.observe({"image": host[i % NB][0], "label": host[i % NB][1]})
+            if kind == "l2p":                                   # trainer.py:592-594 (backward + clip inside observe)
+                opt.zero_grad()
+                pred, acc, loss = m.observe({"image": host[i % NB][0], "label": host[i % NB][1]})
+            else:                                               # trainer.py:601-604 default branch
+                pred, acc, loss = m.observe({"image": host[i % NB][0], "label": host[i % NB][1]})
+                opt.zero_grad()
+                loss.backward()
             opt.step()
             return loss.item()
         for i in range(2):
@@ -443,7 +516,8 @@ def run_ours_l2p(args):
         torch.cuda.synchronize()
         pm = e0.elapsed_time(e1) / Kp
         plugin = {"value": BATCH / (pm * 1e-3), "unit": "images/s", "ms_per_step": pm,
-                  "path": "plugin zero_grad->observe (backward + clip inside)->optim.step->loss.item() (trainer.py:592-611), eager launches"}
+                  "path": ("plugin zero_grad->observe (backward + clip inside)->optim.step->loss.item() (trainer.py:592-611)" if kind == "l2p" else
+                           "plugin observe->zero_grad->loss.backward()->optim.step->loss.item() (trainer.py:601-611)") + ", eager launches"}
     e2e["plugin_eager"] = plugin
     if rank != 0:
         if world > 1:
@@ -454,21 +528,22 @@ def run_ours_l2p(args):
         peak, peak_src = float(json.load(open(peaks_path))["bf16_tflops"]), "MEASURED_PEAKS.json bf16 burst (kernel timed alone)"
     else:
         peak, peak_src = 1650.0, "fallback (B200_PROFILING.md)"
-    us, flops, kname = time_dominant_gemm(eng)
+    us, flops, kname = time_dominant_gemm(eng, tokens=tokens)
     achieved = flops / (us * 1e-6) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "kernel": kname,
                 "us_per_launch": us, "algorithmic_flops_per_launch": flops, "peak_source": peak_src}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        ips, ms, cores = time_oracle_l2p(2, 1, 16)
+        ips, ms, cores = (time_oracle_l2p if kind == "l2p" else time_oracle_inflora)(2, 1, 16)
         cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "ms_per_step": ms,
-               "sample": f"2 full L2P steps of 16 images after 1 warm-up (bounded sample of the bs-128 step; oracle/port.py, PyTorch CPU fp32, {cores} threads)"}
-    flop_step = 3 * 12 * 2 * (768 * 2304 + 768 * 768 + 2 * 768 * 3072) * BATCH * 215.0     # rough: 3 passes x 12 blocks x linear layers
+               "sample": f"2 full {kind} steps of 16 images after 1 warm-up (bounded sample of the bs-128 step; oracle/port.py, PyTorch CPU fp32, {cores} threads)"}
+    passes = 3 if kind == "l2p" else 2                  # L2P: query fwd + prompted fwd + dX bwd; InfLoRA: fwd + dX bwd
+    flop_step = passes * 12 * 2 * (768 * 2304 + 768 * 768 + 2 * 768 * 3072) * BATCH * (215.0 if kind == "l2p" else 197.0)     # rough: linear layers only
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name("l2p"), "global_batch": BATCH * world, "per_gpu_batch": BATCH, "parallelism": f"dp{world}",
+            "config": {"workload": workload_name(kind), "global_batch": BATCH * world, "per_gpu_batch": BATCH, "parallelism": f"dp{world}",
                        "l2": f"per-step working set ~9 GB of saved activations + {NB} rotating 77 MB input batches > 126 MB L2 (no explicit flush)",
-                       "precision": "BF16 GEMM operands (tcgen05 kind::f16), fp32 accumulate in TMEM, fp32 residual stream / LayerNorm / softmax / loss / Adam",
+                       "precision": "BF16 GEMM operands (tcgen05 kind::f16), fp32 accumulate in TMEM, fp32 residual stream / LayerNorm / softmax / loss / optimizer",
                        "final_loss": final_loss, "tensor_core_error": eng.tensor_core_error(),
                        "approx_model_tflops": flop_step / (ms_step * 1e-3) / 1e12},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
@@ -478,7 +553,7 @@ def run_ours_l2p(args):
 
 
 def run_ours(args):
-    if args.workload == "l2p":
+    if args.workload in ("l2p", "inflora"):
         return run_ours_l2p(args)
     import torch
     import torch.distributed as dist

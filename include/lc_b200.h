@@ -178,9 +178,16 @@ int lc_gemm_bf16_ex(const lc_gemm_desc* desc, int* error_flag, lc_stream_t strea
  * the backward.  The T x T score / probability matrices live in TMEM / shared memory only. */
 int lc_attn_forward(const void* qkv_bf16, void* out_bf16, float* lse2, int batch, int T, int heads, int* error_flag, lc_stream_t stream);
 /* Its backward: dQ, dK, dV (written into dqkv with the QKV layout) from dO, with the probabilities recomputed on chip from lse2;
- * rowdot [B][H][T] is scratch (sum_d dO*O per row). */
+ * out_bf16 / rowdot are not read any more (the softmax row term sum_j P_j dP_j is formed on chip from the same probabilities the products use). */
 int lc_attn_backward(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2, float* rowdot, void* dqkv_bf16, int batch, int T,
                      int heads, int* error_flag, lc_stream_t stream);
+/* The same two kernels with P prefix keys / values per image placed in front of the token keys — `MultiHeadAttention.forward(prompt=(pk, pv))`
+ * (transformer.py:175-180; DualPrompt prompt.py:299-316, CodaPrompt prompt.py:199-201): pk / pv BF16 [B][P][H*64], T + P <= 256.  The backward
+ * returns the prefix-row gradients dpk / dpv as fp32 [B][P][H*64] (they are prompt-pool parameters) next to dqkv. */
+int lc_attn_forward_prefix(const void* qkv_bf16, void* out_bf16, float* lse2, int batch, int T, int heads, const void* pk_bf16, const void* pv_bf16, int P,
+                            int* error_flag, lc_stream_t stream);
+int lc_attn_backward_prefix(const void* qkv_bf16, const void* dout_bf16, const float* lse2, void* dqkv_bf16, int batch, int T, int heads, const void* pk_bf16,
+                             const void* pv_bf16, float* dpk, float* dpv, int P, int* error_flag, lc_stream_t stream);
 int lc_vit_patchify(const float* img_nchw, void* out_bf16, int batch, lc_stream_t stream);
 int lc_vit_set_rows(float* x, long long batch_stride, int batch, int row0, int nrows, const float* src, const float* add, int dim, lc_stream_t stream);
 int lc_layernorm_forward(const float* x, const float* gamma, const float* beta, float eps, long long rows, int dim, void* out_bf16, float* out_f32,

@@ -64,6 +64,8 @@ SIGNATURES = {
     "lc_gemm_bf16_ex": (c_int, [P, P, P]),
     "lc_attn_forward": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
     "lc_attn_backward": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P]),
+    "lc_attn_forward_prefix": (c_int, [P, P, P, c_int, c_int, c_int, P, P, c_int, P, P]),
+    "lc_attn_backward_prefix": (c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, c_int, P, P]),
     "lc_vit_patchify": (c_int, [P, P, c_int, P]),
     "lc_vit_set_rows": (c_int, [P, c_longlong, c_int, c_int, c_int, P, P, c_int, P]),
     "lc_layernorm_forward": (c_int, [P, P, P, c_float, c_longlong, c_int, P, P, P, P]),

@@ -218,6 +218,15 @@ __global__ void __launch_bounds__(GemmCfg<BN>::NT, 1) gemm_bf16_kernel(const __g
                         res[j] = (vec && m < a.M) ? *reinterpret_cast<const float4*>(a.residual + rz + (size_t)m * a.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
+                uint2 gaux[8];
+                if constexpr ((EPI & EPI_DGELU) != 0) {                              // likewise the pre-activations GELU' is evaluated at: issued here, consumed
+#pragma unroll                                                                        // after the TMEM read (inside the store loop they would serialise behind the
+                    for (int j = 0; j < 8; ++j) {                                    // stores: `out` and `gelu_aux` may alias as far as the compiler knows)
+                        const int m = mrow0 + j * 4 + rr;
+                        gaux[j] = (vec && m < a.M) ? __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(a.gelu_aux) + cz + (size_t)m * a.ldc + n))
+                                                   : make_uint2(0u, 0u);
+                    }
+                }
                 float v[32];
                 tmem_ld16(trow + (uint32_t)c0, v);
                 tmem_ld16(trow + (uint32_t)(c0 + 16), v + 16);
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(GemmCfg<BN>::NT, 1) gemm_bf16_kernel(const __g
                     if (vec) {
                         if constexpr ((EPI & EPI_RES) != 0) { x0 += res[j].x; x1 += res[j].y; x2 += res[j].z; x3 += res[j].w; }
                         if constexpr ((EPI & EPI_DGELU) != 0) {
-                            const uint2 g = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(a.gelu_aux) + ci);
+                            const uint2 g = gaux[j];
                             x0 *= dgelu_erf(__uint_as_float(g.x << 16)); x1 *= dgelu_erf(__uint_as_float(g.x & 0xffff0000u));
                             x2 *= dgelu_erf(__uint_as_float(g.y << 16)); x3 *= dgelu_erf(__uint_as_float(g.y & 0xffff0000u));
                         }

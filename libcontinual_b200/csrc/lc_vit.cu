@@ -126,33 +126,45 @@ int lc_gemm_bf16(const void* A, int lda, long long strideA, const void* B, int l
     return lc_gemm_bf16_ex(&d, error_flag, stream);
 }
 
-int lc_attn_forward(const void* qkv_bf16, void* out_bf16, float* lse2, int batch, int T, int heads, int* error_flag, lc_stream_t stream) {
-    LC_CHECK_ARG(qkv_bf16 && out_bf16 && lse2 && batch >= 1 && T >= 1 && T <= 256 && heads >= 1);
-    const size_t smem = tc::attn_fwd_smem(T);
+int lc_attn_forward_prefix(const void* qkv_bf16, void* out_bf16, float* lse2, int batch, int T, int heads, const void* pk_bf16, const void* pv_bf16, int P,
+                            int* error_flag, lc_stream_t stream) {
+    LC_CHECK_ARG(qkv_bf16 && out_bf16 && lse2 && batch >= 1 && T >= 1 && heads >= 1 && batch <= 65535 && heads <= 65535);
+    LC_CHECK_ARG(P >= 0 && (P == 0 || (pk_bf16 && pv_bf16)) && T + P <= 256);
+    const size_t smem = tc::attn_fwd_smem(T + P);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         if (cudaFuncSetAttribute(tc::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return LC_ERR_CUDA;
         attr_smem = smem;
     }
-    tc::AttnFwdArgs a{reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), lse2, T, heads, error_flag};
-    tc::attn_fwd_kernel<<<dim3((T + 127) / 128, heads, batch), 128, smem, (cudaStream_t)stream>>>(a);
+    tc::AttnFwdArgs a{reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), lse2, T, heads, error_flag,
+                      P ? reinterpret_cast<const __nv_bfloat16*>(pk_bf16) : nullptr, P ? reinterpret_cast<const __nv_bfloat16*>(pv_bf16) : nullptr, P};
+    tc::attn_fwd_kernel<<<dim3((T + 127) / 128, heads, batch), 256, smem, (cudaStream_t)stream>>>(a);
     return lc_launch_status();
 }
+int lc_attn_forward(const void* qkv_bf16, void* out_bf16, float* lse2, int batch, int T, int heads, int* error_flag, lc_stream_t stream) {
+    return lc_attn_forward_prefix(qkv_bf16, out_bf16, lse2, batch, T, heads, nullptr, nullptr, 0, error_flag, stream);
+}
 
-int lc_attn_backward(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2, float* rowdot, void* dqkv_bf16, int batch, int T,
-                     int heads, int* error_flag, lc_stream_t stream) {
-    LC_CHECK_ARG(qkv_bf16 && out_bf16 && dout_bf16 && lse2 && rowdot && dqkv_bf16 && batch >= 1 && T >= 1 && T <= 256 && heads >= 1 && batch <= 65535);
-    const size_t smem = tc::attn_bwd_smem(T);
+int lc_attn_backward_prefix(const void* qkv_bf16, const void* dout_bf16, const float* lse2, void* dqkv_bf16, int batch, int T, int heads, const void* pk_bf16,
+                             const void* pv_bf16, float* dpk, float* dpv, int P, int* error_flag, lc_stream_t stream) {
+    LC_CHECK_ARG(qkv_bf16 && dout_bf16 && lse2 && dqkv_bf16 && batch >= 1 && T >= 1 && heads >= 1 && batch <= 65535);
+    LC_CHECK_ARG(P >= 0 && (P == 0 || (pk_bf16 && pv_bf16 && dpk && dpv)) && T + P <= 256);
+    const size_t smem = tc::attn_bwd_smem(T + P);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         if (cudaFuncSetAttribute(tc::attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return LC_ERR_CUDA;
         attr_smem = smem;
     }
-    (void)out_bf16;      // the softmax row term is formed on chip from P and dP (attn_tc.cuh); O is not read
-    tc::AttnBwdArgs a{reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse2, rowdot,
-                      reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), T, heads, error_flag};
+    tc::AttnBwdArgs a{reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse2,
+                      reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), T, heads, error_flag, P ? reinterpret_cast<const __nv_bfloat16*>(pk_bf16) : nullptr,
+                      P ? reinterpret_cast<const __nv_bfloat16*>(pv_bf16) : nullptr, dpk, dpv, P};
     tc::attn_bwd_kernel<<<dim3(heads, batch), 256, smem, (cudaStream_t)stream>>>(a);
     return lc_launch_status();
+}
+int lc_attn_backward(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2, float* rowdot, void* dqkv_bf16, int batch, int T,
+                     int heads, int* error_flag, lc_stream_t stream) {
+    (void)out_bf16; (void)rowdot;       // the softmax row term sum_j P_j dP_j is formed on chip (attn_tc.cuh); O and the scratch are not read
+    return lc_attn_backward_prefix(qkv_bf16, dout_bf16, lse2, dqkv_bf16, batch, T, heads, nullptr, nullptr, nullptr, nullptr, 0, error_flag, stream);
 }
 
 int lc_vit_patchify(const float* img, void* out_bf16, int batch, lc_stream_t stream) {
