@@ -216,6 +216,13 @@ int lc_l2p_backward(const float* dprompts, const int64_t* ids, int pool, int top
  * lc_lora_bgrad_rows : out[s][c][j] = sum_n X[n][x0 + s*x_slab_stride + c] * Z[n][s*rank + j]  — the adapter gradient in rank form, e.g.
  *                      d lora_B_k.weight = dK^T (h A_k^T) with X = d(qkv) (BF16) and Z = the saved down-projection (fp32); deterministic
  *                      two-stage sum over `nchunk` row chunks (partial >= lc_lora_bgrad_partial_floats floats).  rank <= 16, dim % 768 == 0. */
+/* DualPrompt's key-query match over the e-prompt layers (prompt.py:270-292): keys[l] / dkeys[l] are HOST arrays of nlayers DEVICE pointers to the
+ * [pool][768] key matrices and their gradients.  task_id >= 0 (training, task-id bootstrap): idx[l][b] = task_id, *loss = sum_l sum_b (1 - cos(q_b,
+ * K_l[task_id])), dkeys[l][task_id] = its gradient (the query is detached).  task_id < 0 (inference): idx[l][b] = argmax_k cos(q_b, K_l[k]).
+ * lc_gather_rows_bf16: out[b][r][:] = bf16(src[idx[b] * idx_stride + r * dim + :]) (idx nullable = 0): the selected prompt halves as per-image prefix rows. */
+int lc_prompt_key_match(const float* query, const float* const* keys, float* const* dkeys, int nlayers, int batch, int pool, int dim, int task_id,
+                        int64_t* idx, float* loss, lc_stream_t stream);
+int lc_gather_rows_bf16(const float* src, const int64_t* idx, long long idx_stride, int rows, int dim, int batch, void* out_bf16, lc_stream_t stream);
 /* out[c][r] = in[r][c] (BF16; columns [rows, ld_out) of out zero-filled): the transposed copy that turns a contraction over token rows
  * (InfLoRA's input matrix sum_n h_n h_n^T, transformer.py:242-244) into the K-major operands of lc_gemm_bf16. */
 int lc_transpose_bf16(const void* in_bf16, long long ld_in, long long rows, int cols, void* out_bf16, long long ld_out, lc_stream_t stream);

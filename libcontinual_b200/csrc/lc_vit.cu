@@ -4,6 +4,7 @@
 #include "attn_tc.cuh"
 #include "vit_ops.cuh"
 #include "lora_ops.cuh"
+#include "prompt_ops.cuh"
 
 using namespace lc;
 
@@ -226,6 +227,22 @@ int lc_cast_bf16(const float* in, void* out_bf16, long long n, lc_stream_t strea
     return lc_launch_status();
 }
 
+int lc_prompt_key_match(const float* query, const float* const* keys, float* const* dkeys, int nlayers, int batch, int pool, int dim, int task_id,
+                        int64_t* idx, float* loss, lc_stream_t stream) {
+    LC_CHECK_ARG(query && keys && idx && nlayers >= 1 && nlayers <= kPromptMaxLayers && batch >= 1 && pool >= 1 && dim == 768 && task_id < pool);
+    LC_CHECK_ARG(task_id < 0 || (dkeys && loss));
+    KeyMatchArgs a{};
+    a.q = query; a.idx = reinterpret_cast<long long*>(idx); a.loss = loss; a.nl = nlayers; a.B = batch; a.pool = pool; a.D = dim; a.task_id = task_id;
+    for (int l = 0; l < nlayers; ++l) { a.K[l] = keys[l]; a.dK[l] = dkeys ? dkeys[l] : nullptr; LC_CHECK_ARG(a.K[l] && (task_id < 0 || a.dK[l])); }
+    prompt_key_match_kernel<768><<<1, 256, 0, (cudaStream_t)stream>>>(a);
+    return lc_launch_status();
+}
+int lc_gather_rows_bf16(const float* src, const int64_t* idx, long long idx_stride, int rows, int dim, int batch, void* out_bf16, lc_stream_t stream) {
+    LC_CHECK_ARG(src && out_bf16 && rows >= 1 && rows <= 65535 && dim % 4 == 0 && batch >= 1);
+    gather_rows_bf16_kernel<<<dim3(batch, rows), 192, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<const long long*>(idx), idx_stride, rows, dim,
+                                                                                  reinterpret_cast<__nv_bfloat16*>(out_bf16));
+    return lc_launch_status();
+}
 int lc_transpose_bf16(const void* in_bf16, long long ld_in, long long rows, int cols, void* out_bf16, long long ld_out, lc_stream_t stream) {
     LC_CHECK_ARG(in_bf16 && out_bf16 && rows >= 1 && cols >= 1 && ld_in >= cols && ld_out >= rows);
     transpose_bf16_kernel<<<dim3((unsigned)((ld_out + 63) / 64), (cols + 63) / 64), 256, 0, (cudaStream_t)stream>>>(

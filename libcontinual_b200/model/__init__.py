@@ -3,3 +3,4 @@ from .backbone import CifarResNet, cifar_resnet20, cifar_resnet32, resnet32_V2  
 from .resnet_methods import EWC, LUCIR, LWF, Finetune, ICarl  # noqa: F401
 from .l2p import L2P, ViTZoo, vit_pt_imnet  # noqa: F401
 from .inflora import InfLoRA_OPT, SiNet  # noqa: F401
+from .dualprompt import DualPrompt, DualPromptPool  # noqa: F401

@@ -72,6 +72,13 @@ class _Workspace:
     def idx(self, layer: int) -> int:
         return layer if self.save else 0
 
+    def prefix_grads(self, layer: int, P: int):
+        """fp32 [B, P, 768] gradients of the prefix keys / values of `layer` (written by the attention backward)."""
+        d = self.__dict__.setdefault("_dprefix", {})
+        if (layer, P) not in d:
+            d[(layer, P)] = (torch.empty(self.B, P, DIM, device=self.y.device), torch.empty(self.B, P, DIM, device=self.y.device))
+        return d[(layer, P)]
+
     def backward_buffers(self):
         """Transient buffers of the input-gradient pass (allocated on first use)."""
         if self.bwd is None:
@@ -227,7 +234,8 @@ class ViTEngine:
             check(self.lib.lc_vit_set_rows(x0.data_ptr(), T * DIM, B, 0, Pn, prompts.data_ptr(), None, DIM, st), "prompt rows")
         self.launches += 3 + (1 if Pn else 0)
 
-    def block_forward(self, i: int, ws: _Workspace):
+    def block_forward(self, i: int, ws: _Workspace, prefix=None):
+        """`prefix` = (pk, pv) BF16 [B, P, 768]: prefix keys / values of this block (transformer.py:175-180), or None."""
         B, T, Tp = ws.B, ws.T, ws.Tp
         st = stream_ptr()
         pre = f"transformer.blocks.{i}."
@@ -242,21 +250,28 @@ class ViTEngine:
             lo = self.lora
             self.gemm(ws.h.data_ptr(), DIM, lo.A_bf[i].data_ptr(), DIM, ws.hA[k].data_ptr(), lo.cols, B * T, lo.cols, DIM, out_f32=True)
         self._linear(ws.h, pre + "attn.qkv.weight", qkv, bias=pre + "attn.qkv.bias")
-        check(self.lib.lc_attn_forward(qkv.data_ptr(), o.data_ptr(), ws.lse[k].data_ptr(), B, T, HEADS, self.err.data_ptr(), st), "attn_forward")
+        if prefix is None:
+            check(self.lib.lc_attn_forward(qkv.data_ptr(), o.data_ptr(), ws.lse[k].data_ptr(), B, T, HEADS, self.err.data_ptr(), st), "attn_forward")
+        else:
+            pk, pv = prefix
+            assert pk.dtype == torch.bfloat16 and pk.shape == pv.shape and pk.shape[0] == B and pk.shape[2] == DIM and pk.is_contiguous() and pv.is_contiguous()
+            check(self.lib.lc_attn_forward_prefix(qkv.data_ptr(), o.data_ptr(), ws.lse[k].data_ptr(), B, T, HEADS, pk.data_ptr(), pv.data_ptr(), pk.shape[1],
+                                                  self.err.data_ptr(), st), "attn_forward_prefix")
         self._linear(o, pre + "attn.proj.weight", xmid, bias=pre + "attn.proj.bias", residual=xin)
         self._ln(xmid, pre + "ln_2", 1e-5, out_bf16=ws.h)
         self._linear(ws.h, pre + "mlp.fc1.weight", upre, bias=pre + "mlp.fc1.bias", out2=ws.u)
         self._linear(ws.u, pre + "mlp.fc2.weight", xout, bias=pre + "mlp.fc2.bias", residual=xmid)
         self.launches += 1
 
-    def forward(self, img: torch.Tensor, prompts: Optional[torch.Tensor] = None, save: bool = False) -> _Workspace:
-        """Runs the backbone; returns the workspace (ws.y = final-LayerNorm tokens fp32 [B, T, 768])."""
+    def forward(self, img: torch.Tensor, prompts: Optional[torch.Tensor] = None, save: bool = False, prefix: Optional[Dict[int, tuple]] = None) -> _Workspace:
+        """Runs the backbone; returns the workspace (ws.y = final-LayerNorm tokens fp32 [B, T, 768]).  `prefix[i]` = (pk, pv) of block i."""
         B = img.shape[0]
         T = PATCHES + 1 + (0 if prompts is None else prompts.shape[0])
         ws = self.workspace(B, T, save)
         self.embed(img, prompts, ws)
+        ws.prefix = prefix if save else None
         for i in range(self.depth):
-            self.block_forward(i, ws)
+            self.block_forward(i, ws, None if prefix is None else prefix.get(i))
         last = ws.x[self.depth] if save else ws.x[self.depth % 2]
         self._ln(last, "norm", 1e-6, out_f32=ws.y, stat=ws.ystat if save else None)
         return ws
@@ -308,8 +323,15 @@ class ViTEngine:
             self._ln_bwd(dh, ws.xmid[i], pre + "ln_2", 1e-5, g, g2, gbf)
             # attention branch: x_mid = x_in + proj(softmax(QK^T/8) V)
             self._linear_t(gbf, pre + "attn.proj.weight", dO)
-            check(self.lib.lc_attn_backward(ws.qkv[i].data_ptr(), ws.o[i].data_ptr(), dO.data_ptr(), ws.lse[i].data_ptr(), rowdot.data_ptr(), dqkv.data_ptr(),
-                                            B, T, HEADS, self.err.data_ptr(), st), "attn_backward")
+            pfx = None if getattr(ws, "prefix", None) is None else ws.prefix.get(i)
+            if pfx is None:
+                check(self.lib.lc_attn_backward(ws.qkv[i].data_ptr(), ws.o[i].data_ptr(), dO.data_ptr(), ws.lse[i].data_ptr(), rowdot.data_ptr(), dqkv.data_ptr(),
+                                                B, T, HEADS, self.err.data_ptr(), st), "attn_backward")
+            else:
+                pk, pv = pfx
+                dpk, dpv = ws.prefix_grads(i, pk.shape[1])
+                check(self.lib.lc_attn_backward_prefix(ws.qkv[i].data_ptr(), dO.data_ptr(), ws.lse[i].data_ptr(), dqkv.data_ptr(), B, T, HEADS, pk.data_ptr(),
+                                                       pv.data_ptr(), dpk.data_ptr(), dpv.data_ptr(), pk.shape[1], self.err.data_ptr(), st), "attn_backward_prefix")
             self.launches += 2
             if self.lora is not None and self.lora.active:
                 self.lora_grads(i, ws, dqkv)

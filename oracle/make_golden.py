@@ -602,6 +602,104 @@ def golden_inflora(core):
     np.savez_compressed(os.path.join(OUT, "inflora_vit.npz"), **out)
 
 
+def synth_dual_pool(seed: int, num_class: int = 100):
+    """DualPrompt pool (uniform(0,1) like `tensor_prompt`, prompt.py:409-418) + classifier from one numpy Generator."""
+    rng = np.random.default_rng(seed)
+    pool = {}
+    for l in (0, 1):
+        pool[f"g_p_{l}"] = torch.from_numpy(rng.uniform(0, 1, (6, 768)).astype(np.float32))
+    for l in (2, 3, 4):
+        pool[f"e_p_{l}"] = torch.from_numpy(rng.uniform(0, 1, (10, 20, 768)).astype(np.float32))
+        pool[f"e_k_{l}"] = torch.from_numpy(rng.uniform(0, 1, (10, 768)).astype(np.float32))
+    bound = 1.0 / np.sqrt(768)
+    fc_w = torch.from_numpy(rng.uniform(-bound, bound, (num_class, 768)).astype(np.float32))
+    fc_b = torch.from_numpy(rng.uniform(-bound, bound, (num_class,)).astype(np.float32))
+    return pool, fc_w, fc_b
+
+
+def ref_prompt_forward(ref_zoo, x, train, task_id):
+    """`ViTZoo.forward` prompt branch (vit.py:121-131) + `VisionTransformer.forward` non-l2p branch (transformer.py:2263-2296) driven through the REAL
+    reference modules (patch_embed, blocks with prompt=(pk, pv), the prompt pool's forward, norm).  The only change: the pool losses are summed
+    out of place — the reference's in-place `prompt_loss += loss` on a leaf tensor raises on CPU under torch >= 2.1."""
+    vt = ref_zoo.feat
+    with torch.no_grad():
+        q, _ = vt(x)
+        q = q[:, 0, :]
+    B = x.shape[0]
+    t = vt.patch_embed(x)
+    t = torch.cat((vt.cls_token.expand(B, -1, -1), t), dim=1)
+    t = vt.pos_drop(t + vt.pos_embed[:, :t.size(1), :])
+    ploss = torch.zeros(())
+    for i, blk in enumerate(vt.transformer.blocks):
+        p_list, loss, t = ref_zoo.prompt.forward(q, i, t, train=train, task_id=task_id)
+        if train:
+            ploss = ploss + loss
+        t = blk(t.permute(1, 0, 2), register_hook=False, prompt=p_list).permute(1, 0, 2)
+    out = vt.norm(t)[:, 0, :]
+    return out, ploss, q
+
+
+def golden_dualprompt(core):
+    """The real `core.model.dualprompt.DualPrompt` (pool + ViT blocks + classifier) on task 0 and task 1, and the per-sample selection at inference."""
+    from core.model.backbone.vit import vit_pt_imnet
+    from core.model.dualprompt import DualPrompt as RefDual
+    print("DualPrompt / ViT-B/16: reference modules vs oracle")
+    out = {}
+    p = synth_vit_state(5150)[0]
+    pool, fc_w, fc_b = synth_dual_pool(930)
+    bb = vit_pt_imnet(pretrained=False)
+    ref = RefDual(bb, 768, 100, device=torch.device("cpu"), task_num=10, init_cls_num=10, inc_cls_num=10, g_prompt_length=6, e_prompt_length=20)
+    bb.feat.load_state_dict(p, strict=True)
+    rp = bb.prompt
+    with torch.no_grad():
+        for k, v in pool.items():
+            getattr(rp, k).copy_(v)
+    for task in (0, 1):
+        ref.before_task(task, None, None, None)
+        n = ref.network.classifier.out_features
+        with torch.no_grad():
+            ref.network.classifier.weight.copy_(fc_w[:n]); ref.network.classifier.bias.copy_(fc_b[:n])
+        for q_ in ref.get_parameters(None):
+            q_.grad = None
+        lo = 10 * task
+        x, y = synth_images(750 + task, 4, lo, lo + 10)
+        # observe() (dualprompt.py:89-104) on the out-of-place forward
+        feat, ploss, q = ref_prompt_forward(bb, x, True, task)
+        logit = ref.network.classifier(feat)
+        logit[:, :ref.last_out_dim] = -float("inf")
+        loss = ploss + (ref.loss_fn(logit, y) * ref.dw_k[-1 * torch.ones(y.size()).long()]).mean()
+        loss.backward()
+        pred = torch.argmax(logit, dim=1)
+        # oracle
+        op = {k: v.clone().requires_grad_(True) for k, v in pool.items()}
+        ow = fc_w[:n].clone().requires_grad_(True); ob = fc_b[:n].clone().requires_grad_(True)
+        ofeat, oploss, oq, _ = port.dualprompt_forward(p, op, x, task, True)
+        ologits = port.linear_head(ofeat, ow, ob)
+        oloss = port.dualprompt_loss(ologits, y, ref.last_out_dim, oploss)
+        oloss.backward()
+        close(oloss, loss, 1e-5, 1e-6, f"dual task{task} loss")
+        close(oq, q, 1e-4, 1e-5, f"dual task{task} query")
+        close(ofeat, feat, 1e-4, 1e-5, f"dual task{task} feat")
+        for k in pool:
+            g_ref = getattr(rp, k).grad
+            close(op[k].grad, g_ref, 1e-4, 2e-6, f"dual task{task} d{k}")
+            out[f"t{task}/d{k}"] = g_ref.numpy().copy()
+        close(ow.grad, ref.network.classifier.weight.grad, 1e-4, 2e-6, f"dual task{task} dW")
+        out[f"t{task}/loss"] = np.float64(loss.item()); out[f"t{task}/ploss"] = np.float64(ploss.item()); out[f"t{task}/pred"] = pred.numpy().copy()
+        out[f"t{task}/feat"] = feat.detach().numpy().copy(); out[f"t{task}/query"] = q.numpy().copy()
+        out[f"t{task}/dW"] = ref.network.classifier.weight.grad.numpy().copy(); out[f"t{task}/db"] = ref.network.classifier.bias.grad.numpy().copy()
+        # inference: per-sample top-1 key (prompt.py:290-292) through the real pool + blocks
+        with torch.no_grad():
+            ifeat, _, _ = ref_prompt_forward(bb, x, False, task)
+            ilogits = ref.network.classifier(ifeat)
+            ofeat_i, _, _, ids = port.dualprompt_forward(p, pool, x, task, False)
+        close(ofeat_i, ifeat, 1e-4, 1e-5, f"dual task{task} inference feat")
+        out[f"t{task}/inf_logits"] = ilogits.numpy().copy()
+        out[f"t{task}/inf_ids"] = torch.stack([ids[l] for l in (2, 3, 4)]).numpy().copy()
+        ref.after_task(task, None, None, None)
+    np.savez_compressed(os.path.join(OUT, "dualprompt_vit.npz"), **out)
+
+
 def main():
     torch.set_num_threads(8)
     os.makedirs(OUT, exist_ok=True)
@@ -619,6 +717,7 @@ def main():
     golden_ops(core)
     golden_l2p(core)
     golden_inflora(core)
+    golden_dualprompt(core)
     print("golden vectors written to", OUT)
 
 

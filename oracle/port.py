@@ -434,6 +434,57 @@ def inflora_init_A(cur_matrix: Tensor, rank: int) -> Tensor:
 
 
 # ----------------------------------------------------------------------------------------------
+# DualPrompt on ViT-B/16  (core/model/backbone/prompt.py:231-337 pool, transformer.py:2263-2296 non-l2p branch, vit.py:121-131,
+# core/model/dualprompt.py:89-104 observe)
+# ----------------------------------------------------------------------------------------------
+DUAL_G_LAYERS, DUAL_E_LAYERS = (0, 1), (2, 3, 4)
+
+
+def dualprompt_prefixes(pool: Dict[str, Tensor], q: Tensor, task_id: int, train: bool):
+    """Per-layer prefix (keys, values) and the key-match loss.  pool: 'g_p_{l}' [Lg, D], 'e_p_{l}' [pool, Le, D], 'e_k_{l}' [pool, D].
+    Training uses the task id (`task_id_bootstrap`, prompt.py:281-284): loss = sum_l sum_b (1 - cos(q_b, K_l[task])), the query detached;
+    inference takes the per-sample top-1 key (prompt.py:290-292).  Returns (prefix dict, loss, selected ids per e-layer)."""
+    B = q.shape[0]
+    prefix: Dict[int, Tuple[Tensor, Tensor]] = {}
+    loss = torch.zeros(())
+    ids = {}
+    for l in DUAL_E_LAYERS:
+        K, pp = pool[f"e_k_{l}"], pool[f"e_p_{l}"]
+        cos = F.normalize(q, dim=1).detach() @ F.normalize(K, dim=1).T
+        if train:
+            loss = loss + (1.0 - cos[:, task_id]).sum()
+            P_ = pp[task_id].expand(B, -1, -1)
+            ids[l] = torch.full((B,), task_id, dtype=torch.int64)
+        else:
+            ids[l] = cos.argmax(dim=1)
+            P_ = pp[ids[l]]
+        i = pp.shape[1] // 2
+        prefix[l] = (P_[:, :i], P_[:, i:])
+    for l in DUAL_G_LAYERS:
+        g = pool[f"g_p_{l}"].expand(B, -1, -1)
+        j = g.shape[1] // 2
+        prefix[l] = (g[:, :j], g[:, j:])
+    return prefix, loss, ids
+
+
+def dualprompt_forward(p: Dict[str, Tensor], pool: Dict[str, Tensor], x: Tensor, task_id: int, train: bool, depth: int = 12, heads: int = 12,
+                       gemm_mode: str = "fp32"):
+    """`ViTZoo.forward` prompt branch (vit.py:121-131): no-grad query pass -> cls feature, prefix-tuned pass -> cls feature."""
+    with torch.no_grad():
+        q = vit_tokens(p, x, None, depth, heads, gemm_mode)[:, 0]
+    prefix, loss, ids = dualprompt_prefixes(pool, q, task_id, train)
+    feat = vit_tokens(p, x, None, depth, heads, gemm_mode, prefix=prefix)[:, 0]
+    return feat, loss, q, ids
+
+
+def dualprompt_loss(logits: Tensor, y: Tensor, last_out_dim: int, prompt_loss: Tensor) -> Tensor:
+    """dualprompt.py:96-100: logits of the previous tasks' classes set to -inf, per-sample CE (weight 1) averaged, plus the pool loss."""
+    masked = logits.clone()
+    masked[:, :last_out_dim] = float("-inf")
+    return prompt_loss + F.cross_entropy(masked, y, reduction="none").mean()
+
+
+# ----------------------------------------------------------------------------------------------
 # iCaRL exemplar management
 # ----------------------------------------------------------------------------------------------
 def herding_select(features: Tensor, targets: Tensor, per_class: int) -> List[int]:

@@ -92,3 +92,18 @@ def synth_lora_state(seed, depth=12, rank=10, n_head=20, slabs="kv"):
     hw = torch.from_numpy(rng.uniform(-bound, bound, (n_head, 768)).astype(np.float32))
     hb = torch.from_numpy(rng.uniform(-bound, bound, (n_head,)).astype(np.float32))
     return lora, hw, hb
+
+
+def synth_dual_pool(seed, num_class=100):
+    """Same draws as oracle/make_golden.py::synth_dual_pool."""
+    rng = np.random.default_rng(seed)
+    pool = {}
+    for l in (0, 1):
+        pool[f"g_p_{l}"] = torch.from_numpy(rng.uniform(0, 1, (6, 768)).astype(np.float32))
+    for l in (2, 3, 4):
+        pool[f"e_p_{l}"] = torch.from_numpy(rng.uniform(0, 1, (10, 20, 768)).astype(np.float32))
+        pool[f"e_k_{l}"] = torch.from_numpy(rng.uniform(0, 1, (10, 768)).astype(np.float32))
+    bound = 1.0 / np.sqrt(768)
+    fc_w = torch.from_numpy(rng.uniform(-bound, bound, (num_class, 768)).astype(np.float32))
+    fc_b = torch.from_numpy(rng.uniform(-bound, bound, (num_class,)).astype(np.float32))
+    return pool, fc_w, fc_b

@@ -196,3 +196,26 @@ def test_inflora_vit_observe_matches_reference():
         ref = torch.from_numpy(g["t0/" + k])
         err = float((v - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
         assert err < 1e-4, (k, err)
+
+
+def test_dualprompt_vit_observe_matches_reference():
+    """Oracle DualPrompt step (prefix keys / values on blocks 0-4, task-id bootstrap key loss, masked CE) vs the real reference pool + ViT blocks +
+    classifier (fixture: tests/golden/dualprompt_vit.npz), task 1 only here (the generator checked task 0 and the inference selection as well)."""
+    from tests.golden_util import synth_dual_pool, synth_images, synth_vit_state
+    g = load("dualprompt_vit.npz")
+    torch.set_num_threads(8)
+    p = synth_vit_state(5150)[0]
+    pool, fc_w, fc_b = synth_dual_pool(930)
+    x, y = synth_images(751, 4, 10, 20)
+    op = {k: v.clone().requires_grad_(True) for k, v in pool.items()}
+    ow = fc_w[:20].clone().requires_grad_(True); ob = fc_b[:20].clone().requires_grad_(True)
+    feat, ploss, q, _ = port.dualprompt_forward(p, op, x, 1, True)
+    loss = port.dualprompt_loss(port.linear_head(feat, ow, ob), y, 10, ploss)
+    loss.backward()
+    assert abs(float(loss) - float(g["t1/loss"])) < 1e-4 and abs(float(ploss) - float(g["t1/ploss"])) < 1e-4
+    got = {"dW": ow.grad, "db": ob.grad, "feat": feat.detach(), "query": q}
+    got.update({"d" + k: v.grad for k, v in op.items()})
+    for k, v in got.items():
+        ref = torch.from_numpy(g["t1/" + k])
+        err = float((v - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
+        assert err < 2e-4, (k, err)
