@@ -222,6 +222,16 @@ int lc_l2p_backward(const float* dprompts, const int64_t* ids, int pool, int top
  * lc_gather_rows_bf16: out[b][r][:] = bf16(src[idx[b] * idx_stride + r * dim + :]) (idx nullable = 0): the selected prompt halves as per-image prefix rows. */
 int lc_prompt_key_match(const float* query, const float* const* keys, float* const* dkeys, int nlayers, int batch, int pool, int dim, int task_id,
                         int64_t* idx, float* loss, lc_stream_t stream);
+/* CodaPrompt's attention-weighted prompt (prompt.py:146-201) for `nlayers` blocks at once; K / A / p / pk / pv (and the gradient arrays) are HOST arrays of
+ * DEVICE pointers, one per block: K, A [pool][768], p [pool][length][768] (the first nk components are used), outputs pk / pv BF16 [batch][length/2][768]:
+ *   alpha[l][b][k] = cos(q_b * A_k, K_k),  P_[b] = sum_k alpha[l][b][k] p[k],  pk = P_[:, :length/2], pv = P_[:, length/2:]
+ * alpha / vnorm ([nlayers][batch][nk], vnorm = |q_b * A_k|) are kept for the backward, which maps the prefix-row gradients dpk / dpv (fp32, from
+ * lc_attn_backward_prefix) to dK, dA ([pool][768], rows < nk) and dp ([pool][length][768], components < nk); dalpha is scratch of the same size. */
+int lc_coda_prompt_forward(const float* query, const float* const* K, const float* const* A, const float* const* p, void* const* pk_bf16, void* const* pv_bf16,
+                           int nlayers, int batch, int nk, int length, int dim, float* alpha, float* vnorm, lc_stream_t stream);
+int lc_coda_prompt_backward(const float* query, const float* const* K, const float* const* A, const float* const* p, const float* const* dpk, const float* const* dpv,
+                            float* const* dK, float* const* dA, float* const* dp, int nlayers, int batch, int nk, int length, int dim, const float* alpha,
+                            const float* vnorm, float* dalpha, lc_stream_t stream);
 int lc_gather_rows_bf16(const float* src, const int64_t* idx, long long idx_stride, int rows, int dim, int batch, void* out_bf16, lc_stream_t stream);
 /* out[c][r] = in[r][c] (BF16; columns [rows, ld_out) of out zero-filled): the transposed copy that turns a contraction over token rows
  * (InfLoRA's input matrix sum_n h_n h_n^T, transformer.py:242-244) into the K-major operands of lc_gemm_bf16. */

@@ -54,6 +54,8 @@ SIGNATURES = {
     "lc_lora_merge_qkv": (c_int, [P, P, P, P, P, P, c_int, c_int, P]),
     "lc_lora_bgrad": (c_int, [P, P, P, c_int, c_int, P]),
     "lc_prompt_key_match": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "lc_coda_prompt_forward": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "lc_coda_prompt_backward": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "lc_gather_rows_bf16": (c_int, [P, P, c_longlong, c_int, c_int, c_int, P, P]),
     "lc_transpose_bf16": (c_int, [P, c_longlong, c_longlong, c_int, P, c_longlong, P]),
     "lc_lora_merge": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P]),

@@ -237,6 +237,35 @@ int lc_prompt_key_match(const float* query, const float* const* keys, float* con
     prompt_key_match_kernel<768><<<1, 256, 0, (cudaStream_t)stream>>>(a);
     return lc_launch_status();
 }
+int lc_coda_prompt_forward(const float* query, const float* const* K, const float* const* A, const float* const* p, void* const* pk_bf16, void* const* pv_bf16,
+                           int nlayers, int batch, int nk, int length, int dim, float* alpha, float* vnorm, lc_stream_t stream) {
+    LC_CHECK_ARG(query && K && A && p && pk_bf16 && pv_bf16 && alpha && vnorm && nlayers >= 1 && nlayers <= kPromptMaxLayers && batch >= 1 && nk >= 1 &&
+                 nk <= kCodaMaxK && length >= 2 && length % 2 == 0 && dim == 768);
+    CodaArgs a{};
+    a.q = query; a.alpha = alpha; a.vnorm = vnorm; a.B = batch; a.nk = nk; a.Lp = length; a.D = dim;
+    for (int l = 0; l < nlayers; ++l) {
+        a.K[l] = K[l]; a.A[l] = A[l]; a.p[l] = p[l]; a.pk[l] = reinterpret_cast<__nv_bfloat16*>(pk_bf16[l]); a.pv[l] = reinterpret_cast<__nv_bfloat16*>(pv_bf16[l]);
+        LC_CHECK_ARG(a.K[l] && a.A[l] && a.p[l] && a.pk[l] && a.pv[l]);
+    }
+    coda_prompt_fwd_kernel<<<dim3(batch, nlayers), 192, 0, (cudaStream_t)stream>>>(a);
+    return lc_launch_status();
+}
+int lc_coda_prompt_backward(const float* query, const float* const* K, const float* const* A, const float* const* p, const float* const* dpk, const float* const* dpv,
+                            float* const* dK, float* const* dA, float* const* dp, int nlayers, int batch, int nk, int length, int dim, const float* alpha,
+                            const float* vnorm, float* dalpha, lc_stream_t stream) {
+    LC_CHECK_ARG(query && K && A && p && dpk && dpv && dK && dA && dp && alpha && vnorm && dalpha && nlayers >= 1 && nlayers <= kPromptMaxLayers && batch >= 1 &&
+                 nk >= 1 && nk <= kCodaMaxK && length >= 2 && length % 2 == 0 && dim == 768);
+    CodaBwdArgs a{};
+    a.q = query; a.alpha = alpha; a.vnorm = vnorm; a.dalpha = dalpha; a.B = batch; a.nk = nk; a.Lp = length; a.D = dim;
+    for (int l = 0; l < nlayers; ++l) {
+        a.K[l] = K[l]; a.A[l] = A[l]; a.p[l] = p[l]; a.dpk[l] = dpk[l]; a.dpv[l] = dpv[l]; a.dK[l] = dK[l]; a.dA[l] = dA[l]; a.dp[l] = dp[l];
+        LC_CHECK_ARG(a.K[l] && a.A[l] && a.p[l] && a.dpk[l] && a.dpv[l] && a.dK[l] && a.dA[l] && a.dp[l]);
+    }
+    coda_prompt_bwd_alpha_kernel<<<dim3(batch, nlayers), 192, 0, (cudaStream_t)stream>>>(a);
+    if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
+    coda_prompt_bwd_param_kernel<<<dim3(length + nk, nlayers), 192, 0, (cudaStream_t)stream>>>(a);
+    return lc_launch_status();
+}
 int lc_gather_rows_bf16(const float* src, const int64_t* idx, long long idx_stride, int rows, int dim, int batch, void* out_bf16, lc_stream_t stream) {
     LC_CHECK_ARG(src && out_bf16 && rows >= 1 && rows <= 65535 && dim % 4 == 0 && batch >= 1);
     gather_rows_bf16_kernel<<<dim3(batch, rows), 192, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<const long long*>(idx), idx_stride, rows, dim,

@@ -4,3 +4,4 @@ from .resnet_methods import EWC, LUCIR, LWF, Finetune, ICarl  # noqa: F401
 from .l2p import L2P, ViTZoo, vit_pt_imnet  # noqa: F401
 from .inflora import InfLoRA_OPT, SiNet  # noqa: F401
 from .dualprompt import DualPrompt, DualPromptPool  # noqa: F401
+from .codaprompt import CodaPrompt, CodaPromptPool  # noqa: F401

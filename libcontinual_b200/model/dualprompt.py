@@ -13,7 +13,7 @@ prompts, keys, classifier) live in one flat arena `theta` in the reference's `ge
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional  # noqa: F401
 
 import torch
 import torch.nn as nn
@@ -68,19 +68,35 @@ class Model(nn.Module):
         self.classifier = None
 
 
-class DualPrompt(nn.Module):
+class _PrefixPromptMethod(nn.Module):
+    """Shared plugin body of the prefix-tuning methods (dualprompt.py:46-128 and codaprompt.py:57-121 are the same class around different pools):
+    flat arena of [pool parameters | classifier], growing classifier, masked CE, `observe` / `inference`.  Subclasses provide the pool and the two
+    pool-specific launches: `_prefixes` (query -> per-image BF16 prefix rows of blocks 0-4) and `_prompt_backward` (prefix-row gradients -> pool)."""
+
+    flag = ""
+
+    def _make_pool(self, kwargs) -> nn.Module:
+        raise NotImplementedError
+
+    def _pool_tensors(self, pool) -> List[nn.Parameter]:
+        raise NotImplementedError
+
+    def _prefix_shapes(self) -> Dict[int, int]:
+        """block index -> number of prefix keys (= values)."""
+        raise NotImplementedError
+
     def __init__(self, backbone: ViTZoo, feat_dim, num_class, **kwargs):
         super().__init__()
         if not isinstance(backbone, ViTZoo):
-            raise LcError("DualPrompt needs a libcontinual_b200 ViTZoo backbone")
+            raise LcError(f"{type(self).__name__} needs a libcontinual_b200 ViTZoo backbone")
         assert feat_dim == DIM
         self.kwargs = kwargs
         self.device = torch.device(kwargs.get("device", backbone.engine.dev))
         self.backbone = backbone
         self.engine = eng = backbone.engine
         self.network = Model(backbone, feat_dim, kwargs["init_cls_num"])
-        pool = DualPromptPool(DIM, kwargs["task_num"], [10, kwargs["e_prompt_length"], kwargs["g_prompt_length"]])
-        backbone.prompt, backbone.prompt_flag = pool, "dual"
+        pool = self._make_pool(kwargs)
+        backbone.prompt, backbone.prompt_flag = pool, self.flag
         self.pool = pool
         self.num_class = num_class
         self.task_idx = 0
@@ -88,9 +104,7 @@ class DualPrompt(nn.Module):
         self.out_dim = 0
         dev = eng.dev
         # flat arena in the order of `list(prompt.parameters()) + list(classifier.parameters())` (dualprompt.py:127-128)
-        tensors = [getattr(pool, f"g_p_{g}") for g in G_LAYERS]
-        for e in E_LAYERS:
-            tensors += [getattr(pool, f"e_p_{e}"), getattr(pool, f"e_k_{e}")]
+        tensors = self._pool_tensors(pool)
         self.n_prompt = sum(t.numel() for t in tensors)
         self.oW, self.ob = self.n_prompt, self.n_prompt + num_class * DIM
         self.theta = torch.zeros(self.ob + num_class, device=dev)
@@ -111,9 +125,10 @@ class DualPrompt(nn.Module):
         self._bufs: Dict[int, dict] = {}
         self.scal = torch.zeros(8, device=dev)
         self.prompt_loss = torch.zeros(1, device=dev)
-        PtrArr = ctypes.c_void_p * len(E_LAYERS)
-        self._keys = PtrArr(*[getattr(pool, f"e_k_{e}").data_ptr() for e in E_LAYERS])
-        self._dkeys = PtrArr(*[self._grad_view(getattr(pool, f"e_k_{e}")).data_ptr() for e in E_LAYERS])
+        self._setup_pool_pointers()
+
+    def _setup_pool_pointers(self):
+        pass
 
     # ---- arena helpers -----------------------------------------------------------------------------
     def _grad_view(self, p: torch.Tensor, arena: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -130,9 +145,7 @@ class DualPrompt(nn.Module):
         if B not in self._bufs:
             dev, C = self.engine.dev, self.num_class
             bf = torch.bfloat16
-            gl, el = self.pool.g_p_length // 2, self.pool.e_p_length // 2
-            pre = {l: (torch.zeros(B, gl, DIM, device=dev, dtype=bf), torch.zeros(B, gl, DIM, device=dev, dtype=bf)) for l in G_LAYERS}
-            pre.update({l: (torch.zeros(B, el, DIM, device=dev, dtype=bf), torch.zeros(B, el, DIM, device=dev, dtype=bf)) for l in E_LAYERS})
+            pre = {l: (torch.zeros(B, n, DIM, device=dev, dtype=bf), torch.zeros(B, n, DIM, device=dev, dtype=bf)) for l, n in self._prefix_shapes().items()}
             self._bufs[B] = dict(logits=torch.zeros(B, C, device=dev), dlogits=torch.zeros(B, C, device=dev), pred=torch.zeros(B, dtype=torch.int64, device=dev),
                                  dfeat=torch.zeros(B, DIM, device=dev), idx=torch.zeros(len(E_LAYERS), B, dtype=torch.int64, device=dev), prefix=pre)
         return self._bufs[B]
@@ -158,33 +171,10 @@ class DualPrompt(nn.Module):
     def after_task(self, task_idx, buffer, train_loader, test_loaders):
         self.last_out_dim = self.out_dim
 
-    def _prefixes(self, x, bb, train: bool):
-        """Query pass + key match + gather of the per-image BF16 prefix rows of blocks 0-4."""
-        eng, lib, st = self.engine, self.engine.lib, stream_ptr()
-        B = x.shape[0]
-        pool = self.pool
-        ws1 = eng.forward(x, None, save=False)
-        q = eng.pooled(ws1, 0)
-        check(lib.lc_prompt_key_match(q.data_ptr(), self._keys, self._dkeys if train else None, len(E_LAYERS), B, pool.e_pool_size, DIM,
-                                      self.task_idx if train else -1, bb["idx"].data_ptr(), self.prompt_loss.data_ptr() if train else None, st), "prompt_key_match")
-        gl, el = pool.g_p_length // 2, pool.e_p_length // 2
-        for l in G_LAYERS:
-            g = getattr(pool, f"g_p_{l}")
-            for half, out in enumerate(bb["prefix"][l]):
-                check(lib.lc_gather_rows_bf16(g.data_ptr() + 4 * half * gl * DIM, None, 0, gl, DIM, B, out.data_ptr(), st), "gather g")
-        for li, l in enumerate(E_LAYERS):
-            e = getattr(pool, f"e_p_{l}")
-            for half, out in enumerate(bb["prefix"][l]):
-                check(lib.lc_gather_rows_bf16(e.data_ptr() + 4 * half * el * DIM, bb["idx"][li].data_ptr(), pool.e_p_length * DIM, el, DIM, B, out.data_ptr(), st),
-                      "gather e")
-        eng.launches += 1 + 2 * (len(G_LAYERS) + len(E_LAYERS))
-        return bb["prefix"]
-
     def _launch_step(self, x, y, clip: bool = True):
         eng, lib, st = self.engine, self.engine.lib, stream_ptr()
         B = x.shape[0]
         bb = self._batch_bufs(B)
-        pool = self.pool
         self.theta_grad.zero_()                  # rows of other tasks' prompts / old classes keep exact zeros (Adam then leaves them untouched)
         prefix = self._prefixes(x, bb, train=True)
         ws = eng.forward(x, None, save=True, prefix=prefix)
@@ -199,17 +189,8 @@ class DualPrompt(nn.Module):
         check(lib.lc_linear_head_backward(bb["dlogits"][:, lo:].data_ptr(), C, feat.data_ptr(), self.head_W[lo].data_ptr(), n - lo, B, DIM, gW.data_ptr(),
                                           gb.data_ptr(), bb["dfeat"].data_ptr(), st), "linear_head_backward")
         eng.backward_tokens(ws, bb["dfeat"], 0, to_tokens=False)
-        # prefix-row gradients: summed over the batch into the prompt parameters (`expand(len(x_querry), -1, -1)`, prompt.py:284,306)
-        gl, el = pool.g_p_length // 2, pool.e_p_length // 2
-        for l in G_LAYERS:
-            gg = self._grad_view(getattr(pool, f"g_p_{l}"))
-            for half, d in enumerate(ws.prefix_grads(l, gl)):
-                check(lib.lc_sum_batch_rows(d.data_ptr(), gl * DIM, B, gl, DIM, gg[half * gl:].data_ptr(), st), "sum g")
-        for l in E_LAYERS:
-            ge = self._grad_view(getattr(pool, f"e_p_{l}"))[self.task_idx]
-            for half, d in enumerate(ws.prefix_grads(l, el)):
-                check(lib.lc_sum_batch_rows(d.data_ptr(), el * DIM, B, el, DIM, ge[half * el:].data_ptr(), st), "sum e")
-        eng.launches += 3 + 2 * (len(G_LAYERS) + len(E_LAYERS))
+        self._prompt_backward(ws, bb)
+        eng.launches += 3
         return bb
 
     def observe(self, data):
@@ -235,3 +216,64 @@ class DualPrompt(nn.Module):
                                     self.scal.data_ptr(), st), "argmax")
         eng.launches += 1
         return bb["pred"], float(self.scal[1].item()) / B
+
+
+class DualPrompt(_PrefixPromptMethod):
+    flag = "dual"
+
+    def _make_pool(self, kwargs):
+        return DualPromptPool(DIM, kwargs["task_num"], [10, kwargs["e_prompt_length"], kwargs["g_prompt_length"]])
+
+    def _pool_tensors(self, pool):
+        tensors = [getattr(pool, f"g_p_{g}") for g in G_LAYERS]
+        for e in E_LAYERS:
+            tensors += [getattr(pool, f"e_p_{e}"), getattr(pool, f"e_k_{e}")]
+        return tensors
+
+    def _prefix_shapes(self):
+        d = {l: self.pool.g_p_length // 2 for l in G_LAYERS}
+        d.update({l: self.pool.e_p_length // 2 for l in E_LAYERS})
+        return d
+
+    def _setup_pool_pointers(self):
+        pool = self.pool
+        PtrArr = ctypes.c_void_p * len(E_LAYERS)
+        self._keys = PtrArr(*[getattr(pool, f"e_k_{e}").data_ptr() for e in E_LAYERS])
+        self._dkeys = PtrArr(*[self._grad_view(getattr(pool, f"e_k_{e}")).data_ptr() for e in E_LAYERS])
+
+    def _prefixes(self, x, bb, train: bool):
+        """Query pass + key match + gather of the per-image BF16 prefix rows of blocks 0-4."""
+        eng, lib, st = self.engine, self.engine.lib, stream_ptr()
+        B = x.shape[0]
+        pool = self.pool
+        ws1 = eng.forward(x, None, save=False)
+        q = eng.pooled(ws1, 0)
+        check(lib.lc_prompt_key_match(q.data_ptr(), self._keys, self._dkeys if train else None, len(E_LAYERS), B, pool.e_pool_size, DIM,
+                                      self.task_idx if train else -1, bb["idx"].data_ptr(), self.prompt_loss.data_ptr() if train else None, st), "prompt_key_match")
+        gl, el = pool.g_p_length // 2, pool.e_p_length // 2
+        for l in G_LAYERS:
+            g = getattr(pool, f"g_p_{l}")
+            for half, out in enumerate(bb["prefix"][l]):
+                check(lib.lc_gather_rows_bf16(g.data_ptr() + 4 * half * gl * DIM, None, 0, gl, DIM, B, out.data_ptr(), st), "gather g")
+        for li, l in enumerate(E_LAYERS):
+            e = getattr(pool, f"e_p_{l}")
+            for half, out in enumerate(bb["prefix"][l]):
+                check(lib.lc_gather_rows_bf16(e.data_ptr() + 4 * half * el * DIM, bb["idx"][li].data_ptr(), pool.e_p_length * DIM, el, DIM, B, out.data_ptr(), st),
+                      "gather e")
+        eng.launches += 1 + 2 * (len(G_LAYERS) + len(E_LAYERS))
+        return bb["prefix"]
+
+    def _prompt_backward(self, ws, bb):
+        """Prefix-row gradients summed over the batch into the prompt parameters (`expand(len(x_querry), -1, -1)`, prompt.py:284,306)."""
+        eng, lib, st, pool = self.engine, self.engine.lib, stream_ptr(), self.pool
+        B = ws.B
+        gl, el = pool.g_p_length // 2, pool.e_p_length // 2
+        for l in G_LAYERS:
+            gg = self._grad_view(getattr(pool, f"g_p_{l}"))
+            for half, d in enumerate(ws.prefix_grads(l, gl)):
+                check(lib.lc_sum_batch_rows(d.data_ptr(), gl * DIM, B, gl, DIM, gg[half * gl:].data_ptr(), st), "sum g")
+        for l in E_LAYERS:
+            ge = self._grad_view(getattr(pool, f"e_p_{l}"))[self.task_idx]
+            for half, d in enumerate(ws.prefix_grads(l, el)):
+                check(lib.lc_sum_batch_rows(d.data_ptr(), el * DIM, B, el, DIM, ge[half * el:].data_ptr(), st), "sum e")
+        eng.launches += 2 * (len(G_LAYERS) + len(E_LAYERS))

@@ -485,6 +485,34 @@ def dualprompt_loss(logits: Tensor, y: Tensor, last_out_dim: int, prompt_loss: T
 
 
 # ----------------------------------------------------------------------------------------------
+# CodaPrompt on ViT-B/16  (core/model/backbone/prompt.py:146-214 pool forward; core/model/codaprompt.py:89-104 observe = DualPrompt's)
+# ----------------------------------------------------------------------------------------------
+CODA_LAYERS = (0, 1, 2, 3, 4)
+
+
+def codaprompt_prefixes(pool: Dict[str, Tensor], q: Tensor, nk: int):
+    """Per-layer prefix (keys, values): P_[b] = sum_k cos(q_b * A_k, K_k) p[k] over the first nk components (task_count stays 0 in the reference:
+    `process_task_count` is never called, so s = 0, f = pool_size / n_tasks in training and at inference alike).  pool: 'e_p_{l}' [pool, Lp, D],
+    'e_k_{l}', 'e_a_{l}' [pool, D]."""
+    prefix: Dict[int, Tuple[Tensor, Tensor]] = {}
+    for l in CODA_LAYERS:
+        K, A, pp = pool[f"e_k_{l}"][:nk], pool[f"e_a_{l}"][:nk], pool[f"e_p_{l}"][:nk]
+        a_q = torch.einsum("bd,kd->bkd", q, A)
+        aq_k = torch.einsum("bkd,kd->bk", F.normalize(a_q, dim=2), F.normalize(K, dim=1))
+        P_ = torch.einsum("bk,kld->bld", aq_k, pp)
+        i = pp.shape[1] // 2
+        prefix[l] = (P_[:, :i], P_[:, i:])
+    return prefix
+
+
+def codaprompt_forward(p: Dict[str, Tensor], pool: Dict[str, Tensor], x: Tensor, nk: int, depth: int = 12, heads: int = 12, gemm_mode: str = "fp32"):
+    with torch.no_grad():
+        q = vit_tokens(p, x, None, depth, heads, gemm_mode)[:, 0]
+    feat = vit_tokens(p, x, None, depth, heads, gemm_mode, prefix=codaprompt_prefixes(pool, q, nk))[:, 0]
+    return feat, q
+
+
+# ----------------------------------------------------------------------------------------------
 # iCaRL exemplar management
 # ----------------------------------------------------------------------------------------------
 def herding_select(features: Tensor, targets: Tensor, per_class: int) -> List[int]:

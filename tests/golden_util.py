@@ -107,3 +107,17 @@ def synth_dual_pool(seed, num_class=100):
     fc_w = torch.from_numpy(rng.uniform(-bound, bound, (num_class, 768)).astype(np.float32))
     fc_b = torch.from_numpy(rng.uniform(-bound, bound, (num_class,)).astype(np.float32))
     return pool, fc_w, fc_b
+
+
+def synth_coda_pool(seed, num_class=100):
+    """Same draws as oracle/make_golden.py::synth_coda_pool."""
+    rng = np.random.default_rng(seed)
+    pool = {}
+    for l in range(5):
+        pool[f"e_p_{l}"] = torch.from_numpy((rng.standard_normal((100, 8, 768)) / np.sqrt(768 * 8)).astype(np.float32))
+        pool[f"e_k_{l}"] = torch.from_numpy((rng.standard_normal((100, 768)) / np.sqrt(768)).astype(np.float32))
+        pool[f"e_a_{l}"] = torch.from_numpy((rng.standard_normal((100, 768)) / np.sqrt(768)).astype(np.float32))
+    bound = 1.0 / np.sqrt(768)
+    fc_w = torch.from_numpy(rng.uniform(-bound, bound, (num_class, 768)).astype(np.float32))
+    fc_b = torch.from_numpy(rng.uniform(-bound, bound, (num_class,)).astype(np.float32))
+    return pool, fc_w, fc_b

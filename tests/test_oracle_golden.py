@@ -219,3 +219,39 @@ def test_dualprompt_vit_observe_matches_reference():
         ref = torch.from_numpy(g["t1/" + k])
         err = float((v - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
         assert err < 2e-4, (k, err)
+
+
+def test_codaprompt_vit_observe_matches_reference():
+    """Oracle CodaPrompt step (attention-weighted prompt components as prefix keys / values on blocks 0-4, masked CE) vs the real reference pool + ViT
+    blocks + classifier (fixture: tests/golden/codaprompt_vit.npz), task 1 only here."""
+    from tests.golden_util import synth_coda_pool, synth_images, synth_vit_state
+    g = load("codaprompt_vit.npz")
+    torch.set_num_threads(8)
+    p = synth_vit_state(5150)[0]
+    pool, fc_w, fc_b = synth_coda_pool(940)
+    x, y = synth_images(761, 4, 10, 20)
+    op = {k: v.clone().requires_grad_(True) for k, v in pool.items()}
+    ow = fc_w[:20].clone().requires_grad_(True); ob = fc_b[:20].clone().requires_grad_(True)
+    feat, q = port.codaprompt_forward(p, op, x, 10)
+    loss = port.dualprompt_loss(port.linear_head(feat, ow, ob), y, 10, torch.zeros(()))
+    loss.backward()
+    assert abs(float(loss) - float(g["t1/loss"])) < 1e-5
+    got = {"dW": ow.grad, "db": ob.grad, "feat": feat.detach()}
+    got.update({"d" + k: v.grad[:10] for k, v in op.items()})
+    for k, v in got.items():
+        ref = torch.from_numpy(g["t1/" + k])
+        err = float((v - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
+        assert err < 1e-3, (k, err)
+
+
+def test_coda_pool_init_matches_reference_draws():
+    """Same torch-RNG draws as the reference constructor (uniform + Gram-Schmidt of the first pool/n_tasks rows, zeros elsewhere: prompt.py:48-64,98-144)."""
+    from libcontinual_b200.model.codaprompt import CodaPromptPool
+    g = load("codaprompt_vit.npz")
+    torch.manual_seed(7)
+    pool = CodaPromptPool(768, 10, [100, 8, 0.0])
+    gram = (pool.e_k_0[:10] @ pool.e_k_0[:10].T).detach().numpy()
+    assert np.allclose(gram, np.eye(10), atol=1e-5) and np.allclose(gram, g["init/e_k_0_gram"], atol=1e-5)
+    assert float(pool.e_p_3[10:].abs().max()) == float(g["init/e_p_3_tail_absmax"]) == 0.0
+    assert np.allclose(pool.e_a_2[:10, :8].detach().numpy(), g["init/e_a_2_head"], atol=1e-6)
+    assert np.allclose(pool.e_p_4[:10, 3, :8].detach().numpy(), g["init/e_p_4_head"], atol=1e-6)
