@@ -236,6 +236,16 @@ int lc_gather_rows_bf16(const float* src, const int64_t* idx, long long idx_stri
 /* out[c][r] = in[r][c] (BF16; columns [rows, ld_out) of out zero-filled): the transposed copy that turns a contraction over token rows
  * (InfLoRA's input matrix sum_n h_n h_n^T, transformer.py:242-244) into the K-major operands of lc_gemm_bf16. */
 int lc_transpose_bf16(const void* in_bf16, long long ld_in, long long rows, int cols, void* out_bf16, long long ld_out, lc_stream_t stream);
+/* lc_rowouter_bf16   : the general form of lc_lora_bgrad_rows: out[s][c][j] = scale * sum_n X[n][x0 + s*x_slab_stride + c] * Z[n][z0 + s*z_slab_stride + j];
+ *                      `transposed` writes out[s][j][c] instead (a lora_A gradient d A = (dY B)^T h with X = h, Z = dY B); scale_dev: nullable DEVICE scalar
+ *                      (SD-LoRA's trainable magnitude, sd_lora.py:122-125).
+ * lc_coldot_accumulate: dmag[i] += sum_{jj < rank} col_weight[i*rank + jj] * sum_n G[n][i*rank + jj] * Z[n][z0 + i*rank + jj], i < cols / rank — the gradient of
+ *                      the per-adapter magnitudes of MultiHeadAttention_SDLoRA (transformer.py:312-332) from G = dY B_cat and Z = h A_cat^T; accumulates
+ *                      (zero dmag once per step).  partial >= nchunk * cols floats. */
+int lc_rowouter_bf16(const void* x_bf16, long long ldx, int x0, int x_slab_stride, int nslab, int dim, const float* z, int ldz, int z0, int z_slab_stride, int rank,
+                     long long rows, float* partial, int nchunk, float* out, int transposed, const float* scale_dev, lc_stream_t stream);
+int lc_coldot_accumulate(const float* g, int ldg, const float* z, int ldz, int z0, int cols, int rank, long long rows, const float* col_weight, float* partial, int nchunk,
+                         float* dmag, lc_stream_t stream);
 int lc_lora_merge(const float* w, const float* A, const float* B, const float* scale, int slab_mask, int layers, int dim, int rank, void* wb_bf16,
                   void* wbt_bf16, float* w_out, lc_stream_t stream);
 long long lc_lora_bgrad_partial_floats(int nslab, int dim, int rank, int nchunk);

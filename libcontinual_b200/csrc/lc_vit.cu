@@ -290,18 +290,31 @@ int lc_lora_merge(const float* w, const float* A, const float* B, const float* s
     return lc_launch_status();
 }
 long long lc_lora_bgrad_partial_floats(int nslab, int dim, int rank, int nchunk) { return (long long)nslab * dim * rank * nchunk; }
-int lc_lora_bgrad_rows(const void* x_bf16, long long ldx, int x0, int x_slab_stride, int nslab, int dim, const float* z, int ldz, int rank, long long rows, float* partial,
-                       int nchunk, float* out, lc_stream_t stream) {
+int lc_rowouter_bf16(const void* x_bf16, long long ldx, int x0, int x_slab_stride, int nslab, int dim, const float* z, int ldz, int z0, int z_slab_stride, int rank,
+                     long long rows, float* partial, int nchunk, float* out, int transposed, const float* scale_dev, lc_stream_t stream) {
     LC_CHECK_ARG(x_bf16 && z && partial && out && nslab >= 1 && dim >= 768 && dim % 768 == 0 && rank >= 1 && rank <= 16 && rows >= 1 && nchunk >= 1);
-    LC_CHECK_ARG(ldx % 4 == 0 && x0 % 4 == 0 && x_slab_stride % 4 == 0 && ldz >= nslab * rank);
+    LC_CHECK_ARG(ldx % 4 == 0 && x0 % 4 == 0 && x_slab_stride % 4 == 0 && z0 >= 0 && ldz >= z0 + (nslab - 1) * z_slab_stride + rank);
     const int rows_per = (int)((rows + nchunk - 1) / nchunk);
     const dim3 grid(nslab * (dim / 768), nchunk);
     const __nv_bfloat16* X = reinterpret_cast<const __nv_bfloat16*>(x_bf16);
-    if (rank <= 10) rowouter_partial_kernel<10><<<grid, 192, 0, (cudaStream_t)stream>>>(X, ldx, x0, x_slab_stride, dim, z, ldz, rank, rows, rows_per, partial);
-    else rowouter_partial_kernel<16><<<grid, 192, 0, (cudaStream_t)stream>>>(X, ldx, x0, x_slab_stride, dim, z, ldz, rank, rows, rows_per, partial);
+    if (rank <= 10) rowouter_partial_kernel<10><<<grid, 192, 0, (cudaStream_t)stream>>>(X, ldx, x0, x_slab_stride, dim, z, ldz, z0, z_slab_stride, rank, rows, rows_per, partial);
+    else rowouter_partial_kernel<16><<<grid, 192, 0, (cudaStream_t)stream>>>(X, ldx, x0, x_slab_stride, dim, z, ldz, z0, z_slab_stride, rank, rows, rows_per, partial);
     if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
     const long long per_chunk = (long long)nslab * dim * rank;
-    rowouter_reduce_kernel<<<grid_for(per_chunk, 256), 256, 0, (cudaStream_t)stream>>>(partial, per_chunk, nchunk, out);
+    rowouter_reduce_kernel<<<grid_for(per_chunk, 256), 256, 0, (cudaStream_t)stream>>>(partial, per_chunk, nchunk, out, dim, rank, transposed, scale_dev);
+    return lc_launch_status();
+}
+int lc_lora_bgrad_rows(const void* x_bf16, long long ldx, int x0, int x_slab_stride, int nslab, int dim, const float* z, int ldz, int rank, long long rows, float* partial,
+                       int nchunk, float* out, lc_stream_t stream) {
+    return lc_rowouter_bf16(x_bf16, ldx, x0, x_slab_stride, nslab, dim, z, ldz, 0, rank, rank, rows, partial, nchunk, out, 0, nullptr, stream);
+}
+int lc_coldot_accumulate(const float* g, int ldg, const float* z, int ldz, int z0, int cols, int rank, long long rows, const float* col_weight, float* partial, int nchunk,
+                         float* dmag, lc_stream_t stream) {
+    LC_CHECK_ARG(g && z && partial && dmag && cols >= 1 && cols <= 128 && rank >= 1 && cols % rank == 0 && rows >= 1 && nchunk >= 1 && ldg >= cols && ldz >= z0 + cols);
+    const int rows_per = (int)((rows + nchunk - 1) / nchunk);
+    coldot_partial_kernel<<<nchunk, 256, 0, (cudaStream_t)stream>>>(g, ldg, z, ldz, z0, cols, rows, rows_per, partial);
+    if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
+    coldot_finish_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(partial, nchunk, cols, rank, col_weight, dmag);
     return lc_launch_status();
 }
 

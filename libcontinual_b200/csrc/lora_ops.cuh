@@ -66,10 +66,10 @@ __global__ void __launch_bounds__(256) lora_merge_kernel(LoraMergeArgs a) {
     }
 }
 
-// out[s][c][j] = sum_n X[n][x0 + s*xs + c] * Z[n][s*R + j]   (X bf16, Z fp32), D a multiple of 768 columns handled 4 per thread.
+// out[s][c][j] = sum_n X[n][x0 + s*xs + c] * Z[n][z0 + s*zs + j]   (X bf16, Z fp32), D a multiple of 768 columns handled 4 per thread.
 // grid (nslab * D/768, nchunk), 192 threads; each CTA sums `rows_per` token rows into partial[chunk][s][c][j].
 template <int R>
-__global__ void __launch_bounds__(192) rowouter_partial_kernel(const __nv_bfloat16* X, long long ldx, int x0, int xs, int D, const float* Z, int ldz, int r_real,
+__global__ void __launch_bounds__(192) rowouter_partial_kernel(const __nv_bfloat16* X, long long ldx, int x0, int xs, int D, const float* Z, int ldz, int z0, int zs, int r_real,
                                                                long long n, int rows_per, float* partial) {
     constexpr int TILE = 32;
     __shared__ float sZ[TILE][R];
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(192) rowouter_partial_kernel(const __nv_bfloat
         __syncthreads();
         for (int i = threadIdx.x; i < TILE * R; i += 192) {
             const int r = i / R, j = i % R;
-            sZ[r][j] = (r < nt && j < r_real) ? __ldg(Z + (size_t)(t0 + r) * ldz + s * r_real + j) : 0.f;
+            sZ[r][j] = (r < nt && j < r_real) ? __ldg(Z + (size_t)(t0 + r) * ldz + z0 + s * zs + j) : 0.f;
         }
         __syncthreads();
 #pragma unroll 1
@@ -118,12 +118,62 @@ __global__ void __launch_bounds__(192) rowouter_partial_kernel(const __nv_bfloat
             if (j < r_real) o[i * r_real + j] = acc[i][j];
 }
 
-// out[i] = (accumulate ? out[i] : 0) + sum_chunk partial[chunk][i], fixed order
-__global__ void __launch_bounds__(256) rowouter_reduce_kernel(const float* partial, long long per_chunk, int nchunk, float* out) {
+// out = scale * sum_chunk partial[chunk] in a fixed order; `transposed`: partial is [s][c][j], out is written as [s][j][c] (a lora_A gradient);
+// scale_ptr (nullable) is a device scalar (SD-LoRA's trainable magnitude of the current adapter)
+__global__ void __launch_bounds__(256) rowouter_reduce_kernel(const float* partial, long long per_chunk, int nchunk, float* out, int D, int r, int transposed,
+                                                              const float* scale_ptr) {
+    const float sc = scale_ptr != nullptr ? __ldg(scale_ptr) : 1.f;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < per_chunk; i += (long long)gridDim.x * 256) {
         float s = 0.f;
         for (int c = 0; c < nchunk; ++c) s += __ldcg(partial + (size_t)c * per_chunk + i);
-        out[i] = s;
+        long long o = i;
+        if (transposed) {
+            const long long slab = i / ((long long)D * r), rem = i % ((long long)D * r);
+            const int col = (int)(rem / r), j = (int)(rem % r);
+            o = slab * D * r + (long long)j * D + col;
+        }
+        out[o] = s * sc;
+    }
+}
+
+// colsum partials of the elementwise product of two fp32 matrices [n][ld] over `cols` columns: partial[chunk][j] = sum_{rows of chunk} G[n][j] * Z[n][zoff + j]
+// grid (nchunk), 256 threads = 8 warps striding rows; cols <= 128
+__global__ void __launch_bounds__(256) coldot_partial_kernel(const float* G, int ldg, const float* Z, int ldz, int zoff, int cols, long long n, int rows_per,
+                                                             float* partial) {
+    __shared__ float s_acc[8][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n0 = (long long)blockIdx.x * rows_per, n1 = n0 + rows_per < n ? n0 + rows_per : n;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long r = n0 + warp; r < n1; r += 8) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = lane + 32 * k;
+            if (j < cols) acc[k] = fmaf(__ldg(G + (size_t)r * ldg + j), __ldg(Z + (size_t)r * ldz + zoff + j), acc[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_acc[warp][lane + 32 * k] = acc[k];
+    __syncthreads();
+    if (threadIdx.x < cols) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += s_acc[w][threadIdx.x];
+        partial[(size_t)blockIdx.x * cols + threadIdx.x] = s;
+    }
+}
+// dmag[i] += w[i*r + jj]-weighted sum: dmag[i] += sum_{jj < r} colw[i*r + jj] * sum_chunk partial[chunk][i*r + jj]   (single block; sequential launches on
+// one stream accumulate in a fixed order)
+__global__ void __launch_bounds__(128) coldot_finish_kernel(const float* partial, int nchunk, int cols, int r, const float* colw, float* dmag) {
+    __shared__ float s_col[128];
+    if (threadIdx.x < cols) {
+        float s = 0.f;
+        for (int c = 0; c < nchunk; ++c) s += partial[(size_t)c * cols + threadIdx.x];
+        s_col[threadIdx.x] = s * (colw != nullptr ? colw[threadIdx.x] : 1.f);
+    }
+    __syncthreads();
+    if (threadIdx.x < cols / r) {
+        float s = 0.f;
+        for (int jj = 0; jj < r; ++jj) s += s_col[threadIdx.x * r + jj];
+        dmag[threadIdx.x] += s;
     }
 }
 

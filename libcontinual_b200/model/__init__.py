@@ -5,3 +5,4 @@ from .l2p import L2P, ViTZoo, vit_pt_imnet  # noqa: F401
 from .inflora import InfLoRA_OPT, SiNet  # noqa: F401
 from .dualprompt import DualPrompt, DualPromptPool  # noqa: F401
 from .codaprompt import CodaPrompt, CodaPromptPool  # noqa: F401
+from .sd_lora import SD_LoRA  # noqa: F401

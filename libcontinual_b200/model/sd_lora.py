@@ -1,0 +1,196 @@
+"""SD-LoRA on ViT-B/16 — mirror of the reference plugin surface (core/model/sd_lora.py:26-216: `Model`, `SD_LoRA`;
+core/model/backbone/transformer.py:276-357 `MultiHeadAttention_SDLoRA`) on top of `ViTEngine`.
+
+    backbone = vit_pt_imnet(pretrained=False, state=<VisionTransformer state_dict>, attn_layer="MultiHeadAttention_SDLoRA", lora_rank=10)
+    model    = SD_LoRA(backbone, device, init_cls_num=10, inc_cls_num=10, task_num=10, embd_dim=768, init_mag=1.0,
+                       rank_reduction=[False, 4, 8, 8, 6], knowledge_dist=[False, 9e-4], dataset="cifar100")
+
+Every task adds one rank-r adapter to the q and v projections of all 12 blocks; the forward adds  mag[t] B_t A_t h  for the current one and
+(mag[i] + assimilated[i]) B_i A_i h / (|B_i| |A_i|)  for the earlier ones — here folded into the BF16 GEMM operands once per step (`lc_lora_merge` with
+per-column scales).  Trainables: the current A_t, B_t (q and v, 12 blocks), ALL magnitudes (shared by the blocks, re-created at `init_mag` every task:
+sd_lora.py:122-125) and the whole classifier.  Gradients: dB_t, dA_t in rank form (`lc_rowouter_bf16`), d mag from G = dY B_cat and Z = h A_cat^T
+(`lc_coldot_accumulate`); nothing of size 768 x 768 is ever formed.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .._lib import LcError, check, stream_ptr
+from ..vit_engine import DIM, SDLoraState
+from .inflora import _FlatLoss
+from .l2p import ViTZoo
+
+
+class _Head(nn.Module):
+    def __init__(self, W, b, out_features):
+        super().__init__()
+        self.in_features, self.out_features = W.shape[1], out_features
+        self.weight = nn.Parameter(W[:out_features])
+        self.bias = nn.Parameter(b[:out_features])
+
+    def _apply(self, fn, recurse=True):
+        return self
+
+
+class Model(nn.Module):
+    """sd_lora.py:26-60: backbone + a classifier re-allocated (and re-initialised for the new rows) every task."""
+
+    def __init__(self, backbone, device, **kwargs):
+        super().__init__()
+        self._cur_task_id = -1
+        self.backbone, self.device = backbone, device
+        self.embed_dim, self.init_cls_num, self.inc_cls_num = kwargs["embd_dim"], kwargs["init_cls_num"], kwargs["inc_cls_num"]
+        self.classifier = None
+
+
+class SD_LoRA(nn.Module):
+    def __init__(self, backbone: ViTZoo, device, **kwargs):
+        super().__init__()
+        if not isinstance(backbone, ViTZoo):
+            raise LcError("SD_LoRA needs a libcontinual_b200 ViTZoo backbone")
+        self.device = torch.device(device)
+        self.init_cls_num, self.inc_cls_num, self.task_num = kwargs["init_cls_num"], kwargs["inc_cls_num"], kwargs["task_num"]
+        self.init_mag = float(kwargs["init_mag"])
+        self.rank_reduction, self.knowledge_dist = kwargs.get("rank_reduction", [False]), kwargs.get("knowledge_dist", [False])
+        if self.rank_reduction[0] or self.knowledge_dist[0]:
+            raise NotImplementedError("rank_reduction / knowledge_dist (SD-LoRA-RR / -KD variants) are not on the CUDA path; the shipped recipes disable both")
+        self._known_classes = 0
+        self.engine = eng = backbone.engine
+        self.rank = r = int(getattr(backbone, "lora_rank", 10))
+        self._network = Model(backbone, device, **kwargs)
+        L, dev = eng.depth, eng.dev
+        self.total_cls = self.init_cls_num + self.inc_cls_num * (self.task_num - 1)
+        nA = L * 2 * r * DIM
+        self.oB, self.oM = nA, 2 * nA
+        self.oW = self.oM + (self.task_num + 3) // 4 * 4
+        self.ob = self.oW + self.total_cls * DIM
+        self.theta = torch.zeros(self.ob + self.total_cls, device=dev)
+        self.theta_grad = torch.zeros_like(self.theta)
+        self.A_cur = self.theta[:nA].view(L, 2, r, DIM)
+        self.B_cur = self.theta[self.oB:self.oM].view(L, 2, DIM, r)
+        self.mag_all = self.theta[self.oM:self.oM + self.task_num]
+        self.head_W = self.theta[self.oW:self.ob].view(self.total_cls, DIM)
+        self.head_b = self.theta[self.ob:]
+        self.A_old: Optional[torch.Tensor] = None        # [L][2][t*r][D]
+        self.B_old: Optional[torch.Tensor] = None        # [L][2][D][t*r]
+        self.cur_task = -1
+        self.n_out = 0
+        self.params: List[nn.Parameter] = []
+        self._bufs = {}
+        self.scal = torch.zeros(8, device=dev)
+        self.autograd_grads: Optional[torch.Tensor] = None
+
+    # ---- flat-arena bookkeeping --------------------------------------------------------------------
+    def _grad_view(self, p, arena=None):
+        off = (p.data_ptr() - self.theta.data_ptr()) // 4
+        return (self.theta_grad if arena is None else arena)[off:off + p.numel()].view(p.shape)
+
+    def trainable_params(self):
+        return self.params
+
+    def get_parameters(self, config):
+        return self.params
+
+    def active_ranges(self):
+        t = self.cur_task
+        return [(0, self.oM), (self.oM, self.oM + t + 1), (self.oW, self.oW + self.n_out * DIM), (self.ob, self.ob + self.n_out)]
+
+    def _batch_bufs(self, B):
+        if B not in self._bufs:
+            dev = self.engine.dev
+            self._bufs[B] = dict(logits=torch.zeros(B, self.total_cls, device=dev), dlogits=torch.zeros(B, self.total_cls, device=dev),
+                                 pred=torch.zeros(B, dtype=torch.int64, device=dev), dfeat=torch.zeros(B, DIM, device=dev))
+        return self._bufs[B]
+
+    def _to_device(self, data):
+        x = data["image"].to(self.engine.dev, torch.float32, non_blocking=True).contiguous()
+        y = data["label"].to(self.engine.dev, torch.int64, non_blocking=True).contiguous()
+        return x, y
+
+    # ---- task boundaries -------------------------------------------------------------------------------
+    @torch.no_grad()
+    def before_task(self, task_idx, buffer, train_loader, test_loaders):
+        """sd_lora.py:107-139: grow + re-initialise the classifier (`update_fc`), reset every magnitude to init_mag, add one adapter per block
+        (A ~ kaiming_uniform(a = sqrt(5)), B = 0), same torch-RNG draw order as the reference."""
+        eng, L, r = self.engine, self.engine.depth, self.rank
+        self._network._cur_task_id += 1
+        self.cur_task = task_idx
+        old, new = self.n_out, self.init_cls_num + self.inc_cls_num * task_idx
+        fresh = nn.Linear(DIM, new, bias=True)
+        nn.init.kaiming_uniform_(fresh.weight, nonlinearity="linear")
+        self.head_W[old:new].copy_(fresh.weight[old:new]); self.head_b[old:new].zero_()
+        self.n_out = new
+        self._network.classifier = _Head(self.head_W, self.head_b, new)
+        self.mag_all[:task_idx + 1].fill_(self.init_mag)
+        A = torch.empty(L, 2, r, DIM)
+        for i in range(L):                                        # init_param() per attention module: lora_A_q then lora_A_v (transformer.py:300-301)
+            nn.init.kaiming_uniform_(A[i, 0], a=math.sqrt(5))
+            nn.init.kaiming_uniform_(A[i, 1], a=math.sqrt(5))
+        self.A_cur.copy_(A)
+        self.B_cur.zero_()
+        self._install_state()
+
+    def _install_state(self):
+        eng, t = self.engine, self.cur_task
+        eng.lora = SDLoraState(eng, self.rank, t + 1, self.A_cur, self._grad_view(self.A_cur), self.B_cur, self._grad_view(self.B_cur),
+                               self.mag_all[:t + 1], self.theta_grad[self.oM:self.oM + t + 1], self.A_old, self.B_old)
+        eng.lora.active = True
+        L = eng.depth
+        self.lora_A_q = nn.ParameterList([nn.Parameter(self.A_cur[i, 0]) for i in range(L)]); self.lora_A_v = nn.ParameterList([nn.Parameter(self.A_cur[i, 1]) for i in range(L)])
+        self.lora_B_q = nn.ParameterList([nn.Parameter(self.B_cur[i, 0]) for i in range(L)]); self.lora_B_v = nn.ParameterList([nn.Parameter(self.B_cur[i, 1]) for i in range(L)])
+        self.mag_lora = nn.ParameterList([nn.Parameter(self.mag_all[i:i + 1]) for i in range(t + 1)])
+        head = self._network.classifier
+        self.params = (list(self.lora_A_q) + list(self.lora_A_v) + list(self.lora_B_q) + list(self.lora_B_v) + list(self.mag_lora) + [head.weight, head.bias])
+
+    @torch.no_grad()
+    def after_task(self, task_idx, buffer, train_loader, test_loaders):
+        """sd_lora.py:141-143 (+ the adapter joins the frozen stack that the next task's forward keeps adding)."""
+        self._known_classes += self.init_cls_num if task_idx == 0 else self.inc_cls_num
+        A, B = self.A_cur.clone(), self.B_cur.clone()
+        self.A_old = A if self.A_old is None else torch.cat([self.A_old, A], dim=2)
+        self.B_old = B if self.B_old is None else torch.cat([self.B_old, B], dim=3)
+
+    # ---- the step ------------------------------------------------------------------------------------
+    def _launch_step(self, x, y, clip: bool = True):
+        eng, lib, st = self.engine, self.engine.lib, stream_ptr()
+        B = x.shape[0]
+        bb = self._batch_bufs(B)
+        eng.lora_merge()
+        ws = eng.forward(x, None, save=True)
+        feat = eng.pooled(ws, 0)
+        C, n, lo = self.total_cls, self.n_out, self._known_classes
+        eng.linear_head(feat, self.head_W[:n], self.head_b[:n], bb["logits"])
+        # CE over logits[:, known:] with y - known; prediction over ALL current logits (sd_lora.py:88-93)
+        check(lib.lc_loss_ce_kd(bb["logits"].data_ptr(), C, None, 0, y.data_ptr(), B, lo, n, 0, 0.0, 1.0, n, bb["dlogits"].data_ptr(), bb["pred"].data_ptr(),
+                                self.scal.data_ptr(), st), "loss_ce")
+        check(lib.lc_linear_head_backward(bb["dlogits"].data_ptr(), C, feat.data_ptr(), self.head_W.data_ptr(), n, B, DIM,
+                                          self.theta_grad[self.oW:].data_ptr(), self.theta_grad[self.ob:].data_ptr(), bb["dfeat"].data_ptr(), st), "linear_head_backward")
+        eng.backward_tokens(ws, bb["dfeat"], 0, to_tokens=False)
+        eng.launches += 2
+        return bb
+
+    def observe(self, data):
+        x, y = self._to_device(data)
+        bb = self._launch_step(x, y)
+        acc = float(self.scal[1].item()) / x.shape[0]
+        return bb["pred"], acc, _FlatLoss.apply(self, self.scal[0], *self.params)
+
+    @torch.no_grad()
+    def inference(self, data):
+        x, y = self._to_device(data)
+        eng, lib, st = self.engine, self.engine.lib, stream_ptr()
+        B = x.shape[0]
+        bb = self._batch_bufs(B)
+        eng.lora_merge()
+        ws = eng.forward(x, None, save=False)
+        feat = eng.pooled(ws, 0)
+        C, n = self.total_cls, self.n_out
+        eng.linear_head(feat, self.head_W[:n], self.head_b[:n], bb["logits"])
+        check(lib.lc_loss_ce_kd(bb["logits"].data_ptr(), C, None, 0, y.data_ptr(), B, 0, n, 0, 0.0, 1.0, n, bb["dlogits"].data_ptr(), bb["pred"].data_ptr(),
+                                self.scal.data_ptr(), st), "argmax")
+        eng.launches += 1
+        return bb["pred"], float(self.scal[1].item()) / B

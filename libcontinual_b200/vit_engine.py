@@ -48,7 +48,7 @@ class _Workspace:
     """Activation buffers of one (batch, tokens) shape.  With `save` every block keeps what its backward needs:
     x_in / x_mid (LayerNorm inputs), qkv, attention output + row log-sum-exp, pre-GELU fc1 output."""
 
-    def __init__(self, B: int, T: int, depth: int, save: bool, dev, lora_cols: int = 0):
+    def __init__(self, B: int, T: int, depth: int, save: bool, dev, lora_cols: int = 0, keep_h: bool = False):
         self.B, self.T, self.Tp, self.save = B, T, _up8(T), save
         bf, f32 = torch.bfloat16, torch.float32
         n = B * T
@@ -67,6 +67,8 @@ class _Workspace:
         self.feat = torch.empty(B, DIM, device=dev, dtype=f32)
         # LoRA down-projections h A^T of every block (fp32 [n, adapted slabs * rank]), kept for the adapter gradients
         self.hA = [torch.empty(n, lora_cols, device=dev, dtype=f32) for _ in range(depth if save else 1)] if lora_cols else None
+        # ln_1 outputs of every block (BF16), kept only when the adapters' down-projections train (SD-LoRA: d lora_A = (dY B)^T h)
+        self.hs = [torch.empty(n, DIM, device=dev, dtype=bf) for _ in range(depth)] if (keep_h and save) else None
         self.bwd = None
 
     def idx(self, layer: int) -> int:
@@ -100,8 +102,11 @@ class LoraState:
         self.slabs, self.ns, self.rank = tuple(slabs), len(slabs), rank
         assert self.ns in (1, 2) and all(0 <= s <= 2 for s in slabs) and list(slabs) == sorted(slabs)
         self.slab_mask = sum(1 << s for s in slabs)
+        self.nad, self.R = 1, rank                    # stacked adapters per slab and their total rank
         self.cols = self.ns * rank
-        assert self.cols % 4 == 0, "adapted slabs * rank must be a multiple of 4 (fp32 rows of the down-projection are stored 16-byte aligned)"
+        self.ldz = (self.cols + 3) // 4 * 4           # row stride of the saved down-projections (fp32 rows 16-byte aligned)
+        self.scale = None
+        self.train_A = False
         self.A = torch.zeros(L, self.ns, rank, DIM, device=engine.dev)
         self.A_bf = torch.zeros(L, self.cols, DIM, device=engine.dev, dtype=torch.bfloat16)
         assert B.shape == (L, self.ns, DIM, rank) and dB.shape == B.shape and B.is_contiguous() and dB.is_contiguous()
@@ -115,6 +120,71 @@ class LoraState:
         """Installs the down-projections for the coming task (and their BF16 GEMM copy)."""
         self.A.copy_(A.reshape(self.A.shape))
         self.engine._cast(self.A.reshape(self.A_bf.shape), self.A_bf)
+
+    def sync(self):
+        """Hook run before every merge (adapters whose parameters change per step refresh their derived copies here)."""
+
+
+class SDLoraState(LoraState):
+    """MultiHeadAttention_SDLoRA (transformer.py:276-357): adapters on q and v, one per task stacked along the rank axis (R = rank * (t + 1)); the
+    current one (A and B trainable, magnitude mag[t]) next to the frozen earlier ones, each scaled by (mag[i] + assimilated[i]) / (|B_i| |A_i|); all
+    magnitudes train and are shared by the 12 blocks (sd_lora.py:122-125).  A_cur [L][2][r][D], B_cur [L][2][D][r], mag [t + 1] and their gradients are
+    views of the owner's flat arenas; A_old / B_old hold the earlier adapters [L][2][t*r][D] / [L][2][D][t*r]."""
+
+    def __init__(self, engine: "ViTEngine", rank: int, nad: int, A_cur, dA_cur, B_cur, dB_cur, mag, dmag, A_old=None, B_old=None, assimilated=None):
+        L, dev = engine.depth, engine.dev
+        self.engine = engine
+        self.slabs, self.ns, self.rank = (0, 2), 2, rank
+        self.slab_mask = 0b101
+        self.nad, self.R = nad, rank * nad
+        assert self.R <= 128, "at most 128 stacked adapter ranks"
+        self.Rp = (self.R + 3) // 4 * 4
+        self.cols = 2 * self.R
+        self.ldz = (self.cols + 3) // 4 * 4
+        self.ldg = 2 * self.Rp
+        self.train_A = True
+        self.A_cur, self.dA_cur, self.B_cur, self.dB_cur, self.mag, self.dmag = A_cur, dA_cur, B_cur, dB_cur, mag, dmag
+        assert A_cur.shape == (L, 2, rank, DIM) and B_cur.shape == (L, 2, DIM, rank) and mag.shape == (nad,)
+        self.A = torch.zeros(L, 2, self.R, DIM, device=dev)
+        self.B = torch.zeros(L, 2, DIM, self.R, device=dev)
+        self.A_bf = torch.zeros(L, self.cols, DIM, device=dev, dtype=torch.bfloat16)
+        self.BT_bf = torch.zeros(L, 2, self.R, DIM, device=dev, dtype=torch.bfloat16)
+        self.scale = torch.ones(L, 2, self.R, device=dev)
+        self.inv_norm = torch.ones(L, 2, self.R, device=dev)            # 1 / (|B_i| |A_i|) per column of an old adapter (0 if either norm is 0), 1 for the current
+        self.assim = torch.zeros(nad, device=dev) if assimilated is None else assimilated.to(dev)
+        r0 = rank * (nad - 1)
+        if nad > 1:
+            self.A[:, :, :r0].copy_(A_old); self.B[:, :, :, :r0].copy_(B_old)
+            for i in range(nad - 1):
+                sl = slice(i * rank, (i + 1) * rank)
+                nb = self.B[:, :, :, sl].flatten(2).norm(dim=2); na = self.A[:, :, sl].flatten(2).norm(dim=2)         # Frobenius norms, per block and slab
+                ok = (nb != 0) & (na != 0)
+                self.inv_norm[:, :, sl] = torch.where(ok, 1.0 / (nb * na).clamp_min(1e-30), torch.zeros_like(nb)).unsqueeze(-1)
+            self.A_bf.view(L, 2, self.R, DIM)[:, :, :r0].copy_(self.A[:, :, :r0])
+            self.BT_bf[:, :, :r0].copy_(self.B[:, :, :, :r0].transpose(2, 3))
+        self.cur = slice(r0, self.R)
+        self.col_adapter = torch.arange(self.R, device=dev) // rank
+        self.nchunk = 148
+        self.partial = torch.empty(engine.lib.lc_lora_bgrad_partial_floats(2, DIM, rank, self.nchunk), device=dev)
+        self.cd_chunks = 296
+        self.cd_partial = torch.empty(self.cd_chunks * self.R, device=dev)
+        self._g = {}
+        self.active = False
+
+    def gbuf(self, n: int) -> torch.Tensor:
+        if n not in self._g:
+            self._g[n] = torch.zeros(n, self.ldg, device=self.engine.dev)
+        return self._g[n]
+
+    def sync(self):
+        """Current adapter -> stacked fp32 / BF16 copies; column scales from the (trainable) magnitudes; zero the magnitude gradient accumulator."""
+        L = self.engine.depth
+        self.A[:, :, self.cur].copy_(self.A_cur)
+        self.B[:, :, :, self.cur].copy_(self.B_cur)
+        self.A_bf.view(L, 2, self.R, DIM)[:, :, self.cur].copy_(self.A_cur)
+        self.BT_bf[:, :, self.cur].copy_(self.B_cur.transpose(2, 3))
+        torch.mul((self.mag + self.assim)[self.col_adapter], self.inv_norm, out=self.scale)
+        self.dmag.zero_()
 
 
 class ViTEngine:
@@ -176,10 +246,11 @@ class ViTEngine:
         return out
 
     def workspace(self, B: int, T: int, save: bool) -> _Workspace:
-        lc = self.lora.cols if self.lora is not None else 0
-        key = (B, T, save, lc)
+        lc = self.lora.ldz if self.lora is not None else 0
+        keep_h = self.lora is not None and self.lora.train_A
+        key = (B, T, save, lc, keep_h)
         if key not in self._ws:
-            self._ws[key] = _Workspace(B, T, self.depth, save, self.dev, lora_cols=lc)
+            self._ws[key] = _Workspace(B, T, self.depth, save, self.dev, lora_cols=lc, keep_h=keep_h)
         return self._ws[key]
 
     def tensor_core_error(self) -> bool:
@@ -243,13 +314,14 @@ class ViTEngine:
         xin = ws.x[i] if ws.save else ws.x[i % 2]
         xout = ws.x[i + 1] if ws.save else ws.x[(i + 1) % 2]
         xmid, qkv, o, upre = ws.xmid[k], ws.qkv[k], ws.o[k], ws.upre[k]
-        self._ln(xin, pre + "ln_1", 1e-5, out_bf16=ws.h)
+        h1 = ws.hs[i] if ws.hs is not None else ws.h
+        self._ln(xin, pre + "ln_1", 1e-5, out_bf16=h1)
         if self.cov is not None:
             self._accumulate_input_matrix(i, ws)
         if self.lora is not None and self.lora.active and ws.save:
             lo = self.lora
-            self.gemm(ws.h.data_ptr(), DIM, lo.A_bf[i].data_ptr(), DIM, ws.hA[k].data_ptr(), lo.cols, B * T, lo.cols, DIM, out_f32=True)
-        self._linear(ws.h, pre + "attn.qkv.weight", qkv, bias=pre + "attn.qkv.bias")
+            self.gemm(h1.data_ptr(), DIM, lo.A_bf[i].data_ptr(), DIM, ws.hA[k].data_ptr(), lo.ldz, B * T, lo.cols, DIM, out_f32=True)
+        self._linear(h1, pre + "attn.qkv.weight", qkv, bias=pre + "attn.qkv.bias")
         if prefix is None:
             check(self.lib.lc_attn_forward(qkv.data_ptr(), o.data_ptr(), ws.lse[k].data_ptr(), B, T, HEADS, self.err.data_ptr(), st), "attn_forward")
         else:
@@ -368,7 +440,9 @@ class ViTEngine:
     def lora_merge(self, w_out: bool = False):
         """W' = W + B A for the adapted slabs of every layer into the BF16 GEMM operands (w_out: also into the fp32 master = `merge_weight`)."""
         lo = self.lora
-        check(self.lib.lc_lora_merge(self.qkv_w.data_ptr(), lo.A.data_ptr(), lo.B.data_ptr(), None, lo.slab_mask, self.depth, DIM, lo.rank,
+        lo.sync()
+        check(self.lib.lc_lora_merge(self.qkv_w.data_ptr(), lo.A.data_ptr(), lo.B.data_ptr(), None if lo.scale is None else lo.scale.data_ptr(), lo.slab_mask,
+                                     self.depth, DIM, lo.R,
                                      self.qkv_wb.data_ptr(), self.qkv_wbt.data_ptr(), self.qkv_w.data_ptr() if w_out else None, stream_ptr()), "lora_merge")
         self.launches += 1
 
@@ -376,10 +450,26 @@ class ViTEngine:
         """d lora_B[i] = d(slab)^T (h A^T): rank-form adapter gradient of block i from the token gradient of the adapted QKV slabs."""
         lo = self.lora
         n = ws.B * ws.T
-        check(self.lib.lc_lora_bgrad_rows(dqkv.data_ptr(), 3 * DIM, lo.slabs[0] * DIM, (lo.slabs[1] - lo.slabs[0]) * DIM if lo.ns > 1 else DIM, lo.ns, DIM,
-                                          ws.hA[i].data_ptr(), lo.cols, lo.rank, n, lo.partial.data_ptr(), lo.nchunk, lo.dB[i].data_ptr(), stream_ptr()),
-              "lora_bgrad_rows")
-        self.launches += 2
+        st = stream_ptr()
+        xs = (lo.slabs[1] - lo.slabs[0]) * DIM if lo.ns > 1 else DIM
+        if not lo.train_A:
+            check(self.lib.lc_lora_bgrad_rows(dqkv.data_ptr(), 3 * DIM, lo.slabs[0] * DIM, xs, lo.ns, DIM, ws.hA[i].data_ptr(), lo.ldz, lo.rank, n, lo.partial.data_ptr(),
+                                              lo.nchunk, lo.dB[i].data_ptr(), st), "lora_bgrad_rows")
+            self.launches += 2
+            return
+        # SD-LoRA: G = d(slab) B_cat ([n, R] per slab) -> magnitudes; current adapter: dB = mag dY^T (h A^T), dA = mag (dY B)^T h
+        G = lo.gbuf(n)
+        z0 = (lo.nad - 1) * lo.rank
+        for si, slab in enumerate(lo.slabs):
+            self.gemm(dqkv.data_ptr() + 2 * slab * DIM, 3 * DIM, lo.BT_bf[i, si].data_ptr(), DIM, G.data_ptr() + 4 * si * lo.Rp, lo.ldg, n, lo.R, DIM, out_f32=True)
+            check(self.lib.lc_coldot_accumulate(G.data_ptr() + 4 * si * lo.Rp, lo.ldg, ws.hA[i].data_ptr(), lo.ldz, si * lo.R, lo.R, lo.rank, n,
+                                                lo.inv_norm[i, si].data_ptr(), lo.cd_partial.data_ptr(), lo.cd_chunks, lo.dmag.data_ptr(), st), "coldot")
+        mag_cur = lo.mag.data_ptr() + 4 * (lo.nad - 1)
+        check(self.lib.lc_rowouter_bf16(dqkv.data_ptr(), 3 * DIM, lo.slabs[0] * DIM, xs, lo.ns, DIM, ws.hA[i].data_ptr(), lo.ldz, z0, lo.R, lo.rank, n,
+                                        lo.partial.data_ptr(), lo.nchunk, lo.dB_cur[i].data_ptr(), 0, mag_cur, st), "rowouter dB")
+        check(self.lib.lc_rowouter_bf16(ws.hs[i].data_ptr(), DIM, 0, 0, lo.ns, DIM, G.data_ptr(), lo.ldg, z0, lo.Rp, lo.rank, n,
+                                        lo.partial.data_ptr(), lo.nchunk, lo.dA_cur[i].data_ptr(), 1, mag_cur, st), "rowouter dA")
+        self.launches += 4 * lo.ns + 4
 
     def prompt_row_grads(self, g: torch.Tensor, n_prompt: int, out: torch.Tensor) -> torch.Tensor:
         """Gradient of the prompt rows shared by the batch: out[r] = sum_b g[b, r]  (the `repeat(B, 1)` of prompt.py:390)."""

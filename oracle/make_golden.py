@@ -779,6 +779,93 @@ def golden_codaprompt(core):
     np.savez_compressed(os.path.join(OUT, "codaprompt_vit.npz"), **out)
 
 
+def synth_sdlora_state(seed: int, n_adapters: int, n_cls: int, depth: int = 12, rank: int = 10):
+    """Adapters of every block for `n_adapters` tasks (small non-zero B so that every term is exercised), magnitudes, classifier."""
+    rng = np.random.default_rng(seed)
+    blocks = []
+    for _ in range(depth):
+        ads = []
+        for _ in range(n_adapters):
+            d = {}
+            for sn in "qv":
+                d[f"A_{sn}"] = torch.from_numpy((rng.uniform(-1, 1, (rank, 768)) / np.sqrt(768)).astype(np.float32))
+                d[f"B_{sn}"] = torch.from_numpy((0.05 * rng.standard_normal((768, rank))).astype(np.float32))
+            ads.append(d)
+        blocks.append(ads)
+    mags = torch.from_numpy(rng.uniform(0.6, 1.4, (n_adapters,)).astype(np.float32))
+    bound = np.sqrt(3.0 / 768)
+    hw = torch.from_numpy(rng.uniform(-bound, bound, (n_cls, 768)).astype(np.float32))
+    hb = torch.from_numpy(rng.uniform(-0.05, 0.05, (n_cls,)).astype(np.float32))
+    return blocks, mags, hw, hb
+
+
+def golden_sdlora(core):
+    """The real `core.model.sd_lora.SD_LoRA` on `vit_pt_imnet(attn_layer='MultiHeadAttention_SDLoRA', lora_rank=10)`: observe() + backward on task 0 (one
+    adapter) and task 2 (three adapters: two frozen + the current one; all three magnitudes train)."""
+    from core.model.backbone.vit import vit_pt_imnet
+    from core.model.sd_lora import SD_LoRA as RefSD
+    print("SD_LoRA / ViT-B/16: reference observe() vs oracle")
+    out = {}
+    p = synth_vit_state(5150)[0]
+    bb = vit_pt_imnet(pretrained=False, attn_layer="MultiHeadAttention_SDLoRA", lora_rank=10)
+    ref = RefSD(bb, torch.device("cpu"), init_cls_num=10, inc_cls_num=10, task_num=10, embd_dim=768, init_mag=1.0, rank_reduction=[False, 4, 8, 8, 6],
+                knowledge_dist=[False, 9e-4], dataset="cifar100")
+    bb.feat.load_state_dict(p, strict=False)
+    for task in (0, 1, 2):
+        ref.before_task(task, None, None, None)
+        nad, ncls = task + 1, 10 * (task + 1)
+        blocks, mags, hw, hb = synth_sdlora_state(970 + task, nad, ncls)
+        if task > 0:                                   # earlier tasks' adapters stay what they were
+            for l in range(12):
+                blocks[l][:task] = prev_blocks[l]
+        with torch.no_grad():
+            for l, mod in enumerate(ref.attention_modules):
+                for i in range(nad):
+                    mod.lora_A_q_list[i].weight.copy_(blocks[l][i]["A_q"]); mod.lora_B_q_list[i].weight.copy_(blocks[l][i]["B_q"])
+                    mod.lora_A_v_list[i].weight.copy_(blocks[l][i]["A_v"]); mod.lora_B_v_list[i].weight.copy_(blocks[l][i]["B_v"])
+            for i in range(nad):
+                ref.attention_modules[0].mag_lora[i].copy_(mags[i:i + 1])
+            ref._network.classifier.weight.copy_(hw); ref._network.classifier.bias.copy_(hb)
+        prev_blocks = blocks
+        if task == 1:
+            ref.after_task(task, None, None, None)
+            continue
+        for q_ in ref._network.parameters():
+            q_.grad = None
+        lo = 10 * task
+        x, y = synth_images(780 + task, 4, lo, lo + 10)
+        ref._network.train()
+        pred, acc, loss = ref.observe({"image": x, "label": y})
+        loss.backward()
+        # oracle
+        ob_ = [[{k: v.clone().requires_grad_(i == task) for k, v in ad.items()} for i, ad in enumerate(blocks[l])] for l in range(12)]
+        om = [mags[i:i + 1].clone().requires_grad_(True) for i in range(nad)]
+        ow = hw.clone().requires_grad_(True); obias = hb.clone().requires_grad_(True)
+        ologits = port.sdlora_logits(p, ob_, om, ow, obias, x)
+        oloss = F.cross_entropy(ologits[:, lo:], y - lo)
+        oloss.backward()
+        close(oloss, loss, 1e-5, 1e-6, f"sdlora task{task} loss")
+        rm = ref.attention_modules
+        for nm, key, lst in (("dA_q", "A_q", "lora_A_q_list"), ("dB_q", "B_q", "lora_B_q_list"), ("dA_v", "A_v", "lora_A_v_list"), ("dB_v", "B_v", "lora_B_v_list")):
+            g_ref = torch.stack([getattr(m, lst)[task].weight.grad for m in rm])
+            g_orc = torch.stack([ob_[l][task][key].grad for l in range(12)])
+            close(g_orc, g_ref, 1e-3, 1e-4 * float(g_ref.abs().max()), f"sdlora task{task} {nm}")
+            out[f"t{task}/{nm}"] = g_ref.numpy().copy()
+        gm_ref = torch.cat([rm[0].mag_lora[i].grad for i in range(nad)])
+        close(torch.cat([m.grad for m in om]), gm_ref, 1e-3, 1e-4 * float(gm_ref.abs().max()), f"sdlora task{task} dmag")
+        close(ow.grad, ref._network.classifier.weight.grad, 1e-4, 2e-6, f"sdlora task{task} dW")
+        out[f"t{task}/dmag"] = gm_ref.numpy().copy()
+        out[f"t{task}/dW"] = ref._network.classifier.weight.grad.numpy().copy(); out[f"t{task}/db"] = ref._network.classifier.bias.grad.numpy().copy()
+        with torch.no_grad():
+            out[f"t{task}/logits"] = ref._network(x).numpy().copy()
+        out[f"t{task}/loss"] = np.float64(loss.item()); out[f"t{task}/pred"] = pred.numpy().copy()
+        # frozen adapters of earlier tasks receive no gradient in the reference
+        if task > 0:
+            assert rm[3].lora_B_q_list[0].weight.grad is None
+        ref.after_task(task, None, None, None)
+    np.savez_compressed(os.path.join(OUT, "sdlora_vit.npz"), **out)
+
+
 def main():
     torch.set_num_threads(8)
     os.makedirs(OUT, exist_ok=True)
@@ -798,6 +885,7 @@ def main():
     golden_inflora(core)
     golden_dualprompt(core)
     golden_codaprompt(core)
+    golden_sdlora(core)
     print("golden vectors written to", OUT)
 
 

@@ -361,6 +361,8 @@ def vit_tokens(p: Dict[str, Tensor], x: Tensor, prompts: Optional[Tensor] = None
             for si, sn in enumerate("qkv"):
                 if f"A_{sn}" in lora[i]:
                     slabs[si] = slabs[si] + lora[i][f"B_{sn}"] @ lora[i][f"A_{sn}"]
+                if f"delta_{sn}" in lora[i]:                     # a ready-made weight delta (SD-LoRA: scaled sum over the tasks' adapters)
+                    slabs[si] = slabs[si] + lora[i][f"delta_{sn}"]
             w_qkv = torch.cat(slabs, dim=0)
         qkv = r(F.linear(r(h), r(w_qkv), p[b + "attn.qkv.bias"]))
         qkv = qkv.reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
@@ -431,6 +433,32 @@ def inflora_init_A(cur_matrix: Tensor, rank: int) -> Tensor:
     """Task-0 adapter basis (InfLoRA_opt.py:248-254): the top-`rank` left singular vectors of the input matrix, scaled by 1/sqrt(3)."""
     U, _, _ = torch.linalg.svd(cur_matrix, full_matrices=False)
     return U[:, :rank].T / math.sqrt(3)
+
+
+# ----------------------------------------------------------------------------------------------
+# SD-LoRA on ViT-B/16  (core/model/backbone/transformer.py:304-357 MultiHeadAttention_SDLoRA.forward; core/model/sd_lora.py:80-94 observe)
+# ----------------------------------------------------------------------------------------------
+def sdlora_deltas(adapters: Sequence[Dict[str, Tensor]], mags: Sequence[Tensor], assimilated: Optional[Sequence[float]] = None) -> Dict[str, Tensor]:
+    """Weight-side form of one block's adapters: the LAST adapter enters as mag[-1] B A, every earlier one as (mag[i] + assimilated[i]) B_i A_i /
+    (|B_i|_F |A_i|_F), skipped when either norm is zero (transformer.py:312-332).  adapters[i] = {'A_q','B_q','A_v','B_v'}."""
+    out = {}
+    for sn in "qv":
+        last = adapters[-1]
+        d = mags[-1] * (last[f"B_{sn}"] @ last[f"A_{sn}"])
+        for i, ad in enumerate(adapters[:-1]):
+            nb, na = torch.norm(ad[f"B_{sn}"]), torch.norm(ad[f"A_{sn}"])
+            if nb != 0 and na != 0:
+                d = d + (mags[i] + (0.0 if assimilated is None else assimilated[i])) * (ad[f"B_{sn}"] @ ad[f"A_{sn}"]) / (nb * na)
+        out[f"delta_{sn}"] = d
+    return out
+
+
+def sdlora_logits(p: Dict[str, Tensor], blocks: Sequence[Sequence[Dict[str, Tensor]]], mags: Sequence[Tensor], head_w: Tensor, head_b: Tensor, x: Tensor,
+                  depth: int = 12, heads: int = 12, gemm_mode: str = "fp32") -> Tensor:
+    """blocks[l] = the adapters of block l in task order; the magnitudes are shared by all blocks (sd_lora.py:122-125)."""
+    lora = [sdlora_deltas(blocks[l], mags) for l in range(depth)]
+    feat = vit_tokens(p, x, None, depth, heads, gemm_mode, lora=lora)[:, 0]
+    return F.linear(feat, head_w, head_b)
 
 
 # ----------------------------------------------------------------------------------------------

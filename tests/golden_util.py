@@ -121,3 +121,36 @@ def synth_coda_pool(seed, num_class=100):
     fc_w = torch.from_numpy(rng.uniform(-bound, bound, (num_class, 768)).astype(np.float32))
     fc_b = torch.from_numpy(rng.uniform(-bound, bound, (num_class,)).astype(np.float32))
     return pool, fc_w, fc_b
+
+
+def synth_sdlora_state(seed, n_adapters, n_cls, depth=12, rank=10):
+    """Same draws as oracle/make_golden.py::synth_sdlora_state."""
+    rng = np.random.default_rng(seed)
+    blocks = []
+    for _ in range(depth):
+        ads = []
+        for _ in range(n_adapters):
+            d = {}
+            for sn in "qv":
+                d[f"A_{sn}"] = torch.from_numpy((rng.uniform(-1, 1, (rank, 768)) / np.sqrt(768)).astype(np.float32))
+                d[f"B_{sn}"] = torch.from_numpy((0.05 * rng.standard_normal((768, rank))).astype(np.float32))
+            ads.append(d)
+        blocks.append(ads)
+    mags = torch.from_numpy(rng.uniform(0.6, 1.4, (n_adapters,)).astype(np.float32))
+    bound = np.sqrt(3.0 / 768)
+    hw = torch.from_numpy(rng.uniform(-bound, bound, (n_cls, 768)).astype(np.float32))
+    hb = torch.from_numpy(rng.uniform(-0.05, 0.05, (n_cls,)).astype(np.float32))
+    return blocks, mags, hw, hb
+
+
+def sdlora_task_states(upto):
+    """The adapter stacks of tasks 0..upto exactly as the golden generator composed them (earlier tasks' adapters carried over)."""
+    prev, states = None, []
+    for task in range(upto + 1):
+        blocks, mags, hw, hb = synth_sdlora_state(970 + task, task + 1, 10 * (task + 1))
+        if task > 0:
+            for l in range(12):
+                blocks[l][:task] = prev[l]
+        prev = blocks
+        states.append((blocks, mags, hw, hb))
+    return states

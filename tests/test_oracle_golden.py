@@ -255,3 +255,29 @@ def test_coda_pool_init_matches_reference_draws():
     assert float(pool.e_p_3[10:].abs().max()) == float(g["init/e_p_3_tail_absmax"]) == 0.0
     assert np.allclose(pool.e_a_2[:10, :8].detach().numpy(), g["init/e_a_2_head"], atol=1e-6)
     assert np.allclose(pool.e_p_4[:10, 3, :8].detach().numpy(), g["init/e_p_4_head"], atol=1e-6)
+
+
+def test_sdlora_vit_observe_matches_reference():
+    """Oracle SD-LoRA step (scaled sum of per-task q / v adapters, shared trainable magnitudes) vs the real `core.model.sd_lora.SD_LoRA`
+    (fixture: tests/golden/sdlora_vit.npz), task 2 (two frozen adapters + the current one)."""
+    import torch.nn.functional as F
+    from tests.golden_util import sdlora_task_states, synth_images, synth_vit_state
+    g = load("sdlora_vit.npz")
+    torch.set_num_threads(8)
+    p = synth_vit_state(5150)[0]
+    blocks, mags, hw, hb = sdlora_task_states(2)[2]
+    x, y = synth_images(782, 4, 20, 30)
+    ob_ = [[{k: v.clone().requires_grad_(i == 2) for k, v in ad.items()} for i, ad in enumerate(blocks[l])] for l in range(12)]
+    om = [mags[i:i + 1].clone().requires_grad_(True) for i in range(3)]
+    ow = hw.clone().requires_grad_(True); obias = hb.clone().requires_grad_(True)
+    logits = port.sdlora_logits(p, ob_, om, ow, obias, x)
+    loss = F.cross_entropy(logits[:, 20:], y - 20)
+    loss.backward()
+    assert abs(float(loss) - float(g["t2/loss"])) < 1e-5
+    got = {"logits": logits.detach(), "dW": ow.grad, "db": obias.grad, "dmag": torch.cat([m.grad for m in om])}
+    for nm, key in (("dA_q", "A_q"), ("dB_q", "B_q"), ("dA_v", "A_v"), ("dB_v", "B_v")):
+        got[nm] = torch.stack([ob_[l][2][key].grad for l in range(12)])
+    for k, v in got.items():
+        ref = torch.from_numpy(g["t2/" + k])
+        err = float((v - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
+        assert err < 1e-3, (k, err)
