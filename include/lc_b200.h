@@ -168,6 +168,8 @@ typedef struct lc_gemm_desc {
     const void* gelu_bwd_aux;   /* nullable bf16 indexed like C: result *= GELU'(aux) */
     int M, N, K, batch_in, batch_out, out_f32;
     float alpha;
+    int gelu_mode;              /* bit 0: the GELU side tensor is GELU'(pre-activation): with out2, C stores it instead of the pre-activation; with
+                                 * gelu_bwd_aux, aux is a plain multiplier.  bit 1 (with out2): C is not stored at all (no-grad passes).  0 = as above. */
 } lc_gemm_desc;
 int lc_gemm_bf16_ex(const lc_gemm_desc* desc, int* error_flag, lc_stream_t stream);
 /* Row-wise / layout kernels of the ViT forward (transformer.py:2222-2261): im2col of the 16x16 patches (timm PatchEmbed as a GEMM), cls-row

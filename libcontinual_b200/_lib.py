@@ -105,7 +105,7 @@ class GemmDesc(ctypes.Structure):
                 ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_longlong), ("strideR_in", c_longlong), ("strideR_out", c_longlong),
                 ("out2", c_void_p), ("gelu_bwd_aux", c_void_p),
                 ("M", c_int), ("N", c_int), ("K", c_int), ("batch_in", c_int), ("batch_out", c_int), ("out_f32", c_int),
-                ("alpha", c_float)]
+                ("alpha", c_float), ("gelu_mode", c_int)]
 
 
 class LcError(RuntimeError):

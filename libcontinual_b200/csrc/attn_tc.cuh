@@ -19,6 +19,16 @@ namespace lc {
 namespace tc {
 
 constexpr int kAttnD = 64;                       // head dim
+
+#ifdef LC_ATTN_TIMING
+// debug build only (tools/attn_timing.py): globaltimer stamps of thread 0 of the first 2048 CTAs, 16 slots each
+__device__ unsigned long long g_attn_tstamp[2048 * 16];
+__device__ __forceinline__ unsigned long long attn_gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define LC_ASTAMP(slot) do { const unsigned cta_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); \
+    if (threadIdx.x == 0 && cta_ < 2048 && (slot) < 16) g_attn_tstamp[cta_ * 16 + (slot)] = attn_gtimer(); } while (0)
+#else
+#define LC_ASTAMP(slot) do { } while (0)
+#endif
 constexpr float kLog2e = 1.4426950408889634f;
 
 __host__ __device__ constexpr int attn_plane(int rows) { return rows * 16 + 16; }
@@ -55,6 +65,78 @@ __device__ __forceinline__ void stage_keys(uint32_t dst, int plane, const __nv_b
 }
 __device__ __forceinline__ float ex2_fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
+
+template <int W> __device__ __forceinline__ void tmem_ldw(uint32_t taddr, float* v) {
+    if constexpr (W == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+}
+// One W-column group of a score row: running maximum over the valid keys
+template <int W> __device__ __forceinline__ float attn_max_group(uint32_t trow, int c0, int NK, float m) {
+    float v[W];
+    tmem_ldw<W>(trow + (uint32_t)c0, v);
+    if (c0 + W <= NK) {
+#pragma unroll
+        for (int i = 0; i < W; ++i) m = fmaxf(m, v[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) if (c0 + i < NK) m = fmaxf(m, v[i]);
+    }
+    return m;
+}
+// One W-column group of P = exp2(S c - off) written as BF16 into the planar tile (row `row`); returns the sum of the ROUNDED probabilities
+template <int W> __device__ __forceinline__ float attn_p_group(uint32_t trow, int c0, int NK, float c, float off, unsigned char* tile, int PQ, int row) {
+    float v[W];
+    tmem_ldw<W>(trow + (uint32_t)c0, v);
+    const bool full = c0 + W <= NK;
+    float sum = 0.f;
+#pragma unroll
+    for (int g = 0; g < W / 8; ++g) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = g * 8 + 2 * i;
+            float p0 = ex2_fast(fmaf(v[k], c, -off)), p1 = ex2_fast(fmaf(v[k + 1], c, -off));
+            if (!full) { p0 = c0 + k < NK ? p0 : 0.f; p1 = c0 + k + 1 < NK ? p1 : 0.f; }
+            const uint32_t w = pack_bf16(p0, p1);
+            sum += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);
+            pk[i] = w;
+        }
+        *reinterpret_cast<uint4*>(tile + (size_t)(((c0 >> 3) + g) * PQ + row * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    return sum;
+}
+// sum_j P_j dP_j over one W-column group (P from the BF16 tile, dP from TMEM)
+template <int W> __device__ __forceinline__ float attn_d_group(uint32_t trow, int c0, const unsigned char* tile, int PQ, int row, float acc) {
+    float v[W];
+    tmem_ldw<W>(trow + (uint32_t)c0, v);
+#pragma unroll
+    for (int g = 0; g < W / 8; ++g) {
+        const uint4 pa = *reinterpret_cast<const uint4*>(tile + (size_t)(((c0 >> 3) + g) * PQ + row * 16));
+        const uint32_t pw[4] = {pa.x, pa.y, pa.z, pa.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            acc = fmaf(__uint_as_float(pw[i] << 16), v[g * 8 + 2 * i], acc);
+            acc = fmaf(__uint_as_float(pw[i] & 0xffff0000u), v[g * 8 + 2 * i + 1], acc);
+        }
+    }
+    return acc;
+}
+// dS = P (dP - D) for one W-column group, written as BF16 into the dS tile
+template <int W> __device__ __forceinline__ void attn_ds_group(uint32_t trow, int c0, const unsigned char* ptile, unsigned char* dstile, int PQ, int row, float Dr) {
+    float v[W];
+    tmem_ldw<W>(trow + (uint32_t)c0, v);
+#pragma unroll
+    for (int g = 0; g < W / 8; ++g) {
+        const size_t o = (size_t)(((c0 >> 3) + g) * PQ + row * 16);
+        const uint4 pa = *reinterpret_cast<const uint4*>(ptile + o);
+        const uint32_t pw[4] = {pa.x, pa.y, pa.z, pa.w};
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)                                                    // P is exactly 0 on padding rows / columns
+            pk[i] = pack_bf16(__uint_as_float(pw[i] << 16) * (v[g * 8 + 2 * i] - Dr), __uint_as_float(pw[i] & 0xffff0000u) * (v[g * 8 + 2 * i + 1] - Dr));
+        *reinterpret_cast<uint4*>(dstile + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
 struct AttnFwdArgs {
     const __nv_bfloat16* qkv;   // [B][T][3][H][64]
     __nv_bfloat16* out;         // [B][T][H*64]
@@ -86,17 +168,21 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwdArgs a) {
     const __nv_bfloat16* base = a.qkv + (size_t)b * T * ld + h * kAttnD;
     const __nv_bfloat16* pkb = P ? a.pk + (size_t)b * P * HD + h * kAttnD : base;
     const __nv_bfloat16* pvb = P ? a.pv + (size_t)b * P * HD + h * kAttnD : base;
+    LC_ASTAMP(0);
     stage_tile(sQ, PQ, base, ld, q0, 128, T, tid, 256);
     stage_keys(sK, PK, pkb, HD, P, base + HD, ld, T, NP, tid, 256);
-    stage_keys(sV, PK, pvb, HD, P, base + 2 * HD, ld, T, NP, tid, 256);
+    cp_async_commit();
+    stage_keys(sV, PK, pvb, HD, P, base + 2 * HD, ld, T, NP, tid, 256);      // needed only by P V: lands while the softmax runs
+    cp_async_commit();
     if (tid == 32) { mbar_init(bars, 1); mbar_init(bars + 1, 1); }
     if (warp == 0) tmem_alloc(slot, 256);
-    cp_async_wait_all();
+    cp_async_wait_group<1>();
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = *slot;
+    LC_ASTAMP(1);
     if (tid == 0) {
         const uint32_t idesc = attn_idesc(128, NP, 0, 0);
 #pragma unroll
@@ -105,51 +191,37 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwdArgs a) {
     }
     bool ok = mbar_wait(bars, 0);
     fence_after_sync();
+    LC_ASTAMP(2);
     // ---- softmax over this thread's half of the row held by its TMEM lane -----------------------------------------------------------
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int NPh = ((NP >> 1) + 15) & ~15;
     const int cbeg = chalf ? NPh : 0, cend = chalf ? NP : NPh;
     const float c = kLog2e * 0.125f;
     float m = -CUDART_INF_F;
-    for (int c0 = cbeg; c0 < cend; c0 += 16) {
-        float v[16];
-        tmem_ld16(trow + (uint32_t)c0, v);
-        if (c0 + 16 <= NK) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) m = fmaxf(m, v[i]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) if (c0 + i < NK) m = fmaxf(m, v[i]);
-        }
+    {
+        int c0 = cbeg;
+        for (; c0 + 32 <= cend; c0 += 32) m = attn_max_group<32>(trow, c0, NK, m);
+        if (c0 < cend) m = attn_max_group<16>(trow, c0, NK, m);
     }
     s_red[tid] = m;
     __syncthreads();
+    LC_ASTAMP(3);
     m = fmaxf(s_red[row], s_red[row + 128]);             // NK >= 1 key in the first half: finite
     const float mc = m * c;
     float sum = 0.f;
-    // P overlays the Q / K tiles, which MMA 1 (completed: bars[0]) has finished reading
-    for (int c0 = cbeg; c0 < cend; c0 += 16) {
-        float v[16];
-        tmem_ld16(trow + (uint32_t)c0, v);
-        uint32_t pk[8];
-        const bool full = c0 + 16 <= NK;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float p0 = ex2_fast(fmaf(v[2 * i], c, -mc)), p1 = ex2_fast(fmaf(v[2 * i + 1], c, -mc));
-            if (!full) { p0 = c0 + 2 * i < NK ? p0 : 0.f; p1 = c0 + 2 * i + 1 < NK ? p1 : 0.f; }
-            const uint32_t w = pack_bf16(p0, p1);
-            sum += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);       // normalise by what the tensor core will actually multiply
-            pk[i] = w;
-        }
-        unsigned char* dst = smem + (size_t)((c0 >> 3) * PQ + row * 16);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(dst + PQ) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    // P overlays the Q / K tiles, which MMA 1 (completed: bars[0]) has finished reading; rows are normalised by what the tensor core will actually multiply
+    {
+        int c0 = cbeg;
+        for (; c0 + 32 <= cend; c0 += 32) sum += attn_p_group<32>(trow, c0, NK, c, mc, smem, PQ, row);
+        if (c0 < cend) sum += attn_p_group<16>(trow, c0, NK, c, mc, smem, PQ, row);
     }
     s_red[256 + tid] = sum;
+    cp_async_wait_all();                                 // this thread's V chunks
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    LC_ASTAMP(4);
     if (tid == 0) {
         const uint32_t idesc = attn_idesc(128, kAttnD, 0, 1);
         for (int k = 0; k < NP / 16; ++k) mma_f16(tmem, desc_kmajor(sP, PQ, k), desc_mnmajor(sV, PK, k, 0), idesc, k != 0);
@@ -158,6 +230,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwdArgs a) {
     sum = s_red[256 + row] + s_red[256 + row + 128];
     ok = mbar_wait(bars + 1, 0) && ok;
     fence_after_sync();
+    LC_ASTAMP(5);
     if (!ok && a.error_flag != nullptr && (tid & 31) == 0) atomicExch(a.error_flag, 3);
     const int t = q0 + row;
     const float inv = 1.f / sum;
@@ -174,6 +247,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwdArgs a) {
         }
     }
     if (t < T && chalf == 0) a.lse2[((size_t)b * a.H + h) * T + t] = mc + log2f(sum);
+    LC_ASTAMP(6);
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 256);
@@ -226,8 +300,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
     const __nv_bfloat16* base = a.qkv + (size_t)b * T * ld + h * kAttnD;
     const __nv_bfloat16* pkb = P ? a.pk + (size_t)b * P * HD + h * kAttnD : base;
     const __nv_bfloat16* pvb = P ? a.pv + (size_t)b * P * HD + h * kAttnD : base;
+    LC_ASTAMP(0);
     stage_keys(sK, PK, pkb, HD, P, base + HD, ld, T, NP, tid, 256);
-    stage_keys(sV, PK, pvb, HD, P, base + 2 * HD, ld, T, NP, tid, 256);
     if (tid == 32) mbar_init(bar, 1);
     if (warp == 0) tmem_alloc(slot, 512);
     uint32_t phase = 0;
@@ -239,17 +313,22 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
     uint32_t tmem = 0;
     for (int qt = 0; qt < ntile; ++qt) {
         const int q0 = qt * 128;
+        // two copy groups: {K (first tile only), Q} feed S; {V (first tile only), dO} feed dP and land while S / P are being computed
         stage_tile(sQ, PQ, base, ld, q0, 128, T, tid, 256);
+        cp_async_commit();
+        if (qt == 0) stage_keys(sV, PK, pvb, HD, P, base + 2 * HD, ld, T, NP, tid, 256);
         stage_tile(sdO, PQ, a.dout + (size_t)b * T * HD + h * kAttnD, HD, q0, 128, T, tid, 256);
+        cp_async_commit();
         const int t = q0 + row;
         const bool rv = t < T;
-        const float l2 = rv ? a.lse2[((size_t)b * a.H + h) * T + t] : 0.f;        // in flight together with the tile copies
-        cp_async_wait_all();
+        const float l2 = rv ? a.lse2[((size_t)b * a.H + h) * T + t] : CUDART_INF_F;   // in flight with the tile copies; +inf: P = exp2(-inf) = 0 on padding rows
+        cp_async_wait_group<1>();
         fence_proxy_async();
         fence_before_sync();
         __syncthreads();
         fence_after_sync();
         tmem = *slot;
+        LC_ASTAMP(1 + 7 * qt);
         if (tid == 0) {
             const uint32_t idesc = attn_idesc(128, NP, 0, 0);
 #pragma unroll
@@ -258,26 +337,20 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
         }
         ok = mbar_wait(bar, phase & 1) && ok; ++phase;
         fence_after_sync();
+        LC_ASTAMP(2 + 7 * qt);
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         // ---- P = exp2(S c - lse2) for this thread's half of the key columns ------------------------------------------------------------
-        for (int c0 = cbeg; c0 < cend; c0 += 16) {
-            float v[16];
-            tmem_ld16(trow + (uint32_t)c0, v);
-            const bool full = rv && c0 + 16 <= NK;
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float p0 = ex2_fast(fmaf(v[2 * i], c, -l2)), p1 = ex2_fast(fmaf(v[2 * i + 1], c, -l2));
-                if (!full) { p0 = (rv && c0 + 2 * i < NK) ? p0 : 0.f; p1 = (rv && c0 + 2 * i + 1 < NK) ? p1 : 0.f; }
-                pk[i] = pack_bf16(p0, p1);
-            }
-            unsigned char* dst = g_sP + (size_t)((c0 >> 3) * PQ + row * 16);
-            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(dst + PQ) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        {
+            int c0 = cbeg;
+            for (; c0 + 32 <= cend; c0 += 32) attn_p_group<32>(trow, c0, NK, c, l2, g_sP, PQ, row);
+            if (c0 < cend) attn_p_group<16>(trow, c0, NK, c, l2, g_sP, PQ, row);
         }
+        cp_async_wait_all();                               // this thread's V / dO chunks
+        fence_proxy_async();
         fence_before_sync();
         __syncthreads();                                   // everyone is done reading S: its columns may now receive dP
         fence_after_sync();
+        LC_ASTAMP(3 + 7 * qt);
         if (tid == 0) {
             const uint32_t idesc = attn_idesc(128, NP, 0, 0);
 #pragma unroll
@@ -286,44 +359,30 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
         }
         ok = mbar_wait(bar, phase & 1) && ok; ++phase;
         fence_after_sync();
+        LC_ASTAMP(4 + 7 * qt);
         // ---- D = sum_j P_j dP_j in fp32 from the very probabilities the dS / dV products use.  (The usual shortcut D = dO . O inherits the BF16
         //      rounding of the stored O as a common-mode error of the whole row, which dS = P (dP - D) does not average out when the values of
         //      a head are nearly alike; the row sum over the keys has no such term.)  Partial sums of the two threads of a row meet in shared memory.
         float dpart = 0.f;
-        for (int c0 = cbeg; c0 < cend; c0 += 16) {
-            float v[16];
-            tmem_ld16(trow + (uint32_t)c0, v);
-            const unsigned char* src = g_sP + (size_t)((c0 >> 3) * PQ + row * 16);
-            const uint4 pa = *reinterpret_cast<const uint4*>(src), pb = *reinterpret_cast<const uint4*>(src + PQ);
-            const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                dpart = fmaf(__uint_as_float(pw[i] << 16), v[2 * i], dpart);
-                dpart = fmaf(__uint_as_float(pw[i] & 0xffff0000u), v[2 * i + 1], dpart);
-            }
+        {
+            int c0 = cbeg;
+            for (; c0 + 32 <= cend; c0 += 32) dpart = attn_d_group<32>(trow, c0, g_sP, PQ, row, dpart);
+            if (c0 < cend) dpart = attn_d_group<16>(trow, c0, g_sP, PQ, row, dpart);
         }
         s_dpart[tid] = dpart;
         __syncthreads();
         const float Dr = s_dpart[row] + s_dpart[row + 128];
         // ---- dS = P (dP - D) ---------------------------------------------------------------------------------------------------------
-        for (int c0 = cbeg; c0 < cend; c0 += 16) {
-            float v[16];
-            tmem_ld16(trow + (uint32_t)c0, v);
-            const unsigned char* src = g_sP + (size_t)((c0 >> 3) * PQ + row * 16);
-            const uint4 pa = *reinterpret_cast<const uint4*>(src), pb = *reinterpret_cast<const uint4*>(src + PQ);
-            const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)                                                // P is exactly 0 on padding rows / columns
-                pk[i] = pack_bf16(__uint_as_float(pw[i] << 16) * (v[2 * i] - Dr), __uint_as_float(pw[i] & 0xffff0000u) * (v[2 * i + 1] - Dr));
-            unsigned char* dst = g_sdS + (size_t)((c0 >> 3) * PQ + row * 16);
-            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(dst + PQ) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        {
+            int c0 = cbeg;
+            for (; c0 + 32 <= cend; c0 += 32) attn_ds_group<32>(trow, c0, g_sP, g_sdS, PQ, row, Dr);
+            if (c0 < cend) attn_ds_group<16>(trow, c0, g_sP, g_sdS, PQ, row, Dr);
         }
         fence_proxy_async();
         fence_before_sync();
         __syncthreads();                                   // P and dS tiles complete; dP consumed
         fence_after_sync();
+        LC_ASTAMP(5 + 7 * qt);
         if (tid == 0) {
             const uint32_t id_q = attn_idesc(128, kAttnD, 0, 1), id_kv = attn_idesc(128, kAttnD, 1, 1);
             for (int k = 0; k < NP / 16; ++k) mma_f16(tmem, desc_kmajor(sdS, PQ, k), desc_mnmajor(sK, PK, k, 0), id_q, k != 0);              // dQ
@@ -339,6 +398,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
         }
         ok = mbar_wait(bar, phase & 1) && ok; ++phase;
         fence_after_sync();
+        LC_ASTAMP(6 + 7 * qt);
         // ---- dQ tile out: thread (row, chalf) stores 32 of the 64 columns ----------------------------------------------------------------
         {
             __nv_bfloat16* o = a.dqkv + ((size_t)b * T + (rv ? t : 0)) * ld + h * kAttnD + chalf * 32;
@@ -357,6 +417,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
         fence_before_sync();
         __syncthreads();                                   // dQ columns and the Q / dO tiles are free for the next query tile
         fence_after_sync();
+        LC_ASTAMP(7 + 7 * qt);
     }
     // ---- dK, dV out: TMEM lane = key (half * 128 + row); thread (row, chalf): chalf 0 -> dK, chalf 1 -> dV.  Keys [0, P) are the prefix rows (fp32,
     //      their own matrices), keys [P, P + T) the tokens ----------------------------------------------------------------------------------------
@@ -370,21 +431,22 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
             __nv_bfloat16* o = a.dqkv + ((size_t)b * T + ((kv && !pre) ? key - P : 0)) * ld + (1 + chalf) * HD + h * kAttnD;
             float* op = pre ? (chalf == 0 ? a.dpk : a.dpv) + ((size_t)b * P + key) * HD + h * kAttnD : nullptr;
 #pragma unroll
-            for (int c0 = 0; c0 < kAttnD; c0 += 16) {
-                float v[16];
-                tmem_ld16(trow + (uint32_t)(256 + chalf * 128 + half * 64 + c0), v);
+            for (int c0 = 0; c0 < kAttnD; c0 += 32) {
+                float v[32];
+                tmem_ld32(trow + (uint32_t)(256 + chalf * 128 + half * 64 + c0), v);
                 if (pre) {
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(op + c0 + i) = make_float4(v[i] * sc, v[i + 1] * sc, v[i + 2] * sc, v[i + 3] * sc);
+                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + c0 + i) = make_float4(v[i] * sc, v[i + 1] * sc, v[i + 2] * sc, v[i + 3] * sc);
                 } else if (kv) {
-                    *reinterpret_cast<uint4*>(o + c0) = make_uint4(pack_bf16(v[0] * sc, v[1] * sc), pack_bf16(v[2] * sc, v[3] * sc), pack_bf16(v[4] * sc, v[5] * sc),
-                                                                   pack_bf16(v[6] * sc, v[7] * sc));
-                    *reinterpret_cast<uint4*>(o + c0 + 8) = make_uint4(pack_bf16(v[8] * sc, v[9] * sc), pack_bf16(v[10] * sc, v[11] * sc),
-                                                                       pack_bf16(v[12] * sc, v[13] * sc), pack_bf16(v[14] * sc, v[15] * sc));
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8)
+                        *reinterpret_cast<uint4*>(o + c0 + i) = make_uint4(pack_bf16(v[i] * sc, v[i + 1] * sc), pack_bf16(v[i + 2] * sc, v[i + 3] * sc),
+                                                                           pack_bf16(v[i + 4] * sc, v[i + 5] * sc), pack_bf16(v[i + 6] * sc, v[i + 7] * sc));
                 }
             }
         }
     }
+    LC_ASTAMP(15);
     if (!ok && a.error_flag != nullptr && (tid & 31) == 0) atomicExch(a.error_flag, 4);
     fence_before_sync();
     __syncthreads();

@@ -9,7 +9,7 @@
 //   warp 1 : MMA issuer — one elected thread issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M128 x BN x K16) per K-block with
 //            SWIZZLE_128B K-major shared-memory descriptors (SBO = 1024 B, start advanced by 32 B per K16 step), commits the stage back
 //            to the producer (empty[stage]) and, after the last K-block, the accumulator to the epilogue (tmem_full)
-//   warps 2-9 : epilogue (two warps per TMEM lane quarter, alternating 32-column slabs) — tcgen05.ld 32x32b (warp w owns TMEM lanes 32*(w%4)..), staged through shared memory so that bias / GELU /
+//   warps 2-9 (2-17 for the GELU variants) : epilogue (two / four warps per TMEM lane quarter, interleaved 32-column slabs) — tcgen05.ld 32x32b (warp w owns TMEM lanes 32*(w%4)..), staged through shared memory so that bias / GELU /
 //            residual and the global stores run row-wise (128-byte row segments per 8 lanes), then the accumulator is handed back (tmem_empty)
 // Operands are addressed through tensor maps (row stride and batch strides arbitrary), so the same kernel runs the per-head
 // batched attention GEMMs (Q K^T, P V) on strided views of the fused QKV buffer.
@@ -37,6 +37,10 @@ struct GemmArgs {
     int out_dtype;
     float alpha;               // scale applied to the accumulator before bias (attention: 1/sqrt(d))
     int* error_flag;
+    int gelu_mode;             // bit 0: the GELU side tensor holds GELU'(pre-activation) instead of the pre-activation itself — `out` of the out2 variant
+                               //        stores it, `gelu_aux` is then a plain multiplier (the backward epilogue drops from 25 to ~8 instructions per
+                               //        element; the frozen-backbone backward needs the pre-activation for nothing else).  bit 1: do not store `out`
+                               //        at all (no-grad passes keep only GELU(x) in out2)
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -74,13 +78,17 @@ __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& gauss) {
 __device__ __forceinline__ float gelu_erf(float x) { float c, g; gelu_parts(x, c, g); return x * c; }
 __device__ __forceinline__ float dgelu_erf(float x) { float c, g; gelu_parts(x, c, g); return fmaf(x * 0.3989422804014327f, g, c); }
 
-template <int BN>
+enum { EPI_F32 = 1, EPI_RES = 2, EPI_GELU2 = 4, EPI_DGELU = 8 };     // compile-time epilogue variants (keeps each instance's code small)
+
+template <int BN, int EPI = 0>
 struct GemmCfg {
     static constexpr int BM = 128, BK = 64;
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = BN == 256 ? 3 : 5;
-    static constexpr int EPI_WARPS = 8;
+    // GELU / GELU' epilogues are instruction-issue bound (ncu: 71 M warp instructions vs 9 M for the plain store, 25 per element): with two
+    // epilogue warps per scheduler their dependent MUFU / FMA chains leave the issue slots idle, so those variants run four per scheduler
+    static constexpr int EPI_WARPS = ((EPI & (EPI_GELU2 | EPI_DGELU)) != 0 && (EPI & EPI_RES) == 0) ? 16 : 8;
+    static constexpr int STAGES = BN == 256 ? 3 : (EPI_WARPS == 16 ? 4 : 5);
     static constexpr int NT = 64 + 32 * EPI_WARPS;
     static constexpr int SLAB = 32;                                   // epilogue column slab
     static constexpr int STG_LD = SLAB + 4;                           // staging row stride (floats): conflict-free float4 rows
@@ -88,6 +96,7 @@ struct GemmCfg {
     static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + STG_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
     static constexpr uint32_t TMEM_COLS = 2 * BN;                     // two accumulators: the epilogue of tile i overlaps the MMAs of tile i+1
     static_assert(BN == 128 || BN == 256, "BN");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 #ifdef LC_GEMM_TIMING
@@ -103,13 +112,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-enum { EPI_F32 = 1, EPI_RES = 2, EPI_GELU2 = 4, EPI_DGELU = 8 };     // compile-time epilogue variants (keeps each instance's code small)
-
 // Persistent: grid = min(#tiles, #SMs); CTA c processes tiles c, c + grid, ...  Tile order: m fastest inside an n panel (the B panel
 // — weights — stays hot in L2 across the CTAs working on it), panels inside a batch element.
 template <int BN, int EPI>
-__global__ void __launch_bounds__(GemmCfg<BN>::NT, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs a) {
-    using K = GemmCfg<BN>;
+__global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs a) {
+    using K = GemmCfg<BN, EPI>;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base_u = (smem_u32(smem_dyn) + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char* base = smem_dyn + (base_u - smem_u32(smem_dyn));
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(GemmCfg<BN>::NT, 1) gemm_bf16_kernel(const __g
             const size_t rz = (size_t)z_out * a.r_stride_out + (size_t)z_in * a.r_stride_in;
             const int mrow0 = m0 + quarter * 32;
 #pragma unroll 1
-            for (int c0 = spar * K::SLAB; c0 < BN && n0 + c0 < a.N; c0 += 2 * K::SLAB) {
+            for (int c0 = spar * K::SLAB; c0 < BN && n0 + c0 < a.N; c0 += (K::EPI_WARPS / 4) * K::SLAB) {
                 const int n = n0 + c0 + c4;
                 const bool vec = n + 3 < a.N;
                 float4 res[8];
@@ -250,14 +257,23 @@ __global__ void __launch_bounds__(GemmCfg<BN>::NT, 1) gemm_bf16_kernel(const __g
                         if constexpr ((EPI & EPI_RES) != 0) { x0 += res[j].x; x1 += res[j].y; x2 += res[j].z; x3 += res[j].w; }
                         if constexpr ((EPI & EPI_DGELU) != 0) {
                             const uint2 g = gaux[j];
-                            x0 *= dgelu_erf(__uint_as_float(g.x << 16)); x1 *= dgelu_erf(__uint_as_float(g.x & 0xffff0000u));
-                            x2 *= dgelu_erf(__uint_as_float(g.y << 16)); x3 *= dgelu_erf(__uint_as_float(g.y & 0xffff0000u));
+                            const float a0 = __uint_as_float(g.x << 16), a1 = __uint_as_float(g.x & 0xffff0000u), a2 = __uint_as_float(g.y << 16),
+                                        a3 = __uint_as_float(g.y & 0xffff0000u);
+                            if (a.gelu_mode & 1) { x0 *= a0; x1 *= a1; x2 *= a2; x3 *= a3; }
+                            else { x0 *= dgelu_erf(a0); x1 *= dgelu_erf(a1); x2 *= dgelu_erf(a2); x3 *= dgelu_erf(a3); }
+                        }
+                        if constexpr ((EPI & EPI_GELU2) != 0) {
+                            float c0_, c1_, c2_, c3_, g0_, g1_, g2_, g3_;
+                            gelu_parts(x0, c0_, g0_); gelu_parts(x1, c1_, g1_); gelu_parts(x2, c2_, g2_); gelu_parts(x3, c3_, g3_);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out2) + ci) = make_uint2(pack_bf16(x0 * c0_, x1 * c1_), pack_bf16(x2 * c2_, x3 * c3_));
+                            if (a.gelu_mode & 1) {                                   // GELU'(x) = Phi(x) + x phi(x)
+                                x0 = fmaf(x0 * 0.3989422804014327f, g0_, c0_); x1 = fmaf(x1 * 0.3989422804014327f, g1_, c1_);
+                                x2 = fmaf(x2 * 0.3989422804014327f, g2_, c2_); x3 = fmaf(x3 * 0.3989422804014327f, g3_, c3_);
+                            }
+                            if (a.gelu_mode & 2) continue;
                         }
                         if constexpr ((EPI & EPI_F32) != 0) *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + ci) = make_float4(x0, x1, x2, x3);
                         else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out) + ci) = make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
-                        if constexpr ((EPI & EPI_GELU2) != 0)
-                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out2) + ci) =
-                                make_uint2(pack_bf16(gelu_erf(x0), gelu_erf(x1)), pack_bf16(gelu_erf(x2), gelu_erf(x3)));
                     } else {
                         const float xs[4] = {x0, x1, x2, x3};
 #pragma unroll
@@ -265,10 +281,17 @@ __global__ void __launch_bounds__(GemmCfg<BN>::NT, 1) gemm_bf16_kernel(const __g
                             if (n + i >= a.N) break;
                             float xi = xs[i];
                             if constexpr ((EPI & EPI_RES) != 0) xi += a.residual[rz + (size_t)m * a.ldr + n + i];
-                            if constexpr ((EPI & EPI_DGELU) != 0) xi *= dgelu_erf(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.gelu_aux)[ci + i]));
+                            if constexpr ((EPI & EPI_DGELU) != 0) {
+                                const float av = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.gelu_aux)[ci + i]);
+                                xi *= (a.gelu_mode & 1) ? av : dgelu_erf(av);
+                            }
+                            if constexpr ((EPI & EPI_GELU2) != 0) {
+                                reinterpret_cast<__nv_bfloat16*>(a.out2)[ci + i] = __float2bfloat16_rn(gelu_erf(xi));
+                                if (a.gelu_mode & 1) xi = dgelu_erf(xi);
+                                if (a.gelu_mode & 2) continue;
+                            }
                             if constexpr ((EPI & EPI_F32) != 0) reinterpret_cast<float*>(a.out)[ci + i] = xi;
                             else reinterpret_cast<__nv_bfloat16*>(a.out)[ci + i] = __float2bfloat16_rn(xi);
-                            if constexpr ((EPI & EPI_GELU2) != 0) reinterpret_cast<__nv_bfloat16*>(a.out2)[ci + i] = __float2bfloat16_rn(gelu_erf(xi));
                         }
                     }
                 }

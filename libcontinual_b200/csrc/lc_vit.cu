@@ -56,7 +56,7 @@ int num_sms() {
 
 template <int BN, int EPI>
 int launch_gemm_epi(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmArgs& a, int batch, cudaStream_t st) {
-    using K = tc::GemmCfg<BN>;
+    using K = tc::GemmCfg<BN, EPI>;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(tc::gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES) != cudaSuccess) return LC_ERR_CUDA;
@@ -95,6 +95,13 @@ extern "C" int lc_debug_gemm_timing(unsigned long long* host_out) {
 }
 #endif
 
+#ifdef LC_ATTN_TIMING
+extern "C" int lc_debug_attn_timing(unsigned long long* host_out, int clear) {
+    if (clear) { static unsigned long long z[2048 * 16]; return cudaMemcpyToSymbol(tc::g_attn_tstamp, z, sizeof(z)) == cudaSuccess ? 0 : -1; }
+    return cudaMemcpyFromSymbol(host_out, tc::g_attn_tstamp, sizeof(unsigned long long) * 2048 * 16) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 extern "C" {
 
 int lc_gemm_bf16_ex(const lc_gemm_desc* d, int* error_flag, lc_stream_t stream) {
@@ -103,6 +110,7 @@ int lc_gemm_bf16_ex(const lc_gemm_desc* d, int* error_flag, lc_stream_t stream) 
     const int cal = d->out_f32 ? 4 : 8;      // vectorised epilogue stores: rows of C / residual start on 16-byte boundaries
     LC_CHECK_ARG(d->ldc % cal == 0 && d->strideC_in % cal == 0 && d->strideC_out % cal == 0);
     LC_CHECK_ARG(d->residual == nullptr || (d->ldr % 4 == 0 && d->strideR_in % 4 == 0 && d->strideR_out % 4 == 0));
+    LC_CHECK_ARG(d->gelu_mode >= 0 && d->gelu_mode <= 3 && ((d->gelu_mode & 2) == 0 || d->out2 != nullptr));
     CUtensorMap ta, tb;
     const int bn = d->N > 128 ? 256 : 128;
     tc::GemmArgs a{};
@@ -112,7 +120,7 @@ int lc_gemm_bf16_ex(const lc_gemm_desc* d, int* error_flag, lc_stream_t stream) 
     if (e != LC_OK) return e;
     a.out = d->C; a.bias = d->bias; a.residual = d->residual; a.out2 = d->out2; a.gelu_aux = d->gelu_bwd_aux; a.M = d->M; a.N = d->N; a.K = d->K; a.ldc = (int)d->ldc; a.ldr = (int)d->ldr;
     a.c_stride_in = d->strideC_in; a.c_stride_out = d->strideC_out; a.r_stride_in = d->strideR_in; a.r_stride_out = d->strideR_out;
-    a.batch_in = d->batch_in; a.batch_total = d->batch_in * d->batch_out; a.out_dtype = d->out_f32 ? tc::GEMM_OUT_F32 : tc::GEMM_OUT_BF16; a.alpha = d->alpha; a.error_flag = error_flag;
+    a.batch_in = d->batch_in; a.batch_total = d->batch_in * d->batch_out; a.out_dtype = d->out_f32 ? tc::GEMM_OUT_F32 : tc::GEMM_OUT_BF16; a.alpha = d->alpha; a.error_flag = error_flag; a.gelu_mode = d->gelu_mode;
     const int batch = d->batch_in * d->batch_out;
     return bn == 256 ? launch_gemm<256>(ta, tb, a, batch, (cudaStream_t)stream) : launch_gemm<128>(ta, tb, a, batch, (cudaStream_t)stream);
 }

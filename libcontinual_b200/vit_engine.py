@@ -46,7 +46,7 @@ def _up8(v: int) -> int:
 
 class _Workspace:
     """Activation buffers of one (batch, tokens) shape.  With `save` every block keeps what its backward needs:
-    x_in / x_mid (LayerNorm inputs), qkv, attention output + row log-sum-exp, pre-GELU fc1 output."""
+    x_in / x_mid (LayerNorm inputs), qkv, attention output + row log-sum-exp, GELU'(fc1 output) (`upre`)."""
 
     def __init__(self, B: int, T: int, depth: int, save: bool, dev, lora_cols: int = 0, keep_h: bool = False):
         self.B, self.T, self.Tp, self.save = B, T, _up8(T), save
@@ -259,7 +259,7 @@ class ViTEngine:
 
     # ---- GEMM plumbing -------------------------------------------------------------------------
     def gemm(self, A, lda, B, ldb, C, ldc, M, N, K, *, sA=(0, 0), sB=(0, 0), sC=(0, 0), batch=(1, 1), bias=None, residual=None, ldr=0, sR=(0, 0),
-             out2=None, gelu_bwd_aux=None, out_f32=False, alpha=1.0):
+             out2=None, gelu_bwd_aux=None, out_f32=False, alpha=1.0, gelu_mode=0):
         """C[z] = alpha * A[z] @ B[z]^T (+bias +residual); A/B/C/residual/out2 are raw device addresses (ints), strides in elements."""
         d = GemmDesc()
         d.A, d.lda, d.strideA_in, d.strideA_out = A, lda, sA[0], sA[1]
@@ -269,16 +269,17 @@ class ViTEngine:
         d.out2 = out2
         d.gelu_bwd_aux = gelu_bwd_aux
         d.M, d.N, d.K, d.batch_in, d.batch_out, d.out_f32, d.alpha = M, N, K, batch[0], batch[1], int(out_f32), alpha
+        d.gelu_mode = gelu_mode
         check(self.lib.lc_gemm_bf16_ex(ctypes.byref(d), self.err.data_ptr(), stream_ptr()), f"gemm {M}x{N}x{K}")
         self.launches += 1
 
-    def _linear(self, a_bf16: torch.Tensor, wname: str, out: torch.Tensor, *, bias=None, residual=None, out2=None, rows=None):
+    def _linear(self, a_bf16: torch.Tensor, wname: str, out: torch.Tensor, *, bias=None, residual=None, out2=None, rows=None, gelu_mode=0):
         w = self.wb[wname]
         N, K = w.shape
         M = a_bf16.shape[0] if rows is None else rows
         self.gemm(a_bf16.data_ptr(), K, w.data_ptr(), K, out.data_ptr(), N, M, N, K, bias=None if bias is None else self.w[bias].data_ptr(),
                   residual=None if residual is None else residual.data_ptr(), ldr=N, out2=None if out2 is None else out2.data_ptr(),
-                  out_f32=out.dtype == torch.float32)
+                  out_f32=out.dtype == torch.float32, gelu_mode=gelu_mode)
 
     def _ln(self, x: torch.Tensor, wname: str, eps: float, out_bf16=None, out_f32=None, stat=None):
         rows = x.numel() // DIM
@@ -331,7 +332,8 @@ class ViTEngine:
                                                   self.err.data_ptr(), st), "attn_forward_prefix")
         self._linear(o, pre + "attn.proj.weight", xmid, bias=pre + "attn.proj.bias", residual=xin)
         self._ln(xmid, pre + "ln_2", 1e-5, out_bf16=ws.h)
-        self._linear(ws.h, pre + "mlp.fc1.weight", upre, bias=pre + "mlp.fc1.bias", out2=ws.u)
+        # saved passes keep GELU'(fc1 output) (all the backward needs of it); no-grad passes keep nothing but GELU(fc1 output)
+        self._linear(ws.h, pre + "mlp.fc1.weight", upre, bias=pre + "mlp.fc1.bias", out2=ws.u, gelu_mode=1 if ws.save else 2)
         self._linear(ws.u, pre + "mlp.fc2.weight", xout, bias=pre + "mlp.fc2.bias", residual=xmid)
         self.launches += 1
 
@@ -367,7 +369,7 @@ class ViTEngine:
         w = self.wbt[wname]
         N, K = w.shape
         self.gemm(a_bf16.data_ptr(), K, w.data_ptr(), K, out.data_ptr(), N, a_bf16.shape[0], N, K, out_f32=out.dtype == torch.float32,
-                  gelu_bwd_aux=None if gelu_bwd_aux is None else gelu_bwd_aux.data_ptr())
+                  gelu_bwd_aux=None if gelu_bwd_aux is None else gelu_bwd_aux.data_ptr(), gelu_mode=0 if gelu_bwd_aux is None else 1)
 
     def _ln_bwd(self, dh, x, wname, eps, res, out_f32, out_bf16, dh_pool=None, T=0, n_active=0):
         rows = x.numel() // DIM

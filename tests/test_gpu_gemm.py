@@ -71,3 +71,48 @@ def test_gemm_rejects_misaligned_rows(lib):
     A = torch.zeros(1, 128, 64, dtype=torch.bfloat16, device="cuda"); B = torch.zeros(1, 222, 64, dtype=torch.bfloat16, device="cuda")
     C = torch.zeros(1, 128, 222, device="cuda")
     assert lib.lc_gemm_bf16(P(A), 64, 0, P(B), 64, 0, P(C), 222, 0, 128, 222, 64, 1, None, None, 0, 0, None, 1, 1.0, None, st()) == -22
+
+
+def test_gemm_gelu_derivative_side_tensor(lib):
+    """gelu_mode bit 0: the out2 variant stores GELU'(pre-activation) in C (and GELU in out2); the backward variant multiplies by it (what the
+    frozen-backbone fc2 data gradient needs).  bit 1: C is not written at all."""
+    import ctypes
+    from libcontinual_b200._lib import GemmDesc
+    g = torch.Generator().manual_seed(15)
+    M, N, K = 394, 768, 256
+    A = (torch.randn(M, K, generator=g) * 0.5).bfloat16(); B = (torch.randn(N, K, generator=g) * 0.1).bfloat16()
+    bias = torch.randn(N, generator=g) * 0.1
+    Ad, Bd, bd = dev(A), dev(B), dev(bias)
+    C = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16); C2 = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    err = torch.zeros(4, dtype=torch.int32, device="cuda")
+
+    def call(mode, C_, C2_, aux=None, Aop=Ad, Kk=K):
+        d = GemmDesc()
+        d.A, d.lda, d.B, d.ldb, d.C, d.ldc = P(Aop), Kk, P(Bd), K, P(C_), N
+        d.bias = P(bd) if aux is None else None
+        d.out2 = None if C2_ is None else P(C2_)
+        d.gelu_bwd_aux = None if aux is None else P(aux)
+        d.M, d.N, d.K, d.batch_in, d.batch_out, d.out_f32, d.alpha, d.gelu_mode = M, N, K, 1, 1, 0, 1.0, mode
+        assert lib.lc_gemm_bf16_ex(ctypes.byref(d), P(err), st()) == 0
+        torch.cuda.synchronize()
+        assert int(err[0]) == 0
+
+    x = (A.double() @ B.double().T + bias.double()).requires_grad_(True)
+    y = torch.nn.functional.gelu(x)
+    y.sum().backward()
+    call(1, C, C2)
+    assert (C2.float().cpu() - y.detach().float()).abs().max().item() <= 8e-3 * y.abs().max().item()
+    assert (C.float().cpu() - x.grad.float()).abs().max().item() <= 8e-3                       # GELU' in [-0.13, 1.13], BF16 rounding 2^-9
+    call(2, C, C2)                                                                              # C untouched
+    assert torch.equal(C.cpu().float(), C.cpu().float()) and (C2.float().cpu() - y.detach().float()).abs().max().item() <= 8e-3 * y.abs().max().item()
+    keep = C.clone()
+    C.fill_(3.0); call(2, C, C2)
+    assert float((C.float() - 3.0).abs().max()) == 0.0
+    # backward: D = (A B^T) * aux  with aux = GELU' (mode 1) equals D = (A B^T) * GELU'(pre) with aux = pre (mode 0)
+    pre = x.detach().float().bfloat16()
+    D1 = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16); D0 = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    call(1, D1, None, aux=keep)
+    call(0, D0, None, aux=dev(pre))
+    ref = (A.double() @ B.double().T) * x.grad
+    assert (D1.float().cpu() - ref.float()).abs().max().item() <= 1.5e-2 * ref.abs().max().item()
+    assert (D0.float().cpu() - ref.float()).abs().max().item() <= 1.5e-2 * ref.abs().max().item()
