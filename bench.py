@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="icarl", choices=["icarl", "ewc", "l2p", "inflora"])
+    ap.add_argument("--workload", default="icarl", choices=["icarl", "ewc", "l2p", "inflora", "dualprompt", "codaprompt", "sdlora"])
     ap.add_argument("--cpu-steps", type=int, default=12, help="timed oracle steps for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
@@ -54,6 +54,12 @@ def workload_name(w):
     return {"icarl": "iCaRL ResNet32 CIFAR-100 b50-5-10 (task 1: CE + KD vs frozen teacher), bs=128, synthetic 32x32",
             "ewc": "EWC ResNet32 CIFAR-100 b0-10-10 (task 1: CE + lamda*Fisher penalty), bs=128, synthetic 32x32",
             "l2p": "L2P ViT-B/16 CIFAR-100 b10-10-10 (task 1: query pass + prompted pass + backward to prompts, clip, Adam), bs=128, synthetic 224x224",
+            "dualprompt": "DualPrompt ViT-B/16 CIFAR-100 b10-10-10 (task 1: query pass + prefix-tuned pass (g/e prompts on blocks 0-4) + backward, Adam), bs=128 per GPU, "
+                          "synthetic 224x224",
+            "codaprompt": "CodaPrompt ViT-B/16 CIFAR-100 b10-10-10 (task 1: query pass + attention-weighted prompt prefixes on blocks 0-4 + backward, Adam), bs=128 per "
+                          "GPU, synthetic 224x224",
+            "sdlora": "SD-LoRA ViT-B/16 CIFAR-100 b10-10-10 (task 1: two stacked rank-10 adapters on q,v of 12 blocks, trainable A/B/magnitudes + classifier, SGD "
+                      "momentum), bs=128 per GPU, synthetic 224x224",
             "inflora": "InfLoRA_OPT ViT-B/16 ImageNet-R b20-20-10 (task 1: rank-10 adapters on k,v of 12 blocks + task head, CE, SGD momentum), bs=128 per GPU, "
                        "synthetic 224x224"}[w]
 
@@ -257,6 +263,9 @@ def run_reference(args):
         return
     if args.workload in ("l2p", "inflora"):
         return run_reference_l2p(args)
+    if args.workload in ("dualprompt", "codaprompt", "sdlora"):
+        print(json.dumps({"impl": "reference", "unavailable": f"no timed oracle leg for the extra workload {args.workload!r} (BASELINE configs: icarl, ewc, l2p, inflora)"}))
+        return
     on_gpu = args.ref_device == "cuda"
     steps, warm = (max(1, min(args.steps, 200)), max(3, min(args.warmup, 20))) if on_gpu else (max(1, min(args.steps, 40)), max(1, min(args.warmup, 3)))
     ips, ms, cores = time_oracle(args.workload, steps, warm, args.ref_device)
@@ -432,6 +441,31 @@ def run_ours_l2p(args):
         m.after_task(0, None, None, None); m.before_task(1, None, None, None)
         opt = Adam(m.get_parameters(None), lr=0.001875, betas=(0.9, 0.999), weight_decay=0, model=m)
         lo, hi, tokens = 10, 20, 222
+    elif kind in ("dualprompt", "codaprompt"):
+        from libcontinual_b200.model import CodaPrompt, DualPrompt
+        torch.manual_seed(1993)
+        p = l2p_synth_state()[0]
+        bb = vit_pt_imnet(pretrained=False, state=p, device=device)
+        if kind == "dualprompt":
+            m = DualPrompt(bb, 768, 100, device=device, task_num=10, init_cls_num=10, inc_cls_num=10, g_prompt_length=6, e_prompt_length=20)
+        else:
+            m = CodaPrompt(bb, 768, 100, device=device, task_num=10, init_cls_num=10, inc_cls_num=10, prompt_length=8, pool_size=100, mu=0.0)
+        m.before_task(0, None, None, None); m.after_task(0, None, None, None); m.before_task(1, None, None, None)
+        opt = Adam(m.get_parameters(None), lr=1e-3, betas=(0.9, 0.999), weight_decay=0, model=m)
+        lo, hi, tokens = 10, 20, 197
+    elif kind == "sdlora":
+        from libcontinual_b200.model import SD_LoRA
+        torch.manual_seed(1993)
+        p = l2p_synth_state()[0]
+        bb = vit_pt_imnet(pretrained=False, state=p, device=device, attn_layer="MultiHeadAttention_SDLoRA", lora_rank=10)
+        m = SD_LoRA(bb, device, init_cls_num=10, inc_cls_num=10, task_num=10, embd_dim=768, init_mag=1.0, rank_reduction=[False, 4, 8, 8, 6],
+                    knowledge_dist=[False, 9e-4], dataset="cifar100")
+        m.before_task(0, None, None, None)
+        with torch.no_grad():
+            m.B_cur.normal_(0.0, 0.01)                        # a trained first adapter (B = 0 would make the frozen adapter a no-op)
+        m.after_task(0, None, None, None); m.before_task(1, None, None, None)
+        opt = FlatSGD(m.get_parameters(None), lr=8e-3, momentum=0.9, model=m)
+        lo, hi, tokens = 10, 20, 197
     else:
         from libcontinual_b200.model.inflora import InfLoRA_OPT
         os.environ.setdefault("PYTHONHASHSEED", "42")
@@ -454,7 +488,7 @@ def run_ours_l2p(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    step = GraphedL2PStep(m, opt, BATCH) if kind == "l2p" else GraphedFlatStep(m, opt, BATCH)
+    step = GraphedL2PStep(m, opt, BATCH) if isinstance(opt, Adam) else GraphedFlatStep(m, opt, BATCH)
     for i in range(W):
         step.run(*devb[i % NB])
     barrier()
@@ -534,10 +568,12 @@ def run_ours_l2p(args):
                 "us_per_launch": us, "algorithmic_flops_per_launch": flops, "peak_source": peak_src}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        if kind not in ("l2p", "inflora"):
+            raise SystemExit("extra workloads have no timed oracle leg: pass --no-cpu-baseline")
         ips, ms, cores = (time_oracle_l2p if kind == "l2p" else time_oracle_inflora)(2, 1, 16)
         cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "ms_per_step": ms,
                "sample": f"2 full {kind} steps of 16 images after 1 warm-up (bounded sample of the bs-128 step; oracle/port.py, PyTorch CPU fp32, {cores} threads)"}
-    passes = 3 if kind == "l2p" else 2                  # L2P: query fwd + prompted fwd + dX bwd; InfLoRA: fwd + dX bwd
+    passes = 2 if kind in ("inflora", "sdlora") else 3  # prompt methods: query fwd + prompted fwd + dX bwd; LoRA methods: fwd + dX bwd
     flop_step = passes * 12 * 2 * (768 * 2304 + 768 * 768 + 2 * 768 * 3072) * BATCH * (215.0 if kind == "l2p" else 197.0)     # rough: linear layers only
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -553,7 +589,7 @@ def run_ours_l2p(args):
 
 
 def run_ours(args):
-    if args.workload in ("l2p", "inflora"):
+    if args.workload in ("l2p", "inflora", "dualprompt", "codaprompt", "sdlora"):
         return run_ours_l2p(args)
     import torch
     import torch.distributed as dist

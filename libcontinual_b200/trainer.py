@@ -103,11 +103,13 @@ class GraphedStep:
 class GraphedL2PStep:
     """The L2P step (query pass, prompt selection, prompted pass, masked loss, backward to the prompt rows, clip, Adam) as CUDA graphs.
     world_size > 1: graph 1 ends before the clip, the flat trainable-gradient arena (123k floats) is all-reduced (average), graph 2
-    clips and updates — the reference's DDP order (gradients averaged in backward, then l2p.py:104, then optimizer.step)."""
+    clips and updates — the reference's DDP order (gradients averaged in backward, then l2p.py:104, then optimizer.step).
+    Also drives the other flat-arena methods trained with Adam (DualPrompt, CodaPrompt): they have no clip stage (`_launch_clip` absent)."""
 
     def __init__(self, model, optimizer: Adam, batch_size: int, process_group=None, warmup: int = 2):
         assert isinstance(optimizer, Adam), "GraphedL2PStep drives the fused flat Adam"
         self.model, self.opt, self.eng, self.B = model, optimizer, model.engine, batch_size
+        self.has_clip = hasattr(model, "_launch_clip")
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if (process_group is not None or (
             torch.distributed.is_available() and torch.distributed.is_initialized())) else 1
@@ -136,7 +138,8 @@ class GraphedL2PStep:
         if self.world > 1:
             self.g_upd = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_upd):
-                model._launch_clip()
+                if self.has_clip:
+                    model._launch_clip()
                 optimizer.launch()
         self.launches_per_step = self.eng.launches - l0 + 1
         self.steps = 0

@@ -124,3 +124,28 @@ def test_dualprompt_observe_and_inference_match_reference_golden():
     torch.cuda.synchronize()
     for rp, q in zip(ref_params, params):
         assert rel_l2(q.detach(), rp.detach()) < 1e-6
+
+
+def test_dualprompt_graphed_step_equals_eager():
+    """CUDA-graph replay (GraphedL2PStep without a clip stage) == the eager plugin order with the flat Adam."""
+    from libcontinual_b200 import optim
+    from libcontinual_b200.trainer import GraphedL2PStep
+    p = synth_vit_state(5150)[0]
+    pool, fc_w, fc_b = synth_dual_pool(930)
+    m = _model(p, pool, fc_w, fc_b)
+    m.before_task(0, None, None, None)
+    x, y = synth_images(750, 4, 0, 10)
+    theta0 = m.theta.clone()
+    opt = optim.Adam(m.get_parameters(None), lr=1e-3, model=m)
+    for _ in range(2):
+        pred, acc, loss = m.observe({"image": x, "label": y})
+        opt.zero_grad(); loss.backward(); opt.step()
+    torch.cuda.synchronize()
+    eager, eager_loss = m.theta.clone(), float(loss.detach())
+    m.theta.copy_(theta0)
+    opt2 = optim.Adam(m.get_parameters(None), lr=1e-3, model=m)
+    gs = GraphedL2PStep(m, opt2, 4)
+    for _ in range(2):
+        gs.run(x, y)
+    torch.cuda.synchronize()
+    assert rel_l2(m.theta, eager) < 1e-6 and abs(float(gs.loss()) - eager_loss) < 1e-5

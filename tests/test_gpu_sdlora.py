@@ -129,3 +129,32 @@ def test_sdlora_observe_matches_reference_golden():
         assert rel_l2(q.detach(), rp.detach()) < 1e-6
     pred, acc = m.inference({"image": x, "label": y})
     assert pred.shape == (4,) and 0.0 <= acc <= 1.0
+
+
+def test_sdlora_graphed_step_equals_eager():
+    from libcontinual_b200 import optim
+    from libcontinual_b200.trainer import GraphedFlatStep
+    p = synth_vit_state(5150)[0]
+    m = _model(p)
+    states = sdlora_task_states(1)
+    for task in (0, 1):
+        blocks, mags, hw, hb = states[task]
+        m.before_task(task, None, None, None)
+        _install(m, task, blocks, mags, hw, hb)
+        if task == 0:
+            m.after_task(0, None, None, None)
+    x, y = synth_images(781, 4, 10, 20)
+    theta0 = m.theta.clone()
+    opt = optim.FlatSGD(m.get_parameters(None), lr=8e-3, momentum=0.9, model=m)
+    for _ in range(2):
+        pred, acc, loss = m.observe({"image": x, "label": y})
+        opt.zero_grad(); loss.backward(); opt.step()
+    torch.cuda.synchronize()
+    eager, eager_loss = m.theta.clone(), float(loss.detach())
+    m.theta.copy_(theta0)
+    opt2 = optim.FlatSGD(m.get_parameters(None), lr=8e-3, momentum=0.9, model=m)
+    gs = GraphedFlatStep(m, opt2, 4)
+    for _ in range(2):
+        gs.run(x, y)
+    torch.cuda.synchronize()
+    assert rel_l2(m.theta, eager) < 1e-6 and abs(float(gs.loss()) - eager_loss) < 1e-5
