@@ -246,44 +246,49 @@ class InfLoRA_OPT(nn.Module):
 
     @torch.no_grad()
     def _update_feature(self, task_idx, train_loader):
-        """DualGPM bookkeeping of InfLoRA_opt.py:278-362 (host side, once per task): keep per block either a basis of the subspace used
-        so far ('remove') or of its complement ('retain'), grown / shrunk so that the captured input-matrix energy crosses `threshold`."""
         acts = self.input_matrices(train_loader).cpu().numpy()
-        threshold = (self.lame - self.lamb) * task_idx / self.task_num + self.lamb
-        for i in range(self.engine.depth):
-            act = acts[i]
-            if task_idx == 0:
-                U, S, _ = np.linalg.svd(act, full_matrices=False)
-                ratio = S ** 2 / (S ** 2).sum()
-                r = max(int(np.sum(np.cumsum(ratio) < threshold)), 1)
-                assert r < act.shape[0] / 2
-                self.feature_list.append(U[:, :r])
-                self.project_type.append("remove")
-                continue
-            total = (np.linalg.svd(act, compute_uv=False) ** 2).sum()
-            F_i = self.feature_list[i]
-            inside = (F_i @ F_i.T).astype(np.float32) @ act
-            if self.project_type[i] == "remove":
-                U, S, _ = np.linalg.svd(act - inside, full_matrices=False)
-                ratio = S ** 2 / total
-                kept = (total - (S ** 2).sum()) / total
-                if kept < threshold:
-                    r = int(np.sum(np.cumsum(ratio) + kept < threshold)) + 1
-                    grown = np.hstack((F_i, U[:, :r]))
-                    self.feature_list[i] = grown[:, :min(grown.shape)]
-            else:
-                U, S, _ = np.linalg.svd(inside, full_matrices=False)
-                ratio = S ** 2 / total
-                kept = (S ** 2).sum() / total
-                if kept >= 1 - threshold:
-                    r = int(np.sum(kept - np.cumsum(ratio) >= 1 - threshold)) + 1
-                    shrunk = F_i - U[:, :r] @ U[:, :r].T @ F_i
-                    U2, _, _ = np.linalg.svd(shrunk)
-                    self.feature_list[i] = U2[:, :F_i.shape[1] - r]
-        for i, F_i in enumerate(self.feature_list):
-            if self.project_type[i] == "remove" and F_i.shape[1] > F_i.shape[0] / 2:
-                U, _, _ = np.linalg.svd(F_i)
-                self.feature_list[i] = U[:, F_i.shape[1]:]
-                self.project_type[i] = "retain"
-            elif self.project_type[i] == "retain":
-                assert F_i.shape[1] <= F_i.shape[0] / 2
+        dualgpm_update(acts, self.feature_list, self.project_type, task_idx, self.task_num, self.lame, self.lamb)
+
+
+def dualgpm_update(acts, feature_list: List[np.ndarray], project_type: List[str], task_idx: int, task_num: int, lame: float, lamb: float):
+    """DualGPM bookkeeping of InfLoRA_opt.py:278-362 (host side, once per task; in place on the two lists): per block keep either a basis of the
+    input subspace used so far ('remove') or of its complement ('retain'), grown / shrunk so that the captured input-matrix energy crosses
+    `threshold`; a 'remove' basis that outgrows half the dimension is swapped for its orthogonal complement.  `acts`: [L, D, D] input matrices."""
+    threshold = (lame - lamb) * task_idx / task_num + lamb
+    for i in range(acts.shape[0]):
+        act = acts[i]
+        if task_idx == 0:
+            U, S, _ = np.linalg.svd(act, full_matrices=False)
+            ratio = S ** 2 / (S ** 2).sum()
+            r = max(int(np.sum(np.cumsum(ratio) < threshold)), 1)
+            assert r < act.shape[0] / 2
+            feature_list.append(U[:, :r])
+            project_type.append("remove")
+            continue
+        total = (np.linalg.svd(act, compute_uv=False) ** 2).sum()
+        F_i = feature_list[i]
+        inside = (F_i @ F_i.T).astype(np.float32) @ act
+        if project_type[i] == "remove":
+            U, S, _ = np.linalg.svd(act - inside, full_matrices=False)
+            ratio = S ** 2 / total
+            kept = (total - (S ** 2).sum()) / total
+            if kept < threshold:
+                r = int(np.sum(np.cumsum(ratio) + kept < threshold)) + 1
+                grown = np.hstack((F_i, U[:, :r]))
+                feature_list[i] = grown[:, :min(grown.shape)]
+        else:
+            U, S, _ = np.linalg.svd(inside, full_matrices=False)
+            ratio = S ** 2 / total
+            kept = (S ** 2).sum() / total
+            if kept >= 1 - threshold:
+                r = int(np.sum(kept - np.cumsum(ratio) >= 1 - threshold)) + 1
+                shrunk = F_i - U[:, :r] @ U[:, :r].T @ F_i
+                U2, _, _ = np.linalg.svd(shrunk)
+                feature_list[i] = U2[:, :F_i.shape[1] - r]
+    for i, F_i in enumerate(feature_list):
+        if project_type[i] == "remove" and F_i.shape[1] > F_i.shape[0] / 2:
+            U, _, _ = np.linalg.svd(F_i)
+            feature_list[i] = U[:, F_i.shape[1]:]
+            project_type[i] = "retain"
+        elif project_type[i] == "retain":
+            assert F_i.shape[1] <= F_i.shape[0] / 2

@@ -866,6 +866,59 @@ def golden_sdlora(core):
     np.savez_compressed(os.path.join(OUT, "sdlora_vit.npz"), **out)
 
 
+def synth_input_matrices(seed: int, L: int = 12, D: int = 768, decay: float = 0.955):
+    """Synthetic PSD input matrices with a geometric spectrum and random eigenvectors (one per block), reproducible from the seed."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for l in range(L):
+        Q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+        ev = (decay + 0.002 * l) ** np.arange(D)
+        out.append(((Q * ev) @ Q.T).astype(np.float32))
+    return np.stack(out)
+
+
+def golden_dualgpm(core):
+    """The real `InfLoRA_OPT._update_feature` (InfLoRA_opt.py:278-362) on preset input matrices (an empty loader leaves `cur_matrix` as given), four
+    tasks in a row with thresholds that exercise growth, the 'remove' -> 'retain' swap and the 'retain' shrink; recorded: basis sizes, types and a
+    random projection of each projector F F^T."""
+    from core.model.backbone.vit import vit_pt_imnet
+    from core.model.InfLoRA_opt import InfLoRA_OPT as RefInfLoRA
+    from core.utils import init_seed
+    print("DualGPM feature update: reference vs libcontinual_b200.model.inflora.dualgpm_update")
+    sys.path.insert(0, os.path.dirname(HERE))
+    from libcontinual_b200.model.inflora import dualgpm_update
+    init_seed(42, True)
+    bb = vit_pt_imnet(pretrained=False, attn_layer="MultiHeadAttention_LoRA", lora_rank=10)
+    # lamb / lame chosen so that the captured subspace passes half the dimension at task 1 (swap to 'retain') and is shrunk at task 2
+    ref = RefInfLoRA(bb, torch.device("cpu"), init_cls_num=20, inc_cls_num=20, task_num=4, lame=0.9999, lamb=0.999, embd_dim=768, use_ca=False,
+                     dataset="imagenet-r")
+    proj = np.random.default_rng(7).standard_normal((768, 4)).astype(np.float32)
+    mine_f, mine_t = [], []
+    out = {}
+    for task in range(4):
+        acts = synth_input_matrices(1200 + task)
+        for i, mod in enumerate(ref.attention_modules):
+            mod.cur_matrix = torch.from_numpy(acts[i].copy()); mod.n_cur_matrix = 1
+        try:
+            ref._update_feature(task, [], None)
+        except TypeError as e:
+            # the 'retain' shrink branch (InfLoRA_opt.py:343-351) mixes a torch Tensor with numpy arrays and raises under numpy 2 / torch 2.11
+            # (it is written for numpy 1.x / torch 2.0.1): no reference output to pin there; ours must still run
+            print(f"   task {task}: reference raises {type(e).__name__} in the 'retain' branch -> not pinned ({e})")
+            dualgpm_update(acts, mine_f, mine_t, task, 4, 0.9999, 0.999)
+            out["unpinned_from_task"] = np.int64(task)
+            break
+        dualgpm_update(acts, mine_f, mine_t, task, 4, 0.9999, 0.999)
+        sizes = np.array([f.shape[1] for f in ref.feature_list])
+        print(f"   task {task}: sizes {sizes.tolist()} types {sorted(set(ref.project_type))}")
+        assert [f.shape[1] for f in mine_f] == sizes.tolist() and mine_t == ref.project_type, (task, [f.shape[1] for f in mine_f], sizes.tolist(), mine_t)
+        P_ref = np.stack([(f @ (f.T @ proj)) for f in ref.feature_list])
+        P_mine = np.stack([(f @ (f.T @ proj)) for f in mine_f])
+        close(P_mine, P_ref, 1e-3, 1e-3, f"dualgpm task{task} projectors")
+        out[f"t{task}/sizes"] = sizes; out[f"t{task}/types"] = np.array([t == "retain" for t in ref.project_type]); out[f"t{task}/P"] = P_ref.astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "dualgpm.npz"), **out)
+
+
 def main():
     torch.set_num_threads(8)
     os.makedirs(OUT, exist_ok=True)
@@ -886,6 +939,7 @@ def main():
     golden_dualprompt(core)
     golden_codaprompt(core)
     golden_sdlora(core)
+    golden_dualgpm(core)
     print("golden vectors written to", OUT)
 
 

@@ -154,3 +154,14 @@ def sdlora_task_states(upto):
         prev = blocks
         states.append((blocks, mags, hw, hb))
     return states
+
+
+def synth_input_matrices(seed, L=12, D=768, decay=0.955):
+    """Same draws as oracle/make_golden.py::synth_input_matrices."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for l in range(L):
+        Q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+        ev = (decay + 0.002 * l) ** np.arange(D)
+        out.append(((Q * ev) @ Q.T).astype(np.float32))
+    return np.stack(out)
