@@ -1,0 +1,103 @@
+"""Final average accuracy of a short synthetic class-incremental stream (EWC, cifar_resnet32, 2 tasks x 10 classes, bs 32, SGD 0.1/0.9/5e-4, lamda 1000:
+config/ewc.yaml with BASELINE config C1's overrides) on the CUDA path (precision 'tc' and 'fp32') next to the CPU oracle, from identical initial
+weights and identical batches.  The data have learnable structure: image = amp * template[class] + N(0, 1) noise.
+A reporting utility: with lr 0.1 / lamda 1000 such short streams are chaotic (the oracle's own result moves by +-15 pp between data seeds), so one
+run cannot establish the +-0.3 pp accuracy parity of BASELINE.json; that needs the real datasets and full-length schedules.
+
+    python tools/accuracy_parity.py [steps_per_task] [n_test_per_task]   -> one JSON line
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+
+def make_stream(seed, steps, n_test, bs=32, n_tasks=2, cpt=10, amp=1.0):
+    rng = np.random.default_rng(seed)
+    templ = rng.standard_normal((n_tasks * cpt, 3, 32, 32)).astype(np.float32)
+
+    def draw(n, lo, hi):
+        y = rng.integers(lo, hi, (n,))
+        x = amp * templ[y] + rng.standard_normal((n, 3, 32, 32)).astype(np.float32)
+        return torch.from_numpy(x), torch.from_numpy(y.astype(np.int64))
+    train = [[draw(bs, t * cpt, (t + 1) * cpt) for _ in range(steps)] for t in range(n_tasks)]
+    test = [draw(n_test, t * cpt, (t + 1) * cpt) for t in range(n_tasks)]
+    return train, test
+
+
+def run_ours(p, b, fc_w, fc_b, train, test, precision):
+    import libcontinual_b200.model as M
+    from libcontinual_b200.optim import SGD
+    bb = M.cifar_resnet32(max_batch=256, precision=precision)
+    bb.load_state_dict({**p, **b}, strict=True)
+    m = M.EWC(bb, 64, 100, device=torch.device("cuda"), init_cls_num=10, inc_cls_num=10, lamda=1000.0)
+
+    class Loader(list):
+        batch_size = 32
+    for t, batches in enumerate(train):
+        m.before_task(t, None, None, None)
+        n = 10 * (t + 1)
+        w, bias = m.engine.fc_views(n)
+        w[10 * t:].copy_(fc_w[10 * t:n].cuda()); bias[10 * t:].copy_(fc_b[10 * t:n].cuda())
+        m.train()
+        opt = SGD(m.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4, engine=m.engine)
+        for x, y in batches:
+            pred, acc, loss = m.observe({"image": x, "label": y})
+            opt.zero_grad(); loss.backward(); opt.step()
+        m.after_task(t, None, Loader([{"image": x, "label": y} for x, y in batches]), None)
+    m.eval()
+    accs = []
+    for x, y in test:
+        ok = 0
+        for i in range(0, x.shape[0], 250):
+            _, a = m.inference({"image": x[i:i + 250], "label": y[i:i + 250]})
+            ok += a * min(250, x.shape[0] - i)
+        accs.append(ok / x.shape[0])
+    return accs
+
+
+def run_oracle(p, b, fc_w, fc_b, train, test):
+    from oracle import port
+    torch.set_num_threads(os.cpu_count() or 1)
+    orc = port.ResNetMethodOracle("ewc", p, b, fc_w[:10], fc_b[:10], init_cls=10, inc_cls=10, lamda=1000.0)
+    for t, batches in enumerate(train):
+        if t > 0:
+            orc.task_idx = t
+            orc.grow_head(fc_w[:10 * (t + 1)], fc_b[:10 * (t + 1)]); orc.reset_optimizer()
+        for x, y in batches:
+            orc.step(x, y)
+        orc.ewc_after_task(batches, 32)
+    accs = []
+    with torch.no_grad():
+        for x, y in test:
+            pred = torch.cat([orc.logits(x[i:i + 500], False).argmax(1) for i in range(0, x.shape[0], 500)])
+            accs.append(float((pred == y).float().mean()))
+    return accs
+
+
+def main():
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+    n_test = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+    from oracle import port
+    rng = np.random.default_rng(77)
+    p, b = port.cifar_resnet_init(rng)
+    bound = 1.0 / 8.0
+    fc_w = torch.from_numpy(rng.uniform(-bound, bound, (20, 64)).astype(np.float32))
+    fc_b = torch.from_numpy(rng.uniform(-bound, bound, (20,)).astype(np.float32))
+    train, test = make_stream(5, steps, n_test)
+    res = {"stream": f"EWC cifar_resnet32, 2 tasks x 10 classes, {steps} steps/task, bs 32, test {n_test}/task (synthetic templates + noise)"}
+    for name, fn in (("cuda_tc", lambda: run_ours(p, b, fc_w, fc_b, train, test, "tc")), ("cuda_fp32", lambda: run_ours(p, b, fc_w, fc_b, train, test, "fp32")),
+                     ("oracle_cpu_fp32", lambda: run_oracle(p, b, fc_w, fc_b, train, test))):
+        accs = fn()
+        res[name] = {"per_task_acc": [round(100 * a, 2) for a in accs], "avg_acc": round(100 * float(np.mean(accs)), 2)}
+    res["delta_pp_tc_vs_oracle"] = round(res["cuda_tc"]["avg_acc"] - res["oracle_cpu_fp32"]["avg_acc"], 2)
+    res["delta_pp_fp32_vs_oracle"] = round(res["cuda_fp32"]["avg_acc"] - res["oracle_cpu_fp32"]["avg_acc"], 2)
+    print(json.dumps(res))
+    return res
+
+
+if __name__ == "__main__":
+    main()
