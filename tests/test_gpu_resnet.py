@@ -452,24 +452,3 @@ def test_icarl_after_task_herding_and_ncm_vs_oracle():
     clear = (top2[:, 1] - top2[:, 0]) > 1e-6 * top2[:, 0]
     assert torch.equal(pred.cpu()[clear], port.ncm_classify(fo, mo)[clear])
     assert int(pred.min()) >= 0 and int(pred.max()) < 4
-
-
-def test_ewc_two_task_stream_end_to_end_learns_like_the_oracle():
-    """End-to-end plugin flow over a 2-task stream (before_task -> observe/backward/step x N -> after_task with the Fisher pass -> inference) on a
-    learnable synthetic stream (tools/accuracy_parity.py), CUDA path (tensor-core and exact modes) vs the CPU oracle from identical weights and batches.
-    This is a sanity check, NOT the +-0.3 pp accuracy-parity claim of BASELINE.json: with lr 0.1 / lamda 1000 short streams are chaotic (the ORACLE's
-    own final accuracy moves by +-15 pp between data seeds), so only 'all three learn, and land in the same regime' is asserted."""
-    import importlib.util
-    import os
-    import sys
-    spec = importlib.util.spec_from_file_location("accuracy_parity", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "accuracy_parity.py"))
-    ap = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(ap)
-    argv, sys.argv = sys.argv, ["accuracy_parity.py", "40", "300"]
-    try:
-        res = ap.main()
-    finally:
-        sys.argv = argv
-    for k in ("cuda_tc", "cuda_fp32", "oracle_cpu_fp32"):
-        assert res[k]["avg_acc"] > 12.0, res                                # chance = 5 %
-    assert abs(res["delta_pp_tc_vs_oracle"]) <= 20.0 and abs(res["delta_pp_fp32_vs_oracle"]) <= 20.0, res
