@@ -187,6 +187,34 @@ class SDLoraState(LoraState):
         self.dmag.zero_()
 
 
+class StackedLoraState(LoraState):
+    """`Attention_LoRA` of vit_inflora.py:176-252 (InfLoRA, original): one rank-r adapter per task on k and v, the forward adds the SUM of the adapters
+    of tasks 0..t (`weight_k = sum_t B_t A_t`, :236-240); only the current task's lora_B trains.  The merge sees all of them stacked along the rank
+    axis (R = r (t + 1)), the gradient path only the current one (exactly InfLoRA_OPT's)."""
+
+    def __init__(self, engine: "ViTEngine", rank: int, nad: int, B_cur: torch.Tensor, dB_cur: torch.Tensor, A_old=None, B_old=None):
+        super().__init__(engine, (1, 2), rank, B_cur, dB_cur)
+        L, dev = engine.depth, engine.dev
+        self.nad, self.R = nad, rank * nad
+        assert self.R <= 128, "at most 128 stacked adapter ranks"
+        self.B_cur = B_cur
+        self.A_stack = torch.zeros(L, 2, self.R, DIM, device=dev)
+        self.B_stack = torch.zeros(L, 2, DIM, self.R, device=dev)
+        if nad > 1:
+            self.A_stack[:, :, :rank * (nad - 1)].copy_(A_old); self.B_stack[:, :, :, :rank * (nad - 1)].copy_(B_old)
+        self.cur = slice(rank * (nad - 1), self.R)
+        self.A_small = self.A                                   # [L, 2, r, D]: the current adapter (gradient path)
+        self.A, self.B = self.A_stack, self.B_stack             # what lc_lora_merge reads
+
+    def set_A(self, A: torch.Tensor):
+        self.A_small.copy_(A.reshape(self.A_small.shape))
+        self.A_stack[:, :, self.cur].copy_(self.A_small)
+        self.engine._cast(self.A_small.reshape(self.A_bf.shape), self.A_bf)
+
+    def sync(self):
+        self.B_stack[:, :, :, self.cur].copy_(self.B_cur)
+
+
 class ViTEngine:
     def __init__(self, depth: int = 12, device=None):
         self.lib = _lib.load()
@@ -202,6 +230,9 @@ class ViTEngine:
         self._ws: Dict[tuple, _Workspace] = {}
         self.launches = 0
         self.lora: Optional[LoraState] = None
+        # LayerNorm eps inside the blocks: 1e-5 in transformer.py's ResidualAttentionBlock (:1289,1315), 1e-6 in vit_inflora.py's timm-style Block; the
+        # final norm is 1e-6 in both
+        self.block_ln_eps = 1e-5
         self.cov: Optional[torch.Tensor] = None       # [L, 768, 768] running sums of h^T h while an input-matrix pass is on (see input_matrix_begin)
         self.cov_rows = 0
 
@@ -316,7 +347,7 @@ class ViTEngine:
         xout = ws.x[i + 1] if ws.save else ws.x[(i + 1) % 2]
         xmid, qkv, o, upre = ws.xmid[k], ws.qkv[k], ws.o[k], ws.upre[k]
         h1 = ws.hs[i] if ws.hs is not None else ws.h
-        self._ln(xin, pre + "ln_1", 1e-5, out_bf16=h1)
+        self._ln(xin, pre + "ln_1", self.block_ln_eps, out_bf16=h1)
         if self.cov is not None:
             self._accumulate_input_matrix(i, ws)
         if self.lora is not None and self.lora.active and ws.save:
@@ -331,7 +362,7 @@ class ViTEngine:
             check(self.lib.lc_attn_forward_prefix(qkv.data_ptr(), o.data_ptr(), ws.lse[k].data_ptr(), B, T, HEADS, pk.data_ptr(), pv.data_ptr(), pk.shape[1],
                                                   self.err.data_ptr(), st), "attn_forward_prefix")
         self._linear(o, pre + "attn.proj.weight", xmid, bias=pre + "attn.proj.bias", residual=xin)
-        self._ln(xmid, pre + "ln_2", 1e-5, out_bf16=ws.h)
+        self._ln(xmid, pre + "ln_2", self.block_ln_eps, out_bf16=ws.h)
         # saved passes keep GELU'(fc1 output) (all the backward needs of it); no-grad passes keep nothing but GELU(fc1 output)
         self._linear(ws.h, pre + "mlp.fc1.weight", upre, bias=pre + "mlp.fc1.bias", out2=ws.u, gelu_mode=1 if ws.save else 2)
         self._linear(ws.u, pre + "mlp.fc2.weight", xout, bias=pre + "mlp.fc2.bias", residual=xmid)
@@ -394,7 +425,7 @@ class ViTEngine:
             # MLP branch: x_out = x_mid + fc2(GELU(fc1(LN2(x_mid))))
             self._linear_t(gbf, pre + "mlp.fc2.weight", dU, gelu_bwd_aux=ws.upre[i])
             self._linear_t(dU, pre + "mlp.fc1.weight", dh)
-            self._ln_bwd(dh, ws.xmid[i], pre + "ln_2", 1e-5, g, g2, gbf)
+            self._ln_bwd(dh, ws.xmid[i], pre + "ln_2", self.block_ln_eps, g, g2, gbf)
             # attention branch: x_mid = x_in + proj(softmax(QK^T/8) V)
             self._linear_t(gbf, pre + "attn.proj.weight", dO)
             pfx = None if getattr(ws, "prefix", None) is None else ws.prefix.get(i)
@@ -412,7 +443,7 @@ class ViTEngine:
             if i == 0 and not to_tokens:          # nothing trainable below the first attention (adapters only): stop here
                 return None
             self._linear_t(dqkv, pre + "attn.qkv.weight", dh)
-            self._ln_bwd(dh, ws.x[i], pre + "ln_1", 1e-5, g2, g, gbf)
+            self._ln_bwd(dh, ws.x[i], pre + "ln_1", self.block_ln_eps, g2, g, gbf)
         return g
 
     # ---- InfLoRA's input matrix (transformer.py:242-244, InfLoRA_opt.py:243-245) ----------------------

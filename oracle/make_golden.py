@@ -919,6 +919,132 @@ def golden_dualgpm(core):
     np.savez_compressed(os.path.join(OUT, "dualgpm.npz"), **out)
 
 
+def synth_timm_vit_state(seed: int):
+    """The synthetic ViT-B/16 weights of `port.vit_init` under timm's state-dict names (vit_inflora.py: blocks.{i}.norm1 / attn / norm2 / mlp)."""
+    p = port.vit_init(np.random.default_rng(seed))
+    out = {}
+    for k, v in p.items():
+        k = k.replace("transformer.blocks.", "blocks.").replace(".ln_1.", ".norm1.").replace(".ln_2.", ".norm2.")
+        out[k] = v
+    return p, out
+
+
+def synth_stacked_adapters(seed: int, n_tasks: int, depth: int = 12, rank: int = 10):
+    rng = np.random.default_rng(seed)
+    blocks = []
+    for _ in range(depth):
+        ads = []
+        for _ in range(n_tasks):
+            ads.append({"A_k": torch.from_numpy((rng.standard_normal((rank, 768)) / np.sqrt(768 * 3)).astype(np.float32)),
+                        "B_k": torch.from_numpy((0.05 * rng.standard_normal((768, rank))).astype(np.float32)),
+                        "A_v": torch.from_numpy((rng.standard_normal((rank, 768)) / np.sqrt(768 * 3)).astype(np.float32)),
+                        "B_v": torch.from_numpy((0.05 * rng.standard_normal((768, rank))).astype(np.float32))})
+        blocks.append(ads)
+    bound = 1.0 / np.sqrt(768)
+    hw = torch.from_numpy(rng.uniform(-bound, bound, (n_tasks, 10, 768)).astype(np.float32))
+    hb = torch.from_numpy(rng.uniform(-bound, bound, (n_tasks, 10)).astype(np.float32))
+    return blocks, hw, hb
+
+
+def golden_inflora_orig(core):
+    """The real `core.model.InfLoRA.InfLoRA` on the real `ViT_lora_co` (SiNet.py) encoder: observe() + backward on task 0 and task 1 (two stacked
+    adapters, only the second trains), the cur-matrix pass, and `update_DualGPM` on preset matrices.  `SiNet_vit.__init__` itself cannot run offline
+    (it builds the encoder through timm's pretrained-model factory): the object is assembled from the same parts (ViT_lora_co + the two head pools)."""
+    import torch.nn as nn
+    from core.model.backbone.SiNet import SiNet_vit, ViT_lora_co
+    from core.model.backbone.vit_inflora import Attention_LoRA
+    from core.model.InfLoRA import InfLoRA as RefInfLoRA
+    sys.path.insert(0, os.path.dirname(HERE))
+    from libcontinual_b200.model.inflora_orig import dualgpm_update_v1
+    print("InfLoRA (original) / timm-style ViT-B/16: reference observe() vs oracle")
+    out = {}
+    p, p_timm = synth_timm_vit_state(5150)
+    sn = SiNet_vit.__new__(SiNet_vit)
+    nn.Module.__init__(sn)
+    sn.image_encoder = ViT_lora_co(patch_size=16, embed_dim=768, depth=12, num_heads=12, n_tasks=10, rank=10)
+    sn.class_num = 10
+    sn.classifier_pool = nn.ModuleList([nn.Linear(768, 10, bias=True) for _ in range(10)])
+    sn.classifier_pool_backup = nn.ModuleList([nn.Linear(768, 10, bias=True) for _ in range(10)])
+    sn.numtask = 0
+    missing = sn.image_encoder.load_state_dict(p_timm, strict=False)
+    assert not [k for k in missing.missing_keys if "lora" not in k and "grow" not in k and "head" not in k], missing.missing_keys
+    ref = RefInfLoRA(sn, 768, 100, inc_cls_num=10, device=torch.device("cpu"), lame=1.0, lamb=0.6, total_sessions=10)
+    mods = [m for m in ref._network.modules() if isinstance(m, Attention_LoRA)]
+    blocks, hw, hb = synth_stacked_adapters(990, 2)
+    for task in (0, 1):
+        # before_task's bookkeeping (InfLoRA.py:112-138) without the loader pass
+        ref._known_classes = ref._total_classes
+        ref._cur_task += 1
+        ref._total_classes = ref._known_classes + ref.inc_cls_num
+        ref._network.update_fc(ref._total_classes)
+        for name, prm in ref._network.named_parameters():
+            prm.requires_grad_(any(f"{s}.{task}." in name for s in ("classifier_pool", "lora_B_k", "lora_B_v")))
+            prm.grad = None
+        with torch.no_grad():
+            for l, mod in enumerate(mods):
+                mod.lora_A_k[task].weight.copy_(blocks[l][task]["A_k"]); mod.lora_B_k[task].weight.copy_(blocks[l][task]["B_k"])
+                mod.lora_A_v[task].weight.copy_(blocks[l][task]["A_v"]); mod.lora_B_v[task].weight.copy_(blocks[l][task]["B_v"])
+            ref._network.classifier_pool[task].weight.copy_(hw[task]); ref._network.classifier_pool[task].bias.copy_(hb[task])
+        lo = 10 * task
+        x, y = synth_images(800 + task, 4, lo, lo + 10)
+        pred, acc, loss = ref.observe({"image": x, "label": y})
+        loss.backward()
+        ob_ = [[{k: v.clone().requires_grad_(i == task and k.startswith("B_")) for k, v in ad.items()} for i, ad in enumerate(blocks[l][:task + 1])] for l in range(12)]
+        ow = hw[task].clone().requires_grad_(True); obias = hb[task].clone().requires_grad_(True)
+        ologits = port.inflora_orig_logits(p, ob_, ow, obias, x)
+        oloss = F.cross_entropy(ologits, y - lo)
+        oloss.backward()
+        close(oloss, loss, 1e-5, 1e-6, f"inflora-orig task{task} loss")
+        dBk = torch.stack([m.lora_B_k[task].weight.grad for m in mods]); dBv = torch.stack([m.lora_B_v[task].weight.grad for m in mods])
+        close(torch.stack([ob_[l][task]["B_k"].grad for l in range(12)]), dBk, 1e-3, 1e-4 * float(dBk.abs().max()), f"inflora-orig task{task} dB_k")
+        close(torch.stack([ob_[l][task]["B_v"].grad for l in range(12)]), dBv, 1e-3, 1e-4 * float(dBv.abs().max()), f"inflora-orig task{task} dB_v")
+        head = ref._network.classifier_pool[task]
+        close(ow.grad, head.weight.grad, 1e-4, 2e-6, f"inflora-orig task{task} dW")
+        if task == 1:
+            assert mods[2].lora_B_k[0].weight.grad is None
+        with torch.no_grad():
+            out[f"t{task}/logits"] = ref._network(x)["logits"].numpy().copy()
+            out[f"t{task}/interface"] = ref._network.interface(x).numpy().copy()
+        out[f"t{task}/loss"] = np.float64(loss.item()); out[f"t{task}/pred"] = pred.numpy().copy()
+        out[f"t{task}/dB_k"] = dBk.numpy().copy(); out[f"t{task}/dB_v"] = dBv.numpy().copy()
+        out[f"t{task}/dW"] = head.weight.grad.numpy().copy(); out[f"t{task}/db"] = head.bias.grad.numpy().copy()
+        if task == 1:
+            # cur-matrix pass (two batches) with both adapters applied
+            xs = [synth_images(810 + j, 3, 0, 20)[0] for j in range(2)]
+            with torch.no_grad():
+                for xb in xs:
+                    ref._network(xb, get_cur_feat=True)
+            proj = torch.from_numpy(np.random.default_rng(99).standard_normal((768, 8)).astype(np.float32))
+            out["cov/proj"] = torch.stack([m.cur_matrix @ proj for m in mods]).numpy().copy()
+            out["cov/trace"] = np.array([float(m.cur_matrix.trace()) for m in mods])
+    # update_DualGPM on preset matrices: four sessions with lame = 1.0, lamb = 0.999 style thresholds as in golden_dualgpm
+    ref2 = RefInfLoRA.__new__(RefInfLoRA)
+    ref2.feature_list, ref2.project_type, ref2.lame, ref2.lamb, ref2.total_sessions = [], [], 0.9999, 0.999, 4
+    mine_f, mine_t = [], []
+    projn = np.random.default_rng(7).standard_normal((768, 4)).astype(np.float32)
+    layers = [0, 10, 11]
+    for task in range(4):
+        acts = synth_input_matrices(1200 + task)[layers]
+        ref2._cur_task = task
+        try:
+            ref2.update_DualGPM([a.copy() for a in acts])      # ndarrays: what np.linalg.svd returned for the tensors under the pinned numpy 1.x
+        except Exception as e:
+            print(f"   session {task}: reference raises {type(e).__name__}: {e} -> not pinned")
+            out["gpm/unpinned_from_task"] = np.int64(task)
+            break
+        dualgpm_update_v1(list(acts), mine_f, mine_t, task, 4, 0.9999, 0.999)
+        sizes = [f.shape[1] for f in ref2.feature_list]
+        print(f"   session {task}: sizes {sizes} types {ref2.project_type}")
+        assert [f.shape[1] for f in mine_f] == sizes and mine_t == ref2.project_type, (task, [f.shape[1] for f in mine_f], sizes, mine_t)
+        P_ref = np.stack([f @ (f.T @ projn) for f in ref2.feature_list]); P_mine = np.stack([f @ (f.T @ projn) for f in mine_f])
+        close(P_mine, P_ref, 1e-3, 1e-3, f"update_DualGPM session {task} projectors")
+        out[f"gpm/t{task}/sizes"] = np.array(sizes); out[f"gpm/t{task}/types"] = np.array([t == "retain" for t in ref2.project_type])
+        out[f"gpm/t{task}/P"] = P_ref.astype(np.float32)
+    else:
+        out["gpm/unpinned_from_task"] = np.int64(4)
+    np.savez_compressed(os.path.join(OUT, "inflora_orig_vit.npz"), **out)
+
+
 def main():
     torch.set_num_threads(8)
     os.makedirs(OUT, exist_ok=True)
@@ -940,6 +1066,7 @@ def main():
     golden_codaprompt(core)
     golden_sdlora(core)
     golden_dualgpm(core)
+    golden_inflora_orig(core)
     print("golden vectors written to", OUT)
 
 

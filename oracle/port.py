@@ -328,13 +328,14 @@ def _bf16_round(t: Tensor) -> Tensor:
 
 def vit_tokens(p: Dict[str, Tensor], x: Tensor, prompts: Optional[Tensor] = None, depth: int = 12, heads: int = 12, gemm_mode: str = "fp32",
                taps: Optional[Dict[str, Tensor]] = None, lora: Optional[Sequence[Dict[str, Tensor]]] = None,
-               prefix: Optional[Dict[int, Tuple[Tensor, Tensor]]] = None, attn_inputs: Optional[List[Tensor]] = None) -> Tensor:
+               prefix: Optional[Dict[int, Tuple[Tensor, Tensor]]] = None, attn_inputs: Optional[List[Tensor]] = None, block_eps: float = 1e-5) -> Tensor:
     """`VisionTransformer.forward(prompt_flag='l2p')` up to and including the final LayerNorm: [B, (P +) 197, D].
     `prompts` [B, P, D] are prepended in front of [cls, patches] AFTER the position embedding was added (transformer.py:2240-2251,
     :2010-2014).  gemm_mode 'bf16' rounds every GEMM operand (and the stored qkv / probabilities / GELU output) to BF16 exactly where
     the CUDA path does; accumulation stays fp32.
     `lora[i]` = {'A_k','B_k','A_v','B_v'} (or 'A_q','B_q'): weight-side adapters of block i, W_s + B_s A_s (transformer.py:246-254).
     `prefix[i]` = (pk, pv) [B, P, D]: prefix keys / values concatenated in front of block i's K, V (transformer.py:175-180).
+    `block_eps`: LayerNorm eps of the blocks (1e-5 in transformer.py:1289,1315; 1e-6 in vit_inflora.py's timm-style blocks).
     `attn_inputs` (a list) receives ln_1(x) of every block, the matrix InfLoRA's `get_input_matrix` accumulates (transformer.py:242-244)."""
     r = _bf16_round if gemm_mode == "bf16" else (lambda t: t)
     B = x.shape[0]
@@ -352,7 +353,7 @@ def vit_tokens(p: Dict[str, Tensor], x: Tensor, prompts: Optional[Tensor] = None
     hd = D // heads
     for i in range(depth):
         b = f"transformer.blocks.{i}."
-        h = F.layer_norm(xs, (D,), p[b + "ln_1.weight"], p[b + "ln_1.bias"], 1e-5)
+        h = F.layer_norm(xs, (D,), p[b + "ln_1.weight"], p[b + "ln_1.bias"], block_eps)
         if attn_inputs is not None:
             attn_inputs.append(h.detach())
         w_qkv = p[b + "attn.qkv.weight"]
@@ -374,7 +375,7 @@ def vit_tokens(p: Dict[str, Tensor], x: Tensor, prompts: Optional[Tensor] = None
         attn = r(((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(dim=-1))
         o = r((attn @ v).transpose(1, 2).reshape(B, T, D))
         xs = xs + F.linear(o, r(p[b + "attn.proj.weight"]), p[b + "attn.proj.bias"])
-        h = F.layer_norm(xs, (D,), p[b + "ln_2.weight"], p[b + "ln_2.bias"], 1e-5)
+        h = F.layer_norm(xs, (D,), p[b + "ln_2.weight"], p[b + "ln_2.bias"], block_eps)
         u = r(F.gelu(F.linear(r(h), r(p[b + "mlp.fc1.weight"]), p[b + "mlp.fc1.bias"])))
         xs = xs + F.linear(u, r(p[b + "mlp.fc2.weight"]), p[b + "mlp.fc2.bias"])
         if taps is not None:
@@ -433,6 +434,18 @@ def inflora_init_A(cur_matrix: Tensor, rank: int) -> Tensor:
     """Task-0 adapter basis (InfLoRA_opt.py:248-254): the top-`rank` left singular vectors of the input matrix, scaled by 1/sqrt(3)."""
     U, _, _ = torch.linalg.svd(cur_matrix, full_matrices=False)
     return U[:, :rank].T / math.sqrt(3)
+
+
+# ----------------------------------------------------------------------------------------------
+# InfLoRA (original) on the timm-style ViT of vit_inflora.py  (Attention_LoRA.forward :222-252, ViT_lora_co.forward SiNet.py:20-35, InfLoRA.observe)
+# ----------------------------------------------------------------------------------------------
+def inflora_orig_logits(p: Dict[str, Tensor], blocks: Sequence[Sequence[Dict[str, Tensor]]], head_w: Tensor, head_b: Tensor, x: Tensor, depth: int = 12,
+                        heads: int = 12, gemm_mode: str = "fp32") -> Tensor:
+    """blocks[l] = adapters {'A_k','B_k','A_v','B_v'} of block l for tasks 0..t: k and v get x (sum_t B_t A_t)^T added (vit_inflora.py:236-240), i.e. the
+    weight-side sum; LayerNorm eps 1e-6 everywhere; feature = cls token of the final norm; logits of the current task's head only."""
+    lora = [{"delta_k": sum(ad["B_k"] @ ad["A_k"] for ad in blocks[l]), "delta_v": sum(ad["B_v"] @ ad["A_v"] for ad in blocks[l])} for l in range(depth)]
+    feat = vit_tokens(p, x, None, depth, heads, gemm_mode, lora=lora, block_eps=1e-6)[:, 0]
+    return F.linear(feat, head_w, head_b)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -96,6 +96,17 @@ def install_stubs() -> None:
     def register_model(fn):
         return fn
 
+    def named_apply(fn, module, name="", depth_first=True, include_root=False):
+        """timm.models.helpers.named_apply (0.6.7 semantics): fn(module=, name=) over the module tree, children before parents by default;
+        used by vit_inflora.VisionTransformer.init_weights (vit_inflora.py:428-435)."""
+        if not depth_first and include_root:
+            fn(module=module, name=name)
+        for cname, child in module.named_children():
+            named_apply(fn, child, ".".join((name, cname)) if name else cname, depth_first, True)
+        if depth_first and include_root:
+            fn(module=module, name=name)
+        return module
+
     def _cfg(url="", **kwargs):
         return dict(url=url, **kwargs)
 
@@ -117,7 +128,7 @@ def install_stubs() -> None:
     )
     timm.models.layers.helpers = _mod("timm.models.layers.helpers", to_2tuple=to_2tuple)
     timm.models.helpers = _mod(
-        "timm.models.helpers", named_apply=_placeholder("named_apply"), adapt_input_conv=_placeholder("adapt_input_conv"),
+        "timm.models.helpers", named_apply=named_apply, adapt_input_conv=_placeholder("adapt_input_conv"),
         build_model_with_cfg=_placeholder("build_model_with_cfg"),
         resolve_pretrained_cfg=_placeholder("resolve_pretrained_cfg"), checkpoint_seq=_placeholder("checkpoint_seq"),
     )

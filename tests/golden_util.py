@@ -165,3 +165,30 @@ def synth_input_matrices(seed, L=12, D=768, decay=0.955):
         ev = (decay + 0.002 * l) ** np.arange(D)
         out.append(((Q * ev) @ Q.T).astype(np.float32))
     return np.stack(out)
+
+
+def synth_timm_vit_state(seed):
+    """(reference-named state, timm-named state) of the same synthetic ViT-B/16 weights (oracle/make_golden.py::synth_timm_vit_state)."""
+    p = port.vit_init(np.random.default_rng(seed))
+    out = {}
+    for k, v in p.items():
+        out[k.replace("transformer.blocks.", "blocks.").replace(".ln_1.", ".norm1.").replace(".ln_2.", ".norm2.")] = v
+    return p, out
+
+
+def synth_stacked_adapters(seed, n_tasks, depth=12, rank=10):
+    """Same draws as oracle/make_golden.py::synth_stacked_adapters."""
+    rng = np.random.default_rng(seed)
+    blocks = []
+    for _ in range(depth):
+        ads = []
+        for _ in range(n_tasks):
+            ads.append({"A_k": torch.from_numpy((rng.standard_normal((rank, 768)) / np.sqrt(768 * 3)).astype(np.float32)),
+                        "B_k": torch.from_numpy((0.05 * rng.standard_normal((768, rank))).astype(np.float32)),
+                        "A_v": torch.from_numpy((rng.standard_normal((rank, 768)) / np.sqrt(768 * 3)).astype(np.float32)),
+                        "B_v": torch.from_numpy((0.05 * rng.standard_normal((768, rank))).astype(np.float32))})
+        blocks.append(ads)
+    bound = 1.0 / np.sqrt(768)
+    hw = torch.from_numpy(rng.uniform(-bound, bound, (n_tasks, 10, 768)).astype(np.float32))
+    hb = torch.from_numpy(rng.uniform(-bound, bound, (n_tasks, 10)).astype(np.float32))
+    return blocks, hw, hb

@@ -281,3 +281,27 @@ def test_sdlora_vit_observe_matches_reference():
         ref = torch.from_numpy(g["t2/" + k])
         err = float((v - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
         assert err < 1e-3, (k, err)
+
+
+def test_inflora_orig_observe_matches_reference():
+    """Oracle InfLoRA (original: sum of the per-task k / v adapters, timm-style ViT with LayerNorm eps 1e-6) vs the real `core.model.InfLoRA.InfLoRA`
+    on the real `ViT_lora_co` (fixture: tests/golden/inflora_orig_vit.npz), task 1 (two stacked adapters, the second one trains)."""
+    import torch.nn.functional as F
+    from tests.golden_util import synth_images, synth_stacked_adapters, synth_timm_vit_state
+    g = load("inflora_orig_vit.npz")
+    torch.set_num_threads(8)
+    p, _ = synth_timm_vit_state(5150)
+    blocks, hw, hb = synth_stacked_adapters(990, 2)
+    x, y = synth_images(801, 4, 10, 20)
+    ob_ = [[{k: v.clone().requires_grad_(i == 1 and k.startswith("B_")) for k, v in ad.items()} for i, ad in enumerate(blocks[l])] for l in range(12)]
+    ow = hw[1].clone().requires_grad_(True); obias = hb[1].clone().requires_grad_(True)
+    logits = port.inflora_orig_logits(p, ob_, ow, obias, x)
+    loss = F.cross_entropy(logits, y - 10)
+    loss.backward()
+    assert abs(float(loss) - float(g["t1/loss"])) < 1e-5
+    got = {"logits": logits.detach(), "dW": ow.grad, "db": obias.grad, "dB_k": torch.stack([ob_[l][1]["B_k"].grad for l in range(12)]),
+           "dB_v": torch.stack([ob_[l][1]["B_v"].grad for l in range(12)])}
+    for k, v in got.items():
+        ref = torch.from_numpy(g["t1/" + k])
+        err = float((v - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
+        assert err < 1e-3, (k, err)
