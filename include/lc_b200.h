@@ -235,6 +235,12 @@ int lc_coda_prompt_backward(const float* query, const float* const* K, const flo
                             float* const* dK, float* const* dA, float* const* dp, int nlayers, int batch, int nk, int length, int dim, const float* alpha,
                             const float* vnorm, float* dalpha, lc_stream_t stream);
 int lc_gather_rows_bf16(const float* src, const int64_t* idx, long long idx_stride, int rows, int dim, int batch, void* out_bf16, lc_stream_t stream);
+/* GPM's gradient projection (gpm.py:78-81) on the tensor cores at fp32-level accuracy: grad <- grad - grad.view(rows, dim) @ proj for a SYMMETRIC proj
+ * (= U U^T, gpm.py:124) given as its two-term BF16 split (lc_split_bf16: x = hi + lo): three BF16 tcgen05 GEMMs (hi hi + lo hi + hi lo, fp32 accumulation,
+ * applied in place through the residual epilogue) reproduce the fp32 product to ~1e-5 relative.  g_hi / g_lo: BF16 scratch [rows][dim]. */
+int lc_split_bf16(const float* x, void* hi_bf16, void* lo_bf16, long long n, lc_stream_t stream);
+int lc_gpm_project_tc(float* grad, const void* proj_hi_bf16, const void* proj_lo_bf16, int rows, int dim, void* g_hi_bf16, void* g_lo_bf16, int* error_flag,
+                      lc_stream_t stream);
 /* out[c][r] = in[r][c] (BF16; columns [rows, ld_out) of out zero-filled): the transposed copy that turns a contraction over token rows
  * (InfLoRA's input matrix sum_n h_n h_n^T, transformer.py:242-244) into the K-major operands of lc_gemm_bf16. */
 int lc_transpose_bf16(const void* in_bf16, long long ld_in, long long rows, int cols, void* out_bf16, long long ld_out, lc_stream_t stream);

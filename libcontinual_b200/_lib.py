@@ -57,6 +57,8 @@ SIGNATURES = {
     "lc_coda_prompt_forward": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "lc_coda_prompt_backward": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "lc_gather_rows_bf16": (c_int, [P, P, c_longlong, c_int, c_int, c_int, P, P]),
+    "lc_split_bf16": (c_int, [P, P, P, c_longlong, P]),
+    "lc_gpm_project_tc": (c_int, [P, P, P, c_int, c_int, P, P, P, P]),
     "lc_transpose_bf16": (c_int, [P, c_longlong, c_longlong, c_int, P, c_longlong, P]),
     "lc_rowouter_bf16": (c_int, [P, c_longlong, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_longlong, P, c_int, P, c_int, P, P]),
     "lc_coldot_accumulate": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_longlong, P, P, c_int, P, P]),

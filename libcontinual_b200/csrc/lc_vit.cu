@@ -280,6 +280,28 @@ int lc_gather_rows_bf16(const float* src, const int64_t* idx, long long idx_stri
                                                                                   reinterpret_cast<__nv_bfloat16*>(out_bf16));
     return lc_launch_status();
 }
+int lc_split_bf16(const float* x, void* hi_bf16, void* lo_bf16, long long n, lc_stream_t stream) {
+    LC_CHECK_ARG(x && hi_bf16 && lo_bf16 && n >= 1);
+    split_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(hi_bf16), reinterpret_cast<__nv_bfloat16*>(lo_bf16), n);
+    return lc_launch_status();
+}
+int lc_gpm_project_tc(float* grad, const void* proj_hi_bf16, const void* proj_lo_bf16, int rows, int dim, void* g_hi_bf16, void* g_lo_bf16, int* error_flag,
+                      lc_stream_t stream) {
+    LC_CHECK_ARG(grad && proj_hi_bf16 && proj_lo_bf16 && g_hi_bf16 && g_lo_bf16 && rows >= 1 && dim >= 8 && dim % 8 == 0);
+    int e = lc_split_bf16(grad, g_hi_bf16, g_lo_bf16, (long long)rows * dim, stream);
+    if (e != LC_OK) return e;
+    // grad <- grad - g M with M symmetric (M = U U^T): B operand [N = j][K = k] = M itself.  Three in-place passes, each grad <- grad - A_i B_i^T
+    const void* As[3] = {g_hi_bf16, g_lo_bf16, g_hi_bf16};
+    const void* Bs[3] = {proj_hi_bf16, proj_hi_bf16, proj_lo_bf16};
+    for (int i = 0; i < 3; ++i) {
+        lc_gemm_desc d{};
+        d.A = As[i]; d.lda = dim; d.B = Bs[i]; d.ldb = dim; d.C = grad; d.ldc = dim; d.residual = grad; d.ldr = dim;
+        d.M = rows; d.N = dim; d.K = dim; d.batch_in = 1; d.batch_out = 1; d.out_f32 = 1; d.alpha = -1.f;
+        e = lc_gemm_bf16_ex(&d, error_flag, stream);
+        if (e != LC_OK) return e;
+    }
+    return LC_OK;
+}
 int lc_transpose_bf16(const void* in_bf16, long long ld_in, long long rows, int cols, void* out_bf16, long long ld_out, lc_stream_t stream) {
     LC_CHECK_ARG(in_bf16 && out_bf16 && rows >= 1 && cols >= 1 && ld_in >= cols && ld_out >= rows);
     transpose_bf16_kernel<<<dim3((unsigned)((ld_out + 63) / 64), (cols + 63) / 64), 256, 0, (cudaStream_t)stream>>>(

@@ -250,4 +250,15 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16
     }
 }
 
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the two-term BF16 split that lets three BF16 tensor-core products (hi hi + lo hi + hi lo) reproduce an
+// fp32 product to ~2^-16 relative (the dropped lo lo term and the residual of the split are both below that)
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float v = x[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
 }  // namespace lc

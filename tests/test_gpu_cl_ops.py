@@ -150,3 +150,26 @@ def test_herding_matches_reference_golden(lib):
     work = torch.empty_like(feats, device="cuda")
     assert lib.lc_herding_select(P(dev(feats)), P(dev(begins)), len(sizes), 64, 25, P(work), P(out), st()) == 0
     assert [int(v) for v in out.cpu().flatten()] == [int(i) for i in load("herding.npz")["idx"]]
+
+
+def test_gpm_project_tensor_core(lib):
+    """The projection of every AlexNet_TRGP layer shape ([64,48], [128,576], [256,512], [2048,1024], [2048,2048]) on the tensor cores
+    through the two-term BF16 split, against `g - g.view(out, -1) @ M` in float64 and against the reference op in fp32 (gpm.py:78-81)."""
+    from libcontinual_b200.gpm import GPMProjector
+    rng = np.random.default_rng(5)
+    shapes = [((64, 3, 4, 4), 48), ((128, 64, 3, 3), 576), ((256, 128, 2, 2), 512), ((2048, 1024), 1024), ((2048, 2048), 2048)]
+    feats = [torch.linalg.qr(torch.from_numpy(rng.standard_normal((D, max(4, D // 10))).astype(np.float32)))[0] for _, D in shapes]
+    proj = GPMProjector(feats)
+    for i, (shape, D) in enumerate(shapes):
+        g = torch.from_numpy(rng.standard_normal(shape).astype(np.float32))
+        M = feats[i] @ feats[i].T
+        ref32 = port.gpm_project(g, M)
+        ref64 = g.double() - (g.double().view(shape[0], -1) @ M.double()).view(shape)
+        got = proj.project_(i, g.cuda().contiguous())
+        torch.cuda.synchronize()
+        assert int(proj.err.item()) == 0
+        e64 = float((got.cpu().double() - ref64).norm() / ref64.norm())
+        e32 = float((ref32.double() - ref64).norm() / ref64.norm())
+        print(f"gpm tc {tuple(shape)}: rel-L2 vs float64 {e64:.1e} (the fp32 reference op itself: {e32:.1e})")
+        assert e64 < 2e-5, (shape, e64)
+        assert float((got.cpu().view(shape[0], -1) @ feats[i]).abs().max()) < 2e-3      # orthogonal to the stored basis
