@@ -92,13 +92,13 @@ __global__ void __launch_bounds__(192) rowouter_partial_kernel(const __nv_bfloat
         }
         __syncthreads();
 #pragma unroll 1
-        for (int rb = 0; rb < nt; rb += 8) {
-            uint2 xv[8];
+        for (int rb = 0; rb < nt; rb += 16) {                                // 16 rows (128 B per thread) in flight: the kernel is HBM-latency bound
+            uint2 xv[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
+            for (int u = 0; u < 16; ++u)
                 xv[u] = rb + u < nt ? __ldg(reinterpret_cast<const uint2*>(xp + (size_t)(t0 + rb + u) * ldx)) : make_uint2(0u, 0u);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < 16; ++u) {
                 const float x0f = __uint_as_float(xv[u].x << 16), x1f = __uint_as_float(xv[u].x & 0xffff0000u);
                 const float x2f = __uint_as_float(xv[u].y << 16), x3f = __uint_as_float(xv[u].y & 0xffff0000u);
 #pragma unroll
