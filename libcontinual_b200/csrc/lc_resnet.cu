@@ -169,6 +169,12 @@ struct lc_resnet {
     int launches_fwd = 0, launches_bwd = 0;
     int mode = 0;     // 0: exact fp32 CUDA-core convs; 1: TF32 tcgen05 convs (fwd + dgrad of the stride-1 3x3 layers)
     int last_relu = 1; // 0: the last residual block has no final ReLU (LUCIR's modified_ResNet, resnet.py:472-502)
+    // backward runs two chains: the data-gradient chain (BN backward -> dgrad -> ...) on the caller's stream and the weight-gradient kernels, which
+    // are leaves of the dependency graph, on `side` — forked / joined with events so that the pair is capturable into one CUDA graph
+    long long off_T1b = 0;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_dy[2] = {nullptr, nullptr}, ev_w[2] = {nullptr, nullptr}, ev_dy3 = nullptr, ev_w3 = nullptr, ev_join = nullptr;
+    int overlap = 1;
 };
 
 extern "C" {
@@ -265,7 +271,16 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
     n->off_T1 = take(B * 32 * 32 * 16);
     n->off_T2 = take(B * 32 * 32 * 16);
     n->off_T3 = take(B * 16 * 16 * 32);
+    n->off_T1b = take(B * 32 * 32 * 16);
     n->ws_floats = o;
+    {
+        const char* env = getenv("LC_RESNET_SERIAL");
+        n->overlap = (env != nullptr && env[0] == '1') ? 0 : 1;
+        bool okev = cudaStreamCreateWithFlags(&n->side, cudaStreamNonBlocking) == cudaSuccess;
+        cudaEvent_t* evs[7] = {&n->ev_dy[0], &n->ev_dy[1], &n->ev_w[0], &n->ev_w[1], &n->ev_dy3, &n->ev_w3, &n->ev_join};
+        for (auto e : evs) okev = okev && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+        if (!okev) { lc_resnet_destroy(n); return LC_ERR_CUDA; }
+    }
 
     // device tables
     std::vector<ConvTabEntry> tab;
@@ -299,6 +314,8 @@ void lc_resnet_destroy(lc_resnet* n) {
     if (!n) return;
     if (n->d_tab) cudaFree(n->d_tab);
     if (n->d_bntab) cudaFree(n->d_bntab);
+    if (n->side) cudaStreamDestroy(n->side);
+    for (cudaEvent_t e : {n->ev_dy[0], n->ev_dy[1], n->ev_w[0], n->ev_w[1], n->ev_dy3, n->ev_w3, n->ev_join}) if (e) cudaEventDestroy(e);
     delete n;
 }
 
@@ -438,14 +455,17 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
 int lc_resnet_backward(lc_resnet* n, const float* x, int batch, const float* params, float* ws, float* grads, lc_stream_t stream) {
     LC_CHECK_ARG(n && x && params && ws && grads && batch >= 1 && batch <= n->max_batch);
     cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t sw = n->overlap ? n->side : st;           // weight-gradient chain
     int launches = 0;
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws + n->off_counters);
     int* err_flag = reinterpret_cast<int*>(counters) + 8;
     float* packed = ws + n->off_packed;
     float* wpart = ws + n->off_wpart;
-    float* T1 = ws + n->off_T1;
-    float* T2 = ws + n->off_T2;
+    float* Tdy[2] = {ws + n->off_T1, ws + n->off_T1b};     // d(conv output), double-buffered: the weight gradient of layer i reads buffer k while
+    float* T2 = ws + n->off_T2;                            // the BN backward of layer i-1 already fills buffer k^1
     float* T3 = ws + n->off_T3;
+    int k = 0;
+    bool wrec[2] = {false, false}, w3rec = false;
 
     auto bn_bwd = [&](const ConvL& c, const float* g, const float* mask_src, int mask_mode, float* dy, float* g_out) {
         BnBwdArgs a{};
@@ -457,6 +477,30 @@ int lc_resnet_backward(lc_resnet* n, const float* x, int batch, const float* par
         a.npix = (long long)batch * c.wo * c.wo; a.C = c.cout;
         return launch_bn_bwd(a, st);
     };
+    // main chain: buffer k may be overwritten once the weight-gradient kernel that last read it has finished
+    auto dy_acquire = [&]() -> int {
+        if (n->overlap && wrec[k] && cudaStreamWaitEvent(st, n->ev_w[k], 0) != cudaSuccess) return LC_ERR_CUDA;
+        return LC_OK;
+    };
+    // buffer k is complete on the main chain: let the weight-gradient chain read it
+    auto dy_publish = [&]() -> int {
+        if (n->overlap && (cudaEventRecord(n->ev_dy[k], st) != cudaSuccess || cudaStreamWaitEvent(sw, n->ev_dy[k], 0) != cudaSuccess)) return LC_ERR_CUDA;
+        return LC_OK;
+    };
+    auto w_done = [&]() -> int {
+        if (n->overlap) { if (cudaEventRecord(n->ev_w[k], sw) != cudaSuccess) return LC_ERR_CUDA; wrec[k] = true; }
+        return LC_OK;
+    };
+    auto wgrad3x3 = [&](const ConvL& c, const float* in, const float* dy, const float* pro_scale, const float* pro_shift, bool nchw) -> int {
+        if (n->mode == 1 && c.wtf_off >= 0) {
+            tc::WgradTcArgs w{};
+            w.in = in; w.dy = dy; w.partial = wpart + c.part_off; w.B = batch; w.error_flag = err_flag; w.pro_scale = pro_scale; w.pro_shift = pro_shift;
+            return launch_wgrad3x3_tc(c.cin, c.wo, w, wgrad_nsplit_tc(c.cin), sw);
+        }
+        WgradArgs w{};
+        w.in = in; w.dy = dy; w.partial = wpart + c.part_off; w.B = batch; w.nsplit = c.nsplit; w.pro_scale = pro_scale; w.pro_shift = pro_shift;
+        return launch_wgrad3x3(c.cin, c.cout, c.wo, c.stride, nchw, w, sw);
+    };
 
     for (int bi = (int)n->blocks.size() - 1; bi >= 0; --bi) {
         const BlockL& bl = n->blocks[bi];
@@ -465,53 +509,44 @@ int lc_resnet_backward(lc_resnet* n, const float* x, int batch, const float* par
         float* G = ws + n->off_G[bl.stage];
         const float* blk_in = bi == 0 ? ws + n->off_a0 : ws + n->blocks[bi - 1].out_off;
         const float* blk_out = ws + bl.out_off;
-        // bn_b (+ ReLU of the block output): T1 = d(y2), G <- masked gradient (the residual-branch gradient)
+        // bn_b (+ ReLU of the block output): dy = d(y2), G <- masked gradient (the residual-branch gradient)
         const bool no_relu = !n->last_relu && bi == (int)n->blocks.size() - 1;
-        LC_TRY(bn_bwd(cb, G, blk_out, no_relu ? LC_MASK_NONE : LC_MASK_FROM_OUT, T1, no_relu ? nullptr : G)); ++launches;
+        LC_TRY(dy_acquire());
+        LC_TRY(bn_bwd(cb, G, blk_out, no_relu ? LC_MASK_NONE : LC_MASK_FROM_OUT, Tdy[k], no_relu ? nullptr : G)); ++launches;
+        LC_TRY(dy_publish());
         if (bl.conv_d >= 0) {
             const ConvL& cd = n->convs[bl.conv_d];
-            LC_TRY(bn_bwd(cd, G, nullptr, LC_MASK_NONE, T3, nullptr)); ++launches;
-            LC_TRY(launch_conv1x1_wgrad(cd.cin, cd.cout, cd.wo, blk_in, T3, wpart + cd.part_off, batch, st));
+            if (n->overlap && w3rec && cudaStreamWaitEvent(st, n->ev_w3, 0) != cudaSuccess) return LC_ERR_CUDA;   // the previous reader of T3
+            LC_TRY(bn_bwd(cd, G, nullptr, LC_MASK_NONE, T3, nullptr)); ++launches;      // T3 is written at the two stage transitions only
+            if (n->overlap && (cudaEventRecord(n->ev_dy3, st) != cudaSuccess || cudaStreamWaitEvent(sw, n->ev_dy3, 0) != cudaSuccess)) return LC_ERR_CUDA;
+            LC_TRY(launch_conv1x1_wgrad(cd.cin, cd.cout, cd.wo, blk_in, T3, wpart + cd.part_off, batch, sw));
+            if (n->overlap) { if (cudaEventRecord(n->ev_w3, sw) != cudaSuccess) return LC_ERR_CUDA; w3rec = true; }
         }
-        {   // conv_b: weight gradient (input = relu(bn_a(y1)) recomputed on load) and data gradient
-            if (n->mode == 1 && cb.wtf_off >= 0) {
-                tc::WgradTcArgs w{};
-                w.in = ws + ca.y_off; w.dy = T1; w.partial = wpart + cb.part_off; w.B = batch; w.error_flag = err_flag;
-                w.pro_scale = ws + ca.aff_off; w.pro_shift = ws + ca.aff_off + ca.cout;
-                LC_TRY(launch_wgrad3x3_tc(cb.cin, cb.wo, w, wgrad_nsplit_tc(cb.cin), st));
-            } else {
-                WgradArgs w{};
-                w.in = ws + ca.y_off; w.dy = T1; w.partial = wpart + cb.part_off; w.B = batch; w.nsplit = cb.nsplit;
-                w.pro_scale = ws + ca.aff_off; w.pro_shift = ws + ca.aff_off + ca.cout;
-                LC_TRY(launch_wgrad3x3(cb.cin, cb.cout, cb.wo, 1, false, w, st));
-            }
-            if (n->mode == 1 && cb.wtd_off >= 0) {
-                tc::ConvTcArgs a{};
-                a.in = T1; a.wtc = packed + cb.wtd_off; a.out = T2; a.B = batch; a.error_flag = err_flag;
-                LC_TRY(launch_conv3x3_tc(cb.cin, cb.wo, a, st));
-            } else {
-                Conv3x3Args a{};
-                a.in = T1; a.wpack = packed + cb.wd_off; a.out = T2; a.B = batch;
-                LC_TRY(launch_conv3x3(cb.cout, cb.cin, cb.wo, 1, false, false, a, st));
-            }
-        }
-        // bn_a (+ ReLU): T1 = d(y1)
-        LC_TRY(bn_bwd(ca, T2, nullptr, LC_MASK_FROM_BN, T1, nullptr)); ++launches;
-        {
-            if (n->mode == 1 && ca.wtf_off >= 0) {
-                tc::WgradTcArgs w{};
-                w.in = blk_in; w.dy = T1; w.partial = wpart + ca.part_off; w.B = batch; w.error_flag = err_flag;
-                LC_TRY(launch_wgrad3x3_tc(ca.cin, ca.wo, w, wgrad_nsplit_tc(ca.cin), st));
-            } else {
-                WgradArgs w{};
-                w.in = blk_in; w.dy = T1; w.partial = wpart + ca.part_off; w.B = batch; w.nsplit = ca.nsplit;
-                LC_TRY(launch_wgrad3x3(ca.cin, ca.cout, ca.wo, ca.stride, false, w, st));
-            }
+        // conv_b: weight gradient (input = relu(bn_a(y1)) recomputed on load) on the side chain, data gradient on the main chain
+        LC_TRY(wgrad3x3(cb, ws + ca.y_off, Tdy[k], ws + ca.aff_off, ws + ca.aff_off + ca.cout, false));
+        LC_TRY(w_done());
+        if (n->mode == 1 && cb.wtd_off >= 0) {
+            tc::ConvTcArgs a{};
+            a.in = Tdy[k]; a.wtc = packed + cb.wtd_off; a.out = T2; a.B = batch; a.error_flag = err_flag;
+            LC_TRY(launch_conv3x3_tc(cb.cin, cb.wo, a, st));
+        } else {
             Conv3x3Args a{};
-            a.in = T1; a.wpack = packed + ca.wd_off; a.B = batch;
+            a.in = Tdy[k]; a.wpack = packed + cb.wd_off; a.out = T2; a.B = batch;
+            LC_TRY(launch_conv3x3(cb.cout, cb.cin, cb.wo, 1, false, false, a, st));
+        }
+        k ^= 1;
+        // bn_a (+ ReLU): dy = d(y1)
+        LC_TRY(dy_acquire());
+        LC_TRY(bn_bwd(ca, T2, nullptr, LC_MASK_FROM_BN, Tdy[k], nullptr)); ++launches;
+        LC_TRY(dy_publish());
+        LC_TRY(wgrad3x3(ca, blk_in, Tdy[k], nullptr, nullptr, false));
+        LC_TRY(w_done());
+        {
+            Conv3x3Args a{};
+            a.in = Tdy[k]; a.wpack = packed + ca.wd_off; a.B = batch;
             if (ca.stride == 1 && n->mode == 1 && ca.wtd_off >= 0) {
                 tc::ConvTcArgs t{};
-                t.in = T1; t.wtc = packed + ca.wtd_off; t.out = G; t.addend = G; t.B = batch; t.error_flag = err_flag;
+                t.in = Tdy[k]; t.wtc = packed + ca.wtd_off; t.out = G; t.addend = G; t.B = batch; t.error_flag = err_flag;
                 LC_TRY(launch_conv3x3_tc(ca.cin, ca.wo, t, st));
             } else if (ca.stride == 1) {
                 a.out = G; a.addend = G;     // identity shortcut: dX = dgrad + masked G (in place)
@@ -524,15 +559,19 @@ int lc_resnet_backward(lc_resnet* n, const float* x, int batch, const float* par
                 LC_TRY(launch_conv1x1_dgrad(cd.cin, cd.cout, cd.wo, T3, params + cd.w_off, Gprev, batch, st));
             }
         }
+        k ^= 1;
     }
     {   // stem
         const ConvL& c = n->convs[0];
         float* G = ws + n->off_G[0];
-        LC_TRY(bn_bwd(c, G, ws + n->off_a0, LC_MASK_FROM_OUT, T1, nullptr)); ++launches;
+        LC_TRY(dy_acquire());
+        LC_TRY(bn_bwd(c, G, ws + n->off_a0, LC_MASK_FROM_OUT, Tdy[k], nullptr)); ++launches;
+        LC_TRY(dy_publish());
         WgradArgs w{};
-        w.in = x; w.dy = T1; w.partial = wpart + c.part_off; w.B = batch; w.nsplit = c.nsplit;
-        LC_TRY(launch_wgrad3x3(c.cin, c.cout, c.wo, 1, true, w, st));
+        w.in = x; w.dy = Tdy[k]; w.partial = wpart + c.part_off; w.B = batch; w.nsplit = c.nsplit;
+        LC_TRY(launch_wgrad3x3(c.cin, c.cout, c.wo, 1, true, w, sw));
     }
+    if (n->overlap && (cudaEventRecord(n->ev_join, sw) != cudaSuccess || cudaStreamWaitEvent(st, n->ev_join, 0) != cudaSuccess)) return LC_ERR_CUDA;
     wgrad_reduce_all_kernel<<<n->tab_blocks, 256, 0, st>>>(n->d_tab, (int)n->convs.size(), wpart, grads, n->mode);
     LC_TRY(lc_launch_status());
     n->launches_bwd = launches;

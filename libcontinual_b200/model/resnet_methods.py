@@ -138,13 +138,28 @@ class _ResNetMethod(nn.Module):
         eng = self.engine
         B = x.shape[0]
         n = eng.ncls
-        tl = eng.teacher_logits(teacher, x) if (teacher is not None and kd_n > 0) else None
+        tl = None
+        if teacher is not None and kd_n > 0:
+            # the frozen teacher's forward is independent of the student's: it runs on a second stream (forked / joined with events, so the pair
+            # is captured as two parallel branches of the step's CUDA graph) — every kernel of a 128-image ResNet32 is far too small to fill 148 SMs
+            main = torch.cuda.current_stream(eng.device)
+            side = self._teacher_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                tl = eng.teacher_logits(teacher, x)
         eng.forward(x, train=True, update_running=True)
         self.backbone.num_batches_pending += 1      # host bookkeeping of BN.num_batches_tracked (never read by the kernels)
         eng.head_forward(B, n)
+        if tl is not None:
+            torch.cuda.current_stream(eng.device).wait_stream(side)
         eng.loss(y, B, ce_lo, ce_hi, pred_n, teacher_logits=tl, kd_n=kd_n, kd_w=kd_w, T=2.0)
         eng.head_backward(B, n)
         eng.backward(x)
+
+    def _teacher_stream(self):
+        if getattr(self, "_tstream", None) is None:
+            self._tstream = torch.cuda.Stream(device=self.engine.device)
+        return self._tstream
 
     def _infer_logits(self, x):
         eng = self.engine
