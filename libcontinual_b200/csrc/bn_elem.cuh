@@ -22,6 +22,7 @@ struct BnActArgs {
 };
 
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(BnActArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // a dependent tensor-core conv may start its data-independent prologue now
     const int c4n = a.C >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % c4n) * 4;
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
 
 // pass 2: dy = c0*g + c1*y + c2  (g masked as in pass 1); optionally writes the masked g back
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // a dependent tensor-core conv may start its data-independent prologue now
     const int C = a.C, c4n = C >> 2;
     const long long n4 = a.npix * c4n;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {

@@ -199,8 +199,6 @@ __global__ void __launch_bounds__(256) conv3x3_tc_kernel(ConvTcArgs a) {
     if (tid == 32) {
         mbar_init(bar, K::T);
         mbar_init(bar + 1, 1);
-        // weights are already in UMMA order in global memory: one bulk copy, tracked by bar[1]
-        bulk_load(smem_u32(sB), a.wtc, (uint32_t)K::B_BYTES, bar + 1);
     }
     if (warp == 0) tmem_alloc(tmem_slot, K::TMEM_COLS);
 
@@ -215,6 +213,13 @@ __global__ void __launch_bounds__(256) conv3x3_tc_kernel(ConvTcArgs a) {
         }
         s_rowsrc[r] = src;
     }
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, the row table) touches nothing a predecessor kernel writes, so
+    // it overlaps the predecessor's tail; weights, activations, BN coefficients and the addend are only read after griddepcontrol.wait
+    // (= predecessor complete and flushed).  Our own dependent may start its prologue right away.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // weights are already in UMMA order in global memory: one bulk copy, tracked by bar[1]
+    if (tid == 32) bulk_load(smem_u32(sB), a.wtc, (uint32_t)K::B_BYTES, bar + 1);
     __syncthreads();
     LC_TSTAMP(7);
 
@@ -359,7 +364,13 @@ static inline int conv_tc_launch(const ConvTcArgs& a, cudaStream_t st) {
     }
     const long long total = (long long)a.B * K::PP;
     const int grid = (int)((total + K::MROWS - 1) / K::MROWS);
-    conv3x3_tc_kernel<C, W><<<grid, K::NT, K::SMEM_BYTES, st>>>(a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(K::NT); cfg.dynamicSmemBytes = K::SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<C, W>, a) != cudaSuccess) return LC_ERR_CUDA;
     return lc_launch_status();
 }
 
