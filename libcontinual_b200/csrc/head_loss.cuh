@@ -49,64 +49,75 @@ struct LossArgs {
     float kd_w, T;
 };
 
-__global__ void __launch_bounds__(256) ce_kd_loss_kernel(LossArgs a) {
-    __shared__ float s_ce[256], s_kd[256];
-    __shared__ int s_ok[256];
+// One block of 1024 threads: warp w owns samples w, w + 32, ...; the lanes stride over the classes (max / sum-exp by warp shuffles), so a 128 x 100 batch
+// is one pass of 4 samples per warp instead of 100-term serial loops in 128 threads (40 us -> a few us on the critical path of every step).  Sums over
+// the samples: per-warp partials in a fixed order (deterministic).
+__global__ void __launch_bounds__(1024) ce_kd_loss_kernel(LossArgs a) {
+    __shared__ float s_ce[32], s_kd[32];
+    __shared__ int s_ok[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float ce_acc = 0.f, kd_acc = 0.f;
     int ok_acc = 0;
     const float invB = 1.f / (float)a.B;
-    for (int n = threadIdx.x; n < a.B; n += 256) {
+    for (int n = warp; n < a.B; n += 32) {
         const float* lg = a.logits + (size_t)n * a.ldl;
         float* dl = a.dlogits + (size_t)n * a.ldl;
         const int y = (int)a.y[n];
         // prediction (first maximal index)
-        float best = -CUDART_INF_F; int bi = a.pred_lo;
-        for (int k = a.pred_lo; k < a.pred_n; ++k) { const float v = lg[k]; if (v > best) { best = v; bi = k; } }
-        a.pred[n] = bi;
-        ok_acc += (bi == y);
-        for (int k = 0; k < a.ncols; ++k) dl[k] = 0.f;
+        float best = -CUDART_INF_F; int bi = 0x7fffffff;
+        for (int k = a.pred_lo + lane; k < a.pred_n; k += 32) { const float v = lg[k]; if (v > best) { best = v; bi = k; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (bi == 0x7fffffff) bi = a.pred_lo;
         // cross entropy on the slice
         float m = -CUDART_INF_F;
-        for (int k = a.ce_lo; k < a.ce_hi; ++k) m = fmaxf(m, lg[k]);
+        for (int k = a.ce_lo + lane; k < a.ce_hi; k += 32) m = fmaxf(m, lg[k]);
+        m = warp_max(m);
         float se = 0.f;
-        for (int k = a.ce_lo; k < a.ce_hi; ++k) se += expf(lg[k] - m);
-        const float lse = m + logf(se);
-        ce_acc += lse - lg[y];
-        const float inv_se = 1.f / se;
-        for (int k = a.ce_lo; k < a.ce_hi; ++k) dl[k] = (expf(lg[k] - m) * inv_se - (k == y ? 1.f : 0.f)) * invB;
+        for (int k = a.ce_lo + lane; k < a.ce_hi; k += 32) se += expf(lg[k] - m);
+        se = warp_sum(se);
+        const float lse = m + logf(se), inv_se = 1.f / se;
         // distillation
+        float ms = -CUDART_INF_F, mt = -CUDART_INF_F, ss = 0.f, stt = 0.f, kd = 0.f, lss = 0.f, inv_ss = 0.f, inv_st = 0.f;
+        const float invT = a.kd_n > 0 ? 1.f / a.T : 0.f;
+        const float* tg = a.kd_n > 0 ? a.teacher + (size_t)n * a.ldt : nullptr;
         if (a.kd_n > 0) {
-            const float* tg = a.teacher + (size_t)n * a.ldt;
-            const float invT = 1.f / a.T;
-            float ms = -CUDART_INF_F, mt = -CUDART_INF_F;
-            for (int k = 0; k < a.kd_n; ++k) { ms = fmaxf(ms, lg[k] * invT); mt = fmaxf(mt, tg[k] * invT); }
-            float ss = 0.f, st = 0.f;
-            for (int k = 0; k < a.kd_n; ++k) { ss += expf(lg[k] * invT - ms); st += expf(tg[k] * invT - mt); }
-            const float lss = ms + logf(ss), inv_ss = 1.f / ss, inv_st = 1.f / st;
-            float kd = 0.f;
-            for (int k = 0; k < a.kd_n; ++k) {
+            for (int k = lane; k < a.kd_n; k += 32) { ms = fmaxf(ms, lg[k] * invT); mt = fmaxf(mt, tg[k] * invT); }
+            ms = warp_max(ms); mt = warp_max(mt);
+            for (int k = lane; k < a.kd_n; k += 32) { ss += expf(lg[k] * invT - ms); stt += expf(tg[k] * invT - mt); }
+            ss = warp_sum(ss); stt = warp_sum(stt);
+            lss = ms + logf(ss); inv_ss = 1.f / ss; inv_st = 1.f / stt;
+        }
+        for (int k = lane; k < a.ncols; k += 32) {
+            float d = 0.f;
+            if (k >= a.ce_lo && k < a.ce_hi) d = (expf(lg[k] - m) * inv_se - (k == y ? 1.f : 0.f)) * invB;
+            if (k < a.kd_n) {
                 const float q = expf(tg[k] * invT - mt) * inv_st;
                 const float ps = expf(lg[k] * invT - ms) * inv_ss;
                 kd -= q * (lg[k] * invT - lss);
-                dl[k] += a.kd_w * invB * invT * (ps - q);
+                d += a.kd_w * invB * invT * (ps - q);
             }
+            dl[k] = d;
+        }
+        kd = warp_sum(kd);
+        if (lane == 0) {
+            a.pred[n] = bi;
+            ok_acc += (bi == y);
+            ce_acc += lse - lg[y];
             kd_acc += kd;
         }
     }
-    s_ce[threadIdx.x] = ce_acc; s_kd[threadIdx.x] = kd_acc; s_ok[threadIdx.x] = ok_acc;
+    if (lane == 0) { s_ce[warp] = ce_acc; s_kd[warp] = kd_acc; s_ok[warp] = ok_acc; }
     __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
-        if (threadIdx.x < off) {
-            s_ce[threadIdx.x] += s_ce[threadIdx.x + off];
-            s_kd[threadIdx.x] += s_kd[threadIdx.x + off];
-            s_ok[threadIdx.x] += s_ok[threadIdx.x + off];
-        }
-        __syncthreads();
-    }
     if (threadIdx.x == 0) {
-        const float ce = s_ce[0] * invB, kd = s_kd[0] * invB;
+        float ces = 0.f, kds = 0.f; int oks = 0;
+        for (int w = 0; w < 32; ++w) { ces += s_ce[w]; kds += s_kd[w]; oks += s_ok[w]; }
+        const float ce = ces * invB, kd = kds * invB;
         a.scal[0] = ce + a.kd_w * kd + (a.extra != nullptr ? a.extra_coeff * *a.extra : 0.f);
-        a.scal[1] = (float)s_ok[0];
+        a.scal[1] = (float)oks;
         a.scal[2] = ce;
         a.scal[3] = kd;
     }

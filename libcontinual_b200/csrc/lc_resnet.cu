@@ -594,7 +594,7 @@ int lc_loss_ce_kd(const float* logits, int ldl, const float* teacher, int ldt, c
     a.logits = logits; a.teacher = teacher; a.y = reinterpret_cast<const long long*>(y); a.dlogits = dlogits;
     a.pred = reinterpret_cast<long long*>(pred); a.scal = scal; a.B = batch; a.ldl = ldl; a.ldt = ldt; a.ncols = ldl;
     a.ce_lo = ce_lo; a.ce_hi = ce_hi; a.kd_n = kd_n; a.pred_n = pred_n; a.kd_w = kd_w; a.T = T;
-    ce_kd_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
+    ce_kd_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
     return lc_launch_status();
 }
 
@@ -604,7 +604,7 @@ int lc_loss_ce_masked(const float* logits, int ldl, const int64_t* y, int batch,
     LossArgs a{};
     a.logits = logits; a.y = reinterpret_cast<const long long*>(y); a.dlogits = dlogits; a.pred = reinterpret_cast<long long*>(pred); a.scal = scal;
     a.B = batch; a.ldl = ldl; a.ncols = ldl; a.ce_lo = lo; a.ce_hi = hi; a.pred_lo = lo; a.pred_n = hi; a.extra = extra; a.extra_coeff = extra_coeff;
-    ce_kd_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
+    ce_kd_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
     return lc_launch_status();
 }
 
