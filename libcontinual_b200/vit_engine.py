@@ -89,7 +89,7 @@ class _Workspace:
             n = B * T
             e = lambda *shape, dt=bf: torch.empty(*shape, device=dev, dtype=dt)
             self.bwd = dict(g=[e(B, T, DIM, dt=f32), e(B, T, DIM, dt=f32)], gbf=e(n, DIM), dU=e(n, MLP), dh=e(n, DIM, dt=f32), dO=e(n, DIM),
-                            rowdot=e(B, HEADS, T, dt=f32), dqkv=e(n, 3 * DIM))
+                            rowdot=e(B, HEADS, T, dt=f32), dqkv=e(n, 3 * DIM), dqkv2=e(n, 3 * DIM))
         return self.bwd
 
 
@@ -418,10 +418,27 @@ class ViTEngine:
         st = stream_ptr()
         bw = ws.backward_buffers()
         g, g2 = bw["g"]
-        gbf, dU, dh, dO, rowdot, dqkv = (bw[k] for k in ("gbf", "dU", "dh", "dO", "rowdot", "dqkv"))
+        gbf, dU, dh, dO, rowdot = (bw[k] for k in ("gbf", "dU", "dh", "dO", "rowdot"))
+        # Adapter gradients are leaves of the dependency graph: they run on a second stream next to the token-gradient chain (the persistent GEMMs leave
+        # registers / issue slots for one CUDA-core CTA per SM).  d(qkv) is double-buffered so that block i-1's attention backward may write one buffer
+        # while block i's adapter kernels still read the other; events carry the edges, and fork / join keep the pair capturable into one CUDA graph.
+        side_on = self.lora is not None and self.lora.active
+        dq = [bw["dqkv"], bw["dqkv2"]] if side_on else [bw["dqkv"], bw["dqkv"]]
+        if side_on:
+            main = torch.cuda.current_stream(self.dev)
+            if getattr(self, "_side", None) is None:
+                self._side = torch.cuda.Stream(device=self.dev)
+                self._ev_ready = [torch.cuda.Event(), torch.cuda.Event()]
+                self._ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+            used = [False, False]
+            self._side.wait_stream(main)
         self._ln_bwd(None, ws.x[self.depth], "norm", 1e-6, None, g, gbf, dh_pool=dfeat, T=T, n_active=max(n_prompt, 1))
         for i in reversed(range(self.depth)):
             pre = f"transformer.blocks.{i}."
+            kb = i & 1
+            dqkv = dq[kb]
+            if side_on and used[kb]:
+                main.wait_event(self._ev_done[kb])          # the adapter kernels that last read this buffer
             # MLP branch: x_out = x_mid + fc2(GELU(fc1(LN2(x_mid))))
             self._linear_t(gbf, pre + "mlp.fc2.weight", dU, gelu_bwd_aux=ws.upre[i])
             self._linear_t(dU, pre + "mlp.fc1.weight", dh)
@@ -438,12 +455,21 @@ class ViTEngine:
                 check(self.lib.lc_attn_backward_prefix(ws.qkv[i].data_ptr(), dO.data_ptr(), ws.lse[i].data_ptr(), dqkv.data_ptr(), B, T, HEADS, pk.data_ptr(),
                                                        pv.data_ptr(), dpk.data_ptr(), dpv.data_ptr(), pk.shape[1], self.err.data_ptr(), st), "attn_backward_prefix")
             self.launches += 2
-            if self.lora is not None and self.lora.active:
-                self.lora_grads(i, ws, dqkv)
+            if side_on:
+                self._ev_ready[kb].record(main)
+                with torch.cuda.stream(self._side):
+                    self._side.wait_event(self._ev_ready[kb])
+                    self.lora_grads(i, ws, dqkv)
+                    self._ev_done[kb].record(self._side)
+                used[kb] = True
             if i == 0 and not to_tokens:          # nothing trainable below the first attention (adapters only): stop here
+                if side_on:
+                    main.wait_stream(self._side)
                 return None
             self._linear_t(dqkv, pre + "attn.qkv.weight", dh)
             self._ln_bwd(dh, ws.x[i], pre + "ln_1", self.block_ln_eps, g2, g, gbf)
+        if side_on:
+            main.wait_stream(self._side)
         return g
 
     # ---- InfLoRA's input matrix (transformer.py:242-244, InfLoRA_opt.py:243-245) ----------------------
