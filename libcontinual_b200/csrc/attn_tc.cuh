@@ -401,17 +401,22 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
         LC_ASTAMP(6 + 7 * qt);
         // ---- dQ tile out: thread (row, chalf) stores 32 of the 64 columns ----------------------------------------------------------------
         {
-            __nv_bfloat16* o = a.dqkv + ((size_t)b * T + (rv ? t : 0)) * ld + h * kAttnD + chalf * 32;
+            // staged through the (now dead) P tile region: 4 lanes write one 64-byte row segment
+            unsigned char* stg = smem + (size_t)warp * 32 * 80;
+            float v[32];
+            tmem_ld32(trow + (uint32_t)(chalf * 32), v);
 #pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 16) {
-                float v[16];
-                tmem_ld16(trow + (uint32_t)(chalf * 32 + c0), v);
-                if (rv) {
-                    *reinterpret_cast<uint4*>(o + c0) = make_uint4(pack_bf16(v[0] * 0.125f, v[1] * 0.125f), pack_bf16(v[2] * 0.125f, v[3] * 0.125f),
-                                                                   pack_bf16(v[4] * 0.125f, v[5] * 0.125f), pack_bf16(v[6] * 0.125f, v[7] * 0.125f));
-                    *reinterpret_cast<uint4*>(o + c0 + 8) = make_uint4(pack_bf16(v[8] * 0.125f, v[9] * 0.125f), pack_bf16(v[10] * 0.125f, v[11] * 0.125f),
-                                                                       pack_bf16(v[12] * 0.125f, v[13] * 0.125f), pack_bf16(v[14] * 0.125f, v[15] * 0.125f));
-                }
+            for (int i = 0; i < 32; i += 8)
+                *reinterpret_cast<uint4*>(stg + (tid & 31) * 80 + i * 2) = make_uint4(pack_bf16(v[i] * 0.125f, v[i + 1] * 0.125f), pack_bf16(v[i + 2] * 0.125f, v[i + 3] * 0.125f),
+                                                                                     pack_bf16(v[i + 4] * 0.125f, v[i + 5] * 0.125f), pack_bf16(v[i + 6] * 0.125f, v[i + 7] * 0.125f));
+            __syncwarp();
+            const int lane = tid & 31, rr = lane >> 2, ch = lane & 3;
+#pragma unroll
+            for (int p4 = 0; p4 < 4; ++p4) {
+                const int r = p4 * 8 + rr;
+                const int tq = q0 + (warp & 3) * 32 + r;
+                if (tq < T)
+                    *reinterpret_cast<uint4*>(a.dqkv + ((size_t)b * T + tq) * ld + h * kAttnD + chalf * 32 + ch * 8) = *reinterpret_cast<const uint4*>(stg + r * 80 + ch * 16);
             }
         }
         fence_before_sync();
@@ -427,9 +432,11 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
         for (int half = 0; half < 2; ++half) {
             if (half * 128 >= NP) break;
             const int key = half * 128 + row;
-            const bool kv = key < NK, pre = key < P;
-            __nv_bfloat16* o = a.dqkv + ((size_t)b * T + ((kv && !pre) ? key - P : 0)) * ld + (1 + chalf) * HD + h * kAttnD;
+            const bool pre = key < P;
             float* op = pre ? (chalf == 0 ? a.dpk : a.dpv) + ((size_t)b * P + key) * HD + h * kAttnD : nullptr;
+            // token rows go out through a per-warp shared-memory stage so that 8 lanes write one 128-byte row segment (thread-per-row 16-byte stores
+            // touch every 32-byte sector twice); the few prefix rows are written directly in fp32
+            unsigned char* stg = smem + (size_t)warp * 32 * 144;
 #pragma unroll
             for (int c0 = 0; c0 < kAttnD; c0 += 32) {
                 float v[32];
@@ -437,13 +444,25 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
                 if (pre) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + c0 + i) = make_float4(v[i] * sc, v[i + 1] * sc, v[i + 2] * sc, v[i + 3] * sc);
-                } else if (kv) {
+                }
 #pragma unroll
-                    for (int i = 0; i < 32; i += 8)
-                        *reinterpret_cast<uint4*>(o + c0 + i) = make_uint4(pack_bf16(v[i] * sc, v[i + 1] * sc), pack_bf16(v[i + 2] * sc, v[i + 3] * sc),
-                                                                           pack_bf16(v[i + 4] * sc, v[i + 5] * sc), pack_bf16(v[i + 6] * sc, v[i + 7] * sc));
+                for (int i = 0; i < 32; i += 8)
+                    *reinterpret_cast<uint4*>(stg + (tid & 31) * 144 + (c0 + i) * 2) = make_uint4(pack_bf16(v[i] * sc, v[i + 1] * sc), pack_bf16(v[i + 2] * sc, v[i + 3] * sc),
+                                                                                                 pack_bf16(v[i + 4] * sc, v[i + 5] * sc), pack_bf16(v[i + 6] * sc, v[i + 7] * sc));
+            }
+            __syncwarp();
+            {
+                const int lane = tid & 31, rr = lane >> 3, ch = lane & 7;
+#pragma unroll
+                for (int p8 = 0; p8 < 8; ++p8) {
+                    const int r = p8 * 4 + rr;
+                    const int key_r = half * 128 + (warp & 3) * 32 + r;
+                    if (key_r >= P && key_r < NK)
+                        *reinterpret_cast<uint4*>(a.dqkv + ((size_t)b * T + (key_r - P)) * ld + (1 + chalf) * HD + h * kAttnD + ch * 8) =
+                            *reinterpret_cast<const uint4*>(stg + r * 144 + ch * 16);
                 }
             }
+            __syncwarp();
         }
     }
     LC_ASTAMP(15);
