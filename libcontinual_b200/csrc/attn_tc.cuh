@@ -234,16 +234,22 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwdArgs a) {
     if (!ok && a.error_flag != nullptr && (tid & 31) == 0) atomicExch(a.error_flag, 3);
     const int t = q0 + row;
     const float inv = 1.f / sum;
-    __nv_bfloat16* o = a.out + ((size_t)b * T + (t < T ? t : 0)) * HD + h * kAttnD + chalf * 32;
+    {
+        // O rows go out through a per-warp stage in the (now dead) P tile region: 4 lanes write one 64-byte row segment
+        unsigned char* stg = smem + (size_t)warp * 32 * 80;
+        float v[32];
+        tmem_ld32(trow + (uint32_t)(chalf * 32), v);        // warp-collective (.sync.aligned): rows past the end take part, only the store is predicated
 #pragma unroll
-    for (int c0 = 0; c0 < 32; c0 += 16) {
-        float v[16];
-        tmem_ld16(trow + (uint32_t)(chalf * 32 + c0), v);   // warp-collective (.sync.aligned): rows past the end take part, only the store is predicated
-        if (t < T) {
-            *reinterpret_cast<uint4*>(o + c0) = make_uint4(pack_bf16(v[0] * inv, v[1] * inv), pack_bf16(v[2] * inv, v[3] * inv),
-                                                           pack_bf16(v[4] * inv, v[5] * inv), pack_bf16(v[6] * inv, v[7] * inv));
-            *reinterpret_cast<uint4*>(o + c0 + 8) = make_uint4(pack_bf16(v[8] * inv, v[9] * inv), pack_bf16(v[10] * inv, v[11] * inv),
-                                                               pack_bf16(v[12] * inv, v[13] * inv), pack_bf16(v[14] * inv, v[15] * inv));
+        for (int i = 0; i < 32; i += 8)
+            *reinterpret_cast<uint4*>(stg + (tid & 31) * 80 + i * 2) = make_uint4(pack_bf16(v[i] * inv, v[i + 1] * inv), pack_bf16(v[i + 2] * inv, v[i + 3] * inv),
+                                                                                 pack_bf16(v[i + 4] * inv, v[i + 5] * inv), pack_bf16(v[i + 6] * inv, v[i + 7] * inv));
+        __syncwarp();
+        const int lane = tid & 31, rr = lane >> 2, ch = lane & 3;
+#pragma unroll
+        for (int p4 = 0; p4 < 4; ++p4) {
+            const int r = p4 * 8 + rr;
+            const int tq = q0 + (warp & 3) * 32 + r;
+            if (tq < T) *reinterpret_cast<uint4*>(a.out + ((size_t)b * T + tq) * HD + h * kAttnD + chalf * 32 + ch * 8) = *reinterpret_cast<const uint4*>(stg + r * 80 + ch * 16);
         }
     }
     if (t < T && chalf == 0) a.lse2[((size_t)b * a.H + h) * T + t] = mc + log2f(sum);
