@@ -181,3 +181,42 @@ def test_inflora_trainer_order_flat_sgd_and_graph():
     assert abs(float(gs.loss()) - losses[1]) < 1e-5
     pred, acc = m.inference({"image": x, "label": y})
     assert pred.shape == (4,) and 0.0 <= acc <= 1.0
+
+
+def test_inflora_opt_task_boundary_flow():
+    """The whole plugin flow with (tiny) loaders: before_task (input-matrix pass + SVD -> lora_A), a training step, after_task (merge_weight + DualGPM
+    update), before_task of the next task (basis outside the kept subspace), inference."""
+    from libcontinual_b200 import optim
+    p = synth_vit_state(5150)[0]
+    m = _model(p)
+    loader0 = [{"image": synth_images(900 + j, 4, 0, 20)[0], "label": synth_images(900 + j, 4, 0, 20)[1]} for j in range(2)]
+    m.before_task(0, None, loader0, None)
+    A0 = m.engine.lora.A.clone()                                   # [L, 2, r, 768]
+    gram = A0[3, 0] @ A0[3, 0].T * 3.0
+    assert torch.allclose(gram, torch.eye(10, device="cuda"), atol=1e-3)          # rows = orthonormal basis / sqrt(3)
+    assert torch.equal(A0[:, 0], A0[:, 1]) and float(m.lora_B.abs().max()) == 0.0
+    opt = optim.FlatSGD(m.get_parameters(None), lr=8e-3, momentum=0.9, model=m)
+    w0 = m.engine.qkv_w.clone()
+    for b in loader0:
+        pred, acc, loss = m.observe(b)
+        opt.zero_grad(); loss.backward(); opt.step()
+    assert float(m.lora_B.abs().max()) > 0.0
+    B_trained, A_used = m.lora_B.clone(), m.engine.lora.A.clone()
+    m.after_task(0, None, loader0, None)
+    # merge_weight: k / v slabs moved by B A, q untouched
+    delta = m.engine.qkv_w - w0
+    assert float(delta[:, :768].abs().max()) == 0.0
+    want = B_trained[5, 0] @ A_used[5, 0]
+    assert float((delta[5, 768:1536] - want).abs().max()) < 1e-6
+    assert len(m.feature_list) == 12 and all(t == "remove" for t in m.project_type) and all(f.shape[1] >= 1 for f in m.feature_list)
+    loader1 = [{"image": synth_images(910 + j, 4, 20, 40)[0], "label": synth_images(910 + j, 4, 20, 40)[1]} for j in range(2)]
+    m.before_task(1, None, loader1, None)
+    assert m._known_classes == 20 and float(m.lora_B.abs().max()) == 0.0
+    # the new basis lies outside the subspace kept from task 0 ('remove' projection)
+    F3 = torch.from_numpy(np.ascontiguousarray(m.feature_list[3])).cuda()
+    A1 = m.engine.lora.A[3, 0]
+    assert float((A1 @ F3).abs().max()) < 5e-3
+    pred, acc, loss = m.observe(loader1[0])
+    assert torch.isfinite(loss.detach()).all() and pred.shape == (4,)
+    ipred, iacc = m.inference(loader1[0])
+    assert int(ipred.max()) < 40 and not m.engine.tensor_core_error()

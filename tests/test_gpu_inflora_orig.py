@@ -78,3 +78,32 @@ def test_inflora_orig_observe_matches_reference_golden():
         gs.run(x, yrel)
     torch.cuda.synchronize()
     assert rel_l2(m.theta, eager) < 1e-6
+
+
+def test_inflora_orig_task_boundary_flow():
+    """before_task (cur-matrix pass + SVD -> lora_A of the new adapter), training steps, after_task (update_DualGPM + projection matrices), next task."""
+    from libcontinual_b200 import optim
+    from libcontinual_b200.model import InfLoRA, SiNet_vit
+    _, p_timm = synth_timm_vit_state(5150)
+    bb = SiNet_vit(total_sessions=10, rank=10, init_cls=10, embd_dim=768, state=p_timm, device="cuda:0")
+    m = InfLoRA(bb, 768, 100, inc_cls_num=10, device="cuda:0", lame=1.0, lamb=0.95, total_sessions=10)
+    mk = lambda seed, lo: [{"image": synth_images(seed + j, 4, lo, lo + 10)[0], "label": synth_images(seed + j, 4, lo, lo + 10)[1]} for j in range(2)]
+    l0 = mk(920, 0)
+    m.before_task(0, None, l0, None)
+    assert bb.numtask == 1 and m.engine.lora.R == 10
+    opt = optim.FlatSGD(m.get_parameters(None), lr=8e-3, momentum=0.9, model=m)
+    for b in l0:
+        pred, acc, loss = m.observe(b)
+        opt.zero_grad(); loss.backward(); opt.step()
+    B0 = m.B_cur.clone()
+    assert float(B0.abs().max()) > 0.0
+    m.after_task(0, None, l0, None)
+    assert len(m.feature_list) == 12 and len(m.feature_mat) == 12 and m.feature_mat[0].shape == (768, 768)
+    l1 = mk(930, 10)
+    m.before_task(1, None, l1, None)
+    assert bb.numtask == 2 and m._known_classes == 10 and m.engine.lora.R == 20
+    assert torch.equal(m.B_old[:, :, :, :10], B0) and float(m.B_cur.abs().max()) == 0.0       # task 0's adapter is frozen in the stack, the new one starts at 0
+    pred, acc, loss = m.observe(l1[0])
+    assert torch.isfinite(loss.detach()).all() and int(pred.max()) < 10
+    ipred, iacc = m.inference(l1[0])
+    assert int(ipred.max()) < 20 and not m.engine.tensor_core_error()
