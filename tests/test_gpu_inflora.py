@@ -220,3 +220,29 @@ def test_inflora_opt_task_boundary_flow():
     assert torch.isfinite(loss.detach()).all() and pred.shape == (4,)
     ipred, iacc = m.inference(loader1[0])
     assert int(ipred.max()) < 40 and not m.engine.tensor_core_error()
+
+
+def test_graphed_step_prefetch_equals_plain_run():
+    """`prefetch(next batch)` + `run(batch)` (double-buffered H2D on a copy stream) gives the same parameters as `run(batch)` alone."""
+    from libcontinual_b200 import optim
+    from libcontinual_b200.trainer import GraphedFlatStep
+    p = synth_vit_state(5150)[0]
+    m = _model(p)
+    lora, hw, hb = synth_lora_state(880)
+    _install(m, 0, lora, hw, hb)
+    batches = [tuple(t.pin_memory() for t in synth_images(940 + j, 4, 0, 20)) for j in range(3)]
+    theta0 = m.theta.clone()
+    outs = []
+    for use_prefetch in (False, True):
+        m.theta.copy_(theta0)
+        opt = optim.FlatSGD(m.get_parameters(None), lr=8e-3, momentum=0.9, model=m)
+        gs = GraphedFlatStep(m, opt, 4)
+        if use_prefetch:
+            gs.prefetch(*batches[0])
+        for j in range(3):
+            gs.run(*batches[j])
+            if use_prefetch and j + 1 < 3:
+                gs.prefetch(*batches[j + 1])
+        torch.cuda.synchronize()
+        outs.append(m.theta.clone())
+    assert torch.equal(outs[0], outs[1])
