@@ -145,6 +145,7 @@ struct Conv3x3Cfg {
     static_assert(32 % WO == 0 && HO % TILE_H == 0 && COUT % COUT_CTA == 0 && COUT_CTA % CT == 0 && CT % 4 == 0, "tiling");
     static_assert(CIN % CIN_CHUNK == 0, "cin chunk");
     static_assert(!(DILATE && STRIDE != 1), "dilated input implies stride 1");
+    static_assert(!DILATE || (PT % 2 == 0), "the dilated kernel skips zero rows by the parity of i + r: tile rows must start on even rows");
 };
 
 template <int CIN, int COUT, int WO, int PT, int CT, int RS, int COUT_CTA, int CIN_CHUNK, int STRIDE, bool DILATE, bool IN_NCHW>
@@ -246,9 +247,14 @@ conv3x3_kernel(Conv3x3Args a) {
                         w[k4 * 4 + 0] = t.x; w[k4 * 4 + 1] = t.y; w[k4 * 4 + 2] = t.z; w[k4 * 4 + 3] = t.w;
                     }
 #pragma unroll
-                    for (int i = 0; i < PT; ++i)
+                    for (int i = 0; i < PT; ++i) {
+                        // dilated input (data gradient of a stride-2 conv): input row oh0 + orow0 + i + r - 1 holds data only when it is even; oh0 and
+                        // orow0 are multiples of PT (even), so the parity of i + r decides at compile time — half of the FMAs of the zero-inserted
+                        // tensor are never issued (the column parity varies per lane and is left alone)
+                        if (DILATE && ((i + r) & 1) == 0) continue;
 #pragma unroll
                         for (int k = 0; k < CT; ++k) acc[i][k] = fmaf(v[i * STRIDE + r], w[k], acc[i][k]);
+                    }
                 }
             }
         }
