@@ -45,6 +45,11 @@ def parse():
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: run the oracle port (plain PyTorch eager ops) on the host cores (default, the contract's "
                          "reference arm) or on cuda:0 (PyTorch/cuDNN eager: the denominator of north_star's >=1.3x single-GPU target)")
+    ap.add_argument("--only", action="store_true", help="time the named --workload alone (default run: the headline iCaRL line plus the EWC-ResNet32 and "
+                    "L2P-ViT-B/16 workloads north_star names, under `workloads`, each with its own value / e2e / roofline / cpu_baseline / ref_gpu)")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the PyTorch-eager-on-cuda:0 leg (the denominator of north_star's >=1.3x target)")
+    ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: shard this global batch over the ranks (reference semantic "
+                    "batch_size // n_gpu, trainer.py:238); 0 = per-GPU batch 128 (weak scaling)")
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
                     help="conv arithmetic: tc = tcgen05 tensor cores (TF32 fwd/dgrad, BF16-operand wgrad, fp32 accumulate), fp32 = exact CUDA-core path")
     return ap.parse_args()
@@ -415,21 +420,14 @@ def time_dominant_gemm(eng, reps=40, tokens=222):
     return us, 2.0 * M * N * K, f"gemm_bf16_kernel<256> (fc1: {M} x 3072 x 768, bias + GELU epilogue, tcgen05 kind::f16 BF16, TMA SW128, TMEM accumulators)"
 
 
-def run_ours_l2p(args):
+def run_ours_l2p(args, ctx, kind):
     import torch
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+    world, rank, local, device = ctx.world, ctx.rank, ctx.local, ctx.device
     from libcontinual_b200.model.l2p import L2P, vit_pt_imnet
     from libcontinual_b200.optim import Adam, FlatSGD
     from libcontinual_b200.trainer import GraphedFlatStep, GraphedL2PStep
+    per = BATCH if not args.global_batch else args.global_batch // world
 
-    kind = args.workload
     if kind == "l2p":
         p, prm, key, fc_w, fc_b = l2p_synth_state()
         bb = vit_pt_imnet(pretrained=False, state=p, device=device)
@@ -479,36 +477,17 @@ def run_ours_l2p(args):
         lo, hi, tokens = 20, 40, 197
     eng = m.engine
     NB = 3
-    host = [(x.pin_memory(), y.pin_memory()) for x, y in l2p_batches(NB, BATCH, lo, hi, seed=7 + rank)]
+    host = [(x.pin_memory(), y.pin_memory()) for x, y in l2p_batches(NB, per, lo, hi, seed=7 + rank)]
     devb = [(x.to(device), y.to(device)) for x, y in host]
     K, W = args.steps, max(3, args.warmup)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    step = GraphedL2PStep(m, opt, BATCH) if isinstance(opt, Adam) else GraphedFlatStep(m, opt, BATCH)
-    for i in range(W):
-        step.run(*devb[i % NB])
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for i in range(K):
-        step.run(*devb[i % NB])
-    e1.record()
-    barrier()
-    t1 = time.perf_counter()
-    clocks = sampler.stop(t0, t1) if sampler else None
+    barrier = ctx.barrier
+    make_step = lambda b: GraphedL2PStep(m, opt, b) if isinstance(opt, Adam) else GraphedFlatStep(m, opt, b)
+    step = make_step(per)
+    ms_step, clocks = timed_steps(ctx, step, devb, K, W, with_clocks=True)
     final_loss = float(step.loss())
-    t = torch.tensor([e0.elapsed_time(e1)], device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t) / K
-    value = world * BATCH / (ms_step * 1e-3)
-    launches = step.launches_per_step * K + (K if world > 1 else 0)
+    value = world * per / (ms_step * 1e-3)
+    launches = step.launches_per_step * K
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     Ke = max(5, min(K, 50))
     for i in range(2):
@@ -522,11 +501,8 @@ def run_ours_l2p(args):
         lossv = step.loss().item()
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t) / Ke
-    e2e = {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * 4 + BATCH * 8 + 32,
+    e2e_ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / Ke
+    e2e = {"value": world * per / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": per * 3 * 224 * 224 * 4 + per * 8,
            "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
            "path": f"libcontinual_b200.trainer.{type(step).__name__}.run(pinned host batch) + .prefetch(next pinned host batch) + loss().item() every step"}
     plugin = None
@@ -551,14 +527,15 @@ def run_ours_l2p(args):
         e1.record()
         torch.cuda.synchronize()
         pm = e0.elapsed_time(e1) / Kp
-        plugin = {"value": BATCH / (pm * 1e-3), "unit": "images/s", "ms_per_step": pm,
+        plugin = {"value": per / (pm * 1e-3), "unit": "images/s", "ms_per_step": pm,
                   "path": ("plugin zero_grad->observe (backward + clip inside)->optim.step->loss.item() (trainer.py:592-611)" if kind == "l2p" else
                            "plugin observe->zero_grad->loss.backward()->optim.step->loss.item() (trainer.py:601-611)") + ", eager launches"}
     e2e["plugin_eager"] = plugin
+    strong = None
+    if not args.global_batch:
+        strong = strong_leg(ctx, make_step, lambda b: [(x[:b].contiguous(), y[:b].contiguous()) for x, y in devb], max(5, min(K, 40)), W)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["bf16_tflops"]), "MEASURED_PEAKS.json bf16 burst (kernel timed alone)"
@@ -575,89 +552,143 @@ def run_ours_l2p(args):
         ips, ms, cores = (time_oracle_l2p if kind == "l2p" else time_oracle_inflora)(2, 1, 16)
         cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "ms_per_step": ms,
                "sample": f"2 full {kind} steps of 16 images after 1 warm-up (bounded sample of the bs-128 step; oracle/port.py, PyTorch CPU fp32, {cores} threads)"}
+    ref_gpu = None
+    if world == 1 and not args.no_ref_gpu and kind in ("l2p", "inflora"):
+        del devb
+        torch.cuda.empty_cache()
+        ips, ms, _ = (time_oracle_l2p if kind == "l2p" else time_oracle_inflora)(6, 2, BATCH, "cuda")
+        ref_gpu = {"value": ips, "unit": "images/s", "ms_per_step": ms, "steps": 6, "warmup": 2,
+                   "kind": "oracle/port.py = the reference's op sequence as plain PyTorch ops, eager on cuda:0, fp32 matmuls (allow_tf32 off, PyTorch's "
+                           "default, which the reference never changes: SURVEY 2.3), batch 128",
+                   "ours_over_ref_gpu": value / ips}
     passes = 2 if kind in ("inflora", "sdlora") else 3  # prompt methods: query fwd + prompted fwd + dX bwd; LoRA methods: fwd + dX bwd
-    flop_step = passes * 12 * 2 * (768 * 2304 + 768 * 768 + 2 * 768 * 3072) * BATCH * (215.0 if kind == "l2p" else 197.0)     # rough: linear layers only
+    flop_step = passes * 12 * 2 * (768 * 2304 + 768 * 768 + 2 * 768 * 3072) * per * (215.0 if kind == "l2p" else 197.0)     # rough: linear layers only
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(kind), "global_batch": BATCH * world, "per_gpu_batch": BATCH, "parallelism": f"dp{world}",
+            "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(kind), "global_batch": per * world, "per_gpu_batch": per, "parallelism": f"dp{world}",
+                       "collective": step.collective,
                        "l2": f"per-step working set ~9 GB of saved activations + {NB} rotating 77 MB input batches > 126 MB L2 (no explicit flush)",
                        "precision": "BF16 GEMM operands (tcgen05 kind::f16), fp32 accumulate in TMEM, fp32 residual stream / LayerNorm / softmax / loss / optimizer",
                        "final_loss": final_loss, "tensor_core_error": eng.tensor_core_error(),
                        "approx_model_tflops": flop_step / (ms_step * 1e-3) / 1e12},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "ref_gpu": ref_gpu, "strong": strong}
+    return line
 
 
-def run_ours(args):
-    if args.workload in ("l2p", "inflora", "dualprompt", "codaprompt", "sdlora"):
-        return run_ours_l2p(args)
-    import torch
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    from libcontinual_b200.optim import SGD
-    from libcontinual_b200.trainer import GraphedStep, train_step_eager
+class Ctx:
+    """Process-wide distributed context (one process per GPU; torchrun env)."""
 
-    m, lo, hi = build_model(args.workload, device, args.precision)
-    opt = SGD(m.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4, engine=m.engine)
-    eng = m.engine
-    host = synth_batches(8, hi, lo, seed=7 + rank)
-    host = [(x.pin_memory(), y.pin_memory()) for x, y in host]
-    devb = [(x.to(device), y.to(device)) for x, y in host]
-    K, W = args.steps, max(3, args.warmup)
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.device = torch.device("cuda", self.local)
+        if self.world > 1 and not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=self.device)
 
-    def barrier():
-        if world > 1:
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: HBM-resident inputs, graph replay ---------------------------------------------------------------------
-    step = GraphedStep(m, opt, BATCH)
+    def max_over_ranks(self, ms):
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=self.device)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    def close(self):
+        import torch.distributed as dist
+        if self.world > 1 and dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def timed_steps(ctx, step, batches, K, W, with_clocks=False):
+    """W untimed + K timed `step.run` calls bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks."""
+    import torch
     for i in range(W):
-        step.run(*devb[i % len(devb)])
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+        step.run(*batches[i % len(batches)])
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local) if (with_clocks and ctx.rank == 0) else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
     for i in range(K):
-        step.run(*devb[i % len(devb)])
+        step.run(*batches[i % len(batches)])
     e1.record()
-    barrier()
+    ctx.barrier()
     t1 = time.perf_counter()
-    ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop(t0, t1) if sampler else None
+    return ctx.max_over_ranks(e0.elapsed_time(e1)) / K, clocks
+
+
+def ncu_traffic(kernel_key):
+    """`dram__bytes_read.sum + dram__bytes_write.sum` per launch of the dominant kernel, from THIS round's committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py from the .ncu-rep; never a number typed into this file).  None if absent."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(path))[kernel_key]
+        return float(d["dram_bytes_per_launch"]), d.get("source")
+    except Exception:
+        return None, None
+
+
+def strong_leg(ctx, make_step, make_batches, K, W, global_batch=BATCH):
+    """North_star's sharding (trainer.py:230-241: `batch_size // n_gpu`): the SAME global batch split over the ranks, one gradient exchange per step."""
+    if ctx.world == 1 or global_batch % ctx.world:
+        return None
+    per = global_batch // ctx.world
+    step = make_step(per)
+    ms, _ = timed_steps(ctx, step, make_batches(per), K, W)
+    return {"scaling": "strong", "global_batch": global_batch, "per_gpu_batch": per, "ms_per_step": ms, "value": global_batch / (ms * 1e-3),
+            "unit": "images/s", "collective": step.collective}
+
+
+def run_ours(args, ctx, workload):
+    if workload in ("l2p", "inflora", "dualprompt", "codaprompt", "sdlora"):
+        return run_ours_l2p(args, ctx, workload)
+    import torch
+    from libcontinual_b200.optim import SGD
+    from libcontinual_b200.trainer import GraphedStep, train_step_eager
+    world, rank, device = ctx.world, ctx.rank, ctx.device
+    per = BATCH if not args.global_batch else args.global_batch // world
+
+    m, lo, hi = build_model(workload, device, args.precision)
+    opt = SGD(m.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4, engine=m.engine)
+    eng = m.engine
+    host = synth_batches(8, hi, lo, seed=7 + rank)
+    host = [(x[:per].contiguous().pin_memory(), y[:per].contiguous().pin_memory()) for x, y in host]
+    devb = [(x.to(device), y.to(device)) for x, y in host]
+    K, W = args.steps, max(3, args.warmup)
+
+    # ---- value: HBM-resident inputs, graph replay ---------------------------------------------------------------------
+    step = GraphedStep(m, opt, per)
+    ms_step, clocks = timed_steps(ctx, step, devb, K, W, with_clocks=True)
     final_loss = float(step.loss())
-    t = torch.tensor([ms_total], device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t) / K
-    value = world * BATCH / (ms_step * 1e-3)
-    launches = step.launches_per_step * K + (K if world > 1 else 0)
+    value = world * per / (ms_step * 1e-3)
+    launches = step.launches_per_step * K
 
     # ---- e2e: public step API with pinned HOST batches; H2D copy and the D2H loss read are inside the timed region -------
     Ke = max(10, min(K, 200))
     for i in range(3):
         step.run(*host[i % 8]); float(step.loss())
-    barrier()
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(Ke):
         step.run(*host[i % 8])
         lossv = step.loss().item()
     e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t) / Ke
-    e2e = {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": BATCH * 3 * 32 * 32 * 4 + BATCH * 8,
+    ctx.barrier()
+    e2e_ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / Ke
+    e2e = {"value": world * per / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": per * 3 * 32 * 32 * 4 + per * 8,
            "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
            "path": "libcontinual_b200.trainer.GraphedStep.run(pinned host batch) + loss().item() every step"}
     # the literal reference Trainer order on the plugin surface (eager, autograd hand-off), single replica
@@ -673,14 +704,16 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         pm = e0.elapsed_time(e1) / Kp
-        plugin = {"value": BATCH / (pm * 1e-3), "unit": "images/s", "ms_per_step": pm,
+        plugin = {"value": per / (pm * 1e-3), "unit": "images/s", "ms_per_step": pm,
                   "path": "plugin observe->zero_grad->loss.backward()->optim.step->loss.item() (trainer.py:601-612), eager launches"}
     e2e["plugin_eager"] = plugin
 
+    strong = None
+    if not args.global_batch:
+        strong = strong_leg(ctx, lambda b: GraphedStep(m, opt, b), lambda b: [(x[:b].contiguous(), y[:b].contiguous()) for x, y in devb],
+                            max(10, min(K, 200)), W)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     # ---- roofline of the dominant kernel + cpu baseline (rank 0) ------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -690,37 +723,61 @@ def run_ours(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     us, algo, kname = time_dominant_kernel(eng, args.precision)
     achieved = algo / (us * 1e-6) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
-    # (profiles/r1e_ncu_conv3x3_tc.txt: 8.45 MB read = the input tensor once, 0 B written: the 8.4 MB output was still in the
-    # 126 MB L2 when the capture ended); null for the CUDA-core kernel (not captured)
-    traffic = 8448256 if args.precision == "tc" else None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    traffic, traffic_src = ncu_traffic("conv3x3_tc_kernel<16,32>" if args.precision == "tc" else "conv3x3_kernel<16,16,32>")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": kname, "us_per_launch": us,
-                "algorithmic_bytes_per_launch": algo, "peak_source": peak_src}
+                "algorithmic_bytes_per_launch": algo, "peak_source": peak_src,
+                "step": {"algorithmic_bytes_per_image": 3 * 642048 * 4, "achieved_gbs": 3 * 642048 * 4 * per / (ms_step * 1e-3) / 1e9,
+                         "frac": 3 * 642048 * 4 * per / (ms_step * 1e-3) / 1e9 / peak,
+                         "note": "whole step against SURVEY 8d's conv traffic (3 x 642 048 fp32 activation elements per image)"}}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        ips, ms, cores = time_oracle(args.workload, args.cpu_steps, 1)
+        ips, ms, cores = time_oracle(workload, args.cpu_steps, 1)
         cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "ms_per_step": ms,
                "sample": f"{args.cpu_steps} full training steps of batch {BATCH} after 1 warm-up (oracle/port.py, PyTorch CPU fp32, {cores} threads)"}
+    ref_gpu = None
+    if world == 1 and not args.no_ref_gpu:
+        ips, ms, _ = time_oracle(workload, 60, 10, "cuda")
+        ref_gpu = {"value": ips, "unit": "images/s", "ms_per_step": ms, "steps": 60, "warmup": 10,
+                   "kind": "oracle/port.py = the reference's op sequence as plain PyTorch ops, eager on cuda:0 (cuDNN convs with TF32 allowed, "
+                           "cudnn.benchmark off, fp32 elsewhere: the reference's GPU semantics, SURVEY 2.3); the port's iCaRL teacher runs under no_grad, "
+                           "the reference's does not (icarl.py:212), so this leg is FASTER than the true reference",
+                   "ours_over_ref_gpu": value / ips}
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.precision == "tc" else "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload), "global_batch": BATCH * world, "per_gpu_batch": BATCH, "parallelism": f"dp{world}",
+            "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
+            "dtype": "tf32" if args.precision == "tc" else "f32", "data": "synthetic",
+            "config": {"workload": workload_name(workload), "global_batch": per * world, "per_gpu_batch": per, "parallelism": f"dp{world}",
+                       "collective": step.collective,
                        "l2": "per-step working set ~330 MB of fp32 activations + 8 rotating input batches > 126 MB L2 (no explicit flush)",
                        "precision": ("fp32 storage; 3x3 stride-1 convs on tcgen05: TF32 operands fwd/dgrad, BF16 operands wgrad, fp32 accumulate in TMEM; "
                                       "everything else fp32 FMA" if args.precision == "tc" else "fp32 storage, fp32 FMA (exact mode)"),
                        "final_loss": final_loss, "tensor_core_error": eng.tensor_core_error()},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "ref_gpu": ref_gpu, "strong": strong}
+    return line
 
 
 def main():
     args = parse()
     if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+        return run_reference(args)
+    import gc
+    import torch
+    ctx = Ctx()
+    line = run_ours(args, ctx, args.workload)
+    if args.workload == "icarl" and not args.only:
+        # the two workloads north_star's >= 1.3x target names, timed by the same command and attached to the headline line
+        extra = {}
+        for w in ("ewc", "l2p"):
+            gc.collect(); torch.cuda.empty_cache()
+            sub = argparse.Namespace(**vars(args))
+            if w == "l2p":
+                sub.steps, sub.warmup = max(5, min(args.steps, 40)), max(3, min(args.warmup, 5))
+            extra[w] = run_ours(sub, ctx, w)
+        if line is not None:
+            line["workloads"] = extra
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    ctx.close()
 
 
 if __name__ == "__main__":

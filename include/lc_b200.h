@@ -97,6 +97,9 @@ int lc_avgpool_backward(const float* dfeat, int batch, int hw, int feat_dim, flo
  * lc_fisher_accumulate: fisher += grad^2 * weight (ewc.py:173).   lc_fisher_merge: fisher/num_samples, alpha-EMA (ewc.py:129-131,202-204).
  * lc_sgd_momentum     : torch.optim.SGD step, hp = {lr, momentum, weight_decay}.
  * lc_adam             : torch.optim.Adam step, hp = {lr, b1, b2, eps, wd, 1-b1^t, 1-b2^t}.
+ * lc_adam_tick        : device-side step counter: hp[7] += 1, hp[5] = 1-b1^hp[7], hp[6] = 1-b2^hp[7] with b1, b2 read as DOUBLES from
+ *                       hp[8..11] (hp: 12 floats, 8-byte aligned); a captured step replays it in front of lc_adam, so bias corrections
+ *                       never depend on host staging.
  * lc_clip_grad_norm   : torch.nn.utils.clip_grad_norm_(.., max_norm) over one arena (l2p.py:104); scratch >= 2*296 floats.
  * ------------------------------------------------------------------------------------------------------------------- */
 int lc_ewc_penalty_grad(const float* theta, const float* theta_ref, const float* fisher, float* grad, long long n, const float* hp_lamda,
@@ -108,6 +111,7 @@ int lc_sgd_momentum(float* p, const float* g, float* m, long long n, const float
 int lc_sgd_momentum_frozen(float* p, const float* g, float* m, long long n, const float* hp, long long freeze_lo, long long freeze_hi,
                            lc_stream_t stream);
 int lc_adam(float* p, const float* g, float* m, float* v, long long n, const float* hp, lc_stream_t stream);
+int lc_adam_tick(float* hp, lc_stream_t stream);
 int lc_clip_grad_norm(float* g, long long n, float max_norm, float* scratch, float* norm_out, lc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------------

@@ -44,6 +44,7 @@ SIGNATURES = {
     "lc_sgd_momentum": (c_int, [P, P, P, c_longlong, P, P]),
     "lc_sgd_momentum_frozen": (c_int, [P, P, P, c_longlong, P, c_longlong, c_longlong, P]),
     "lc_adam": (c_int, [P, P, P, P, c_longlong, P, P]),
+    "lc_adam_tick": (c_int, [P, P]),
     "lc_clip_grad_norm": (c_int, [P, c_longlong, c_float, P, P, P]),
     "lc_cosine_head_forward": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, c_int, P]),
     "lc_cosine_head_backward": (c_int, [P, c_int, P, P, P, c_int, c_int, c_int, P, P, P]),

@@ -31,23 +31,25 @@ class HerdingBuffer:
             self.labels = [y[:per] for y in self.labels]
 
     @torch.no_grad()
-    def _features(self, model, x: torch.Tensor) -> torch.Tensor:
+    def _features(self, model, x: torch.Tensor, transform=None) -> torch.Tensor:
+        """L2-normalised eval-mode features of raw items `x`, each batch passed through `transform` (the validation transform, :97) first."""
         bb = model.backbone
         was = bb.training
         bb.eval()
         out = []
         for i in range(0, x.shape[0], 32):                 # batch 32, no shuffle (:118-126)
-            f = bb(x[i:i + 32])["features"]
+            xb = x[i:i + 32]
+            f = bb(xb if transform is None else transform(xb))["features"]
             out.append(f / f.norm(dim=1).view(-1, 1))
         bb.train(was)
         return torch.cat(out)
 
     @torch.no_grad()
-    def herding_indices(self, model, x: torch.Tensor, y: torch.Tensor, per_class: int) -> torch.Tensor:
+    def herding_indices(self, model, x: torch.Tensor, y: torch.Tensor, per_class: int, transform=None) -> torch.Tensor:
         """x/y: the current task's samples, sorted by class.  Returns the selected global indices (class-major)."""
         lib = load()
         dev = model.engine.device
-        feats = self._features(model, x.to(dev)).contiguous()
+        feats = self._features(model, x.to(dev), transform).contiguous()
         classes, counts = torch.unique_consecutive(y.cpu(), return_counts=True)
         assert torch.equal(classes, torch.sort(classes)[0]) and len(torch.unique(classes)) == len(classes), "task data must be sorted by class"
         begins = torch.zeros(len(classes) + 1, dtype=torch.int32)
@@ -59,9 +61,10 @@ class HerdingBuffer:
                                     torch.cuda.current_stream().cuda_stream), "lc_herding_select")
         return out
 
-    def update(self, model, x: torch.Tensor, y: torch.Tensor, total_cls_num: int) -> torch.Tensor:
+    def update(self, model, x: torch.Tensor, y: torch.Tensor, total_cls_num: int, transform=None) -> torch.Tensor:
+        """x: RAW task items (stored as they are, like the reference stores paths); `transform` only shapes what the feature pass sees."""
         per = max(1, self.buffer_size // total_cls_num)
-        idx = self.herding_indices(model, x, y, per).cpu()
+        idx = self.herding_indices(model, x, y, per, transform).cpu()
         for row in idx:
             row = row[row >= 0]
             self.images.append(x[row])
@@ -70,12 +73,12 @@ class HerdingBuffer:
         return idx
 
     @torch.no_grad()
-    def class_means(self, model) -> torch.Tensor:
+    def class_means(self, model, transform=None) -> torch.Tensor:
         """`ICarl.calc_class_mean` (core/model/icarl.py:226-287): per class mean of the L2-normalised exemplar features, re-normalised."""
         dev = model.engine.device
         means = []
         for x in self.images:
-            f = self._features(model, x.to(dev))
+            f = self._features(model, x.to(dev), transform)
             m = f.mean(0)
             means.append(m / m.norm())
         return torch.stack(means)

@@ -124,6 +124,19 @@ __global__ void __launch_bounds__(256) adam_kernel(float* p, const float* g, flo
     }
 }
 
+// step counter + bias corrections kept on the device, so that a captured step needs no per-step host staging: hp[7] = t (as float), and the betas
+// once more as DOUBLES in hp[8..11] (torch.optim.Adam forms `1 - beta ** step` from the Python doubles, not from their fp32 roundings)
+//   t += 1 ; hp[5] = 1 - b1^t ; hp[6] = 1 - b2^t      (double pow, rounded to fp32 once)
+__global__ void adam_tick_kernel(float* hp) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const float t = hp[7] + 1.f;
+        const double* betas = reinterpret_cast<const double*>(hp + 8);
+        hp[7] = t;
+        hp[5] = (float)(1.0 - pow(betas[0], (double)t));
+        hp[6] = (float)(1.0 - pow(betas[1], (double)t));
+    }
+}
+
 // clip_grad_norm_ (l2p.py:104): scale = min(1, max_norm / (||g|| + 1e-6)); two launches: norm partials, then scale
 __global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* g, long long n, double* partial) {
     __shared__ double s_red[256];

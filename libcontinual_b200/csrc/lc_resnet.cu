@@ -660,6 +660,11 @@ int lc_adam(float* p, const float* g, float* m, float* v, long long n, const flo
     adam_kernel<<<kFlatBlocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hp);
     return lc_launch_status();
 }
+int lc_adam_tick(float* hp, lc_stream_t stream) {
+    LC_CHECK_ARG(hp != nullptr && ((uintptr_t)hp % 8 == 0));
+    adam_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(hp);
+    return lc_launch_status();
+}
 int lc_clip_grad_norm(float* g, long long n, float max_norm, float* scratch, float* norm_out, lc_stream_t stream) {
     LC_CHECK_ARG(g && n > 0 && scratch && ((uintptr_t)scratch % 8 == 0));
     double* part = reinterpret_cast<double*>(scratch);

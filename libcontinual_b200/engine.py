@@ -132,6 +132,10 @@ class ResNetEngine:
     def set_precision(self, precision: str):
         """'fp32': exact CUDA-core convolutions; 'tc': tcgen05 tensor-core convolutions for the stride-1 3x3 layers (TF32 operands
         for forward / data gradient, BF16 operands for the weight gradient, fp32 accumulation in TMEM)."""
+        alias = {"fp32": "fp32", "exact": "fp32", "tc": "tc", "tf32": "tc"}
+        if precision not in alias:
+            raise ValueError(f"precision must be one of {sorted(alias)} ('tf32' is an alias of 'tc'), got {precision!r}")
+        precision = alias[precision]
         mode = {"fp32": 0, "tc": 1}[precision]
         check(self.lib.lc_resnet_set_mode(self.h, mode), "lc_resnet_set_mode")
         self.precision = precision

@@ -55,7 +55,7 @@ class CifarResNet(nn.Module):
         self.engine.set_precision(precision)
         self.out_dim = 64
         self.num_batches_pending = 0
-        self._names = []
+        self._nbt = []
         eng = self.engine
         # same init distributions and the same RNG draw order as resnet.py:345-352
         for name, shape in eng.layout:
@@ -74,45 +74,33 @@ class CifarResNet(nn.Module):
             self._register_buffer(bn + ".running_var", v)
             self._register_buffer(bn + ".num_batches_tracked", torch.zeros((), dtype=torch.long))
 
-    # flat registration under dotted reference names --------------------------------------------------------------------
-    @staticmethod
-    def _key(name: str) -> str:
-        return name.replace(".", "__")
+    # registration under the reference's dotted names: a tree of bare container modules (`stage_1` -> `0` -> `conv_a` ...) whose leaves hold the arena
+    # views, so that named_parameters() / state_dict() / load_state_dict() give the reference's keys at this level AND through any parent module
+    # (nn.Module's own recursion does the work: no renaming overrides that a parent would bypass)
+    def _leaf(self, name: str):
+        *path, leaf = name.split(".")
+        mod = self
+        for part in path:
+            nxt = mod._modules.get(part)
+            if nxt is None:
+                nxt = _Node()
+                mod.add_module(part, nxt)
+            mod = nxt
+        return mod, leaf
 
     def _register(self, name, p):
-        self.register_parameter(self._key(name), p)
-        self._names.append(name)
+        mod, leaf = self._leaf(name)
+        mod.register_parameter(leaf, p)
 
     def _register_buffer(self, name, b):
-        self.register_buffer(self._key(name), b)
+        mod, leaf = self._leaf(name)
+        mod.register_buffer(leaf, b)
+        if leaf == "num_batches_tracked":
+            self._nbt.append(b)
 
-    def named_parameters(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True):
-        for k, p in super().named_parameters(prefix="", recurse=recurse, remove_duplicate=remove_duplicate):
-            yield (prefix + ("." if prefix else "") + k.replace("__", ".")), p
-
-    def named_buffers(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True):
-        for k, b in super().named_buffers(prefix="", recurse=recurse, remove_duplicate=remove_duplicate):
-            yield (prefix + ("." if prefix else "") + k.replace("__", ".")), b
-
-    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+    def state_dict(self, *args, **kwargs):
         self._flush_num_batches()
-        sd = super().state_dict(*args, destination=None, prefix="", keep_vars=keep_vars)
-        out = destination if destination is not None else type(sd)()
-        for k, v in sd.items():
-            out[prefix + k.replace("__", ".")] = v
-        return out
-
-    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
-        own = {k.replace("__", "."): v for k, v in super().state_dict(keep_vars=True).items()}
-        missing = [k for k in own if k not in state_dict]
-        unexpected = [k for k in state_dict if k not in own]
-        if strict and (missing or unexpected):
-            raise RuntimeError(f"load_state_dict: missing {missing[:4]}..., unexpected {unexpected[:4]}...")
-        with torch.no_grad():
-            for k, v in state_dict.items():
-                if k in own:
-                    own[k].copy_(v)      # in place: the arenas keep owning the storage
-        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+        return super().state_dict(*args, **kwargs)
 
     def _apply(self, fn, recurse=True):
         # parameters are views into the engine arenas: moving/casting them would silently detach them from the kernels
@@ -126,8 +114,8 @@ class CifarResNet(nn.Module):
 
     def _flush_num_batches(self):
         if self.num_batches_pending:
-            for bn in self.engine.bn_names:
-                getattr(self, self._key(bn + ".num_batches_tracked")).add_(self.num_batches_pending)
+            for t in self._nbt:
+                t.add_(self.num_batches_pending)
             self.num_batches_pending = 0
 
     # reference interface -------------------------------------------------------------------------------------------------
@@ -142,6 +130,11 @@ class CifarResNet(nn.Module):
 
     def feature(self, x):
         return self.forward(x)["features"]
+
+
+class _Node(nn.Module):
+    """Bare container (one path component of a reference parameter name).  Loading copies IN PLACE (nn.Module's default for
+    parameters and buffers), so the arenas keep owning the storage."""
 
 
 class _NoCtx:

@@ -73,6 +73,24 @@ def _draw_linear(in_f: int, out_f: int):
     return m.weight.data, m.bias.data
 
 
+def _raw_task_samples(dataset):
+    """Every item of a task dataset, untransformed, in dataset order: `(images, labels)` tensors.  Tensor-backed datasets expose `.images` / `.labels`
+    (the reference's datasets hold image PATHS under the same attribute names, core/data/dataset.py:232-266); anything else is indexed item by item
+    with its transform switched off for the duration."""
+    imgs, labels = getattr(dataset, "images", None), getattr(dataset, "labels", None)
+    if torch.is_tensor(imgs) and labels is not None:
+        return imgs, torch.as_tensor(labels, dtype=torch.int64)
+    saved = getattr(dataset, "trfms", None)
+    if saved is not None:
+        dataset.trfms = None
+    try:
+        items = [dataset[i] for i in range(len(dataset))]
+    finally:
+        if saved is not None:
+            dataset.trfms = saved
+    return torch.stack([torch.as_tensor(d["image"]) for d in items]), torch.as_tensor([int(d["label"]) for d in items], dtype=torch.int64)
+
+
 class _ResNetMethod(nn.Module):
     def __init__(self, backbone, feat_dim, num_class, **kwargs):
         super().__init__()
@@ -291,23 +309,51 @@ class ICarl(_ResNetMethod):
     def after_task(self, task_idx, buffer, train_loader, test_loaders):
         """icarl.py:169-191: freeze the teacher, shrink + refill the exemplar memory by herding, recompute the class means."""
         self.snapshot_teacher()
+        val_transform = None
+        if test_loaders:
+            val_transform = getattr(test_loaders[0].dataset, "trfms", None)
         if buffer is not None and hasattr(buffer, "herding_indices") and train_loader is not None:
-            # tensor-backed memory (libcontinual_b200.buffer.HerdingBuffer): current-task samples, class-sorted
-            xs, ys = [], []
-            for data in train_loader:
-                xs.append(data["image"]); ys.append(data["label"])
-            x, y = torch.cat(xs), torch.cat(ys)
-            keep = (y >= int(self.cur_cls_indexes[0])) & (y <= int(self.cur_cls_indexes[-1]))     # drop replayed exemplars
+            # tensor-backed memory (libcontinual_b200.buffer.HerdingBuffer).  Like linearherdingbuffer.py:94-111 the pool is the task's DATASET, not
+            # the training loader: raw items in dataset order (no shuffle, nothing dropped, no training augmentation), replayed exemplars removed,
+            # features taken under the validation transform; the raw items are what gets stored.
+            x, y = _raw_task_samples(train_loader.dataset)
+            keep = (y >= int(self.cur_cls_indexes[0])) & (y <= int(self.cur_cls_indexes[-1]))
             x, y = x[keep], y[keep]
-            order = torch.sort(y, stable=True)[1]
+            order = torch.sort(y, stable=True)[1]             # remove_buffer_sample_in_dataset regroups by class, order kept inside a class
             buffer.reduce_old_data(self.cur_task_id, self.accu_cls_num)
-            buffer.update(self, x[order], y[order], self.accu_cls_num)
-            self.class_means = buffer.class_means(self).to(self.engine.device).contiguous()
+            buffer.update(self, x[order], y[order], self.accu_cls_num, transform=val_transform)
+            self.class_means = buffer.class_means(self, transform=val_transform).to(self.engine.device).contiguous()
         elif buffer is not None and hasattr(buffer, "reduce_old_data"):
+            # a reference-style path buffer (core/model/buffer/linearherdingbuffer.py): its own update, then icarl.py:187-190
             buffer.reduce_old_data(self.cur_task_id, self.accu_cls_num)
-            val_transform = test_loaders[0].dataset.trfms
             buffer.update(self.network, train_loader, val_transform, self.cur_task_id, self.accu_cls_num, self.cur_cls_indexes, self.device)
+            self.class_means = self.calc_class_mean(buffer, train_loader, val_transform, self.device).to(self.engine.device).contiguous()
         self.cur_task_id += 1
+
+    @torch.no_grad()
+    def calc_class_mean(self, buffer, train_loader, val_transform, device):
+        """icarl.py:226-287 for a buffer of image paths: decode every stored exemplar under the validation transform, per class the mean of the
+        L2-normalised backbone features, re-normalised."""
+        import os
+        import PIL.Image
+        ds = train_loader.dataset
+        root, mode = ds.data_root, ds.mode
+        was = self.backbone.training
+        self.backbone.eval()
+        feats, labels = [], []
+        bs = train_loader.batch_size or 32
+        for i in range(0, len(buffer.labels), bs):
+            imgs = [val_transform(PIL.Image.open(os.path.join(root, mode, pth)).convert("RGB")) for pth in buffer.images[i:i + bs]]
+            f = self.backbone(torch.stack(imgs))["features"]
+            feats.append((f / f.norm(dim=1).view(-1, 1)).cpu())
+            labels.extend(int(l) for l in buffer.labels[i:i + bs])
+        self.backbone.train(was)
+        feats, labels = torch.cat(feats), np.asarray(labels)
+        means = []
+        for c in np.unique(labels):
+            m = feats[np.where(labels == c)[0]].mean(0)
+            means.append(m / m.norm())
+        return torch.stack(means)
 
     def _launch_step(self, x, y):
         kd = self.cur_task_id > 0 and self.old_network is not None

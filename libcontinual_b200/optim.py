@@ -76,7 +76,7 @@ class Adam(torch.optim.Optimizer):
         self.model = model
         self.m = torch.zeros_like(model.theta)
         self.v = torch.zeros_like(model.theta)
-        self.hp = torch.zeros(8, device=model.theta.device)
+        self.hp = torch.zeros(12, device=model.theta.device)      # [0..7] fp32 (see `hyper`), [8..11] = (beta1, beta2) as float64 for `lc_adam_tick`
         self.t = 0
         from . import _lib
         self.lib = _lib.load()
@@ -84,7 +84,7 @@ class Adam(torch.optim.Optimizer):
     def hyper(self, t: int):
         g = self.param_groups[0]
         b1, b2 = g["betas"]
-        return [float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]), 1.0 - b1 ** t, 1.0 - b2 ** t, 0.0]
+        return [float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]), 1.0 - b1 ** t, 1.0 - b2 ** t, float(t)]
 
     def zero_grad(self, set_to_none: bool = True):
         # gradients are overwritten (not accumulated) by the model's backward kernels
@@ -96,7 +96,7 @@ class Adam(torch.optim.Optimizer):
     def step(self, closure=None):
         mdl = self.model
         self.t += 1
-        self.hp.copy_(torch.tensor(self.hyper(self.t), dtype=torch.float32), non_blocking=False)
+        self.hp[:8].copy_(torch.tensor(self.hyper(self.t), dtype=torch.float32), non_blocking=False)
         base = mdl.theta.data_ptr()
         for grp in self.param_groups:
             for p in grp["params"]:
@@ -108,9 +108,12 @@ class Adam(torch.optim.Optimizer):
         self.launch()
         return None
 
-    def launch(self):
-        """The update kernel alone (hp already on the device): what a captured step replays."""
+    def launch(self, tick: bool = False):
+        """The update kernel alone (hp already on the device): what a captured step replays.  tick=True puts the device-side step counter
+        (`lc_adam_tick`: t += 1 and the two bias corrections) in front of it, so that a replayed graph needs no per-step host staging."""
         mdl = self.model
+        if tick:
+            check(self.lib.lc_adam_tick(self.hp.data_ptr(), torch.cuda.current_stream().cuda_stream), "adam_tick")
         check(self.lib.lc_adam(mdl.theta.data_ptr(), mdl.theta_grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), mdl.theta.numel(),
                                self.hp.data_ptr(), torch.cuda.current_stream().cuda_stream), "adam")
 

@@ -19,6 +19,34 @@ from .optim import SGD, Adam
 from .parallel import allreduce_mean_
 
 
+def _capture_with_collective(launch_fwd_bwd, flat_grads, launch_update, pg, world):
+    """One step as CUDA graph(s).  world == 1: one graph.  world > 1: forward/backward, the gradient all-reduce (NCCL average over NVLink/NVSwitch — NCCL
+    collectives are capturable) and the optimizer kernels in ONE graph, so a step is a single graph launch with no host work between backward and update
+    (at 16 images per GPU the whole step is ~1 ms and a second graph launch plus an eager collective would be a tenth of it).
+    `LC_DP_COLLECTIVE=eager` keeps the collective outside (two graphs).  Returns (g_main, g_upd, description)."""
+    import os
+    g_main = torch.cuda.CUDAGraph()
+    if world == 1:
+        with torch.cuda.graph(g_main):
+            launch_fwd_bwd()
+            launch_update()
+        return g_main, None, "none (single replica)"
+    if os.environ.get("LC_DP_COLLECTIVE", "graph") != "eager":
+        allreduce_mean_(flat_grads, pg)                       # communicator and NCCL buffers exist before capture starts
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g_main):
+            launch_fwd_bwd()
+            allreduce_mean_(flat_grads, pg)
+            launch_update()
+        return g_main, None, f"ncclAvg all-reduce of the flat gradient arena ({flat_grads.numel() * 4} B, one bucket) captured inside the step's CUDA graph"
+    with torch.cuda.graph(g_main):
+        launch_fwd_bwd()
+    g_upd = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_upd):
+        launch_update()
+    return g_main, g_upd, f"eager ncclAvg all-reduce of the flat gradient arena ({flat_grads.numel() * 4} B, one bucket) between two CUDA graphs"
+
+
 def train_step_eager(model, optimizer, batch):
     """trainer.py:601-612, default branch."""
     pred, acc, loss = model.observe(batch)
@@ -40,6 +68,9 @@ class GraphedStep:
         self.x = torch.zeros(batch_size, eng.in_ch, eng.img, eng.img, device=dev)
         self.y = torch.zeros(batch_size, dtype=torch.int64, device=dev)
         self._sync_hp()
+        # param groups beyond the first must be frozen ranges (LUCIR's old-class embedding, lucir.py:229-240): the captured update skips them exactly
+        # like the eager `SGD.step` does; anything else raises here instead of silently training with group 0's hyper-parameters
+        self._frozen = optimizer._frozen_range()
         # warm-up on a side stream (sets func attributes, primes the allocator), then capture
         pending0 = model.backbone.num_batches_pending
         side = torch.cuda.Stream(device=dev)
@@ -53,17 +84,8 @@ class GraphedStep:
         torch.cuda.synchronize(dev)
         eng.params.copy_(saved[0]); eng.rstat.copy_(saved[1]); optimizer.buf.copy_(saved[2])
         l0 = eng.launches
-        self.g_main = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_main):
-            self._fwd_bwd()
-            if self.world == 1:
-                self._update()
-        self.g_upd = None
-        if self.world > 1:
-            self.g_upd = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_upd):
-                self._update()
-        self.launches_per_step = eng.launches - l0
+        self.g_main, self.g_upd, self.collective = _capture_with_collective(self._fwd_bwd, eng.grads, self._update, self.pg, self.world)
+        self.launches_per_step = eng.launches - l0 + (1 if self.world > 1 else 0)
         model.backbone.num_batches_pending = pending0      # warm-up / capture launches restored above do not count
         self.steps = 0
 
@@ -78,7 +100,7 @@ class GraphedStep:
         self.model._launch_step(self.x, self.y)
 
     def _update(self):
-        self.eng.sgd_step(self.opt.buf, self.opt.hp)
+        self.eng.sgd_step(self.opt.buf, self.opt.hp, frozen=self._frozen)
 
     def run(self, x: torch.Tensor, y: torch.Tensor, non_blocking: bool = True):
         """One step on a batch that is either device-resident or in (pinned) host memory.  Returns nothing: read
@@ -87,7 +109,7 @@ class GraphedStep:
         self.x.copy_(x, non_blocking=non_blocking)
         self.y.copy_(y, non_blocking=non_blocking)
         self.g_main.replay()
-        if self.world > 1:
+        if self.g_upd is not None:
             allreduce_mean_(self.eng.grads, self.pg)
             self.g_upd.replay()
         self.steps += 1
@@ -153,32 +175,30 @@ class GraphedL2PStep:
         dev = self.eng.dev
         self.x = torch.zeros(batch_size, 3, 224, 224, device=dev)
         self.y = torch.zeros(batch_size, dtype=torch.int64, device=dev)
-        self.hp_host = torch.zeros(8, dtype=torch.float32).pin_memory()
-        self._stage_hp(1)
+        self._hp_static = None
+        self._t_dev = None
+        self._stage_hp()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         saved = (model.theta.clone(), optimizer.m.clone(), optimizer.v.clone())
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 model._launch_step(self.x, self.y, clip=True)
-                optimizer.launch()
+                optimizer.launch(tick=True)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         model.theta.copy_(saved[0]); optimizer.m.copy_(saved[1]); optimizer.v.copy_(saved[2])
+        self._t_dev = None
+        self._stage_hp()
         l0 = self.eng.launches
-        self.g_main = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_main):
-            model._launch_step(self.x, self.y, clip=self.world == 1)
-            if self.world == 1:
-                optimizer.launch()
-        self.g_upd = None
-        if self.world > 1:
-            self.g_upd = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_upd):
-                if self.has_clip:
-                    model._launch_clip()
-                optimizer.launch()
-        self.launches_per_step = self.eng.launches - l0 + 1
+
+        def upd():
+            if self.has_clip:
+                model._launch_clip()               # non-linear in g: runs on the REDUCED gradient (l2p.py:104 after DDP's averaging)
+            optimizer.launch(tick=True)
+        self.g_main, self.g_upd, self.collective = _capture_with_collective(lambda: model._launch_step(self.x, self.y, clip=False), model.theta_grad, upd,
+                                                                            self.pg, self.world)
+        self.launches_per_step = self.eng.launches - l0 + 2 + (1 if self.world > 1 else 0)
         self.steps = 0
         self.stager = _InputStager(self.x, self.y)
 
@@ -186,16 +206,26 @@ class GraphedL2PStep:
         """Optional: start the host -> device copy of the batch that the NEXT `run` will be given."""
         self.stager.prefetch(x, y)
 
-    def _stage_hp(self, t: int):
-        self.hp_host.copy_(torch.tensor(self.opt.hyper(t), dtype=torch.float32))
-        self.opt.hp.copy_(self.hp_host, non_blocking=True)
+    def _stage_hp(self):
+        """Hyper-parameters reach the device only when they CHANGE (scheduler step), through a pageable-source copy that is complete for the host
+        when it returns; the step count and both bias corrections live on the device (`lc_adam_tick` inside the graph), so a replay that runs
+        behind the host can never see a later step's values (the race a re-used pinned staging buffer would have)."""
+        h = self.opt.hyper(max(self.opt.t, 1))
+        if self._hp_static != h[:5]:
+            self.opt.hp[:5].copy_(torch.tensor(h[:5], dtype=torch.float32))
+            self.opt.hp[8:12].view(torch.float64).copy_(torch.tensor(h[1:3], dtype=torch.float64))     # betas as doubles for the device-side 1 - beta^t
+            self._hp_static = h[:5]
+        if self._t_dev != self.opt.t:                    # (re)seed the device counter: construction, or eager steps taken in between
+            self.opt.hp[7:8].copy_(torch.tensor([float(self.opt.t)], dtype=torch.float32))
+            self._t_dev = self.opt.t
 
     def run(self, x: torch.Tensor, y: torch.Tensor, non_blocking: bool = True):
+        self._stage_hp()
         self.opt.t += 1
-        self._stage_hp(self.opt.t)
+        self._t_dev = self.opt.t                         # the graph's tick kernel advances the device counter
         self.stager.load(x, y, self.x, self.y, non_blocking)
         self.g_main.replay()
-        if self.world > 1:
+        if self.g_upd is not None:
             allreduce_mean_(self.model.theta_grad, self.pg)
             self.g_upd.replay()
         self.steps += 1
@@ -234,17 +264,9 @@ class GraphedFlatStep:
         torch.cuda.synchronize(dev)
         model.theta.copy_(saved[0]); optimizer.buf.copy_(saved[1])
         l0 = self.eng.launches
-        self.g_main = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_main):
-            model._launch_step(self.x, self.y)
-            if self.world == 1:
-                optimizer.launch()
-        self.g_upd = None
-        if self.world > 1:
-            self.g_upd = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_upd):
-                optimizer.launch()
-        self.launches_per_step = self.eng.launches - l0 + len(model.active_ranges())
+        self.g_main, self.g_upd, self.collective = _capture_with_collective(lambda: model._launch_step(self.x, self.y), model.theta_grad, optimizer.launch,
+                                                                            self.pg, self.world)
+        self.launches_per_step = self.eng.launches - l0 + len(model.active_ranges()) + (1 if self.world > 1 else 0)
         self.steps = 0
         self.stager = _InputStager(self.x, self.y)
 
@@ -256,7 +278,7 @@ class GraphedFlatStep:
         self.opt.sync_hp()
         self.stager.load(x, y, self.x, self.y, non_blocking)
         self.g_main.replay()
-        if self.world > 1:
+        if self.g_upd is not None:
             allreduce_mean_(self.model.theta_grad, self.pg)
             self.g_upd.replay()
         self.steps += 1

@@ -411,10 +411,20 @@ def test_icarl_after_task_herding_and_ncm_vs_oracle():
     y = torch.arange(4).repeat_interleave(n_per)
     x = torch.from_numpy(rng.standard_normal((4 * n_per, 3, 32, 32)).astype(np.float32))
     perm = torch.from_numpy(rng.permutation(4 * n_per))
-    loader = [{"image": x[perm][i:i + 32], "label": y[perm][i:i + 32]} for i in range(0, 4 * n_per, 32)]
+
+    class _DS:                      # tensor-backed task dataset: raw items under the reference's attribute names (dataset.py:232-266)
+        images, labels, trfms = x[perm], y[perm], None
+
+    class _Loader:                  # what TRAINING sees: augmented (flipped), shuffled, ragged tail dropped — none of which may reach the herding pool
+        dataset, batch_size = _DS, 32
+
+        def __iter__(self):
+            sh = torch.from_numpy(np.random.default_rng(5).permutation(4 * n_per))
+            return iter([{"image": x[perm][sh][i:i + 32].flip(3), "label": y[perm][sh][i:i + 32]} for i in range(0, 4 * n_per - 31, 32)])
+
     buf = HerdingBuffer(buffer_size=40)
     m.eval()
-    m.after_task(0, buf, loader, None)
+    m.after_task(0, buf, _Loader(), None)
     # oracle: same class-sorted data, eval-mode features in batches of 32, normalised, greedy herding
     order = torch.sort(y[perm], stable=True)[1]
     xs, ys = x[perm][order], y[perm][order]
