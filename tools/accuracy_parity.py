@@ -29,11 +29,16 @@ def make_stream(seed, steps, n_test, bs=32, n_tasks=2, cpt=10, amp=1.0):
     return train, test
 
 
+METHOD, LR, AMP = "ewc", 0.1, 1.0
+
+
 def run_ours(p, b, fc_w, fc_b, train, test, precision):
     import libcontinual_b200.model as M
     from libcontinual_b200.optim import SGD
     bb = M.cifar_resnet32(max_batch=256, precision=precision)
     bb.load_state_dict({**p, **b}, strict=True)
+    if METHOD == "lwf":
+        return run_ours_lwf(bb, fc_w, fc_b, train, test)
     m = M.EWC(bb, 64, 100, device=torch.device("cuda"), init_cls_num=10, inc_cls_num=10, lamda=1000.0)
 
     class Loader(list):
@@ -44,11 +49,15 @@ def run_ours(p, b, fc_w, fc_b, train, test, precision):
         w, bias = m.engine.fc_views(n)
         w[10 * t:].copy_(fc_w[10 * t:n].cuda()); bias[10 * t:].copy_(fc_b[10 * t:n].cuda())
         m.train()
-        opt = SGD(m.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4, engine=m.engine)
+        opt = SGD(m.get_parameters(None), lr=LR, momentum=0.9, weight_decay=5e-4, engine=m.engine)
         for x, y in batches:
             pred, acc, loss = m.observe({"image": x, "label": y})
             opt.zero_grad(); loss.backward(); opt.step()
         m.after_task(t, None, Loader([{"image": x, "label": y} for x, y in batches]), None)
+    return eval_ours(m, test)
+
+
+def eval_ours(m, test):
     m.eval()
     accs = []
     for x, y in test:
@@ -60,17 +69,38 @@ def run_ours(p, b, fc_w, fc_b, train, test, precision):
     return accs
 
 
+def run_ours_lwf(bb, fc_w, fc_b, train, test):
+    """LwF (lwf.py:52-70: CE on the new slice + 3 * KD(T=2) against the frozen previous model), same stream."""
+    import libcontinual_b200.model as M
+    from libcontinual_b200.optim import SGD
+    m = M.LWF(bb, 64, 100, device=torch.device("cuda"), init_cls_num=10, inc_cls_num=10)
+    for t, batches in enumerate(train):
+        m.before_task(t, None, None, None)
+        n = 10 * (t + 1)
+        w, bias = m.engine.fc_views(n)
+        w[10 * t:].copy_(fc_w[10 * t:n].cuda()); bias[10 * t:].copy_(fc_b[10 * t:n].cuda())
+        m.train()
+        opt = SGD(m.get_parameters(None), lr=LR, momentum=0.9, weight_decay=5e-4, engine=m.engine)
+        for x, y in batches:
+            pred, acc, loss = m.observe({"image": x, "label": y})
+            opt.zero_grad(); loss.backward(); opt.step()
+    return eval_ours(m, test)
+
+
 def run_oracle(p, b, fc_w, fc_b, train, test):
     from oracle import port
     torch.set_num_threads(os.cpu_count() or 1)
-    orc = port.ResNetMethodOracle("ewc", p, b, fc_w[:10], fc_b[:10], init_cls=10, inc_cls=10, lamda=1000.0)
+    orc = port.ResNetMethodOracle(METHOD, p, b, fc_w[:10], fc_b[:10], init_cls=10, inc_cls=10, lamda=1000.0, lr=LR)
     for t, batches in enumerate(train):
         if t > 0:
+            if METHOD == "lwf":
+                orc.snapshot_teacher(); orc.prev_cls = 10 * t
             orc.task_idx = t
             orc.grow_head(fc_w[:10 * (t + 1)], fc_b[:10 * (t + 1)]); orc.reset_optimizer()
         for x, y in batches:
             orc.step(x, y)
-        orc.ewc_after_task(batches, 32)
+        if METHOD == "ewc":
+            orc.ewc_after_task(batches, 32)
     accs = []
     with torch.no_grad():
         for x, y in test:
@@ -86,7 +116,7 @@ def one_seed(seed, steps, n_test):
     bound = 1.0 / 8.0
     fc_w = torch.from_numpy(rng.uniform(-bound, bound, (20, 64)).astype(np.float32))
     fc_b = torch.from_numpy(rng.uniform(-bound, bound, (20,)).astype(np.float32))
-    train, test = make_stream(2000 + seed, steps, n_test)
+    train, test = make_stream(2000 + seed, steps, n_test, amp=AMP)
     # control arm: the SAME oracle from initial weights moved by one fp32 ulp (relative 6e-8) — how far the reference's final accuracy moves under a
     # perturbation no implementation can be asked to reproduce
     prng = np.random.default_rng(3000 + seed)
@@ -105,10 +135,20 @@ def main():
     ap.add_argument("steps", nargs="?", type=int, default=60)
     ap.add_argument("n_test", nargs="?", type=int, default=1000)
     ap.add_argument("--seeds", type=int, default=1)
+    ap.add_argument("--method", default="ewc", choices=["ewc", "lwf"])
+    ap.add_argument("--lr", type=float, default=0.1)
+    ap.add_argument("--amp", type=float, default=1.0, help="class-template amplitude against unit noise")
+    ap.add_argument("--oracle-only", action="store_true", help="CPU: only the oracle and its 1-ulp control arm (stream design)")
     a = ap.parse_args()
+    global METHOD, LR, AMP
+    METHOD, LR, AMP = a.method, a.lr, a.amp
+    if a.oracle_only:
+        global run_ours
+        run_ours = lambda *args, **kw: [float("nan")]
     rows = [one_seed(s, a.steps, a.n_test) for s in range(a.seeds)]
     arms = list(rows[0])
-    res = {"stream": f"EWC cifar_resnet32, 2 tasks x 10 classes, {a.steps} steps/task, bs 32, SGD 0.1/0.9/5e-4, lamda 1000, test {a.n_test}/task "
+    res = {"stream": f"{METHOD.upper()} cifar_resnet32, 2 tasks x 10 classes, {a.steps} steps/task, bs 32, SGD {LR}/0.9/5e-4, "
+                     + ("lamda 1000, " if METHOD == "ewc" else "KD weight 3 T 2, ") + f"template amplitude {AMP}, test {a.n_test}/task "
                      f"(synthetic class templates + N(0,1) noise); {a.seeds} seeds (weights and data re-drawn per seed); metric = final average accuracy (%)",
            "per_seed": rows}
     for arm in arms:
