@@ -174,8 +174,23 @@ typedef struct lc_gemm_desc {
     float alpha;
     int gelu_mode;              /* bit 0: the GELU side tensor is GELU'(pre-activation): with out2, C stores it instead of the pre-activation; with
                                  * gelu_bwd_aux, aux is a plain multiplier.  bit 1 (with out2): C is not stored at all (no-grad passes).  0 = as above. */
+    int ksplit;                 /* > 1: split-K — the K blocks are divided over ksplit fp32 partial outputs, partial s at C + s * strideC_split
+                                 * (out_f32 must be 1, no epilogue extras; every split gets at least one K block: ksplit <= ceil(K / 64)) */
+    long long strideC_split;
 } lc_gemm_desc;
 int lc_gemm_bf16_ex(const lc_gemm_desc* desc, int* error_flag, lc_stream_t stream);
+
+/* Implicit-GEMM convolution on the same kernel (F.conv2d of resnet.py:48-64 BasicBlock / :133-150 stem, and its stride-1 data gradient):
+ *   Y[(n, ho, wo)][co] = sum_{kh, kw, c} X[n][ho*stride - pad + kh][wo*stride - pad + kw][c] * Wk[co][(kh*ks + kw)*C + c]  (+ bias, + residual)
+ * X: BF16 NHWC, C % 64 == 0; Wk: BF16 [Cout][ks*ks*C] (lc_nn_pack_weight, tap-major); Y: fp32 or BF16 [N*Ho*Wo][ldc].  The producer warp reads X
+ * through a rank-4 tensor map {C, W, H, N} whose box is one 128-pixel output tile; the filter tap is a coordinate offset of the box and the zero
+ * padding is TMA's out-of-bounds fill, so no im2col matrix is ever written.  Wo must divide 128 and Ho*Wo must divide or be a multiple of 128. */
+typedef struct lc_conv_desc {
+    const void* X; const void* Wk; void* Y;
+    const float* bias; const float* residual; long long ldc, ldr;
+    int N, H, W, C, Cout, ks, stride, pad, Ho, Wo, out_f32;
+} lc_conv_desc;
+int lc_conv_gemm_bf16(const lc_conv_desc* desc, int* error_flag, lc_stream_t stream);
 /* Row-wise / layout kernels of the ViT forward (transformer.py:2222-2261): im2col of the 16x16 patches (timm PatchEmbed as a GEMM), cls-row
  * assembly, LayerNorm (fp32 in -> bf16 and/or fp32 out, optional (mean, rstd) per row), mean over a row range (L2P: the prompt positions, transformer.py:2256-2259), fp32 linear head,
  * fp32 -> bf16 cast. */
@@ -305,6 +320,49 @@ int lc_bn_act_forward(const float* y, const float* scale, const float* shift, co
  * mean, invstd}.  Writes dy, dgamma[C], dbeta[C]; g_out (nullable) receives the masked g.  scratch >= 592*2*C + 3*C + 64. */
 int lc_bn_backward(const float* g, const float* mask_src, int mask_mode, const float* y, const float* stat, float* dy, float* g_out,
                    float* dgamma, float* dbeta, long long npix, int C, float* scratch, lc_stream_t stream);
+
+
+/* ---- generic layer kernels for ResNet18 (resnet.py:26-64,110-246; LwF lwf.py:52-70) and AlexNet_TRGP (alexnet.py:94-156; GPM gpm.py:45-204) --------
+ * Activations NHWC; a conv output is the row-major matrix [M = N*Ho*Wo][Cout] the GEMM epilogue writes.  korder: 0 = k = (kh*ks + kw)*C + c (tap-major,
+ * what lc_conv_gemm_bf16 contracts over), 1 = k = (c*ks + kh)*ks + kw (= weight.view(Cout, -1), the order of GPM's bases, gpm.py:79,163-168).
+ * src_kind: 0 NHWC bf16, 1 NCHW fp32 (network input), 2 NHWC fp32. */
+long long lc_nn_bn_scratch_floats(int C);
+/* Patch matrix of F.conv2d's input: col [M][ld_col] and / or its transpose colT [Kp][ld_colT] (BF16; columns / rows beyond K and M are zero).  Also GPM's
+ * representation matrix (the Python triple loop of gpm.py:157-168) when called with korder = 1. */
+int lc_nn_im2col(const void* src, int src_kind, int N, int H, int W, int C, int ks, int stride, int pad, int korder, void* col_bf16, long long ld_col,
+                 void* colT_bf16, long long ld_colT, int Kp, lc_stream_t stream);
+/* Data gradient of a conv from dcol = dY * W ([M][ld] BF16): dx (fp32 NHWC) = addend + fold(dcol). */
+int lc_nn_col2im(const void* dcol_bf16, long long ld, const float* addend, float* dx, int N, int H, int W, int C, int ks, int stride, int pad, int korder,
+                 lc_stream_t stream);
+/* nn.BatchNorm2d / 1d in train mode over y [M][C] (C % 64 == 0): aff = [scale | shift | mean | invstd]; running = [mean | var] updated when non-null
+ * (momentum, unbiased variance); gamma / beta nullable.  scratch >= lc_nn_bn_scratch_floats(C).  Deterministic (fixed-order fp64 finalize). */
+int lc_nn_bn_stats(const float* y, long long M, int C, const float* gamma, const float* beta, float eps, float momentum, float* running, float* aff,
+                   float* scratch, lc_stream_t stream);
+int lc_nn_bn_eval_affine(const float* running, int C, const float* gamma, const float* beta, float eps, float* aff, lc_stream_t stream);
+/* out = dropout(relu(y*scale + shift + [res | res*res_scale + res_shift])): BF16 and / or fp32.  Dropout (alexnet.py:130,136,142,149,154): keep mask =
+ * counter-based hash of (rng[0] = seed, rng[1] = step, rng_stream = layer, element index), survivors scaled by 1/(1-p); rng == NULL or p == 0: off. */
+int lc_nn_bn_act(const float* y, const float* aff, const float* res, const float* res_aff, long long M, int C, int relu, float drop_p,
+                 const unsigned long long* rng, int rng_stream, void* out_bf16, float* out_f32, lc_stream_t stream);
+int lc_nn_dropout_mask(const unsigned long long* rng, int rng_stream, float drop_p, long long n, unsigned char* keep, lc_stream_t stream);
+int lc_nn_rng_advance(unsigned long long* rng, lc_stream_t stream);
+/* native_batch_norm_backward + threshold_backward (+ dropout): dz = g * [act > 0] * gscale (act = the stored layer output; NULL, NULL: no mask);
+ * dgamma = sum dz*xhat, dbeta = sum dz; dy = scale*(dz - dbeta/M - xhat*dgamma/M) as BF16 and / or fp32; dz_out (nullable) = dz. */
+int lc_nn_bn_backward(const float* g, const float* act_f32, const void* act_bf16, float gscale, const float* y, const float* aff, long long M, int C,
+                      float* dgamma, float* dbeta, void* dy_bf16, float* dy_f32, float* dz_out, float* scratch, lc_stream_t stream);
+/* nn.MaxPool2d(k, stride, pad) on fp32 NHWC; idx keeps the window position of the (first) maximum for the backward. */
+int lc_nn_maxpool_forward(const float* in, int N, int H, int W, int C, int k, int stride, int pad, float* out_f32, void* out_bf16, unsigned char* idx,
+                          lc_stream_t stream);
+int lc_nn_maxpool_backward(const float* g, const unsigned char* idx, int N, int H, int W, int C, int k, int stride, int pad, float* dx, lc_stream_t stream);
+/* nn.AdaptiveAvgPool2d((1, 1)) over fp32 NHWC [N][HW][C] and its backward. */
+int lc_nn_avgpool_forward(const float* in, int N, int HW, int C, float* out, lc_stream_t stream);
+int lc_nn_avgpool_backward(const float* dfeat, int N, int HW, int C, float* dx, lc_stream_t stream);
+/* OIHW fp32 weights -> BF16 GEMM operands.  mode 0: [Cout][K] (korder); 1: [K][Cout] (B operand of dcol = dY * W); 2: [Cin][flipped taps][Cout]
+ * (stride-1 data gradient as a convolution of dY).  Row length ld, tail zero. */
+int lc_nn_pack_weight(const float* w, int Cout, int Cin, int ks, int korder, int mode, void* out_bf16, long long ld, lc_stream_t stream);
+/* dW (OIHW fp32) = sum of nsplit split-K partials [nsplit][Cout][ldp] (columns in korder), fixed order. */
+int lc_nn_wgrad_reduce(const float* partial, int nsplit, int Cout, int Cin, int ks, int korder, long long ldp, float* dw, lc_stream_t stream);
+/* fp32 [rows][cols] -> BF16 [rows][ld] and / or its transpose [cols][ldT] (tails zero). */
+int lc_nn_cast_transpose(const float* src, long long rows, int cols, void* out_bf16, long long ld, void* outT_bf16, long long ldT, lc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,23 @@ SIGNATURES = {
     "lc_gemm_bf16": (c_int, [P, c_int, c_longlong, P, c_int, c_longlong, P, c_int, c_longlong, c_int, c_int, c_int, c_int, P, P, c_int, c_longlong, P, c_int,
                              c_float, P, P]),
     "lc_gemm_bf16_ex": (c_int, [P, P, P]),
+    "lc_conv_gemm_bf16": (c_int, [P, P, P]),
+    "lc_nn_bn_scratch_floats": (c_longlong, [c_int]),
+    "lc_nn_im2col": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_longlong, P, c_longlong, c_int, P]),
+    "lc_nn_col2im": (c_int, [P, c_longlong, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "lc_nn_bn_stats": (c_int, [P, c_longlong, c_int, P, P, c_float, c_float, P, P, P, P]),
+    "lc_nn_bn_eval_affine": (c_int, [P, c_int, P, P, c_float, P, P]),
+    "lc_nn_bn_act": (c_int, [P, P, P, P, c_longlong, c_int, c_int, c_float, P, c_int, P, P, P]),
+    "lc_nn_dropout_mask": (c_int, [P, c_int, c_float, c_longlong, P, P]),
+    "lc_nn_rng_advance": (c_int, [P, P]),
+    "lc_nn_bn_backward": (c_int, [P, P, P, c_float, P, P, c_longlong, c_int, P, P, P, P, P, P, P]),
+    "lc_nn_maxpool_forward": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "lc_nn_maxpool_backward": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "lc_nn_avgpool_forward": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "lc_nn_avgpool_backward": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "lc_nn_pack_weight": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, c_longlong, P]),
+    "lc_nn_wgrad_reduce": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_longlong, P, P]),
+    "lc_nn_cast_transpose": (c_int, [P, c_longlong, c_int, P, c_longlong, P, c_longlong, P]),
     "lc_attn_forward": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
     "lc_attn_backward": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P]),
     "lc_attn_forward_prefix": (c_int, [P, P, P, c_int, c_int, c_int, P, P, c_int, P, P]),
@@ -108,7 +125,14 @@ class GemmDesc(ctypes.Structure):
                 ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_longlong), ("strideR_in", c_longlong), ("strideR_out", c_longlong),
                 ("out2", c_void_p), ("gelu_bwd_aux", c_void_p),
                 ("M", c_int), ("N", c_int), ("K", c_int), ("batch_in", c_int), ("batch_out", c_int), ("out_f32", c_int),
-                ("alpha", c_float), ("gelu_mode", c_int)]
+                ("alpha", c_float), ("gelu_mode", c_int), ("ksplit", c_int), ("strideC_split", c_longlong)]
+
+
+class ConvDesc(ctypes.Structure):
+    """`lc_conv_desc` of include/lc_b200.h."""
+    _fields_ = [("X", c_void_p), ("Wk", c_void_p), ("Y", c_void_p), ("bias", c_void_p), ("residual", c_void_p), ("ldc", c_longlong), ("ldr", c_longlong),
+                ("N", c_int), ("H", c_int), ("W", c_int), ("C", c_int), ("Cout", c_int), ("ks", c_int), ("stride", c_int), ("pad", c_int),
+                ("Ho", c_int), ("Wo", c_int), ("out_f32", c_int)]
 
 
 class LcError(RuntimeError):

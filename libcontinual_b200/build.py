@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "liblc_b200.so")
-SOURCES = ["lc_resnet.cu", "lc_ops.cu", "lc_vit.cu"]
+SOURCES = ["lc_resnet.cu", "lc_ops.cu", "lc_vit.cu", "lc_nn.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

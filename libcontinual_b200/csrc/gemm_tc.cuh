@@ -37,6 +37,13 @@ struct GemmArgs {
     int out_dtype;
     float alpha;               // scale applied to the accumulator before bias (attention: 1/sqrt(d))
     int* error_flag;
+    // split-K: the K blocks are divided over `ksplit` partial outputs (fp32, partial s at out + s * c_stride_split); 0 / 1 = off
+    int ksplit;
+    long long c_stride_split;
+    // implicit convolution (conv_ks > 0): A is an NHWC BF16 activation addressed through a rank-4 {C, W, H, N} tensor map whose box is one 128-pixel
+    // output tile (Nt images x Ht rows x Wo columns, element strides = conv stride); K block kb = tap * conv_cchunks + channel chunk, and the tap is a
+    // coordinate offset of the box (zero fill outside the image = the padding).  No im2col matrix exists anywhere.
+    int conv_ks, conv_cchunks, conv_stride, conv_pad, conv_hw, conv_wo;
     int gelu_mode;             // bit 0: the GELU side tensor holds GELU'(pre-activation) instead of the pre-activation itself — `out` of the out2 variant
                                //        stores it, `gelu_aux` is then a plain multiplier (the backward epilogue drops from 25 to ~8 instructions per
                                //        element; the frozen-backbone backward needs the pre-activation for nothing else).  bit 1: do not store `out`
@@ -132,7 +139,9 @@ __global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(cons
     const int nkb = (a.K + K::BK - 1) / K::BK;
     const int m_tiles = (a.M + K::BM - 1) / K::BM, n_tiles = (a.N + BN - 1) / BN;
     const int per_z = m_tiles * n_tiles;
-    const int total = per_z * a.batch_total;
+    const int ksplit = a.ksplit > 1 ? a.ksplit : 1;
+    const int kper = (nkb + ksplit - 1) / ksplit;
+    const int total = per_z * a.batch_total * ksplit;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < K::STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -150,17 +159,26 @@ __global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(cons
             uint32_t it = 0;
             int tl = 0; (void)tl;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const int z = tile / per_z, r = tile % per_z;
+                const int sp = tile % ksplit, tq = tile / ksplit;
+                const int z = tq / per_z, r = tq % per_z;
                 const int n0 = (r % n_tiles) * BN, m0 = (r / n_tiles) * K::BM;
                 const int z_in = z % a.batch_in, z_out = z / a.batch_in;
+                const int kb0 = sp * kper, kb1 = kb0 + kper < nkb ? kb0 + kper : nkb;
+                const int cv_n = a.conv_ks > 0 ? m0 / a.conv_hw : 0, cv_h = a.conv_ks > 0 ? (m0 % a.conv_hw) / a.conv_wo * a.conv_stride - a.conv_pad : 0;
                 LC_GSTAMP(tl, 0);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % K::STAGES;
                     const uint32_t ph = (it / K::STAGES) & 1u;
                     ok = mbar_wait(empty + s, ph ^ 1u) && ok;
                     mbar_expect_tx(full + s, (uint32_t)K::STAGE_BYTES);
                     const uint32_t sa = base_u + (uint32_t)s * K::STAGE_BYTES;
-                    tma_load_4d(sa, &tmA, full + s, kb * K::BK, m0, (a.a_bcast & 1) ? 0 : z_in, (a.a_bcast & 2) ? 0 : z_out);
+                    if (a.conv_ks > 0) {
+                        const int tap = kb / a.conv_cchunks, chunk = kb - tap * a.conv_cchunks;
+                        const int kh = tap / a.conv_ks, kw = tap - kh * a.conv_ks;
+                        tma_load_4d(sa, &tmA, full + s, chunk * K::BK, kw - a.conv_pad, cv_h + kh, cv_n);
+                    } else {
+                        tma_load_4d(sa, &tmA, full + s, kb * K::BK, m0, (a.a_bcast & 1) ? 0 : z_in, (a.a_bcast & 2) ? 0 : z_out);
+                    }
                     tma_load_4d(sa + K::A_BYTES, &tmB, full + s, kb * K::BK, n0, (a.b_bcast & 1) ? 0 : z_in, (a.b_bcast & 2) ? 0 : z_out);
                 }
                 LC_GSTAMP(tl, 1);
@@ -178,7 +196,9 @@ __global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(cons
                 fence_after_sync();
                 LC_GSTAMP(t, 3);
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int sp = tile % ksplit;
+                const int kb0 = sp * kper, kb1 = kb0 + kper < nkb ? kb0 + kper : nkb;
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % K::STAGES;
                     const uint32_t ph = (it / K::STAGES) & 1u;
                     ok = mbar_wait(full + s, ph) && ok;
@@ -187,7 +207,7 @@ __global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(cons
                     const uint64_t ad = make_desc_sw128(sa), bd = make_desc_sw128(sa + K::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < K::BK / 16; ++k)                           // +32 B (2 x 16-byte units) per K16 step inside the swizzle atom
-                        mma_f16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                        mma_f16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
                     mma_commit(empty + s);                                         // frees the stage when these MMAs have read it
                 }
                 mma_commit(tmem_full + acc);
@@ -202,7 +222,8 @@ __global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(cons
         const int rr = lane >> 3, c4 = (lane & 7) * 4;
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
-            const int z = tile / per_z, r = tile % per_z;
+            const int sp = tile % ksplit, tq = tile / ksplit;
+            const int z = tq / per_z, r = tq % per_z;
             const int n0 = (r % n_tiles) * BN, m0 = (r / n_tiles) * K::BM;
             const int z_in = z % a.batch_in, z_out = z / a.batch_in;
             const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
@@ -211,7 +232,7 @@ __global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(cons
             fence_after_sync();
             if (warp == 2 && lane == 0) LC_GSTAMP(t, 6);
             const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
-            const size_t cz = (size_t)z_out * a.c_stride_out + (size_t)z_in * a.c_stride_in;
+            const size_t cz = (size_t)z_out * a.c_stride_out + (size_t)z_in * a.c_stride_in + (size_t)sp * (size_t)a.c_stride_split;
             const size_t rz = (size_t)z_out * a.r_stride_out + (size_t)z_in * a.r_stride_in;
             const int mrow0 = m0 + quarter * 32;
 #pragma unroll 1

@@ -62,7 +62,7 @@ int launch_gemm_epi(const CUtensorMap& ta, const CUtensorMap& tb, const tc::Gemm
         if (cudaFuncSetAttribute(tc::gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES) != cudaSuccess) return LC_ERR_CUDA;
         attr_done = true;
     }
-    const long long tiles = (long long)((a.N + BN - 1) / BN) * ((a.M + 127) / 128) * batch;
+    const long long tiles = (long long)((a.N + BN - 1) / BN) * ((a.M + 127) / 128) * batch * (a.ksplit > 1 ? a.ksplit : 1);
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
     tc::gemm_bf16_kernel<BN, EPI><<<grid, K::NT, K::SMEM_BYTES, st>>>(ta, tb, a);
     return lc_launch_status();
@@ -121,8 +121,45 @@ int lc_gemm_bf16_ex(const lc_gemm_desc* d, int* error_flag, lc_stream_t stream) 
     a.out = d->C; a.bias = d->bias; a.residual = d->residual; a.out2 = d->out2; a.gelu_aux = d->gelu_bwd_aux; a.M = d->M; a.N = d->N; a.K = d->K; a.ldc = (int)d->ldc; a.ldr = (int)d->ldr;
     a.c_stride_in = d->strideC_in; a.c_stride_out = d->strideC_out; a.r_stride_in = d->strideR_in; a.r_stride_out = d->strideR_out;
     a.batch_in = d->batch_in; a.batch_total = d->batch_in * d->batch_out; a.out_dtype = d->out_f32 ? tc::GEMM_OUT_F32 : tc::GEMM_OUT_BF16; a.alpha = d->alpha; a.error_flag = error_flag; a.gelu_mode = d->gelu_mode;
+    if (d->ksplit > 1) {
+        const int nkb = (d->K + 63) / 64, kper = (nkb + d->ksplit - 1) / d->ksplit;
+        LC_CHECK_ARG(d->out_f32 && !d->bias && !d->residual && !d->out2 && !d->gelu_bwd_aux && (long long)(d->ksplit - 1) * kper < nkb && d->strideC_split % 4 == 0);
+        a.ksplit = d->ksplit; a.c_stride_split = d->strideC_split;
+    }
     const int batch = d->batch_in * d->batch_out;
     return bn == 256 ? launch_gemm<256>(ta, tb, a, batch, (cudaStream_t)stream) : launch_gemm<128>(ta, tb, a, batch, (cudaStream_t)stream);
+}
+
+int lc_conv_gemm_bf16(const lc_conv_desc* d, int* error_flag, lc_stream_t stream) {
+    LC_CHECK_ARG(d && d->X && d->Wk && d->Y && d->N >= 1 && d->C >= 64 && d->C % 64 == 0 && d->Cout >= 1 && d->ks >= 1 && d->ks <= 7 && d->stride >= 1 && d->pad >= 0);
+    LC_CHECK_ARG(d->Ho == (d->H + 2 * d->pad - d->ks) / d->stride + 1 && d->Wo == (d->W + 2 * d->pad - d->ks) / d->stride + 1 && d->Wo >= 1 && 128 % d->Wo == 0);
+    const int hw = d->Ho * d->Wo;
+    LC_CHECK_ARG(hw % 128 == 0 || 128 % hw == 0);
+    LC_CHECK_ARG(d->ldc >= d->Cout && d->ldc % (d->out_f32 ? 4 : 8) == 0 && (d->residual == nullptr || d->ldr % 4 == 0) && ((uintptr_t)d->X % 16) == 0);
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) return LC_ERR_CUDA;
+    const int Ht = hw >= 128 ? 128 / d->Wo : d->Ho, Nt = hw >= 128 ? 1 : 128 / hw;
+    // box extents are in tensor elements: Wt outputs at element stride s span (Wt - 1) * s + 1 inputs
+    CUtensorMap ta, tb;
+    {
+        cuuint64_t gdim[4] = {(cuuint64_t)d->C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+        cuuint64_t gstr[3] = {(cuuint64_t)d->C * 2, (cuuint64_t)d->W * d->C * 2, (cuuint64_t)d->H * d->W * d->C * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)((d->Wo - 1) * d->stride + 1), (cuuint32_t)((Ht - 1) * d->stride + 1), (cuuint32_t)Nt};
+        cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+        LC_CHECK_ARG(box[1] <= 256 && box[2] <= 256);
+        if (enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->X), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return LC_ERR_INVALID;
+    }
+    const int K = d->ks * d->ks * d->C;
+    const int bn = d->Cout > 128 ? 256 : 128;
+    tc::GemmArgs a{};
+    int e = make_tmap(&tb, d->Wk, K, d->Cout, 1, 1, K, 0, 0, bn, &a.b_bcast);
+    if (e != LC_OK) return e;
+    a.b_bcast = 0;
+    a.out = d->Y; a.bias = d->bias; a.residual = d->residual; a.M = d->N * hw; a.N = d->Cout; a.K = K; a.ldc = (int)d->ldc; a.ldr = (int)d->ldr;
+    a.batch_in = 1; a.batch_total = 1; a.out_dtype = d->out_f32 ? tc::GEMM_OUT_F32 : tc::GEMM_OUT_BF16; a.alpha = 1.f; a.error_flag = error_flag;
+    a.conv_ks = d->ks; a.conv_cchunks = d->C / 64; a.conv_stride = d->stride; a.conv_pad = d->pad; a.conv_hw = hw; a.conv_wo = d->Wo;
+    return bn == 256 ? launch_gemm<256>(ta, tb, a, 1, (cudaStream_t)stream) : launch_gemm<128>(ta, tb, a, 1, (cudaStream_t)stream);
 }
 
 int lc_gemm_bf16(const void* A, int lda, long long strideA, const void* B, int ldb, long long strideB, void* C, int ldc, long long strideC, int M, int N,
