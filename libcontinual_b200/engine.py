@@ -62,7 +62,7 @@ class TeacherState:
     def __init__(self, eng: "ResNetEngine"):
         self.params = eng.params.clone()
         self.rstat = eng.rstat.clone()
-        self.ws = torch.zeros_like(eng.ws)
+        self.ws = eng.new_teacher_workspace() if hasattr(eng, "new_teacher_workspace") else torch.zeros_like(eng.ws)
         self.logits = torch.zeros_like(eng.logits)
         self.ncls = eng.ncls
 

@@ -132,6 +132,77 @@ class CifarResNet(nn.Module):
         return self.forward(x)["features"]
 
 
+class ResNet18(CifarResNet):
+    """torchvision-style ResNet18 of the reference (`ResNet(BasicBlock, [2, 2, 2, 2])`, resnet.py:110-246, factory :259-267) on `ResNet18Engine`.
+    Parameter / buffer names follow the reference (`conv1.0.weight`, `layer2.0.downsample.1.running_mean`, ...); the initial weights consume the torch
+    RNG exactly as the reference constructor does (constructor draws of every nn.Conv2d, then kaiming_normal_(fan_out) in `modules()` order, then the
+    unused `fc = nn.Linear(512, 20)` of resnet.py:191)."""
+
+    def __init__(self, device=None, max_batch: int = 256, num_class_cap: int = 200, img: int = 64, maxpool: bool = True):
+        nn.Module.__init__(self)
+        from ...nn_engine import ResNet18Engine
+        self.engine = ResNet18Engine(max_batch=max_batch, num_class_cap=num_class_cap, device=device, img=img, maxpool=maxpool)
+        self.out_dim = 512
+        self.num_batches_pending = 0
+        self._nbt = []
+        eng = self.engine
+        shapes = dict(eng.layout)
+        draws = {}
+        order = []
+        # construction order: stem conv; per layer `_make_layer` builds the downsample conv BEFORE the block's conv1 / conv2 (resnet.py:203-212)
+        order.append("conv1.0.weight")
+        for li in range(1, 5):
+            for b in range(2):
+                pre = f"layer{li}.{b}"
+                if pre + ".downsample.0.weight" in shapes:
+                    order.append(pre + ".downsample.0.weight")
+                order += [pre + ".conv1.weight", pre + ".conv2.weight"]
+        for name in order:
+            co, ci, kh, kw = shapes[name]
+            draws[name] = nn.Conv2d(ci, co, kh, bias=False).weight.data          # the constructor's kaiming_uniform draw (discarded below)
+        for name, shape in eng.layout:                                           # `for m in self.modules()` (resnet.py:163-168): registration order
+            if len(shape) == 4:
+                nn.init.kaiming_normal_(draws[name], mode="fan_out", nonlinearity="relu")
+        fc = nn.Linear(512, 20)
+        for name, shape in eng.layout:
+            view = eng.param_view(name)
+            if len(shape) == 4:
+                view.copy_(draws[name])
+            elif name.endswith(".weight"):
+                view.fill_(1.0)
+            else:
+                view.zero_()
+            self._register(name, nn.Parameter(view))
+        for bn in eng.bn_names:
+            m, v = eng.running_views(bn)
+            self._register_buffer(bn + ".running_mean", m)
+            self._register_buffer(bn + ".running_var", v)
+            self._register_buffer(bn + ".num_batches_tracked", torch.zeros((), dtype=torch.long))
+        # the reference's unused head (never in the forward: no gradient, never updated); kept so that state_dicts interoperate
+        self._register("fc.weight", nn.Parameter(fc.weight.data.to(eng.device)))
+        self._register("fc.bias", nn.Parameter(fc.bias.data.to(eng.device)))
+
+
+def resnet18(pretrained: bool = False, progress: bool = True, **kwargs):
+    """Factory named in the YAML recipes (`backbone.name: resnet18`, resnet.py:259-267).  `args` selects the stem like resnet.py:133-150:
+    'cifar' / '5-datasets' -> 3x3 stride-1 conv; '*imagenet*' with init_cls_num != inc_cls_num -> the same conv + MaxPool(3, 2, 1).  The 7x7 stride-2
+    ImageNet stem (init_cls_num == inc_cls_num) is not built."""
+    if pretrained:
+        raise NotImplementedError
+    args = kwargs.get("args") or {}
+    ds = str(args.get("dataset", "tiny-imagenet"))
+    if "cifar" in ds or "5-datasets" in ds:
+        maxpool, img = False, kwargs.get("img", 32)
+    elif "imagenet" in ds:
+        if args.get("init_cls_num") is not None and args.get("init_cls_num") == args.get("inc_cls_num"):
+            raise NotImplementedError("the 7x7 stride-2 stem (resnet.py:136-142) is not built; BASELINE config C5 has init_cls_num != inc_cls_num")
+        maxpool, img = True, kwargs.get("img", 64)
+    else:
+        raise ValueError(f"resnet18: unknown dataset {ds!r} (resnet.py:133-150 knows cifar / 5-datasets / *imagenet*)")
+    return ResNet18(device=kwargs.get("device"), max_batch=kwargs.get("max_batch", 256), num_class_cap=kwargs.get("num_classes", 200), img=img,
+                    maxpool=maxpool)
+
+
 class _Node(nn.Module):
     """Bare container (one path component of a reference parameter name).  Loading copies IN PLACE (nn.Module's default for
     parameters and buffers), so the arenas keep owning the storage."""

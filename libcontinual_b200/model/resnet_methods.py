@@ -128,7 +128,8 @@ class _ResNetMethod(nn.Module):
         self.network = _Network(self.backbone, _Head(eng, n_new))
 
     def _params(self):
-        return [p for _, p in self.backbone.named_parameters()] + [self.network.classifier.weight, self.network.classifier.bias]
+        # arena-backed parameters only (resnet18 also registers the reference's unused `fc`, resnet.py:191, which never receives a gradient)
+        return [p for n, p in self.backbone.named_parameters() if n in self.engine.param_off] + [self.network.classifier.weight, self.network.classifier.bias]
 
     def _grad_views(self, arena=None):
         eng = self.engine

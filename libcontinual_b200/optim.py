@@ -41,6 +41,8 @@ class SGD(torch.optim.Optimizer):
             for grp in self.param_groups:
                 for p in grp["params"]:
                     off = (p.data_ptr() - base) // 4
+                    if not (0 <= off < eng.n_total):
+                        continue          # a parameter outside the arena (never part of the fused step, e.g. the reference's unused backbone.fc)
                     if p.grad is None:
                         src[off:off + p.numel()].zero_()
                     else:

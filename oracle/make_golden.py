@@ -262,6 +262,75 @@ def golden_lwf(core):
     np.savez_compressed(os.path.join(OUT, "lwf_resnet32.npz"), **out)
 
 
+def synth_resnet18_state(seed: int, n_head: int):
+    rng = np.random.default_rng(seed)
+    p, b = port.resnet18_init(rng)
+    bound = 1.0 / np.sqrt(512)
+    fc_w = torch.from_numpy(rng.uniform(-bound, bound, (n_head, 512)).astype(np.float32))
+    fc_b = torch.from_numpy(rng.uniform(-bound, bound, (n_head,)).astype(np.float32))
+    return p, b, fc_w, fc_b
+
+
+def golden_lwf18(core):
+    """BASELINE config C5's method/backbone pair: the real `LWF` on the real `resnet18` with the tiny-imagenet stem (3x3 conv + maxpool, resnet.py:145-150)
+    at 64 x 64: task 0 (CE) and two task-1 steps (CE on the new slice + 3 * KD against the frozen copy)."""
+    import core.model as M
+    print("LwF / resnet18 (tiny-imagenet stem), 64x64")
+    B, init_cls, inc_cls = 4, 10, 10
+    p, b, fc_w, fc_b = synth_resnet18_state(1818, 20)
+    out = {}
+    bb = M.resnet18(args={"dataset": "tiny-imagenet", "init_cls_num": init_cls * 2, "inc_cls_num": inc_cls})
+    sd = {**p, **b, "fc.weight": bb.fc.weight.data.clone(), "fc.bias": bb.fc.bias.data.clone()}
+    bb.load_state_dict(sd, strict=True)
+    ref = M.LWF(bb, 512, 200, device=torch.device("cpu"), init_cls_num=init_cls, inc_cls_num=inc_cls)
+    ref.before_task(0, None, None, None)
+    with torch.no_grad():
+        ref.classifier.weight.copy_(fc_w[:10]); ref.classifier.bias.copy_(fc_b[:10])
+    ref.train()
+
+    def named():
+        d = {"backbone." + n: q for n, q in ref.backbone.named_parameters() if not n.startswith("fc.")}
+        d.update({"classifier." + n: q for n, q in ref.classifier.named_parameters()})
+        return d
+
+    opt = torch.optim.SGD(list(named().values()), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    orc = port.ResNetMethodOracle("lwf", p, b, fc_w[:10], fc_b[:10], init_cls=init_cls, inc_cls=inc_cls, arch="resnet18", maxpool=True)
+
+    def both(x, y, tag):
+        pred, acc, loss = ref.observe({"image": x, "label": y})
+        opt.zero_grad(); loss.backward()
+        assert ref.backbone.fc.weight.grad is None                 # the backbone's own `fc` (resnet.py:191) is never in the forward
+        grads = {n: q.grad.clone() for n, q in named().items()}
+        opt.step()
+        out[tag + "/loss"] = np.float64(loss.item()); out[tag + "/pred"] = pred.numpy().copy()
+        summarize(tag + "/grad", grads, out)
+        po, ao, lo, go = orc.step(x, y)
+        close(lo, loss.detach(), 1e-5, 1e-6, tag + " loss")
+        assert torch.equal(po, pred)
+        worst = max(float((go[n] - grads[n]).abs().max() / (grads[n].abs().max() + 1e-12)) for n in grads)
+        print(f"   worst rel grad err over all tensors: {worst:.3e}")
+        assert worst < 1e-3
+
+    x, y = synth_batch(1900, B, 0, 10, img=64)
+    both(x, y, "t0s0")
+    with torch.no_grad():
+        f = ref.backbone(x)
+        fo = port.resnet18_forward({k: v.detach() for k, v in orc.p.items()}, orc.b, x, True, True)      # both sides move their running statistics once more
+        close(fo["features"], f["features"], 1e-4, 1e-5, "features after one step")
+        out["t0s0/features_after"] = f["features"].numpy().copy()
+    ref.before_task(1, None, None, None)
+    with torch.no_grad():
+        ref.classifier.weight[10:].copy_(fc_w[10:20]); ref.classifier.bias[10:].copy_(fc_b[10:20])
+    ref.train(); ref.old_backbone.eval(); ref.old_fc.eval()
+    opt = torch.optim.SGD(list(named().values()), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    orc.snapshot_teacher(); orc.prev_cls = 10; orc.task_idx = 1
+    orc.grow_head(fc_w[:20], fc_b[:20]); orc.reset_optimizer()
+    for s in range(2):
+        x, y = synth_batch(1910 + s, B, 10, 20, img=64)
+        both(x, y, f"t1s{s}")
+    np.savez_compressed(os.path.join(OUT, "lwf_resnet18.npz"), **out)
+
+
 # ---- LUCIR --------------------------------------------------------------------------------------
 def cifar_to_lucir_name(n: str) -> str:
     """cifar_resnet32 parameter name -> modified_ResNet (resnet32_V2) name: same topology / order, other names."""
@@ -1057,6 +1126,7 @@ def main():
     golden_ewc(core)
     golden_icarl(core)
     golden_lwf(core)
+    golden_lwf18(core)
     golden_lucir(core)
     golden_herding(core)
     golden_ops(core)

@@ -152,6 +152,113 @@ def cifar_resnet_forward(p: Dict[str, Tensor], b: Dict[str, Tensor], x: Tensor, 
 
 
 # ----------------------------------------------------------------------------------------------
+# resnet18  (core/model/backbone/resnet.py:26-64 BasicBlock, :110-246 ResNet, factory :259-267)
+# ----------------------------------------------------------------------------------------------
+def resnet18_layout(in_ch: int = 3) -> Tuple[List[Tuple[str, Tuple[int, ...]]], List[Tuple[str, Tuple[int, ...]]]]:
+    """Parameter / buffer (name, shape) lists in the reference's registration order: stem `conv1` = Sequential(Conv2d, BatchNorm2d, ReLU[, MaxPool2d])
+    (resnet.py:133-150), `layerN.M.{conv1,bn1,conv2,bn2[,downsample.0,downsample.1]}` (:196-218, :40-46).  The unused `fc` (:191) is left out."""
+    params: List[Tuple[str, Tuple[int, ...]]] = []
+    bufs: List[Tuple[str, Tuple[int, ...]]] = []
+
+    def bn(prefix, c):
+        params.append((prefix + ".weight", (c,)))
+        params.append((prefix + ".bias", (c,)))
+        bufs.append((prefix + ".running_mean", (c,)))
+        bufs.append((prefix + ".running_var", (c,)))
+        bufs.append((prefix + ".num_batches_tracked", ()))
+
+    params.append(("conv1.0.weight", (64, in_ch, 3, 3)))
+    bn("conv1.1", 64)
+    inpl = 64
+    for li, (planes, stride) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)], start=1):
+        for b in range(2):
+            pre = f"layer{li}.{b}"
+            s, cin = (stride, inpl) if b == 0 else (1, planes)
+            params.append((pre + ".conv1.weight", (planes, cin, 3, 3)))
+            bn(pre + ".bn1", planes)
+            params.append((pre + ".conv2.weight", (planes, planes, 3, 3)))
+            bn(pre + ".bn2", planes)
+            if b == 0 and (s != 1 or cin != planes):
+                params.append((pre + ".downsample.0.weight", (planes, cin, 1, 1)))
+                bn(pre + ".downsample.1", planes)
+        inpl = planes
+    return params, bufs
+
+
+def resnet18_init(rng: np.random.Generator, in_ch: int = 3) -> Tuple[Dict[str, Tensor], Dict[str, Tensor]]:
+    """Same init DISTRIBUTIONS as resnet.py:163-168 (kaiming_normal_, fan_out, relu: N(0, sqrt(2 / (k*k*Cout))); BN weight 1 / bias 0), drawn from a
+    numpy Generator so that fixtures are platform-stable."""
+    pl, bl = resnet18_layout(in_ch)
+    params, bufs = {}, {}
+    for name, shape in pl:
+        if len(shape) == 4:
+            params[name] = torch.from_numpy((rng.standard_normal(shape) * math.sqrt(2.0 / (shape[0] * shape[2] * shape[3]))).astype(np.float32))
+        elif name.endswith(".weight"):
+            params[name] = torch.ones(shape)
+        else:
+            params[name] = torch.zeros(shape)
+    for name, shape in bl:
+        bufs[name] = torch.ones(shape) if name.endswith("running_var") else (torch.zeros((), dtype=torch.int64) if name.endswith("num_batches_tracked")
+                                                                           else torch.zeros(shape))
+    return params, bufs
+
+
+class _BF16Conv(torch.autograd.Function):
+    """Arithmetic class of the product's ResNet18 / AlexNet path: every contraction (forward, data gradient, weight gradient) multiplies
+    BF16-rounded operands (round-to-nearest-even) and accumulates in fp32."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, padding):
+        ctx.save_for_backward(x, w)
+        ctx.sp = (stride, padding)
+        return F.conv2d(x.bfloat16().float(), w.bfloat16().float(), None, stride, padding)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        stride, padding = ctx.sp
+        dyr = dy.bfloat16().float()
+        dx = torch.nn.grad.conv2d_input(x.shape, w.bfloat16().float(), dyr, stride=stride, padding=padding) if ctx.needs_input_grad[0] else None
+        dw = torch.nn.grad.conv2d_weight(x.bfloat16().float(), w.shape, dyr, stride=stride, padding=padding)
+        return dx, dw, None, None
+
+
+def _conv(x: Tensor, w: Tensor, stride: int, padding: int, conv_mode: str) -> Tensor:
+    if conv_mode == "bf16":
+        return _BF16Conv.apply(x, w, stride, padding)
+    return F.conv2d(x, w, None, stride, padding)
+
+
+def resnet18_forward(p: Dict[str, Tensor], b: Dict[str, Tensor], x: Tensor, train: bool, maxpool: bool = True, conv_mode: str = "fp32",
+                     relu=None) -> Dict[str, object]:
+    """resnet.py:220-234 (`_forward_impl`) with the 3x3 stride-1 stem of :133-150 (+ MaxPool2d(3, 2, 1) for the imagenet-like datasets) and the
+    BasicBlock of :48-64.  Returns {'fmaps': [x_1, x_2, x_3, x_4], 'features': [B, 512]}.
+    `relu(name, t)` (tests only) replaces F.relu at the site `name` ('conv1', 'layerN.M.relu1', 'layerN.M.relu2') — used to pin the ReLU routing to
+    another implementation's masks, which removes the mask-flip discontinuity from a gradient comparison."""
+    rl = (lambda name, t: F.relu(t)) if relu is None else relu
+    h = _conv(x, p["conv1.0.weight"], 1, 1, conv_mode)
+    h = rl("conv1", _bn(h, p, b, "conv1.1", train))
+    if maxpool:
+        h = F.max_pool2d(h, 3, 2, 1)
+    fmaps = []
+    for li, stride in enumerate((1, 2, 2, 2), start=1):
+        for k in range(2):
+            pre = f"layer{li}.{k}"
+            s = stride if k == 0 else 1
+            identity = h
+            y = _conv(h, p[pre + ".conv1.weight"], s, 1, conv_mode)
+            y = rl(pre + ".relu1", _bn(y, p, b, pre + ".bn1", train))
+            y = _conv(y, p[pre + ".conv2.weight"], 1, 1, conv_mode)
+            y = _bn(y, p, b, pre + ".bn2", train)
+            if (pre + ".downsample.0.weight") in p:
+                identity = _bn(_conv(h, p[pre + ".downsample.0.weight"], s, 0, conv_mode), p, b, pre + ".downsample.1", train)
+            h = rl(pre + ".relu2", y + identity)
+        fmaps.append(h)
+    feats = torch.flatten(F.adaptive_avg_pool2d(h, (1, 1)), 1)
+    return {"fmaps": fmaps, "features": feats}
+
+
+# ----------------------------------------------------------------------------------------------
 # heads and losses
 # ----------------------------------------------------------------------------------------------
 def linear_head(feat: Tensor, w: Tensor, bias: Optional[Tensor]) -> Tensor:
@@ -614,9 +721,9 @@ class ResNetMethodOracle:
 
     def __init__(self, method: str, p: Dict[str, Tensor], b: Dict[str, Tensor], fc_w: Tensor, fc_b: Tensor, *,
                  init_cls: int, inc_cls: int, lamda: float = 1000.0, lr: float = 0.1, momentum: float = 0.9, wd: float = 5e-4,
-                 depth: int = 32, conv_mode: str = "fp32"):
-        assert method in ("finetune", "ewc", "icarl", "lwf")
-        self.method, self.depth, self.conv_mode = method, depth, conv_mode
+                 depth: int = 32, conv_mode: str = "fp32", arch: str = "cifar_resnet", maxpool: bool = True):
+        assert method in ("finetune", "ewc", "icarl", "lwf") and arch in ("cifar_resnet", "resnet18")
+        self.method, self.depth, self.conv_mode, self.arch, self.maxpool = method, depth, conv_mode, arch, maxpool
         self.p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
         self.b = {k: v.clone() for k, v in b.items()}
         self.fc_w = fc_w.clone().requires_grad_(True)
@@ -638,15 +745,18 @@ class ResNetMethodOracle:
         d["classifier.bias"] = self.fc_b
         return d
 
+    def backbone(self, p, b, x: Tensor, train: bool):
+        if self.arch == "resnet18":
+            return resnet18_forward(p, b, x, train, self.maxpool, self.conv_mode)
+        return cifar_resnet_forward(p, b, x, train, self.depth, self.conv_mode)
+
     def logits(self, x: Tensor, train: bool) -> Tensor:
-        feat = cifar_resnet_forward(self.p, self.b, x, train, self.depth, self.conv_mode)["features"]
-        return linear_head(feat, self.fc_w, self.fc_b)
+        return linear_head(self.backbone(self.p, self.b, x, train)["features"], self.fc_w, self.fc_b)
 
     def teacher_logits(self, x: Tensor) -> Tensor:
         tp, tb, tw, tbias = self.teacher
         with torch.no_grad():
-            feat = cifar_resnet_forward(tp, tb, x, False, self.depth, self.conv_mode)["features"]
-            return linear_head(feat, tw, tbias)
+            return linear_head(self.backbone(tp, tb, x, False)["features"], tw, tbias)
 
     def snapshot_teacher(self):
         self.teacher = ({k: v.detach().clone() for k, v in self.p.items()}, {k: v.clone() for k, v in self.b.items()},

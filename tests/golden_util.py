@@ -24,6 +24,15 @@ def synth_resnet_state(seed, n_head, feat=64):
     return p, b, fc_w, fc_b
 
 
+def synth_resnet18_state(seed, n_head):
+    rng = np.random.default_rng(seed)
+    p, b = port.resnet18_init(rng)
+    bound = 1.0 / np.sqrt(512)
+    fc_w = torch.from_numpy(rng.uniform(-bound, bound, (n_head, 512)).astype(np.float32))
+    fc_b = torch.from_numpy(rng.uniform(-bound, bound, (n_head,)).astype(np.float32))
+    return p, b, fc_w, fc_b
+
+
 def synth_batch(seed, B, lo, hi, img=32):
     rng = np.random.default_rng(seed)
     x = torch.from_numpy(rng.standard_normal((B, 3, img, img)).astype(np.float32))

@@ -66,6 +66,24 @@ def test_lwf_trajectory_matches_reference():
         _run(orc, g, f"t1s{s}", *synth_batch(3100 + s, B, 10, 20))
 
 
+def test_lwf_resnet18_trajectory_matches_reference():
+    """BASELINE config C5's pair: the oracle's resnet18 (tiny-imagenet stem, 64 x 64) + LwF against the golden written by the real `LWF` on the real
+    `resnet18` (oracle/make_golden.py::golden_lwf18)."""
+    from tests.golden_util import synth_resnet18_state
+    g = load("lwf_resnet18.npz")
+    p, b, fc_w, fc_b = synth_resnet18_state(1818, 20)
+    orc = port.ResNetMethodOracle("lwf", p, b, fc_w[:10], fc_b[:10], init_cls=10, inc_cls=10, arch="resnet18", maxpool=True)
+    x, y = synth_batch(1900, 4, 0, 10, img=64)
+    _run(orc, g, "t0s0", x, y)
+    with torch.no_grad():
+        f = port.resnet18_forward({k: v.detach() for k, v in orc.p.items()}, orc.b, x, True, True)["features"]
+    assert np.allclose(f.numpy(), g["t0s0/features_after"], rtol=1e-4, atol=1e-5)
+    orc.snapshot_teacher(); orc.prev_cls = 10; orc.task_idx = 1
+    orc.grow_head(fc_w[:20], fc_b[:20]); orc.reset_optimizer()
+    for s in range(2):
+        _run(orc, g, f"t1s{s}", *synth_batch(1910 + s, 4, 10, 20, img=64))
+
+
 def test_l2p_select_matches_reference():
     g = load("ops_small.npz")
     rng = np.random.default_rng(404)
