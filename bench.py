@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="icarl", choices=["icarl", "ewc", "l2p", "inflora", "dualprompt", "codaprompt", "sdlora"])
+    ap.add_argument("--workload", default="icarl", choices=["icarl", "ewc", "lwf18", "l2p", "inflora", "dualprompt", "codaprompt", "sdlora"])
     ap.add_argument("--cpu-steps", type=int, default=12, help="timed oracle steps for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
@@ -58,6 +58,7 @@ def parse():
 def workload_name(w):
     return {"icarl": "iCaRL ResNet32 CIFAR-100 b50-5-10 (task 1: CE + KD vs frozen teacher), bs=128, synthetic 32x32",
             "ewc": "EWC ResNet32 CIFAR-100 b0-10-10 (task 1: CE + lamda*Fisher penalty), bs=128, synthetic 32x32",
+            "lwf18": "LwF ResNet18 Tiny-ImageNet b100-20-6 (task 1: CE on the new slice + 3*KD vs the frozen copy, 120 classes), bs=256, synthetic 64x64",
             "l2p": "L2P ViT-B/16 CIFAR-100 b10-10-10 (task 1: query pass + prompted pass + backward to prompts, clip, Adam), bs=128, synthetic 224x224",
             "dualprompt": "DualPrompt ViT-B/16 CIFAR-100 b10-10-10 (task 1: query pass + prefix-tuned pass (g/e prompts on blocks 0-4) + backward, Adam), bs=128 per GPU, "
                           "synthetic 224x224",
@@ -77,6 +78,15 @@ def make_oracle(workload, seed=1993):
     import torch
     from oracle import port
     rng = np.random.default_rng(seed)
+    if workload == "lwf18":
+        p, b = port.resnet18_init(rng)
+        bound = 1.0 / np.sqrt(512)
+        fc_w = torch.from_numpy(rng.uniform(-bound, bound, (120, 512)).astype(np.float32))
+        fc_b = torch.from_numpy(rng.uniform(-bound, bound, (120,)).astype(np.float32))
+        orc = port.ResNetMethodOracle("lwf", p, b, fc_w[:100], fc_b[:100], init_cls=100, inc_cls=20, arch="resnet18", maxpool=True)
+        orc.snapshot_teacher(); orc.prev_cls, orc.task_idx = 100, 1
+        orc.grow_head(fc_w, fc_b)
+        return orc, 120
     p, b = port.cifar_resnet_init(rng)
     bound = 1.0 / 8.0
     if workload == "icarl":
@@ -98,12 +108,16 @@ def make_oracle(workload, seed=1993):
     return orc, hi
 
 
-def synth_batches(n, hi, lo=0, seed=7):
+def batch_of(workload):
+    return 256 if workload == "lwf18" else BATCH
+
+
+def synth_batches(n, hi, lo=0, seed=7, batch=BATCH, img=32):
     import numpy as np
     import torch
     rng = np.random.default_rng(seed)
-    return [(torch.from_numpy(rng.standard_normal((BATCH, 3, 32, 32)).astype(np.float32)),
-             torch.from_numpy(rng.integers(lo, hi, (BATCH,)).astype(np.int64))) for _ in range(n)]
+    return [(torch.from_numpy(rng.standard_normal((batch, 3, img, img)).astype(np.float32)),
+             torch.from_numpy(rng.integers(lo, hi, (batch,)).astype(np.int64))) for _ in range(n)]
 
 
 def time_oracle(workload, steps, warmup, device="cpu"):
@@ -111,8 +125,9 @@ def time_oracle(workload, steps, warmup, device="cpu"):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     orc, hi = make_oracle(workload)
-    lo = 10 if workload == "ewc" else 0
-    batches = synth_batches(2, hi, lo)
+    lo = {"ewc": 10, "lwf18": 100}.get(workload, 0)
+    nb = batch_of(workload) if (device == "cuda" or workload != "lwf18") else 32        # CPU leg of the 64x64 ResNet18 step: a bounded 32-image sample
+    batches = synth_batches(2, hi, lo, batch=nb, img=64 if workload == "lwf18" else 32)
     if device == "cuda":
         # the reference's own device semantics: eager PyTorch on the GPU, cuDNN convs (TF32 allowed, PyTorch default), fp32 elsewhere
         dev = torch.device("cuda", 0)
@@ -134,7 +149,7 @@ def time_oracle(workload, steps, warmup, device="cpu"):
         orc.step(*batches[i % 2])
     sync()
     dt = time.perf_counter() - t0
-    return BATCH * steps / dt, dt / steps * 1e3, cores
+    return nb * steps / dt, dt / steps * 1e3, cores
 
 
 # ---- L2P / ViT-B/16 ---------------------------------------------------------------------------------------------------
@@ -334,6 +349,13 @@ def build_model(workload, device, precision="tc"):
     import libcontinual_b200.model as M
     from libcontinual_b200.engine import TeacherState
     torch.manual_seed(1993)
+    if workload == "lwf18":
+        bb = M.resnet18(args={"dataset": "tiny-imagenet", "init_cls_num": 100, "inc_cls_num": 20}, max_batch=256, num_classes=200)
+        m = M.LWF(bb, 512, 200, device=device, init_cls_num=100, inc_cls_num=20)
+        m.before_task(0, None, None, None)
+        m.before_task(1, None, None, None)                # 120 classes, teacher = frozen copy of the task-0 network
+        m.train()
+        return m, 100, 120
     bb = M.cifar_resnet32(max_batch=BATCH, num_classes=100, precision=precision)
     if workload == "icarl":
         m = M.ICarl(bb, 64, 100, device=device, init_cls_num=50, inc_cls_num=5, task_num=11)
@@ -393,6 +415,47 @@ def time_dominant_kernel(eng, precision, reps=48):
     us = e0.elapsed_time(e1) * 1e3 / reps
     algo_bytes = 2 * n * 4 + C * C * 9 * 4          # read X, write Y, read W   (|X|+|Y| per conv)
     return us, algo_bytes, name
+
+
+def roofline_conv18(eng, B, ms_step):
+    """ResNet18 at 64x64: the 3x3 convolutions are tensor-core work.  Each implicit-GEMM layer shape is timed alone with CUDA events over
+    rotating operand sets (> L2); `roofline` reports the layer2 shape (128 -> 128 @16x16, K = 1152), the per-shape list sits beside it, and `step`
+    relates the whole step to the LwF step's 4.47 GFLOP per image."""
+    import torch
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["bf16_tflops"]), "MEASURED_PEAKS.json bf16 burst (kernel timed alone)"
+    else:
+        peak, peak_src = 1650.0, "fallback (B200_PROFILING.md)"
+    rows = []
+    for (C, H) in ((64, 32), (128, 16), (256, 8), (512, 4)):
+        M = B * H * H
+        sets = max(3, int(400e6 // (M * C * 6)) + 1)
+        xs = [torch.randn(M, C, device=eng.device).bfloat16() for _ in range(sets)]
+        ys = [torch.empty(M, C, device=eng.device) for _ in range(sets)]
+        wk = (torch.randn(C, 9 * C, device=eng.device) * 0.05).bfloat16()
+        launch = lambda i: eng.conv(xs[i].data_ptr(), wk.data_ptr(), ys[i].data_ptr(), B, H, H, C, C, 3, 1, 1)
+        for i in range(sets):
+            launch(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 30
+        e0.record()
+        for i in range(reps):
+            launch(i % sets)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        flops = 2.0 * M * C * 9 * C
+        rows.append({"shape": f"{C}->{C} @{H}x{H}, M={M}, K={9 * C}", "us_per_launch": us, "tflops": flops / (us * 1e-6) / 1e12,
+                     "algorithmic_bytes": M * C * 2 + M * C * 4 + 9 * C * C * 2, "gbs": (M * C * 6 + 18 * C * C) / (us * 1e-6) / 1e9})
+    r = rows[1]
+    step_flops = 4.47e9 * B
+    return {"bound": "tensor", "achieved": r["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": r["tflops"] / peak, "traffic": None,
+            "kernel": "gemm_bf16_kernel<128> in implicit-convolution mode (layer2 3x3 conv: " + r["shape"] + "; TMA boxes with tap offsets, tcgen05 kind::f16, TMEM)",
+            "us_per_launch": r["us_per_launch"], "algorithmic_flops_per_launch": 2.0 * B * 256 * 128 * 1152, "peak_source": peak_src, "per_shape": rows,
+            "step": {"algorithmic_flops_per_image": 4.47e9, "achieved_tflops": step_flops / (ms_step * 1e-3) / 1e12,
+                     "frac": step_flops / (ms_step * 1e-3) / 1e12 / peak, "note": "whole LwF step against SURVEY 8d's 4.47 GFLOP per image"}}
 
 
 def time_dominant_gemm(eng, reps=40, tokens=222):
@@ -658,13 +721,15 @@ def run_ours(args, ctx, workload):
     from libcontinual_b200.optim import SGD
     from libcontinual_b200.trainer import GraphedStep, train_step_eager
     world, rank, device = ctx.world, ctx.rank, ctx.device
-    per = BATCH if not args.global_batch else args.global_batch // world
+    GB = batch_of(workload)
+    img = 64 if workload == "lwf18" else 32
+    per = GB if not args.global_batch else args.global_batch // world
 
     m, lo, hi = build_model(workload, device, args.precision)
     opt = SGD(m.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4, engine=m.engine)
     eng = m.engine
-    host = synth_batches(8, hi, lo, seed=7 + rank)
-    host = [(x[:per].contiguous().pin_memory(), y[:per].contiguous().pin_memory()) for x, y in host]
+    host = synth_batches(8 if img == 32 else 4, hi, lo, seed=7 + rank, batch=per, img=img)
+    host = [(x.contiguous().pin_memory(), y.contiguous().pin_memory()) for x, y in host]
     devb = [(x.to(device), y.to(device)) for x, y in host]
     K, W = args.steps, max(3, args.warmup)
 
@@ -677,30 +742,31 @@ def run_ours(args, ctx, workload):
 
     # ---- e2e: public step API with pinned HOST batches; H2D copy and the D2H loss read are inside the timed region -------
     Ke = max(10, min(K, 200))
+    NH = len(host)
     for i in range(3):
-        step.run(*host[i % 8]); float(step.loss())
+        step.run(*host[i % NH]); float(step.loss())
     ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(Ke):
-        step.run(*host[i % 8])
+        step.run(*host[i % NH])
         lossv = step.loss().item()
     e1.record()
     ctx.barrier()
     e2e_ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / Ke
-    e2e = {"value": world * per / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": per * 3 * 32 * 32 * 4 + per * 8,
+    e2e = {"value": world * per / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": per * 3 * img * img * 4 + per * 8,
            "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
            "path": "libcontinual_b200.trainer.GraphedStep.run(pinned host batch) + loss().item() every step"}
     # the literal reference Trainer order on the plugin surface (eager, autograd hand-off), single replica
     plugin = None
     if world == 1:
         for i in range(3):
-            train_step_eager(m, opt, {"image": host[i % 8][0], "label": host[i % 8][1]})
+            train_step_eager(m, opt, {"image": host[i % NH][0], "label": host[i % NH][1]})
         torch.cuda.synchronize()
         Kp = max(10, min(K, 50))
         e0.record()
         for i in range(Kp):
-            train_step_eager(m, opt, {"image": host[i % 8][0], "label": host[i % 8][1]})
+            train_step_eager(m, opt, {"image": host[i % NH][0], "label": host[i % NH][1]})
         e1.record()
         torch.cuda.synchronize()
         pm = e0.elapsed_time(e1) / Kp
@@ -711,7 +777,7 @@ def run_ours(args, ctx, workload):
     strong = None
     if not args.global_batch:
         strong = strong_leg(ctx, lambda b: GraphedStep(m, opt, b), lambda b: [(x[:b].contiguous(), y[:b].contiguous()) for x, y in devb],
-                            max(10, min(K, 200)), W)
+                            max(10, min(K, 200)), W, global_batch=GB)
     if rank != 0:
         return None
 
@@ -721,36 +787,45 @@ def run_ours(args, ctx, workload):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    us, algo, kname = time_dominant_kernel(eng, args.precision)
-    achieved = algo / (us * 1e-6) / 1e9
-    traffic, traffic_src = ncu_traffic("conv3x3_tc_kernel<16,32>" if args.precision == "tc" else "conv3x3_kernel<16,16,32>")
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": kname, "us_per_launch": us,
-                "algorithmic_bytes_per_launch": algo, "peak_source": peak_src,
-                "step": {"algorithmic_bytes_per_image": 3 * 642048 * 4, "achieved_gbs": 3 * 642048 * 4 * per / (ms_step * 1e-3) / 1e9,
-                         "frac": 3 * 642048 * 4 * per / (ms_step * 1e-3) / 1e9 / peak,
-                         "note": "whole step against SURVEY 8d's conv traffic (3 x 642 048 fp32 activation elements per image)"}}
+    if workload == "lwf18":
+        roofline = roofline_conv18(eng, per, ms_step)
+    else:
+        us, algo, kname = time_dominant_kernel(eng, args.precision)
+        achieved = algo / (us * 1e-6) / 1e9
+        traffic, traffic_src = ncu_traffic("conv3x3_tc_kernel<16,32>" if args.precision == "tc" else "conv3x3_kernel<16,16,32>")
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "kernel": kname, "us_per_launch": us,
+                    "algorithmic_bytes_per_launch": algo, "peak_source": peak_src,
+                    "step": {"algorithmic_bytes_per_image": 3 * 642048 * 4, "achieved_gbs": 3 * 642048 * 4 * per / (ms_step * 1e-3) / 1e9,
+                             "frac": 3 * 642048 * 4 * per / (ms_step * 1e-3) / 1e9 / peak,
+                             "note": "whole step against SURVEY 8d's conv traffic (3 x 642 048 fp32 activation elements per image)"}}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        ips, ms, cores = time_oracle(workload, args.cpu_steps, 1)
+        csteps = args.cpu_steps if workload != "lwf18" else 4
+        ips, ms, cores = time_oracle(workload, csteps, 1)
         cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "ms_per_step": ms,
-               "sample": f"{args.cpu_steps} full training steps of batch {BATCH} after 1 warm-up (oracle/port.py, PyTorch CPU fp32, {cores} threads)"}
+               "sample": (f"{csteps} full training steps of batch {BATCH} after 1 warm-up (oracle/port.py, PyTorch CPU fp32, {cores} threads)" if workload != "lwf18"
+                          else f"{csteps} full LwF steps on 32 of the 256 images after 1 warm-up (bounded sample; oracle/port.py, PyTorch CPU fp32, {cores} threads)")}
     ref_gpu = None
     if world == 1 and not args.no_ref_gpu:
-        ips, ms, _ = time_oracle(workload, 60, 10, "cuda")
-        ref_gpu = {"value": ips, "unit": "images/s", "ms_per_step": ms, "steps": 60, "warmup": 10,
+        rs, rw = (60, 10) if workload != "lwf18" else (20, 5)
+        ips, ms, _ = time_oracle(workload, rs, rw, "cuda")
+        ref_gpu = {"value": ips, "unit": "images/s", "ms_per_step": ms, "steps": rs, "warmup": rw,
                    "kind": "oracle/port.py = the reference's op sequence as plain PyTorch ops, eager on cuda:0 (cuDNN convs with TF32 allowed, "
                            "cudnn.benchmark off, fp32 elsewhere: the reference's GPU semantics, SURVEY 2.3); the port's iCaRL teacher runs under no_grad, "
                            "the reference's does not (icarl.py:212), so this leg is FASTER than the true reference",
                    "ours_over_ref_gpu": value / ips}
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
-            "dtype": "tf32" if args.precision == "tc" else "f32", "data": "synthetic",
+            "dtype": "bf16" if workload == "lwf18" else ("tf32" if args.precision == "tc" else "f32"), "data": "synthetic",
             "config": {"workload": workload_name(workload), "global_batch": per * world, "per_gpu_batch": per, "parallelism": f"dp{world}",
                        "collective": step.collective,
-                       "l2": "per-step working set ~330 MB of fp32 activations + 8 rotating input batches > 126 MB L2 (no explicit flush)",
-                       "precision": ("fp32 storage; 3x3 stride-1 convs on tcgen05: TF32 operands fwd/dgrad, BF16 operands wgrad, fp32 accumulate in TMEM; "
-                                      "everything else fp32 FMA" if args.precision == "tc" else "fp32 storage, fp32 FMA (exact mode)"),
+                       "l2": ("per-step working set of several GB of saved activations > 126 MB L2 (no explicit flush)" if workload == "lwf18" else
+                              "per-step working set ~330 MB of fp32 activations + 8 rotating input batches > 126 MB L2 (no explicit flush)"),
+                       "precision": ("BF16 GEMM operands (implicit-GEMM convolutions on tcgen05 kind::f16), fp32 accumulate in TMEM; fp32 BatchNorm statistics, "
+                                     "residual stream, loss, parameter gradients and optimizer" if workload == "lwf18" else
+                                     "fp32 storage; 3x3 stride-1 convs on tcgen05: TF32 operands fwd/dgrad, BF16 operands wgrad, fp32 accumulate in TMEM; "
+                                     "everything else fp32 FMA" if args.precision == "tc" else "fp32 storage, fp32 FMA (exact mode)"),
                        "final_loss": final_loss, "tensor_core_error": eng.tensor_core_error()},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "ref_gpu": ref_gpu, "strong": strong}
     return line

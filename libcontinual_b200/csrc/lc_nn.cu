@@ -27,6 +27,12 @@ int lc_nn_im2col(const void* src, int src_kind, int N, int H, int W, int C, int 
     LC_CHECK_ARG(Kp >= a.K && (col_bf16 == nullptr || ld_col >= Kp) && (colT_bf16 == nullptr || ld_colT >= a.M));
     a.col = reinterpret_cast<__nv_bfloat16*>(col_bf16); a.ld_col = ld_col; a.colT = reinterpret_cast<__nv_bfloat16*>(colT_bf16); a.ld_colT = ld_colT;
     const long long mspan = colT_bf16 != nullptr ? ld_colT : a.M;      // the zero tail of the transposed rows is written too
+    if (col_bf16 == nullptr && src_kind == SRC_NHWC_BF16 && korder == KORDER_TAP_C && C % 64 == 0 && Kp == a.K && ld_colT % 8 == 0 &&
+        ((uintptr_t)colT_bf16 % 16) == 0 && ((uintptr_t)src % 16) == 0) {
+        dim3 grid((unsigned)((mspan + 63) / 64), (unsigned)(ks * ks * (C / 64)));
+        im2colT_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+        return lc_launch_status();
+    }
     dim3 grid((unsigned)((mspan + 63) / 64), (unsigned)((Kp + 63) / 64));
     im2col_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     return lc_launch_status();
@@ -49,7 +55,7 @@ int lc_nn_bn_stats(const float* y, long long M, int C, const float* gamma, const
     const int gx = colsum_gx(M);
     bn_colsum_kernel<<<dim3(gx, C / 64), 256, 0, (cudaStream_t)stream>>>(y, M, C, scratch);
     if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scratch, gx, M, C, gamma, beta, eps, momentum, running, aff);
+    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(scratch, gx, M, C, gamma, beta, eps, momentum, running, aff);
     return lc_launch_status();
 }
 
@@ -92,7 +98,7 @@ int lc_nn_bn_backward(const float* g, const float* act_f32, const void* act_bf16
     cudaStream_t st = (cudaStream_t)stream;
     bn_bwd_colsum_kernel<<<dim3(gx, C / 64), 256, 0, st>>>(a);
     if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(a, gx);
+    bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(a, gx);
     if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
     bn_bwd_apply_kernel2<<<nn_grid(M * (C / 4)), 256, 0, st>>>(a);
     return lc_launch_status();
@@ -104,7 +110,8 @@ int lc_nn_maxpool_forward(const float* in, int N, int H, int W, int C, int k, in
     PoolArgs a{};
     a.in = in; a.out_f32 = out_f32; a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); a.idx = idx; a.N = N; a.H = H; a.W = W; a.C = C; a.k = k;
     a.stride = stride; a.pad = pad; a.Ho = (H + 2 * pad - k) / stride + 1; a.Wo = (W + 2 * pad - k) / stride + 1;
-    maxpool_fwd_kernel<<<nn_grid((long long)N * a.Ho * a.Wo * C), 256, 0, (cudaStream_t)stream>>>(a);
+    LC_CHECK_ARG(C % 4 == 0);
+    maxpool_fwd_kernel<<<nn_grid((long long)N * a.Ho * a.Wo * (C / 4)), 256, 0, (cudaStream_t)stream>>>(a);
     return lc_launch_status();
 }
 int lc_nn_maxpool_backward(const float* g, const unsigned char* idx, int N, int H, int W, int C, int k, int stride, int pad, float* dx, lc_stream_t stream) {
@@ -112,7 +119,8 @@ int lc_nn_maxpool_backward(const float* g, const unsigned char* idx, int N, int 
     PoolBwdArgs a{};
     a.g = g; a.idx = idx; a.dx = dx; a.N = N; a.H = H; a.W = W; a.C = C; a.k = k; a.stride = stride; a.pad = pad;
     a.Ho = (H + 2 * pad - k) / stride + 1; a.Wo = (W + 2 * pad - k) / stride + 1;
-    maxpool_bwd_kernel<<<nn_grid((long long)N * H * W * C), 256, 0, (cudaStream_t)stream>>>(a);
+    LC_CHECK_ARG(C % 4 == 0);
+    maxpool_bwd_kernel<<<nn_grid((long long)N * H * W * (C / 4)), 256, 0, (cudaStream_t)stream>>>(a);
     return lc_launch_status();
 }
 

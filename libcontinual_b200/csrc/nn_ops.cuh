@@ -90,6 +90,48 @@ __global__ void __launch_bounds__(256) im2col_kernel(Im2colArgs a) {
     }
 }
 
+// Fast path of the transposed patch matrix (the B operand of every weight-gradient GEMM): NHWC BF16 source, C % 64 == 0, tap-major K.  A block moves
+// 64 pixels x 64 channels of ONE tap: 16-byte loads of whole channel runs (two index decodes per thread instead of one per element), a padded
+// shared-memory transpose, 16-byte stores of 8 consecutive pixels per channel row.  grid (ceil(ld_colT / 64), taps * C / 64).
+__global__ void __launch_bounds__(256) im2colT_nhwc_kernel(Im2colArgs a) {
+    __shared__ __align__(16) __nv_bfloat16 tile[64][72];
+    const long long m0 = (long long)blockIdx.x * 64;
+    const int cch = a.C >> 6;
+    const int tap = blockIdx.y / cch, c0 = (blockIdx.y - tap * cch) << 6;
+    const int kh = tap / a.ks, kw = tap - kh * a.ks;
+    const int v = threadIdx.x & 7, r = threadIdx.x >> 3;
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(a.src);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int row = r + 32 * half;
+        const long long m = m0 + row;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (m < a.M) {
+            const int wo = (int)(m % a.Wo);
+            const long long t = m / a.Wo;
+            const int ho = (int)(t % a.Ho);
+            const int n = (int)(t / a.Ho);
+            const int hi = ho * a.stride - a.pad + kh, wi = wo * a.stride - a.pad + kw;
+            if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W)
+                val = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)n * a.H + hi) * a.W + wi) * a.C + c0 + v * 8));
+        }
+        *reinterpret_cast<uint4*>(&tile[row][v * 8]) = val;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int cr = r + 32 * half;                       // channel row of this tap
+        const long long m = m0 + v * 8;
+        if (m >= a.ld_colT) continue;
+        __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = tile[v * 8 + j][cr];
+        __nv_bfloat16* dst = a.colT + (size_t)(tap * a.C + c0 + cr) * a.ld_colT + m;
+        if (m + 8 <= a.ld_colT) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+        else for (int j = 0; j < 8 && m + j < a.ld_colT; ++j) dst[j] = o[j];
+    }
+}
+
 // ---- col2im: dX[n][hi][wi][c] = (addend) + sum over (kh, kw) with (hi + pad - kh) % stride == 0 of dcol[(n, ho, wo)][k(kh, kw, c)] -----------
 struct Col2imArgs {
     const __nv_bfloat16* dcol;     // [M][ld]
@@ -107,14 +149,15 @@ __global__ void __launch_bounds__(256) col2im_kernel(Col2imArgs a) {
         const int hi = (int)(t % a.H);
         const int n = (int)(t / a.H);
         float acc = a.addend != nullptr ? a.addend[e] : 0.f;
-        for (int kh = 0; kh < a.ks; ++kh) {
+        // only taps with (hi + pad - kh) % stride == 0 contribute: start at the right residue and step by the stride
+        for (int kh = (hi + a.pad) % a.stride; kh < a.ks; kh += a.stride) {
             const int hn = hi + a.pad - kh;
-            if (hn < 0 || hn % a.stride != 0) continue;
+            if (hn < 0) break;
             const int ho = hn / a.stride;
             if (ho >= a.Ho) continue;
-            for (int kw = 0; kw < a.ks; ++kw) {
+            for (int kw = (wi + a.pad) % a.stride; kw < a.ks; kw += a.stride) {
                 const int wn = wi + a.pad - kw;
-                if (wn < 0 || wn % a.stride != 0) continue;
+                if (wn < 0) break;
                 const int wo = wn / a.stride;
                 if (wo >= a.Wo) continue;
                 const int k = a.korder == KORDER_TAP_C ? (kh * a.ks + kw) * a.C + c : (c * a.ks + kh) * a.ks + kw;
@@ -156,12 +199,24 @@ __global__ void __launch_bounds__(256) bn_colsum_kernel(const float* __restrict_
     }
 }
 // aff = [scale | shift | mean | invstd] (4*C); running = [mean | var] (nullable); unbiased variance for the running update (nn.BatchNorm)
+// fixed-order sum of the per-block partials of channel c: 8 slices (threadIdx.y) of the partial rows, then a fixed-order combine in shared memory
+// block (32, 8): 32 channels per block
+__device__ __forceinline__ void colsum_combine(const float* __restrict__ partial, int nparts, int C, int c, double& S1, double& S2) {
+    __shared__ double sh[2][8][32];
+    double a1 = 0.0, a2 = 0.0;
+    if (c < C)
+        for (int p = threadIdx.y; p < nparts; p += 8) { a1 += (double)partial[((size_t)p * 2 + 0) * C + c]; a2 += (double)partial[((size_t)p * 2 + 1) * C + c]; }
+    sh[0][threadIdx.y][threadIdx.x] = a1; sh[1][threadIdx.y][threadIdx.x] = a2;
+    __syncthreads();
+    S1 = 0.0; S2 = 0.0;
+    for (int q = 0; q < 8; ++q) { S1 += sh[0][q][threadIdx.x]; S2 += sh[1][q][threadIdx.x]; }
+}
 __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nparts, long long M, int C, const float* gamma, const float* beta, float eps,
                                    float momentum, float* running, float* aff) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double S1 = 0.0, S2 = 0.0;
-    for (int p = 0; p < nparts; ++p) { S1 += (double)partial[((size_t)p * 2 + 0) * C + c]; S2 += (double)partial[((size_t)p * 2 + 1) * C + c]; }
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double S1, S2;
+    colsum_combine(partial, nparts, C, c, S1, S2);
+    if (c >= C || threadIdx.y != 0) return;
     const double mean = S1 / (double)M;
     double var = S2 / (double)M - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -313,10 +368,10 @@ __global__ void __launch_bounds__(256) bn_bwd_colsum_kernel(BnBwdArgs2 a) {
     }
 }
 __global__ void bn_bwd_finalize_kernel(BnBwdArgs2 a, int nparts) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.C) return;
-    double S1 = 0.0, S2 = 0.0;
-    for (int p = 0; p < nparts; ++p) { S1 += (double)a.partial[((size_t)p * 2 + 0) * a.C + c]; S2 += (double)a.partial[((size_t)p * 2 + 1) * a.C + c]; }
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double S1, S2;
+    colsum_combine(a.partial, nparts, a.C, c, S1, S2);
+    if (c >= a.C || threadIdx.y != 0) return;
     const double N = (double)a.M, sc = (double)a.aff[c], m = (double)a.aff[2 * a.C + c], istd = (double)a.aff[3 * a.C + c];
     const double c1 = -sc * S2 / N * istd;
     a.coef[c] = (float)sc;
@@ -356,16 +411,17 @@ struct PoolArgs {
     unsigned char* idx;            // [N][Ho][Wo][C] window index kh*k + kw of the maximum (first maximum in scan order, like ATen)
     int N, H, W, C, k, stride, pad, Ho, Wo;
 };
-__global__ void __launch_bounds__(256) maxpool_fwd_kernel(PoolArgs a) {
-    const long long total = (long long)a.N * a.Ho * a.Wo * a.C;
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(PoolArgs a) {      // one thread = 4 channels of one output pixel (C % 4 == 0)
+    const int c4n = a.C >> 2;
+    const long long total = (long long)a.N * a.Ho * a.Wo * c4n;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(e % a.C);
-        long long t = e / a.C;
+        const int c = (int)(e % c4n) * 4;
+        long long t = e / c4n;
         const int wo = (int)(t % a.Wo); t /= a.Wo;
         const int ho = (int)(t % a.Ho);
         const int n = (int)(t / a.Ho);
-        float best = -INFINITY;
-        int bi = 0;
+        float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        int b0 = 0, b1 = 0, b2 = 0, b3 = 0;
         bool any = false;
         for (int kh = 0; kh < a.k; ++kh) {
             const int hi = ho * a.stride - a.pad + kh;
@@ -373,13 +429,24 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(PoolArgs a) {
             for (int kw = 0; kw < a.k; ++kw) {
                 const int wi = wo * a.stride - a.pad + kw;
                 if (wi < 0 || wi >= a.W) continue;
-                const float v = a.in[(((size_t)n * a.H + hi) * a.W + wi) * a.C + c];
-                if (!any || v > best) { best = v; bi = kh * a.k + kw; any = true; }
+                const float4 v = ldg4(a.in + (((size_t)n * a.H + hi) * a.W + wi) * a.C + c);
+                const int id = kh * a.k + kw;
+                if (!any || v.x > best.x) { best.x = v.x; b0 = id; }
+                if (!any || v.y > best.y) { best.y = v.y; b1 = id; }
+                if (!any || v.z > best.z) { best.z = v.z; b2 = id; }
+                if (!any || v.w > best.w) { best.w = v.w; b3 = id; }
+                any = true;
             }
         }
-        if (a.out_f32 != nullptr) a.out_f32[e] = best;
-        if (a.out_bf16 != nullptr) a.out_bf16[e] = __float2bfloat16_rn(best);
-        a.idx[e] = (unsigned char)bi;
+        const size_t o = (size_t)e * 4;
+        if (a.out_f32 != nullptr) *reinterpret_cast<float4*>(a.out_f32 + o) = best;
+        if (a.out_bf16 != nullptr) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(best.x, best.y), hi2 = __floats2bfloat162_rn(best.z, best.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const unsigned int*>(&lo); pk.y = *reinterpret_cast<const unsigned int*>(&hi2);
+            *reinterpret_cast<uint2*>(a.out_bf16 + o) = pk;
+        }
+        *reinterpret_cast<uchar4*>(a.idx + o) = make_uchar4((unsigned char)b0, (unsigned char)b1, (unsigned char)b2, (unsigned char)b3);
     }
 }
 // gather form: every input element sums the gradients of the windows whose argmax it is
@@ -389,30 +456,37 @@ struct PoolBwdArgs {
     float* dx;                     // [N][H][W][C]
     int N, H, W, C, k, stride, pad, Ho, Wo;
 };
-__global__ void __launch_bounds__(256) maxpool_bwd_kernel(PoolBwdArgs a) {
-    const long long total = (long long)a.N * a.H * a.W * a.C;
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(PoolBwdArgs a) {      // one thread = 4 channels of one input pixel
+    const int c4n = a.C >> 2;
+    const long long total = (long long)a.N * a.H * a.W * c4n;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(e % a.C);
-        long long t = e / a.C;
+        const int c = (int)(e % c4n) * 4;
+        long long t = e / c4n;
         const int wi = (int)(t % a.W); t /= a.W;
         const int hi = (int)(t % a.H);
         const int n = (int)(t / a.H);
-        float acc = 0.f;
-        for (int kh = 0; kh < a.k; ++kh) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kh = (hi + a.pad) % a.stride; kh < a.k; kh += a.stride) {        // windows whose row kh lands on hi
             const int hn = hi + a.pad - kh;
-            if (hn < 0 || hn % a.stride != 0) continue;
+            if (hn < 0) break;
             const int ho = hn / a.stride;
             if (ho >= a.Ho) continue;
-            for (int kw = 0; kw < a.k; ++kw) {
+            for (int kw = (wi + a.pad) % a.stride; kw < a.k; kw += a.stride) {
                 const int wn = wi + a.pad - kw;
-                if (wn < 0 || wn % a.stride != 0) continue;
+                if (wn < 0) break;
                 const int wo = wn / a.stride;
                 if (wo >= a.Wo) continue;
                 const size_t o = (((size_t)n * a.Ho + ho) * a.Wo + wo) * a.C + c;
-                if (a.idx[o] == kh * a.k + kw) acc += a.g[o];
+                const uchar4 id = *reinterpret_cast<const uchar4*>(a.idx + o);
+                const float4 g = ldg4(a.g + o);
+                const int me = kh * a.k + kw;
+                if (id.x == me) acc.x += g.x;
+                if (id.y == me) acc.y += g.y;
+                if (id.z == me) acc.z += g.z;
+                if (id.w == me) acc.w += g.w;
             }
         }
-        a.dx[e] = acc;
+        *reinterpret_cast<float4*>(a.dx + (size_t)e * 4) = acc;
     }
 }
 

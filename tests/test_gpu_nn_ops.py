@@ -120,6 +120,22 @@ def test_im2col_and_transpose(lib, N, C, H, ks, stride, pad, korder, kind):
     assert torch.equal(colT[:K, :M].float().cpu(), ref.t()) and float(colT[K:].float().abs().sum()) == 0.0 and float(colT[:, M:].float().abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("N,C,H,ks,stride,pad", [(3, 64, 32, 3, 1, 1), (2, 128, 16, 3, 2, 1), (5, 256, 8, 3, 1, 1), (7, 64, 16, 1, 2, 0), (3, 512, 4, 3, 1, 1)])
+def test_im2col_transposed_fast_path(lib, N, C, H, ks, stride, pad):
+    """The vectorised transposed patch matrix (NHWC BF16, C % 64 == 0, tap-major K): bit-identical to the generic kernel's definition."""
+    g = torch.Generator().manual_seed(C * H + N)
+    x = _bf(torch.randn(N, C, H, H, generator=g))
+    Ho = (H + 2 * pad - ks) // stride + 1
+    M, K = N * Ho * Ho, C * ks * ks
+    ldT = (M + 7) // 8 * 8 + 8
+    unf = F.unfold(x, ks, padding=pad, stride=stride)
+    ref = unf.permute(0, 2, 1).reshape(M, C, ks * ks).permute(0, 2, 1).reshape(M, K)
+    colT = torch.full((K, ldT), float("nan"), dtype=torch.bfloat16, device="cuda")
+    assert lib.lc_nn_im2col(P(dev(nhwc(x).bfloat16())), 0, N, H, H, C, ks, stride, pad, 0, None, 0, P(colT), ldT, K, st()) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(colT[:, :M].float().cpu(), ref.t()) and float(colT[:, M:].float().abs().sum()) == 0.0
+
+
 @pytest.mark.parametrize("N,C,H,ks,stride,pad,korder", [(2, 64, 14, 3, 1, 0, 1), (2, 64, 16, 3, 2, 1, 0), (3, 64, 16, 1, 2, 0, 0), (2, 128, 6, 2, 1, 0, 1)])
 def test_col2im(lib, N, C, H, ks, stride, pad, korder):
     g = torch.Generator().manual_seed(7 * C + H)
