@@ -331,6 +331,9 @@ long long lc_nn_bn_scratch_floats(int C);
  * representation matrix (the Python triple loop of gpm.py:157-168) when called with korder = 1. */
 int lc_nn_im2col(const void* src, int src_kind, int N, int H, int W, int C, int ks, int stride, int pad, int korder, void* col_bf16, long long ld_col,
                  void* colT_bf16, long long ld_colT, int Kp, lc_stream_t stream);
+/* The same patch matrix in fp32 (K unpadded): GPM's representation matrices feed an SVD (gpm.py:157-168, 170-204). */
+int lc_nn_im2col_f32(const void* src, int src_kind, int N, int H, int W, int C, int ks, int stride, int pad, int korder, float* col, long long ld_col, float* colT,
+                     long long ld_colT, lc_stream_t stream);
 /* Data gradient of a conv from dcol = dY * W ([M][ld] BF16): dx (fp32 NHWC) = addend + fold(dcol). */
 int lc_nn_col2im(const void* dcol_bf16, long long ld, const float* addend, float* dx, int N, int H, int W, int C, int ks, int stride, int pad, int korder,
                  lc_stream_t stream);

@@ -74,6 +74,7 @@ SIGNATURES = {
     "lc_conv_gemm_bf16": (c_int, [P, P, P]),
     "lc_nn_bn_scratch_floats": (c_longlong, [c_int]),
     "lc_nn_im2col": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_longlong, P, c_longlong, c_int, P]),
+    "lc_nn_im2col_f32": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_longlong, P, c_longlong, P]),
     "lc_nn_col2im": (c_int, [P, c_longlong, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "lc_nn_bn_stats": (c_int, [P, c_longlong, c_int, P, P, c_float, c_float, P, P, P, P]),
     "lc_nn_bn_eval_affine": (c_int, [P, c_int, P, P, c_float, P, P]),

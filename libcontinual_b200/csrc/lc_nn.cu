@@ -34,7 +34,25 @@ int lc_nn_im2col(const void* src, int src_kind, int N, int H, int W, int C, int 
         return lc_launch_status();
     }
     dim3 grid((unsigned)((mspan + 63) / 64), (unsigned)((Kp + 63) / 64));
-    im2col_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    im2col_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    return lc_launch_status();
+}
+
+int lc_nn_im2col_f32(const void* src, int src_kind, int N, int H, int W, int C, int ks, int stride, int pad, int korder, float* col, long long ld_col, float* colT,
+                     long long ld_colT, lc_stream_t stream) {
+    LC_CHECK_ARG(src && (col || colT) && N >= 1 && H >= 1 && W >= 1 && C >= 1 && ks >= 1 && stride >= 1 && pad >= 0 && src_kind >= 0 && src_kind <= 2 &&
+                 (korder == 0 || korder == 1));
+    Im2colArgs a{};
+    a.src = src; a.src_kind = src_kind; a.N = N; a.H = H; a.W = W; a.C = C; a.ks = ks; a.stride = stride; a.pad = pad; a.korder = korder;
+    a.Ho = (H + 2 * pad - ks) / stride + 1; a.Wo = (W + 2 * pad - ks) / stride + 1;
+    LC_CHECK_ARG(a.Ho >= 1 && a.Wo >= 1);
+    a.K = ks * ks * C; a.Kp = a.K;
+    a.M = (long long)N * a.Ho * a.Wo;
+    LC_CHECK_ARG((col == nullptr || ld_col >= a.K) && (colT == nullptr || ld_colT >= a.M));
+    a.col = reinterpret_cast<__nv_bfloat16*>(col); a.ld_col = ld_col; a.colT = reinterpret_cast<__nv_bfloat16*>(colT); a.ld_colT = ld_colT;
+    const long long mspan = colT != nullptr ? ld_colT : a.M;
+    dim3 grid((unsigned)((mspan + 63) / 64), (unsigned)((a.K + 63) / 64));
+    im2col_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     return lc_launch_status();
 }
 

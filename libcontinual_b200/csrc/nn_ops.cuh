@@ -65,8 +65,16 @@ __device__ __forceinline__ float im2col_fetch(const Im2colArgs& a, long long m, 
 
 // 64 (m) x 64 (k) tile per block: the load phase runs k-fastest (coalesced reads of NHWC channels, coalesced writes of `col`), the transposed
 // copy leaves through shared memory m-fastest
+template <typename OutT> __device__ __forceinline__ OutT im2col_cvt(float v);
+template <> __device__ __forceinline__ __nv_bfloat16 im2col_cvt<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ float im2col_cvt<float>(float v) { return v; }
+
+// OutT = __nv_bfloat16 (GEMM operands) or float (GPM's representation matrices, which feed an SVD: gpm.py:157-168)
+template <typename OutT>
 __global__ void __launch_bounds__(256) im2col_kernel(Im2colArgs a) {
-    __shared__ __nv_bfloat16 tile[64][66];
+    __shared__ OutT tile[64][65];
+    OutT* col = reinterpret_cast<OutT*>(a.col);
+    OutT* colT = reinterpret_cast<OutT*>(a.colT);
     const long long m0 = (long long)blockIdx.x * 64;
     const int k0 = blockIdx.y * 64;
     const int lo = threadIdx.x & 63, hi4 = threadIdx.x >> 6;
@@ -75,18 +83,18 @@ __global__ void __launch_bounds__(256) im2col_kernel(Im2colArgs a) {
         const int ml = hi4 + 4 * i;
         const long long m = m0 + ml;
         const int k = k0 + lo;
-        const __nv_bfloat16 v = __float2bfloat16_rn(im2col_fetch(a, m, k));
+        const OutT v = im2col_cvt<OutT>(im2col_fetch(a, m, k));
         tile[ml][lo] = v;
-        if (a.col != nullptr && m < a.M && k < a.Kp) a.col[(size_t)m * a.ld_col + k] = v;
+        if (col != nullptr && m < a.M && k < a.Kp) col[(size_t)m * a.ld_col + k] = v;
     }
-    if (a.colT == nullptr) return;
+    if (colT == nullptr) return;
     __syncthreads();
 #pragma unroll 4
     for (int i = 0; i < 16; ++i) {
         const int kl = hi4 + 4 * i;
         const int k = k0 + kl;
         const long long m = m0 + lo;
-        if (k < a.Kp && m < a.ld_colT) a.colT[(size_t)k * a.ld_colT + m] = tile[lo][kl];     // columns [M, ld_colT) get the zeros of im2col_fetch
+        if (k < a.Kp && m < a.ld_colT) colT[(size_t)k * a.ld_colT + m] = tile[lo][kl];     // columns [M, ld_colT) get the zeros of im2col_fetch
     }
 }
 

@@ -7,3 +7,4 @@ from .dualprompt import DualPrompt, DualPromptPool  # noqa: F401
 from .codaprompt import CodaPrompt, CodaPromptPool  # noqa: F401
 from .sd_lora import SD_LoRA  # noqa: F401
 from .inflora_orig import InfLoRA, SiNet_vit  # noqa: F401
+from .gpm import GPM, AlexNet_TRGP  # noqa: F401

@@ -536,3 +536,220 @@ class ResNet18Engine(NNOps):
         self.forward(x, train=False, update_running=False, params=t.params, rstat=t.rstat, ws=t.ws)
         self.head_forward(B, t.ncls, params=t.params, ws=t.ws, logits=t.logits)
         return t.logits
+
+
+# ======================================================================================================================================================
+# AlexNet_TRGP
+# ======================================================================================================================================================
+ALEXNET_SPEC = (  # name, bn, cin, cout, ks, H_in, H_out (conv) / in, out (linear), dropout p, pooled H
+    ("conv1", "bn1", 3, 64, 4, 32, 29, 0.2, 14), ("conv2", "bn2", 64, 128, 3, 14, 12, 0.2, 6), ("conv3", "bn3", 128, 256, 2, 6, 5, 0.5, 2),
+    ("fc1", "bn4", 1024, 2048, 1, 1, 1, 0.5, 1), ("fc2", "bn5", 2048, 2048, 1, 1, 1, 0.5, 1))
+
+
+def alexnet_param_layout():
+    """(name, shape) in the reference's registration order (alexnet.py:100-114)."""
+    out = []
+    for name, bn, cin, cout, ks, *_ in ALEXNET_SPEC:
+        out += [(name + ".weight", (cout, cin, ks, ks) if name.startswith("conv") else (cout, cin)), (bn + ".weight", (cout,)), (bn + ".bias", (cout,))]
+    return out
+
+
+class _ALayer:
+    __slots__ = ("name", "bn", "cin", "cout", "ks", "H", "Ho", "p", "Hp", "K", "w_off", "g_off", "b_off", "wk", "wT", "col", "colT", "y", "aff", "a", "pool_f32",
+                 "pool_bf", "idx", "M", "Mp", "nsplit")
+
+
+class AlexNetEngine(NNOps):
+    """`AlexNet_TRGP.forward` (alexnet.py:124-156) + backward.  Every layer is patch matrix -> tcgen05 GEMM (K in weight.view(out, -1) order, the order
+    of GPM's bases) -> BatchNorm with batch statistics (track_running_stats=False: also in eval) -> ReLU -> dropout -> MaxPool2d(2).  The trainable
+    arena `theta` holds the backbone parameters in registration order followed by the per-task bias-free heads (gpm.py:29-32)."""
+
+    def __init__(self, max_batch: int = 128, head_sizes=(10,), device=None):
+        super().__init__(device)
+        dev = self.device
+        self.dev = dev
+        self.max_batch, self.feat_dim, self.img, self.in_ch = max_batch, 2048, 32, 3
+        self.layout = alexnet_param_layout()
+        self.param_off: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        off = 0
+        for name, shape in self.layout:
+            n = 1
+            for d in shape:
+                n *= d
+            self.param_off[name] = (off, shape)
+            off += n
+        self.n_backbone = off
+        self.head_sizes = list(head_sizes)
+        self.head_off = []
+        for n in self.head_sizes:
+            self.head_off.append(off)
+            off += n * self.feat_dim
+        self.n_total = _up(off, 4)
+        self.theta = torch.zeros(self.n_total, device=dev)
+        self.theta_grad = torch.zeros(self.n_total, device=dev)
+        B = max_batch
+        f32, bf = torch.float32, torch.bfloat16
+        e = lambda *s, dt=f32: torch.zeros(*s, device=dev, dtype=dt)
+        self.layers: List[_ALayer] = []
+        for (name, bn, cin, cout, ks, H, Ho, p, Hp) in ALEXNET_SPEC:
+            L = _ALayer()
+            L.name, L.bn, L.cin, L.cout, L.ks, L.H, L.Ho, L.p, L.Hp = name, bn, cin, cout, ks, H, Ho, p, Hp
+            L.K = cin * ks * ks
+            L.M = B * Ho * Ho
+            L.Mp = _up(L.M, 8)
+            L.w_off, L.g_off, L.b_off = self.param_off[name + ".weight"][0], self.param_off[bn + ".weight"][0], self.param_off[bn + ".bias"][0]
+            L.wk, L.wT = e(cout, L.K, dt=bf), e(L.K, cout, dt=bf)
+            L.col, L.colT = e(L.M, L.K, dt=bf), e(L.K, L.Mp, dt=bf)
+            L.y, L.aff, L.a = e(L.M, cout), e(4 * cout), e(L.M, cout)
+            if name.startswith("conv"):
+                L.pool_f32, L.pool_bf = e(B * Hp * Hp, cout), e(B * Hp * Hp, cout, dt=bf)
+                L.idx = torch.zeros(B * Hp * Hp, cout, device=dev, dtype=torch.uint8)
+            L.nsplit = self.wgrad_splits(cout, L.K, L.M)
+            self.layers.append(L)
+        self.a_bf = [e(B, 2048, dt=bf) for _ in range(2)]          # BF16 copies of the linear layers' outputs (next GEMM operand)
+        gmax = max(L.M * L.cout for L in self.layers)
+        self.G = [e(gmax), e(gmax)]
+        self.dy_bf = e(gmax, dt=bf)
+        self.dyT = e(max(L.cout * L.Mp for L in self.layers), dt=bf)
+        self.dcol = e(max(L.M * L.K for L in self.layers[1:]), dt=bf)
+        self.wpart = e(max(L.nsplit * L.cout * _up(L.K, 4) for L in self.layers))
+        self.dpool = e(max(B * L.Hp * L.Hp * L.cout for L in self.layers[:3]))
+        ncls = max(self.head_sizes)
+        self.cap = ncls
+        self.logits_all = e(B, sum(self.head_sizes))
+        self.logits = e(B, ncls)
+        self.dlogits = e(B, ncls)
+        self.pred = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.scal = e(8)
+        self.dfeat = e(B, 2048)
+        self.rng = torch.tensor([0x5EED, 0], dtype=torch.int64, device=dev)      # dropout: {seed, step}
+        self.yshift = torch.zeros(B, dtype=torch.int64, device=dev)
+
+    # ---- views -----------------------------------------------------------------------------------------------------------------------------------
+    def param_view(self, name: str, arena: Optional[torch.Tensor] = None) -> torch.Tensor:
+        off, shape = self.param_off[name]
+        n = 1
+        for d in shape:
+            n *= d
+        return (self.theta if arena is None else arena)[off:off + n].view(shape)
+
+    def head_view(self, t: int, arena: Optional[torch.Tensor] = None) -> torch.Tensor:
+        a = self.theta if arena is None else arena
+        return a[self.head_off[t]:self.head_off[t] + self.head_sizes[t] * self.feat_dim].view(self.head_sizes[t], self.feat_dim)
+
+    def features(self, batch: int) -> torch.Tensor:
+        return self.layers[-1].a[:batch]
+
+    # ---- forward ---------------------------------------------------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, train: bool, need_backward: Optional[bool] = None):
+        """train: dropout on (masks from the device-side {seed, step} pair).  BatchNorm uses batch statistics in either mode."""
+        B = x.shape[0]
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape[1:]) == (3, 32, 32) and B <= self.max_batch
+        need_backward = train if need_backward is None else need_backward
+        th = self.theta
+        src, kind, Hin, Cin = x.data_ptr(), SRC_NCHW_F32, 32, 3
+        for i, L in enumerate(self.layers):
+            M = B * L.Ho * L.Ho
+            self.pack(_p(th, L.w_off), L.cout, L.cin, L.ks, KORDER_C_TAP, 0, L.wk.data_ptr(), L.K)
+            if i == 3:                       # x.view(B, -1) of the NCHW tensor (alexnet.py:144): a 2x2 "patch" in (c, kh, kw) order is exactly that flatten
+                self.im2col(src, kind, B, 2, 2, 256, 2, 1, 0, KORDER_C_TAP, L.col.data_ptr(), L.K, L.colT.data_ptr() if need_backward else None, _up(M, 8), L.K)
+            elif i == 4:
+                self.cast_transpose(self.layers[3].a.data_ptr(), B, 2048, L.col.data_ptr(), L.K, L.colT.data_ptr() if need_backward else None, _up(M, 8))
+            else:
+                self.im2col(src, kind, B, Hin, Hin, Cin, L.ks, 1, 0, KORDER_C_TAP, L.col.data_ptr(), L.K, L.colT.data_ptr() if need_backward else None, _up(M, 8), L.K)
+            self.gemm(L.col.data_ptr(), L.K, L.wk.data_ptr(), L.K, L.y.data_ptr(), L.cout, M, L.cout, L.K)
+            self.bn_stats(L.y.data_ptr(), M, L.cout, _p(th, L.g_off), _p(th, L.b_off), None, L.aff.data_ptr())
+            self.bn_act(L.y.data_ptr(), L.aff.data_ptr(), M, L.cout, drop_p=L.p if train else 0.0, rng=self.rng.data_ptr() if train else None, rng_stream=i,
+                        out_f32=L.a.data_ptr())
+            if i < 3:
+                check(self.lib.lc_nn_maxpool_forward(L.a.data_ptr(), B, L.Ho, L.Ho, L.cout, 2, 2, 0, L.pool_f32.data_ptr(), L.pool_bf.data_ptr(), L.idx.data_ptr(),
+                                                     stream_ptr()), "lc_nn_maxpool_forward")
+                self.launches += 1
+                src, kind, Hin, Cin = L.pool_bf.data_ptr(), SRC_NHWC_BF16, L.Hp, L.cout
+
+    def heads_forward(self, batch: int, task: Optional[int] = None):
+        """logits of one head into `logits` (training), or of every head side by side into `logits_all` (gpm.py:34-41)."""
+        feat = self.layers[-1].a
+        if task is not None:
+            check(self.lib.lc_linear_head(feat.data_ptr(), _p(self.theta, self.head_off[task]), None, batch, self.head_sizes[task], 2048, self.logits.data_ptr(),
+                                          self.cap, stream_ptr()), "lc_linear_head")
+            self.launches += 1
+            return self.logits[:batch, :self.head_sizes[task]]
+        tot = sum(self.head_sizes)
+        check(self.lib.lc_linear_head(feat.data_ptr(), _p(self.theta, self.head_off[0]), None, batch, tot, 2048, self.logits_all.data_ptr(), tot, stream_ptr()),
+              "lc_linear_head")                   # the heads are contiguous rows of one [total][2048] matrix
+        self.launches += 1
+        return self.logits_all[:batch]
+
+    def loss_backward_head(self, y_shifted: torch.Tensor, batch: int, task: int):
+        n = self.head_sizes[task]
+        check(self.lib.lc_loss_ce_kd(self.logits.data_ptr(), self.cap, None, self.cap, y_shifted.data_ptr(), batch, 0, n, 0, 0.0, 2.0, n, self.dlogits.data_ptr(),
+                                     self.pred.data_ptr(), self.scal.data_ptr(), stream_ptr()), "lc_loss_ce_kd")
+        check(self.lib.lc_linear_head_backward(self.dlogits.data_ptr(), self.cap, self.layers[-1].a.data_ptr(), _p(self.theta, self.head_off[task]), n, batch, 2048,
+                                               _p(self.theta_grad, self.head_off[task]), None, self.dfeat.data_ptr(), stream_ptr()), "lc_linear_head_backward")
+        self.launches += 2
+
+    # ---- backward --------------------------------------------------------------------------------------------------------------------------------
+    def backward(self, batch: int):
+        """From `dfeat` = d(loss)/d(features) to the gradient of every backbone parameter (in `theta_grad`)."""
+        B, th, g = batch, self.theta, self.theta_grad
+        gin = self.dfeat
+        for i in range(4, -1, -1):
+            L = self.layers[i]
+            M = B * L.Ho * L.Ho
+            Mp = _up(M, 8)
+            if i < 3:        # gradient arrives at the pooled map: route it back to the window maxima
+                check(self.lib.lc_nn_maxpool_backward(gin.data_ptr(), L.idx.data_ptr(), B, L.Ho, L.Ho, L.cout, 2, 2, 0, self.G[0].data_ptr(), stream_ptr()),
+                      "lc_nn_maxpool_backward")
+                self.launches += 1
+                gin = self.G[0]
+            # BN + ReLU + dropout (a kept unit carries 1/(1-p), a dropped one is stored as 0: one mask)
+            self.bn_bwd(gin.data_ptr(), L.y.data_ptr(), L.aff.data_ptr(), M, L.cout, act_f32=L.a.data_ptr(), gscale=1.0 / (1.0 - L.p) if self._train_step else 1.0,
+                        dgamma=_p(g, L.g_off), dbeta=_p(g, L.b_off), dy_bf16=self.dy_bf.data_ptr())
+            # dW = dY^T col
+            self.transpose_bf16(self.dy_bf.data_ptr(), L.cout, M, L.cout, self.dyT.data_ptr(), Mp)
+            ns, ldp = self.wgrad_splits(L.cout, L.K, M), _up(L.K, 4)
+            if ns > 1:
+                self.gemm(self.dyT.data_ptr(), Mp, L.colT.data_ptr(), Mp, self.wpart.data_ptr(), ldp, L.cout, L.K, Mp, ksplit=ns, stride_split=L.cout * ldp)
+                self.wgrad_reduce(self.wpart.data_ptr(), ns, L.cout, L.cin, L.ks, KORDER_C_TAP, ldp, _p(g, L.w_off))
+            else:
+                self.gemm(self.dyT.data_ptr(), Mp, L.colT.data_ptr(), Mp, _p(g, L.w_off), L.K, L.cout, L.K, Mp)
+            if i == 0:
+                break
+            # d(input) = fold(dY W)
+            self.pack(_p(th, L.w_off), L.cout, L.cin, L.ks, KORDER_C_TAP, 1, L.wT.data_ptr(), L.cout)
+            P = self.layers[i - 1]
+            if i == 4:
+                self.gemm(self.dy_bf.data_ptr(), L.cout, L.wT.data_ptr(), L.cout, self.G[1].data_ptr(), L.K, M, L.K, L.cout)      # fp32 d(a4) directly
+                gin = self.G[1]
+            else:
+                self.gemm(self.dy_bf.data_ptr(), L.cout, L.wT.data_ptr(), L.cout, self.dcol.data_ptr(), L.K, M, L.K, L.cout, out_f32=False)
+                if i == 3:
+                    self.col2im(self.dcol.data_ptr(), L.K, None, self.dpool.data_ptr(), B, 2, 2, 256, 2, 1, 0, KORDER_C_TAP)
+                else:
+                    self.col2im(self.dcol.data_ptr(), L.K, None, self.dpool.data_ptr(), B, P.Hp, P.Hp, P.cout, L.ks, 1, 0, KORDER_C_TAP)
+                gin = self.dpool
+
+    _train_step = True
+
+    # ---- GPM's representation matrices (gpm.py:144-168) on the device ------------------------------------------------------------------------------------
+    def representation_matrices(self, x125: torch.Tensor, batch_list=(24, 100, 100)) -> List[torch.Tensor]:
+        """Eval-mode forward of the 125 selected samples, then per TRGP layer the fp32 matrix whose columns are the layer's input patches:
+        conv: [Cin*k*k][n*s*s] of the first 24 / 100 / 100 samples (the reference's Python triple loop, here one im2col launch each); linear: input^T."""
+        B = x125.shape[0]
+        self.forward(x125, train=False, need_backward=False)
+        mats = []
+        srcs = [(x125.data_ptr(), SRC_NCHW_F32, 32, 3)] + [(L.pool_f32.data_ptr(), SRC_NHWC_F32, L.Hp, L.cout) for L in self.layers[:2]]
+        for (ptr, kind, H, C), L, n in zip(srcs, self.layers[:3], batch_list):
+            n = min(n, B)
+            M = n * L.Ho * L.Ho
+            m = torch.empty(L.K, M, device=self.device)
+            check(self.lib.lc_nn_im2col_f32(ptr, kind, n, H, H, C, L.ks, 1, 0, KORDER_C_TAP, None, 0, m.data_ptr(), M, stream_ptr()), "lc_nn_im2col_f32")
+            mats.append(m)
+        f0 = torch.empty(1024, B, device=self.device)
+        check(self.lib.lc_nn_im2col_f32(self.layers[2].pool_f32.data_ptr(), SRC_NHWC_F32, B, 2, 2, 256, 2, 1, 0, KORDER_C_TAP, None, 0, f0.data_ptr(), B, stream_ptr()),
+              "lc_nn_im2col_f32")
+        mats.append(f0)
+        mats.append(self.layers[3].a[:B].t().contiguous())
+        self.launches += 4
+        return mats

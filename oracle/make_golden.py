@@ -1114,6 +1114,85 @@ def golden_inflora_orig(core):
     np.savez_compressed(os.path.join(OUT, "inflora_orig_vit.npz"), **out)
 
 
+def synth_alexnet_state(seed: int, n_tasks: int = 3, cls_per_task: int = 10):
+    rng = np.random.default_rng(seed)
+    p = port.alexnet_init(rng)
+    b = 1.0 / np.sqrt(2048)
+    heads = [torch.from_numpy(rng.uniform(-b, b, (cls_per_task, 2048)).astype(np.float32)) for _ in range(n_tasks)]
+    return p, heads
+
+
+def golden_gpm(core):
+    """The real `GPM` on the real `AlexNet_TRGP` (gpm.py:43-206, alexnet.py:94-156), network in eval() so that dropout is off (BatchNorm has
+    track_running_stats=False and normalises with batch statistics in either mode): task-0 step, basis construction from 125 samples, task-1 step with
+    the projected gradients and frozen BN affine, basis growth."""
+    import core.model as M
+    from core.model.backbone.alexnet import AlexNet_TRGP
+    print("GPM / AlexNet_TRGP")
+    B = 16
+    p, heads = synth_alexnet_state(4040)
+    out = {}
+    bb = AlexNet_TRGP()
+    bb.load_state_dict(p, strict=True)
+    ref = M.GPM(bb, torch.device("cpu"), init_cls_num=10, inc_cls_num=10, task_num=3)
+    with torch.no_grad():
+        for t in range(3):
+            ref.network.classifiers[t].weight.copy_(heads[t])
+    orc = port.GPMOracle(p, heads, 10, 10, lr=0.01)
+    rng = np.random.default_rng(4141)
+    pool = torch.from_numpy(rng.standard_normal((160, 3, 32, 32)).astype(np.float32))
+
+    def named_grads():
+        d = {n: q.grad.clone() for n, q in ref.network.named_parameters() if q.grad is not None}
+        return {k.replace("backbone.", ""): v for k, v in d.items()}
+
+    def both(x, y, tag):
+        opt = torch.optim.SGD([q for q in ref.network.parameters()], lr=0.01)
+        ref.network.eval()
+        opt.zero_grad()
+        pred, acc, loss = ref.observe({"image": x, "label": y})
+        grads = named_grads()
+        opt.step()
+        out[tag + "/loss"] = np.float64(loss.item()); out[tag + "/pred"] = pred.numpy().copy()
+        summarize(tag + "/grad", grads, out)
+        po, ao, lo, go = orc.step(x, y)
+        close(lo, loss.detach(), 1e-5, 1e-6, tag + " loss")
+        assert torch.equal(po, pred)
+        assert set(go.keys()) == set(grads.keys()), (sorted(go.keys()), sorted(grads.keys()))
+        worst = max(float((go[n] - grads[n]).abs().max() / (grads[n].abs().max() + 1e-12)) for n in grads)
+        print(f"   worst rel grad err over all tensors: {worst:.3e}")
+        assert worst < 1e-3
+
+    def task_boundary(task, x_all):
+        loader = [{"image": x_all[i:i + 40]} for i in range(0, x_all.shape[0], 40)]
+        torch.manual_seed(900 + task)
+        ref.after_task(task, None, loader, None)
+        torch.manual_seed(900 + task)
+        sel = torch.randperm(x_all.size(0))[:125]
+        orc.after_task(x_all[sel])
+        ranks = [f.shape[1] for f in ref.feature_list]
+        assert ranks == [f.shape[1] for f in orc.feature_list], (ranks, [f.shape[1] for f in orc.feature_list])
+        out[f"t{task}/rank"] = np.array(ranks)
+        prng = np.random.default_rng(77 + task)
+        for i, (fr, fo) in enumerate(zip(ref.feature_list, orc.feature_list)):
+            v = prng.standard_normal(fr.shape[0])
+            pr, po = fr @ (fr.T @ v), fo @ (fo.T @ v)
+            close(po, pr, 1e-5, 1e-6, f"t{task} projector of layer {i} on a probe vector (rank {fr.shape[1]})")
+            out[f"t{task}/proj_probe/{i}"] = pr
+        print("   ranks", ranks)
+
+    ref.before_task(0, None, None, None); orc.before_task(0)
+    x, y = pool[:B], torch.from_numpy(rng.integers(0, 10, (B,)).astype(np.int64))
+    both(x, y, "t0s0")
+    task_boundary(0, pool[:150])
+    ref.before_task(1, None, None, None); orc.before_task(1)
+    for s_ in range(2):
+        x, y = pool[20 + 16 * s_:36 + 16 * s_], torch.from_numpy(rng.integers(10, 20, (B,)).astype(np.int64))
+        both(x, y, f"t1s{s_}")
+    task_boundary(1, pool[10:160])
+    np.savez_compressed(os.path.join(OUT, "gpm_alexnet.npz"), **out)
+
+
 def main():
     torch.set_num_threads(8)
     os.makedirs(OUT, exist_ok=True)
@@ -1137,6 +1216,7 @@ def main():
     golden_sdlora(core)
     golden_dualgpm(core)
     golden_inflora_orig(core)
+    golden_gpm(core)
     print("golden vectors written to", OUT)
 
 

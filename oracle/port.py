@@ -700,6 +700,161 @@ def gpm_project(grad: Tensor, feature_mat: Tensor) -> Tensor:
 
 
 # ----------------------------------------------------------------------------------------------
+# AlexNet_TRGP + GPM  (core/model/backbone/alexnet.py:94-156, core/model/gpm.py:22-204)
+# ----------------------------------------------------------------------------------------------
+ALEXNET_LAYERS = (("conv1", "bn1", (64, 3, 4, 4)), ("conv2", "bn2", (128, 64, 3, 3)), ("conv3", "bn3", (256, 128, 2, 2)), ("fc1", "bn4", (2048, 1024)),
+                  ("fc2", "bn5", (2048, 2048)))
+ALEXNET_DROP = (0.2, 0.2, 0.5, 0.5, 0.5)          # dropout1 after conv1 / conv2, dropout2 after conv3 / fc1 / fc2 (alexnet.py:127-154)
+
+
+def alexnet_layout() -> List[Tuple[str, Tuple[int, ...]]]:
+    """Parameter (name, shape) list in the reference's registration order (alexnet.py:100-114); no buffers (track_running_stats=False)."""
+    out = []
+    for w, bn, shape in ALEXNET_LAYERS:
+        out += [(w + ".weight", shape), (bn + ".weight", (shape[0],)), (bn + ".bias", (shape[0],))]
+    return out
+
+
+def alexnet_init(rng: np.random.Generator) -> Dict[str, Tensor]:
+    """nn.Conv2d / nn.Linear default init DISTRIBUTIONS (kaiming_uniform(a=sqrt(5)) = U(-1/sqrt(fan_in), 1/sqrt(fan_in))), BN weight 1 / bias 0."""
+    p = {}
+    for name, shape in alexnet_layout():
+        if len(shape) >= 2:
+            fan_in = int(np.prod(shape[1:]))
+            b = 1.0 / math.sqrt(fan_in)
+            p[name] = torch.from_numpy(rng.uniform(-b, b, shape).astype(np.float32))
+        elif name.endswith(".weight"):
+            p[name] = torch.ones(shape)
+        else:
+            p[name] = torch.zeros(shape)
+    return p
+
+
+class _BF16Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return F.linear(x.bfloat16().float(), w.bfloat16().float())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dyr = dy.bfloat16().float()
+        return dyr @ w.bfloat16().float(), dyr.t() @ x.bfloat16().float()
+
+
+def alexnet_forward(p: Dict[str, Tensor], x: Tensor, masks: Optional[Sequence[Tensor]] = None, gemm_mode: str = "fp32", keep: Optional[dict] = None) -> Tensor:
+    """`AlexNet_TRGP.forward` (alexnet.py:124-156): [conv -> BN(batch statistics, always: track_running_stats=False) -> ReLU -> dropout -> maxpool(2)] x 3,
+    flatten (NCHW order), [linear -> BN1d -> ReLU -> dropout] x 2.  `masks`: five keep-masks (train mode; survivors are scaled by 1/(1-p)); None = eval
+    (no dropout).  `keep` (optional dict) receives the INPUT of every TRGP layer, what `compute_input_matrix=True` stashes (alexnet.py:36-37,78-79)."""
+    conv = (lambda h, w: _BF16Conv.apply(h, w, 1, 0)) if gemm_mode == "bf16" else (lambda h, w: F.conv2d(h, w))
+    lin = (lambda h, w: _BF16Linear.apply(h, w)) if gemm_mode == "bf16" else (lambda h, w: F.linear(h, w))
+    h = x
+    for i, (wn, bn, shape) in enumerate(ALEXNET_LAYERS):
+        if i == 3:
+            h = h.reshape(h.shape[0], -1)
+        if keep is not None:
+            keep[wn] = h.detach()
+        h = conv(h, p[wn + ".weight"]) if i < 3 else lin(h, p[wn + ".weight"])
+        h = F.relu(F.batch_norm(h, None, None, p[bn + ".weight"], p[bn + ".bias"], True, 0.1, 1e-5))
+        if masks is not None:
+            h = h * masks[i].to(h.dtype) / (1.0 - ALEXNET_DROP[i])
+        if i < 3:
+            h = F.max_pool2d(h, 2)
+    return h
+
+
+def gpm_representation_matrices(inputs: Dict[str, Tensor]) -> List[np.ndarray]:
+    """gpm.py:144-168: im2col of the first 24 / 100 / 100 stashed conv inputs (the reference's Python triple loop, restated with unfold: column
+    (n, i, j) = the (c, kh, kw)-flattened patch at (i, j)), and the transposed 125-sample inputs of the two linear layers."""
+    mats = []
+    for (wn, _, shape), bsz in zip(ALEXNET_LAYERS[:3], (24, 100, 100)):
+        act = inputs[wn][:bsz].double()
+        cols = F.unfold(act, shape[2])                                   # [bsz][C*k*k][s*s], positions row-major (i, j)
+        mats.append(cols.permute(1, 0, 2).reshape(cols.shape[1], -1).numpy())
+    for wn, _, _ in ALEXNET_LAYERS[3:]:
+        mats.append(inputs[wn].double().numpy().T)
+    return mats
+
+
+def gpm_update_bases(feature_list: List[np.ndarray], mats: Sequence[np.ndarray], task_idx: int) -> List[np.ndarray]:
+    """gpm.py:170-204: grow the per-layer bases so that they hold `threshold = 0.97 + 0.003 * task_idx` of each representation's energy."""
+    threshold = 0.97 + task_idx * 0.003
+    if task_idx == 0:
+        out = []
+        for activation in mats:
+            U, S, _ = np.linalg.svd(activation, full_matrices=False)
+            ratio = (S ** 2) / (S ** 2).sum()
+            r = int(np.sum(np.cumsum(ratio) < threshold))
+            out.append(U[:, :r])
+        return out
+    out = list(feature_list)
+    for i, activation in enumerate(mats):
+        _, S, _ = np.linalg.svd(activation, full_matrices=False)
+        total = (S ** 2).sum()
+        act_hat = activation - out[i] @ out[i].T @ activation
+        U, S, _ = np.linalg.svd(act_hat, full_matrices=False)
+        hat = (S ** 2).sum()
+        ratio = (S ** 2) / total
+        accumulated = (total - hat) / total
+        if accumulated >= threshold:
+            continue
+        r = int(np.sum(np.cumsum(ratio) + accumulated < threshold)) + 1
+        Ui = np.hstack((out[i], U[:, :r]))
+        out[i] = Ui[:, :min(Ui.shape[0], Ui.shape[1])]
+    return out
+
+
+class GPMOracle:
+    """`GPM` (gpm.py:43-206) on AlexNet_TRGP: per-task bias-free heads, CE on the current head, gradient projection of the five TRGP layers for
+    task > 0, BN affine frozen after task 0, plain SGD."""
+
+    def __init__(self, p: Dict[str, Tensor], heads: Sequence[Tensor], init_cls: int, inc_cls: int, lr: float = 0.01, gemm_mode: str = "fp32"):
+        self.p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+        self.heads = [h.clone().requires_grad_(True) for h in heads]
+        self.init_cls, self.inc_cls, self.lr, self.gemm_mode = init_cls, inc_cls, lr, gemm_mode
+        self.cur_task, self.known = 0, 0
+        self.feature_list: List[np.ndarray] = []
+        self.feature_mat: List[Tensor] = []
+
+    def before_task(self, task_idx: int):
+        self.cur_task = task_idx
+        if task_idx == 1:
+            self.known += self.init_cls
+        elif task_idx > 1:
+            self.known += self.inc_cls
+        if task_idx > 0:
+            self.feature_mat = [torch.tensor(f @ f.T, dtype=torch.float32) for f in self.feature_list]
+
+    def trainable(self) -> Dict[str, Tensor]:
+        d = {k: v for k, v in self.p.items() if not (self.cur_task > 0 and "bn" in k)}
+        d[f"classifiers.{self.cur_task}.weight"] = self.heads[self.cur_task]
+        return d
+
+    def step(self, x: Tensor, y: Tensor, masks=None, apply_update: bool = True):
+        feat = alexnet_forward(self.p, x, masks, self.gemm_mode)
+        logits = F.linear(feat, self.heads[self.cur_task])
+        loss = F.cross_entropy(logits, y - self.known)
+        tr = self.trainable()
+        grads = dict(zip(tr.keys(), torch.autograd.grad(loss, list(tr.values()))))
+        if self.cur_task > 0:
+            for i, (wn, _, _) in enumerate(ALEXNET_LAYERS):
+                grads[wn + ".weight"] = gpm_project(grads[wn + ".weight"], self.feature_mat[i])
+        pred = logits.argmax(1)
+        if apply_update:
+            with torch.no_grad():
+                for k, v in tr.items():
+                    v.sub_(self.lr * grads[k])
+        return pred, float((pred == (y - self.known)).sum()) / x.shape[0], loss.detach(), grads
+
+    def after_task(self, x125: Tensor):
+        keep = {}
+        with torch.no_grad():
+            alexnet_forward({k: v.detach() for k, v in self.p.items()}, x125, None, self.gemm_mode, keep=keep)
+        self.feature_list = gpm_update_bases(self.feature_list, gpm_representation_matrices(keep), self.cur_task)
+
+
+# ----------------------------------------------------------------------------------------------
 # InfLoRA_OPT weight-side LoRA (core/model/backbone/transformer.py:246-254)
 # ----------------------------------------------------------------------------------------------
 def lora_merge_qkv(qkv_w: Tensor, A_k: Tensor, B_k: Tensor, A_v: Tensor, B_v: Tensor) -> Tensor:

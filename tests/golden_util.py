@@ -33,6 +33,14 @@ def synth_resnet18_state(seed, n_head):
     return p, b, fc_w, fc_b
 
 
+def synth_alexnet_state(seed, n_tasks=3, cls_per_task=10):
+    rng = np.random.default_rng(seed)
+    p = port.alexnet_init(rng)
+    b = 1.0 / np.sqrt(2048)
+    heads = [torch.from_numpy(rng.uniform(-b, b, (cls_per_task, 2048)).astype(np.float32)) for _ in range(n_tasks)]
+    return p, heads
+
+
 def synth_batch(seed, B, lo, hi, img=32):
     rng = np.random.default_rng(seed)
     x = torch.from_numpy(rng.standard_normal((B, 3, img, img)).astype(np.float32))

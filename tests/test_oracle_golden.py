@@ -84,6 +84,45 @@ def test_lwf_resnet18_trajectory_matches_reference():
         _run(orc, g, f"t1s{s}", *synth_batch(1910 + s, 4, 10, 20, img=64))
 
 
+def test_gpm_alexnet_matches_reference():
+    """`oracle.port.GPMOracle` (AlexNet_TRGP forward, projected gradients, basis construction / growth) against the golden written by the real `GPM`
+    on the real `AlexNet_TRGP` (oracle/make_golden.py::golden_gpm): losses, predictions, per-tensor gradient norms, basis ranks, projectors on probe vectors."""
+    from tests.golden_util import synth_alexnet_state
+    g = load("gpm_alexnet.npz")
+    p, heads = synth_alexnet_state(4040)
+    orc = port.GPMOracle(p, heads, 10, 10, lr=0.01)
+    rng = np.random.default_rng(4141)
+    pool = torch.from_numpy(rng.standard_normal((160, 3, 32, 32)).astype(np.float32))
+
+    def step(x, y, tag):
+        pred, acc, loss, grads = orc.step(x, y)
+        assert abs(float(loss) - float(g[tag + "/loss"])) <= 1e-5 * abs(float(g[tag + "/loss"])) + 1e-6
+        assert np.array_equal(pred.numpy(), g[tag + "/pred"])
+        names = [str(n) for n in g[tag + "/grad/names"]]
+        assert sorted(names) == sorted(grads.keys())
+        for i, n in enumerate(names):
+            ref = float(g[tag + "/grad/norm"][i])
+            assert abs(float(grads[n].double().norm()) - ref) <= 1e-4 * ref + 1e-7, (tag, n)
+
+    def boundary(task, x_all):
+        torch.manual_seed(900 + task)
+        sel = torch.randperm(x_all.size(0))[:125]
+        orc.after_task(x_all[sel])
+        assert [f.shape[1] for f in orc.feature_list] == list(g[f"t{task}/rank"])
+        prng = np.random.default_rng(77 + task)
+        for i, f in enumerate(orc.feature_list):
+            v = prng.standard_normal(f.shape[0])
+            assert np.allclose(f @ (f.T @ v), g[f"t{task}/proj_probe/{i}"], rtol=1e-4, atol=1e-5)
+
+    orc.before_task(0)
+    step(pool[:16], torch.from_numpy(rng.integers(0, 10, (16,)).astype(np.int64)), "t0s0")
+    boundary(0, pool[:150])
+    orc.before_task(1)
+    for s in range(2):
+        step(pool[20 + 16 * s:36 + 16 * s], torch.from_numpy(rng.integers(10, 20, (16,)).astype(np.int64)), f"t1s{s}")
+    boundary(1, pool[10:160])
+
+
 def test_l2p_select_matches_reference():
     g = load("ops_small.npz")
     rng = np.random.default_rng(404)
