@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="icarl", choices=["icarl", "ewc", "lwf18", "l2p", "inflora", "dualprompt", "codaprompt", "sdlora"])
+    ap.add_argument("--workload", default="icarl", choices=["icarl", "ewc", "lwf18", "gpm", "l2p", "inflora", "dualprompt", "codaprompt", "sdlora"])
     ap.add_argument("--cpu-steps", type=int, default=12, help="timed oracle steps for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
@@ -59,6 +59,8 @@ def workload_name(w):
     return {"icarl": "iCaRL ResNet32 CIFAR-100 b50-5-10 (task 1: CE + KD vs frozen teacher), bs=128, synthetic 32x32",
             "ewc": "EWC ResNet32 CIFAR-100 b0-10-10 (task 1: CE + lamda*Fisher penalty), bs=128, synthetic 32x32",
             "lwf18": "LwF ResNet18 Tiny-ImageNet b100-20-6 (task 1: CE on the new slice + 3*KD vs the frozen copy, 120 classes), bs=256, synthetic 64x64",
+            "gpm": "GPM AlexNet_TRGP CIFAR-100 b10-10-10 (task 1: CE on the task head + projection of the five layer gradients onto the complement of the "
+                   "stored bases, plain SGD), bs=64, synthetic 32x32",
             "l2p": "L2P ViT-B/16 CIFAR-100 b10-10-10 (task 1: query pass + prompted pass + backward to prompts, clip, Adam), bs=128, synthetic 224x224",
             "dualprompt": "DualPrompt ViT-B/16 CIFAR-100 b10-10-10 (task 1: query pass + prefix-tuned pass (g/e prompts on blocks 0-4) + backward, Adam), bs=128 per GPU, "
                           "synthetic 224x224",
@@ -714,7 +716,128 @@ def strong_leg(ctx, make_step, make_batches, K, W, global_batch=BATCH):
             "unit": "images/s", "collective": step.collective}
 
 
+def gpm_synth(seed=1993):
+    """Random-init AlexNet_TRGP + 10 task heads + orthonormal bases of the ranks the reference reaches after its first CIFAR-100 task on synthetic
+    data (tests/golden/gpm_alexnet.npz: 46 / 400 / 363 / 99 / 113)."""
+    import numpy as np
+    import torch
+    from oracle import port      # only the init helper (weights are data, not compute)
+    rng = np.random.default_rng(seed)
+    p = port.alexnet_init(rng)
+    b = 1.0 / np.sqrt(2048)
+    heads = [torch.from_numpy(rng.uniform(-b, b, (10, 2048)).astype(np.float32)) for _ in range(10)]
+    bases = [np.linalg.qr(rng.standard_normal((d, r)))[0] for d, r in ((48, 46), (576, 400), (512, 363), (1024, 99), (2048, 113))]
+    return p, heads, bases
+
+
+def time_oracle_gpm(steps, warmup, device="cpu"):
+    import numpy as np
+    import torch
+    from oracle import port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p, heads, bases = gpm_synth()
+    dev = torch.device("cuda", 0) if device == "cuda" else torch.device("cpu")
+    orc = port.GPMOracle({k: v.to(dev) for k, v in p.items()}, [h.to(dev) for h in heads], 10, 10, lr=0.01)
+    orc.feature_list = bases
+    orc.before_task(1)
+    orc.feature_mat = [f.to(dev) for f in orc.feature_mat]
+    rng = np.random.default_rng(7)
+    batches = [(torch.from_numpy(rng.standard_normal((64, 3, 32, 32)).astype(np.float32)).to(dev), torch.from_numpy(rng.integers(10, 20, (64,)).astype(np.int64)).to(dev))
+               for _ in range(2)]
+    sync = (lambda: torch.cuda.synchronize()) if device == "cuda" else (lambda: None)
+    for i in range(warmup):
+        orc.step(*batches[i % 2])
+    sync()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        orc.step(*batches[i % 2])
+    sync()
+    dt = time.perf_counter() - t0
+    return 64 * steps / dt, dt / steps * 1e3, cores
+
+
+def run_ours_gpm(args, ctx):
+    """GPM on AlexNet_TRGP (config/zz_GPM/gpm_cil-alexnet-cifar100-b10-10-10.yaml: bs 64, SGD 0.01), task 1: forward/backward + the five projections."""
+    import numpy as np
+    import torch
+    import libcontinual_b200.model as M
+    from libcontinual_b200.optim import FlatSGD
+    from libcontinual_b200.trainer import GraphedFlatStep
+    world, rank, device = ctx.world, ctx.rank, ctx.device
+    GB = 64
+    per = GB if not args.global_batch else args.global_batch // world
+    p, heads, bases = gpm_synth()
+    torch.manual_seed(1993)
+    m = M.GPM(M.AlexNet_TRGP(max_batch=GB, device=device), device, init_cls_num=10, inc_cls_num=10, task_num=10)
+    sd = {"network.backbone." + k: v for k, v in p.items()}
+    sd.update({f"network.classifiers.{t}.weight": h for t, h in enumerate(heads)})
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    m.before_task(0, None, None, None)
+    m.feature_list = bases
+    m.before_task(1, None, None, None)
+    opt = FlatSGD(m.get_parameters(None), lr=0.01, model=m)
+    rng = np.random.default_rng(7 + rank)
+    host = [(torch.from_numpy(rng.standard_normal((per, 3, 32, 32)).astype(np.float32)).pin_memory(), torch.from_numpy(rng.integers(10, 20, (per,)).astype(np.int64)).pin_memory())
+            for _ in range(8)]
+    devb = [(x.to(device), y.to(device)) for x, y in host]
+    K, W = args.steps, max(3, args.warmup)
+    step = GraphedFlatStep(m, opt, per, img=32)
+    ms_step, clocks = timed_steps(ctx, step, devb, K, W, with_clocks=True)
+    value = world * per / (ms_step * 1e-3)
+    Ke = max(10, min(K, 200))
+    for i in range(3):
+        step.run(*host[i % 8]); float(step.loss())
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(Ke):
+        step.run(*host[i % 8])
+        lossv = step.loss().item()
+    e1.record()
+    ctx.barrier()
+    e2e_ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / Ke
+    e2e = {"value": world * per / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": per * 3 * 32 * 32 * 4 + per * 8, "d2h_bytes_per_step": 4,
+           "ms_per_step": e2e_ms, "path": "libcontinual_b200.trainer.GraphedFlatStep.run(pinned host batch) + loss().item() every step"}
+    if rank != 0:
+        return None
+    # dominant work: the fc2 projection (2 * 2048 * 2048^2 = 17.2 GFLOP of the step's 21.7 GFLOP of projections, SURVEY K14) = three BF16 GEMMs
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["bf16_tflops"]) if os.path.exists(peaks_path) else 1650.0
+    g = torch.randn(2048, 2048, device=device)
+    e0.record()
+    for _ in range(20):
+        m._project(4, g)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / 20
+    flops = 3 * 2.0 * 2048 * 2048 * 2048
+    roofline = {"bound": "tensor", "achieved": flops / (us * 1e-6) / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / (us * 1e-6) / 1e12 / peak, "traffic": None,
+                "kernel": "lc_gpm_project_tc on fc2 (2048 x 2048 gradient, 2048^2 projector): split + three gemm_bf16_kernel launches (hi*hi + lo*hi + hi*lo)",
+                "us_per_launch": us, "algorithmic_flops_per_launch": flops,
+                "note": "algorithmic flops of the fp32 product the reference computes: 2*2048^3 = 17.2 GFLOP; the split costs 3x that in BF16 flops"}
+    cpu = ref_gpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ips, ms, cores = time_oracle_gpm(10, 2)
+        cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "ms_per_step": ms,
+               "sample": f"10 full GPM steps of batch 64 after 2 warm-ups (oracle/port.py GPMOracle without dropout, PyTorch CPU fp32, {cores} threads)"}
+    if world == 1 and not args.no_ref_gpu:
+        ips, ms, _ = time_oracle_gpm(100, 10, "cuda")
+        ref_gpu = {"value": ips, "unit": "images/s", "ms_per_step": ms, "steps": 100, "warmup": 10,
+                   "kind": "oracle/port.py GPMOracle = the reference's op sequence as plain PyTorch ops (no dropout), eager on cuda:0", "ours_over_ref_gpu": value / ips}
+    return {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name("gpm"), "global_batch": per * world, "per_gpu_batch": per, "parallelism": f"dp{world}", "collective": step.collective,
+                       "l2": "8 rotating input batches; the five projectors alone (26 MB) and the weights (26 MB) stream from HBM / L2 every step (no explicit flush)",
+                       "precision": "BF16 GEMM operands, fp32 accumulate; projection through a two-term BF16 split (fp32-level accuracy)",
+                       "final_loss": float(step.loss()), "tensor_core_error": m.engine.tensor_core_error()},
+            "e2e": e2e, "gpu_launches": step.launches_per_step * K, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "ref_gpu": ref_gpu, "strong": None}
+
+
 def run_ours(args, ctx, workload):
+    if workload == "gpm":
+        return run_ours_gpm(args, ctx)
     if workload in ("l2p", "inflora", "dualprompt", "codaprompt", "sdlora"):
         return run_ours_l2p(args, ctx, workload)
     import torch
