@@ -5,6 +5,7 @@
 // (native_batch_norm_backward + threshold_backward + add).
 #pragma once
 #include "common.cuh"
+#include "conv_simt.cuh"
 
 namespace lc {
 
@@ -19,15 +20,24 @@ struct BnActArgs {
     long long n4;             // number of float4 elements
     int C;
     int no_relu;              // 1: skip the final ReLU (last block of LUCIR's modified_ResNet, resnet.py:501-502)
+    BnLazy lazy;              // lazy.partial != null: scale / shift of `y` are reduced here from the producing conv's partial rows (conv_simt.cuh)
 };
 
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(BnActArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // a dependent tensor-core conv may start its data-independent prologue now
+    __shared__ double s_red[1024];
+    __shared__ __align__(16) float s_aff[128];
     const int c4n = a.C >> 2;
+    const float* scale = a.scale;
+    const float* shift = a.shift;
+    if (a.lazy.partial != nullptr) {
+        bn_lazy_affine(a.lazy, a.C, s_red, s_aff);
+        scale = s_aff; shift = s_aff + a.C;
+    }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % c4n) * 4;
         float4 v = ldg4(a.y + i * 4);
-        const float4 sc = ldg4(a.scale + c), sh = ldg4(a.shift + c);
+        const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
         v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
         if (a.res != nullptr) {
             float4 r = ldg4(a.res + i * 4);
@@ -63,6 +73,8 @@ struct BnBwdArgs {
     long long npix;
     int C;
     int mask_mode;
+    int reduce_writes_g;      // 1: the reduction pass stores the masked gradient to g_out (fused flow: no apply pass follows)
+    BnBwdLazy blazy;          // apply pass: .partial != null -> coefficients reduced here from a fused epilogue's partial rows (conv_simt.cuh)
 };
 
 __device__ __forceinline__ float4 bn_masked_grad(const BnBwdArgs& a, long long e, int c, float4 yv) {
@@ -96,6 +108,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
         const long long e = p * C + c;
         const float4 yv = ldg4(a.y + e);
         const float4 g = bn_masked_grad(a, e, c, yv);
+        if (a.reduce_writes_g) *reinterpret_cast<float4*>(a.g_out + e) = g;       // masked gradient (may alias g: one reader per element)
         s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
         s2.x = fmaf(g.x, (yv.x - mu.x) * is.x, s2.x);
         s2.y = fmaf(g.y, (yv.y - mu.y) * is.y, s2.y);
@@ -119,60 +132,29 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
         *reinterpret_cast<float4*>(a.partial + ((size_t)blockIdx.x * 2 + 0) * C + c) = r1[threadIdx.x];
         *reinterpret_cast<float4*>(a.partial + ((size_t)blockIdx.x * 2 + 1) * C + c) = r2[threadIdx.x];
     }
-    if (last_block_done(a.counter, gridDim.x)) {
-        // float4 column groups x slices of the partial rows: few, wide, independent loads (see bn_finalize_last_block)
-        double* red = reinterpret_cast<double*>(s_red);
-        constexpr int COLS = 2 * C;
-        constexpr int CQ = COLS / 4;
-        constexpr int NSL = 256 / CQ;
-        const int cq2 = threadIdx.x % CQ, sl = threadIdx.x / CQ;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        const float4* base = reinterpret_cast<const float4*>(a.partial) + cq2;
-#pragma unroll 4
-        for (int p = sl; p < (int)gridDim.x; p += NSL) {
-            const float4 v = __ldcg(base + (size_t)p * CQ);
-            a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
-        }
-        for (int k = 0; k < 4; ++k) {
-            __syncthreads();
-            red[threadIdx.x] = k == 0 ? a0 : (k == 1 ? a1 : (k == 2 ? a2 : a3));
-            __syncthreads();
-            if (threadIdx.x < CQ) {
-                double t = 0.0;
-                for (int q = 0; q < NSL; ++q) t += red[q * CQ + threadIdx.x];
-                a0 = k == 0 ? t : a0; a1 = k == 1 ? t : a1; a2 = k == 2 ? t : a2; a3 = k == 3 ? t : a3;
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x < CQ) {
-            red[threadIdx.x * 4 + 0] = a0; red[threadIdx.x * 4 + 1] = a1; red[threadIdx.x * 4 + 2] = a2; red[threadIdx.x * 4 + 3] = a3;
-        }
-        __syncthreads();
-        if (threadIdx.x < C) {
-            const int ch = threadIdx.x;
-            const double S1 = red[ch], S2 = red[C + ch], N = (double)a.npix;
-            const double sc = (double)a.scale[ch], istd = (double)a.invstd[ch], m = (double)a.mean[ch];
-            const double c1 = -sc * S2 / N * istd;
-            a.coef[ch] = (float)sc;
-            a.coef[C + ch] = (float)c1;
-            a.coef[2 * C + ch] = (float)(-sc * S1 / N - c1 * m);
-            a.dgamma[ch] = (float)S2;
-            a.dbeta[ch] = (float)S1;
-        }
-    }
+    if (last_block_done(a.counter, gridDim.x))
+        bn_bwd_finalize_last_block<C>(a.partial, (int)gridDim.x, (double)a.npix, a.scale, a.mean, a.invstd, a.coef, a.dgamma, a.dbeta, s_red);
 }
 
 // pass 2: dy = c0*g + c1*y + c2  (g masked as in pass 1); optionally writes the masked g back
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // a dependent tensor-core conv may start its data-independent prologue now
+    __shared__ double s_red[1024];
+    __shared__ __align__(16) float s_coef[192];
     const int C = a.C, c4n = C >> 2;
     const long long n4 = a.npix * c4n;
+    const float* coef = a.coef;
+    if (a.blazy.partial != nullptr) {
+        bn_bwd_lazy_coef(a.blazy, C, s_red, s_coef);
+        coef = s_coef;
+    }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % c4n) * 4;
         const long long e = i * 4;
         const float4 yv = ldg4(a.y + e);
         const float4 g = bn_masked_grad(a, e, c, yv);
-        const float4 c0 = ldg4(a.coef + c), c1 = ldg4(a.coef + C + c), c2 = ldg4(a.coef + 2 * C + c);
+        const float4 c0 = *reinterpret_cast<const float4*>(coef + c), c1 = *reinterpret_cast<const float4*>(coef + C + c),
+                     c2 = *reinterpret_cast<const float4*>(coef + 2 * C + c);
         float4 d;
         d.x = fmaf(c0.x, g.x, fmaf(c1.x, yv.x, c2.x));
         d.y = fmaf(c0.y, g.y, fmaf(c1.y, yv.y, c2.y));

@@ -34,6 +34,44 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// Column sums of a [32 lanes][16 values] register tile in 16 shuffles (instead of 16 x 5): each butterfly stage halves the number of live columns
+// per lane (keep one half, send the other to the partner).  On return every lane holds in v[0] the sum over the 32 lanes of column (lane >> 1)
+// (lanes 2k and 2k+1 both hold column k).  Fixed tree order: deterministic.
+__device__ __forceinline__ float warp_colsum16(float (&v)[16]) {
+    const unsigned lane = threadIdx.x & 31u;
+    {
+        const bool up = (lane & 16u) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float keep = up ? v[i + 8] : v[i], send = up ? v[i] : v[i + 8];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = (lane & 8u) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool up = (lane & 4u) != 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float keep = up ? v[i + 2] : v[i], send = up ? v[i] : v[i + 2];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool up = (lane & 2u) != 0;
+        const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return v[0];
+}
+
 // "last block done" election (threadFenceReduction pattern).  `counter` must be zero before the first launch and
 // resets itself (atomicInc wraps), so the same counter can be reused by consecutive launches on one stream.
 // Call from all threads after the block's partial results have been written to global memory.

@@ -29,7 +29,148 @@ struct BnStatArgs {
     float momentum;
     float eps;
     int update_running;
+    int defer;                 // 1: only write this CTA's partial row; the consumers reduce the rows themselves (BnLazy) — no election, no serial tail
 };
+
+// Consumer-side BatchNorm finalisation.  A convolution that produced `partial` rows ([nparts][2][C]: per-CTA sum and sum of squares of its output)
+// with stat.defer = 1 leaves the reduction to whoever needs scale / shift next: every consumer CTA sums the rows itself, in the same fixed order and
+// in fp64, so all CTAs (and the end-of-forward bn_finalize_layers_kernel that serves the backward pass and the running statistics) obtain bit-identical
+// coefficients — and the producer has no threadfence + atomic + last-CTA tail (measured: ~7 us of a 17 us stage-1 convolution).
+struct BnLazy {
+    const float* partial;      // null -> not lazy (use the finalised scale / shift arrays)
+    const float* gamma;
+    const float* beta;
+    int nparts;
+    float count;               // elements per channel (B*H*W)
+    float eps;
+};
+
+// Fixed-order fp64 column sums of partial[nparts][2][C] by a 256-thread CTA.  red: 1024 doubles of shared memory; on return red[0..2C) holds the sums
+// (visible to all threads).  C in {16, 32, 64}.
+// Phase 1 (no barrier): this thread's slice of the rows -> red.  Phase 2 (three barriers): combine.  Split so that a kernel can put independent
+// work (its tile copies) between the two and so that the 12 row registers of phase 1 are dead before that work's registers go live.
+__device__ __forceinline__ void bn_partial_sums_load(const float* partial, int nparts, int C, double* red) {
+    const int CQ = C >> 1, NSL = 256 / CQ;             // float4 column groups; row slices
+    const int cq = threadIdx.x % CQ, sl = threadIdx.x / CQ;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const float4* base = reinterpret_cast<const float4*>(partial) + cq;
+    // batches of 12 rows: all loads of a batch are issued before the first add, so a batch costs one L2 round trip (B = 128: one batch per thread)
+    for (int p0 = sl; p0 < nparts; p0 += 12 * NSL) {
+        float4 v[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const int p = p0 + k * NSL;
+            v[k] = p < nparts ? __ldcg(base + (size_t)p * CQ) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) { a0 += (double)v[k].x; a1 += (double)v[k].y; a2 += (double)v[k].z; a3 += (double)v[k].w; }
+    }
+    red[threadIdx.x * 4 + 0] = a0; red[threadIdx.x * 4 + 1] = a1; red[threadIdx.x * 4 + 2] = a2; red[threadIdx.x * 4 + 3] = a3;
+}
+__device__ __forceinline__ void bn_partial_sums_finish(int C, double* red) {
+    const int CQ = C >> 1, NSL = 256 / CQ;
+    __syncthreads();
+    double t = 0.0;
+    if ((int)threadIdx.x < 2 * C) {
+        const int cqi = threadIdx.x >> 2, k = threadIdx.x & 3;
+        for (int q = 0; q < NSL; ++q) t += red[(q * CQ + cqi) * 4 + k];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < 2 * C) red[threadIdx.x] = t;
+    __syncthreads();
+}
+__device__ __forceinline__ void bn_partial_sums(const float* partial, int nparts, int C, double* red) {
+    bn_partial_sums_load(partial, nparts, C, red);
+    bn_partial_sums_finish(C, red);
+}
+
+// scale / shift / mean / invstd of one channel from its sums (the one place this arithmetic lives for the lazy path)
+__device__ __forceinline__ void bn_affine_from_sums(double s1, double s2, double count, float gamma, float beta, float eps, float* sc, float* sh, float* mean,
+                                                    float* invstd, double* var_out) {
+    const double m = s1 / count;
+    double var = s2 / count - m * m;
+    if (var < 0.0) var = 0.0;
+    const double istd = 1.0 / sqrt(var + (double)eps);
+    *sc = (float)((double)gamma * istd);
+    *sh = (float)((double)beta - m * (double)gamma * istd);
+    *mean = (float)m;
+    *invstd = (float)istd;
+    *var_out = var;
+}
+
+// lazy scale / shift into shared memory: s_aff[0..C) = scale, s_aff[C..2C) = shift (all 256 threads must call; ends with a barrier)
+__device__ __forceinline__ void bn_lazy_affine_finish(const BnLazy& z, int C, double* red, float* s_aff) {
+    bn_partial_sums_finish(C, red);
+    if ((int)threadIdx.x < C) {
+        float sc, sh, m, is; double var;
+        bn_affine_from_sums(red[threadIdx.x], red[C + threadIdx.x], (double)z.count, z.gamma[threadIdx.x], z.beta[threadIdx.x], z.eps, &sc, &sh, &m, &is, &var);
+        s_aff[threadIdx.x] = sc; s_aff[C + threadIdx.x] = sh;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void bn_lazy_affine(const BnLazy& z, int C, double* red, float* s_aff) {
+    bn_partial_sums_load(z.partial, z.nparts, C, red);
+    bn_lazy_affine_finish(z, C, red, s_aff);
+}
+
+// The same for the BatchNorm BACKWARD sums: partial rows [nparts][2][C] = per-CTA (sum g, sum g*xhat) left by the fused epilogue of a tensor-core
+// data-gradient conv.  Consumers (the next data-gradient conv, the weight-gradient kernel, bn_bwd_apply_kernel) derive dy = c0*g + c1*y + c2 themselves;
+// CTA 0 of a consumer launched with write_grads also stores dgamma / dbeta.
+struct BnBwdLazy {
+    const float* partial;      // null -> not lazy (use the finalised coefficient array)
+    const float* scale;        // [C] forward affine of the BatchNorm
+    const float* mean;
+    const float* invstd;
+    float* dgamma;             // [C]
+    float* dbeta;
+    int nparts;
+    float count;
+    int write_grads;
+};
+// s_coef[0..3C) = c0, c1, c2 (all 256 threads must call; ends with a barrier)
+__device__ __forceinline__ void bn_bwd_lazy_coef_finish(const BnBwdLazy& z, int C, double* red, float* s_coef) {
+    bn_partial_sums_finish(C, red);
+    if ((int)threadIdx.x < C) {
+        const int ch = threadIdx.x;
+        const double S1 = red[ch], S2 = red[C + ch], N = (double)z.count;
+        const double sc = (double)z.scale[ch], istd = (double)z.invstd[ch], m = (double)z.mean[ch];
+        const double c1 = -sc * S2 / N * istd;
+        s_coef[ch] = (float)sc;
+        s_coef[C + ch] = (float)c1;
+        s_coef[2 * C + ch] = (float)(-sc * S1 / N - c1 * m);
+        if (z.write_grads && blockIdx.x == 0) { z.dgamma[ch] = (float)S2; z.dbeta[ch] = (float)S1; }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void bn_bwd_lazy_coef(const BnBwdLazy& z, int C, double* red, float* s_coef) {
+    bn_partial_sums_load(z.partial, z.nparts, C, red);
+    bn_bwd_lazy_coef_finish(z, C, red, s_coef);
+}
+
+// End-of-forward finalisation of every deferred layer (one CTA per layer): scale / shift / mean / invstd for the backward pass + running statistics.
+struct BnFinEntry { long long part_off, gamma_off, beta_off, rstat_off, aff_off; int C, pp, mrows, hw; };   // nparts = ceil(B*pp / mrows), count = B*hw
+static __global__ void __launch_bounds__(256) bn_finalize_layers_kernel(const BnFinEntry* tab, const float* params, float* rstat, float* ws, int batch,
+                                                                        float momentum, float eps, int update_running) {
+    __shared__ double red[1024];
+    const BnFinEntry e = tab[blockIdx.x];
+    const int nparts = (int)(((long long)batch * e.pp + e.mrows - 1) / e.mrows);
+    const float cnt = (float)((long long)batch * e.hw);
+    bn_partial_sums(ws + e.part_off, nparts, e.C, red);
+    if ((int)threadIdx.x < e.C) {
+        const int c = threadIdx.x;
+        float sc, sh, m, is; double var;
+        bn_affine_from_sums(red[c], red[e.C + c], (double)cnt, params[e.gamma_off + c], params[e.beta_off + c], eps, &sc, &sh, &m, &is, &var);
+        float* aff = ws + e.aff_off;
+        aff[c] = sc; aff[e.C + c] = sh; aff[2 * e.C + c] = m; aff[3 * e.C + c] = is;
+        if (update_running && rstat != nullptr) {
+            const double count = (double)cnt;
+            const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+            float* rm = rstat + e.rstat_off; float* rv = rm + e.C;
+            rm[c] = (float)((1.0 - (double)momentum) * (double)rm[c] + (double)momentum * (double)(red[c] / count));
+            rv[c] = (float)((1.0 - (double)momentum) * (double)rv[c] + (double)momentum * unb);
+        }
+    }
+}
 
 template <int C, int NT>
 __device__ __forceinline__ void bn_finalize_last_block(const BnStatArgs& s, int nparts, double count, float* s_red /* >= max(2*NT, 4*C) floats, 8B aligned */) {
@@ -89,6 +230,52 @@ __device__ __forceinline__ void bn_finalize_last_block(const BnStatArgs& s, int 
             s.running_mean[c] = (float)((1.0 - (double)s.momentum) * (double)s.running_mean[c] + (double)s.momentum * m);
             s.running_var[c] = (float)((1.0 - (double)s.momentum) * (double)s.running_var[c] + (double)s.momentum * unb);
         }
+    }
+}
+
+// Last CTA of a BatchNorm-backward reduction (256 threads): fixed-order fp64 sum of the per-CTA partial rows [nparts][2][C] -> the apply
+// coefficients dy = c0*g + c1*y + c2, dgamma, dbeta.  Shared by bn_bwd_reduce_kernel and the fused epilogue of the tensor-core data-gradient conv.
+template <int C>
+__device__ __forceinline__ void bn_bwd_finalize_last_block(const float* partial, int nparts, double N, const float* scale, const float* mean,
+                                                           const float* invstd, float* coef, float* dgamma, float* dbeta, float* s_red /* 512 floats */) {
+    // float4 column groups x slices of the partial rows: few, wide, independent loads (see bn_finalize_last_block)
+    double* red = reinterpret_cast<double*>(s_red);
+    constexpr int COLS = 2 * C;
+    constexpr int CQ = COLS / 4;
+    constexpr int NSL = 256 / CQ;
+    const int cq2 = threadIdx.x % CQ, sl = threadIdx.x / CQ;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const float4* base = reinterpret_cast<const float4*>(partial) + cq2;
+#pragma unroll 4
+    for (int p = sl; p < nparts; p += NSL) {
+        const float4 v = __ldcg(base + (size_t)p * CQ);
+        a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+    }
+    for (int k = 0; k < 4; ++k) {
+        __syncthreads();
+        red[threadIdx.x] = k == 0 ? a0 : (k == 1 ? a1 : (k == 2 ? a2 : a3));
+        __syncthreads();
+        if (threadIdx.x < CQ) {
+            double t = 0.0;
+            for (int q = 0; q < NSL; ++q) t += red[q * CQ + threadIdx.x];
+            a0 = k == 0 ? t : a0; a1 = k == 1 ? t : a1; a2 = k == 2 ? t : a2; a3 = k == 3 ? t : a3;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < CQ) {
+        red[threadIdx.x * 4 + 0] = a0; red[threadIdx.x * 4 + 1] = a1; red[threadIdx.x * 4 + 2] = a2; red[threadIdx.x * 4 + 3] = a3;
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+        const int ch = threadIdx.x;
+        const double S1 = red[ch], S2 = red[C + ch];
+        const double sc = (double)scale[ch], istd = (double)invstd[ch], m = (double)mean[ch];
+        const double c1 = -sc * S2 / N * istd;
+        coef[ch] = (float)sc;
+        coef[C + ch] = (float)c1;
+        coef[2 * C + ch] = (float)(-sc * S1 / N - c1 * m);
+        dgamma[ch] = (float)S2;
+        dbeta[ch] = (float)S1;
     }
 }
 

@@ -18,6 +18,10 @@
 #pragma once
 #include "conv_simt.cuh"
 
+#ifndef LC_BWD_MAXNREG
+#define LC_BWD_MAXNREG 72      // two data-gradient CTAs + one weight-gradient CTA per SM fit the register file
+#endif
+
 namespace lc {
 namespace tc {
 
@@ -134,13 +138,38 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 #define LC_TSTAMP(slot) do { } while (0)
 #endif
 
+// Fused BatchNorm backward (kernel variant BWD = 1).  The data-gradient conv of layer L produces g = d(loss)/d(ReLU output of the
+// BatchNorm in front of L); its epilogue applies that ReLU's mask, stores the masked g and accumulates the two per-channel sums
+// of the BatchNorm backward (sum g, sum g*xhat) -> per-CTA partials -> last CTA: the coefficients dy = c0*g + c1*y + c2, dgamma, dbeta.
+// The consumer kernels (the data-gradient conv and the weight-gradient kernel of the layer below) evaluate dy while staging, so
+// neither native_batch_norm_backward's reduction nor its elementwise pass exists as a launch (resnet.py:306-316 + autograd).
+struct BnBwdFuse {
+    const float* y;          // raw conv output feeding the BatchNorm being differentiated (same shape as `out`)
+    const float* mask_out;   // nullable: materialised ReLU output (mask = mask_out > 0); else mask = scale*y+shift > 0 when `scale` is set
+    const float* scale;      // [C] forward affine of that BatchNorm
+    const float* shift;
+    const float* mean;
+    const float* invstd;
+    float* partial;          // [grid][2][C]  (null -> no reduction)
+    int defer;               // 1: only write the partial row (consumers use BnBwdLazy): no election, no last-CTA tail
+    unsigned int* counter;
+    float* coef;             // out [3][C]
+    float* dgamma;           // out [C]
+    float* dbeta;            // out [C]
+};
+
 struct ConvTcArgs {
     const float* in;         // NHWC [B][W][W][C]
     const float* wtc;        // packed [9][C/4][COUT][4]  (tap, 16-byte K chunk, output channel, 4 input channels)
     float* out;              // NHWC [B][W][W][COUT]
     const float* pro_scale;  // nullable
     const float* pro_shift;
+    BnLazy pro_lazy;         // forward variant: pro_lazy.partial != null -> the prologue's scale / shift are reduced here from the producer's partial rows
     const float* addend;     // nullable (may alias out)
+    const float* pro_y;      // BWD variant, nullable: staged value = coef0[c]*in + coef1[c]*pro_y + coef2[c] (BatchNorm backward apply)
+    const float* pro_coef;   // [3][C]
+    BnBwdLazy pro_blazy;     // BWD variant: .partial != null -> the coefficients are reduced here from the producing epilogue's partial rows
+    BnBwdFuse bw;            // BWD variant
     BnStatArgs stat;         // stat.partial nullable: [ntiles][2][COUT]
     int* error_flag;         // set to 1 if the MMA completion barrier timed out
     int B;
@@ -166,12 +195,14 @@ struct ConvTcCfg {
     static constexpr int B_BYTES = 9 * BTAP;
     static constexpr int ROWTAB_BYTES = ((ROWS * 4 + 15) / 16) * 16;
     static constexpr int PART_FLOATS = 8 * 16 * 2 * 2;                 // [warp][16 cols][sum,sq] x 2 items
-    static constexpr int RED_FLOATS = 2 * NT > 4 * N ? 2 * NT : 4 * N;
+    static constexpr int RED_FLOATS = 2048;                            // 1024 doubles: bn_partial_sums / the last-CTA finalisers
     static constexpr int OFF_B = A_BYTES;
     static constexpr int OFF_ROWTAB = OFF_B + B_BYTES;
     static constexpr int OFF_PART = OFF_ROWTAB + ROWTAB_BYTES;
-    static constexpr int OFF_RED = OFF_PART + PART_FLOATS * 4;
-    static constexpr int OFF_BAR = OFF_RED + RED_FLOATS * 4;
+    static constexpr int OFF_RED = (OFF_PART + PART_FLOATS * 4 + 15) / 16 * 16;
+    static constexpr int OFF_AFF = OFF_RED + RED_FLOATS * 4;          // BWD variant: scale, shift, mean, invstd of the differentiated BatchNorm
+    static constexpr int OFF_COEF = OFF_AFF + 4 * N * 4;               // BWD variant: c0, c1, c2 of the apply evaluated in the prologue (lazy path)
+    static constexpr int OFF_BAR = OFF_COEF + 3 * N * 4;
     static constexpr size_t SMEM_BYTES = OFF_BAR + 64;
     static constexpr uint32_t TMEM_COLS = 64;
     static constexpr int ITEMS = T * (N / 16);     // (tile, 16-column block) epilogue work items: always 4
@@ -179,8 +210,8 @@ struct ConvTcCfg {
     static_assert(NT % CH == 0 && NE <= 32 && T * N == 64 && ITEMS == 4, "tiling");
 };
 
-template <int C, int W>
-__global__ void __launch_bounds__(256) conv3x3_tc_kernel(ConvTcArgs a) {
+template <int C, int W, int BWD>
+__global__ void __launch_bounds__(256) __maxnreg__(BWD ? LC_BWD_MAXNREG : 64) conv3x3_tc_kernel(ConvTcArgs a) {
     using K = ConvTcCfg<C, W>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* sA = smem_raw;
@@ -188,6 +219,7 @@ __global__ void __launch_bounds__(256) conv3x3_tc_kernel(ConvTcArgs a) {
     int* s_rowsrc = reinterpret_cast<int*>(smem_raw + K::OFF_ROWTAB);     // per staged row: source pixel index, or -1 (border)
     float* s_part = reinterpret_cast<float*>(smem_raw + K::OFF_PART);
     float* s_red = reinterpret_cast<float*>(smem_raw + K::OFF_RED);
+    float* s_aff = reinterpret_cast<float*>(smem_raw + K::OFF_AFF);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + K::OFF_BAR);   // [0] MMA done, [1] weights landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
 
@@ -220,14 +252,27 @@ __global__ void __launch_bounds__(256) conv3x3_tc_kernel(ConvTcArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // weights are already in UMMA order in global memory: one bulk copy, tracked by bar[1]
     if (tid == 32) bulk_load(smem_u32(sB), a.wtc, (uint32_t)K::B_BYTES, bar + 1);
+    if (BWD && a.bw.y != nullptr && tid < K::N) {
+        const bool bn = a.bw.scale != nullptr;
+        s_aff[tid] = bn ? a.bw.scale[tid] : 1.f; s_aff[K::N + tid] = bn ? a.bw.shift[tid] : 0.f;
+        s_aff[2 * K::N + tid] = a.bw.mean[tid]; s_aff[3 * K::N + tid] = a.bw.invstd[tid];
+    }
     __syncthreads();
     LC_TSTAMP(7);
+
+    // lazy BatchNorm coefficients, phase 1: this thread's rows of the producer's partial sums (their registers die before the tile copies start)
+    const bool lazy = !BWD && a.pro_lazy.partial != nullptr;
+    const bool blazy = BWD && a.pro_y != nullptr && a.pro_blazy.partial != nullptr;
+    if (lazy) bn_partial_sums_load(a.pro_lazy.partial, a.pro_lazy.nparts, C, reinterpret_cast<double*>(s_red));
+    if (blazy) bn_partial_sums_load(a.pro_blazy.partial, a.pro_blazy.nparts, C, reinterpret_cast<double*>(s_red));
 
     // ---- stage A: thread -> fixed 16-byte channel chunk j, rows r0, r0+RSTEP, ...  All copies are issued before any wait ---
     const int j = tid % K::CH, r0 = tid / K::CH;
     const uint32_t sA_col = smem_u32(sA) + (uint32_t)j * K::PLANE;
     const float* in_col = a.in + j * 4;
     uint32_t validmask = 0;
+    const bool proy = BWD && a.pro_y != nullptr;
+    float4 yreg[BWD ? K::NE : 1];      // BWD: the second operand of the BatchNorm-backward apply stays in registers
 #pragma unroll
     for (int i = 0; i < K::NE; ++i) {
         const int r = r0 + i * K::RSTEP;
@@ -236,12 +281,24 @@ __global__ void __launch_bounds__(256) conv3x3_tc_kernel(ConvTcArgs a) {
             const bool ok = src >= 0;
             cp_async16(sA_col + (uint32_t)r * 16, ok ? in_col + (size_t)src * C : a.in, ok ? 16u : 0u);
             validmask |= (ok ? 1u : 0u) << i;
+            if (BWD) { if (proy && ok) yreg[i] = ldg4(a.pro_y + (size_t)src * C + j * 4); }
         }
     }
     LC_TSTAMP(1);
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool pro = a.pro_scale != nullptr;
-    if (pro) { sc = ldg4(a.pro_scale + j * 4); sh = ldg4(a.pro_shift + j * 4); }
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), c2 = sh;
+    const bool pro = !BWD && (a.pro_scale != nullptr || lazy);
+    if (lazy) {      // while the tile copies are in flight: this CTA's own reduction of the producer's statistics
+        bn_lazy_affine_finish(a.pro_lazy, C, reinterpret_cast<double*>(s_red), s_aff);
+        sc = *reinterpret_cast<const float4*>(s_aff + j * 4); sh = *reinterpret_cast<const float4*>(s_aff + C + j * 4);
+    } else if (pro) { sc = ldg4(a.pro_scale + j * 4); sh = ldg4(a.pro_shift + j * 4); }
+    if (proy) {
+        if (blazy) {
+            float* s_coef = reinterpret_cast<float*>(smem_raw + K::OFF_COEF);
+            bn_bwd_lazy_coef_finish(a.pro_blazy, C, reinterpret_cast<double*>(s_red), s_coef);
+            sc = *reinterpret_cast<const float4*>(s_coef + j * 4); sh = *reinterpret_cast<const float4*>(s_coef + C + j * 4);
+            c2 = *reinterpret_cast<const float4*>(s_coef + 2 * C + j * 4);
+        } else { sc = ldg4(a.pro_coef + j * 4); sh = ldg4(a.pro_coef + C + j * 4); c2 = ldg4(a.pro_coef + 2 * C + j * 4); }
+    }
     cp_async_wait_all();
     LC_TSTAMP(2);
     // each thread transforms the chunks it copied itself: producer BN + ReLU (prologue) and round-to-nearest TF32
@@ -250,7 +307,14 @@ __global__ void __launch_bounds__(256) conv3x3_tc_kernel(ConvTcArgs a) {
         if (validmask & (1u << i)) {
             float4* p4 = reinterpret_cast<float4*>(sA + (size_t)j * K::PLANE + (size_t)(r0 + i * K::RSTEP) * 16);
             float4 v = *p4;
-            if (pro) {
+            if (BWD) {
+                if (proy) {       // dy = c0*g + c1*y + c2 (same fma order as bn_bwd_apply_kernel)
+                    v.x = fmaf(sc.x, v.x, fmaf(sh.x, yreg[i].x, c2.x));
+                    v.y = fmaf(sc.y, v.y, fmaf(sh.y, yreg[i].y, c2.y));
+                    v.z = fmaf(sc.z, v.z, fmaf(sh.z, yreg[i].z, c2.z));
+                    v.w = fmaf(sc.w, v.w, fmaf(sh.w, yreg[i].w, c2.w));
+                }
+            } else if (pro) {
                 v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
                 v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
                 v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
@@ -296,7 +360,7 @@ __global__ void __launch_bounds__(256) conv3x3_tc_kernel(ConvTcArgs a) {
     if (!done && tid == 0 && a.error_flag != nullptr) atomicExch(a.error_flag, 1);
 
     // ---- epilogue: 4 work items (tile, 16-column block); warp w reads TMEM lanes 32*(w%4).., warp group w/4 takes 2 items ------
-    const bool stats = a.stat.partial != nullptr;
+    const bool stats = BWD ? (a.bw.partial != nullptr) : (a.stat.partial != nullptr);
     const int quarter = warp & 3, grp = warp >> 2;
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
@@ -306,6 +370,7 @@ __global__ void __launch_bounds__(256) conv3x3_tc_kernel(ConvTcArgs a) {
         const int src = s_rowsrc[K::HALO + t * 128 + m];
         const bool valid = src >= 0;
         float v[16];
+        float yv[BWD ? 16 : 1];
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * K::N + c0), v);
         if (valid) {
             const size_t obase = (size_t)src * K::N + c0;
@@ -316,18 +381,41 @@ __global__ void __launch_bounds__(256) conv3x3_tc_kernel(ConvTcArgs a) {
                     v[k4 * 4] += x4.x; v[k4 * 4 + 1] += x4.y; v[k4 * 4 + 2] += x4.z; v[k4 * 4 + 3] += x4.w;
                 }
             }
+            if (BWD && a.bw.y != nullptr) {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 y4 = ldg4(a.bw.y + obase + k4 * 4);
+                    yv[k4 * 4] = y4.x; yv[k4 * 4 + 1] = y4.y; yv[k4 * 4 + 2] = y4.z; yv[k4 * 4 + 3] = y4.w;
+                }
+                if (a.bw.mask_out != nullptr) {
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 o4 = ldg4(a.bw.mask_out + obase + k4 * 4);
+                        v[k4 * 4] = o4.x > 0.f ? v[k4 * 4] : 0.f; v[k4 * 4 + 1] = o4.y > 0.f ? v[k4 * 4 + 1] : 0.f;
+                        v[k4 * 4 + 2] = o4.z > 0.f ? v[k4 * 4 + 2] : 0.f; v[k4 * 4 + 3] = o4.w > 0.f ? v[k4 * 4 + 3] : 0.f;
+                    }
+                } else if (a.bw.scale != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaf(yv[i], s_aff[c0 + i], s_aff[K::N + c0 + i]) > 0.f ? v[i] : 0.f;
+                }
+            }
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)
                 *reinterpret_cast<float4*>(a.out + obase + k4 * 4) = make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
         }
         if (stats) {
-            // per-warp column sums over its 32 rows (butterfly: fixed order), lane 0 publishes
+            // per-warp column sums over its 32 rows: halving butterfly (16 shuffles per statistic), lanes 2k / 2k+1 publish column k's two sums
+            // in place (v is stored already): v <- x, x2 <- x * x (forward: sum, sum of squares) or x * xhat (BWD: sum g, sum g * xhat)
+            float x2[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const float x = valid ? v[i] : 0.f;
-                const float sm = warp_sum(x), sq = warp_sum(x * x);
-                if (lane == 0) { s_part[((warp * 2 + it) * 16 + i) * 2] = sm; s_part[((warp * 2 + it) * 16 + i) * 2 + 1] = sq; }
+                float m2 = x;
+                if (BWD) m2 = valid ? (yv[i] - s_aff[2 * K::N + c0 + i]) * s_aff[3 * K::N + c0 + i] : 0.f;
+                v[i] = x; x2[i] = x * m2;
             }
+            const float r1 = warp_colsum16(v), r2 = warp_colsum16(x2);
+            s_part[((warp * 2 + it) * 16 + (lane >> 1)) * 2 + (lane & 1)] = (lane & 1) ? r2 : r1;
         }
     }
     fence_before_sync();
@@ -346,20 +434,23 @@ __global__ void __launch_bounds__(256) conv3x3_tc_kernel(ConvTcArgs a) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) tsum += s_part[(((g * 4 + q) * 2 + it) * 16 + (c & 15)) * 2 + stat];
             }
-            a.stat.partial[((size_t)blockIdx.x * 2 + stat) * K::N + c] = tsum;
+            (BWD ? a.bw.partial : a.stat.partial)[((size_t)blockIdx.x * 2 + stat) * K::N + c] = tsum;
         }
-        if (last_block_done(a.stat.counter, gridDim.x)) {
-            bn_finalize_last_block<K::N, K::NT>(a.stat, (int)gridDim.x, (double)a.B * W * W, s_red);
+        if (BWD ? a.bw.defer : a.stat.defer) return;       // consumers reduce the partial rows themselves (BnLazy)
+        if (last_block_done(BWD ? a.bw.counter : a.stat.counter, gridDim.x)) {
+            if (BWD) bn_bwd_finalize_last_block<K::N>(a.bw.partial, (int)gridDim.x, (double)a.B * W * W, a.bw.scale, a.bw.mean, a.bw.invstd, a.bw.coef,
+                                                      a.bw.dgamma, a.bw.dbeta, s_red);
+            else bn_finalize_last_block<K::N, K::NT>(a.stat, (int)gridDim.x, (double)a.B * W * W, s_red);
         }
     }
 }
 
-template <int C, int W>
+template <int C, int W, int BWD = 0>
 static inline int conv_tc_launch(const ConvTcArgs& a, cudaStream_t st) {
     using K = ConvTcCfg<C, W>;
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(conv3x3_tc_kernel<C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES) != cudaSuccess) return LC_ERR_CUDA;
+        if (cudaFuncSetAttribute(conv3x3_tc_kernel<C, W, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES) != cudaSuccess) return LC_ERR_CUDA;
         attr_done = true;
     }
     const long long total = (long long)a.B * K::PP;
@@ -370,7 +461,7 @@ static inline int conv_tc_launch(const ConvTcArgs& a, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<C, W>, a) != cudaSuccess) return LC_ERR_CUDA;
+    if (cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<C, W, BWD>, a) != cudaSuccess) return LC_ERR_CUDA;
     return lc_launch_status();
 }
 

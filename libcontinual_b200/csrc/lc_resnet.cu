@@ -80,6 +80,13 @@ int launch_conv3x3_tc(int c, int wo, const tc::ConvTcArgs& a, cudaStream_t st) {
     if (c == 64 && wo == 8) return tc::conv_tc_launch<64, 8>(a, st);
     return LC_ERR_INVALID;
 }
+// data-gradient variant with the fused BatchNorm backward (apply in the prologue, mask + reduction in the epilogue)
+int launch_conv3x3_tc_bwd(int c, int wo, const tc::ConvTcArgs& a, cudaStream_t st) {
+    if (c == 16 && wo == 32) return tc::conv_tc_launch<16, 32, 1>(a, st);
+    if (c == 32 && wo == 16) return tc::conv_tc_launch<32, 16, 1>(a, st);
+    if (c == 64 && wo == 8) return tc::conv_tc_launch<64, 8, 1>(a, st);
+    return LC_ERR_INVALID;
+}
 
 int wgrad_nsplit(int cin, int cout) {
     if (cout == 16) return 256;
@@ -118,21 +125,30 @@ int launch_conv1x1_wgrad(int cin, int cout, int wo, const float* in, const float
     return lc_launch_status();
 }
 
-int launch_bn_bwd(const BnBwdArgs& a0, cudaStream_t st) {
-    BnBwdArgs a = a0;
+int launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t st) {
     long long blocks = (a.npix + 127) / 128;
     const int grid = (int)(blocks < kBnBwdBlocks ? blocks : kBnBwdBlocks);
     if (a.C == 16) bn_bwd_reduce_kernel<16><<<grid, 256, 0, st>>>(a);
     else if (a.C == 32) bn_bwd_reduce_kernel<32><<<grid, 256, 0, st>>>(a);
     else if (a.C == 64) bn_bwd_reduce_kernel<64><<<grid, 256, 0, st>>>(a);
     else return LC_ERR_INVALID;
-    if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
-    bn_bwd_apply_kernel<<<elem_grid(a.npix * (a.C / 4)), 256, 0, st>>>(a);
     return lc_launch_status();
+}
+int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st) {
+    int grid = elem_grid(a.npix * (a.C / 4));
+    if (a.blazy.partial != nullptr && grid > 2 * kNumSMs) grid = 2 * kNumSMs;
+    bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(a);
+    return lc_launch_status();
+}
+int launch_bn_bwd(const BnBwdArgs& a, cudaStream_t st) {
+    if (launch_bn_bwd_reduce(a, st) != LC_OK) return LC_ERR_CUDA;
+    return launch_bn_bwd_apply(a, st);
 }
 
 int launch_bn_act(const BnActArgs& a, cudaStream_t st) {
-    bn_act_fwd_kernel<<<elem_grid(a.n4), 256, 0, st>>>(a);
+    int grid = elem_grid(a.n4);
+    if (a.lazy.partial != nullptr && grid > 2 * kNumSMs) grid = 2 * kNumSMs;     // every CTA re-reduces the partial rows: fewer, longer CTAs
+    bn_act_fwd_kernel<<<grid, 256, 0, st>>>(a);
     return lc_launch_status();
 }
 
@@ -145,6 +161,8 @@ struct ConvL {
     long long y_off;                      // workspace: raw conv output
     long long wf_off, wd_off, part_off;   // workspace-relative (packed weights / partials)
     long long wtf_off, wtd_off;           // tensor-core packings (-1 when the layer stays on the CUDA-core path)
+    long long fpartL_off;                 // workspace: this layer's own forward-statistics partial rows (deferred finalisation), -1 if not tensor-core
+    long long bpartL_off;                 // workspace: this layer's BatchNorm-backward partial rows (written by a fused data-gradient epilogue)
     int nsplit;
 };
 struct BlockL {
@@ -165,6 +183,8 @@ struct lc_resnet {
     long long packed_floats = 0, wpart_floats = 0;
     ConvTabEntry* d_tab = nullptr;
     BnEvalEntry* d_bntab = nullptr;
+    BnFinEntry* d_fintab = nullptr;
+    int n_deferred = 0, lazy_stats = 1;
     int tab_blocks = 0;
     int launches_fwd = 0, launches_bwd = 0;
     int mode = 0;     // 0: exact fp32 CUDA-core convs; 1: TF32 tcgen05 convs (fwd + dgrad of the stride-1 3x3 layers)
@@ -172,10 +192,223 @@ struct lc_resnet {
     // backward runs two chains: the data-gradient chain (BN backward -> dgrad -> ...) on the caller's stream and the weight-gradient kernels, which
     // are leaves of the dependency graph, on `side` — forked / joined with events so that the pair is capturable into one CUDA graph
     long long off_T1b = 0;
+    // fused-backward flow (mode 1): per-layer BatchNorm-backward coefficients, a second gradient buffer per stage and a second conv_b data-gradient
+    // buffer, so that a weight-gradient kernel on the side chain can still read version k while the main chain already writes version k^1
+    // The weight-gradient kernels are leaves, independent of each other: they are dealt round-robin to `nside` side streams so that several run beside
+    // the main chain at once, and G / the conv_b data gradient live in rings of kRing versions so that the main chain can run ahead of its readers.
+    static constexpr int kRing = 4, kMaxSide = 3;
+    long long off_coefL = 0, off_Gr[3][kRing] = {}, off_T2r[kRing] = {};
+    cudaEvent_t ev_pub[2 * kRing] = {}, ev_rd[2 * kRing] = {}, ev_joinS[kMaxSide] = {};
+    cudaStream_t sides[kMaxSide] = {};
+    int nside = 2;
+    int debug_skip = 0;
+    int fused = 1;
     cudaStream_t side = nullptr;
     cudaEvent_t ev_dy[2] = {nullptr, nullptr}, ev_w[2] = {nullptr, nullptr}, ev_dy3 = nullptr, ev_w3 = nullptr, ev_join = nullptr;
     int overlap = 1;
 };
+
+
+#define LC_TRY(expr)                  \
+    do {                              \
+        int _e = (expr);              \
+        if (_e != LC_OK) return _e;   \
+        ++launches;                   \
+    } while (0)
+#define LC_CALL(expr)                 \
+    do {                              \
+        int _e = (expr);              \
+        if (_e != LC_OK) return _e;   \
+    } while (0)
+
+// Backward of the tensor-core mode with the BatchNorm backward folded into the convolutions (resnet.py:306-316,382 + autograd): per residual block the
+// main chain is TWO launches — the data-gradient conv of conv_b and of conv_a — instead of six.  Each conv's epilogue masks its result with the ReLU
+// that precedes it in the forward pass, stores the masked gradient and reduces (sum g, sum g*xhat) for the BatchNorm below; the last CTA leaves the
+// coefficients of dy = c0*g + c1*y + c2, which the next data-gradient conv and the weight-gradient kernel evaluate while staging their operands.
+// Stage transitions (stride-2 conv_a, 1x1 shortcut) and the stem stay on the CUDA-core kernels and use the stand-alone reduce / apply launches.
+static int resnet_backward_fused(lc_resnet* n, const float* x, int batch, const float* params, float* ws, float* grads, cudaStream_t st) {
+    constexpr int R = lc_resnet::kRing;
+    cudaStream_t sw = n->overlap ? n->side : st;        // CUDA-core weight-gradient kernels (stage transitions, stem)
+    int wsel = 0;                                       // round-robin over the side streams for the tensor-core weight gradients
+    bool side_used[lc_resnet::kMaxSide] = {false, false, false};
+    int launches = 0;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws + n->off_counters);
+    int* err_flag = reinterpret_cast<int*>(counters) + 8;
+    float* packed = ws + n->off_packed;
+    float* wpart = ws + n->off_wpart;
+    float* Gv[3][R];
+    float* T2v[R];
+    for (int r = 0; r < R; ++r) { for (int q = 0; q < 3; ++q) Gv[q][r] = ws + n->off_Gr[q][r]; T2v[r] = ws + n->off_T2r[r]; }
+    float* Tdy[2] = {ws + n->off_T1, ws + n->off_T1b};
+    float* T3 = ws + n->off_T3;
+    int gk = 0, tk = 0, dk = 0;
+    bool rd_rec[2 * R] = {}, wrec[2] = {false, false}, w3rec = false;
+    bool g_fused = false;                       // the current G is already masked and the coefficients of its BatchNorm are ready
+
+    auto coef_of = [&](int conv) { return ws + n->off_coefL + (long long)conv * 3 * 64; };
+    // coef_lazy[i]: the BatchNorm-backward sums of layer i exist only as the partial rows of a fused epilogue; its consumers reduce them (BnBwdLazy)
+    const bool lazyb = n->lazy_stats != 0;
+    std::vector<char> coef_lazy(n->convs.size(), 0);
+    auto blazy_of = [&](int conv_idx, int write_grads) {
+        BnBwdLazy z{};
+        if (!coef_lazy[conv_idx]) return z;
+        const ConvL& c = n->convs[conv_idx];
+        const float* aff = ws + c.aff_off;
+        const int mrows = 128 * (c.cout == 16 ? 4 : (c.cout == 32 ? 2 : 1));
+        z.partial = ws + c.bpartL_off; z.scale = aff; z.mean = aff + 2 * c.cout; z.invstd = aff + 3 * c.cout;
+        z.dgamma = grads + c.gamma_off; z.dbeta = grads + c.beta_off;
+        z.nparts = (int)(((long long)batch * (c.wo + 2) * (c.wo + 2) + mrows - 1) / mrows);
+        z.count = (float)((long long)batch * c.wo * c.wo); z.write_grads = write_grads;
+        return z;
+    };
+    auto bn_args = [&](const ConvL& c, int conv_idx, const float* g, const float* mask_src, int mask_mode) {
+        BnBwdArgs a{};
+        const float* aff = ws + c.aff_off;
+        a.g = g; a.mask_src = mask_src; a.mask_mode = mask_mode; a.y = ws + c.y_off;
+        a.scale = aff; a.shift = aff + c.cout; a.mean = aff + 2 * c.cout; a.invstd = aff + 3 * c.cout;
+        a.partial = ws + n->off_bpart; a.counter = counters + 1; a.coef = coef_of(conv_idx);
+        a.dgamma = grads + c.gamma_off; a.dbeta = grads + c.beta_off;
+        a.npix = (long long)batch * c.wo * c.wo; a.C = c.cout;
+        return a;
+    };
+    // slot s: [0, R) = the G ring, [R, 2R) = the ring of conv_b data-gradient buffers
+    cudaStream_t swt = st;                      // side stream of the tensor-core weight gradient being issued
+    auto acquire = [&](int slot) -> int {       // main chain is about to overwrite the buffer: its last side-chain reader must be done
+        if (n->overlap && rd_rec[slot] && cudaStreamWaitEvent(st, n->ev_rd[slot], 0) != cudaSuccess) return LC_ERR_CUDA;
+        return LC_OK;
+    };
+    auto publish = [&](int slot) -> int {       // buffer (and the coefficients that go with it) complete on the main chain: pick the reader's stream
+        if (!n->overlap) { swt = st; return LC_OK; }
+        swt = n->sides[wsel]; side_used[wsel] = true; wsel = (wsel + 1) % n->nside;
+        if (cudaEventRecord(n->ev_pub[slot], st) != cudaSuccess || cudaStreamWaitEvent(swt, n->ev_pub[slot], 0) != cudaSuccess) return LC_ERR_CUDA;
+        return LC_OK;
+    };
+    auto read_done = [&](int slot) -> int {
+        if (n->overlap) { if (cudaEventRecord(n->ev_rd[slot], swt) != cudaSuccess) return LC_ERR_CUDA; rd_rec[slot] = true; }
+        return LC_OK;
+    };
+    auto wgrad_tc = [&](const ConvL& c, int conv_idx, const float* in, const float* pro_scale, const float* pro_shift, const float* g) {
+        tc::WgradTcArgs w{};
+        w.in = in; w.dy = g; w.dy_y = ws + c.y_off; w.dy_coef = coef_of(conv_idx); w.dy_blazy = blazy_of(conv_idx, 1);
+        w.partial = wpart + c.part_off; w.B = batch; w.error_flag = err_flag;
+        w.pro_scale = pro_scale; w.pro_shift = pro_shift;
+        if (n->debug_skip == 1) return LC_OK;            // timing experiments only (LC_RESNET_DEBUG_SKIP=1): main chain without the weight gradients
+        return launch_wgrad3x3_tc(c.cin, c.wo, w, wgrad_nsplit_tc(c.cin), swt);
+    };
+    // fused data-gradient conv: in = c0*g + c1*y + c2 of layer c; the result is the gradient w.r.t. the ReLU output of BatchNorm `below`
+    auto dgrad_tc = [&](const ConvL& c, int conv_idx, const float* g, float* out, const float* addend, const ConvL& below, int below_idx,
+                        const float* mask_out) {
+        tc::ConvTcArgs t{};
+        t.in = g; t.pro_y = ws + c.y_off; t.pro_coef = coef_of(conv_idx); t.pro_blazy = blazy_of(conv_idx, 0);
+        t.wtc = packed + c.wtd_off; t.out = out; t.addend = addend; t.B = batch;
+        t.error_flag = err_flag;
+        const float* aff = ws + below.aff_off;
+        t.bw.y = ws + below.y_off; t.bw.mask_out = mask_out;
+        t.bw.scale = aff; t.bw.shift = aff + below.cout; t.bw.mean = aff + 2 * below.cout; t.bw.invstd = aff + 3 * below.cout;
+        t.bw.partial = lazyb ? ws + below.bpartL_off : ws + n->off_fpart; t.bw.defer = lazyb ? 1 : 0;
+        t.bw.counter = counters + 0; t.bw.coef = coef_of(below_idx);
+        t.bw.dgamma = grads + below.gamma_off; t.bw.dbeta = grads + below.beta_off;
+        coef_lazy[below_idx] = lazyb ? 1 : 0;
+        if (n->debug_skip == 2) return LC_OK;            // LC_RESNET_DEBUG_SKIP=2: weight-gradient kernels without the data-gradient chain
+        return launch_conv3x3_tc_bwd(c.cin, c.wo, t, st);
+    };
+    // materialised dy for a CUDA-core consumer (stride-2 conv_a, stem): Tdy[dk] <- c0*g + c1*y + c2
+    auto apply_to_tdy = [&](const ConvL& c, int conv_idx, const float* g) -> int {
+        if (n->overlap && wrec[dk] && cudaStreamWaitEvent(st, n->ev_w[dk], 0) != cudaSuccess) return LC_ERR_CUDA;
+        BnBwdArgs a = bn_args(c, conv_idx, g, nullptr, LC_MASK_NONE);
+        a.dy = Tdy[dk]; a.blazy = blazy_of(conv_idx, 1);
+        if (launch_bn_bwd_apply(a, st) != LC_OK) return LC_ERR_CUDA;
+        if (n->overlap && (cudaEventRecord(n->ev_dy[dk], st) != cudaSuccess || cudaStreamWaitEvent(sw, n->ev_dy[dk], 0) != cudaSuccess)) return LC_ERR_CUDA;
+        return LC_OK;
+    };
+    auto tdy_read_done = [&]() -> int {
+        if (n->overlap) { if (cudaEventRecord(n->ev_w[dk], sw) != cudaSuccess) return LC_ERR_CUDA; wrec[dk] = true; }
+        dk ^= 1;
+        return LC_OK;
+    };
+
+    for (int bi = (int)n->blocks.size() - 1; bi >= 0; --bi) {
+        const BlockL& bl = n->blocks[bi];
+        const ConvL& ca = n->convs[bl.conv_a];
+        const ConvL& cb = n->convs[bl.conv_b];
+        const int s = bl.stage;
+        const float* blk_in = bi == 0 ? ws + n->off_a0 : ws + n->blocks[bi - 1].out_off;
+        float* G = Gv[s][gk];
+        if (!g_fused) {
+            // G arrives unmasked (head backward, or the CUDA-core data gradient of a stage transition): stand-alone reduction, which also masks G in place
+            const bool no_relu = !n->last_relu && bi == (int)n->blocks.size() - 1;
+            BnBwdArgs a = bn_args(cb, bl.conv_b, G, ws + bl.out_off, no_relu ? LC_MASK_NONE : LC_MASK_FROM_OUT);
+            a.g_out = G; a.reduce_writes_g = no_relu ? 0 : 1;
+            LC_TRY(launch_bn_bwd_reduce(a, st));
+        }
+        LC_CALL(publish(gk));
+        if (bl.conv_d >= 0) {
+            const ConvL& cd = n->convs[bl.conv_d];
+            if (n->overlap && w3rec && cudaStreamWaitEvent(st, n->ev_w3, 0) != cudaSuccess) return LC_ERR_CUDA;
+            BnBwdArgs a = bn_args(cd, bl.conv_d, G, nullptr, LC_MASK_NONE);
+            a.dy = T3;
+            LC_TRY(launch_bn_bwd_reduce(a, st));
+            LC_TRY(launch_bn_bwd_apply(a, st));
+            if (n->overlap && (cudaEventRecord(n->ev_dy3, st) != cudaSuccess || cudaStreamWaitEvent(sw, n->ev_dy3, 0) != cudaSuccess)) return LC_ERR_CUDA;
+            LC_TRY(launch_conv1x1_wgrad(cd.cin, cd.cout, cd.wo, blk_in, T3, wpart + cd.part_off, batch, sw));
+            if (n->overlap) { if (cudaEventRecord(n->ev_w3, sw) != cudaSuccess) return LC_ERR_CUDA; w3rec = true; }
+        }
+        // conv_b: weight gradient on the side chain (input = relu(bn_a(y_a)) and dy = bn_b backward of G, both evaluated while staging)
+        LC_TRY(wgrad_tc(cb, bl.conv_b, ws + ca.y_off, ws + ca.aff_off, ws + ca.aff_off + ca.cout, G));
+        LC_CALL(read_done(gk));
+        // conv_b data gradient -> T2 = masked d(relu(bn_a)) + the bn_a reduction
+        float* T2 = T2v[tk];
+        LC_CALL(acquire(R + tk));
+        LC_TRY(dgrad_tc(cb, bl.conv_b, G, T2, nullptr, ca, bl.conv_a, nullptr));
+        if (ca.stride == 1) {
+            LC_CALL(publish(R + tk));
+            LC_TRY(wgrad_tc(ca, bl.conv_a, blk_in, nullptr, nullptr, T2));
+            LC_CALL(read_done(R + tk));
+            // conv_a data gradient + the residual-branch gradient -> next G (masked with the ReLU that produced blk_in) + the reduction of its BatchNorm
+            const int below_idx = bi == 0 ? 0 : n->blocks[bi - 1].conv_b;
+            const int gn = (gk + 1) % R;
+            LC_CALL(acquire(gn));
+            LC_TRY(dgrad_tc(ca, bl.conv_a, T2, Gv[s][gn], G, n->convs[below_idx], below_idx, blk_in));
+            gk = gn;
+            g_fused = true;
+        } else {
+            const ConvL& cd = n->convs[bl.conv_d];
+            LC_CALL(apply_to_tdy(ca, bl.conv_a, T2)); ++launches;
+            WgradArgs w{};
+            w.in = blk_in; w.dy = Tdy[dk]; w.partial = wpart + ca.part_off; w.B = batch; w.nsplit = ca.nsplit;
+            LC_TRY(launch_wgrad3x3(ca.cin, ca.cout, ca.wo, ca.stride, false, w, sw));
+            const int gn = (gk + 1) % R;
+            float* Gprev = Gv[s - 1][gn];
+            LC_CALL(acquire(gn));
+            Conv3x3Args a{};
+            a.in = Tdy[dk]; a.wpack = packed + ca.wd_off; a.B = batch; a.out = Gprev;
+            LC_TRY(launch_conv3x3(ca.cout, ca.cin, ca.wo * 2, 1, true, false, a, st));
+            LC_TRY(launch_conv1x1_dgrad(cd.cin, cd.cout, cd.wo, T3, params + cd.w_off, Gprev, batch, st));
+            LC_CALL(tdy_read_done());
+            gk = gn;
+            g_fused = false;
+        }
+        tk = (tk + 1) % R;
+    }
+    {   // stem: G is masked with the stem ReLU and its coefficients are ready (block 0's conv_a epilogue)
+        const ConvL& c = n->convs[0];
+        if (!g_fused) return LC_ERR_INVALID;
+        LC_CALL(apply_to_tdy(c, 0, Gv[0][gk])); ++launches;
+        WgradArgs w{};
+        w.in = x; w.dy = Tdy[dk]; w.partial = wpart + c.part_off; w.B = batch; w.nsplit = c.nsplit;
+        LC_TRY(launch_wgrad3x3(c.cin, c.cout, c.wo, 1, true, w, sw));
+    }
+    if (n->overlap) {
+        side_used[0] = true;        // sw
+        for (int i = 0; i < lc_resnet::kMaxSide; ++i)
+            if (side_used[i] && (cudaEventRecord(n->ev_joinS[i], n->sides[i]) != cudaSuccess || cudaStreamWaitEvent(st, n->ev_joinS[i], 0) != cudaSuccess))
+                return LC_ERR_CUDA;
+    }
+    wgrad_reduce_all_kernel<<<n->tab_blocks, 256, 0, st>>>(n->d_tab, (int)n->convs.size(), wpart, grads, n->mode);
+    LC_TRY(lc_launch_status());
+    n->launches_bwd = launches;
+    return LC_OK;
+}
 
 extern "C" {
 
@@ -272,13 +505,39 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
     n->off_T2 = take(B * 32 * 32 * 16);
     n->off_T3 = take(B * 16 * 16 * 32);
     n->off_T1b = take(B * 32 * 32 * 16);
+    n->off_coefL = take((long long)n->convs.size() * 3 * 64);
+    for (int r = 0; r < lc_resnet::kRing; ++r) {
+        n->off_Gr[0][r] = r == 0 ? n->off_G[0] : take(B * 32 * 32 * 16);
+        n->off_Gr[1][r] = r == 0 ? n->off_G[1] : take(B * 16 * 16 * 32);
+        n->off_Gr[2][r] = r == 0 ? n->off_G[2] : take(B * 8 * 8 * 64);
+        n->off_T2r[r] = r == 0 ? n->off_T2 : take(B * 32 * 32 * 16);
+    }
+    for (auto& c : n->convs)
+        c.fpartL_off = c.wtf_off >= 0 ? take(tc::conv_tc_tiles((int)B, c.wo) * 2 * c.cout) : -1;
+    for (auto& c : n->convs) c.bpartL_off = c.ksize == 3 ? take(tc::conv_tc_tiles((int)B, c.wo) * 2 * c.cout) : -1;
     n->ws_floats = o;
     {
         const char* env = getenv("LC_RESNET_SERIAL");
         n->overlap = (env != nullptr && env[0] == '1') ? 0 : 1;
+        const char* envf = getenv("LC_RESNET_UNFUSED");
+        n->fused = (envf != nullptr && envf[0] == '1') ? 0 : 1;
+        const char* envl = getenv("LC_RESNET_EAGER_STATS");
+        n->lazy_stats = (envl != nullptr && envl[0] == '1') ? 0 : 1;
         bool okev = cudaStreamCreateWithFlags(&n->side, cudaStreamNonBlocking) == cudaSuccess;
         cudaEvent_t* evs[7] = {&n->ev_dy[0], &n->ev_dy[1], &n->ev_w[0], &n->ev_w[1], &n->ev_dy3, &n->ev_w3, &n->ev_join};
         for (auto e : evs) okev = okev && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < 2 * lc_resnet::kRing; ++i)
+            okev = okev && cudaEventCreateWithFlags(&n->ev_pub[i], cudaEventDisableTiming) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&n->ev_rd[i], cudaEventDisableTiming) == cudaSuccess;
+        n->sides[0] = n->side;
+        for (int i = 0; i < lc_resnet::kMaxSide; ++i) {
+            if (i > 0) okev = okev && cudaStreamCreateWithFlags(&n->sides[i], cudaStreamNonBlocking) == cudaSuccess;
+            okev = okev && cudaEventCreateWithFlags(&n->ev_joinS[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        const char* envd = getenv("LC_RESNET_DEBUG_SKIP");
+        if (envd != nullptr && (envd[0] == '1' || envd[0] == '2')) n->debug_skip = envd[0] - '0';
+        const char* envs = getenv("LC_RESNET_SIDE");
+        if (envs != nullptr && envs[0] >= '1' && envs[0] <= '3') n->nside = envs[0] - '0';
         if (!okev) { lc_resnet_destroy(n); return LC_ERR_CUDA; }
     }
 
@@ -300,6 +559,20 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
         e.gamma_off = c.gamma_off; e.beta_off = c.beta_off; e.rstat_off = c.rstat_off; e.aff_off = c.aff_off; e.C = c.cout;
         bt.push_back(e);
     }
+    std::vector<BnFinEntry> ft;
+    for (auto& c : n->convs) {
+        if (c.fpartL_off < 0) continue;
+        BnFinEntry e{};
+        e.part_off = c.fpartL_off; e.gamma_off = c.gamma_off; e.beta_off = c.beta_off; e.rstat_off = c.rstat_off; e.aff_off = c.aff_off; e.C = c.cout;
+        e.pp = (c.wo + 2) * (c.wo + 2); e.mrows = 128 * (c.cout == 16 ? 4 : (c.cout == 32 ? 2 : 1)); e.hw = c.wo * c.wo;
+        ft.push_back(e);
+    }
+    n->n_deferred = (int)ft.size();
+    if (cudaMalloc(&n->d_fintab, (ft.size() + 1) * sizeof(BnFinEntry)) != cudaSuccess ||
+        cudaMemcpy(n->d_fintab, ft.data(), ft.size() * sizeof(BnFinEntry), cudaMemcpyHostToDevice) != cudaSuccess) {
+        lc_resnet_destroy(n);
+        return LC_ERR_CUDA;
+    }
     if (cudaMalloc(&n->d_tab, tab.size() * sizeof(ConvTabEntry)) != cudaSuccess || cudaMalloc(&n->d_bntab, bt.size() * sizeof(BnEvalEntry)) != cudaSuccess ||
         cudaMemcpy(n->d_tab, tab.data(), tab.size() * sizeof(ConvTabEntry), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(n->d_bntab, bt.data(), bt.size() * sizeof(BnEvalEntry), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -314,8 +587,14 @@ void lc_resnet_destroy(lc_resnet* n) {
     if (!n) return;
     if (n->d_tab) cudaFree(n->d_tab);
     if (n->d_bntab) cudaFree(n->d_bntab);
+    if (n->d_fintab) cudaFree(n->d_fintab);
     if (n->side) cudaStreamDestroy(n->side);
     for (cudaEvent_t e : {n->ev_dy[0], n->ev_dy[1], n->ev_w[0], n->ev_w[1], n->ev_dy3, n->ev_w3, n->ev_join}) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2 * lc_resnet::kRing; ++i) { if (n->ev_pub[i]) cudaEventDestroy(n->ev_pub[i]); if (n->ev_rd[i]) cudaEventDestroy(n->ev_rd[i]); }
+    for (int i = 0; i < lc_resnet::kMaxSide; ++i) {
+        if (i > 0 && n->sides[i]) cudaStreamDestroy(n->sides[i]);
+        if (n->ev_joinS[i]) cudaEventDestroy(n->ev_joinS[i]);
+    }
     delete n;
 }
 
@@ -365,13 +644,6 @@ long long lc_resnet_ws_offset(const lc_resnet* n, int what) {
     }
 }
 
-#define LC_TRY(expr)                  \
-    do {                              \
-        int _e = (expr);              \
-        if (_e != LC_OK) return _e;   \
-        ++launches;                   \
-    } while (0)
-
 int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* params, float* rstat, float* ws, int train, int update_running,
                       lc_stream_t stream) {
     LC_CHECK_ARG(n && x && params && ws && batch >= 1 && batch <= n->max_batch && (rstat || (train && !update_running)));
@@ -386,6 +658,8 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
         bn_eval_affine_kernel<<<(int)n->convs.size(), 64, 0, st>>>(n->d_bntab, (int)n->convs.size(), params, rstat, ws, kBnEps);
         LC_TRY(lc_launch_status());
     }
+    const bool lazy = train && n->mode == 1 && n->lazy_stats;
+    auto mrows_of = [](int cout) { return 128 * (cout == 16 ? 4 : (cout == 32 ? 2 : 1)); };
     auto stat_for = [&](const ConvL& c) {
         BnStatArgs s{};
         if (!train) return s;
@@ -395,7 +669,17 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
         float* aff = ws + c.aff_off;
         s.scale = aff; s.shift = aff + c.cout; s.mean = aff + 2 * c.cout; s.invstd = aff + 3 * c.cout;
         s.momentum = kBnMomentum; s.eps = kBnEps; s.update_running = (update_running && rstat) ? 1 : 0;
+        if (lazy && c.fpartL_off >= 0) { s.partial = ws + c.fpartL_off; s.defer = 1; }
         return s;
+    };
+    // consumer-side view of a deferred layer's statistics (conv_simt.cuh: BnLazy); .partial == null -> the layer was finalised by its producer
+    auto lazy_of = [&](const ConvL& c) {
+        BnLazy z{};
+        if (!(lazy && c.fpartL_off >= 0)) return z;
+        z.partial = ws + c.fpartL_off; z.gamma = params + c.gamma_off; z.beta = params + c.beta_off;
+        z.nparts = (int)(((long long)batch * (c.wo + 2) * (c.wo + 2) + mrows_of(c.cout) - 1) / mrows_of(c.cout));
+        z.count = (float)((long long)batch * c.wo * c.wo); z.eps = kBnEps;
+        return z;
     };
     // stem
     {
@@ -424,7 +708,7 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
         if (n->mode == 1 && cb.wtf_off >= 0) {
             tc::ConvTcArgs a{};
             a.in = ws + ca.y_off; a.wtc = packed + cb.wtf_off; a.out = ws + cb.y_off; a.stat = stat_for(cb); a.B = batch; a.error_flag = err_flag;
-            a.pro_scale = ws + ca.aff_off; a.pro_shift = ws + ca.aff_off + ca.cout;
+            a.pro_scale = ws + ca.aff_off; a.pro_shift = ws + ca.aff_off + ca.cout; a.pro_lazy = lazy_of(ca);
             LC_TRY(launch_conv3x3_tc(cb.cin, cb.wo, a, st));
         } else {
             Conv3x3Args a{};
@@ -434,7 +718,7 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
         }
         BnActArgs e{};
         e.y = ws + cb.y_off; e.scale = ws + cb.aff_off; e.shift = ws + cb.aff_off + cb.cout; e.out = ws + bl.out_off;
-        e.n4 = (long long)batch * cb.wo * cb.wo * cb.cout / 4; e.C = cb.cout;
+        e.n4 = (long long)batch * cb.wo * cb.wo * cb.cout / 4; e.C = cb.cout; e.lazy = lazy_of(cb);
         if (bl.conv_d >= 0) {
             const ConvL& cd = n->convs[bl.conv_d];
             Conv1x1Args a{};
@@ -448,6 +732,10 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
         LC_TRY(launch_bn_act(e, st));
         cur = ws + bl.out_off;
     }
+    if (lazy && n->n_deferred > 0) {      // scale / shift / mean / invstd of the deferred layers for the backward pass, and their running statistics
+        bn_finalize_layers_kernel<<<n->n_deferred, 256, 0, st>>>(n->d_fintab, params, rstat, ws, batch, kBnMomentum, kBnEps, (update_running && rstat) ? 1 : 0);
+        LC_TRY(lc_launch_status());
+    }
     n->launches_fwd = launches;
     return LC_OK;
 }
@@ -455,6 +743,7 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
 int lc_resnet_backward(lc_resnet* n, const float* x, int batch, const float* params, float* ws, float* grads, lc_stream_t stream) {
     LC_CHECK_ARG(n && x && params && ws && grads && batch >= 1 && batch <= n->max_batch);
     cudaStream_t st = (cudaStream_t)stream;
+    if (n->mode == 1 && n->fused) return resnet_backward_fused(n, x, batch, params, ws, grads, st);
     cudaStream_t sw = n->overlap ? n->side : st;           // weight-gradient chain
     int launches = 0;
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws + n->off_counters);

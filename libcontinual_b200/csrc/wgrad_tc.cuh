@@ -50,6 +50,9 @@ struct WgradTcArgs {
     float* partial;           // [gridDim.x][9][C][C]  (tap, ci, co)
     const float* pro_scale;   // nullable
     const float* pro_shift;
+    const float* dy_y;        // nullable: dY = coef0[c]*dy + coef1[c]*dy_y + coef2[c] evaluated while staging (fused BatchNorm backward apply,
+    const float* dy_coef;     //           see BnBwdFuse in conv_tc.cuh); dy_coef = [3][C]
+    BnBwdLazy dy_blazy;       // .partial != null: the coefficients are reduced here from the producing epilogue's partial rows (CTA 0 also writes dgamma / dbeta)
     int* error_flag;
     int B;
 };
@@ -73,7 +76,8 @@ struct WgradTcCfg {
     static constexpr int OFF_ROWTAB = OFF_Y + (Y_BYTES > PAD_BYTES ? Y_BYTES : PAD_BYTES);
     static constexpr int ROWTAB_BYTES = ((ROWS_X * 4 + 15) / 16) * 16;
     static constexpr int OFF_BAR = OFF_ROWTAB + ROWTAB_BYTES;
-    static constexpr size_t SMEM_BYTES = OFF_BAR + 64;
+    static constexpr int OFF_RED = OFF_BAR + 64;                 // 1024 doubles (bn_partial_sums) + c0, c1, c2
+    static constexpr size_t SMEM_BYTES = OFF_RED + 8192 + 3 * C * 4;
     static constexpr int NACC = C == 64 ? 6 : 3;
     static constexpr uint32_t TMEM_COLS = C == 16 ? 64 : (C == 32 ? 128 : 512);
     static constexpr int RSTEP = NT / CH8;
@@ -96,6 +100,10 @@ __global__ void __launch_bounds__(256) wgrad3x3_tc_kernel(WgradTcArgs a) {
     const int total = a.B * K::PP;
     const int ntiles = (total + 127) / 128;
 
+    // lazy BatchNorm-backward coefficients, phase 1 (independent loads first; combined below)
+    const bool dyaff = a.dy_y != nullptr;
+    const bool dylazy = dyaff && a.dy_blazy.partial != nullptr;
+    if (dylazy) bn_partial_sums_load(a.dy_blazy.partial, a.dy_blazy.nparts, C, reinterpret_cast<double*>(smem_raw + K::OFF_RED));
     if (tid == 32) mbar_init(bar, 1);
     if (warp == 0) tmem_alloc(tmem_slot, K::TMEM_COLS);
     fence_before_sync();
@@ -109,6 +117,18 @@ __global__ void __launch_bounds__(256) wgrad3x3_tc_kernel(WgradTcArgs a) {
     if (pro) {
         sc0 = ldg4(a.pro_scale + j * 8); sc1 = ldg4(a.pro_scale + j * 8 + 4);
         sh0 = ldg4(a.pro_shift + j * 8); sh1 = ldg4(a.pro_shift + j * 8 + 4);
+    }
+    float4 k0a = sc0, k0b = sc0, k1a = sh0, k1b = sh0, k2a = sh0, k2b = sh0;
+    if (dylazy) {
+        float* s_coef = reinterpret_cast<float*>(smem_raw + K::OFF_RED + 8192);
+        bn_bwd_lazy_coef_finish(a.dy_blazy, C, reinterpret_cast<double*>(smem_raw + K::OFF_RED), s_coef);
+        k0a = *reinterpret_cast<const float4*>(s_coef + j * 8); k0b = *reinterpret_cast<const float4*>(s_coef + j * 8 + 4);
+        k1a = *reinterpret_cast<const float4*>(s_coef + C + j * 8); k1b = *reinterpret_cast<const float4*>(s_coef + C + j * 8 + 4);
+        k2a = *reinterpret_cast<const float4*>(s_coef + 2 * C + j * 8); k2b = *reinterpret_cast<const float4*>(s_coef + 2 * C + j * 8 + 4);
+    } else if (dyaff) {
+        k0a = ldg4(a.dy_coef + j * 8); k0b = ldg4(a.dy_coef + j * 8 + 4);
+        k1a = ldg4(a.dy_coef + C + j * 8); k1b = ldg4(a.dy_coef + C + j * 8 + 4);
+        k2a = ldg4(a.dy_coef + 2 * C + j * 8); k2b = ldg4(a.dy_coef + 2 * C + j * 8 + 4);
     }
     const uint32_t sX_u = smem_u32(sX), sY_u = smem_u32(sY);
 
@@ -157,6 +177,14 @@ __global__ void __launch_bounds__(256) wgrad3x3_tc_kernel(WgradTcArgs a) {
                 if (src >= 0) {
                     const float* g = a.dy + (size_t)src * C + j * 8;
                     ya[i] = ldg4(g); yb[i] = ldg4(g + 4);
+                    if (dyaff) {
+                        const float* yy = a.dy_y + (size_t)src * C + j * 8;
+                        const float4 ua = ldg4(yy), ub = ldg4(yy + 4);
+                        ya[i].x = fmaf(k0a.x, ya[i].x, fmaf(k1a.x, ua.x, k2a.x)); ya[i].y = fmaf(k0a.y, ya[i].y, fmaf(k1a.y, ua.y, k2a.y));
+                        ya[i].z = fmaf(k0a.z, ya[i].z, fmaf(k1a.z, ua.z, k2a.z)); ya[i].w = fmaf(k0a.w, ya[i].w, fmaf(k1a.w, ua.w, k2a.w));
+                        yb[i].x = fmaf(k0b.x, yb[i].x, fmaf(k1b.x, ub.x, k2b.x)); yb[i].y = fmaf(k0b.y, yb[i].y, fmaf(k1b.y, ub.y, k2b.y));
+                        yb[i].z = fmaf(k0b.z, yb[i].z, fmaf(k1b.z, ub.z, k2b.z)); yb[i].w = fmaf(k0b.w, yb[i].w, fmaf(k1b.w, ub.w, k2b.w));
+                    }
                 }
             }
         }
