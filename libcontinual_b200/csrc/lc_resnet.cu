@@ -934,7 +934,12 @@ int lc_fisher_merge(float* f_new, const float* f_old, long long n, float num_sam
     return lc_launch_status();
 }
 int lc_sgd_momentum(float* p, const float* g, float* m, long long n, const float* hp, lc_stream_t stream) {
-    LC_CHECK_ARG(p && g && m && hp && n > 0 && ((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0));
+    LC_CHECK_ARG(p && g && m && hp && n > 0);
+    if (((uintptr_t)p % 16) || ((uintptr_t)g % 16) || ((uintptr_t)m % 16)) {
+        // a range that does not start on a 16-byte boundary (e.g. the bias slice of a 10-class task head inside a flat arena): scalar kernel
+        sgd_momentum_frozen_kernel<<<kFlatBlocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, n, hp, 0, 0);
+        return lc_launch_status();
+    }
     sgd_momentum_kernel<<<kFlatBlocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, n, hp);
     return lc_launch_status();
 }

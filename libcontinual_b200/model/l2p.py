@@ -14,6 +14,7 @@ them with one kernel; `torch.optim.Adam` on `get_parameters()` works as well.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -55,9 +56,15 @@ class ViTZoo(nn.Module):
         self.engine = ViTEngine(depth=depth, device=device)
         if state is None:
             if pretrained:
-                raise _lib.LcError(f"pretrained weights for {model_name} must be passed as state= (a VisionTransformer / timm state_dict): "
-                                   "this build has no network access and does not depend on timm")
-            state = self._random_state(depth)
+                # the reference asks timm to download `model_name` (vit.py:67); here the checkpoint must already be on disk
+                ckpt = os.environ.get("LC_B200_VIT_CHECKPOINT")
+                if not ckpt or not os.path.exists(ckpt):
+                    raise _lib.LcError(f"pretrained=True ({model_name}): point LC_B200_VIT_CHECKPOINT at a local VisionTransformer / timm state_dict "
+                                       "(torch.save file), or pass state=; this build has no network access and does not depend on timm")
+                state = torch.load(ckpt, map_location="cpu")
+                state = state.get("state_dict", state.get("model", state)) if isinstance(state, dict) else state
+            else:
+                state = self._random_state(depth)
         self.load_backbone_state(state)
         self.prompt = None
         self.prompt_flag = ""

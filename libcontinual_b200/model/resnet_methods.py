@@ -444,7 +444,7 @@ class _CosineHead(nn.Module):
         self.in_features, self.out_features = eng.feat_dim, n
         w, b = eng.fc_views(n)
         self.sigma = nn.Parameter(eng.params[eng.off_fc_b:eng.off_fc_b + 1])
-        if n_new == 0:
+        if n_old == 0:                     # task 0: a plain CosineLinear (one weight); later tasks: SplitCosineLinear (fc1 = old rows, fc2 = new rows)
             self.weight = nn.Parameter(w)
         else:
             self.fc1 = _CosineHead._Part(w[:n_old])

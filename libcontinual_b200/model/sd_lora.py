@@ -57,7 +57,10 @@ class SD_LoRA(nn.Module):
         self.init_mag = float(kwargs["init_mag"])
         self.rank_reduction, self.knowledge_dist = kwargs.get("rank_reduction", [False]), kwargs.get("knowledge_dist", [False])
         if self.rank_reduction[0] or self.knowledge_dist[0]:
-            raise NotImplementedError("rank_reduction / knowledge_dist (SD-LoRA-RR / -KD variants) are not on the CUDA path; the shipped recipes disable both")
+            # knowledge_dist: the one shipped recipe that enables it (zz_SD-LoRA/sd_lora-vit-imagenetr-b10-10-20.yaml:77, `[True, 9e-4]`) cannot run in
+            # the reference either: YAML reads `9e-4` as a string, so `alphas.residuals < self.knowledge_dist[1]` (sd_lora.py:186) raises TypeError at
+            # the first after_task with task_idx > 0 (and `alphas.solution[i]` at :191 indexes past the solution).  rank_reduction is disabled everywhere.
+            raise NotImplementedError("rank_reduction / knowledge_dist (SD-LoRA-RR / -KD variants) are not on the CUDA path; see INTEGRATION.md")
         self._known_classes = 0
         self.engine = eng = backbone.engine
         self.rank = r = int(getattr(backbone, "lora_rank", 10))

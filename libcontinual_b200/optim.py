@@ -167,7 +167,6 @@ class FlatSGD(torch.optim.Optimizer):
         mdl = self.model
         g = mdl.theta_grad if grads is None else grads
         st = torch.cuda.current_stream().cuda_stream
-        for lo, hi in mdl.active_ranges():
-            assert lo % 4 == 0
+        for lo, hi in mdl.active_ranges():          # a range may start off a 16-byte boundary (10-class head bias): lc_sgd_momentum falls back to its scalar kernel
             check(self.lib.lc_sgd_momentum(mdl.theta.data_ptr() + 4 * lo, g.data_ptr() + 4 * lo, self.buf.data_ptr() + 4 * lo, hi - lo, self.hp.data_ptr(), st),
                   "sgd_momentum")
