@@ -367,6 +367,28 @@ int lc_nn_wgrad_reduce(const float* partial, int nsplit, int Cout, int Cin, int 
 /* fp32 [rows][cols] -> BF16 [rows][ld] and / or its transpose [cols][ldT] (tails zero). */
 int lc_nn_cast_transpose(const float* src, long long rows, int cols, void* out_bf16, long long ld, void* outT_bf16, long long ldT, lc_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Input pipeline and evaluation meter on the device.  The uint8 dataset [N][H][W][3] is resident in HBM; one call per batch
+ * gathers `idx`, applies the reference's transform chain with PIL's / torchvision's own arithmetic and writes the fp32 NCHW batch.  The random draws
+ * come from the host (libcontinual_b200/data.py restates torchvision's get_params).
+ * lc_augment_cifar_u8 : RandomCrop(H, padding=pad) -> RandomHorizontalFlip -> ColorJitter(brightness) -> ToTensor -> Normalize (core/data/data.py:11-16);
+ *                       draw[b] = {dx, dy, flip, 0} with (dx, dy) the crop origin inside the zero-padded image, bright[b] the PIL brightness factor
+ *                       (NULL = 1).  Identity draws {pad, pad, 0} = the test transform (data.py:18).
+ * lc_resize_crop_u8   : RandomResizedCrop(out) / Resize (+CenterCrop) -> flip -> ToTensor -> Normalize (data.py:27-36), bit-exact to PIL's two-pass
+ *                       fixed-point bilinear resize.  draw[b] = {top, left, h, w, OH, OW, oy, ox}: crop box, resized size, origin of the out x out window.
+ *                       scratch: lc_resize_scratch_bytes(batch, H, out) bytes, 16-byte aligned.
+ * lc_eval_meter       : counts[t] += {#correct, #seen} per task (Trainer._validate, core/trainer.py:616-720): task >= 0 -> every sample to row `task`;
+ *                       task < 0 -> the row whose class range [bounds[t], bounds[t+1]) holds the label.  counts: uint64 [ntask][2].
+ * ------------------------------------------------------------------------------------------------------------------- */
+int lc_augment_cifar_u8(const uint8_t* src, const int64_t* idx, const int* draw, const float* bright, float* out, int batch, int H, int W, int pad,
+                        const float* mean3, const float* std3, lc_stream_t stream);
+long long lc_resize_scratch_bytes(int batch, int H, int out);
+int lc_resize_crop_u8(const uint8_t* src, const int64_t* idx, const int* draw, const int* flip, float* out, int batch, int H, int W, int out_size,
+                      const float* mean3, const float* std3, void* scratch, lc_stream_t stream);
+int lc_eval_meter(const int64_t* pred, const int64_t* label, int n, const int* bounds, int ntask, int task, unsigned long long* counts, lc_stream_t stream);
+/* total[t] += batch[t] and batch[t] = 0.  reference_rounding = 1 adds int(correct / seen * seen) in double, i.e. `int(acc * batch_size)` (trainer.py:644). */
+int lc_eval_fold(unsigned long long* batch_counts, unsigned long long* total, int ntask, int reference_rounding, lc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

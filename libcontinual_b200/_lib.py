@@ -114,6 +114,11 @@ SIGNATURES = {
     "lc_conv3x3_wgrad_tc": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P]),
     "lc_conv1x1s2": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "lc_bn_act_forward": (c_int, [P, P, P, P, P, P, P, c_longlong, c_int, P]),
+    "lc_augment_cifar_u8": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P]),
+    "lc_resize_scratch_bytes": (c_longlong, [c_int, c_int, c_int]),
+    "lc_resize_crop_u8": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "lc_eval_meter": (c_int, [P, P, c_int, P, c_int, c_int, P, P]),
+    "lc_eval_fold": (c_int, [P, P, c_int, c_int, P]),
     "lc_bn_backward": (c_int, [P, P, c_int, P, P, P, P, P, P, c_longlong, c_int, P, P]),
 }
 
@@ -173,3 +178,12 @@ def ptr(t):
 
 def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
+
+
+def host_acc(model, count, n):
+    """Accuracy as the Python float the reference returns from `inference` (a device->host sync, finetune.py:33-36) — unless the caller runs
+    `libcontinual_b200.trainer.validate`, which sets `model._defer_metrics` and keeps the counts on the device (lc_eval_meter): then NaN is returned and
+    nothing synchronises."""
+    if getattr(model, "_defer_metrics", False):
+        return float("nan")
+    return float(count.item()) / n

@@ -1,6 +1,7 @@
 // C entry points of the continual-learning specific kernels (cl_ops.cuh).  See include/lc_b200.h.
 #include "../../include/lc_b200.h"
 #include "cl_ops.cuh"
+#include "data_ops.cuh"
 
 using namespace lc;
 
@@ -90,6 +91,58 @@ int lc_herding_select(const float* feats, const int* cls_begin, int ncls, int di
 int lc_ncm_classify(const float* feat, const float* means, int batch, int ncls, int dim, int64_t* pred, lc_stream_t stream) {
     LC_CHECK_ARG(feat && means && pred && batch >= 1 && ncls >= 1 && dim == 64);
     ncm_classify_kernel<64><<<(batch + 3) / 4, 128, 0, (cudaStream_t)stream>>>(feat, means, batch, ncls, reinterpret_cast<long long*>(pred));
+    return lc_launch_status();
+}
+
+// ---- input pipeline / evaluation meter (data_ops.cuh) ------------------------------------------------------------------------------------------------
+static inline int data_grid(long long n) {
+    long long b = (n + 255) / 256;
+    const long long cap = (long long)kNumSMs * 8;
+    return (int)(b < 1 ? 1 : (b < cap ? b : cap));
+}
+
+int lc_augment_cifar_u8(const uint8_t* src, const int64_t* idx, const int* draw, const float* bright, float* out, int batch, int H, int W, int pad,
+                        const float* mean3, const float* std3, lc_stream_t stream) {
+    LC_CHECK_ARG(src && draw && out && mean3 && std3 && batch >= 1 && H >= 1 && W >= 1 && pad >= 0);
+    AugCifarArgs a{};
+    a.src = src; a.idx = reinterpret_cast<const long long*>(idx); a.draw = draw; a.bright = bright; a.out = out; a.B = batch; a.H = H; a.W = W; a.pad = pad;
+    for (int c = 0; c < 3; ++c) { a.mean[c] = mean3[c]; a.std[c] = std3[c]; }
+    augment_cifar_kernel<<<data_grid((long long)batch * H * W), 256, 0, (cudaStream_t)stream>>>(a);
+    return lc_launch_status();
+}
+
+long long lc_resize_scratch_bytes(int batch, int H, int out) {
+    return (long long)batch * 2 * out * (kResizeKMax + 2) * 4 + (long long)batch * H * out * 3;
+}
+
+int lc_resize_crop_u8(const uint8_t* src, const int64_t* idx, const int* draw, const int* flip, float* out, int batch, int H, int W, int out_size,
+                      const float* mean3, const float* std3, void* scratch, lc_stream_t stream) {
+    LC_CHECK_ARG(src && draw && out && mean3 && std3 && scratch && batch >= 1 && H >= 1 && W >= 1 && out_size >= 1 && ((uintptr_t)scratch % 16 == 0));
+    ResizeArgs a{};
+    a.src = src; a.idx = reinterpret_cast<const long long*>(idx); a.draw = draw; a.flip = flip; a.out = out; a.B = batch; a.H = H; a.W = W; a.OUT = out_size;
+    for (int c = 0; c < 3; ++c) { a.mean[c] = mean3[c]; a.std[c] = std3[c]; }
+    a.coef = reinterpret_cast<int*>(scratch);
+    a.cmin = a.coef + (size_t)batch * 2 * out_size * kResizeKMax;
+    a.tmp = reinterpret_cast<unsigned char*>(a.cmin + (size_t)batch * 2 * out_size * 2);
+    cudaStream_t st = (cudaStream_t)stream;
+    resize_coeffs_kernel<<<(batch * 2 * out_size + 127) / 128, 128, 0, st>>>(a);
+    if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
+    resize_h_kernel<<<data_grid((long long)batch * H * out_size), 256, 0, st>>>(a);
+    if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
+    resize_v_kernel<<<data_grid((long long)batch * out_size * out_size), 256, 0, st>>>(a);
+    return lc_launch_status();
+}
+
+int lc_eval_meter(const int64_t* pred, const int64_t* label, int n, const int* bounds, int ntask, int task, unsigned long long* counts, lc_stream_t stream) {
+    LC_CHECK_ARG(pred && label && counts && n >= 1 && ((task >= 0) || (bounds && ntask >= 1)));
+    eval_meter_kernel<<<data_grid(n), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(pred), reinterpret_cast<const long long*>(label), n,
+                                                                       bounds, ntask, task, counts);
+    return lc_launch_status();
+}
+
+int lc_eval_fold(unsigned long long* batch_counts, unsigned long long* total, int ntask, int reference_rounding, lc_stream_t stream) {
+    LC_CHECK_ARG(batch_counts && total && ntask >= 1 && ntask <= 1024);
+    eval_fold_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(batch_counts, total, ntask, reference_rounding);
     return lc_launch_status();
 }
 

@@ -18,7 +18,7 @@ from typing import Dict, List, Optional  # noqa: F401
 import torch
 import torch.nn as nn
 
-from .._lib import LcError, check, stream_ptr
+from .._lib import LcError, check, stream_ptr, host_acc
 from ..vit_engine import DIM
 from .inflora import _FlatLoss
 from .l2p import ViTZoo
@@ -215,7 +215,7 @@ class _PrefixPromptMethod(nn.Module):
         check(lib.lc_loss_ce_masked(bb["logits"].data_ptr(), C, y.data_ptr(), B, 0, n, None, 0.0, bb["dlogits"].data_ptr(), bb["pred"].data_ptr(),
                                     self.scal.data_ptr(), st), "argmax")
         eng.launches += 1
-        return bb["pred"], float(self.scal[1].item()) / B
+        return bb["pred"], host_acc(self, self.scal[1], B)
 
 
 class DualPrompt(_PrefixPromptMethod):

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .._lib import check, stream_ptr
+from .._lib import check, stream_ptr, host_acc
 from ..nn_engine import ALEXNET_SPEC, AlexNetEngine
 from .backbone.resnet import _Node
 
@@ -277,5 +277,4 @@ class GPM(nn.Module):
             preds = eng.heads_forward(B, task_id).max(1)[1] + bias
         else:
             preds = eng.heads_forward(B, None).max(1)[1]
-        acc = preds.eq(y).sum().item() / y.size(0)
-        return preds, acc
+        return preds, host_acc(self, preds.eq(y).sum(), y.size(0))

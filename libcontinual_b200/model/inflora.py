@@ -23,7 +23,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .._lib import LcError, check, stream_ptr
+from .._lib import LcError, check, stream_ptr, host_acc
 from ..vit_engine import DIM, LoraState
 from .l2p import ViTZoo
 
@@ -184,7 +184,7 @@ class InfLoRA_OPT(nn.Module):
         check(lib.lc_loss_ce_masked(bb["logits"].data_ptr(), C, y.data_ptr(), B, 0, seen, None, 0.0, bb["dlogits"].data_ptr(), bb["pred"].data_ptr(),
                                     self.scal.data_ptr(), st), "argmax")
         eng.launches += 2
-        return bb["pred"], float(self.scal[1].item()) / B
+        return bb["pred"], host_acc(self, self.scal[1], B)
 
     # ---- task boundaries -------------------------------------------------------------------------------
     @torch.no_grad()

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .._lib import LcError, check, stream_ptr
+from .._lib import LcError, check, stream_ptr, host_acc
 from ..vit_engine import DIM, StackedLoraState
 from .inflora import _FlatLoss
 from .l2p import ViTZoo
@@ -223,7 +223,7 @@ class InfLoRA(nn.Module):
         check(lib.lc_loss_ce_masked(bb["logits"].data_ptr(), C, y.data_ptr(), B, 0, n, None, 0.0, bb["dlogits"].data_ptr(), bb["pred"].data_ptr(),
                                     self.scal.data_ptr(), st), "argmax")
         eng.launches += 2
-        return bb["pred"], float(self.scal[1].item()) / B
+        return bb["pred"], host_acc(self, self.scal[1], B)
 
 
 def dualgpm_update_v1(mat_list, feature_list: List[np.ndarray], project_type: List[str], cur_task: int, total_sessions: int, lame: float, lamb: float):

@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from .._lib import check, stream_ptr
+from .._lib import check, stream_ptr, host_acc
 from ..vit_engine import DIM, ViTEngine, vit_param_layout
 
 CLIP_SCRATCH_FLOATS = 2 * 296 + 8
@@ -268,4 +268,4 @@ class L2P(nn.Module):
         check(lib.lc_loss_ce_masked(bb["logits"].data_ptr(), C, y.data_ptr(), B, 0, C, None, 0.0, bb["dlogits"].data_ptr(), bb["pred"].data_ptr(),
                                     self.scal.data_ptr(), stream_ptr()), "argmax")
         eng.launches += 1
-        return bb["pred"], float(self.scal[1].item()) / B
+        return bb["pred"], host_acc(self, self.scal[1], B)

@@ -13,6 +13,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .._lib import host_acc
+
 from ..engine import ResNetEngine, TeacherState
 from .backbone.resnet import CifarResNet
 
@@ -202,8 +204,7 @@ class _ResNetMethod(nn.Module):
         x, y = self._to_device(data)
         logit = self._infer_logits(x)
         pred = torch.argmax(logit, dim=1)
-        acc = torch.sum(pred == y).item()
-        return pred, acc / x.size(0)
+        return pred, host_acc(self, torch.sum(pred == y), x.size(0))
 
 
 class Finetune(_ResNetMethod):
@@ -381,7 +382,7 @@ class ICarl(_ResNetMethod):
         else:
             logits = self._infer_logits(x)[:, :self.accu_cls_num]
             pred = torch.argmax(logits, dim=1)
-        return pred, torch.sum(pred == y).item() / x.size(0)
+        return pred, host_acc(self, torch.sum(pred == y), x.size(0))
 
 
 class LWF(_ResNetMethod):

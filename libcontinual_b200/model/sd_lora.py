@@ -19,7 +19,7 @@ from typing import List, Optional
 import torch
 import torch.nn as nn
 
-from .._lib import LcError, check, stream_ptr
+from .._lib import LcError, check, stream_ptr, host_acc
 from ..vit_engine import DIM, SDLoraState
 from .inflora import _FlatLoss
 from .l2p import ViTZoo
@@ -196,4 +196,4 @@ class SD_LoRA(nn.Module):
         check(lib.lc_loss_ce_kd(bb["logits"].data_ptr(), C, None, 0, y.data_ptr(), B, 0, n, 0, 0.0, 1.0, n, bb["dlogits"].data_ptr(), bb["pred"].data_ptr(),
                                 self.scal.data_ptr(), st), "argmax")
         eng.launches += 1
-        return bb["pred"], float(self.scal[1].item()) / B
+        return bb["pred"], host_acc(self, self.scal[1], B)

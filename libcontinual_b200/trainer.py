@@ -288,3 +288,77 @@ class GraphedFlatStep:
 
     def correct(self) -> torch.Tensor:
         return self.model.scal[1]
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------------------
+# Evaluation loop: `Trainer._validate` (core/trainer.py:616-720)
+# ---------------------------------------------------------------------------------------------------------------------------------------------------
+class EvalMeter:
+    """#correct / #seen per task, accumulated on the device by `lc_eval_meter` (integer atomics) and read back ONCE per validation pass.  The reference
+    converts every batch's accuracy to a Python float (`.item()` inside `inference`, then `int(acc * batch_size)`, trainer.py:644-645) — a device
+    synchronisation per batch that bounds small-model evaluation once the step itself is a graph replay."""
+
+    def __init__(self, ntask: int, device, bounds=None):
+        from . import _lib
+        self.lib = _lib.load()
+        self.ntask = int(ntask)
+        self.counts = torch.zeros(self.ntask, 2, dtype=torch.int64, device=device)       # uint64 on the device; values stay far below 2^63
+        self.batch = torch.zeros(self.ntask, 2, dtype=torch.int64, device=device)        # the current batch's counts, folded into `counts` per batch
+        self.bounds = None if bounds is None else torch.tensor(list(bounds), dtype=torch.int32, device=device)
+        assert self.bounds is None or self.bounds.numel() == self.ntask + 1
+
+    def update(self, pred: torch.Tensor, label: torch.Tensor, task: int = -1, reference_rounding: bool = False):
+        """reference_rounding: fold the batch as `int(acc * batch_size)` (trainer.py:644, per-task mode) instead of the exact count."""
+        from ._lib import check
+        assert pred.is_cuda and label.is_cuda and pred.dtype == torch.int64 and label.dtype == torch.int64 and pred.is_contiguous() and label.is_contiguous()
+        st = torch.cuda.current_stream(pred.device).cuda_stream
+        check(self.lib.lc_eval_meter(pred.data_ptr(), label.data_ptr(), int(pred.numel()), None if self.bounds is None else self.bounds.data_ptr(), self.ntask,
+                                     int(task), self.batch.data_ptr(), st), "lc_eval_meter")
+        check(self.lib.lc_eval_fold(self.batch.data_ptr(), self.counts.data_ptr(), self.ntask, int(reference_rounding), st), "lc_eval_fold")
+
+    def result(self):
+        c = self.counts.cpu().numpy()                     # the one synchronisation of the pass
+        return c[:, 0].copy(), c[:, 1].copy()
+
+
+@torch.no_grad()
+def validate(model, dataloaders, task_idx: int, *, setting: str = "task-agnostic", testing_per_task: bool = True, init_cls_num: Optional[int] = None,
+             inc_cls_num: Optional[int] = None):
+    """`Trainer._validate(task_idx)` (trainer.py:616-720) -> {'avg_acc', 'per_task_acc'} with the same rounding (`round(100 * correct / count, 2)`).
+
+    dataloaders: the per-task test loaders of tasks 0..task_idx (iterables of {'image', 'label'} batches; `libcontinual_b200.data.GpuLoader` keeps them on
+    the device).  testing_per_task=True runs them one after another (task-aware: `inference(batch, task_id=t)`); False evaluates all batches and attributes
+    every sample to the task whose class range holds its label (needs init_cls_num / inc_cls_num), like the reference's merged loader — whose shuffling
+    cannot change integer counts."""
+    model.eval()
+    dev = next((p.device for p in model.parameters()), torch.device("cuda", torch.cuda.current_device()))
+    nt = task_idx + 1
+    loaders = list(dataloaders)[:nt]
+    if testing_per_task:
+        meter = EvalMeter(nt, dev)
+    else:
+        if setting == "task-aware":
+            raise NotImplementedError("task-aware evaluation needs testing_per_task=True (trainer.py:693-695)")
+        assert init_cls_num is not None and inc_cls_num is not None
+        bounds = [0]
+        for t in range(nt):
+            bounds.append(bounds[-1] + (init_cls_num if t == 0 else inc_cls_num))
+        meter = EvalMeter(nt, dev, bounds)
+    prev = getattr(model, "_defer_metrics", False)
+    model._defer_metrics = True          # `inference` keeps its metric on the device (no .item())
+    try:
+        for t, loader in enumerate(loaders):
+            for batch in loader:
+                if setting == "task-aware":
+                    pred, _ = model.inference(batch, task_id=t)
+                else:
+                    pred, _ = model.inference(batch)
+                label = batch["label"].to(pred.device, torch.int64, non_blocking=True).contiguous()
+                # per-task mode counts `int(acc * batch_size)` per batch (trainer.py:644); the merged mode counts exactly (np.sum(preds == labels), :700)
+                meter.update(pred.contiguous(), label, t if testing_per_task else -1, reference_rounding=testing_per_task)
+    finally:
+        model._defer_metrics = prev
+    correct, count = meter.result()
+    per_task = [round(int(c) * 100 / int(n), 2) if n > 0 else 0 for c, n in zip(correct, count)]
+    avg = round(int(correct.sum()) * 100 / int(count.sum()), 2)
+    return {"avg_acc": avg, "per_task_acc": per_task}
