@@ -896,6 +896,32 @@ def run_ours(args, ctx, workload):
         plugin = {"value": per / (pm * 1e-3), "unit": "images/s", "ms_per_step": pm,
                   "path": "plugin observe->zero_grad->loss.backward()->optim.step->loss.item() (trainer.py:601-612), eager launches"}
     e2e["plugin_eager"] = plugin
+    # the device-resident input pipeline in front of the same step: uint8 dataset in HBM, per-batch random draws from pinned host memory,
+    # RandomCrop + flip + brightness + normalise in one launch (libcontinual_b200.data.GpuLoader), then GraphedStep.run + loss().item()
+    pipeline = None
+    if world == 1 and img == 32:
+        import numpy as np
+        from libcontinual_b200.data import DeviceImageDataset, GpuLoader
+        rngp = np.random.default_rng(11)
+        nimg = per * 20
+        ds = DeviceImageDataset(rngp.integers(0, 256, (nimg, 32, 32, 3), dtype=np.uint8), rngp.integers(lo, hi, nimg), device=device)
+        loader = GpuLoader(ds, per, "cifar_train", shuffle=True, drop_last=True, seed=3)
+        for b in loader:                       # warm-up epoch
+            step.run(b["image"], b["label"]); float(step.loss())
+        torch.cuda.synchronize()
+        nst = 0
+        e0.record()
+        for _ in range(max(1, Ke // len(loader))):
+            for b in loader:
+                step.run(b["image"], b["label"])
+                lossv = step.loss().item()
+                nst += 1
+        e1.record()
+        torch.cuda.synchronize()
+        pm = e0.elapsed_time(e1) / nst
+        pipeline = {"value": per / (pm * 1e-3), "unit": "images/s", "ms_per_step": pm, "h2d_bytes_per_step": per * (8 + 16 + 4), "d2h_bytes_per_step": 4,
+                    "path": "GpuLoader(uint8 dataset resident in HBM, cifar_train transform on the device) -> GraphedStep.run -> loss().item() every step"}
+    e2e["pipeline"] = pipeline
 
     strong = None
     if not args.global_batch:

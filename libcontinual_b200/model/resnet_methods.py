@@ -34,7 +34,7 @@ class _ArenaLoss(torch.autograd.Function):
         # autograd gets its own copy (one 1.9 MB kernel): p.grad must never alias the live arena, which the next fused step
         # overwrites, or gradient accumulation / in-place clipping on p.grad would corrupt either side
         eng.autograd_grads = eng.grads * g
-        return (None, None, *owner._grad_views(eng.autograd_grads))
+        return (None, None, *owner._grad_views_fast(eng.autograd_grads))
 
 
 class _Head(nn.Module):
@@ -148,9 +148,40 @@ class _ResNetMethod(nn.Module):
         y = data["label"].to(self.engine.device, dtype=torch.int64, non_blocking=True).contiguous()
         return x, y
 
+    def _params_cached(self):
+        """`_params()` walks named_parameters() of the whole backbone (0.4 ms of host time per step); the list only changes when the head does."""
+        key = (self.engine.ncls, id(self.network.classifier), getattr(self, "n_old_rows", None))
+        c = self.__dict__.get("_params_cache")
+        if c is None or c[0] != key:
+            c = (key, self._params())
+            self.__dict__["_params_cache"] = c
+        return c[1]
+
+    def _grad_views_fast(self, arena):
+        """`_grad_views(arena)` with the slicing plan cached: one split_with_sizes + one view per tensor instead of a dict lookup, a slice and a view
+        each (fresh tensor objects every call, so that autograd can adopt them as p.grad without a copy)."""
+        key = (self.engine.ncls, getattr(self, "n_old_rows", None))
+        c = self.__dict__.get("_gv_plan")
+        if c is None or c[0] != key:
+            ref = self._grad_views(arena)
+            base = arena.data_ptr()
+            offs = [(v.data_ptr() - base) // 4 for v in ref]
+            sizes, shapes, pos = [], [], 0
+            if any(o2 < o1 + v1.numel() for o1, o2, v1 in zip(offs, offs[1:], ref)):
+                return ref                       # not in ascending, disjoint arena order: keep the plain path
+            for o, v in zip(offs, ref):          # views are in arena order; gaps (alignment padding, unused head rows) become their own chunks
+                if o > pos:
+                    sizes.append(o - pos); shapes.append(None)
+                sizes.append(v.numel()); shapes.append(tuple(v.shape)); pos = o + v.numel()
+            if pos < arena.numel():
+                sizes.append(arena.numel() - pos); shapes.append(None)
+            c = (key, sizes, shapes)
+            self.__dict__["_gv_plan"] = c
+        return tuple(ch.view(sh) for ch, sh in zip(arena.split_with_sizes(c[1]), c[2]) if sh is not None)
+
     def _finish(self, B, y):
         eng = self.engine
-        loss = _ArenaLoss.apply(self, eng.scal[0], *self._params())
+        loss = _ArenaLoss.apply(self, eng.scal[0], *self._params_cached())
         pred = eng.pred[:B].clone()
         acc = eng.scal[1].item()                 # the reference syncs here too (finetune.py:24)
         return pred, acc / B, loss
@@ -176,6 +207,44 @@ class _ResNetMethod(nn.Module):
         eng.loss(y, B, ce_lo, ce_hi, pred_n, teacher_logits=tl, kd_n=kd_n, kd_w=kd_w, T=2.0)
         eng.head_backward(B, n)
         eng.backward(x)
+
+    # -- observe() as a CUDA-graph replay ---------------------------------------------------------------------------------------
+    def _graph_key(self):
+        eng = self.engine
+        return (self.task_idx, eng.ncls, getattr(eng, "precision", None), id(getattr(self, "fisher", None)), id(getattr(self, "teacher", None)),
+                id(getattr(self, "ref_model", None)), getattr(self, "cur_lamda", None))
+
+    def _observe_launch(self, x, y):
+        """The kernels of one `observe` (forward, loss, backward, regulariser).  A Trainer calls observe with the same shapes thousands of times per task
+        (trainer.py:563-614): the first two calls of a configuration launch eagerly (~200 launches through ctypes), the third captures the same launch
+        sequence into a CUDA graph and every later call is a copy into the graph's input buffers plus one replay — the plugin surface stays exactly the
+        reference's, the per-launch host work disappears.  LC_B200_EAGER_OBSERVE=1 keeps every call eager."""
+        import os
+        if os.environ.get("LC_B200_EAGER_OBSERVE") == "1" or not self.training:
+            return self._launch_step(x, y)
+        obs = self.__dict__.setdefault("_obs_graphs", {})
+        key = (x.shape[0],) + self._graph_key()
+        st = obs.get(key)
+        if st is None:
+            if obs and next(iter(obs))[1:] != key[1:]:
+                obs.clear()                               # a new task / head size: the old task's graphs (and their memory pool) are released
+            st = obs[key] = {"n": 0}
+        st["n"] += 1
+        if st["n"] <= 2:
+            return self._launch_step(x, y)
+        if "g" not in st:
+            st["x"], st["y"] = torch.empty_like(x), torch.empty_like(y)
+            pending = self.backbone.num_batches_pending
+            torch.cuda.synchronize(self.engine.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch_step(st["x"], st["y"])
+            self.backbone.num_batches_pending = pending   # capture runs the host bookkeeping once without executing a kernel
+            st["g"] = g
+        st["x"].copy_(x, non_blocking=True)
+        st["y"].copy_(y, non_blocking=True)
+        st["g"].replay()
+        self.backbone.num_batches_pending += 1
 
     def _teacher_stream(self):
         if getattr(self, "_tstream", None) is None:
@@ -220,7 +289,7 @@ class Finetune(_ResNetMethod):
 
     def observe(self, data):
         x, y = self._to_device(data)
-        self._launch_step(x, y)
+        self._observe_launch(x, y)
         return self._finish(x.shape[0], y)
 
 
@@ -252,7 +321,7 @@ class EWC(_ResNetMethod):
 
     def observe(self, data):
         x, y = self._to_device(data)
-        self._launch_step(x, y)
+        self._observe_launch(x, y)
         return self._finish(x.shape[0], y)
 
     def after_task(self, task_idx, buffer, train_loader, test_loaders):
@@ -364,7 +433,7 @@ class ICarl(_ResNetMethod):
 
     def observe(self, data):
         x, y = self._to_device(data)
-        self._launch_step(x, y)
+        self._observe_launch(x, y)
         return self._finish(x.shape[0], y)
 
     def inference(self, data):
@@ -422,7 +491,7 @@ class LWF(_ResNetMethod):
 
     def observe(self, data):
         x, y = self._to_device(data)
-        self._launch_step(x, y)
+        self._observe_launch(x, y)
         return self._finish(x.shape[0], y)
 
 
@@ -587,7 +656,7 @@ class LUCIR(_ResNetMethod):
 
     def observe(self, data):
         x, y = self._to_device(data)
-        self._launch_step(x, y)
+        self._observe_launch(x, y)
         return self._finish(x.shape[0], y)
 
     def _infer_logits(self, x):

@@ -29,9 +29,9 @@ def rel_l2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def make_backbone(p, b, max_batch=B):
+def make_backbone(p, b, max_batch=B, precision="fp32"):
     import libcontinual_b200.model as M
-    bb = M.cifar_resnet32(max_batch=max_batch)
+    bb = M.cifar_resnet32(max_batch=max_batch, precision=precision)
     sd = {**p, **b}
     bb.load_state_dict(sd, strict=True)
     return bb
@@ -462,3 +462,61 @@ def test_icarl_after_task_herding_and_ncm_vs_oracle():
     clear = (top2[:, 1] - top2[:, 0]) > 1e-6 * top2[:, 0]
     assert torch.equal(pred.cpu()[clear], port.ncm_classify(fo, mo)[clear])
     assert int(pred.min()) >= 0 and int(pred.max()) < 4
+
+
+@pytest.mark.parametrize("method", ["ewc", "icarl", "lucir"])
+def test_graph_replayed_observe_equals_eager_observe(method, monkeypatch):
+    """`observe` turns itself into a CUDA-graph replay from the third call of a configuration on (_observe_launch): six reference-order steps
+    (observe -> zero_grad -> backward -> step) give bit-identical parameters, running statistics and per-step losses with and without it
+    (tensor-core mode, batch 128: the benchmark configuration of the plugin path)."""
+    import libcontinual_b200.model as M
+    from libcontinual_b200.optim import SGD
+
+    def run(eager):
+        if eager:
+            monkeypatch.setenv("LC_B200_EAGER_OBSERVE", "1")
+        else:
+            monkeypatch.delenv("LC_B200_EAGER_OBSERVE", raising=False)
+        torch.manual_seed(5)
+        p, b, fc_w, fc_b = synth_resnet_state(77, 60)
+        if method == "lucir":
+            from oracle.make_golden import cifar_to_lucir_name
+            bb = M.resnet32_V2(max_batch=128, precision="tc")
+            bb.load_state_dict({cifar_to_lucir_name(k): v for k, v in {**p, **b}.items()}, strict=True)
+            m = M.LUCIR(bb, 64, 100, device=torch.device("cuda"), init_cls_num=50, inc_cls_num=10, K=2, lw_mr=1, lamda=5, dist=0.5)
+            m.before_task(0, None, None, None)
+            m.before_task(1, None, None, None)
+            hi = 60
+        elif method == "icarl":
+            bb = make_backbone(p, b, max_batch=128, precision="tc")
+            m = M.ICarl(bb, 64, 100, device=torch.device("cuda"), init_cls_num=50, inc_cls_num=5, task_num=11)
+            m.before_task(0, None, None, None)
+            m.snapshot_teacher(); m.cur_task_id += 1
+            m.before_task(1, None, None, None)
+            hi = 55
+        else:
+            bb = make_backbone(p, b, max_batch=128, precision="tc")
+            m = M.EWC(bb, 64, 100, device=torch.device("cuda"), init_cls_num=10, inc_cls_num=10, lamda=1000.0)
+            m.before_task(0, None, None, None)
+            m.before_task(1, None, None, None)
+            m.ref_param = m.engine.params * 0.999
+            m.fisher = torch.rand_like(m.engine.params) * 1e-3
+            hi = 20
+        m.train()
+        opt = SGD(m.get_parameters(None), lr=0.05, momentum=0.9, weight_decay=5e-4, engine=m.engine)
+        losses = []
+        for s in range(6):
+            x, y = synth_batch(3000 + s, 128, 0, hi)
+            pred, acc, loss = m.observe({"image": x, "label": y})
+            opt.zero_grad(); loss.backward(); opt.step()
+            losses.append(float(loss))
+        torch.cuda.synchronize()
+        assert not m.engine.tensor_core_error()
+        graphed = any("g" in st for st in m.__dict__.get("_obs_graphs", {}).values())
+        return m.engine.params.clone(), m.engine.rstat.clone(), losses, graphed, int(m.backbone.num_batches_pending)
+
+    pe, re_, le, ge, ne = run(True)
+    pg, rg, lg, gg, ng = run(False)
+    assert not ge and gg                                   # the second run really went through the graph
+    assert le == lg and ne == ng
+    assert torch.equal(pe, pg) and torch.equal(re_, rg)
