@@ -31,6 +31,21 @@ sys.path.insert(0, ROOT)
 
 METRIC = "images/sec/task-step"
 BATCH = 128
+GPM_PROJECT = False          # --gpm-project: BASELINE config C5 in full ("LwF + GPM"): the lwf18 step + the GPM projection of every conv gradient
+
+
+def c5_bases(layout, seed=97):
+    """seeded orthonormal U_l of rank 10 % of Cin*k*k for every conv whose Cin*k*k is a multiple of 8 (all but the 3-channel stem)."""
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape in layout:
+        if len(shape) == 4 and (shape[1] * shape[2] * shape[3]) % 8 == 0:
+            D = shape[1] * shape[2] * shape[3]
+            q, _ = np.linalg.qr(rng.standard_normal((D, max(1, D // 10))))
+            out[name] = torch.from_numpy(q.astype(np.float32))
+    return out
 
 
 def parse():
@@ -50,6 +65,8 @@ def parse():
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the PyTorch-eager-on-cuda:0 leg (the denominator of north_star's >=1.3x target)")
     ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: shard this global batch over the ranks (reference semantic "
                     "batch_size // n_gpu, trainer.py:238); 0 = per-GPU batch 128 (weak scaling)")
+    ap.add_argument("--gpm-project", action="store_true", help="--workload lwf18 only: add the GPM projection of every conv gradient onto the complement of "
+                    "seeded orthonormal bases (rank 10 %% of Cin*k*k) after backward — BASELINE config C5 'LwF + GPM' in full (SURVEY 8d)")
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
                     help="conv arithmetic: tc = tcgen05 tensor cores (TF32 fwd/dgrad, BF16-operand wgrad, fp32 accumulate), fp32 = exact CUDA-core path")
     return ap.parse_args()
@@ -88,6 +105,9 @@ def make_oracle(workload, seed=1993):
         orc = port.ResNetMethodOracle("lwf", p, b, fc_w[:100], fc_b[:100], init_cls=100, inc_cls=20, arch="resnet18", maxpool=True)
         orc.snapshot_teacher(); orc.prev_cls, orc.task_idx = 100, 1
         orc.grow_head(fc_w, fc_b)
+        if GPM_PROJECT:
+            layout = [(k, tuple(v.shape)) for k, v in p.items()]
+            orc.proj = {"backbone." + n: (U @ U.T) for n, U in c5_bases(layout).items()}
         return orc, 120
     p, b = port.cifar_resnet_init(rng)
     bound = 1.0 / 8.0
@@ -140,6 +160,8 @@ def time_oracle(workload, steps, warmup, device="cpu"):
         if orc.teacher is not None:
             tp, tb, tw, tbias = orc.teacher
             orc.teacher = (mv(tp), mv(tb), tw.to(dev), tbias.to(dev))
+        if getattr(orc, "proj", None):
+            orc.proj = mv(orc.proj)
         orc.ref, orc.fisher = mv(orc.ref), mv(orc.fisher)
         batches = [(x.to(dev), y.to(dev)) for x, y in batches]
     sync = (lambda: torch.cuda.synchronize()) if device == "cuda" else (lambda: None)
@@ -356,6 +378,8 @@ def build_model(workload, device, precision="tc"):
         m = M.LWF(bb, 512, 200, device=device, init_cls_num=100, inc_cls_num=20)
         m.before_task(0, None, None, None)
         m.before_task(1, None, None, None)                # 120 classes, teacher = frozen copy of the task-0 network
+        if GPM_PROJECT:
+            m.set_gradient_projection(c5_bases(m.engine.layout))
         m.train()
         return m, 100, 120
     bb = M.cifar_resnet32(max_batch=BATCH, num_classes=100, precision=precision)
@@ -967,7 +991,8 @@ def run_ours(args, ctx, workload):
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
             "dtype": "bf16" if workload == "lwf18" else ("tf32" if args.precision == "tc" else "f32"), "data": "synthetic",
-            "config": {"workload": workload_name(workload), "global_batch": per * world, "per_gpu_batch": per, "parallelism": f"dp{world}",
+            "config": {"workload": workload_name(workload) + (" + GPM projection of every conv gradient (20 layers, rank 10 % bases): config C5 in full"
+                                                             if GPM_PROJECT else ""), "global_batch": per * world, "per_gpu_batch": per, "parallelism": f"dp{world}",
                        "collective": step.collective,
                        "l2": ("per-step working set of several GB of saved activations > 126 MB L2 (no explicit flush)" if workload == "lwf18" else
                               "per-step working set ~330 MB of fp32 activations + 8 rotating input batches > 126 MB L2 (no explicit flush)"),
@@ -981,7 +1006,9 @@ def run_ours(args, ctx, workload):
 
 
 def main():
+    global GPM_PROJECT
     args = parse()
+    GPM_PROJECT = bool(args.gpm_project) and args.workload == "lwf18"
     if args.impl == "reference":
         return run_reference(args)
     import gc

@@ -207,12 +207,13 @@ class _ResNetMethod(nn.Module):
         eng.loss(y, B, ce_lo, ce_hi, pred_n, teacher_logits=tl, kd_n=kd_n, kd_w=kd_w, T=2.0)
         eng.head_backward(B, n)
         eng.backward(x)
+        self._project_gradients()
 
     # -- observe() as a CUDA-graph replay ---------------------------------------------------------------------------------------
     def _graph_key(self):
         eng = self.engine
         return (self.task_idx, eng.ncls, getattr(eng, "precision", None), id(getattr(self, "fisher", None)), id(getattr(self, "teacher", None)),
-                id(getattr(self, "ref_model", None)), getattr(self, "cur_lamda", None))
+                id(getattr(self, "ref_model", None)), getattr(self, "cur_lamda", None), id(getattr(self, "_gpm", None)))
 
     def _observe_launch(self, x, y):
         """The kernels of one `observe` (forward, loss, backward, regulariser).  A Trainer calls observe with the same shapes thousands of times per task
@@ -245,6 +246,34 @@ class _ResNetMethod(nn.Module):
         st["y"].copy_(y, non_blocking=True)
         st["g"].replay()
         self.backbone.num_batches_pending += 1
+
+    # -- GPM-style gradient projection on top of any ResNet method (BASELINE config C5: "LwF + GPM") ---------------------------------------
+    def set_gradient_projection(self, bases):
+        """bases: {parameter name (as in `engine.layout`): U [Cin*k*k, r]} — after every backward the named conv gradients lose their component inside
+        span(U): g <- g - g.view(Cout, -1) @ (U U^T)  (gpm.py:78-81), in place in the gradient arena through `GPMProjector` (three BF16 tcgen05 GEMMs on
+        a two-term split per layer, fp32-level accuracy).  `None` removes it.  The reference has no recipe that combines LwF with GPM (its GPM is
+        AlexNet-only); this is the operator C5 names, applied where the reference's GPM applies it: between backward and step."""
+        if not bases:
+            self._gpm = None
+            return
+        from ..gpm import GPMProjector
+        names = list(bases.keys())
+        for n in names:
+            shape = self.engine.param_off[n][1]
+            assert len(shape) == 4 and (shape[1] * shape[2] * shape[3]) % 8 == 0, f"{n}: Cin*k*k must be a multiple of 8 for the tcgen05 projection"
+        self._gpm = (names, GPMProjector([bases[n] for n in names], device=self.engine.device))
+        self.__dict__.get("_obs_graphs", {}).clear()
+
+    def _project_gradients(self):
+        gp = getattr(self, "_gpm", None)
+        if gp is None:
+            return
+        names, proj = gp
+        eng = self.engine
+        for i, n in enumerate(names):
+            g = eng.param_view(n, eng.grads)
+            proj.project_(i, g.view(g.shape[0], -1))
+        eng.launches += 4 * len(names)
 
     def _teacher_stream(self):
         if getattr(self, "_tstream", None) is None:

@@ -948,6 +948,9 @@ class ResNetMethodOracle:
         named = self.named()
         grads = torch.autograd.grad(loss, list(named.values()), allow_unused=True)
         gd = {n: (g if g is not None else torch.zeros_like(v)) for (n, v), g in zip(named.items(), grads)}
+        # BASELINE config C5 ("LwF + GPM"): every conv gradient loses its component inside span(U_l), exactly gpm.py:78-81
+        for n, M in (getattr(self, "proj", None) or {}).items():
+            gd[n] = gpm_project(gd[n], M)
         pred = lg.argmax(dim=1)
         acc = float((pred == y).sum()) / x.shape[0]
         if apply_update:

@@ -232,3 +232,62 @@ def test_lwf_resnet18_graphed_step_equals_eager():
         torch.cuda.synchronize()
         outs.append((m.engine.params.clone(), m.engine.rstat.clone(), float(m.engine.scal[0])))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
+
+
+def test_lwf_resnet18_with_gradient_projection_c5():
+    """BASELINE config C5 ("LwF + GPM" on ResNet18): the LwF task-1 step followed by the GPM projection of every 3x3 / 1x1 conv gradient onto the
+    complement of seeded orthonormal bases (rank = 10 % of Cin*k*k).  Checks: (1) the projected gradient equals the SAME step's unprojected
+    gradient projected in float64 (the projection operator alone, 2e-5); (2) it is orthogonal to the bases; (3) non-projected tensors are untouched;
+    (4) the step through the oracle with `proj` agrees to the LwF tolerance."""
+    import libcontinual_b200.model as M
+    torch.manual_seed(3)
+    p, b, fc_w, fc_b = synth_resnet18_state(2020, 20)
+
+    def build():
+        torch.manual_seed(3)
+        bb = make_backbone(p, b)
+        m = M.LWF(bb, 512, 200, device=torch.device("cuda"), init_cls_num=10, inc_cls_num=10)
+        m.before_task(0, None, None, None)
+        w, bias = m.engine.fc_views(10)
+        w.copy_(fc_w[:10].cuda()); bias.copy_(fc_b[:10].cuda())
+        m.before_task(1, None, None, None)
+        w, bias = m.engine.fc_views(20)
+        w[10:].copy_(fc_w[10:20].cuda()); bias[10:].copy_(fc_b[10:20].cuda())
+        m.train()
+        return m
+
+    m0, m1 = build(), build()
+    eng = m1.engine
+    rng = np.random.default_rng(55)
+    bases = {}
+    for name, shape in eng.layout:
+        if len(shape) == 4 and (shape[1] * shape[2] * shape[3]) % 8 == 0:
+            D = shape[1] * shape[2] * shape[3]
+            q, _ = np.linalg.qr(rng.standard_normal((D, max(1, D // 10))))
+            bases[name] = torch.from_numpy(q.astype(np.float32))
+    assert len(bases) >= 19                                   # every conv but the 3-channel stem
+    m1.set_gradient_projection(bases)
+    x, y = synth_batch(2100, B, 10, 20, img=64)
+    m0.observe({"image": x, "label": y})
+    m1.observe({"image": x, "label": y})
+    torch.cuda.synchronize()
+    assert not eng.tensor_core_error()
+    for name, shape in eng.layout:
+        g0 = m0.engine.param_view(name, m0.engine.grads).double().cpu()
+        g1 = eng.param_view(name, eng.grads).double().cpu()
+        if name in bases:
+            U = bases[name].double()
+            want = g0.view(shape[0], -1) - (g0.view(shape[0], -1) @ U) @ U.T
+            assert rel_l2(g1.view(shape[0], -1), want) < 2e-5, name
+            assert float((g1.view(shape[0], -1) @ U).norm() / (g0.view(shape[0], -1) @ U).norm()) < 1e-4, name
+        else:
+            assert torch.equal(g0, g1), name
+    orc = port.ResNetMethodOracle("lwf", p, b, fc_w[:10], fc_b[:10], init_cls=10, inc_cls=10, arch="resnet18", maxpool=True, conv_mode="bf16")
+    orc.snapshot_teacher(); orc.prev_cls = 10; orc.task_idx = 1
+    orc.grow_head(fc_w[:20], fc_b[:20])
+    orc.proj = {"backbone." + n: (U @ U.T) for n, U in bases.items()}
+    _, _, lo, go = orc.step(x, y, apply_update=False)
+    assert abs(float(eng.scal[0]) - float(lo)) <= 5e-3
+    got = torch.cat([eng.param_view(n, eng.grads).reshape(-1).double().cpu() for n in bases])
+    ref = torch.cat([go["backbone." + n].reshape(-1).double() for n in bases])
+    assert float((got - ref).norm() / ref.norm()) <= 3.5e-1
