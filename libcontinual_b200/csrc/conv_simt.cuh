@@ -50,6 +50,7 @@ struct BnLazy {
 // Phase 1 (no barrier): this thread's slice of the rows -> red.  Phase 2 (three barriers): combine.  Split so that a kernel can put independent
 // work (its tile copies) between the two and so that the 12 row registers of phase 1 are dead before that work's registers go live.
 __device__ __forceinline__ void bn_partial_sums_load(const float* partial, int nparts, int C, double* red) {
+    if (threadIdx.x >= 256) return;                    // CTAs may carry extra (non-worker) warps: the reduction is laid out for 256 threads
     const int CQ = C >> 1, NSL = 256 / CQ;             // float4 column groups; row slices
     const int cq = threadIdx.x % CQ, sl = threadIdx.x / CQ;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;

@@ -166,6 +166,8 @@ struct ConvTcArgs {
     const float* pro_shift;
     BnLazy pro_lazy;         // forward variant: pro_lazy.partial != null -> the prologue's scale / shift are reduced here from the producer's partial rows
     const float* addend;     // nullable (may alias out)
+    const float* pro_res;    // MODE 2: residual operand of the prologue (the previous block's input), same shape as `in`
+    float* pro_out;          // MODE 2: the previous block's output, written for the rows each CTA owns
     const float* pro_y;      // BWD variant, nullable: staged value = coef0[c]*in + coef1[c]*pro_y + coef2[c] (BatchNorm backward apply)
     const float* pro_coef;   // [3][C]
     BnBwdLazy pro_blazy;     // BWD variant: .partial != null -> the coefficients are reduced here from the producing epilogue's partial rows
@@ -210,8 +212,21 @@ struct ConvTcCfg {
     static_assert(NT % CH == 0 && NE <= 32 && T * N == 64 && ITEMS == 4, "tiling");
 };
 
-template <int C, int W, int BWD>
-__global__ void __launch_bounds__(256) __maxnreg__(BWD ? LC_BWD_MAXNREG : 64) conv3x3_tc_kernel(ConvTcArgs a) {
+// round-to-nearest (ties away, = cvt.rna.tf32.f32 on finite values) with two integer operations: the cvt instruction runs at a fraction of the ALU rate
+// and the staging transform converts every element of the tile
+__device__ __forceinline__ float to_tf32_fast(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
+// 288 threads: warps 0-7 stage / transform / run the epilogue, lane 0 of warp 8 issues every MMA.  The CTA's T tiles are processed as two halves
+// (T >= 2): the copies of both halves are issued up front as two cp.async groups; while the tensor core works on the first half the workers transform
+// the second, and the first half's epilogue overlaps the second half's MMAs.
+// MODE 0: forward (optional BN + ReLU prologue, optional statistics);  1: data gradient with the fused BatchNorm backward (BnBwdFuse);
+// MODE 2: forward whose prologue also finishes the PREVIOUS residual block — staged value = relu(scale*in + shift + pro_res) with `in` the raw conv_b
+//         output of that block and pro_res its input — and writes that block output to pro_out for the rows this CTA owns: `F.relu(residual + bn_b(..))`
+//         (resnet.py:382) never runs as a launch of its own between two stride-1 blocks.
+template <int C, int W, int MODE>
+__global__ void __launch_bounds__(288) __maxnreg__(MODE == 1 ? LC_BWD_MAXNREG : (MODE == 2 ? 80 : 64)) conv3x3_tc_kernel(ConvTcArgs a) {
+    constexpr int BWD = MODE == 1 ? 1 : 0;
+    constexpr bool RES = MODE == 2;
     using K = ConvTcCfg<C, W>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* sA = smem_raw;
@@ -220,22 +235,27 @@ __global__ void __launch_bounds__(256) __maxnreg__(BWD ? LC_BWD_MAXNREG : 64) co
     float* s_part = reinterpret_cast<float*>(smem_raw + K::OFF_PART);
     float* s_red = reinterpret_cast<float*>(smem_raw + K::OFF_RED);
     float* s_aff = reinterpret_cast<float*>(smem_raw + K::OFF_AFF);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + K::OFF_BAR);   // [0] MMA done, [1] weights landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + K::OFF_BAR);   // [0] first half's MMAs done, [1] weights landed, [2] second half's MMAs done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool worker = tid < K::NT;
     const int total = a.B * K::PP;
     const int q0 = (int)blockIdx.x * K::MROWS;
+    constexpr int HALF = K::T >= 2 ? K::T / 2 : 1;                         // tiles in the first half
+    constexpr int ROWS0 = HALF * 128 + 2 * K::HALO;                       // staged rows the first half reads
+    constexpr int I0 = K::T >= 2 ? ((ROWS0 + K::RSTEP - 1) / K::RSTEP < K::NE ? (ROWS0 + K::RSTEP - 1) / K::RSTEP : K::NE) : K::NE;
     LC_TSTAMP(0);
 
     if (tid == 32) {
-        mbar_init(bar, K::T);
+        mbar_init(bar, 1);
         mbar_init(bar + 1, 1);
+        mbar_init(bar + 2, 1);
     }
     if (warp == 0) tmem_alloc(tmem_slot, K::TMEM_COLS);
 
     // ---- row table: the only place that divides.  Row r of the staged tile <-> padded position Q = q0 - HALO + r ----------
-    for (int r = tid; r < K::ROWS; r += K::NT) {
+    for (int r = tid; r < K::ROWS; r += 288) {
         const int Q = q0 - K::HALO + r;
         int src = -1;
         if (Q >= 0 && Q < total) {
@@ -266,22 +286,41 @@ __global__ void __launch_bounds__(256) __maxnreg__(BWD ? LC_BWD_MAXNREG : 64) co
     if (lazy) bn_partial_sums_load(a.pro_lazy.partial, a.pro_lazy.nparts, C, reinterpret_cast<double*>(s_red));
     if (blazy) bn_partial_sums_load(a.pro_blazy.partial, a.pro_blazy.nparts, C, reinterpret_cast<double*>(s_red));
 
-    // ---- stage A: thread -> fixed 16-byte channel chunk j, rows r0, r0+RSTEP, ...  All copies are issued before any wait ---
+    // ---- stage A: worker thread -> fixed 16-byte channel chunk j, rows r0, r0+RSTEP, ...  Source rows first (registers), then every copy of both
+    //      halves is issued before any wait: iterations [0, I0) form cp.async group 0 (all rows the first half's MMAs read), the rest group 1 ---------
     const int j = tid % K::CH, r0 = tid / K::CH;
     const uint32_t sA_col = smem_u32(sA) + (uint32_t)j * K::PLANE;
     const float* in_col = a.in + j * 4;
     uint32_t validmask = 0;
     const bool proy = BWD && a.pro_y != nullptr;
-    float4 yreg[BWD ? K::NE : 1];      // BWD: the second operand of the BatchNorm-backward apply stays in registers
+    const bool pres = RES && a.pro_res != nullptr;
+    float4 yreg[(BWD || RES) ? K::NE : 1];      // BWD / RES: the second operand of the prologue (BatchNorm input / residual) stays in registers
+    if (worker) {
+        int srcs[K::NE];
 #pragma unroll
-    for (int i = 0; i < K::NE; ++i) {
-        const int r = r0 + i * K::RSTEP;
-        if (r < K::ROWS) {
-            const int src = s_rowsrc[r];
-            const bool ok = src >= 0;
-            cp_async16(sA_col + (uint32_t)r * 16, ok ? in_col + (size_t)src * C : a.in, ok ? 16u : 0u);
-            validmask |= (ok ? 1u : 0u) << i;
-            if (BWD) { if (proy && ok) yreg[i] = ldg4(a.pro_y + (size_t)src * C + j * 4); }
+        for (int i = 0; i < K::NE; ++i) {
+            const int r = r0 + i * K::RSTEP;
+            srcs[i] = r < K::ROWS ? s_rowsrc[r] : -2;
+        }
+#pragma unroll
+        for (int i = 0; i < K::NE; ++i) {
+            const int r = r0 + i * K::RSTEP;
+            const int src = srcs[i];
+            if (src != -2) {
+                const bool ok = src >= 0;
+                cp_async16(sA_col + (uint32_t)r * 16, ok ? in_col + (size_t)src * C : a.in, ok ? 16u : 0u);
+                validmask |= (ok ? 1u : 0u) << i;
+            }
+            if (i == I0 - 1) cp_async_commit();
+        }
+        cp_async_commit();
+        if (BWD || RES) {
+            if (proy || pres) {
+                const float* second = BWD ? a.pro_y : a.pro_res;
+#pragma unroll
+                for (int i = 0; i < K::NE; ++i)
+                    if (validmask & (1u << i)) yreg[i] = ldg4(second + (size_t)srcs[i] * C + j * 4);
+            }
         }
     }
     LC_TSTAMP(1);
@@ -299,73 +338,102 @@ __global__ void __launch_bounds__(256) __maxnreg__(BWD ? LC_BWD_MAXNREG : 64) co
             c2 = *reinterpret_cast<const float4*>(s_coef + 2 * C + j * 4);
         } else { sc = ldg4(a.pro_coef + j * 4); sh = ldg4(a.pro_coef + C + j * 4); c2 = ldg4(a.pro_coef + 2 * C + j * 4); }
     }
-    cp_async_wait_all();
-    LC_TSTAMP(2);
-    // each thread transforms the chunks it copied itself: producer BN + ReLU (prologue) and round-to-nearest TF32
+    // each worker transforms the chunks it copied itself: producer BN + ReLU (forward) or the BatchNorm-backward apply (BWD), then TF32 rounding
+    auto transform = [&](int ibeg, int iend) {
 #pragma unroll
-    for (int i = 0; i < K::NE; ++i) {
-        if (validmask & (1u << i)) {
-            float4* p4 = reinterpret_cast<float4*>(sA + (size_t)j * K::PLANE + (size_t)(r0 + i * K::RSTEP) * 16);
-            float4 v = *p4;
-            if (BWD) {
-                if (proy) {       // dy = c0*g + c1*y + c2 (same fma order as bn_bwd_apply_kernel)
-                    v.x = fmaf(sc.x, v.x, fmaf(sh.x, yreg[i].x, c2.x));
-                    v.y = fmaf(sc.y, v.y, fmaf(sh.y, yreg[i].y, c2.y));
-                    v.z = fmaf(sc.z, v.z, fmaf(sh.z, yreg[i].z, c2.z));
-                    v.w = fmaf(sc.w, v.w, fmaf(sh.w, yreg[i].w, c2.w));
+        for (int i = 0; i < K::NE; ++i) {
+            if (i >= ibeg && i < iend && (validmask & (1u << i))) {
+                float4* p4 = reinterpret_cast<float4*>(sA + (size_t)j * K::PLANE + (size_t)(r0 + i * K::RSTEP) * 16);
+                float4 v = *p4;
+                if (BWD) {
+                    if (proy) {       // dy = c0*g + c1*y + c2 (same fma order as bn_bwd_apply_kernel)
+                        v.x = fmaf(sc.x, v.x, fmaf(sh.x, yreg[i].x, c2.x));
+                        v.y = fmaf(sc.y, v.y, fmaf(sh.y, yreg[i].y, c2.y));
+                        v.z = fmaf(sc.z, v.z, fmaf(sh.z, yreg[i].z, c2.z));
+                        v.w = fmaf(sc.w, v.w, fmaf(sh.w, yreg[i].w, c2.w));
+                    }
+                } else if (RES) {
+                    if (pres) {       // the previous block's output: relu(bn_b(y) + residual), same operation order as bn_act_fwd_kernel
+                        v.x = fmaxf(fmaf(v.x, sc.x, sh.x) + yreg[i].x, 0.f);
+                        v.y = fmaxf(fmaf(v.y, sc.y, sh.y) + yreg[i].y, 0.f);
+                        v.z = fmaxf(fmaf(v.z, sc.z, sh.z) + yreg[i].z, 0.f);
+                        v.w = fmaxf(fmaf(v.w, sc.w, sh.w) + yreg[i].w, 0.f);
+                        const int r = r0 + i * K::RSTEP;
+                        if (r >= K::HALO && r < K::HALO + K::MROWS)       // rows this CTA owns (the halo rows belong to its neighbours)
+                            *reinterpret_cast<float4*>(a.pro_out + (size_t)s_rowsrc[r] * C + j * 4) = v;
+                    }
+                } else if (pro) {
+                    v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
+                    v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+                    v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
+                    v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
                 }
-            } else if (pro) {
-                v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
-                v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
-                v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
-                v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+                v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
+                *p4 = v;
             }
-            v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-            *p4 = v;
         }
+    };
+    // MMAs of tiles [t0, t1): fully unrolled so that every descriptor is base + immediate; one commit per half
+    auto issue = [&](int t0, int t1, uint64_t* done, uint32_t tmem_base) {
+        constexpr uint32_t idesc = make_idesc_tf32(K::N);
+        const uint64_t a_hi = make_desc(0, K::PLANE, 128), b_hi = make_desc(0, K::N * 16, 128);
+        const uint32_t bBase = smem_u32(sB) >> 4;
+#pragma unroll
+        for (int t = 0; t < K::T; ++t) {
+            if (t < t0 || t >= t1) continue;
+            const uint32_t aBase = (smem_u32(sA) >> 4) + (uint32_t)(t * 128 + K::HALO);     // 16-byte units: one row each
+            const uint32_t dcol = tmem_base + (uint32_t)(t * K::N);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                for (int kc = 0; kc < C / 8; ++kc) {
+                    const int shift = (tap / 3 - 1) * K::WP + (tap % 3 - 1);
+                    const uint64_t ad = a_hi | (uint64_t)((aBase + (uint32_t)(shift + 2 * kc * (K::PLANE >> 4))) & 0x3FFF);
+                    const uint64_t bd = b_hi | (uint64_t)((bBase + (uint32_t)(tap * (K::BTAP >> 4) + 2 * kc * K::N)) & 0x3FFF);
+                    mma_tf32(dcol, ad, bd, idesc, (tap | kc) != 0 ? 1u : 0u);
+                }
+            }
+        }
+        mma_commit(done);          // implies tcgen05.fence::before_thread_sync
+    };
+
+    if (worker) {
+        if (K::T >= 2) cp_async_wait_group<1>(); else cp_async_wait_all();
     }
+    LC_TSTAMP(2);
+    if (worker) transform(0, I0);
     fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     LC_TSTAMP(3);
-
-    // ---- MMA issue: lane 0 of warp t issues tile t (T issuing threads -> the per-instruction issue latency of a single thread
-    //      overlaps across tiles); fully unrolled so that every descriptor is base + immediate.  All commit to bar[0] (count T).
-    if (warp < K::T && lane == 0) {
-        mbar_wait(bar + 1, 0);     // weights landed (async-proxy write, ordered by the mbarrier)
-        constexpr uint32_t idesc = make_idesc_tf32(K::N);
-        const uint64_t a_hi = make_desc(0, K::PLANE, 128), b_hi = make_desc(0, K::N * 16, 128);
-        const uint32_t aBase = (smem_u32(sA) >> 4) + (uint32_t)(warp * 128 + K::HALO);     // 16-byte units: one row each
-        const uint32_t bBase = smem_u32(sB) >> 4;
-        const uint32_t dcol = tmem_base + (uint32_t)(warp * K::N);
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-#pragma unroll
-            for (int kc = 0; kc < C / 8; ++kc) {
-                constexpr int dummy = 0; (void)dummy;
-                const int shift = (tap / 3 - 1) * K::WP + (tap % 3 - 1);
-                const uint64_t ad = a_hi | (uint64_t)((aBase + (uint32_t)(shift + 2 * kc * (K::PLANE >> 4))) & 0x3FFF);
-                const uint64_t bd = b_hi | (uint64_t)((bBase + (uint32_t)(tap * (K::BTAP >> 4) + 2 * kc * K::N)) & 0x3FFF);
-                mma_tf32(dcol, ad, bd, idesc, (tap | kc) != 0 ? 1u : 0u);
-            }
-        }
-        mma_commit(bar);           // implies tcgen05.fence::before_thread_sync
-        LC_TSTAMP(4);
+    if (tid == K::NT) {             // the issuer: first half (every tile when T == 1)
+        mbar_wait(bar + 1, 0);      // weights landed (async-proxy write, ordered by the mbarrier)
+        issue(0, HALF, bar, tmem_base);
     }
-    const bool done = mbar_wait(bar, 0);
-    fence_after_sync();
-    LC_TSTAMP(5);
-    if (!done && tid == 0 && a.error_flag != nullptr) atomicExch(a.error_flag, 1);
+    if (K::T >= 2) {
+        if (worker) { cp_async_wait_all(); transform(I0, K::NE); }
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+        if (tid == K::NT) issue(HALF, K::T, bar + 2, tmem_base);
+    }
+    LC_TSTAMP(4);
 
-    // ---- epilogue: 4 work items (tile, 16-column block); warp w reads TMEM lanes 32*(w%4).., warp group w/4 takes 2 items ------
+    // ---- epilogue: 4 work items (tile, 16-column block), first-half items first; warp w reads TMEM lanes 32*(w%4).., warp group w/4 takes item it*2+grp
     const bool stats = BWD ? (a.bw.partial != nullptr) : (a.stat.partial != nullptr);
     const int quarter = warp & 3, grp = warp >> 2;
+    bool done = true;
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-        const int item = grp * 2 + it;
+        if (!worker) break;           // the issuer warp owns no TMEM lanes; it only keeps the barriers below company
+        const int item = it * 2 + grp;
         const int t = item / (K::N / 16), c0 = (item % (K::N / 16)) * 16;
+        done = mbar_wait((K::T >= 2 && t >= HALF) ? bar + 2 : bar, 0) && done;
+        fence_after_sync();
+        if (it == 0) LC_TSTAMP(5);
         const int m = quarter * 32 + lane;                                  // accumulator row == TMEM lane
         const int src = s_rowsrc[K::HALO + t * 128 + m];
         const bool valid = src >= 0;
@@ -418,26 +486,27 @@ __global__ void __launch_bounds__(256) __maxnreg__(BWD ? LC_BWD_MAXNREG : 64) co
             s_part[((warp * 2 + it) * 16 + (lane >> 1)) * 2 + (lane & 1)] = (lane & 1) ? r2 : r1;
         }
     }
+    if (!done && tid == 0 && a.error_flag != nullptr) atomicExch(a.error_flag, 1);
     fence_before_sync();
     __syncthreads();
     LC_TSTAMP(6);
     if (warp == 0) tmem_dealloc(tmem_base, K::TMEM_COLS);
 
     if (stats) {
-        // channel c of tile t lives in item (t, c/16): sum the 4 warp quarters of every tile in fixed order
+        // channel c of tile t lives in item (t, c/16) = it * 2 + grp: sum the 4 warp quarters of every tile in fixed order
         if (tid < 2 * K::N) {
             const int stat = tid / K::N, c = tid % K::N;
             float tsum = 0.f;
 #pragma unroll
             for (int t = 0; t < K::T; ++t) {
-                const int item = t * (K::N / 16) + c / 16, g = item >> 1, it = item & 1;
+                const int item = t * (K::N / 16) + c / 16, g = item & 1, it = item >> 1;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) tsum += s_part[(((g * 4 + q) * 2 + it) * 16 + (c & 15)) * 2 + stat];
             }
             (BWD ? a.bw.partial : a.stat.partial)[((size_t)blockIdx.x * 2 + stat) * K::N + c] = tsum;
         }
-        if (BWD ? a.bw.defer : a.stat.defer) return;       // consumers reduce the partial rows themselves (BnLazy)
-        if (last_block_done(BWD ? a.bw.counter : a.stat.counter, gridDim.x)) {
+        if (BWD ? a.bw.defer : a.stat.defer) return;       // consumers reduce the partial rows themselves (BnLazy / BnBwdLazy)
+        if (last_block_done(BWD ? a.bw.counter : a.stat.counter, gridDim.x)) {      // (the 32 issuer-warp threads only add barrier arrivals below)
             if (BWD) bn_bwd_finalize_last_block<K::N>(a.bw.partial, (int)gridDim.x, (double)a.B * W * W, a.bw.scale, a.bw.mean, a.bw.invstd, a.bw.coef,
                                                       a.bw.dgamma, a.bw.dbeta, s_red);
             else bn_finalize_last_block<K::N, K::NT>(a.stat, (int)gridDim.x, (double)a.B * W * W, s_red);
@@ -445,7 +514,7 @@ __global__ void __launch_bounds__(256) __maxnreg__(BWD ? LC_BWD_MAXNREG : 64) co
     }
 }
 
-template <int C, int W, int BWD = 0>
+template <int C, int W, int BWD = 0>      // BWD = the kernel's MODE (0 forward, 1 fused data gradient, 2 forward + previous block's residual output)
 static inline int conv_tc_launch(const ConvTcArgs& a, cudaStream_t st) {
     using K = ConvTcCfg<C, W>;
     static bool attr_done = false;
@@ -456,7 +525,7 @@ static inline int conv_tc_launch(const ConvTcArgs& a, cudaStream_t st) {
     const long long total = (long long)a.B * K::PP;
     const int grid = (int)((total + K::MROWS - 1) / K::MROWS);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(K::NT); cfg.dynamicSmemBytes = K::SMEM_BYTES; cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(K::NT + 32); cfg.dynamicSmemBytes = K::SMEM_BYTES; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;

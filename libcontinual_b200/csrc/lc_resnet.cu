@@ -80,6 +80,13 @@ int launch_conv3x3_tc(int c, int wo, const tc::ConvTcArgs& a, cudaStream_t st) {
     if (c == 64 && wo == 8) return tc::conv_tc_launch<64, 8>(a, st);
     return LC_ERR_INVALID;
 }
+// forward variant whose prologue finishes the previous residual block (conv_tc.cuh MODE 2)
+int launch_conv3x3_tc_res(int c, int wo, const tc::ConvTcArgs& a, cudaStream_t st) {
+    if (c == 16 && wo == 32) return tc::conv_tc_launch<16, 32, 2>(a, st);
+    if (c == 32 && wo == 16) return tc::conv_tc_launch<32, 16, 2>(a, st);
+    if (c == 64 && wo == 8) return tc::conv_tc_launch<64, 8, 2>(a, st);
+    return LC_ERR_INVALID;
+}
 // data-gradient variant with the fused BatchNorm backward (apply in the prologue, mask + reduction in the epilogue)
 int launch_conv3x3_tc_bwd(int c, int wo, const tc::ConvTcArgs& a, cudaStream_t st) {
     if (c == 16 && wo == 32) return tc::conv_tc_launch<16, 32, 1>(a, st);
@@ -202,6 +209,7 @@ struct lc_resnet {
     cudaStream_t sides[kMaxSide] = {};
     int nside = 2;
     int debug_skip = 0;
+    int fuse_block_out = 1;
     int fused = 1;
     cudaStream_t side = nullptr;
     cudaEvent_t ev_dy[2] = {nullptr, nullptr}, ev_w[2] = {nullptr, nullptr}, ev_dy3 = nullptr, ev_w3 = nullptr, ev_join = nullptr;
@@ -534,6 +542,8 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
             if (i > 0) okev = okev && cudaStreamCreateWithFlags(&n->sides[i], cudaStreamNonBlocking) == cudaSuccess;
             okev = okev && cudaEventCreateWithFlags(&n->ev_joinS[i], cudaEventDisableTiming) == cudaSuccess;
         }
+        const char* envb = getenv("LC_RESNET_NO_BLOCK_FUSE");
+        n->fuse_block_out = (envb != nullptr && envb[0] == '1') ? 0 : 1;
         const char* envd = getenv("LC_RESNET_DEBUG_SKIP");
         if (envd != nullptr && (envd[0] == '1' || envd[0] == '2')) n->debug_skip = envd[0] - '0';
         const char* envs = getenv("LC_RESNET_SIDE");
@@ -693,14 +703,39 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
         LC_TRY(launch_bn_act(e, st));
     }
     const float* cur = ws + n->off_a0;
-    for (const BlockL& bl : n->blocks) {
+    // `pending`: the previous block's output relu(bn_b(y_b) + residual) has not been materialised yet — the next tensor-core conv_a evaluates it in its
+    // prologue (and stores it); any other consumer gets it from bn_act_fwd_kernel first
+    const BlockL* pend = nullptr;
+    const float* pend_res = nullptr;
+    const bool fuse_out = n->mode == 1 && n->fuse_block_out;
+    auto flush_pending = [&]() -> int {
+        if (pend == nullptr) return LC_OK;
+        const ConvL& pb = n->convs[pend->conv_b];
+        BnActArgs e{};
+        e.y = ws + pb.y_off; e.scale = ws + pb.aff_off; e.shift = ws + pb.aff_off + pb.cout; e.out = ws + pend->out_off;
+        e.n4 = (long long)batch * pb.wo * pb.wo * pb.cout / 4; e.C = pb.cout; e.lazy = lazy_of(pb); e.res = pend_res;
+        pend = nullptr;
+        return launch_bn_act(e, st);
+    };
+    for (size_t bi = 0; bi < n->blocks.size(); ++bi) {
+        const BlockL& bl = n->blocks[bi];
         const ConvL& ca = n->convs[bl.conv_a];
         const ConvL& cb = n->convs[bl.conv_b];
         if (n->mode == 1 && ca.wtf_off >= 0) {
             tc::ConvTcArgs a{};
-            a.in = cur; a.wtc = packed + ca.wtf_off; a.out = ws + ca.y_off; a.stat = stat_for(ca); a.B = batch; a.error_flag = err_flag;
-            LC_TRY(launch_conv3x3_tc(ca.cin, ca.wo, a, st));
+            a.wtc = packed + ca.wtf_off; a.out = ws + ca.y_off; a.stat = stat_for(ca); a.B = batch; a.error_flag = err_flag;
+            if (pend != nullptr) {
+                const ConvL& pb = n->convs[pend->conv_b];
+                a.in = ws + pb.y_off; a.pro_scale = ws + pb.aff_off; a.pro_shift = ws + pb.aff_off + pb.cout; a.pro_lazy = lazy_of(pb);
+                a.pro_res = pend_res; a.pro_out = ws + pend->out_off;
+                pend = nullptr;
+                LC_TRY(launch_conv3x3_tc_res(ca.cin, ca.wo, a, st));
+            } else {
+                a.in = cur;
+                LC_TRY(launch_conv3x3_tc(ca.cin, ca.wo, a, st));
+            }
         } else {
+            if (pend != nullptr) LC_TRY(flush_pending());
             Conv3x3Args a{};
             a.in = cur; a.wpack = packed + ca.wf_off; a.out = ws + ca.y_off; a.stat = stat_for(ca); a.B = batch;
             LC_TRY(launch_conv3x3(ca.cin, ca.cout, ca.wo, ca.stride, false, false, a, st));
@@ -716,20 +751,28 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
             a.pro_scale = ws + ca.aff_off; a.pro_shift = ws + ca.aff_off + ca.cout;
             LC_TRY(launch_conv3x3(cb.cin, cb.cout, cb.wo, 1, false, false, a, st));
         }
-        BnActArgs e{};
-        e.y = ws + cb.y_off; e.scale = ws + cb.aff_off; e.shift = ws + cb.aff_off + cb.cout; e.out = ws + bl.out_off;
-        e.n4 = (long long)batch * cb.wo * cb.wo * cb.cout / 4; e.C = cb.cout; e.lazy = lazy_of(cb);
-        if (bl.conv_d >= 0) {
-            const ConvL& cd = n->convs[bl.conv_d];
-            Conv1x1Args a{};
-            a.in = cur; a.w = packed + cd.wf_off; a.out = ws + cd.y_off; a.stat = stat_for(cd); a.B = batch;
-            LC_TRY(launch_conv1x1_fwd(cd.cin, cd.cout, cd.wo, a, st));
-            e.res = ws + cd.y_off; e.res_scale = ws + cd.aff_off; e.res_shift = ws + cd.aff_off + cd.cout;
+        const bool last = bi + 1 == n->blocks.size();
+        // the block output can stay pending when the next block's conv_a is a tensor-core conv (same stage, stride 1) and this block has an identity
+        // shortcut and a final ReLU
+        const bool defer_out = fuse_out && bl.conv_d < 0 && !last && n->convs[n->blocks[bi + 1].conv_a].wtf_off >= 0;
+        if (defer_out) {
+            pend = &bl; pend_res = cur;
         } else {
-            e.res = cur;
+            BnActArgs e{};
+            e.y = ws + cb.y_off; e.scale = ws + cb.aff_off; e.shift = ws + cb.aff_off + cb.cout; e.out = ws + bl.out_off;
+            e.n4 = (long long)batch * cb.wo * cb.wo * cb.cout / 4; e.C = cb.cout; e.lazy = lazy_of(cb);
+            if (bl.conv_d >= 0) {
+                const ConvL& cd = n->convs[bl.conv_d];
+                Conv1x1Args a{};
+                a.in = cur; a.w = packed + cd.wf_off; a.out = ws + cd.y_off; a.stat = stat_for(cd); a.B = batch;
+                LC_TRY(launch_conv1x1_fwd(cd.cin, cd.cout, cd.wo, a, st));
+                e.res = ws + cd.y_off; e.res_scale = ws + cd.aff_off; e.res_shift = ws + cd.aff_off + cd.cout;
+            } else {
+                e.res = cur;
+            }
+            e.no_relu = (!n->last_relu && last) ? 1 : 0;
+            LC_TRY(launch_bn_act(e, st));
         }
-        e.no_relu = (!n->last_relu && &bl == &n->blocks.back()) ? 1 : 0;
-        LC_TRY(launch_bn_act(e, st));
         cur = ws + bl.out_off;
     }
     if (lazy && n->n_deferred > 0) {      // scale / shift / mean / invstd of the deferred layers for the backward pass, and their running statistics

@@ -24,6 +24,10 @@
 #include "conv_tc.cuh"
 #include <cuda_bf16.h>
 
+#ifndef LC_WGRAD16_MAXNREG
+#define LC_WGRAD16_MAXNREG 88      // stage-1 weight-gradient CTA (256 x 88) + two data-gradient CTAs (288 x 72) = one SM register file
+#endif
+
 namespace lc {
 namespace tc {
 
@@ -87,7 +91,7 @@ struct WgradTcCfg {
 };
 
 template <int C, int W>
-__global__ void __launch_bounds__(256) wgrad3x3_tc_kernel(WgradTcArgs a) {
+__global__ void __launch_bounds__(256) __maxnreg__(C == 16 ? LC_WGRAD16_MAXNREG : 168) wgrad3x3_tc_kernel(WgradTcArgs a) {
     using K = WgradTcCfg<C, W>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* sX = smem_raw;
