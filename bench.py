@@ -632,8 +632,9 @@ def run_ours_l2p(args, ctx, kind):
         peak, peak_src = 1650.0, "fallback (B200_PROFILING.md)"
     us, flops, kname = time_dominant_gemm(eng, tokens=tokens)
     achieved = flops / (us * 1e-6) / 1e12
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "kernel": kname,
-                "us_per_launch": us, "algorithmic_flops_per_launch": flops, "peak_source": peak_src}
+    traffic, traffic_src = ncu_traffic("gemm_bf16_kernel fc1+GELU T=222") if tokens == 222 else (None, None)
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "kernel": kname, "us_per_launch": us, "algorithmic_flops_per_launch": flops, "peak_source": peak_src}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         if kind not in ("l2p", "inflora"):
