@@ -87,15 +87,19 @@ __device__ __forceinline__ float dgelu_erf(float x) { float c, g; gelu_parts(x, 
 
 enum { EPI_F32 = 1, EPI_RES = 2, EPI_GELU2 = 4, EPI_DGELU = 8 };     // compile-time epilogue variants (keeps each instance's code small)
 
-template <int BN, int EPI = 0>
+// CG = 2: a pair of CTAs (a 2-CTA cluster on one TPC) computes a 256 x BN block with tcgen05.mma.cta_group::2 — each CTA stages its own 128 rows of A
+// and HALF of the B panel (BN / 2 rows), the tensor cores of both SMs read both halves, each CTA keeps its 128 accumulator rows in its own TMEM.
+// Per K block a CTA pulls 32 KB through its L2 port instead of 48 KB for the same math: ncu showed the single-CTA kernel at 51 % tensor pipe with
+// no DRAM / L2 limiter except the per-SM fill rate (profiles/r2k_ncu_gemm_fc1.txt).
+template <int BN, int EPI = 0, int CG = 1>
 struct GemmCfg {
     static constexpr int BM = 128, BK = 64;
-    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / CG) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     // GELU / GELU' epilogues are instruction-issue bound (ncu: 71 M warp instructions vs 9 M for the plain store, 25 per element): with two
     // epilogue warps per scheduler their dependent MUFU / FMA chains leave the issue slots idle, so those variants run four per scheduler
     static constexpr int EPI_WARPS = ((EPI & (EPI_GELU2 | EPI_DGELU)) != 0 && (EPI & EPI_RES) == 0) ? 16 : 8;
-    static constexpr int STAGES = BN == 256 ? 3 : (EPI_WARPS == 16 ? 4 : 5);
+    static constexpr int STAGES = CG == 2 ? (EPI_WARPS == 16 ? 4 : 5) : (BN == 256 ? 3 : (EPI_WARPS == 16 ? 4 : 5));
     static constexpr int NT = 64 + 32 * EPI_WARPS;
     static constexpr int SLAB = 32;                                   // epilogue column slab
     static constexpr int STG_LD = SLAB + 4;                           // staging row stride (floats): conflict-free float4 rows
@@ -103,6 +107,7 @@ struct GemmCfg {
     static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + STG_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
     static constexpr uint32_t TMEM_COLS = 2 * BN;                     // two accumulators: the epilogue of tile i overlaps the MMAs of tile i+1
     static_assert(BN == 128 || BN == 256, "BN");
+    static_assert(CG == 1 || (CG == 2 && BN == 256), "the CTA-pair variant exists for 256-wide panels");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -118,13 +123,57 @@ __device__ __forceinline__ unsigned long long gemm_gtimer() { unsigned long long
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- CTA-pair (cta_group::2) primitives ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // shared::cluster address with the CTA-pair peer bit cleared = the same offset in the leader CTA
+// executed by both CTAs of a pair: the tile lands in THIS CTA's shared memory, the transaction bytes are reported to the LEADER's barrier
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+                 "l"(tmap), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of every MMA issued so far by this thread -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void mma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
 
 // Persistent: grid = min(#tiles, #SMs); CTA c processes tiles c, c + grid, ...  Tile order: n fastest inside an m row-block, so the CTAs that run
 // concurrently share A row-blocks through L2.  A (the token matrix, up to 155 MB) is the operand that does not fit the 126 MB L2, the weights (<= 4.7 MB)
 // always do: with m fastest every n panel streamed A from DRAM again (ncu: 548 MB read for 237 MB algorithmic on fc2, N = 768 -> 3 panels).
-template <int BN, int EPI>
-__global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs a) {
-    using K = GemmCfg<BN, EPI>;
+template <int BN, int EPI, int CG = 1>
+__global__ void __launch_bounds__(GemmCfg<BN, EPI, CG>::NT, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs a) {
+    using K = GemmCfg<BN, EPI, CG>;
+    // CG == 2: blockIdx.x = 2 * pair + rank; a pair walks the 256 x BN blocks, rank r owns rows [128 r, 128 r + 128) of a block and rows
+    // [128 r, ..) of its B panel; only the leader (rank 0) issues MMAs, both ranks load, both drain their own TMEM half
+    const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;
+    const int worker = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, nworkers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    constexpr int MB = K::BM * CG;                  // rows of an output block
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base_u = (smem_u32(smem_dyn) + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char* base = smem_dyn + (base_u - smem_u32(smem_dyn));
@@ -137,7 +186,7 @@ __global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = (a.K + K::BK - 1) / K::BK;
-    const int m_tiles = (a.M + K::BM - 1) / K::BM, n_tiles = (a.N + BN - 1) / BN;
+    const int m_tiles = (a.M + MB - 1) / MB, n_tiles = (a.N + BN - 1) / BN;
     const int per_z = m_tiles * n_tiles;
     const int ksplit = a.ksplit > 1 ? a.ksplit : 1;
     const int kper = (nkb + ksplit - 1) / ksplit;
@@ -145,11 +194,11 @@ __global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(cons
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < K::STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, K::EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, K::EPI_WARPS * CG); }    // CG == 2: both CTAs' epilogue warps
     }
-    if (warp == 1) tmem_alloc(tmem_slot, K::TMEM_COLS);
+    if (warp == 1) { if (CG == 2) tmem_alloc_2sm(tmem_slot, K::TMEM_COLS); else tmem_alloc(tmem_slot, K::TMEM_COLS); }
     fence_before_sync();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();      // (pair) barriers initialised before any remote arrival / multicast commit
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     bool ok = true;
@@ -158,10 +207,10 @@ __global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(cons
         if (lane == 0) {
             uint32_t it = 0;
             int tl = 0; (void)tl;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            for (int tile = worker; tile < total; tile += nworkers) {
                 const int sp = tile % ksplit, tq = tile / ksplit;
                 const int z = tq / per_z, r = tq % per_z;
-                const int n0 = (r % n_tiles) * BN, m0 = (r / n_tiles) * K::BM;
+                const int n0 = (r % n_tiles) * BN, m0 = (r / n_tiles) * MB + (int)crank * K::BM;
                 const int z_in = z % a.batch_in, z_out = z / a.batch_in;
                 const int kb0 = sp * kper, kb1 = kb0 + kper < nkb ? kb0 + kper : nkb;
                 const int cv_n = a.conv_ks > 0 ? m0 / a.conv_hw : 0, cv_h = a.conv_ks > 0 ? (m0 % a.conv_hw) / a.conv_wo * a.conv_stride - a.conv_pad : 0;
@@ -170,8 +219,16 @@ __global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(cons
                     const int s = it % K::STAGES;
                     const uint32_t ph = (it / K::STAGES) & 1u;
                     ok = mbar_wait(empty + s, ph ^ 1u) && ok;
-                    mbar_expect_tx(full + s, (uint32_t)K::STAGE_BYTES);
                     const uint32_t sa = base_u + (uint32_t)s * K::STAGE_BYTES;
+                    if constexpr (CG == 2) {
+                        // both CTAs' bytes are reported to the leader's full[s]; only the leader arrives on it
+                        if (crank == 0) mbar_expect_tx(full + s, (uint32_t)(2 * K::STAGE_BYTES));
+                        tma_load_4d_2sm(sa, &tmA, full + s, kb * K::BK, m0, (a.a_bcast & 1) ? 0 : z_in, (a.a_bcast & 2) ? 0 : z_out);
+                        tma_load_4d_2sm(sa + K::A_BYTES, &tmB, full + s, kb * K::BK, n0 + (int)crank * (BN / 2), (a.b_bcast & 1) ? 0 : z_in,
+                                        (a.b_bcast & 2) ? 0 : z_out);
+                        continue;
+                    }
+                    mbar_expect_tx(full + s, (uint32_t)K::STAGE_BYTES);
                     if (a.conv_ks > 0) {
                         const int tap = kb / a.conv_cchunks, chunk = kb - tap * a.conv_cchunks;
                         const int kh = tap / a.conv_ks, kw = tap - kh * a.conv_ks;
@@ -186,10 +243,10 @@ __global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(cons
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+        if (lane == 0 && crank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128 * CG, BN);
             uint32_t it = 0, t = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
+            for (int tile = worker; tile < total; tile += nworkers, ++t) {
                 const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
                 LC_GSTAMP(t, 2);
                 ok = mbar_wait(tmem_empty + acc, aph ^ 1u) && ok;                   // the epilogue has drained this accumulator
@@ -206,11 +263,13 @@ __global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(cons
                     const uint32_t sa = base_u + (uint32_t)s * K::STAGE_BYTES;
                     const uint64_t ad = make_desc_sw128(sa), bd = make_desc_sw128(sa + K::A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < K::BK / 16; ++k)                           // +32 B (2 x 16-byte units) per K16 step inside the swizzle atom
-                        mma_f16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
-                    mma_commit(empty + s);                                         // frees the stage when these MMAs have read it
+                    for (int k = 0; k < K::BK / 16; ++k) {                         // +32 B (2 x 16-byte units) per K16 step inside the swizzle atom
+                        if constexpr (CG == 2) mma_f16_2sm(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+                        else mma_f16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+                    }
+                    if constexpr (CG == 2) mma_commit_2sm(empty + s); else mma_commit(empty + s);     // frees the stage (in both CTAs) when these MMAs have read it
                 }
-                mma_commit(tmem_full + acc);
+                if constexpr (CG == 2) mma_commit_2sm(tmem_full + acc); else mma_commit(tmem_full + acc);
                 LC_GSTAMP(t, 4);
             }
         }
@@ -221,10 +280,10 @@ __global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(cons
         float* stg = staging + (size_t)(warp - 2) * 32 * K::STG_LD;
         const int rr = lane >> 3, c4 = (lane & 7) * 4;
         uint32_t t = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
+        for (int tile = worker; tile < total; tile += nworkers, ++t) {
             const int sp = tile % ksplit, tq = tile / ksplit;
             const int z = tq / per_z, r = tq % per_z;
-            const int n0 = (r % n_tiles) * BN, m0 = (r / n_tiles) * K::BM;
+            const int n0 = (r % n_tiles) * BN, m0 = (r / n_tiles) * MB + (int)crank * K::BM;
             const int z_in = z % a.batch_in, z_out = z / a.batch_in;
             const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
             if (warp == 2 && lane == 0) LC_GSTAMP(t, 5);
@@ -321,14 +380,14 @@ __global__ void __launch_bounds__(GemmCfg<BN, EPI>::NT, 1) gemm_bf16_kernel(cons
             }
             fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + acc);
+            if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tmem_empty + acc, 0); else mbar_arrive(tmem_empty + acc); }     // the leader's MMA thread waits on it
             if (warp == 2 && lane == 0) LC_GSTAMP(t, 7);
         }
     }
     if (!ok && lane == 0 && a.error_flag != nullptr) atomicExch(a.error_flag, 2);
     fence_before_sync();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, K::TMEM_COLS);
+    if (CG == 2) cluster_sync_all(); else __syncthreads();      // (pair) the peer's shared memory and TMEM stay alive until the last MMA / remote arrival
+    if (warp == 1) { if (CG == 2) tmem_dealloc_2sm(tmem_base, K::TMEM_COLS); else tmem_dealloc(tmem_base, K::TMEM_COLS); }
 }
 
 }  // namespace tc

@@ -68,6 +68,44 @@ int launch_gemm_epi(const CUtensorMap& ta, const CUtensorMap& tb, const tc::Gemm
     return lc_launch_status();
 }
 
+// CTA-pair variant (gemm_tc.cuh CG = 2): 2-CTA clusters, 256 x 256 blocks, tb's box holds 128 rows
+template <int EPI>
+int launch_gemm_epi_cg2(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmArgs& a, int batch, cudaStream_t st) {
+    using K = tc::GemmCfg<256, EPI, 2>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(tc::gemm_bf16_kernel<256, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES) != cudaSuccess) return LC_ERR_CUDA;
+        attr_done = true;
+    }
+    const long long blocks = (long long)((a.N + 255) / 256) * ((a.M + 255) / 256) * batch;
+    const long long pairs = blocks < num_sms() / 2 ? blocks : num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs)); cfg.blockDim = dim3(K::NT); cfg.dynamicSmemBytes = K::SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, tc::gemm_bf16_kernel<256, EPI, 2>, ta, tb, a) != cudaSuccess) return LC_ERR_CUDA;
+    return lc_launch_status();
+}
+int launch_gemm_cg2(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmArgs& a, int batch, cudaStream_t st) {
+    const int epi = (a.out_dtype == tc::GEMM_OUT_F32 ? tc::EPI_F32 : 0) | (a.residual != nullptr ? tc::EPI_RES : 0) | (a.out2 != nullptr ? tc::EPI_GELU2 : 0) |
+                    (a.gelu_aux != nullptr ? tc::EPI_DGELU : 0);
+    switch (epi) {
+#define LC_EPI_CASE(E) case E: return launch_gemm_epi_cg2<E>(ta, tb, a, batch, st);
+        LC_EPI_CASE(0) LC_EPI_CASE(1) LC_EPI_CASE(2) LC_EPI_CASE(3) LC_EPI_CASE(4) LC_EPI_CASE(5) LC_EPI_CASE(6) LC_EPI_CASE(7)
+        LC_EPI_CASE(8) LC_EPI_CASE(9) LC_EPI_CASE(10) LC_EPI_CASE(11) LC_EPI_CASE(12) LC_EPI_CASE(13) LC_EPI_CASE(14) LC_EPI_CASE(15)
+#undef LC_EPI_CASE
+    }
+    return LC_ERR_INVALID;
+}
+// 0: single-CTA kernel only; 1 (default): CTA pairs for the wide, tall GEMMs.  LC_GEMM_CG2=0 switches the pair variant off.
+int gemm_cg2_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LC_GEMM_CG2"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+
 template <int BN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmArgs& a, int batch, cudaStream_t st) {
     const int epi = (a.out_dtype == tc::GEMM_OUT_F32 ? tc::EPI_F32 : 0) | (a.residual != nullptr ? tc::EPI_RES : 0) | (a.out2 != nullptr ? tc::EPI_GELU2 : 0) |
@@ -113,10 +151,13 @@ int lc_gemm_bf16_ex(const lc_gemm_desc* d, int* error_flag, lc_stream_t stream) 
     LC_CHECK_ARG(d->gelu_mode >= 0 && d->gelu_mode <= 3 && ((d->gelu_mode & 2) == 0 || d->out2 != nullptr));
     CUtensorMap ta, tb;
     const int bn = d->N > 128 ? 256 : 128;
+    // CTA pairs when a 256 x 256 block grid still fills the machine: wide panels, at least 74 block pairs' worth of rows
+    const bool cg2 = gemm_cg2_enabled() && bn == 256 && d->ksplit <= 1 &&
+                     (long long)((d->M + 255) / 256) * ((d->N + 255) / 256) * d->batch_in * d->batch_out >= 74;
     tc::GemmArgs a{};
     int e = make_tmap(&ta, d->A, d->K, d->M, d->batch_in, d->batch_out, d->lda, d->strideA_in, d->strideA_out, 128, &a.a_bcast);
     if (e != LC_OK) return e;
-    e = make_tmap(&tb, d->B, d->K, d->N, d->batch_in, d->batch_out, d->ldb, d->strideB_in, d->strideB_out, bn, &a.b_bcast);
+    e = make_tmap(&tb, d->B, d->K, d->N, d->batch_in, d->batch_out, d->ldb, d->strideB_in, d->strideB_out, cg2 ? 128 : bn, &a.b_bcast);
     if (e != LC_OK) return e;
     a.out = d->C; a.bias = d->bias; a.residual = d->residual; a.out2 = d->out2; a.gelu_aux = d->gelu_bwd_aux; a.M = d->M; a.N = d->N; a.K = d->K; a.ldc = (int)d->ldc; a.ldr = (int)d->ldr;
     a.c_stride_in = d->strideC_in; a.c_stride_out = d->strideC_out; a.r_stride_in = d->strideR_in; a.r_stride_out = d->strideR_out;
@@ -127,6 +168,7 @@ int lc_gemm_bf16_ex(const lc_gemm_desc* d, int* error_flag, lc_stream_t stream) 
         a.ksplit = d->ksplit; a.c_stride_split = d->strideC_split;
     }
     const int batch = d->batch_in * d->batch_out;
+    if (cg2) return launch_gemm_cg2(ta, tb, a, batch, (cudaStream_t)stream);
     return bn == 256 ? launch_gemm<256>(ta, tb, a, batch, (cudaStream_t)stream) : launch_gemm<128>(ta, tb, a, batch, (cudaStream_t)stream);
 }
 

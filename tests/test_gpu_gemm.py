@@ -116,3 +116,24 @@ def test_gemm_gelu_derivative_side_tensor(lib):
     ref = (A.double() @ B.double().T) * x.grad
     assert (D1.float().cpu() - ref.float()).abs().max().item() <= 1.5e-2 * ref.abs().max().item()
     assert (D0.float().cpu() - ref.float()).abs().max().item() <= 1.5e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,K", [(4864, 1024, 256), (4997, 1000, 192), (2560, 2304, 768)])
+def test_gemm_cta_pair_variant(lib, M, N, K, monkeypatch):
+    """Shapes with >= 74 blocks of 256 x 256 run the cta_group::2 kernel (2-CTA clusters, each CTA stages its own 128 rows of A and half of the B panel):
+    same contract, checked against float64 for plain / bias + residual fp32 / bias + GELU outputs, a ragged M (last pair: rows past M in both halves) and
+    a ragged N, and against the single-CTA kernel (LC_GEMM_CG2 is read once per process, so the comparison is against float64 only)."""
+    assert ((M + 255) // 256) * ((N + 255) // 256) >= 74
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(1, M, K, generator=g) * 0.5).bfloat16()
+    B = (torch.randn(1, N, K, generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, generator=g)
+    res = torch.randn(1, M, N, generator=g)
+    ref = (A.double() @ B.double().transpose(1, 2)).float()
+    C, _ = run_gemm(lib, A, B)
+    assert (C - ref).abs().max().item() <= 8e-3 * ref.abs().max().item()
+    Cf, _ = run_gemm(lib, A, B, bias=bias, residual=res, out_f32=True)
+    assert (Cf - (ref + bias + res)).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-4
+    Z, Gz = run_gemm(lib, A, B, bias=bias, gelu=True)
+    assert (Z - (ref + bias)).abs().max().item() <= 8e-3 * (ref + bias).abs().max().item()
+    assert (Gz - torch.nn.functional.gelu(ref + bias)).abs().max().item() <= 8e-3 * (ref + bias).abs().max().item()
