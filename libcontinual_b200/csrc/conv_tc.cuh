@@ -207,9 +207,11 @@ struct ConvTcCfg {
     static constexpr int OFF_BAR = OFF_COEF + 3 * N * 4;
     static constexpr size_t SMEM_BYTES = OFF_BAR + 64;
     static constexpr uint32_t TMEM_COLS = 64;
-    static constexpr int ITEMS = T * (N / 16);     // (tile, 16-column block) epilogue work items: always 4
+    static constexpr int CB = C == 16 ? 16 : 32;   // columns per epilogue work item (64 B / 128 B of an output row)
+    static constexpr int ITEMS = T * (N / CB);     // (tile, CB-column block) epilogue work items: 4 (C = 16) or 2
+    static constexpr int NIT = ITEMS / 2;          // items per warp: the two warp groups (warps 0-3 / 4-7) alternate
     static_assert(C % 8 == 0 && (C == 16 || C == 32 || C == 64), "tensor-core conv: C in {16,32,64}");
-    static_assert(NT % CH == 0 && NE <= 32 && T * N == 64 && ITEMS == 4, "tiling");
+    static_assert(NT % CH == 0 && NE <= 32 && T * N == 64 && NIT * 2 == ITEMS && NIT * CB == 32 && PLANE >= 2048, "tiling");
 };
 
 // round-to-nearest (ties away, = cvt.rna.tf32.f32 on finite values) with two integer operations: the cvt instruction runs at a fraction of the ALU rate
@@ -422,69 +424,95 @@ __global__ void __launch_bounds__(288) __maxnreg__(MODE == 1 ? LC_BWD_MAXNREG : 
     }
     LC_TSTAMP(4);
 
-    // ---- epilogue: 4 work items (tile, 16-column block), first-half items first; warp w reads TMEM lanes 32*(w%4).., warp group w/4 takes item it*2+grp
+    // ---- epilogue: work items = (tile, CB-column block), first-half items first; warp w reads TMEM lanes 32*(w%4).., warp group w/4 takes item it*2+grp.
+    // An accumulator row (one output pixel) arrives in ONE thread, but a warp storing 32 x 16 B at a pixel stride touches 16-32 cache lines per
+    // instruction — and the data gradient reads up to three more tensors the same way.  So the rows go through a warp-private staging buffer (dead
+    // rows of the A tile, XOR-swizzled 64-byte rows) and every global access of the epilogue runs lane-linear instead: the valid rows of a warp are
+    // CONSECUTIVE pixels in memory (borders hold no pixel), i.e. one contiguous block, read / written 512 B per instruction.  In that layout a lane
+    // keeps one 4-channel group (c = lane % CPR) of rows p = k*(32/CPR) + lane/CPR, so the BatchNorm sums are 4 running sums + log2(32/CPR) shuffles.
     const bool stats = BWD ? (a.bw.partial != nullptr) : (a.stat.partial != nullptr);
     const int quarter = warp & 3, grp = warp >> 2;
+    constexpr int CB = K::CB, CPR = CB / 4, NIT = K::NIT;
+    auto stage = [&](int p, int c) -> float4* {      // 2 KB pieces (plane, 128-row block) the MMAs of the other half never read
+        const int plane = C == 16 ? quarter : (C == 32 ? 2 * quarter + (c >> 2) : 2 * warp + (c >> 2));
+        const int beta = C == 64 ? 0 : grp;
+        return reinterpret_cast<float4*>(sA + (size_t)plane * K::PLANE + beta * 2048 + p * 64 + (((c & 3) ^ ((p >> 1) & 3)) << 4));
+    };
     bool done = true;
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < NIT; ++it) {
         if (!worker) break;           // the issuer warp owns no TMEM lanes; it only keeps the barriers below company
         const int item = it * 2 + grp;
-        const int t = item / (K::N / 16), c0 = (item % (K::N / 16)) * 16;
+        const int t = item / (K::N / CB), c0 = (item % (K::N / CB)) * CB;
+        const int src = s_rowsrc[K::HALO + t * 128 + quarter * 32 + lane];    // accumulator row == TMEM lane
+        const unsigned vmask = __ballot_sync(0xffffffffu, src >= 0);
+        const int nvalid = __popc(vmask), rank = __popc(vmask & ((1u << lane) - 1u));
+        const int src_first = __shfl_sync(0xffffffffu, src, vmask ? __ffs(vmask) - 1 : 0);
         done = mbar_wait((K::T >= 2 && t >= HALF) ? bar + 2 : bar, 0) && done;
         fence_after_sync();
         if (it == 0) LC_TSTAMP(5);
-        const int m = quarter * 32 + lane;                                  // accumulator row == TMEM lane
-        const int src = s_rowsrc[K::HALO + t * 128 + m];
-        const bool valid = src >= 0;
-        float v[16];
-        float yv[BWD ? 16 : 1];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * K::N + c0), v);
-        if (valid) {
-            const size_t obase = (size_t)src * K::N + c0;
-            if (a.addend != nullptr) {
+        {
+            float v[CB];
+            if (CB == 16) tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * K::N + c0), v);
+            else tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * K::N + c0), v);
+            if (src >= 0) {
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const float4 x4 = *reinterpret_cast<const float4*>(a.addend + obase + k4 * 4);
-                    v[k4 * 4] += x4.x; v[k4 * 4 + 1] += x4.y; v[k4 * 4 + 2] += x4.z; v[k4 * 4 + 3] += x4.w;
-                }
+                for (int c = 0; c < CPR; ++c) *stage(rank, c) = make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
             }
-            if (BWD && a.bw.y != nullptr) {
+        }
+        __syncwarp();
+        const int c = lane % CPR, cc = c0 + c * 4;
+        float4 asc = make_float4(0.f, 0.f, 0.f, 0.f), ash = asc, amean = asc, aistd = asc;
+        const bool by = BWD && a.bw.y != nullptr;
+        if (by) {
+            asc = *reinterpret_cast<const float4*>(s_aff + cc); ash = *reinterpret_cast<const float4*>(s_aff + K::N + cc);
+            amean = *reinterpret_cast<const float4*>(s_aff + 2 * K::N + cc); aistd = *reinterpret_cast<const float4*>(s_aff + 3 * K::N + cc);
+        }
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const float4 y4 = ldg4(a.bw.y + obase + k4 * 4);
-                    yv[k4 * 4] = y4.x; yv[k4 * 4 + 1] = y4.y; yv[k4 * 4 + 2] = y4.z; yv[k4 * 4 + 3] = y4.w;
+        for (int k = 0; k < CPR; ++k) {
+            const int p = k * (32 / CPR) + lane / CPR;
+            if (p < nvalid) {
+                float4 x = *stage(p, c);
+                const size_t g = (size_t)(src_first + p) * K::N + cc;
+                float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a.addend != nullptr) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(a.addend + g);
+                    x.x += a4.x; x.y += a4.y; x.z += a4.z; x.w += a4.w;
                 }
-                if (a.bw.mask_out != nullptr) {
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        const float4 o4 = ldg4(a.bw.mask_out + obase + k4 * 4);
-                        v[k4 * 4] = o4.x > 0.f ? v[k4 * 4] : 0.f; v[k4 * 4 + 1] = o4.y > 0.f ? v[k4 * 4 + 1] : 0.f;
-                        v[k4 * 4 + 2] = o4.z > 0.f ? v[k4 * 4 + 2] : 0.f; v[k4 * 4 + 3] = o4.w > 0.f ? v[k4 * 4 + 3] : 0.f;
+                if (by) {
+                    y4 = ldg4(a.bw.y + g);
+                    if (a.bw.mask_out != nullptr) {
+                        const float4 o4 = ldg4(a.bw.mask_out + g);
+                        x.x = o4.x > 0.f ? x.x : 0.f; x.y = o4.y > 0.f ? x.y : 0.f; x.z = o4.z > 0.f ? x.z : 0.f; x.w = o4.w > 0.f ? x.w : 0.f;
+                    } else if (a.bw.scale != nullptr) {
+                        x.x = fmaf(y4.x, asc.x, ash.x) > 0.f ? x.x : 0.f; x.y = fmaf(y4.y, asc.y, ash.y) > 0.f ? x.y : 0.f;
+                        x.z = fmaf(y4.z, asc.z, ash.z) > 0.f ? x.z : 0.f; x.w = fmaf(y4.w, asc.w, ash.w) > 0.f ? x.w : 0.f;
                     }
-                } else if (a.bw.scale != nullptr) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = fmaf(yv[i], s_aff[c0 + i], s_aff[K::N + c0 + i]) > 0.f ? v[i] : 0.f;
+                }
+                *reinterpret_cast<float4*>(a.out + g) = x;
+                if (stats) {      // forward: sum, sum of squares;  BWD: sum g, sum g * xhat
+                    float4 m2 = x;
+                    if (BWD) m2 = make_float4((y4.x - amean.x) * aistd.x, (y4.y - amean.y) * aistd.y, (y4.z - amean.z) * aistd.z, (y4.w - amean.w) * aistd.w);
+                    s1.x += x.x; s1.y += x.y; s1.z += x.z; s1.w += x.w;
+                    s2.x = fmaf(x.x, m2.x, s2.x); s2.y = fmaf(x.y, m2.y, s2.y); s2.z = fmaf(x.z, m2.z, s2.z); s2.w = fmaf(x.w, m2.w, s2.w);
                 }
             }
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-                *reinterpret_cast<float4*>(a.out + obase + k4 * 4) = make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
         }
-        if (stats) {
-            // per-warp column sums over its 32 rows: halving butterfly (16 shuffles per statistic), lanes 2k / 2k+1 publish column k's two sums
-            // in place (v is stored already): v <- x, x2 <- x * x (forward: sum, sum of squares) or x * xhat (BWD: sum g, sum g * xhat)
-            float x2[16];
+        if (stats) {      // lanes sharing a channel group differ in the bits above log2(CPR): fixed-order butterfly
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float x = valid ? v[i] : 0.f;
-                float m2 = x;
-                if (BWD) m2 = valid ? (yv[i] - s_aff[2 * K::N + c0 + i]) * s_aff[3 * K::N + c0 + i] : 0.f;
-                v[i] = x; x2[i] = x * m2;
+            for (int off = CPR; off < 32; off <<= 1) {
+                s1.x += __shfl_xor_sync(0xffffffffu, s1.x, off); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, off);
+                s1.z += __shfl_xor_sync(0xffffffffu, s1.z, off); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, off);
+                s2.x += __shfl_xor_sync(0xffffffffu, s2.x, off); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, off);
+                s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
             }
-            const float r1 = warp_colsum16(v), r2 = warp_colsum16(x2);
-            s_part[((warp * 2 + it) * 16 + (lane >> 1)) * 2 + (lane & 1)] = (lane & 1) ? r2 : r1;
+            if (lane < CPR) {
+                float* sp = s_part + (size_t)((warp * NIT + it) * 2) * CB + c * 4;
+                *reinterpret_cast<float4*>(sp) = s1; *reinterpret_cast<float4*>(sp + CB) = s2;
+            }
         }
+        __syncwarp();      // the next item's rows overwrite this warp's staging piece
     }
     if (!done && tid == 0 && a.error_flag != nullptr) atomicExch(a.error_flag, 1);
     fence_before_sync();
@@ -493,15 +521,15 @@ __global__ void __launch_bounds__(288) __maxnreg__(MODE == 1 ? LC_BWD_MAXNREG : 
     if (warp == 0) tmem_dealloc(tmem_base, K::TMEM_COLS);
 
     if (stats) {
-        // channel c of tile t lives in item (t, c/16) = it * 2 + grp: sum the 4 warp quarters of every tile in fixed order
+        // channel c of tile t lives in item (t, c/CB) = it * 2 + grp: sum the 4 warp quarters of every tile in fixed order
         if (tid < 2 * K::N) {
             const int stat = tid / K::N, c = tid % K::N;
             float tsum = 0.f;
 #pragma unroll
             for (int t = 0; t < K::T; ++t) {
-                const int item = t * (K::N / 16) + c / 16, g = item & 1, it = item >> 1;
+                const int item = t * (K::N / CB) + c / CB, g = item & 1, it = item >> 1;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) tsum += s_part[(((g * 4 + q) * 2 + it) * 16 + (c & 15)) * 2 + stat];
+                for (int q = 0; q < 4; ++q) tsum += s_part[(size_t)((((g * 4 + q) * NIT + it) * 2) + stat) * CB + (c % CB)];
             }
             (BWD ? a.bw.partial : a.stat.partial)[((size_t)blockIdx.x * 2 + stat) * K::N + c] = tsum;
         }

@@ -81,7 +81,7 @@ struct WgradTcCfg {
     static constexpr int ROWTAB_BYTES = ((ROWS_X * 4 + 15) / 16) * 16;
     static constexpr int OFF_BAR = OFF_ROWTAB + ROWTAB_BYTES;
     static constexpr int OFF_RED = OFF_BAR + 64;                 // 1024 doubles (bn_partial_sums) + c0, c1, c2
-    static constexpr size_t SMEM_BYTES = OFF_RED + 8192 + 3 * C * 4;
+    static constexpr size_t SMEM_BYTES = OFF_RED + 8192 + 5 * C * 4;
     static constexpr int NACC = C == 64 ? 6 : 3;
     static constexpr uint32_t TMEM_COLS = C == 16 ? 64 : (C == 32 ? 128 : 512);
     static constexpr int RSTEP = NT / CH8;
@@ -96,9 +96,10 @@ __global__ void __launch_bounds__(256) __maxnreg__(C == 16 ? LC_WGRAD16_MAXNREG 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* sX = smem_raw;
     unsigned char* sY = smem_raw + K::OFF_Y;
-    int* s_rowsrc = reinterpret_cast<int*>(smem_raw + K::OFF_ROWTAB);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + K::OFF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    float* s_coef = reinterpret_cast<float*>(smem_raw + K::OFF_RED + 8192);      // c0, c1, c2 of the fused BatchNorm-backward apply
+    float* s_pro = s_coef + 3 * C;                                              // scale, shift of the producer BatchNorm (input prologue)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int total = a.B * K::PP;
@@ -110,93 +111,64 @@ __global__ void __launch_bounds__(256) __maxnreg__(C == 16 ? LC_WGRAD16_MAXNREG 
     if (dylazy) bn_partial_sums_load(a.dy_blazy.partial, a.dy_blazy.nparts, C, reinterpret_cast<double*>(smem_raw + K::OFF_RED));
     if (tid == 32) mbar_init(bar, 1);
     if (warp == 0) tmem_alloc(tmem_slot, K::TMEM_COLS);
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
 
     const int j = tid % K::CH8, r0 = tid / K::CH8;               // this thread's 8-channel chunk column and first row
-    float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
     const bool pro = a.pro_scale != nullptr;
-    if (pro) {
-        sc0 = ldg4(a.pro_scale + j * 8); sc1 = ldg4(a.pro_scale + j * 8 + 4);
-        sh0 = ldg4(a.pro_shift + j * 8); sh1 = ldg4(a.pro_shift + j * 8 + 4);
-    }
-    float4 k0a = sc0, k0b = sc0, k1a = sh0, k1b = sh0, k2a = sh0, k2b = sh0;
-    if (dylazy) {
-        float* s_coef = reinterpret_cast<float*>(smem_raw + K::OFF_RED + 8192);
-        bn_bwd_lazy_coef_finish(a.dy_blazy, C, reinterpret_cast<double*>(smem_raw + K::OFF_RED), s_coef);
-        k0a = *reinterpret_cast<const float4*>(s_coef + j * 8); k0b = *reinterpret_cast<const float4*>(s_coef + j * 8 + 4);
-        k1a = *reinterpret_cast<const float4*>(s_coef + C + j * 8); k1b = *reinterpret_cast<const float4*>(s_coef + C + j * 8 + 4);
-        k2a = *reinterpret_cast<const float4*>(s_coef + 2 * C + j * 8); k2b = *reinterpret_cast<const float4*>(s_coef + 2 * C + j * 8 + 4);
-    } else if (dyaff) {
-        k0a = ldg4(a.dy_coef + j * 8); k0b = ldg4(a.dy_coef + j * 8 + 4);
-        k1a = ldg4(a.dy_coef + C + j * 8); k1b = ldg4(a.dy_coef + C + j * 8 + 4);
-        k2a = ldg4(a.dy_coef + 2 * C + j * 8); k2b = ldg4(a.dy_coef + 2 * C + j * 8 + 4);
-    }
-    const uint32_t sX_u = smem_u32(sX), sY_u = smem_u32(sY);
-
-    uint32_t phase = 0, first = 1;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // flattened padded position -> source pixel index (-1: border / outside the batch); PP and WP are compile-time, so the divisions are multiplies
+    auto src_of = [&](int Q) -> int {
+        if (Q < 0 || Q >= total) return -1;
+        const int n = Q / K::PP, rem = Q - n * K::PP;
+        const int hp = rem / K::WP, wp = rem - hp * K::WP;
+        return (hp >= 1 && hp <= W && wp >= 1 && wp <= W) ? (n * W + (hp - 1)) * W + (wp - 1) : -1;
+    };
+    // ---- software pipeline: the global loads of tile k+1 (raw fp32, registers) are issued right after tile k's MMAs and land while the tensor core
+    //      works; affine transforms + BF16 conversion happen when the registers are stored to shared memory -------------------------------------
+    float4 xa[K::NEX], xb[K::NEX], ya[K::NEY], yb[K::NEY], ua[K::NEY], ub[K::NEY];
+    uint32_t xvalid = 0, yvalid = 0;
+    auto load_tile = [&](int tile) {
         const int q0 = tile * 128;
-        // row table for the input rows [q0-HALO, q0+128+HALO)
-        for (int r = tid; r < K::ROWS_X; r += K::NT) {
-            const int Q = q0 - K::HALO + r;
-            int src = -1;
-            if (Q >= 0 && Q < total) {
-                const int n = Q / K::PP, rem = Q - n * K::PP;
-                const int hp = rem / K::WP, wp = rem - hp * K::WP;
-                if (hp >= 1 && hp <= W && wp >= 1 && wp <= W) src = (n * W + (hp - 1)) * W + (wp - 1);
-            }
-            s_rowsrc[r] = src;
-        }
-        __syncthreads();     // also: every thread is past the previous tile's MMA-completion wait, so smem may be overwritten
-
-        // ---- stage (all global loads first, then convert + store): 8 channels of one row per item ----------------------------
-        float4 xa[K::NEX], xb[K::NEX], ya[K::NEY], yb[K::NEY];
+        xvalid = 0; yvalid = 0;
 #pragma unroll
         for (int i = 0; i < K::NEX; ++i) {
             const int r = r0 + i * K::RSTEP;
-            xa[i] = make_float4(0.f, 0.f, 0.f, 0.f); xb[i] = xa[i];
-            if (r < K::ROWS_X) {
-                const int src = s_rowsrc[r];
-                if (src >= 0) {
-                    const float* g = a.in + (size_t)src * C + j * 8;
-                    xa[i] = ldg4(g); xb[i] = ldg4(g + 4);
-                    if (pro) {
-                        xa[i].x = fmaxf(fmaf(xa[i].x, sc0.x, sh0.x), 0.f); xa[i].y = fmaxf(fmaf(xa[i].y, sc0.y, sh0.y), 0.f);
-                        xa[i].z = fmaxf(fmaf(xa[i].z, sc0.z, sh0.z), 0.f); xa[i].w = fmaxf(fmaf(xa[i].w, sc0.w, sh0.w), 0.f);
-                        xb[i].x = fmaxf(fmaf(xb[i].x, sc1.x, sh1.x), 0.f); xb[i].y = fmaxf(fmaf(xb[i].y, sc1.y, sh1.y), 0.f);
-                        xb[i].z = fmaxf(fmaf(xb[i].z, sc1.z, sh1.z), 0.f); xb[i].w = fmaxf(fmaf(xb[i].w, sc1.w, sh1.w), 0.f);
-                    }
-                }
+            const int src = r < K::ROWS_X ? src_of(q0 - K::HALO + r) : -1;
+            if (src >= 0) {
+                const float* g = a.in + (size_t)src * C + j * 8;
+                xa[i] = ldg4(g); xb[i] = ldg4(g + 4);
+                xvalid |= 1u << i;
             }
         }
 #pragma unroll
         for (int i = 0; i < K::NEY; ++i) {
             const int m = r0 + i * K::RSTEP;
-            ya[i] = make_float4(0.f, 0.f, 0.f, 0.f); yb[i] = ya[i];
-            if (m < 128) {
-                const int src = s_rowsrc[K::HALO + m];
-                if (src >= 0) {
-                    const float* g = a.dy + (size_t)src * C + j * 8;
-                    ya[i] = ldg4(g); yb[i] = ldg4(g + 4);
-                    if (dyaff) {
-                        const float* yy = a.dy_y + (size_t)src * C + j * 8;
-                        const float4 ua = ldg4(yy), ub = ldg4(yy + 4);
-                        ya[i].x = fmaf(k0a.x, ya[i].x, fmaf(k1a.x, ua.x, k2a.x)); ya[i].y = fmaf(k0a.y, ya[i].y, fmaf(k1a.y, ua.y, k2a.y));
-                        ya[i].z = fmaf(k0a.z, ya[i].z, fmaf(k1a.z, ua.z, k2a.z)); ya[i].w = fmaf(k0a.w, ya[i].w, fmaf(k1a.w, ua.w, k2a.w));
-                        yb[i].x = fmaf(k0b.x, yb[i].x, fmaf(k1b.x, ub.x, k2b.x)); yb[i].y = fmaf(k0b.y, yb[i].y, fmaf(k1b.y, ub.y, k2b.y));
-                        yb[i].z = fmaf(k0b.z, yb[i].z, fmaf(k1b.z, ub.z, k2b.z)); yb[i].w = fmaf(k0b.w, yb[i].w, fmaf(k1b.w, ub.w, k2b.w));
-                    }
-                }
+            const int src = m < 128 ? src_of(q0 + m) : -1;
+            if (src >= 0) {
+                const float* g = a.dy + (size_t)src * C + j * 8;
+                ya[i] = ldg4(g); yb[i] = ldg4(g + 4);
+                if (dyaff) { const float* yy = a.dy_y + (size_t)src * C + j * 8; ua[i] = ldg4(yy); ub[i] = ldg4(yy + 4); }
+                yvalid |= 1u << i;
             }
         }
+    };
+    auto store_tile = [&]() {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < K::NEX; ++i) {
             const int r = r0 + i * K::RSTEP;
             if (r < K::ROWS_X) {
-                const uint4 v = make_uint4(pack_bf16(xa[i].x, xa[i].y), pack_bf16(xa[i].z, xa[i].w), pack_bf16(xb[i].x, xb[i].y), pack_bf16(xb[i].z, xb[i].w));
+                float4 p = z4, q = z4;
+                if (xvalid & (1u << i)) {
+                    p = xa[i]; q = xb[i];
+                    if (pro) {
+                        const float4 sc0 = *reinterpret_cast<const float4*>(s_pro + j * 8), sc1 = *reinterpret_cast<const float4*>(s_pro + j * 8 + 4);
+                        const float4 sh0 = *reinterpret_cast<const float4*>(s_pro + C + j * 8), sh1 = *reinterpret_cast<const float4*>(s_pro + C + j * 8 + 4);
+                        p.x = fmaxf(fmaf(p.x, sc0.x, sh0.x), 0.f); p.y = fmaxf(fmaf(p.y, sc0.y, sh0.y), 0.f);
+                        p.z = fmaxf(fmaf(p.z, sc0.z, sh0.z), 0.f); p.w = fmaxf(fmaf(p.w, sc0.w, sh0.w), 0.f);
+                        q.x = fmaxf(fmaf(q.x, sc1.x, sh1.x), 0.f); q.y = fmaxf(fmaf(q.y, sc1.y, sh1.y), 0.f);
+                        q.z = fmaxf(fmaf(q.z, sc1.z, sh1.z), 0.f); q.w = fmaxf(fmaf(q.w, sc1.w, sh1.w), 0.f);
+                    }
+                }
+                const uint4 v = make_uint4(pack_bf16(p.x, p.y), pack_bf16(p.z, p.w), pack_bf16(q.x, q.y), pack_bf16(q.z, q.w));
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {      // copy c holds tile row r at copy row r-(c-1)
                     const int rr = r - (c - 1);
@@ -207,10 +179,41 @@ __global__ void __launch_bounds__(256) __maxnreg__(C == 16 ? LC_WGRAD16_MAXNREG 
 #pragma unroll
         for (int i = 0; i < K::NEY; ++i) {
             const int m = r0 + i * K::RSTEP;
-            if (m < 128)
+            if (m < 128) {
+                float4 p = z4, q = z4;
+                if (yvalid & (1u << i)) {
+                    p = ya[i]; q = yb[i];
+                    if (dyaff) {      // dY = c0*g + c1*y + c2 (same fma order as bn_bwd_apply_kernel)
+                        const float4 k0a = *reinterpret_cast<const float4*>(s_coef + j * 8), k0b = *reinterpret_cast<const float4*>(s_coef + j * 8 + 4);
+                        const float4 k1a = *reinterpret_cast<const float4*>(s_coef + C + j * 8), k1b = *reinterpret_cast<const float4*>(s_coef + C + j * 8 + 4);
+                        const float4 k2a = *reinterpret_cast<const float4*>(s_coef + 2 * C + j * 8), k2b = *reinterpret_cast<const float4*>(s_coef + 2 * C + j * 8 + 4);
+                        p.x = fmaf(k0a.x, p.x, fmaf(k1a.x, ua[i].x, k2a.x)); p.y = fmaf(k0a.y, p.y, fmaf(k1a.y, ua[i].y, k2a.y));
+                        p.z = fmaf(k0a.z, p.z, fmaf(k1a.z, ua[i].z, k2a.z)); p.w = fmaf(k0a.w, p.w, fmaf(k1a.w, ua[i].w, k2a.w));
+                        q.x = fmaf(k0b.x, q.x, fmaf(k1b.x, ub[i].x, k2b.x)); q.y = fmaf(k0b.y, q.y, fmaf(k1b.y, ub[i].y, k2b.y));
+                        q.z = fmaf(k0b.z, q.z, fmaf(k1b.z, ub[i].z, k2b.z)); q.w = fmaf(k0b.w, q.w, fmaf(k1b.w, ub[i].w, k2b.w));
+                    }
+                }
                 *reinterpret_cast<uint4*>(sY + (size_t)(j * K::PLANE_Y + m * 16)) =
-                    make_uint4(pack_bf16(ya[i].x, ya[i].y), pack_bf16(ya[i].z, ya[i].w), pack_bf16(yb[i].x, yb[i].y), pack_bf16(yb[i].z, yb[i].w));
+                    make_uint4(pack_bf16(p.x, p.y), pack_bf16(p.z, p.w), pack_bf16(q.x, q.y), pack_bf16(q.z, q.w));
+            }
         }
+    };
+
+    int tile = blockIdx.x;
+    if (tile < ntiles) load_tile(tile);          // in flight across the coefficient reduction below
+
+    if (pro && tid < 2 * C) s_pro[tid] = tid < C ? a.pro_scale[tid] : a.pro_shift[tid - C];
+    if (dylazy) bn_bwd_lazy_coef_finish(a.dy_blazy, C, reinterpret_cast<double*>(smem_raw + K::OFF_RED), s_coef);
+    else if (dyaff && tid < 3 * C) s_coef[tid] = a.dy_coef[tid];
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t sX_u = smem_u32(sX), sY_u = smem_u32(sY);
+
+    uint32_t phase = 0, first = 1;
+    for (; tile < ntiles; tile += gridDim.x) {
+        store_tile();
         fence_proxy_async();
         fence_before_sync();
         __syncthreads();
@@ -243,7 +246,8 @@ __global__ void __launch_bounds__(256) __maxnreg__(C == 16 ? LC_WGRAD16_MAXNREG 
             mma_commit(bar);
         }
         first = 0;
-        const bool done = mbar_wait(bar, phase);
+        if (tile + (int)gridDim.x < ntiles) load_tile(tile + (int)gridDim.x);      // next tile's loads fly while the tensor core reads this one
+        const bool done = mbar_wait(bar, phase);      // MMAs complete: shared memory may be overwritten
         phase ^= 1;
         fence_after_sync();
         if (!done && tid == 0 && a.error_flag != nullptr) atomicExch(a.error_flag, 1);

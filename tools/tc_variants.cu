@@ -1,6 +1,6 @@
 // Debug harness: CUDA-event time per launch of the tensor-core conv in each prologue / epilogue configuration, 200 back-to-back launches
 // (programmatic dependent launch, as in the step) rotating over NBUF buffer sets.  Build: see tools/build_variants.sh.
-#include "../libcontinual_b200/csrc/conv_tc.cuh"
+#include "conv_tc.cuh"
 #include <cstdio>
 #include <vector>
 using namespace lc;
