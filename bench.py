@@ -422,7 +422,9 @@ def time_dominant_kernel(eng, precision, reps=48):
         wpack = scratch.data_ptr() + 4 * (96 + 2 * 9 * C * C)
         err = scratch.data_ptr() + 4 * 8
         launch = lambda i: check(lib.lc_conv3x3_tc_packed(xs[i].data_ptr(), wpack, ys[i].data_ptr(), B, C, W, None, None, err, st))
-        name = "conv3x3_tc_kernel<16,32> (stage-1 3x3 conv fwd/dgrad, tcgen05 kind::tf32, TMEM accumulators)"
+        name = ("conv3x3_tcp_kernel<16,32> (stage-1 3x3 conv forward: persistent, warp-specialised — TMA bulk loads -> transform -> tcgen05 kind::tf32 -> "
+                "TMEM -> coalesced stores)" if os.environ.get("LC_CONV_PERSIST", "1") != "0" else
+                "conv3x3_tc_kernel<16,32> (stage-1 3x3 conv fwd/dgrad, tcgen05 kind::tf32, TMEM accumulators)")
     else:
         scratch = torch.zeros(int(lib.lc_conv_scratch_floats(B, C, C, W)), device=eng.device)
         check(lib.lc_conv3x3(xs[0].data_ptr(), w.data_ptr(), ys[0].data_ptr(), B, C, C, W, 1, 0, 0, None, None, None, None, None, None, None, scratch.data_ptr(), st))
@@ -966,7 +968,8 @@ def run_ours(args, ctx, workload):
     else:
         us, algo, kname = time_dominant_kernel(eng, args.precision)
         achieved = algo / (us * 1e-6) / 1e9
-        traffic, traffic_src = ncu_traffic("conv3x3_tc_kernel<16,32>" if args.precision == "tc" else "conv3x3_kernel<16,16,32>")
+        traffic, traffic_src = ncu_traffic(("conv3x3_tcp_kernel<16,32>" if os.environ.get("LC_CONV_PERSIST", "1") != "0" else "conv3x3_tc_kernel<16,32>")
+                                           if args.precision == "tc" else "conv3x3_kernel<16,16,32>")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "kernel": kname, "us_per_launch": us,
                     "algorithmic_bytes_per_launch": algo, "peak_source": peak_src,

@@ -149,12 +149,19 @@ __device__ __forceinline__ void bn_bwd_lazy_coef(const BnBwdLazy& z, int C, doub
 }
 
 // End-of-forward finalisation of every deferred layer (one CTA per layer): scale / shift / mean / invstd for the backward pass + running statistics.
-struct BnFinEntry { long long part_off, gamma_off, beta_off, rstat_off, aff_off; int C, pp, mrows, hw; };   // nparts = ceil(B*pp / mrows), count = B*hw
+struct BnFinEntry { long long part_off, gamma_off, beta_off, rstat_off, aff_off; int C, pp, mrows, hw, tmax, nsm; };   // nparts = ceil(B*pp / mrows), or (tmax > 0)
+                                                                                                                        // the persistent conv's grid; count = B*hw
 static __global__ void __launch_bounds__(256) bn_finalize_layers_kernel(const BnFinEntry* tab, const float* params, float* rstat, float* ws, int batch,
                                                                         float momentum, float eps, int update_running) {
     __shared__ double red[1024];
     const BnFinEntry e = tab[blockIdx.x];
-    const int nparts = (int)(((long long)batch * e.pp + e.mrows - 1) / e.mrows);
+    int nparts = (int)(((long long)batch * e.pp + e.mrows - 1) / e.mrows);
+    if (e.tmax > 0) {      // conv_tcp_grid(): one row per CTA of the persistent kernel
+        const long long ntiles = ((long long)batch * e.pp + 127) / 128;
+        long long g = (ntiles + e.tmax - 1) / e.tmax;
+        g = g < e.nsm ? e.nsm : g;
+        nparts = (int)(g > ntiles ? ntiles : g);
+    }
     const float cnt = (float)((long long)batch * e.hw);
     bn_partial_sums(ws + e.part_off, nparts, e.C, red);
     if ((int)threadIdx.x < e.C) {

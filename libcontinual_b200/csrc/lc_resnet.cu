@@ -5,6 +5,7 @@
 #include "conv_aux.cuh"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
+#include "conv_tcp.cuh"
 #include "wgrad_tc.cuh"
 #include "flat_ops.cuh"
 #include "head_loss.cuh"
@@ -74,14 +75,37 @@ int launch_wgrad3x3(int cin, int cout, int wo, int stride, bool nchw, const Wgra
 bool tc_eligible(int cin, int cout, int wo, int stride, int ksize) {
     return ksize == 3 && stride == 1 && cin == cout && ((cin == 16 && wo == 32) || (cin == 32 && wo == 16) || (cin == 64 && wo == 8));
 }
-int launch_conv3x3_tc(int c, int wo, const tc::ConvTcArgs& a, cudaStream_t st) {
+// LC_CONV_PERSIST=0 keeps every forward conv on the one-wave kernel (conv_tc.cuh); default: stages 1 and 2 run the persistent, warp-specialised
+// kernel (conv_tcp.cuh), whose grid — and therefore the number of BatchNorm partial rows — is conv_tcp_grid()
+int conv_persist_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LC_CONV_PERSIST"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+int device_sms() {
+    static int v = 0;
+    if (v == 0) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148; }
+    return v;
+}
+bool tcp_eligible(int c, int wo) { return (c == 16 && wo == 32) || (c == 32 && wo == 16); }
+// partial rows a forward tensor-core conv of this shape writes (= its grid size)
+int conv_tc_fwd_parts(long long batch, int c, int wo, bool persist) {
+    if (persist && tcp_eligible(c, wo)) return tc::conv_tcp_grid(batch, c, wo, device_sms());
+    const int mrows = 128 * (c == 16 ? 4 : (c == 32 ? 2 : 1));
+    return (int)((batch * (wo + 2) * (wo + 2) + mrows - 1) / mrows);
+}
+int launch_conv3x3_tc(int c, int wo, const tc::ConvTcArgs& a, cudaStream_t st, bool persist = false) {
+    if (persist && c == 16 && wo == 32) return tc::conv_tcp_launch<16, 32, 0>(a, device_sms(), st);
+    if (persist && c == 32 && wo == 16) return tc::conv_tcp_launch<32, 16, 0>(a, device_sms(), st);
     if (c == 16 && wo == 32) return tc::conv_tc_launch<16, 32>(a, st);
     if (c == 32 && wo == 16) return tc::conv_tc_launch<32, 16>(a, st);
     if (c == 64 && wo == 8) return tc::conv_tc_launch<64, 8>(a, st);
     return LC_ERR_INVALID;
 }
 // forward variant whose prologue finishes the previous residual block (conv_tc.cuh MODE 2)
-int launch_conv3x3_tc_res(int c, int wo, const tc::ConvTcArgs& a, cudaStream_t st) {
+int launch_conv3x3_tc_res(int c, int wo, const tc::ConvTcArgs& a, cudaStream_t st, bool persist = false) {
+    if (persist && c == 16 && wo == 32) return tc::conv_tcp_launch<16, 32, 2>(a, device_sms(), st);
+    if (persist && c == 32 && wo == 16) return tc::conv_tcp_launch<32, 16, 2>(a, device_sms(), st);
     if (c == 16 && wo == 32) return tc::conv_tc_launch<16, 32, 2>(a, st);
     if (c == 32 && wo == 16) return tc::conv_tc_launch<32, 16, 2>(a, st);
     if (c == 64 && wo == 8) return tc::conv_tc_launch<64, 8, 2>(a, st);
@@ -209,6 +233,7 @@ struct lc_resnet {
     cudaStream_t sides[kMaxSide] = {};
     int nside = 2;
     int debug_skip = 0;
+    int persist = 1;               // forward convs of stages 1 / 2 on the persistent kernel (conv_tcp.cuh)
     int fuse_block_out = 1;
     int fused = 1;
     cudaStream_t side = nullptr;
@@ -544,6 +569,7 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
         }
         const char* envb = getenv("LC_RESNET_NO_BLOCK_FUSE");
         n->fuse_block_out = (envb != nullptr && envb[0] == '1') ? 0 : 1;
+        n->persist = conv_persist_enabled();
         const char* envd = getenv("LC_RESNET_DEBUG_SKIP");
         if (envd != nullptr && (envd[0] == '1' || envd[0] == '2')) n->debug_skip = envd[0] - '0';
         const char* envs = getenv("LC_RESNET_SIDE");
@@ -575,6 +601,7 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
         BnFinEntry e{};
         e.part_off = c.fpartL_off; e.gamma_off = c.gamma_off; e.beta_off = c.beta_off; e.rstat_off = c.rstat_off; e.aff_off = c.aff_off; e.C = c.cout;
         e.pp = (c.wo + 2) * (c.wo + 2); e.mrows = 128 * (c.cout == 16 ? 4 : (c.cout == 32 ? 2 : 1)); e.hw = c.wo * c.wo;
+        if (n->persist && tcp_eligible(c.cout, c.wo)) { e.tmax = c.cout == 16 ? 8 : 3; e.nsm = device_sms(); }
         ft.push_back(e);
     }
     n->n_deferred = (int)ft.size();
@@ -669,7 +696,7 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
         LC_TRY(lc_launch_status());
     }
     const bool lazy = train && n->mode == 1 && n->lazy_stats;
-    auto mrows_of = [](int cout) { return 128 * (cout == 16 ? 4 : (cout == 32 ? 2 : 1)); };
+    const bool persist = n->persist != 0;
     auto stat_for = [&](const ConvL& c) {
         BnStatArgs s{};
         if (!train) return s;
@@ -687,7 +714,7 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
         BnLazy z{};
         if (!(lazy && c.fpartL_off >= 0)) return z;
         z.partial = ws + c.fpartL_off; z.gamma = params + c.gamma_off; z.beta = params + c.beta_off;
-        z.nparts = (int)(((long long)batch * (c.wo + 2) * (c.wo + 2) + mrows_of(c.cout) - 1) / mrows_of(c.cout));
+        z.nparts = conv_tc_fwd_parts(batch, c.cout, c.wo, n->persist != 0);
         z.count = (float)((long long)batch * c.wo * c.wo); z.eps = kBnEps;
         return z;
     };
@@ -729,10 +756,10 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
                 a.in = ws + pb.y_off; a.pro_scale = ws + pb.aff_off; a.pro_shift = ws + pb.aff_off + pb.cout; a.pro_lazy = lazy_of(pb);
                 a.pro_res = pend_res; a.pro_out = ws + pend->out_off;
                 pend = nullptr;
-                LC_TRY(launch_conv3x3_tc_res(ca.cin, ca.wo, a, st));
+                LC_TRY(launch_conv3x3_tc_res(ca.cin, ca.wo, a, st, persist));
             } else {
                 a.in = cur;
-                LC_TRY(launch_conv3x3_tc(ca.cin, ca.wo, a, st));
+                LC_TRY(launch_conv3x3_tc(ca.cin, ca.wo, a, st, persist));
             }
         } else {
             if (pend != nullptr) LC_TRY(flush_pending());
@@ -744,7 +771,7 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
             tc::ConvTcArgs a{};
             a.in = ws + ca.y_off; a.wtc = packed + cb.wtf_off; a.out = ws + cb.y_off; a.stat = stat_for(cb); a.B = batch; a.error_flag = err_flag;
             a.pro_scale = ws + ca.aff_off; a.pro_shift = ws + ca.aff_off + ca.cout; a.pro_lazy = lazy_of(ca);
-            LC_TRY(launch_conv3x3_tc(cb.cin, cb.wo, a, st));
+            LC_TRY(launch_conv3x3_tc(cb.cin, cb.wo, a, st, persist));
         } else {
             Conv3x3Args a{};
             a.in = ws + ca.y_off; a.wpack = packed + cb.wf_off; a.out = ws + cb.y_off; a.stat = stat_for(cb); a.B = batch;
@@ -1092,7 +1119,7 @@ int lc_conv3x3_tc(const float* in, const float* w_oihw, float* out, int batch, i
     a.error_flag = reinterpret_cast<int*>(scratch) + 8;
     a.wtc = packed + (mode == 0 ? 2 * ne : 3 * ne);
     if (mode == 0 && stat_out) { LC_CHECK_ARG(gamma && beta); fill_stat(a.stat, gamma, beta, rstat, stat_out, c, partial, reinterpret_cast<unsigned int*>(scratch)); }
-    return launch_conv3x3_tc(c, width, a, st);
+    return launch_conv3x3_tc(c, width, a, st, mode == 0 && conv_persist_enabled());
 }
 // One launch of the tensor-core conv on pre-packed TF32 weights ([9][c/4][c][4], as left at scratch+96+2*9*c*c by lc_conv3x3_tc):
 // no packing, no statistics.  Used by bench.py to time the dominant kernel in isolation.
@@ -1101,7 +1128,7 @@ int lc_conv3x3_tc_packed(const float* in, const float* wtc, float* out, int batc
     LC_CHECK_ARG(in && wtc && out && batch >= 1 && tc_eligible(c, c, width, 1, 3));
     tc::ConvTcArgs a{};
     a.in = in; a.wtc = wtc; a.out = out; a.pro_scale = pro_scale; a.pro_shift = pro_shift; a.B = batch; a.error_flag = error_flag;
-    return launch_conv3x3_tc(c, width, a, (cudaStream_t)stream);
+    return launch_conv3x3_tc(c, width, a, (cudaStream_t)stream, conv_persist_enabled() != 0);
 }
 long long lc_conv_tc_scratch_floats(int batch, int c, int width) {
     const long long ne = (long long)c * c * 9;

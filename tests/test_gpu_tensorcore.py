@@ -22,7 +22,7 @@ def tf32_round(t):
 
 
 @pytest.mark.parametrize("c,w", [(16, 32), (32, 16), (64, 8)])
-@pytest.mark.parametrize("B", [1, 3, 8])
+@pytest.mark.parametrize("B", [1, 3, 8, 37, 200])      # 37: ragged tile ranges; 200: more CTAs than SMs for the persistent stage-1 kernel (conv_tcp.cuh)
 def test_conv3x3_tc_forward(lib, c, w, B):
     g = torch.Generator().manual_seed(100 * c + B)
     x = torch.randn(B, c, w, w, generator=g)

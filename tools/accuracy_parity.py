@@ -139,13 +139,24 @@ def main():
     ap.add_argument("--lr", type=float, default=0.1)
     ap.add_argument("--amp", type=float, default=1.0, help="class-template amplitude against unit noise")
     ap.add_argument("--oracle-only", action="store_true", help="CPU: only the oracle and its 1-ulp control arm (stream design)")
+    ap.add_argument("--ours-only", action="store_true", help="GPU box: only the two CUDA arms (the oracle arms of the same seeds run on a CPU-only machine)")
+    ap.add_argument("--merge", nargs=2, metavar=("OURS_JSON", "ORACLE_JSON"), help="combine an --ours-only and an --oracle-only run of the same seeds")
     a = ap.parse_args()
     global METHOD, LR, AMP
     METHOD, LR, AMP = a.method, a.lr, a.amp
     if a.oracle_only:
         global run_ours
         run_ours = lambda *args, **kw: [float("nan")]
-    rows = [one_seed(s, a.steps, a.n_test) for s in range(a.seeds)]
+    if a.ours_only:
+        global run_oracle
+        run_oracle = lambda *args, **kw: [float("nan")]
+    if a.merge:
+        ours, orc = (json.load(open(f)) for f in a.merge)
+        assert len(ours["per_seed"]) == len(orc["per_seed"])
+        rows = [{k: (o[k] if k.startswith("cuda") else r[k]) for k in o} for o, r in zip(ours["per_seed"], orc["per_seed"])]
+        a.seeds = len(rows)
+    else:
+        rows = [one_seed(s, a.steps, a.n_test) for s in range(a.seeds)]
     arms = list(rows[0])
     res = {"stream": f"{METHOD.upper()} cifar_resnet32, 2 tasks x 10 classes, {a.steps} steps/task, bs 32, SGD {LR}/0.9/5e-4, "
                      + ("lamda 1000, " if METHOD == "ewc" else "KD weight 3 T 2, ") + f"template amplitude {AMP}, test {a.n_test}/task "

@@ -1,11 +1,11 @@
 // Debug harness: CUDA-event time per launch of the tensor-core conv in each prologue / epilogue configuration, 200 back-to-back launches
 // (programmatic dependent launch, as in the step) rotating over NBUF buffer sets.  Build: see tools/build_variants.sh.
-#include "conv_tc.cuh"
+#include "conv_tcp.cuh"
 #include <cstdio>
 #include <vector>
 using namespace lc;
 
-template <int C, int W>
+template <int C, int W, bool PERSIST = false>
 void run(int B) {
     using K = tc::ConvTcCfg<C, W>;
     constexpr int NBUF = 6;
@@ -17,7 +17,7 @@ void run(int B) {
     cudaMalloc(&aff, 4 * C * 4); cudaMemset(aff, 0, 4 * C * 4);
     cudaMalloc(&coef, 3 * C * 4); cudaMemset(coef, 0, 3 * C * 4);
     cudaMalloc(&gamma, C * 4); cudaMalloc(&beta, C * 4); cudaMalloc(&dg, 2 * C * 4); cudaMemset(gamma, 0, C * 4); cudaMemset(beta, 0, C * 4);
-    const int grid = (int)(((long long)B * K::PP + K::MROWS - 1) / K::MROWS);
+    const int grid = PERSIST ? tc::conv_tcp_grid(B, C, W, 148) : (int)(((long long)B * K::PP + K::MROWS - 1) / K::MROWS);
     cudaMalloc(&part, (size_t)grid * 2 * C * 4 * 2); cudaMemset(part, 0, (size_t)grid * 2 * C * 4 * 2);
     cudaMalloc(&counter, 64); cudaMemset(counter, 0, 64); cudaMalloc(&err, 4); cudaMemset(err, 0, 4);
     cudaStream_t st; cudaStreamCreate(&st);
@@ -42,7 +42,7 @@ void run(int B) {
     const char* names[] = {"fwd plain", "fwd + BN/ReLU prologue", "fwd + prologue + stats (last-CTA finalise)", "fwd + prologue + stats (deferred)",
                            "fwd + lazy prologue + stats (deferred)", "bwd: apply prologue (coef array)", "bwd: + mask(BN) + reduce (last-CTA)",
                            "bwd: + mask(BN) + reduce (deferred)", "bwd: lazy coef + addend + mask(out) + reduce (deferred)", "bwd: mask(BN) only, no reduce"};
-    for (int v = 0; v < 10; ++v) {
+    for (int v = 0; v < (PERSIST ? 5 : 10); ++v) {
         float best = 1e9f;
         for (int rep = 0; rep < 3; ++rep) {
             cudaEventRecord(e0, st);
@@ -54,7 +54,10 @@ void run(int B) {
                 if (v == 2) stat(a, 0);
                 if (v == 3 || v == 4) stat(a, 1);
                 if (v == 4) lazy(a);
-                if (v < 5) { tc::conv_tc_launch<C, W, 0>(a, st); continue; }
+                if (v < 5) {
+                    if constexpr (PERSIST) tc::conv_tcp_launch<C, W, 0>(a, 148, st); else tc::conv_tc_launch<C, W, 0>(a, st);
+                    continue;
+                }
                 a.pro_y = y[i]; a.pro_coef = coef;
                 if (v == 6) bw(a, i, 1, 0, 0);
                 if (v == 7) bw(a, i, 1, 1, 0);
@@ -75,7 +78,11 @@ void run(int B) {
 
 int main() {
     run<16, 32>(128);
+    printf("persistent kernel (conv_tcp.cuh):\n");
+    run<16, 32, true>(128);
     run<32, 16>(128);
+    printf("persistent kernel (conv_tcp.cuh):\n");
+    run<32, 16, true>(128);
     run<64, 8>(128);
     return 0;
 }
