@@ -301,6 +301,11 @@ long long lc_conv_tc_scratch_floats(int batch, int c, int width);
 int lc_conv3x3_tc(const float* in, const float* w_oihw, float* out, int batch, int c, int width, int mode, const float* pro_scale,
                   const float* pro_shift, const float* addend, const float* gamma, const float* beta, float* rstat, float* stat_out,
                   float* scratch, lc_stream_t stream);
+/* tcgen05 forward of the stride-2 3x3 convs at the stage transitions (cin -> 2*cin; (cin, width_out) in {(16,16),(32,8)}; parity-plane implicit
+ * GEMM, csrc/conv_s2_tc.cuh) — replaces the cuDNN fprop of core/model/backbone/resnet.py:341-343 at stride 2.  Optional BatchNorm statistics of the
+ * output (gamma / beta / stat_out as lc_conv3x3).  scratch >= lc_conv_scratch_floats(batch, cin, 2*cin, width_out), first 64 words zero. */
+int lc_conv3x3s2_tc(const float* in, const float* w_oihw, float* out, int batch, int cin, int width_out, const float* gamma, const float* beta,
+                    float* rstat, float* stat_out, float* scratch, lc_stream_t stream);
 /* One launch of the tensor-core conv on pre-packed weights (lc_conv3x3_tc leaves the forward packing at scratch+96+2*9*c*c). */
 int lc_conv3x3_tc_packed(const float* in, const float* wtc, float* out, int batch, int c, int width, const float* pro_scale,
                          const float* pro_shift, int* error_flag, lc_stream_t stream);

@@ -110,6 +110,7 @@ SIGNATURES = {
     "lc_conv_tc_scratch_floats": (c_longlong, [c_int, c_int, c_int]),
     "lc_conv3x3_tc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P]),
     "lc_conv3x3_tc_packed": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P]),
+    "lc_conv3x3s2_tc": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P, P, P]),
     "lc_conv3x3_wgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "lc_conv3x3_wgrad_tc": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P]),
     "lc_conv1x1s2": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),

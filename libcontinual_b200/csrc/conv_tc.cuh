@@ -31,6 +31,7 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 // bounded wait: returns false if the phase never completed (a mis-programmed MMA must not hang the GPU)
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);

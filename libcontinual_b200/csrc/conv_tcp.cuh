@@ -28,7 +28,6 @@ namespace tc {
 #endif
 
 __device__ __forceinline__ void tcp_bar256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }      // the 8 transform warps
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 
 template <int C, int W>
 struct ConvTcpCfg {

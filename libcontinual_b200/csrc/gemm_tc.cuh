@@ -120,9 +120,7 @@ __device__ __forceinline__ unsigned long long gemm_gtimer() { unsigned long long
 #define LC_GSTAMP(tile_local, slot) do { } while (0)
 #endif
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
+// mbar_arrive: conv_tc.cuh
 // ---- CTA-pair (cta_group::2) primitives ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {

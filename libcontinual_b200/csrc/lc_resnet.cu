@@ -6,6 +6,7 @@
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
 #include "conv_tcp.cuh"
+#include "conv_s2_tc.cuh"
 #include "wgrad_tc.cuh"
 #include "flat_ops.cuh"
 #include "head_loss.cuh"
@@ -86,6 +87,20 @@ int device_sms() {
     static int v = 0;
     if (v == 0) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148; }
     return v;
+}
+// stride-2 first conv of stages 2 / 3 on the tensor cores (forward only); LC_CONV_S2_TC=0 keeps them on the CUDA-core kernel
+bool s2_tc_eligible(int cin, int cout, int wo, int stride, int ksize) {
+    return ksize == 3 && stride == 2 && cout == 2 * cin && ((cin == 16 && wo == 16) || (cin == 32 && wo == 8));
+}
+int conv_s2_tc_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LC_CONV_S2_TC"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+int launch_conv3x3s2_tc(int cin, int wo, const tc::ConvS2Args& a, cudaStream_t st) {
+    if (cin == 16 && wo == 16) return tc::conv_s2_tc_launch<16, 16>(a, st);
+    if (cin == 32 && wo == 8) return tc::conv_s2_tc_launch<32, 8>(a, st);
+    return LC_ERR_INVALID;
 }
 bool tcp_eligible(int c, int wo) { return (c == 16 && wo == 32) || (c == 32 && wo == 16); }
 // partial rows a forward tensor-core conv of this shape writes (= its grid size)
@@ -192,6 +207,7 @@ struct ConvL {
     long long y_off;                      // workspace: raw conv output
     long long wf_off, wd_off, part_off;   // workspace-relative (packed weights / partials)
     long long wtf_off, wtd_off;           // tensor-core packings (-1 when the layer stays on the CUDA-core path)
+    long long wts_off = -1;               // stride-2 layers: tensor-core FORWARD packing (conv_s2_tc.cuh); dgrad / wgrad stay on the CUDA-core kernels
     long long fpartL_off;                 // workspace: this layer's own forward-statistics partial rows (deferred finalisation), -1 if not tensor-core
     long long bpartL_off;                 // workspace: this layer's BatchNorm-backward partial rows (written by a fused data-gradient epilogue)
     int nsplit;
@@ -510,6 +526,7 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
         c.wf_off = pk; pk += ne;
         if (c.ksize == 3) { c.wd_off = pk; pk += ne; } else c.wd_off = -1;
         if (tc_eligible(c.cin, c.cout, c.wo, c.stride, c.ksize)) { c.wtf_off = pk; pk += ne; c.wtd_off = pk; pk += ne; } else { c.wtf_off = c.wtd_off = -1; }
+        if (s2_tc_eligible(c.cin, c.cout, c.wo, c.stride, c.ksize) && conv_s2_tc_enabled()) { c.wts_off = pk; pk += ne; }
         c.nsplit = c.ksize == 3 ? wgrad_nsplit(c.cin, c.cout) : k1x1Split;
         c.part_off = wp; wp += ne * std::max(c.nsplit, c.wtf_off >= 0 ? wgrad_nsplit_tc(c.cout) : 0);
     }
@@ -546,7 +563,8 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
         n->off_T2r[r] = r == 0 ? n->off_T2 : take(B * 32 * 32 * 16);
     }
     for (auto& c : n->convs)
-        c.fpartL_off = c.wtf_off >= 0 ? take(tc::conv_tc_tiles((int)B, c.wo) * 2 * c.cout) : -1;
+        c.fpartL_off = c.wtf_off >= 0 ? take(tc::conv_tc_tiles((int)B, c.wo) * 2 * c.cout)
+                                      : (c.wts_off >= 0 ? take((long long)tc::conv_s2_tc_grid(B, c.wo) * 2 * c.cout) : -1);
     for (auto& c : n->convs) c.bpartL_off = c.ksize == 3 ? take(tc::conv_tc_tiles((int)B, c.wo) * 2 * c.cout) : -1;
     n->ws_floats = o;
     {
@@ -583,6 +601,7 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
     for (auto& c : n->convs) {
         ConvTabEntry t{};
         t.w_off = c.w_off; t.wf_off = c.wf_off; t.wd_off = c.wd_off; t.part_off = c.part_off; t.wtf_off = c.wtf_off; t.wtd_off = c.wtd_off;
+        t.wts_off1 = c.wts_off >= 0 ? c.wts_off + 1 : 0;
         t.cout = c.cout; t.cin = c.cin; t.ntap = c.ksize * c.ksize; t.nsplit = c.nsplit; t.blk_begin = blk;
         t.nsplit_tc = c.wtf_off >= 0 ? wgrad_nsplit_tc(c.cout) : c.nsplit;
         blk += (c.cout * c.cin * t.ntap + 255) / 256;
@@ -601,7 +620,8 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
         BnFinEntry e{};
         e.part_off = c.fpartL_off; e.gamma_off = c.gamma_off; e.beta_off = c.beta_off; e.rstat_off = c.rstat_off; e.aff_off = c.aff_off; e.C = c.cout;
         e.pp = (c.wo + 2) * (c.wo + 2); e.mrows = 128 * (c.cout == 16 ? 4 : (c.cout == 32 ? 2 : 1)); e.hw = c.wo * c.wo;
-        if (n->persist && tcp_eligible(c.cout, c.wo)) { e.tmax = c.cout == 16 ? 8 : 3; e.nsm = device_sms(); }
+        if (c.wts_off >= 0) { e.pp = (c.wo + 1) * (c.wo + 1); e.mrows = 128; }      // conv_s2_tc_grid()
+        else if (n->persist && tcp_eligible(c.cout, c.wo)) { e.tmax = c.cout == 16 ? 8 : 3; e.nsm = device_sms(); }
         ft.push_back(e);
     }
     n->n_deferred = (int)ft.size();
@@ -714,7 +734,7 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
         BnLazy z{};
         if (!(lazy && c.fpartL_off >= 0)) return z;
         z.partial = ws + c.fpartL_off; z.gamma = params + c.gamma_off; z.beta = params + c.beta_off;
-        z.nparts = conv_tc_fwd_parts(batch, c.cout, c.wo, n->persist != 0);
+        z.nparts = c.wts_off >= 0 ? tc::conv_s2_tc_grid(batch, c.wo) : conv_tc_fwd_parts(batch, c.cout, c.wo, n->persist != 0);
         z.count = (float)((long long)batch * c.wo * c.wo); z.eps = kBnEps;
         return z;
     };
@@ -761,6 +781,11 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
                 a.in = cur;
                 LC_TRY(launch_conv3x3_tc(ca.cin, ca.wo, a, st, persist));
             }
+        } else if (n->mode == 1 && ca.wts_off >= 0) {       // stage transition: stride-2 conv on the tensor cores (parity planes)
+            if (pend != nullptr) LC_TRY(flush_pending());
+            tc::ConvS2Args a{};
+            a.in = cur; a.wtc = packed + ca.wts_off; a.out = ws + ca.y_off; a.stat = stat_for(ca); a.B = batch; a.error_flag = err_flag;
+            LC_TRY(launch_conv3x3s2_tc(ca.cin, ca.wo, a, st));
         } else {
             if (pend != nullptr) LC_TRY(flush_pending());
             Conv3x3Args a{};
@@ -1120,6 +1145,27 @@ int lc_conv3x3_tc(const float* in, const float* w_oihw, float* out, int batch, i
     a.wtc = packed + (mode == 0 ? 2 * ne : 3 * ne);
     if (mode == 0 && stat_out) { LC_CHECK_ARG(gamma && beta); fill_stat(a.stat, gamma, beta, rstat, stat_out, c, partial, reinterpret_cast<unsigned int*>(scratch)); }
     return launch_conv3x3_tc(c, width, a, st, mode == 0 && conv_persist_enabled());
+}
+// Stride-2 tensor-core forward conv (cin -> 2*cin, output width wo) with optional BatchNorm statistics of the output; scratch as lc_conv3x3
+// (>= lc_conv_scratch_floats(batch, cin, 2*cin, wo), first 64 words zero); scratch word 8 (int) is set to 1 if the MMA completion barrier timed out.
+int lc_conv3x3s2_tc(const float* in, const float* w_oihw, float* out, int batch, int cin, int width_out, const float* gamma, const float* beta,
+                    float* rstat, float* stat_out, float* scratch, lc_stream_t stream) {
+    LC_CHECK_ARG(in && w_oihw && out && scratch && batch >= 1 && ((uintptr_t)scratch % 16 == 0) && s2_tc_eligible(cin, 2 * cin, width_out, 2, 3));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int cout = 2 * cin;
+    const long long ne = (long long)cout * cin * 9;
+    ConvTabEntry t{};
+    t.w_off = 0; t.wf_off = 0; t.wd_off = -1; t.wtf_off = -1; t.wtd_off = -1; t.wts_off1 = ne + 1; t.cout = cout; t.cin = cin; t.ntap = 9; t.blk_begin = 0;
+    ConvTabEntry* d_t = reinterpret_cast<ConvTabEntry*>(scratch + 64);
+    float* packed = scratch + kOpData;
+    float* partial = packed + round4(2 * ne);
+    if (cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, st) != cudaSuccess) return LC_ERR_CUDA;
+    pack_weights_kernel<<<(int)((ne + 255) / 256), 256, 0, st>>>(d_t, 1, w_oihw, packed);
+    if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
+    tc::ConvS2Args a{};
+    a.in = in; a.wtc = packed + ne; a.out = out; a.B = batch; a.error_flag = reinterpret_cast<int*>(scratch) + 8;
+    if (stat_out) { LC_CHECK_ARG(gamma && beta); fill_stat(a.stat, gamma, beta, rstat, stat_out, cout, partial, reinterpret_cast<unsigned int*>(scratch)); }
+    return launch_conv3x3s2_tc(cin, width_out, a, st);
 }
 // One launch of the tensor-core conv on pre-packed TF32 weights ([9][c/4][c][4], as left at scratch+96+2*9*c*c by lc_conv3x3_tc):
 // no packing, no statistics.  Used by bench.py to time the dominant kernel in isolation.

@@ -99,3 +99,34 @@ def test_conv3x3_tc_wgrad(lib, c, w, B):
         # contraction of the same BF16-rounded operands only the summation order differs
         assert err <= 1e-2 * scale, (err, scale)
         assert err_tf <= 2e-4 * scale, (err_tf, scale)
+
+
+@pytest.mark.parametrize("cin,wo", [(16, 16), (32, 8)])
+@pytest.mark.parametrize("B", [1, 5, 37, 128])
+def test_conv3x3s2_tc_forward(lib, cin, wo, B):
+    """Stride-2 stage-transition conv on tcgen05 (parity-plane implicit GEMM, csrc/conv_s2_tc.cuh) against PyTorch fp32 conv2d(stride=2, padding=1)
+    (resnet.py:341-343 at stride 2); same TF32 bound as the stride-1 kernel, BatchNorm statistics of the output included."""
+    cout, win = 2 * cin, 2 * wo
+    g = torch.Generator().manual_seed(1000 * cin + B)
+    x = torch.randn(B, cin, win, win, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * 0.1
+    gamma, beta = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
+    ref = F.conv2d(x, wt, None, 2, 1)
+    out = torch.full((B, wo, wo, cout), float("nan"), device="cuda")
+    scratch = torch.zeros(int(lib.lc_conv_scratch_floats(B, cin, cout, wo)), device="cuda")
+    stat = torch.zeros(4 * cout, device="cuda")
+    rc = lib.lc_conv3x3s2_tc(P(dev(nhwc(x))), P(dev(wt)), P(out), B, cin, wo, P(dev(gamma)), P(dev(beta)), None, P(stat), P(scratch), st())
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert int(scratch.view(torch.int32)[8]) == 0, "tensor-core barrier timed out"
+    got = nchw(out).cpu()
+    assert torch.isfinite(got).all()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    e_rn = (got - F.conv2d(tf32_round(x), tf32_round(wt), None, 2, 1)).abs().max().item()
+    print(f"s2 cin={cin} wo={wo} B={B}: max|err| {err:.3e} (ref max {scale:.2f}); vs tf32-round operands {e_rn:.3e}")
+    assert err <= 4e-3 * scale, (err, scale)
+    assert e_rn <= 2e-5 * scale, (e_rn, scale)
+    mean, var = ref.mean((0, 2, 3)), ref.var((0, 2, 3), unbiased=False)
+    close(stat[2 * cout:3 * cout], mean, 1e-2, 2e-3, "mean")
+    close(stat[3 * cout:], 1 / torch.sqrt(var + 1e-5), 1e-2, 1e-3, "invstd")
