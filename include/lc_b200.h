@@ -306,6 +306,9 @@ int lc_conv3x3_tc(const float* in, const float* w_oihw, float* out, int batch, i
  * output (gamma / beta / stat_out as lc_conv3x3).  scratch >= lc_conv_scratch_floats(batch, cin, 2*cin, width_out), first 64 words zero. */
 int lc_conv3x3s2_tc(const float* in, const float* w_oihw, float* out, int batch, int cin, int width_out, const float* gamma, const float* beta,
                     float* rstat, float* stat_out, float* scratch, lc_stream_t stream);
+/* Data gradient of the same stride-2 conv on tcgen05 (one staged dy tile, nine tap groups into four parity-plane accumulators; replaces cuDNN's
+ * dgrad, i.e. autograd of resnet.py:341-343 at stride 2): dy [B][wo][wo][2*cin] -> dx [B][2*wo][2*wo][cin]. */
+int lc_conv3x3s2_dgrad_tc(const float* dy, const float* w_oihw, float* dx, int batch, int cin, int width_out, float* scratch, lc_stream_t stream);
 /* One launch of the tensor-core conv on pre-packed weights (lc_conv3x3_tc leaves the forward packing at scratch+96+2*9*c*c). */
 int lc_conv3x3_tc_packed(const float* in, const float* wtc, float* out, int batch, int c, int width, const float* pro_scale,
                          const float* pro_shift, int* error_flag, lc_stream_t stream);

@@ -111,6 +111,7 @@ SIGNATURES = {
     "lc_conv3x3_tc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P]),
     "lc_conv3x3_tc_packed": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P]),
     "lc_conv3x3s2_tc": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P, P, P]),
+    "lc_conv3x3s2_dgrad_tc": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
     "lc_conv3x3_wgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "lc_conv3x3_wgrad_tc": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P]),
     "lc_conv1x1s2": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),

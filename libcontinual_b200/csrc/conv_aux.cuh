@@ -177,6 +177,7 @@ struct ConvTabEntry {
     long long wtf_off;    // tensor-core forward packing  [tap][ci/4][co][ci%4]   (-1: layer not on the tensor-core path)
     long long wtd_off;    // tensor-core dgrad packing    [8-tap][co/4][ci][co%4]
     long long wts_off1;   // 1 + offset of the tensor-core forward packing of a STRIDE-2 layer (conv_s2_tc.cuh; same [tap][ci/4][co][ci%4] order); 0: none
+    long long wtsd_off1;  // 1 + offset of the stride-2 layer's tensor-core DATA-GRADIENT packing [tap][co/4][ci][co%4] (tap not flipped); 0: none
     int cout, cin, ntap, nsplit;
     int blk_begin;        // first block of this layer in the table kernels
     int nsplit_tc;        // split count used by the tensor-core weight-gradient kernel (<= nsplit)
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const ConvTabEntry* t
         uint32_t r;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(w));
         packed[t.wts_off1 - 1 + (((size_t)tap * (t.cin >> 2) + (ci >> 2)) * t.cout + co) * 4 + (ci & 3)] = __uint_as_float(r);
+        if (t.wtsd_off1 > 0) packed[t.wtsd_off1 - 1 + (((size_t)tap * (t.cout >> 2) + (co >> 2)) * t.cin + ci) * 4 + (co & 3)] = __uint_as_float(r);
     }
     if (t.wtf_off >= 0) {      // tensor-core operands are pre-rounded to TF32 (round-to-nearest-away) once per step
         uint32_t r;

@@ -248,5 +248,197 @@ static inline int conv_s2_tc_launch(const ConvS2Args& a, cudaStream_t st) {
     return lc_launch_status();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------------------------------
+// Data gradient of the same stride-2 conv: dX[n][y][x][ci] = sum over taps / co of dY[n][i][j][co] * W[co][ci][dr+1][dc+1] with y = 2i + dr, x = 2j + dc.
+// Per PARITY PLANE of dX (py, px) = (y & 1, x & 1) only the taps with dr = py, dc = px (mod 2) contribute, each a constant row shift of the flattened dY
+// grid (one TRAILING pad row / column: Q = (n*(WO+1) + i)*(WO+1) + j; tap dr = -1 reads i = a + 1, dr = 0 / +1 read i = a):
+//     plane (0,0): tap (0,0)            plane (0,1): taps (0,-1), (0,+1)            plane (1,0): taps (-1,0), (+1,0)            plane (1,1): the four corners
+// so the nine taps are nine MMA groups (K = COUT) over ONE staged dY tile into four TMEM accumulators (128 positions x CIN each) — no multiplication by
+// the zeros of a dilated gradient, which is what the CUDA-core kernel it replaces spends 3/4 of its time on.  The epilogue writes pixel PAIRS: planes
+// (py, 0) and (py, 1) of a position are neighbouring pixels of dX, 2*CIN contiguous floats.
+struct DgradS2Args {
+    const float* dy;         // NHWC [B][WO][WO][COUT]
+    const float* wtc;        // packed [9][COUT/4][CIN][4] (tap NOT flipped), TF32-rounded
+    float* out;              // NHWC [B][2*WO][2*WO][CIN]  (every element written)
+    int* error_flag;
+    int B;
+};
+
+template <int CIN, int WO>
+struct DgradS2Cfg {
+    static constexpr int KC = 2 * CIN;               // contraction = COUT
+    static constexpr int WIN = 2 * WO;
+    static constexpr int WP = WO + 1;
+    static constexpr int PP = WP * WP;
+    static constexpr int HALO = WP + 1;              // high side only
+    static constexpr int ROWS = 128 + HALO;
+    static constexpr int CH = KC / 4;
+    static constexpr int NT = 256;
+    static constexpr int RSTEP = NT / CH;
+    static constexpr int NE = (ROWS + RSTEP - 1) / RSTEP;
+    static constexpr int PLANE = ROWS * 16;
+    static constexpr int A_BYTES = CH * PLANE;
+    static constexpr int BTAP = CH * CIN * 16;
+    static constexpr int B_BYTES = 9 * BTAP;
+    static constexpr int PAIRB = 2 * CIN * 4;        // bytes of one output pixel pair
+    static constexpr int CPR = PAIRB / 16;           // 16-byte chunks per pair: 8 / 16
+    static constexpr int STG_WARP = 32 * PAIRB;      // 4 KB / 8 KB
+    static constexpr int OFF_B = (A_BYTES + 127) / 128 * 128;
+    static constexpr int OFF_STG = (OFF_B + B_BYTES + 127) / 128 * 128;
+    static constexpr int OFF_ROWTAB = OFF_STG + 8 * STG_WARP;                // [ROWS] dY pixel index or -1
+    static constexpr int OFF_DST = OFF_ROWTAB + (ROWS * 4 + 15) / 16 * 16;   // [128] dX pixel index of (2a, 2b) or -1
+    static constexpr int OFF_DSTW = OFF_DST + 512;                           // [8 warps][32] compacted per warp
+    static constexpr int OFF_BAR = OFF_DSTW + 8 * 32 * 4;
+    static constexpr size_t SMEM_BYTES = OFF_BAR + 64;
+    static constexpr uint32_t TMEM_COLS = 4 * CIN;   // 64 / 128
+    static_assert((CIN == 16 && WO == 16) || (CIN == 32 && WO == 8), "stage transitions of the CIFAR ResNet");
+    static_assert(NE <= 16, "staging");
+};
+
+template <int CIN, int WO>
+__global__ void __launch_bounds__(288) dgrad3x3s2_tc_kernel(DgradS2Args a) {
+    using K = DgradS2Cfg<CIN, WO>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* sA = smem_raw;
+    unsigned char* sB = smem_raw + K::OFF_B;
+    int* s_rowsrc = reinterpret_cast<int*>(smem_raw + K::OFF_ROWTAB);
+    int* s_dst = reinterpret_cast<int*>(smem_raw + K::OFF_DST);
+    int* s_dstw = reinterpret_cast<int*>(smem_raw + K::OFF_DSTW);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + K::OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool worker = tid < K::NT;
+    const int total = a.B * K::PP;
+    const int q0 = (int)blockIdx.x * 128;
+
+    if (tid == 32) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+    if (warp == 0) tmem_alloc(tmem_slot, K::TMEM_COLS);
+    for (int r = tid; r < K::ROWS; r += 288) {
+        const int Q = q0 + r;
+        int src = -1, dst = -1;
+        if (Q < total) {
+            const int n = Q / K::PP, rem = Q - n * K::PP;
+            const int i = rem / K::WP, j = rem - i * K::WP;
+            if (i < WO && j < WO) {
+                src = (n * WO + i) * WO + j;
+                dst = (n * K::WIN + 2 * i) * K::WIN + 2 * j;
+            }
+        }
+        s_rowsrc[r] = src;
+        if (r < 128) s_dst[r] = dst;
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 32) bulk_load(smem_u32(sB), a.wtc, (uint32_t)K::B_BYTES, bar + 1);
+    __syncthreads();
+
+    const int j = tid % K::CH, r0 = tid / K::CH;
+    if (worker) {
+        uint32_t validmask = 0;
+        const uint32_t dstp = smem_u32(sA) + (uint32_t)(j * K::PLANE);
+#pragma unroll
+        for (int i = 0; i < K::NE; ++i) {
+            const int r = r0 + i * K::RSTEP;
+            if (r < K::ROWS) {
+                const int src = s_rowsrc[r];
+                const bool ok = src >= 0;
+                cp_async16(dstp + (uint32_t)r * 16, ok ? a.dy + (size_t)src * K::KC + j * 4 : a.dy, ok ? 16u : 0u);
+                validmask |= (ok ? 1u : 0u) << i;
+            }
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+#pragma unroll
+        for (int i = 0; i < K::NE; ++i) {
+            if (validmask & (1u << i)) {
+                float4* p4 = reinterpret_cast<float4*>(sA + (size_t)j * K::PLANE + (size_t)(r0 + i * K::RSTEP) * 16);
+                float4 v = *p4;
+                v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
+                *p4 = v;
+            }
+        }
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (tid == K::NT) {
+        mbar_wait(bar + 1, 0);
+        constexpr uint32_t idesc = make_idesc_tf32(CIN);
+        const uint64_t a0 = make_desc(0, K::PLANE, 128) | (uint64_t)(smem_u32(sA) >> 4), b0 = make_desc(0, CIN * 16, 128) | (uint64_t)(smem_u32(sB) >> 4);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int dr = tap / 3 - 1, dc = tap % 3 - 1;
+            const int par = (dr & 1) * 2 + (dc & 1);
+            const int shift = (dr < 0 ? K::WP : 0) + (dc < 0 ? 1 : 0);
+            const bool first = tap == 0 || tap == 1 || tap == 3 || tap == 4;       // first tap of its parity plane's accumulator
+#pragma unroll
+            for (int kc = 0; kc < K::KC / 8; ++kc) {
+                const uint64_t ad = a0 + (uint64_t)(2 * kc * (K::PLANE >> 4) + shift);
+                const uint64_t bd = b0 + (uint64_t)(tap * (K::BTAP >> 4) + 2 * kc * CIN);
+                mma_tf32(tmem_base + (uint32_t)(par * CIN), ad, bd, idesc, (first && kc == 0) ? 0u : 1u);
+            }
+        }
+        mma_commit(bar);
+    }
+
+    // ---- epilogue: warp (quarter, py): positions 32*quarter.. , planes (py, 0) and (py, 1) = one pixel pair per position -----------------------------------
+    bool done = true;
+    if (worker) {
+        const int quarter = warp & 3, py = warp >> 2;
+        const int dst = s_dst[quarter * 32 + lane];
+        const unsigned vmask = __ballot_sync(0xffffffffu, dst >= 0);
+        const int nvalid = __popc(vmask), rank = __popc(vmask & ((1u << lane) - 1u));
+        if (dst >= 0) s_dstw[warp * 32 + rank] = dst + py * K::WIN;
+        done = mbar_wait(bar, 0);
+        fence_after_sync();
+        unsigned char* stg = smem_raw + K::OFF_STG + (size_t)warp * K::STG_WARP;
+        auto stage = [&](int p, int cc) -> float4* {      // 2 KB pieces of 32 x 64-byte sub-rows, XOR-swizzled
+            return reinterpret_cast<float4*>(stg + (size_t)(cc >> 2) * 2048 + p * 64 + (((cc & 3) ^ ((p >> 1) & 3)) << 4));
+        };
+#pragma unroll
+        for (int h = 0; h < 2 * CIN / 32; ++h) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(py * 2 * CIN + h * 32), v);
+            if (dst >= 0) {
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) *stage(rank, h * 8 + cc) = make_float4(v[cc * 4], v[cc * 4 + 1], v[cc * 4 + 2], v[cc * 4 + 3]);
+            }
+        }
+        __syncwarp();
+        const int c = lane % K::CPR;
+#pragma unroll
+        for (int kk = 0; kk < K::CPR; ++kk) {
+            const int p = kk * (32 / K::CPR) + lane / K::CPR;
+            if (p < nvalid) *reinterpret_cast<float4*>(a.out + (size_t)s_dstw[warp * 32 + p] * CIN + c * 4) = *stage(p, c);
+        }
+    }
+    if (!done && lane == 0 && a.error_flag != nullptr) atomicExch(a.error_flag, 1);
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, K::TMEM_COLS);
+}
+
+template <int CIN, int WO>
+static inline int dgrad_s2_tc_launch(const DgradS2Args& a, cudaStream_t st) {
+    using K = DgradS2Cfg<CIN, WO>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(dgrad3x3s2_tc_kernel<CIN, WO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES) != cudaSuccess) return LC_ERR_CUDA;
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)conv_s2_tc_grid(a.B, WO)); cfg.blockDim = dim3(K::NT + 32); cfg.dynamicSmemBytes = K::SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, dgrad3x3s2_tc_kernel<CIN, WO>, a) != cudaSuccess) return LC_ERR_CUDA;
+    return lc_launch_status();
+}
+
 }  // namespace tc
 }  // namespace lc

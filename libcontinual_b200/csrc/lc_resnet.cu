@@ -102,6 +102,11 @@ int launch_conv3x3s2_tc(int cin, int wo, const tc::ConvS2Args& a, cudaStream_t s
     if (cin == 32 && wo == 8) return tc::conv_s2_tc_launch<32, 8>(a, st);
     return LC_ERR_INVALID;
 }
+int launch_dgrad3x3s2_tc(int cin, int wo, const tc::DgradS2Args& a, cudaStream_t st) {
+    if (cin == 16 && wo == 16) return tc::dgrad_s2_tc_launch<16, 16>(a, st);
+    if (cin == 32 && wo == 8) return tc::dgrad_s2_tc_launch<32, 8>(a, st);
+    return LC_ERR_INVALID;
+}
 bool tcp_eligible(int c, int wo) { return (c == 16 && wo == 32) || (c == 32 && wo == 16); }
 // partial rows a forward tensor-core conv of this shape writes (= its grid size)
 int conv_tc_fwd_parts(long long batch, int c, int wo, bool persist) {
@@ -207,7 +212,7 @@ struct ConvL {
     long long y_off;                      // workspace: raw conv output
     long long wf_off, wd_off, part_off;   // workspace-relative (packed weights / partials)
     long long wtf_off, wtd_off;           // tensor-core packings (-1 when the layer stays on the CUDA-core path)
-    long long wts_off = -1;               // stride-2 layers: tensor-core FORWARD packing (conv_s2_tc.cuh); dgrad / wgrad stay on the CUDA-core kernels
+    long long wts_off = -1, wtsd_off = -1; // stride-2 layers: tensor-core forward / data-gradient packings (conv_s2_tc.cuh); the weight gradient stays on CUDA cores
     long long fpartL_off;                 // workspace: this layer's own forward-statistics partial rows (deferred finalisation), -1 if not tensor-core
     long long bpartL_off;                 // workspace: this layer's BatchNorm-backward partial rows (written by a fused data-gradient epilogue)
     int nsplit;
@@ -429,9 +434,15 @@ static int resnet_backward_fused(lc_resnet* n, const float* x, int batch, const 
             const int gn = (gk + 1) % R;
             float* Gprev = Gv[s - 1][gn];
             LC_CALL(acquire(gn));
-            Conv3x3Args a{};
-            a.in = Tdy[dk]; a.wpack = packed + ca.wd_off; a.B = batch; a.out = Gprev;
-            LC_TRY(launch_conv3x3(ca.cout, ca.cin, ca.wo * 2, 1, true, false, a, st));
+            if (ca.wtsd_off >= 0) {       // parity-plane data gradient on the tensor cores
+                tc::DgradS2Args a{};
+                a.dy = Tdy[dk]; a.wtc = packed + ca.wtsd_off; a.out = Gprev; a.B = batch; a.error_flag = err_flag;
+                LC_TRY(launch_dgrad3x3s2_tc(ca.cin, ca.wo, a, st));
+            } else {
+                Conv3x3Args a{};
+                a.in = Tdy[dk]; a.wpack = packed + ca.wd_off; a.B = batch; a.out = Gprev;
+                LC_TRY(launch_conv3x3(ca.cout, ca.cin, ca.wo * 2, 1, true, false, a, st));
+            }
             LC_TRY(launch_conv1x1_dgrad(cd.cin, cd.cout, cd.wo, T3, params + cd.w_off, Gprev, batch, st));
             LC_CALL(tdy_read_done());
             gk = gn;
@@ -526,7 +537,7 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
         c.wf_off = pk; pk += ne;
         if (c.ksize == 3) { c.wd_off = pk; pk += ne; } else c.wd_off = -1;
         if (tc_eligible(c.cin, c.cout, c.wo, c.stride, c.ksize)) { c.wtf_off = pk; pk += ne; c.wtd_off = pk; pk += ne; } else { c.wtf_off = c.wtd_off = -1; }
-        if (s2_tc_eligible(c.cin, c.cout, c.wo, c.stride, c.ksize) && conv_s2_tc_enabled()) { c.wts_off = pk; pk += ne; }
+        if (s2_tc_eligible(c.cin, c.cout, c.wo, c.stride, c.ksize) && conv_s2_tc_enabled()) { c.wts_off = pk; pk += ne; c.wtsd_off = pk; pk += ne; }
         c.nsplit = c.ksize == 3 ? wgrad_nsplit(c.cin, c.cout) : k1x1Split;
         c.part_off = wp; wp += ne * std::max(c.nsplit, c.wtf_off >= 0 ? wgrad_nsplit_tc(c.cout) : 0);
     }
@@ -601,7 +612,7 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
     for (auto& c : n->convs) {
         ConvTabEntry t{};
         t.w_off = c.w_off; t.wf_off = c.wf_off; t.wd_off = c.wd_off; t.part_off = c.part_off; t.wtf_off = c.wtf_off; t.wtd_off = c.wtd_off;
-        t.wts_off1 = c.wts_off >= 0 ? c.wts_off + 1 : 0;
+        t.wts_off1 = c.wts_off >= 0 ? c.wts_off + 1 : 0; t.wtsd_off1 = c.wtsd_off >= 0 ? c.wtsd_off + 1 : 0;
         t.cout = c.cout; t.cin = c.cin; t.ntap = c.ksize * c.ksize; t.nsplit = c.nsplit; t.blk_begin = blk;
         t.nsplit_tc = c.wtf_off >= 0 ? wgrad_nsplit_tc(c.cout) : c.nsplit;
         blk += (c.cout * c.cin * t.ntap + 255) / 256;
@@ -1166,6 +1177,24 @@ int lc_conv3x3s2_tc(const float* in, const float* w_oihw, float* out, int batch,
     a.in = in; a.wtc = packed + ne; a.out = out; a.B = batch; a.error_flag = reinterpret_cast<int*>(scratch) + 8;
     if (stat_out) { LC_CHECK_ARG(gamma && beta); fill_stat(a.stat, gamma, beta, rstat, stat_out, cout, partial, reinterpret_cast<unsigned int*>(scratch)); }
     return launch_conv3x3s2_tc(cin, width_out, a, st);
+}
+// Data gradient of the same conv: dy [B][wo][wo][2*cin] -> dx [B][2*wo][2*wo][cin] (every element written).  scratch as lc_conv3x3s2_tc.
+int lc_conv3x3s2_dgrad_tc(const float* dy, const float* w_oihw, float* dx, int batch, int cin, int width_out, float* scratch, lc_stream_t stream) {
+    LC_CHECK_ARG(dy && w_oihw && dx && scratch && batch >= 1 && ((uintptr_t)scratch % 16 == 0) && s2_tc_eligible(cin, 2 * cin, width_out, 2, 3));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int cout = 2 * cin;
+    const long long ne = (long long)cout * cin * 9;
+    ConvTabEntry t{};
+    t.w_off = 0; t.wf_off = 0; t.wd_off = -1; t.wtf_off = -1; t.wtd_off = -1; t.wts_off1 = ne + 1; t.wtsd_off1 = 2 * ne + 1; t.cout = cout; t.cin = cin; t.ntap = 9;
+    t.blk_begin = 0;
+    ConvTabEntry* d_t = reinterpret_cast<ConvTabEntry*>(scratch + 64);
+    float* packed = scratch + kOpData;      // [wf | wts | wtsd]: 3 * ne floats (the scratch holds >= 2 * ne + ne * 256)
+    if (cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, st) != cudaSuccess) return LC_ERR_CUDA;
+    pack_weights_kernel<<<(int)((ne + 255) / 256), 256, 0, st>>>(d_t, 1, w_oihw, packed);
+    if (lc_launch_status() != LC_OK) return LC_ERR_CUDA;
+    tc::DgradS2Args a{};
+    a.dy = dy; a.wtc = packed + 2 * ne; a.out = dx; a.B = batch; a.error_flag = reinterpret_cast<int*>(scratch) + 8;
+    return launch_dgrad3x3s2_tc(cin, width_out, a, st);
 }
 // One launch of the tensor-core conv on pre-packed TF32 weights ([9][c/4][c][4], as left at scratch+96+2*9*c*c by lc_conv3x3_tc):
 // no packing, no statistics.  Used by bench.py to time the dominant kernel in isolation.

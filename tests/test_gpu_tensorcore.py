@@ -130,3 +130,28 @@ def test_conv3x3s2_tc_forward(lib, cin, wo, B):
     mean, var = ref.mean((0, 2, 3)), ref.var((0, 2, 3), unbiased=False)
     close(stat[2 * cout:3 * cout], mean, 1e-2, 2e-3, "mean")
     close(stat[3 * cout:], 1 / torch.sqrt(var + 1e-5), 1e-2, 1e-3, "invstd")
+
+
+@pytest.mark.parametrize("cin,wo", [(16, 16), (32, 8)])
+@pytest.mark.parametrize("B", [1, 5, 37, 128])
+def test_conv3x3s2_tc_dgrad(lib, cin, wo, B):
+    """Data gradient of the stride-2 conv on tcgen05 (nine tap groups into four parity-plane accumulators) against autograd of conv2d(stride=2)."""
+    cout, win = 2 * cin, 2 * wo
+    g = torch.Generator().manual_seed(77 * cin + B)
+    x = torch.randn(B, cin, win, win, generator=g, requires_grad=True)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * 0.1
+    dy = torch.randn(B, cout, wo, wo, generator=g)
+    dx_ref, = torch.autograd.grad(F.conv2d(x, wt, None, 2, 1), [x], dy)
+    dx_rn, = torch.autograd.grad(F.conv2d(x, tf32_round(wt), None, 2, 1), [x], tf32_round(dy))
+    dx = torch.full((B, win, win, cin), float("nan"), device="cuda")
+    scratch = torch.zeros(int(lib.lc_conv_scratch_floats(B, cin, cout, wo)), device="cuda")
+    assert lib.lc_conv3x3s2_dgrad_tc(P(dev(nhwc(dy))), P(dev(wt)), P(dx), B, cin, wo, P(scratch), st()) == 0
+    torch.cuda.synchronize()
+    assert int(scratch.view(torch.int32)[8]) == 0, "tensor-core barrier timed out"
+    got = nchw(dx).cpu()
+    assert torch.isfinite(got).all()
+    scale = dx_ref.abs().max().item()
+    err, e_rn = (got - dx_ref).abs().max().item(), (got - dx_rn).abs().max().item()
+    print(f"s2 dgrad cin={cin} wo={wo} B={B}: max|err| {err:.3e} (ref max {scale:.2f}); vs tf32-round operands {e_rn:.3e}")
+    assert err <= 4e-3 * scale, (err, scale)
+    assert e_rn <= 2e-5 * scale, (e_rn, scale)
