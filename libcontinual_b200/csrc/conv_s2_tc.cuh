@@ -20,6 +20,11 @@ struct ConvS2Args {
     const float* wtc;        // packed [9][CIN/4][COUT][4], TF32-rounded
     float* out;              // NHWC [B][WO][WO][COUT]
     BnStatArgs stat;         // stat.partial nullable: [grid][2][COUT]
+    // optional fused shortcut: the block's 1x1 / stride-2 downsample conv (resnet.py:365) reads X[n][2i][2j] = parity plane (0,0) at shift 0, which is already
+    // staged: CIN/8 more MMAs into a second accumulator, its own output and BatchNorm statistics (always finalised here: its consumer wants scale / shift)
+    const float* w1;         // nullable: packed [CIN/4][COUT][4], TF32-rounded
+    float* out1;             // NHWC [B][WO][WO][COUT]
+    BnStatArgs stat1;
     int* error_flag;
     int B;
 };
@@ -43,13 +48,15 @@ struct ConvS2Cfg {
     static constexpr int CB = N / 2;                 // output columns per epilogue work item (one per warp: quarter x column half)
     static constexpr int CPR = CB / 4;
     static constexpr int OFF_B = (A_BYTES + 127) / 128 * 128;
-    static constexpr int OFF_ROWTAB = OFF_B + B_BYTES;                       // [ROWS] pixel index of X[n][2a][2b], or -1
+    static constexpr int B1_BYTES = CH * N * 16;     // the 1x1 shortcut weights
+    static constexpr int OFF_B1 = OFF_B + B_BYTES;
+    static constexpr int OFF_ROWTAB = OFF_B1 + B1_BYTES;                     // [ROWS] pixel index of X[n][2a][2b], or -1
     static constexpr int OFF_DST = OFF_ROWTAB + (ROWS * 4 + 15) / 16 * 16;   // [128] output pixel index, or -1
-    static constexpr int OFF_PART = OFF_DST + 512;                           // [8 warps][2][CB]
-    static constexpr int OFF_RED = OFF_PART + 8 * 2 * CB * 4;               // 1024 doubles (last-CTA finaliser)
+    static constexpr int OFF_PART = OFF_DST + 512;                           // [2 outputs][8 warps][2][CB]
+    static constexpr int OFF_RED = OFF_PART + 2 * 8 * 2 * CB * 4;           // 1024 doubles (last-CTA finaliser)
     static constexpr int OFF_BAR = OFF_RED + 8192;
     static constexpr size_t SMEM_BYTES = OFF_BAR + 64;
-    static constexpr uint32_t TMEM_COLS = N;         // 32 / 64
+    static constexpr uint32_t TMEM_COLS = 2 * N;     // conv accumulator + shortcut accumulator: 64 / 128
     static_assert((CIN == 16 && WO == 16) || (CIN == 32 && WO == 8), "stride-2 tensor-core conv: stage transitions of the CIFAR ResNet");
     static_assert(8 * 32 * CB * 4 <= A_BYTES && PLANE >= 2048 && NE <= 8, "epilogue staging lives in the dead A tile");
 };
@@ -90,7 +97,15 @@ __global__ void __launch_bounds__(288) conv3x3s2_tc_kernel(ConvS2Args a) {
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (tid == 32) bulk_load(smem_u32(sB), a.wtc, (uint32_t)K::B_BYTES, bar + 1);
+    const bool sc1 = a.w1 != nullptr;
+    if (tid == 32) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar + 1)), "r"((uint32_t)(K::B_BYTES + (sc1 ? K::B1_BYTES : 0))) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sB)), "l"(a.wtc), "r"((uint32_t)K::B_BYTES),
+                     "r"(smem_u32(bar + 1)) : "memory");
+        if (sc1)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_raw + K::OFF_B1)), "l"(a.w1),
+                         "r"((uint32_t)K::B1_BYTES), "r"(smem_u32(bar + 1)) : "memory");
+    }
     __syncthreads();
 
     // ---- stage the four parity tiles: worker thread -> fixed 16-byte channel chunk j, rows r0, r0 + RSTEP, ... of every plane ----------------------
@@ -155,6 +170,12 @@ __global__ void __launch_bounds__(288) conv3x3s2_tc_kernel(ConvS2Args a) {
                 mma_tf32(tmem_base, ad, bd, idesc, (tap | kc) != 0 ? 1u : 0u);
             }
         }
+        if (sc1) {       // shortcut: parity plane (0,0), no shift
+            const uint64_t b1 = make_desc(0, K::N * 16, 128) | (uint64_t)(smem_u32(smem_raw + K::OFF_B1) >> 4);
+#pragma unroll
+            for (int kc = 0; kc < CIN / 8; ++kc)
+                mma_tf32(tmem_base + (uint32_t)K::N, a0 + (uint64_t)(2 * kc * (K::PLANE >> 4) + K::HALO), b1 + (uint64_t)(2 * kc * K::N), idesc, kc != 0 ? 1u : 0u);
+        }
         mma_commit(bar);
     }
 
@@ -174,40 +195,47 @@ __global__ void __launch_bounds__(288) conv3x3s2_tc_kernel(ConvS2Args a) {
         auto stage = [&](int p, int cc) -> float4* {
             return reinterpret_cast<float4*>(stg + (size_t)(cc >> 2) * 2048 + p * 64 + (((cc & 3) ^ ((p >> 1) & 3)) << 4));
         };
-        {
-            float v[K::CB];
-            if (K::CB == 16) tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-            else tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-            if (dst >= 0) {
-#pragma unroll
-                for (int cc = 0; cc < K::CPR; ++cc) *stage(rank, cc) = make_float4(v[cc * 4], v[cc * 4 + 1], v[cc * 4 + 2], v[cc * 4 + 3]);
-            }
-        }
-        __syncwarp();
         const int c = lane % K::CPR;
-        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
 #pragma unroll
-        for (int kk = 0; kk < K::CPR; ++kk) {
-            const int p = kk * (32 / K::CPR) + lane / K::CPR;
-            if (p < nvalid) {
-                const float4 x = *stage(p, c);
-                *reinterpret_cast<float4*>(a.out + (size_t)(dst_first + p) * K::N + c0 + c * 4) = x;
-                s1.x += x.x; s1.y += x.y; s1.z += x.z; s1.w += x.w;
-                s2.x = fmaf(x.x, x.x, s2.x); s2.y = fmaf(x.y, x.y, s2.y); s2.z = fmaf(x.z, x.z, s2.z); s2.w = fmaf(x.w, x.w, s2.w);
-            }
-        }
-        if (stats) {
+        for (int o = 0; o < 2; ++o) {            // o = 0: the 3x3 conv; o = 1: the fused 1x1 shortcut
+            if (o == 1 && !sc1) break;
+            float* outp = o == 0 ? a.out : a.out1;
+            const bool st_o = o == 0 ? stats : (a.stat1.partial != nullptr);
+            {
+                float v[K::CB];
+                if (K::CB == 16) tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(o * K::N + c0), v);
+                else tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(o * K::N + c0), v);
+                if (dst >= 0) {
 #pragma unroll
-            for (int off = K::CPR; off < 32; off <<= 1) {
-                s1.x += __shfl_xor_sync(0xffffffffu, s1.x, off); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, off);
-                s1.z += __shfl_xor_sync(0xffffffffu, s1.z, off); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, off);
-                s2.x += __shfl_xor_sync(0xffffffffu, s2.x, off); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, off);
-                s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
+                    for (int cc = 0; cc < K::CPR; ++cc) *stage(rank, cc) = make_float4(v[cc * 4], v[cc * 4 + 1], v[cc * 4 + 2], v[cc * 4 + 3]);
+                }
             }
-            if (lane < K::CPR) {
-                float* sp = s_part + (size_t)warp * 2 * K::CB + c * 4;
-                *reinterpret_cast<float4*>(sp) = s1; *reinterpret_cast<float4*>(sp + K::CB) = s2;
+            __syncwarp();
+            float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll
+            for (int kk = 0; kk < K::CPR; ++kk) {
+                const int p = kk * (32 / K::CPR) + lane / K::CPR;
+                if (p < nvalid) {
+                    const float4 x = *stage(p, c);
+                    *reinterpret_cast<float4*>(outp + (size_t)(dst_first + p) * K::N + c0 + c * 4) = x;
+                    s1.x += x.x; s1.y += x.y; s1.z += x.z; s1.w += x.w;
+                    s2.x = fmaf(x.x, x.x, s2.x); s2.y = fmaf(x.y, x.y, s2.y); s2.z = fmaf(x.z, x.z, s2.z); s2.w = fmaf(x.w, x.w, s2.w);
+                }
             }
+            if (st_o) {
+#pragma unroll
+                for (int off = K::CPR; off < 32; off <<= 1) {
+                    s1.x += __shfl_xor_sync(0xffffffffu, s1.x, off); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, off);
+                    s1.z += __shfl_xor_sync(0xffffffffu, s1.z, off); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, off);
+                    s2.x += __shfl_xor_sync(0xffffffffu, s2.x, off); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, off);
+                    s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
+                }
+                if (lane < K::CPR) {
+                    float* sp = s_part + (size_t)(o * 8 + warp) * 2 * K::CB + c * 4;
+                    *reinterpret_cast<float4*>(sp) = s1; *reinterpret_cast<float4*>(sp + K::CB) = s2;
+                }
+            }
+            __syncwarp();      // the second output reuses this warp's staging block
         }
     }
     if (!done && lane == 0 && a.error_flag != nullptr) atomicExch(a.error_flag, 1);
@@ -215,16 +243,26 @@ __global__ void __launch_bounds__(288) conv3x3s2_tc_kernel(ConvS2Args a) {
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, K::TMEM_COLS);
 
-    if (stats) {
+    const bool stats1 = sc1 && a.stat1.partial != nullptr;
+    if (stats || stats1) {
         if (tid < 2 * K::N) {
             const int stat = tid / K::N, ch = tid % K::N, g = ch / K::CB;
-            float tsum = 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) tsum += s_part[(size_t)((g * 4 + q) * 2 + stat) * K::CB + (ch % K::CB)];
-            a.stat.partial[((size_t)blockIdx.x * 2 + stat) * K::N + ch] = tsum;
+            for (int o = 0; o < 2; ++o) {
+                if (o == 0 ? !stats : !stats1) continue;
+                float tsum = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tsum += s_part[(size_t)((o * 8 + g * 4 + q) * 2 + stat) * K::CB + (ch % K::CB)];
+                (o == 0 ? a.stat.partial : a.stat1.partial)[((size_t)blockIdx.x * 2 + stat) * K::N + ch] = tsum;
+            }
         }
-        if (a.stat.defer) return;
-        if (last_block_done(a.stat.counter, gridDim.x)) bn_finalize_last_block<K::N, 256>(a.stat, (int)gridDim.x, (double)a.B * WO * WO, s_red);
+        const bool fin0 = stats && !a.stat.defer;
+        if (!fin0 && !stats1) return;       // deferred: consumers reduce the partial rows themselves (BnLazy)
+        if (last_block_done(stats1 ? a.stat1.counter : a.stat.counter, gridDim.x)) {
+            if (fin0) bn_finalize_last_block<K::N, 256>(a.stat, (int)gridDim.x, (double)a.B * WO * WO, s_red);
+            if (fin0 && stats1) __syncthreads();
+            if (stats1) bn_finalize_last_block<K::N, 256>(a.stat1, (int)gridDim.x, (double)a.B * WO * WO, s_red);
+        }
     }
 }
 

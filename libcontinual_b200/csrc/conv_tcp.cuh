@@ -278,6 +278,8 @@ __global__ void __launch_bounds__(608, 1) conv3x3_tcp_kernel(ConvTcArgs a) {
                         } else if (pro) {
                             v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f); v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
                             v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f); v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+                            // MODE 2 without a residual operand: the producer's relu(bn(y)) is itself wanted in HBM (the stem's activation = block 0's residual)
+                            if (RES && a.pro_out != nullptr && r >= K::HALO && r < K::HALO + nT * 128) *reinterpret_cast<float4*>(a.pro_out + (size_t)px * C + j * 4) = v;
                         }
                         v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
                     }

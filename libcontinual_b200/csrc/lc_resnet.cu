@@ -538,6 +538,8 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
         if (c.ksize == 3) { c.wd_off = pk; pk += ne; } else c.wd_off = -1;
         if (tc_eligible(c.cin, c.cout, c.wo, c.stride, c.ksize)) { c.wtf_off = pk; pk += ne; c.wtd_off = pk; pk += ne; } else { c.wtf_off = c.wtd_off = -1; }
         if (s2_tc_eligible(c.cin, c.cout, c.wo, c.stride, c.ksize) && conv_s2_tc_enabled()) { c.wts_off = pk; pk += ne; c.wtsd_off = pk; pk += ne; }
+        // the 1x1 / stride-2 shortcut of the same blocks: forward fused into conv3x3s2_tc_kernel (its operand is the staged parity plane (0,0))
+        if (c.ksize == 1 && c.stride == 2 && conv_s2_tc_enabled() && s2_tc_eligible(c.cin, c.cout, c.wo, 2, 3)) { c.wts_off = pk; pk += ne; }
         c.nsplit = c.ksize == 3 ? wgrad_nsplit(c.cin, c.cout) : k1x1Split;
         c.part_off = wp; wp += ne * std::max(c.nsplit, c.wtf_off >= 0 ? wgrad_nsplit_tc(c.cout) : 0);
     }
@@ -575,7 +577,7 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
     }
     for (auto& c : n->convs)
         c.fpartL_off = c.wtf_off >= 0 ? take(tc::conv_tc_tiles((int)B, c.wo) * 2 * c.cout)
-                                      : (c.wts_off >= 0 ? take((long long)tc::conv_s2_tc_grid(B, c.wo) * 2 * c.cout) : -1);
+                                      : (c.wts_off >= 0 && c.ksize == 3 ? take((long long)tc::conv_s2_tc_grid(B, c.wo) * 2 * c.cout) : -1);
     for (auto& c : n->convs) c.bpartL_off = c.ksize == 3 ? take(tc::conv_tc_tiles((int)B, c.wo) * 2 * c.cout) : -1;
     n->ws_floats = o;
     {
@@ -755,6 +757,13 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
         Conv3x3Args a{};
         a.in = x; a.wpack = packed + c.wf_off; a.out = ws + c.y_off; a.stat = stat_for(c); a.B = batch;
         LC_TRY(launch_conv3x3(c.cin, c.cout, c.wo, 1, false, true, a, st));
+    }
+    // the stem's relu(bn(y)) is evaluated (and stored to a0: it is block 0's residual) by block 0's conv_a prologue when that conv runs the persistent
+    // kernel (conv_tcp.cuh MODE 2 without a residual operand); otherwise by bn_act_fwd_kernel
+    const bool stem_fused = n->mode == 1 && n->fuse_block_out && n->persist && !n->blocks.empty() &&
+                            n->convs[n->blocks[0].conv_a].wtf_off >= 0 && tcp_eligible(n->convs[n->blocks[0].conv_a].cout, n->convs[n->blocks[0].conv_a].wo);
+    if (!stem_fused) {
+        const ConvL& c = n->convs[0];
         BnActArgs e{};
         e.y = ws + c.y_off; e.scale = ws + c.aff_off; e.shift = ws + c.aff_off + c.cout; e.out = ws + n->off_a0;
         e.n4 = (long long)batch * c.wo * c.wo * c.cout / 4; e.C = c.cout;
@@ -779,6 +788,7 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
         const BlockL& bl = n->blocks[bi];
         const ConvL& ca = n->convs[bl.conv_a];
         const ConvL& cb = n->convs[bl.conv_b];
+        bool shortcut_done = false;
         if (n->mode == 1 && ca.wtf_off >= 0) {
             tc::ConvTcArgs a{};
             a.wtc = packed + ca.wtf_off; a.out = ws + ca.y_off; a.stat = stat_for(ca); a.B = batch; a.error_flag = err_flag;
@@ -788,6 +798,10 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
                 a.pro_res = pend_res; a.pro_out = ws + pend->out_off;
                 pend = nullptr;
                 LC_TRY(launch_conv3x3_tc_res(ca.cin, ca.wo, a, st, persist));
+            } else if (bi == 0 && stem_fused) {
+                const ConvL& c0 = n->convs[0];
+                a.in = ws + c0.y_off; a.pro_scale = ws + c0.aff_off; a.pro_shift = ws + c0.aff_off + c0.cout; a.pro_out = ws + n->off_a0;
+                LC_TRY(launch_conv3x3_tc_res(ca.cin, ca.wo, a, st, true));
             } else {
                 a.in = cur;
                 LC_TRY(launch_conv3x3_tc(ca.cin, ca.wo, a, st, persist));
@@ -796,6 +810,13 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
             if (pend != nullptr) LC_TRY(flush_pending());
             tc::ConvS2Args a{};
             a.in = cur; a.wtc = packed + ca.wts_off; a.out = ws + ca.y_off; a.stat = stat_for(ca); a.B = batch; a.error_flag = err_flag;
+            // the block's 1x1 shortcut conv rides along (training: only with deferred statistics for conv_a — the two layers must not share the eager
+            // partial buffer)
+            if (bl.conv_d >= 0 && n->convs[bl.conv_d].wts_off >= 0 && (!train || (lazy && ca.fpartL_off >= 0))) {
+                const ConvL& cd = n->convs[bl.conv_d];
+                a.w1 = packed + cd.wts_off; a.out1 = ws + cd.y_off; a.stat1 = stat_for(cd);
+                shortcut_done = true;
+            }
             LC_TRY(launch_conv3x3s2_tc(ca.cin, ca.wo, a, st));
         } else {
             if (pend != nullptr) LC_TRY(flush_pending());
@@ -826,9 +847,11 @@ int lc_resnet_forward(lc_resnet* n, const float* x, int batch, const float* para
             e.n4 = (long long)batch * cb.wo * cb.wo * cb.cout / 4; e.C = cb.cout; e.lazy = lazy_of(cb);
             if (bl.conv_d >= 0) {
                 const ConvL& cd = n->convs[bl.conv_d];
-                Conv1x1Args a{};
-                a.in = cur; a.w = packed + cd.wf_off; a.out = ws + cd.y_off; a.stat = stat_for(cd); a.B = batch;
-                LC_TRY(launch_conv1x1_fwd(cd.cin, cd.cout, cd.wo, a, st));
+                if (!shortcut_done) {
+                    Conv1x1Args a{};
+                    a.in = cur; a.w = packed + cd.wf_off; a.out = ws + cd.y_off; a.stat = stat_for(cd); a.B = batch;
+                    LC_TRY(launch_conv1x1_fwd(cd.cin, cd.cout, cd.wo, a, st));
+                }
                 e.res = ws + cd.y_off; e.res_scale = ws + cd.aff_off; e.res_shift = ws + cd.aff_off + cd.cout;
             } else {
                 e.res = cur;
