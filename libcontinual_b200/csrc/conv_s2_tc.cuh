@@ -298,6 +298,10 @@ struct DgradS2Args {
     const float* dy;         // NHWC [B][WO][WO][COUT]
     const float* wtc;        // packed [9][COUT/4][CIN][4] (tap NOT flipped), TF32-rounded
     float* out;              // NHWC [B][2*WO][2*WO][CIN]  (every element written)
+    // optional fused data gradient of the block's 1x1 / stride-2 shortcut conv: dX[n][2i][2j] += W1^T dY1[n][i][j], i.e. KC/8 more MMAs on a second staged
+    // tile into the accumulator of parity plane (0,0)
+    const float* dy1;        // nullable: NHWC [B][WO][WO][COUT]
+    const float* w1;         // packed [COUT/4][CIN][4], TF32-rounded
     int* error_flag;
     int B;
 };
@@ -322,7 +326,12 @@ struct DgradS2Cfg {
     static constexpr int CPR = PAIRB / 16;           // 16-byte chunks per pair: 8 / 16
     static constexpr int STG_WARP = 32 * PAIRB;      // 4 KB / 8 KB
     static constexpr int OFF_B = (A_BYTES + 127) / 128 * 128;
-    static constexpr int OFF_STG = (OFF_B + B_BYTES + 127) / 128 * 128;
+    static constexpr int A1_PLANE = 128 * 16;        // shortcut gradient tile: 128 rows, no halo
+    static constexpr int A1_BYTES = CH * A1_PLANE;
+    static constexpr int B1_BYTES = CH * CIN * 16;
+    static constexpr int OFF_A1 = (OFF_B + B_BYTES + 127) / 128 * 128;
+    static constexpr int OFF_B1 = OFF_A1 + A1_BYTES;
+    static constexpr int OFF_STG = (OFF_B1 + B1_BYTES + 127) / 128 * 128;
     static constexpr int OFF_ROWTAB = OFF_STG + 8 * STG_WARP;                // [ROWS] dY pixel index or -1
     static constexpr int OFF_DST = OFF_ROWTAB + (ROWS * 4 + 15) / 16 * 16;   // [128] dX pixel index of (2a, 2b) or -1
     static constexpr int OFF_DSTW = OFF_DST + 512;                           // [8 warps][32] compacted per warp
@@ -368,13 +377,32 @@ __global__ void __launch_bounds__(288) dgrad3x3s2_tc_kernel(DgradS2Args a) {
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (tid == 32) bulk_load(smem_u32(sB), a.wtc, (uint32_t)K::B_BYTES, bar + 1);
+    const bool sc1 = a.dy1 != nullptr;
+    if (tid == 32) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar + 1)), "r"((uint32_t)(K::B_BYTES + (sc1 ? K::B1_BYTES : 0))) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sB)), "l"(a.wtc), "r"((uint32_t)K::B_BYTES),
+                     "r"(smem_u32(bar + 1)) : "memory");
+        if (sc1)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_raw + K::OFF_B1)), "l"(a.w1),
+                         "r"((uint32_t)K::B1_BYTES), "r"(smem_u32(bar + 1)) : "memory");
+    }
     __syncthreads();
 
     const int j = tid % K::CH, r0 = tid / K::CH;
     if (worker) {
         uint32_t validmask = 0;
         const uint32_t dstp = smem_u32(sA) + (uint32_t)(j * K::PLANE);
+        if (sc1) {       // shortcut gradient tile: rows [0, 128) only (the 1x1 conv has no taps to shift to)
+            const uint32_t dst1 = smem_u32(smem_raw + K::OFF_A1) + (uint32_t)(j * K::A1_PLANE);
+#pragma unroll
+            for (int i = 0; i < (128 + K::RSTEP - 1) / K::RSTEP; ++i) {
+                const int r = r0 + i * K::RSTEP;
+                if (r < 128) {
+                    const int src = s_rowsrc[r];
+                    cp_async16(dst1 + (uint32_t)r * 16, src >= 0 ? a.dy1 + (size_t)src * K::KC + j * 4 : a.dy1, src >= 0 ? 16u : 0u);
+                }
+            }
+        }
 #pragma unroll
         for (int i = 0; i < K::NE; ++i) {
             const int r = r0 + i * K::RSTEP;
@@ -394,6 +422,18 @@ __global__ void __launch_bounds__(288) dgrad3x3s2_tc_kernel(DgradS2Args a) {
                 float4 v = *p4;
                 v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
                 *p4 = v;
+            }
+        }
+        if (sc1) {
+#pragma unroll
+            for (int i = 0; i < (128 + K::RSTEP - 1) / K::RSTEP; ++i) {
+                const int r = r0 + i * K::RSTEP;
+                if (r < 128 && s_rowsrc[r] >= 0) {
+                    float4* p4 = reinterpret_cast<float4*>(smem_raw + K::OFF_A1 + (size_t)j * K::A1_PLANE + (size_t)r * 16);
+                    float4 v = *p4;
+                    v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
+                    *p4 = v;
+                }
             }
         }
     }
@@ -419,6 +459,13 @@ __global__ void __launch_bounds__(288) dgrad3x3s2_tc_kernel(DgradS2Args a) {
                 const uint64_t bd = b0 + (uint64_t)(tap * (K::BTAP >> 4) + 2 * kc * CIN);
                 mma_tf32(tmem_base + (uint32_t)(par * CIN), ad, bd, idesc, (first && kc == 0) ? 0u : 1u);
             }
+        }
+        if (sc1) {       // shortcut: accumulate into parity plane (0,0) (after its own tap above)
+            const uint64_t a1 = make_desc(0, K::A1_PLANE, 128) | (uint64_t)(smem_u32(smem_raw + K::OFF_A1) >> 4);
+            const uint64_t b1 = make_desc(0, CIN * 16, 128) | (uint64_t)(smem_u32(smem_raw + K::OFF_B1) >> 4);
+#pragma unroll
+            for (int kc = 0; kc < K::KC / 8; ++kc)
+                mma_tf32(tmem_base, a1 + (uint64_t)(2 * kc * (K::A1_PLANE >> 4)), b1 + (uint64_t)(2 * kc * CIN), idesc, 1u);
         }
         mma_commit(bar);
     }

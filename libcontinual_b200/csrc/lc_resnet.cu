@@ -434,16 +434,18 @@ static int resnet_backward_fused(lc_resnet* n, const float* x, int batch, const 
             const int gn = (gk + 1) % R;
             float* Gprev = Gv[s - 1][gn];
             LC_CALL(acquire(gn));
+            bool shortcut_dgrad_done = false;
             if (ca.wtsd_off >= 0) {       // parity-plane data gradient on the tensor cores
                 tc::DgradS2Args a{};
                 a.dy = Tdy[dk]; a.wtc = packed + ca.wtsd_off; a.out = Gprev; a.B = batch; a.error_flag = err_flag;
+                if (cd.wtsd_off >= 0) { a.dy1 = T3; a.w1 = packed + cd.wtsd_off; shortcut_dgrad_done = true; }      // the shortcut's data gradient rides along
                 LC_TRY(launch_dgrad3x3s2_tc(ca.cin, ca.wo, a, st));
             } else {
                 Conv3x3Args a{};
                 a.in = Tdy[dk]; a.wpack = packed + ca.wd_off; a.B = batch; a.out = Gprev;
                 LC_TRY(launch_conv3x3(ca.cout, ca.cin, ca.wo * 2, 1, true, false, a, st));
             }
-            LC_TRY(launch_conv1x1_dgrad(cd.cin, cd.cout, cd.wo, T3, params + cd.w_off, Gprev, batch, st));
+            if (!shortcut_dgrad_done) LC_TRY(launch_conv1x1_dgrad(cd.cin, cd.cout, cd.wo, T3, params + cd.w_off, Gprev, batch, st));
             LC_CALL(tdy_read_done());
             gk = gn;
             g_fused = false;
@@ -539,7 +541,7 @@ int lc_resnet_create(int depth, int in_ch, int img, int max_batch, lc_resnet** o
         if (tc_eligible(c.cin, c.cout, c.wo, c.stride, c.ksize)) { c.wtf_off = pk; pk += ne; c.wtd_off = pk; pk += ne; } else { c.wtf_off = c.wtd_off = -1; }
         if (s2_tc_eligible(c.cin, c.cout, c.wo, c.stride, c.ksize) && conv_s2_tc_enabled()) { c.wts_off = pk; pk += ne; c.wtsd_off = pk; pk += ne; }
         // the 1x1 / stride-2 shortcut of the same blocks: forward fused into conv3x3s2_tc_kernel (its operand is the staged parity plane (0,0))
-        if (c.ksize == 1 && c.stride == 2 && conv_s2_tc_enabled() && s2_tc_eligible(c.cin, c.cout, c.wo, 2, 3)) { c.wts_off = pk; pk += ne; }
+        if (c.ksize == 1 && c.stride == 2 && conv_s2_tc_enabled() && s2_tc_eligible(c.cin, c.cout, c.wo, 2, 3)) { c.wts_off = pk; pk += ne; c.wtsd_off = pk; pk += ne; }
         c.nsplit = c.ksize == 3 ? wgrad_nsplit(c.cin, c.cout) : k1x1Split;
         c.part_off = wp; wp += ne * std::max(c.nsplit, c.wtf_off >= 0 ? wgrad_nsplit_tc(c.cout) : 0);
     }
