@@ -44,10 +44,17 @@ __global__ void __launch_bounds__(256) ewc_penalty_grad_kernel(const float* thet
     }
     if (threadIdx.x == 0) partial[blockIdx.x] = s_red[0];
     if (last_block_done(counter, gridDim.x)) {
+        // the per-block partials in parallel (one L2 round trip), then a fixed-order tree: a serial loop over ~300 dependent loads was 2/3 of this kernel
+        double t = 0.0;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += __ldcg(partial + b);
+        s_red[threadIdx.x] = t;
+        __syncthreads();
+        for (int off = 128; off > 0; off >>= 1) {
+            if (threadIdx.x < off) s_red[threadIdx.x] += s_red[threadIdx.x + off];
+            __syncthreads();
+        }
         if (threadIdx.x == 0) {
-            double t = 0.0;
-            for (unsigned int b = 0; b < gridDim.x; ++b) t += __ldcg(partial + b);
-            const float pen = (float)(0.5 * t);
+            const float pen = (float)(0.5 * s_red[0]);
             scal[4] = pen;
             scal[0] += lam * pen;
         }
