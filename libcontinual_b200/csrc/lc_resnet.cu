@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <cstdio>
 #include <new>
 #include <vector>
 
@@ -144,7 +145,18 @@ int wgrad_nsplit(int cin, int cout) {
     if (cout == 32) return 128;
     return 64;      // cout 64 (CUDA-core kernel: x CIN_SPLIT CTAs)
 }
-int wgrad_nsplit_tc(int c) { return c == 64 ? 50 : (c == 32 ? 148 : 296); }
+int wgrad_nsplit_tc(int c) {
+    // CTAs (= split-K partials) per layer.  Measured inside the step (tools/step_breakdown.py), where these kernels share the SMs with the data-gradient
+    // chain — not alone, where more CTAs always win: LC_WGRAD_NSPLIT="n16,n32,n64" overrides for A/B runs.
+    static int ns[3] = {0, 0, 0};
+    if (ns[0] == 0) {
+        ns[0] = 296; ns[1] = 148; ns[2] = 34;
+        const char* e = getenv("LC_WGRAD_NSPLIT");
+        int a = 0, b = 0, d = 0;
+        if (e != nullptr && sscanf(e, "%d,%d,%d", &a, &b, &d) == 3 && a >= 1 && a <= 296 && b >= 1 && b <= 148 && d >= 1 && d <= 100) { ns[0] = a; ns[1] = b; ns[2] = d; }
+    }
+    return c == 64 ? ns[2] : (c == 32 ? ns[1] : ns[0]);
+}
 int launch_wgrad3x3_tc(int c, int wo, const tc::WgradTcArgs& a, int nsplit, cudaStream_t st) {
     if (c == 16 && wo == 32) return tc::wgrad_tc_launch<16, 32>(a, nsplit, st);
     if (c == 32 && wo == 16) return tc::wgrad_tc_launch<32, 16>(a, nsplit, st);
