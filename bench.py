@@ -13,7 +13,11 @@ backward to the prompt rows + clip + Adam), BF16 tcgen05 GEMMs with fp32 accumul
 value : whole-job images/s, inputs resident in HBM, one CUDA-graph replay per step, timed with CUDA events, max over ranks.
 e2e   : the same metric through the plugin surface a reference Trainer uses (observe -> zero_grad -> backward -> step ->
         loss.item()) with batches in pinned HOST memory: H2D copy and the D2H metric reads are inside the timed region.
-N > 1 : one process per GPU (torchrun), per-GPU batch fixed at 128 (weak scaling), flat-gradient NCCL all-reduce per step.
+N > 1 : one process per GPU (torchrun), per-GPU batch fixed at 128 (weak scaling), flat-gradient NCCL all-reduce per step; `strong` in the same line =
+        the global batch of the config sharded over the ranks (the reference's `batch_size // n_gpu`, trainer.py:238).
+default run (no --only): the headline iCaRL line carries `workloads.{ewc, l2p, inflora, lwf18_gpm}` — BASELINE.json's other four configs (C1 at bs 128,
+        C3, C4 at bs 128 per GPU, C5 = LwF + GPM projection on ResNet18 @64^2 at bs 256 per GPU), each a full line of its own (value / e2e / roofline /
+        cpu_baseline / ref_gpu / strong) measured by the same command.
 --impl reference : the oracle port (oracle/port.py, PyTorch CPU, all host threads) on the same workload, rank 0 only.
 """
 from __future__ import annotations
@@ -1020,14 +1024,30 @@ def main():
     ctx = Ctx()
     line = run_ours(args, ctx, args.workload)
     if args.workload == "icarl" and not args.only:
-        # the two workloads north_star's >= 1.3x target names, timed by the same command and attached to the headline line
+        # the two workloads north_star's >= 1.3x target names (EWC-ResNet32, L2P-ViT-B/16) and BASELINE's remaining configs (C4 InfLoRA ViT-B/16, C5 LwF +
+        # GPM projection on ResNet18 @64^2), timed by the same command and attached to the headline line.  A failure of an attached workload is recorded
+        # in its slot and never costs the headline line.
         extra = {}
-        for w in ("ewc", "l2p"):
+        for w in ("ewc", "l2p", "inflora", "lwf18_gpm"):
             gc.collect(); torch.cuda.empty_cache()
             sub = argparse.Namespace(**vars(args))
-            if w == "l2p":
+            if w != "ewc":
                 sub.steps, sub.warmup = max(5, min(args.steps, 40)), max(3, min(args.warmup, 5))
-            extra[w] = run_ours(sub, ctx, w)
+            GPM_PROJECT = w == "lwf18_gpm"
+            err = None
+            try:
+                extra[w] = run_ours(sub, ctx, "lwf18" if w == "lwf18_gpm" else w)
+            except Exception as e:          # noqa: BLE001
+                err = f"{type(e).__name__}: {e}"[:400]
+            if ctx.world > 1:                # the ranks agree on the outcome before anyone moves on
+                import torch.distributed as dist
+                flag = torch.tensor([1.0 if err else 0.0], device=ctx.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                if flag.item() > 0 and err is None:
+                    err = "failed on another rank"
+            if err is not None:
+                extra[w] = {"error": err}
+            GPM_PROJECT = False
         if line is not None:
             line["workloads"] = extra
     if line is not None:

@@ -34,20 +34,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "lc_b200.h"))
-    objs = []
+    objs, jobs = [], []
     for src in SOURCES:
         sp = os.path.join(CSRC, src)
         if not os.path.exists(sp):
             continue
         obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
         if force or _stale(obj, [sp] + headers):
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", obj]
-            r = subprocess.run(cmd, capture_output=True, text=True)
+            jobs.append([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", obj])
+        objs.append(obj)
+    if jobs:                                    # the translation units are independent: one nvcc process each, side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+            results = list(ex.map(lambda c: (c, subprocess.run(c, capture_output=True, text=True)), jobs))
+        for cmd, r in results:
             if verbose:
                 print(r.stderr)
             if r.returncode != 0:
                 raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-        objs.append(obj)
     if force or _stale(LIB, objs):
         cmd = [_nvcc(), "-shared", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(256) lucir_loss_kernel(LucirArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// L2P prompt selection (single CTA: B <= 1024 samples, pool <= 32 prompts, D = embed dim)
+// L2P prompt selection: the B x P cosine similarities on B CTAs, then one CTA for the vote / pull constraint (B <= 4096 samples, pool <= 32 prompts,
+// D = embed dim)
 // Tie rules (the reference leaves them to torch.topk): per-sample top-k by (value desc, index asc); majority top-k over the
 // histogram by (count desc, id asc) after the reference's "pad with ids[0] / count 0" step.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -196,17 +197,40 @@ struct L2pArgs {
     int B, P, D, top_k;
 };
 
-__global__ void __launch_bounds__(256) l2p_select_kernel(L2pArgs a) {
+// (1) similarities: one CTA per sample, warp w owns prompts w, w + 8, ...  (inverse norms recomputed per warp: 2 x D floats out of L1 / L2)
+__global__ void __launch_bounds__(256) l2p_sim_kernel(L2pArgs a) {
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* q = a.query + (size_t)b * a.D;
+    float s = 0.f;
+    for (int j = lane; j < a.D; j += 32) s = fmaf(q[j], q[j], s);
+    s = warp_sum(s);
+    const float qn = 1.f / fmaxf(sqrtf(s), 1e-12f);
+    for (int p = warp; p < a.P; p += 8) {
+        const float* k = a.key + (size_t)p * a.D;
+        float n2 = 0.f;
+        for (int j = lane; j < a.D; j += 32) n2 = fmaf(k[j], k[j], n2);
+        n2 = warp_sum(n2);
+        const float kn = 1.f / fmaxf(sqrtf(n2), 1e-12f);
+        float d = 0.f;
+        for (int j = lane; j < a.D; j += 32) d = fmaf(q[j] * qn, k[j] * kn, d);
+        d = warp_sum(d);
+        if (lane == 0) a.sim[(size_t)b * a.P + p] = d;
+    }
+}
+
+// (2) vote + pull constraint: single CTA of kL2pNT threads over the [B][P] similarities
+constexpr int kL2pNT = 768, kL2pNW = kL2pNT / 32;
+__global__ void __launch_bounds__(kL2pNT) l2p_select_kernel(L2pArgs a) {
     extern __shared__ float sm[];
     float* s_knorm = sm;                  // [P] inverse norms
     float* s_qn = sm + 32;                // [B] inverse norms
     int* s_hist = reinterpret_cast<int*>(sm + 32 + a.B);     // [32]
     int* s_ids = s_hist + 32;             // [32]
-    float* s_part = reinterpret_cast<float*>(s_ids + 32);    // [8] per-warp partial sums
+    float* s_part = reinterpret_cast<float*>(s_ids + 32);    // [32] per-warp partial sums
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 32) s_hist[tid] = 0;
     // inverse norms: one warp per row
-    for (int r = warp; r < a.P + a.B; r += 8) {
+    for (int r = warp; r < a.P + a.B; r += kL2pNW) {
         const float* x = r < a.P ? a.key + (size_t)r * a.D : a.query + (size_t)(r - a.P) * a.D;
         float s = 0.f;
         for (int j = lane; j < a.D; j += 32) s = fmaf(x[j], x[j], s);
@@ -214,19 +238,8 @@ __global__ void __launch_bounds__(256) l2p_select_kernel(L2pArgs a) {
         if (lane == 0) { const float inv = 1.f / fmaxf(sqrtf(s), 1e-12f); if (r < a.P) s_knorm[r] = inv; else s_qn[r - a.P] = inv; }
     }
     __syncthreads();
-    // similarities: one warp per (b, p) pair
-    for (int idx = warp; idx < a.B * a.P; idx += 8) {
-        const int b = idx / a.P, p = idx % a.P;
-        const float* q = a.query + (size_t)b * a.D;
-        const float* k = a.key + (size_t)p * a.D;
-        float s = 0.f;
-        for (int j = lane; j < a.D; j += 32) s = fmaf(q[j] * s_qn[b], k[j] * s_knorm[p], s);
-        s = warp_sum(s);
-        if (lane == 0) a.sim[idx] = s;
-    }
-    __syncthreads();
     // per-sample top-k -> histogram (integer atomics: order-independent)
-    for (int b = tid; b < a.B; b += 256) {
+    for (int b = tid; b < a.B; b += kL2pNT) {
         const float* s = a.sim + (size_t)b * a.P;
         float last = CUDART_INF_F; int last_idx = -1;
         for (int t = 0; t < a.top_k; ++t) {
@@ -258,10 +271,10 @@ __global__ void __launch_bounds__(256) l2p_select_kernel(L2pArgs a) {
         }
         for (int p = 0; p < a.P; ++p) a.hist[p] = s_hist[p];
     }
-    __syncthreads();
-    // qsum[j] = sum_b qhat_b[j]  (fixed order) ; reduce_sim = sum_{t} khat_{id_t} . qsum / B
-    for (int j = tid; j < a.D; j += 256) {
+    // qsum[j] = sum_b qhat_b[j]  (fixed order; the loads of a column are independent of each other) ; reduce_sim = sum_{t} khat_{id_t} . qsum / B
+    for (int j = tid; j < a.D; j += kL2pNT) {
         float s = 0.f;
+#pragma unroll 8
         for (int b = 0; b < a.B; ++b) s = fmaf(a.query[(size_t)b * a.D + j], s_qn[b], s);
         a.qsum[j] = s;
     }
@@ -269,19 +282,19 @@ __global__ void __launch_bounds__(256) l2p_select_kernel(L2pArgs a) {
     float part = 0.f;
     for (int t = 0; t < a.top_k; ++t) {
         const int p = s_ids[t];
-        for (int j = tid; j < a.D; j += 256) part = fmaf(a.key[(size_t)p * a.D + j] * s_knorm[p], a.qsum[j], part);
+        for (int j = tid; j < a.D; j += kL2pNT) part = fmaf(a.key[(size_t)p * a.D + j] * s_knorm[p], a.qsum[j], part);
     }
     part = warp_sum(part);
     if (lane == 0) s_part[warp] = part;
     __syncthreads();
     if (tid == 0) {
         float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += s_part[w];
+        for (int w = 0; w < kL2pNW; ++w) t += s_part[w];
         *a.reduce_sim = t / (float)a.B;
     }
     // d(reduce_sim)/d(key_p) = mult_p * (v - khat (khat . v)) / ||k||,  v = qsum / B,  mult_p = #times p appears in ids
     if (a.dkey != nullptr) {
-        for (int p = warp; p < a.P; p += 8) {
+        for (int p = warp; p < a.P; p += kL2pNW) {
             int mult = 0;
             for (int t = 0; t < a.top_k; ++t) mult += (s_ids[t] == p);
             const float* k = a.key + (size_t)p * a.D;

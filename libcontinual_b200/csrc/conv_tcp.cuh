@@ -48,6 +48,20 @@ struct ConvTcpCfg {
     static constexpr int EPI_WARP = 32 * ROWB;       // epilogue staging per warp
     static constexpr int NTHREADS = 608;             // 8 transform + 8 epilogue warps (one warp per scheduler cannot hide its own latencies) + 2 issuers + loader
     static constexpr int NTRANS = 256;
+    // Two measured-and-rejected variants stay behind compile-time switches (profiles/r3j_tcp_variants.txt, r3j_step_ab.txt): neither changes the kernel timed
+    // alone on cold inputs (8.5 us: it is bound by the arrival rate of its chunks), both cost ~0.7 us per launch inside the step, where the inputs come
+    // out of L2 and the staged -> MMA latency is exposed.
+#ifdef LC_TCP_TWO_GROUPS
+    static constexpr int NGROUP = 2;                // transform warps 0-3 stage the even chunks, 4-7 the odd ones
+#else
+    static constexpr int NGROUP = 1;                // all 8 transform warps work on the same chunk
+#endif
+    static constexpr int GTHREADS = NTRANS / NGROUP;
+#ifdef LC_TCP_ELECTED_ARRIVE
+    static constexpr int NARRIVE = GTHREADS / 32;   // one elected arrival per transform warp (the elected lane's serial arrivals sit on the critical path)
+#else
+    static constexpr int NARRIVE = GTHREADS;        // every transform thread arrives on empty[] / staged[] right behind its own proxy fence
+#endif
     static constexpr int OFF_B = (A_BYTES + 127) / 128 * 128;
     static constexpr int OFF_RING = (OFF_B + B_BYTES + 127) / 128 * 128;
     static constexpr int OFF_EPI = OFF_RING + NS * SLOT;
@@ -130,13 +144,41 @@ __global__ void __launch_bounds__(608, 1) conv3x3_tcp_kernel(ConvTcArgs a) {
     const int nops = pres ? 2 : 1;
     const int njobs = (nT + 1) * nops;                       // (chunk, operand) loads; chunk nT holds the last 2 * HALO rows
 
-    if (warp == 1 && lane < K::NBAR / 2 + 1) {       // 34 / 19 barriers: two per lane, one fence per lane (a single thread initialising them all is ~1 us)
+    // pixels below the first row of chunk k: the loader's copy of s_lo[] (it starts before the table exists)
+    auto chunk_lo = [&](int k) { return tcp_pixels_below<W>(Qbase + (k * 128 < R ? k * 128 : R), total); };
+    // one load job: chunk k of operand op -> ring slot jx % NS.  The chunk's valid rows are the pixels [lo, hi): one contiguous block.
+    auto issue_job = [&](int jx) {
+        const int k = jx / nops, op = jx - k * nops, s = jx % K::NS;
+        const int lo = chunk_lo(k), hi = chunk_lo(k + 1);
+        const float* src = (op == 0 ? a.in : a.pro_res) + (size_t)lo * C;
+        if (hi > lo) bulk_load(smem_u32(sRing + (size_t)s * K::SLOT), src, (uint32_t)(hi - lo) * K::ROWB, full + s);
+        else mbar_arrive(full + s);
+    };
+    int jx_next = 0;
+#ifndef LC_TCP_LATE_LOADER
+    if (warp == 18) {
+        // The loader does not wait for the CTA's set-up (TMEM allocation, row table, the other barriers: ~1 us): it initialises the barriers its copies
+        // complete on, waits for the predecessor grid and has a ring-full of chunks + the weights in flight before the CTA-wide barrier below.
+        if (lane < 1 + K::NS) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + lane)), "r"(1));          // wbar, full[]
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (lane == 0) {
+            bulk_load(smem_u32(sB), a.wtc, (uint32_t)K::B_BYTES, wbar);
+            for (; jx_next < njobs && jx_next < K::NS; ++jx_next) issue_job(jx_next);
+        }
+    }
+    constexpr int BAR0 = 1 + K::NS;              // warp 1 initialises the rest
+#else
+    constexpr int BAR0 = 0;
+#endif
+    if (warp == 1 && lane < (K::NBAR - BAR0) / 2 + 1) {       // <= 34 / 19 barriers: two per lane, one fence per lane (a single thread initialising them all is ~1 us)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int i = lane * 2 + h;
+            const int i = BAR0 + lane * 2 + h;
             if (i < K::NBAR) {
                 const bool many = (i >= 1 + K::NS && i < 1 + 2 * K::NS) || (i >= 1 + 2 * K::NS && i < 1 + 2 * K::NS + K::TMAX + 1);      // empty[], staged[]
-                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + i)), "r"(many ? K::NTRANS : 1));
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + i)), "r"(many ? K::NARRIVE : 1));
             }
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -157,15 +199,6 @@ __global__ void __launch_bounds__(608, 1) conv3x3_tcp_kernel(ConvTcArgs a) {
     const uint32_t tmem_base = *tmem_slot;
     if (tid == 0) LC_PSTAMP(1);
 
-    // one load job: chunk k of operand op -> ring slot jx % NS.  The chunk's valid rows are the pixels [lo, hi): one contiguous block.
-    auto issue_job = [&](int jx) {
-        const int k = jx / nops, op = jx - k * nops, s = jx % K::NS;
-        const int lo = s_lo[k], hi = s_lo[k + 1];
-        const float* src = (op == 0 ? a.in : a.pro_res) + (size_t)lo * C;
-        if (hi > lo) bulk_load(smem_u32(sRing + (size_t)s * K::SLOT), src, (uint32_t)(hi - lo) * K::ROWB, full + s);
-        else mbar_arrive(full + s);
-    };
-    int jx_next = 0;
     const bool lazy = a.pro_lazy.partial != nullptr;
     const bool pro = a.pro_scale != nullptr || lazy;
     bool ok = true;
@@ -174,8 +207,10 @@ __global__ void __launch_bounds__(608, 1) conv3x3_tcp_kernel(ConvTcArgs a) {
     if (warp == 18) {
         // ---------------------------------------------------------------- loader: weights, a ring-full of chunks at once, then refills as slots are released
         if (lane == 0) {
+#ifdef LC_TCP_LATE_LOADER
             bulk_load(smem_u32(sB), a.wtc, (uint32_t)K::B_BYTES, wbar);
             for (; jx_next < njobs && jx_next < K::NS; ++jx_next) issue_job(jx_next);
+#endif
             for (; jx_next < njobs; ++jx_next) {
                 const int s = jx_next % K::NS, u = jx_next / K::NS;
                 ok = mbar_wait(empty + s, (uint32_t)((u - 1) & 1)) && ok;
@@ -216,8 +251,9 @@ __global__ void __launch_bounds__(608, 1) conv3x3_tcp_kernel(ConvTcArgs a) {
         }
     } else if (warp < 8) {
         // ---------------------------------------------------------------- transform: ring slot -> prologue -> TF32 -> planar tile
-        const int j = tid % K::CH, rr0 = tid / K::CH;                 // this thread's 16-byte channel chunk; first row of a pass
-        constexpr int RPP = K::NTRANS / K::CH;                        // rows per pass
+        const int grp = tid / K::GTHREADS, gt = tid - grp * K::GTHREADS;
+        const int j = gt % K::CH, rr0 = gt / K::CH;                   // this thread's 16-byte channel chunk; first row of a pass
+        constexpr int RPP = K::GTHREADS / K::CH;                      // rows per pass
         constexpr int NPASS = 128 / RPP;
         // prologue BatchNorm coefficients: only these 256 threads need them (lazy: reduced here from the producer's partial rows while the first chunks
         // fly), so the reduction synchronises on a named barrier and never holds up the loader / issuers
@@ -247,7 +283,7 @@ __global__ void __launch_bounds__(608, 1) conv3x3_tcp_kernel(ConvTcArgs a) {
         }
         if (tid == 0) LC_PSTAMP(2);
         const float4 sc = *reinterpret_cast<const float4*>(s_aff + j * 4), sh = *reinterpret_cast<const float4*>(s_aff + C + j * 4);
-        for (int k = 0; k <= nT; ++k) {
+        for (int k = grp; k <= nT; k += K::NGROUP) {
             const int jin = k * nops, s_in = jin % K::NS;
             ok = mbar_wait(full + s_in, (uint32_t)((jin / K::NS) & 1)) && ok;
             const unsigned char* raw_in = sRing + (size_t)s_in * K::SLOT;
@@ -258,7 +294,7 @@ __global__ void __launch_bounds__(608, 1) conv3x3_tcp_kernel(ConvTcArgs a) {
                 ok = mbar_wait(full + s_res, (uint32_t)(((jin + 1) / K::NS) & 1)) && ok;
                 raw_res = sRing + (size_t)s_res * K::SLOT;
             }
-            if (tid == 0) LC_PSTAMP(10 + k);
+            if (gt == 0) LC_PSTAMP(10 + k);
             const int lo = s_lo[k];
 #pragma unroll
             for (int i = 0; i < NPASS; ++i) {
@@ -286,11 +322,21 @@ __global__ void __launch_bounds__(608, 1) conv3x3_tcp_kernel(ConvTcArgs a) {
                     *reinterpret_cast<float4*>(sA + (size_t)j * K::PLANE + (size_t)r * 16) = v;
                 }
             }
+#ifndef LC_TCP_ELECTED_ARRIVE
             mbar_arrive(empty + s_in);                  // this thread is done reading the slot(s)
             if (pres) mbar_arrive(empty + s_res);
             fence_proxy_async();                        // generic-proxy writes of the planar tile -> visible to the tensor core
             mbar_arrive(staged + k);
-            if (tid == 0) LC_PSTAMP(20 + k);
+#else
+            fence_proxy_async();                        // generic-proxy writes of the planar tile -> visible to the tensor core
+            __syncwarp();                               // every lane has read its ring rows and fenced its tile rows: lane 0 arrives for the warp
+            if (lane == 0) {
+                mbar_arrive(empty + s_in);
+                if (pres) mbar_arrive(empty + s_res);
+                mbar_arrive(staged + k);
+            }
+#endif
+            if (gt == 0) LC_PSTAMP(20 + k);
         }
     } else {
         // ---------------------------------------------------------------- epilogue (warps 8-15: TMEM lane quarter = warp % 4, tiles k = warp / 4 (mod 2))

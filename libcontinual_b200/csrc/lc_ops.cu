@@ -44,8 +44,9 @@ int lc_l2p_select(const float* query, const float* key, int batch, int pool, int
     L2pArgs a{};
     a.query = query; a.key = key; a.sim = sim; a.ids = reinterpret_cast<long long*>(ids); a.hist = hist; a.reduce_sim = reduce_sim; a.dkey = dkey;
     a.qsum = scratch; a.B = batch; a.P = pool; a.D = dim; a.top_k = top_k;
-    const size_t smem = (32 + batch) * sizeof(float) + 64 * sizeof(int) + 8 * sizeof(float);
-    l2p_select_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(a);
+    const size_t smem = (32 + batch) * sizeof(float) + 64 * sizeof(int) + 32 * sizeof(float);
+    l2p_sim_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(a);
+    l2p_select_kernel<<<1, kL2pNT, smem, (cudaStream_t)stream>>>(a);
     return lc_launch_status();
 }
 

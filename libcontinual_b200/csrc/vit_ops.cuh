@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(192) linear_head_bwd_kernel(const float* dlogi
         const int k = blockIdx.x;
         for (int j = threadIdx.x * 4; j < D; j += 192 * 4) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8                                                 // eight independent row loads in flight (the chain of FMAs keeps its order)
             for (int n = 0; n < B; ++n) {
                 const float d = __ldg(dlogits + (size_t)n * ldl + k);
                 const float4 f = ldg4(feat + (size_t)n * D + j);
@@ -197,9 +198,10 @@ __global__ void __launch_bounds__(192) linear_head_bwd_kernel(const float* dlogi
         const int n = blockIdx.x - ncls;
         for (int j = threadIdx.x * 4; j < D; j += 192 * 4) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            // classes outside the task mask carry exactly zero gradient: fma(0, w, acc) == acc, so no branch (a branch would serialise the row loads)
+#pragma unroll 8
             for (int k = 0; k < ncls; ++k) {
                 const float d = __ldg(dlogits + (size_t)n * ldl + k);
-                if (d == 0.f) continue;                      // classes outside the task mask carry exactly zero gradient
                 const float4 w = ldg4(W + (size_t)k * D + j);
                 acc.x = fmaf(d, w.x, acc.x); acc.y = fmaf(d, w.y, acc.y); acc.z = fmaf(d, w.z, acc.z); acc.w = fmaf(d, w.w, acc.w);
             }

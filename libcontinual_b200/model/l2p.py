@@ -215,7 +215,7 @@ class L2P(nn.Module):
         ws2 = eng.forward(x, self.prompts, save=save)
         feat = eng.pooled(ws2, self.n_prompt)
         eng.linear_head(feat, self._view(2).view(self.total_cls_num, DIM), self._view(3), bb["logits"])
-        eng.launches += 2
+        eng.launches += 3          # l2p_sim + l2p_select, l2p_gather (the head counts its own)
         return ws2, feat, bb
 
     def _launch_step(self, x, y, clip: bool = True):

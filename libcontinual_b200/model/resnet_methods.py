@@ -20,21 +20,44 @@ from .backbone.resnet import CifarResNet
 
 
 class _ArenaLoss(torch.autograd.Function):
-    """loss tensor whose backward returns the arena gradient views produced by the fused step."""
+    """loss tensor whose backward hands the gradients the fused step already produced to the parameters.
+
+    Default: the autograd graph has ONE input (a one-element anchor tensor), and `backward` assigns `p.grad` itself — 101 cached views of a persistent
+    flat copy of the gradient arena scaled by the incoming gradient (one kernel).  Returning 101 tensors through the autograd engine instead costs
+    ~0.5 ms of host time per step (a view object + an AccumulateGrad node each), a third of a whole 128-image ResNet32 step.  When a parameter already
+    holds a gradient (no `zero_grad()` since the last backward: gradient accumulation) the new gradient is added to it, as autograd would.
+    `LC_B200_AUTOGRAD_VIEWS=1` restores the engine-mediated hand-off (needed only for `torch.autograd.grad(loss, params)`-style callers)."""
 
     @staticmethod
-    def forward(ctx, owner, loss_value, *params):
+    def forward(ctx, owner, loss_value, *inputs):
         ctx.owner = owner
+        ctx.direct = len(inputs) == 1 and inputs[0] is owner.__dict__.get("_anchor")
         return loss_value.clone()
 
     @staticmethod
     def backward(ctx, g):
         owner = ctx.owner
         eng = owner.engine
-        # autograd gets its own copy (one 1.9 MB kernel): p.grad must never alias the live arena, which the next fused step
-        # overwrites, or gradient accumulation / in-place clipping on p.grad would corrupt either side
-        eng.autograd_grads = eng.grads * g
-        return (None, None, *owner._grad_views_fast(eng.autograd_grads))
+        if not ctx.direct:
+            # autograd gets its own copy (one 1.9 MB kernel): p.grad must never alias the live arena, which the next fused step
+            # overwrites, or gradient accumulation / in-place clipping on p.grad would corrupt either side
+            eng.autograd_grads = eng.grads * g
+            return (None, None, *owner._grad_views_fast(eng.autograd_grads))
+        params = owner._params_cached()
+        if all(p.grad is None for p in params):          # the Trainer's order: zero_grad() precedes backward() (trainer.py:601-604)
+            buf, views = owner._grad_buffer()
+            torch.mul(eng.grads, g, out=buf)
+            for p, v in zip(params, views):
+                if p.requires_grad:
+                    p.grad = v
+            eng.autograd_grads = buf
+        else:
+            fresh = eng.grads * g
+            for p, v in zip(params, owner._grad_views_fast(fresh)):
+                if p.requires_grad:
+                    p.grad = v if p.grad is None else p.grad + v
+            eng.autograd_grads = None                    # p.grad are no longer views of one flat buffer: the optimizer gathers them
+        return (None, None, None)
 
 
 class _Head(nn.Module):
@@ -179,9 +202,28 @@ class _ResNetMethod(nn.Module):
             self.__dict__["_gv_plan"] = c
         return tuple(ch.view(sh) for ch, sh in zip(arena.split_with_sizes(c[1]), c[2]) if sh is not None)
 
+    def _grad_buffer(self):
+        """Persistent flat gradient copy handed to the parameters + its cached per-parameter views (never the live arena: the next fused step overwrites
+        that one while p.grad may still be read, clipped in place or stepped on)."""
+        eng = self.engine
+        key = (eng.ncls, getattr(self, "n_old_rows", None), eng.grads.data_ptr(), eng.grads.numel())
+        c = self.__dict__.get("_grad_buf")
+        if c is None or c[0] != key:
+            buf = torch.empty_like(eng.grads)
+            c = (key, buf, self._grad_views(buf))
+            self.__dict__["_grad_buf"] = c
+        return c[1], c[2]
+
     def _finish(self, B, y):
         eng = self.engine
-        loss = _ArenaLoss.apply(self, eng.scal[0], *self._params_cached())
+        import os
+        if os.environ.get("LC_B200_AUTOGRAD_VIEWS") == "1":
+            loss = _ArenaLoss.apply(self, eng.scal[0], *self._params_cached())
+        else:
+            anchor = self.__dict__.get("_anchor")
+            if anchor is None:
+                anchor = self.__dict__["_anchor"] = torch.zeros(1, device=eng.device, requires_grad=True)
+            loss = _ArenaLoss.apply(self, eng.scal[0], anchor)
         pred = eng.pred[:B].clone()
         acc = eng.scal[1].item()                 # the reference syncs here too (finetune.py:24)
         return pred, acc / B, loss

@@ -24,6 +24,7 @@ from . import _lib
 from ._lib import GemmDesc, check, stream_ptr
 
 DIM, HEADS, HDIM, MLP, GRID, PATCHES = 768, 12, 64, 3072, 14, 196
+COV_SPLIT = 8          # split-K factor of the input-matrix GEMM (18 output tiles x 8 = 144 CTAs)
 
 
 def vit_param_layout(depth: int = 12):
@@ -290,8 +291,9 @@ class ViTEngine:
 
     # ---- GEMM plumbing -------------------------------------------------------------------------
     def gemm(self, A, lda, B, ldb, C, ldc, M, N, K, *, sA=(0, 0), sB=(0, 0), sC=(0, 0), batch=(1, 1), bias=None, residual=None, ldr=0, sR=(0, 0),
-             out2=None, gelu_bwd_aux=None, out_f32=False, alpha=1.0, gelu_mode=0):
-        """C[z] = alpha * A[z] @ B[z]^T (+bias +residual); A/B/C/residual/out2 are raw device addresses (ints), strides in elements."""
+             out2=None, gelu_bwd_aux=None, out_f32=False, alpha=1.0, gelu_mode=0, ksplit=0, stride_split=0):
+        """C[z] = alpha * A[z] @ B[z]^T (+bias +residual); A/B/C/residual/out2 are raw device addresses (ints), strides in elements.
+        ksplit > 1: the K blocks are dealt to `ksplit` fp32 partial outputs, partial s at C + s * stride_split elements (no epilogue operands)."""
         d = GemmDesc()
         d.A, d.lda, d.strideA_in, d.strideA_out = A, lda, sA[0], sA[1]
         d.B, d.ldb, d.strideB_in, d.strideB_out = B, ldb, sB[0], sB[1]
@@ -301,6 +303,7 @@ class ViTEngine:
         d.gelu_bwd_aux = gelu_bwd_aux
         d.M, d.N, d.K, d.batch_in, d.batch_out, d.out_f32, d.alpha = M, N, K, batch[0], batch[1], int(out_f32), alpha
         d.gelu_mode = gelu_mode
+        d.ksplit, d.strideC_split = ksplit, stride_split
         check(self.lib.lc_gemm_bf16_ex(ctypes.byref(d), self.err.data_ptr(), stream_ptr()), f"gemm {M}x{N}x{K}")
         self.launches += 1
 
@@ -489,8 +492,15 @@ class ViTEngine:
         if getattr(ws, "hT", None) is None:
             ws.hT = torch.empty(DIM, npad, device=self.dev, dtype=torch.bfloat16)
         check(self.lib.lc_transpose_bf16(ws.h.data_ptr(), DIM, n, DIM, ws.hT.data_ptr(), npad, stream_ptr()), "transpose_bf16")
-        c = self.cov[i]
-        self.gemm(ws.hT.data_ptr(), npad, ws.hT.data_ptr(), npad, c.data_ptr(), DIM, DIM, DIM, npad, residual=c.data_ptr(), ldr=DIM, out_f32=True)
+        # K = all tokens of the batch against a 768 x 768 output: 18 output tiles, so the K blocks are dealt to COV_SPLIT partial outputs (144 CTAs on 148
+        # SMs instead of 18) and summed in a fixed order
+        if getattr(ws, "cov_part", None) is None:
+            ws.cov_part = torch.empty(COV_SPLIT, DIM, DIM, device=self.dev)
+        nkb, ks = (npad + 63) // 64, COV_SPLIT
+        while ks > 1 and (ks - 1) * ((nkb + ks - 1) // ks) >= nkb:      # every split must own at least one K block (lc_gemm_bf16_ex checks the same)
+            ks -= 1
+        self.gemm(ws.hT.data_ptr(), npad, ws.hT.data_ptr(), npad, ws.cov_part.data_ptr(), DIM, DIM, DIM, npad, out_f32=True, ksplit=ks, stride_split=DIM * DIM)
+        self.cov[i] += ws.cov_part[:ks].sum(0)
         self.launches += 1
         if i == 0:
             self.cov_rows += n

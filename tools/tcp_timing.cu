@@ -34,6 +34,18 @@ void run() {
         for (int k = 0; k <= K::TMAX; ++k)
             printf("   k=%d  chunk arrived %6.2f  staged %6.2f | mma issued %6.2f | acc seen %6.2f  stored %6.2f\n", k, T(10 + k), T(20 + k), T(30 + k), T(40 + k), T(50 + k));
     }
+    {   // event-timed average over the rotating buffers (cold HBM: 12 x 2 x |X| > L2 for C = 16; back-to-back launches, no host sync in between)
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        const int reps = 240;
+        cudaEventRecord(e0);
+        for (int it = 0; it < reps; ++it) {
+            tc::ConvTcArgs a{}; a.in = x[it % NB]; a.wtc = w; a.out = y[it % NB]; a.B = B; a.error_flag = err; a.timing = tm;
+            tc::conv_tcp_launch<C, W, 0>(a, 148, 0);
+        }
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf(" average over %d back-to-back launches: %.2f us\n", reps, ms * 1e3 / reps);
+    }
     int e; cudaMemcpy(&e, err, 4, cudaMemcpyDeviceToHost); printf("err %d %s\n", e, cudaGetErrorString(cudaGetLastError()));
 }
 int main() { run<16, 32>(); run<32, 16>(); return 0; }
