@@ -144,23 +144,25 @@ __global__ void __launch_bounds__(608, 1) conv3x3_tcp_kernel(ConvTcArgs a) {
     const int nops = pres ? 2 : 1;
     const int njobs = (nT + 1) * nops;                       // (chunk, operand) loads; chunk nT holds the last 2 * HALO rows
 
-    // pixels below the first row of chunk k: the loader's copy of s_lo[] (it starts before the table exists)
-    auto chunk_lo = [&](int k) { return tcp_pixels_below<W>(Qbase + (k * 128 < R ? k * 128 : R), total); };
     // one load job: chunk k of operand op -> ring slot jx % NS.  The chunk's valid rows are the pixels [lo, hi): one contiguous block.
     auto issue_job = [&](int jx) {
         const int k = jx / nops, op = jx - k * nops, s = jx % K::NS;
-        const int lo = chunk_lo(k), hi = chunk_lo(k + 1);
+        const int lo = s_lo[k], hi = s_lo[k + 1];
         const float* src = (op == 0 ? a.in : a.pro_res) + (size_t)lo * C;
         if (hi > lo) bulk_load(smem_u32(sRing + (size_t)s * K::SLOT), src, (uint32_t)(hi - lo) * K::ROWB, full + s);
         else mbar_arrive(full + s);
     };
     int jx_next = 0;
-#ifndef LC_TCP_LATE_LOADER
+#ifdef LC_TCP_EARLY_LOADER
     if (warp == 18) {
-        // The loader does not wait for the CTA's set-up (TMEM allocation, row table, the other barriers: ~1 us): it initialises the barriers its copies
-        // complete on, waits for the predecessor grid and has a ring-full of chunks + the weights in flight before the CTA-wide barrier below.
+        // Opt-in variant (-DLC_TCP_EARLY_LOADER): the loader does not wait for the CTA's set-up (TMEM allocation, row table, the other barriers: ~1 us) — its
+        // warp initialises the barriers its copies complete on and the pixel offset of every chunk (one lane each), waits for the predecessor grid and has the
+        // weights + a ring-full of chunks in flight before the CTA-wide barrier below.  Timed alone on cold inputs it wins (8.89 -> 8.44 us at C = 16,
+        // 7.71 -> 7.38 at C = 32); inside the step, where programmatic dependent launch already hides the set-up under the predecessor's tail, the forward pass
+        // is 8 us SLOWER with it (354 -> 362 us over 20 launches, profiles/r3l_step_ab.txt), so it is off.
         if (lane < 1 + K::NS) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + lane)), "r"(1));          // wbar, full[]
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (lane <= nT + 1) s_lo[lane] = tcp_pixels_below<W>(Qbase + (lane * 128 < R ? lane * 128 : R), total);
         __syncwarp();
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if (lane == 0) {
@@ -189,7 +191,9 @@ __global__ void __launch_bounds__(608, 1) conv3x3_tcp_kernel(ConvTcArgs a) {
         const int Q = Qbase + r;
         s_rowsrc[r] = tcp_valid<W>(Q, total) ? tcp_pixels_below<W>(Q, total) : -1;
     }
+#ifndef LC_TCP_EARLY_LOADER
     if (tid <= nT + 1) s_lo[tid] = tcp_pixels_below<W>(Qbase + (tid * 128 < R ? tid * 128 : R), total);
+#endif
     // Programmatic dependent launch: nothing above reads what a predecessor writes
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(608, 1) conv3x3_tcp_kernel(ConvTcArgs a) {
     if (warp == 18) {
         // ---------------------------------------------------------------- loader: weights, a ring-full of chunks at once, then refills as slots are released
         if (lane == 0) {
-#ifdef LC_TCP_LATE_LOADER
+#ifndef LC_TCP_EARLY_LOADER
             bulk_load(smem_u32(sB), a.wtc, (uint32_t)K::B_BYTES, wbar);
             for (; jx_next < njobs && jx_next < K::NS; ++jx_next) issue_job(jx_next);
 #endif
