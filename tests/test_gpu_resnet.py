@@ -262,6 +262,54 @@ def test_reference_trainer_order_with_torch_sgd():
     assert rel_l2(w, orc.fc_w) < 1e-4
 
 
+def test_backward_hands_gradients_to_parameters_like_autograd(monkeypatch):
+    """`loss.backward()` on the plugin surface: p.grad of every parameter equals the engine-mediated hand-off (LC_B200_AUTOGRAD_VIEWS=1), scales with the
+    incoming gradient, never aliases the live gradient arena, and ACCUMULATES when zero_grad() was not called (what autograd's AccumulateGrad does)."""
+    import libcontinual_b200.model as M
+    p, b, fc_w, fc_b = synth_resnet_state(211, 20)
+
+    def build():
+        bb = make_backbone(p, b)
+        m = M.EWC(bb, 64, 100, device=torch.device("cuda"), init_cls_num=10, inc_cls_num=10, lamda=1000.0)
+        m.before_task(0, None, None, None)
+        load_head(m, fc_w[:10], fc_b[:10])
+        m.train()
+        return m
+
+    x, y = synth_batch(212, B, 0, 10)
+    monkeypatch.setenv("LC_B200_AUTOGRAD_VIEWS", "1")
+    m_ref = build()
+    _, _, loss = m_ref.observe({"image": x, "label": y})
+    (loss * 0.5).backward()
+    ref = [q.grad.clone() for q in m_ref.get_parameters(None)[0]["params"]]
+    monkeypatch.delenv("LC_B200_AUTOGRAD_VIEWS")
+
+    m = build()
+    params = m.get_parameters(None)[0]["params"]
+    _, _, loss = m.observe({"image": x, "label": y})
+    (loss * 0.5).backward()
+    eng = m.engine
+    lo, hi = eng.grads.data_ptr(), eng.grads.data_ptr() + eng.grads.numel() * 4
+    for q, r in zip(params, ref):
+        assert q.grad is not None and q.grad.shape == q.shape
+        assert torch.equal(q.grad, r)
+        assert not (lo <= q.grad.data_ptr() < hi), "p.grad aliases the live gradient arena"
+    # the fused optimizer recognises the flat copy (fast path), and a second backward without zero_grad() accumulates
+    assert params[0].grad.data_ptr() == eng.autograd_grads.data_ptr()
+    _, _, loss2 = m.observe({"image": x, "label": y})
+    loss2.backward()
+    for q, r in zip(params, ref):
+        assert torch.allclose(q.grad, 3.0 * r, rtol=1e-6, atol=1e-12)      # 0.5 g + 1.0 g of the same (deterministic) step
+    assert eng.autograd_grads is None                                       # the optimizer must gather p.grad now
+    # ... and after zero_grad() the next backward assigns again
+    for q in params:
+        q.grad = None
+    _, _, loss3 = m.observe({"image": x, "label": y})
+    loss3.backward()
+    for q, r in zip(params, ref):
+        assert torch.allclose(q.grad, 2.0 * r, rtol=1e-6, atol=1e-12)
+
+
 def test_full_batch_128_properties():
     """BASELINE size (bs 128): reference-free properties — finite loss near ln(10) at init, EWC penalty exactly 0 with zero
     gradient contribution when theta == theta*, deterministic replay (bit-identical gradients run to run)."""
