@@ -71,6 +71,8 @@ def parse():
                     "batch_size // n_gpu, trainer.py:238); 0 = per-GPU batch 128 (weak scaling)")
     ap.add_argument("--gpm-project", action="store_true", help="--workload lwf18 only: add the GPM projection of every conv gradient onto the complement of "
                     "seeded orthonormal bases (rank 10 %% of Cin*k*k) after backward — BASELINE config C5 'LwF + GPM' in full (SURVEY 8d)")
+    ap.add_argument("--sync-vote", action="store_true", help="--workload l2p under N > 1: vote on the prompt histogram of the GLOBAL batch (one extra [pool] int32 "
+                    "all-reduce per step, captured in the step's graph) instead of each rank's shard")
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
                     help="conv arithmetic: tc = tcgen05 tensor cores (TF32 fwd/dgrad, BF16-operand wgrad, fp32 accumulate), fp32 = exact CUDA-core path")
     return ap.parse_args()
@@ -527,7 +529,7 @@ def run_ours_l2p(args, ctx, kind):
         p, prm, key, fc_w, fc_b = l2p_synth_state()
         bb = vit_pt_imnet(pretrained=False, state=p, device=device)
         m = L2P(bb, device, init_cls_num=10, inc_cls_num=10, num_class=100, task_num=10, feat_dim=768, prompt_length=5, pool_size=10, top_k=5,
-                pull_constraint_coeff=1.0)
+                pull_constraint_coeff=1.0, sync_vote=bool(getattr(args, "sync_vote", False)))
         with torch.no_grad():
             bb.prompt.prompt.copy_(prm); bb.prompt.prompt_key.copy_(key)
             m.network.classifier.weight.copy_(fc_w); m.network.classifier.bias.copy_(fc_b)
@@ -662,7 +664,8 @@ def run_ours_l2p(args, ctx, kind):
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(kind), "global_batch": per * world, "per_gpu_batch": per, "parallelism": f"dp{world}",
-                       "collective": step.collective,
+                       "collective": step.collective + ("; + SUM all-reduce of the [pool] int32 prompt histogram (global-batch vote)"
+                                                        if kind == "l2p" and getattr(args, "sync_vote", False) and world > 1 else ""),
                        "l2": f"per-step working set ~9 GB of saved activations + {NB} rotating 77 MB input batches > 126 MB L2 (no explicit flush)",
                        "precision": "BF16 GEMM operands (tcgen05 kind::f16), fp32 accumulate in TMEM, fp32 residual stream / LayerNorm / softmax / loss / optimizer",
                        "final_loss": final_loss, "tensor_core_error": eng.tensor_core_error(),

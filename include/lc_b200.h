@@ -137,6 +137,11 @@ int lc_lucir_loss(const float* logits, const float* scores, int ld, const float*
                   float* dfeat, int64_t* pred, float* scal, float* dsigma /* nullable: sum(dlogits*scores) */, lc_stream_t stream);
 int lc_l2p_select(const float* query, const float* key, int batch, int pool, int dim, int top_k, float* sim, int64_t* ids, int* hist,
                   float* reduce_sim, float* dkey, float* scratch, lc_stream_t stream);
+/* The same selection in two phases for data parallelism: phase 1 = similarities + per-sample top-k -> `hist` (this rank's counts); the caller SUM-all-reduces
+ * `hist` over the ranks; phase 2 = majority vote on that histogram, `reduce_sim` and `dkey` of this rank's samples for the voted ids (prompt.py:380-401 on the
+ * GLOBAL batch).  phase 0 = lc_l2p_select. */
+int lc_l2p_select_phase(const float* query, const float* key, int batch, int pool, int dim, int top_k, float* sim, int64_t* ids, int* hist,
+                        float* reduce_sim, float* dkey, float* scratch, int phase, lc_stream_t stream);
 int lc_l2p_gather(const float* prompt, const int64_t* ids, float* out, int batch, int top_k, int length, int dim, lc_stream_t stream);
 int lc_gpm_project(float* grad, const float* proj, int rows, int dim, lc_stream_t stream);
 int lc_lora_merge_qkv(const float* qkv_w, const float* A_k, const float* B_k, const float* A_v, const float* B_v, float* out, int dim, int rank,

@@ -50,6 +50,7 @@ SIGNATURES = {
     "lc_cosine_head_backward": (c_int, [P, c_int, P, P, P, c_int, c_int, c_int, P, P, P]),
     "lc_lucir_loss": (c_int, [P, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P, P, P, P, P]),
     "lc_l2p_select": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "lc_l2p_select_phase": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, P]),
     "lc_l2p_gather": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     "lc_gpm_project": (c_int, [P, P, c_int, c_int, P]),
     "lc_lora_merge_qkv": (c_int, [P, P, P, P, P, P, c_int, c_int, P]),

@@ -195,7 +195,8 @@ struct L2pArgs {
     float* dkey;             // [P][D]  out: d(reduce_sim)/d(key)  (nullable)
     float* qsum;             // [D]     scratch: sum_b qhat_b
     int B, P, D, top_k;
-};
+    int phase;               // 0: vote on this batch's own histogram; 1: per-sample top-k -> hist only; 2: vote on the histogram found in `hist`
+};                           // (1 + 2 with a SUM all-reduce of `hist` in between = the batch-wide majority vote of the GLOBAL batch under data parallelism)
 
 // (1) similarities: one CTA per sample, warp w owns prompts w, w + 8, ...  (inverse norms recomputed per warp: 2 x D floats out of L1 / L2)
 __global__ void __launch_bounds__(256) l2p_sim_kernel(L2pArgs a) {
@@ -228,8 +229,9 @@ __global__ void __launch_bounds__(kL2pNT) l2p_select_kernel(L2pArgs a) {
     int* s_ids = s_hist + 32;             // [32]
     float* s_part = reinterpret_cast<float*>(s_ids + 32);    // [32] per-warp partial sums
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 32) s_hist[tid] = 0;
+    if (tid < 32) s_hist[tid] = (a.phase == 2 && tid < a.P) ? a.hist[tid] : 0;
     // inverse norms: one warp per row
+    if (a.phase != 1)
     for (int r = warp; r < a.P + a.B; r += kL2pNW) {
         const float* x = r < a.P ? a.key + (size_t)r * a.D : a.query + (size_t)(r - a.P) * a.D;
         float s = 0.f;
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(kL2pNT) l2p_select_kernel(L2pArgs a) {
     }
     __syncthreads();
     // per-sample top-k -> histogram (integer atomics: order-independent)
+    if (a.phase != 2)
     for (int b = tid; b < a.B; b += kL2pNT) {
         const float* s = a.sim + (size_t)b * a.P;
         float last = CUDART_INF_F; int last_idx = -1;
@@ -255,6 +258,10 @@ __global__ void __launch_bounds__(kL2pNT) l2p_select_kernel(L2pArgs a) {
         }
     }
     __syncthreads();
+    if (a.phase == 1) {                                  // uniform: the vote happens after the histograms of all ranks have been summed
+        if (tid < a.P) a.hist[tid] = s_hist[tid];
+        return;
+    }
     if (tid == 0) {
         // reference: ids = unique(sorted) padded with ids[0]; counts padded with 0; topk(counts) -> ids
         int present[32], cnt[32], np = 0;

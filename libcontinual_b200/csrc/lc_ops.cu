@@ -39,13 +39,19 @@ int lc_lucir_loss(const float* logits, const float* scores, int ld, const float*
 
 int lc_l2p_select(const float* query, const float* key, int batch, int pool, int dim, int top_k, float* sim, int64_t* ids, int* hist,
                   float* reduce_sim, float* dkey, float* scratch, lc_stream_t stream) {
+    return lc_l2p_select_phase(query, key, batch, pool, dim, top_k, sim, ids, hist, reduce_sim, dkey, scratch, 0, stream);
+}
+
+int lc_l2p_select_phase(const float* query, const float* key, int batch, int pool, int dim, int top_k, float* sim, int64_t* ids, int* hist,
+                        float* reduce_sim, float* dkey, float* scratch, int phase, lc_stream_t stream) {
     LC_CHECK_ARG(query && key && sim && ids && hist && reduce_sim && scratch && batch >= 1 && batch <= 4096 && pool >= 1 && pool <= 32 && top_k >= 1 &&
-                 top_k <= pool && dim >= 1);
+                 top_k <= pool && dim >= 1 && phase >= 0 && phase <= 2);
     L2pArgs a{};
+    a.phase = phase;
     a.query = query; a.key = key; a.sim = sim; a.ids = reinterpret_cast<long long*>(ids); a.hist = hist; a.reduce_sim = reduce_sim; a.dkey = dkey;
     a.qsum = scratch; a.B = batch; a.P = pool; a.D = dim; a.top_k = top_k;
     const size_t smem = (32 + batch) * sizeof(float) + 64 * sizeof(int) + 32 * sizeof(float);
-    l2p_sim_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(a);
+    if (phase != 2) l2p_sim_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(a);
     l2p_select_kernel<<<1, kL2pNT, smem, (cudaStream_t)stream>>>(a);
     return lc_launch_status();
 }

@@ -131,6 +131,10 @@ class L2P(nn.Module):
         self.task_num = kwargs["task_num"]
         self.embed_dim = kwargs["feat_dim"]
         self.pull_constraint_coeff = kwargs["pull_constraint_coeff"]
+        # extension (not a reference kwarg): under torch.distributed, vote on the prompt histogram of the GLOBAL batch instead of each rank's shard — exactly
+        # the single-GPU result at the global batch size (the reference's own DDP path is dead code; per-rank voting is what plain DDP would do)
+        self.sync_vote = bool(kwargs.get("sync_vote", False))
+        self.vote_group = kwargs.get("vote_group", None)
         self.cur_task_id = 0
         self._known_classes = 0
         assert self.embed_dim == DIM
@@ -187,6 +191,10 @@ class L2P(nn.Module):
                                  dfeat=torch.zeros(B, DIM, device=dev))
         return self._bufs[B]
 
+    def _vote_is_global(self) -> bool:
+        import torch.distributed as dist
+        return self.sync_vote and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.vote_group) > 1
+
     # ---- plugin surface --------------------------------------------------------------------------
     def before_task(self, task_idx, buffer, train_loader, test_loaders):
         self.cur_task_id = task_idx
@@ -209,8 +217,18 @@ class L2P(nn.Module):
         bb = self._batch_bufs(B)
         ws1 = eng.forward(x, None, save=False)
         q = eng.pooled(ws1, 0)
-        check(lib.lc_l2p_select(q.data_ptr(), self._view(1).data_ptr(), B, self.pool_size, DIM, self.top_k, bb["sim"].data_ptr(), self.ids.data_ptr(),
-                                self.hist.data_ptr(), self.reduce_sim.data_ptr(), self.dkey_raw.data_ptr(), self.sel_scratch.data_ptr(), st), "l2p_select")
+        sel = (q.data_ptr(), self._view(1).data_ptr(), B, self.pool_size, DIM, self.top_k, bb["sim"].data_ptr(), self.ids.data_ptr(), self.hist.data_ptr(),
+               self.reduce_sim.data_ptr(), self.dkey_raw.data_ptr(), self.sel_scratch.data_ptr())
+        if self._vote_is_global():
+            # data parallel with `sync_vote`: the majority vote (prompt.py:380-401) is taken over the GLOBAL batch — per-rank counts, one SUM all-reduce of
+            # the [pool] int32 histogram (capturable, like the gradient all-reduce), then the vote / pull constraint on the summed histogram
+            from ..parallel import allreduce_sum_
+            check(lib.lc_l2p_select_phase(*sel, 1, st), "l2p_select(counts)")
+            allreduce_sum_(self.hist, self.vote_group)
+            check(lib.lc_l2p_select_phase(*sel, 2, st), "l2p_select(vote)")
+            eng.launches += 2      # the all-reduce + one more launch of the vote kernel
+        else:
+            check(lib.lc_l2p_select(*sel, st), "l2p_select")
         check(lib.lc_l2p_gather(self._view(0).data_ptr(), self.ids.data_ptr(), self.prompts.data_ptr(), 1, self.top_k, self.length, DIM, st), "l2p_gather")
         ws2 = eng.forward(x, self.prompts, save=save)
         feat = eng.pooled(ws2, self.n_prompt)

@@ -27,6 +27,13 @@ def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
     return flat
 
 
+def allreduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place SUM over ranks of a small integer / float tensor (L2P's prompt histogram: the batch-wide vote of the GLOBAL batch)."""
+    if dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
 def assert_replicas_identical(flat: torch.Tensor, group=None, what: str = "state") -> None:
     """Debug check that replicated continual-learning state (theta*, Fisher, teacher, ...) is bit-identical across ranks."""
     world = dist.get_world_size(group)

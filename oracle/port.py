@@ -384,6 +384,13 @@ def l2p_majority_ids_numpy(sim: np.ndarray, top_k: int) -> np.ndarray:
         order = sorted(range(pool), key=lambda j: (-float(sim[b, j]), j))[:top_k]
         for j in order:
             hist[j] += 1
+    return l2p_majority_from_hist_numpy(hist, top_k)
+
+
+def l2p_majority_from_hist_numpy(hist: np.ndarray, top_k: int) -> np.ndarray:
+    """The majority step of `l2p_majority_ids_numpy` alone (prompt.py:380-401 after `torch.unique(..., return_counts=True)`): a histogram of
+    per-sample top-k picks -> the top_k most frequent prompt ids.  Under data parallelism the histogram is the SUM over the ranks' shards."""
+    pool = len(hist)
     present = [j for j in range(pool) if hist[j] > 0]
     # reference pads the id list with ids[0] / count 0 (prompt.py:384-385)
     ids = present + [present[0]] * (pool - len(present))

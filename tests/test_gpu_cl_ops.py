@@ -173,3 +173,50 @@ def test_gpm_project_tensor_core(lib):
         print(f"gpm tc {tuple(shape)}: rel-L2 vs float64 {e64:.1e} (the fp32 reference op itself: {e32:.1e})")
         assert e64 < 2e-5, (shape, e64)
         assert float((got.cpu().view(shape[0], -1) @ feats[i]).abs().max()) < 2e-3      # orthogonal to the stored basis
+
+
+def test_l2p_select_phases_and_global_batch_vote(lib):
+    """lc_l2p_select_phase: (1) counts + (2) vote == the one-call selection bit for bit; and the data-parallel use — counts of two half batches,
+    histograms summed (what the SUM all-reduce does), vote on the sum — picks the ids of the WHOLE batch (prompt.py:380-401 at the global batch)."""
+    rng = np.random.default_rng(909)
+    B, pool, topk, D = 64, 10, 5, 768
+    key = torch.from_numpy(rng.uniform(0, 1, (pool, D)).astype(np.float32))
+    q = torch.from_numpy(rng.standard_normal((B, D)).astype(np.float32))
+
+    def run(qq, phase, hist=None):
+        n = qq.shape[0]
+        sim = torch.zeros(n, pool, device="cuda"); ids = torch.zeros(topk, dtype=torch.int64, device="cuda")
+        hist = torch.zeros(pool, dtype=torch.int32, device="cuda") if hist is None else hist
+        rs = torch.zeros(1, device="cuda"); dkey = torch.zeros(pool, D, device="cuda"); scratch = torch.zeros(D, device="cuda")
+        qd, kd = dev(qq), dev(key)
+        if phase == "one":
+            assert lib.lc_l2p_select(P(qd), P(kd), n, pool, D, topk, P(sim), P(ids), P(hist), P(rs), P(dkey), P(scratch), st()) == 0
+        elif phase == "two":
+            assert lib.lc_l2p_select_phase(P(qd), P(kd), n, pool, D, topk, P(sim), P(ids), P(hist), P(rs), P(dkey), P(scratch), 1, st()) == 0
+            assert lib.lc_l2p_select_phase(P(qd), P(kd), n, pool, D, topk, P(sim), P(ids), P(hist), P(rs), P(dkey), P(scratch), 2, st()) == 0
+        elif phase == 1:
+            assert lib.lc_l2p_select_phase(P(qd), P(kd), n, pool, D, topk, P(sim), P(ids), P(hist), P(rs), P(dkey), P(scratch), 1, st()) == 0
+        else:
+            assert lib.lc_l2p_select_phase(P(qd), P(kd), n, pool, D, topk, P(sim), P(ids), P(hist), P(rs), P(dkey), P(scratch), 2, st()) == 0
+        torch.cuda.synchronize()
+        return sim.cpu(), ids.cpu(), hist, rs.cpu(), dkey.cpu()
+
+    one = run(q, "one")
+    two = run(q, "two")
+    for a, b in zip(one, two):
+        assert torch.equal(a.cpu(), b.cpu())
+    assert lib.lc_l2p_select_phase(None, None, B, pool, D, topk, None, None, None, None, None, None, 3, st()) != 0      # bad phase / pointers: error code
+
+    # two "ranks": counts per half, summed histogram, vote on each half with the global histogram
+    h0 = run(q[:32], 1)[2]
+    h1 = run(q[32:], 1)[2]
+    total = (h0 + h1).clone()
+    assert torch.equal(total.cpu(), one[2].cpu())                       # the summed counts ARE the whole batch's histogram
+    r0 = run(q[:32], 2, hist=total.clone())
+    r1 = run(q[32:], 2, hist=total.clone())
+    assert torch.equal(r0[1], one[1]) and torch.equal(r1[1], one[1])   # both ranks pick the whole batch's ids
+    kn, qn = F.normalize(key, dim=-1), F.normalize(q, dim=-1)
+    assert np.array_equal(one[1].numpy(), port.l2p_majority_ids_numpy((qn @ kn.T).numpy(), topk))
+    # the mean of the two ranks' pull-constraint terms (what DDP's loss / gradient averaging yields) is the whole batch's
+    assert abs(0.5 * (float(r0[3]) + float(r1[3])) - float(one[3])) < 1e-5
+    close(0.5 * (r0[4] + r1[4]), one[4], 1e-4, 1e-6, "d(reduce_sim)/d(key), averaged over the two shards")

@@ -33,6 +33,44 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _vote_worker(rank, world, port, q):
+    """L2P's global-batch vote under data parallelism: per-rank top-k counts, SUM all-reduce of the histogram, the reference's majority rule on the sum
+    == the rule applied to the whole batch on one rank (oracle/port.py restates prompt.py:380-401)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import numpy as np
+        from libcontinual_b200.parallel import allreduce_sum_
+        from oracle import port as oport
+        rng = np.random.default_rng(77)
+        sim = rng.standard_normal((64, 10)).astype(np.float32)          # the global batch: identical on every rank
+        topk = 5
+        whole = oport.l2p_majority_ids_numpy(sim, topk)
+        shard = sim[rank * 32:(rank + 1) * 32]
+        idx = np.argsort(-shard, axis=1, kind="stable")[:, :topk]
+        hist = torch.from_numpy(np.bincount(idx.reshape(-1), minlength=10).astype(np.int32))
+        allreduce_sum_(hist)
+        full_hist = np.bincount(np.argsort(-sim, axis=1, kind="stable")[:, :topk].reshape(-1), minlength=10)
+        ok = np.array_equal(hist.numpy(), full_hist) and np.array_equal(oport.l2p_majority_from_hist_numpy(hist.numpy(), topk), whole)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_l2p_global_vote_histogram_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_vote_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=10) for _ in range(2))
+    assert res == {0: True, 1: True}
+
+
 def test_flat_bucket_mean_and_replica_consistency_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
