@@ -905,15 +905,17 @@ def run_ours(args, ctx, workload):
     ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    step.prefetch(*host[0])                         # inside the timed region: every step's H2D copy is counted (plus one extra at the end)
     for i in range(Ke):
         step.run(*host[i % NH])
+        step.prefetch(*host[(i + 1) % NH])          # the next batch crosses PCIe on the copy stream while this step computes
         lossv = step.loss().item()
     e1.record()
     ctx.barrier()
     e2e_ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / Ke
     e2e = {"value": world * per / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": per * 3 * img * img * 4 + per * 8,
            "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
-           "path": "libcontinual_b200.trainer.GraphedStep.run(pinned host batch) + loss().item() every step"}
+           "path": "libcontinual_b200.trainer.GraphedStep.run(pinned host batch) + .prefetch(next pinned host batch) + loss().item() every step"}
     # the literal reference Trainer order on the plugin surface (eager, autograd hand-off), single replica
     plugin = None
     if world == 1:

@@ -88,6 +88,12 @@ class GraphedStep:
         self.launches_per_step = eng.launches - l0 + (1 if self.world > 1 else 0)
         model.backbone.num_batches_pending = pending0      # warm-up / capture launches restored above do not count
         self.steps = 0
+        self.stager = _InputStager(self.x, self.y)
+
+    def prefetch(self, x: torch.Tensor, y: torch.Tensor):
+        """Optional: start the host -> device copy of the batch that the NEXT `run` will be given (copy stream, double-buffered): the 1.6 MB of a
+        128-image CIFAR batch is 60 us of PCIe time, 4 % of a step, that otherwise sits in front of every replay."""
+        self.stager.prefetch(x, y)
 
     def _sync_hp(self):
         g = self.opt.param_groups[0]
@@ -106,8 +112,7 @@ class GraphedStep:
         """One step on a batch that is either device-resident or in (pinned) host memory.  Returns nothing: read
         `loss()` / `correct()` when needed (device scalars)."""
         self._sync_hp()
-        self.x.copy_(x, non_blocking=non_blocking)
-        self.y.copy_(y, non_blocking=non_blocking)
+        self.stager.load(x, y, self.x, self.y, non_blocking)
         self.g_main.replay()
         if self.g_upd is not None:
             allreduce_mean_(self.eng.grads, self.pg)

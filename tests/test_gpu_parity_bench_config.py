@@ -227,6 +227,39 @@ def test_graphed_step_matches_eager_b128_tc():
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
 
 
+def test_graphed_step_prefetch_from_pinned_host_equals_device_batches():
+    """`GraphedStep.run(pinned host batch)` with `.prefetch(next pinned host batch)` (the bench's e2e loop: double-buffered H2D on a copy stream) leaves the
+    same parameters, bit for bit, as `run` on device-resident batches."""
+    import libcontinual_b200.model as M
+    from libcontinual_b200.optim import SGD
+    from libcontinual_b200.trainer import GraphedStep
+    outs = []
+    batches = [synth_batch(700 + s, B, 0, 10) for s in range(4)]
+    for mode in ("device", "prefetch"):
+        p, b, fc_w, fc_b = synth_resnet_state(78, 100)
+        bb = _backbone(p, b, "tc")
+        m = M.EWC(bb, 64, 100, device=torch.device("cuda"), init_cls_num=10, inc_cls_num=10, lamda=1000.0)
+        m.before_task(0, None, None, None)
+        load_head(m, fc_w[:10], fc_b[:10])
+        m.train()
+        opt = SGD(m.get_parameters(None), lr=0.1, momentum=0.9, weight_decay=5e-4, engine=m.engine)
+        step = GraphedStep(m, opt, B)
+        if mode == "device":
+            for x, y in batches:
+                step.run(x.cuda(), y.cuda())
+        else:
+            host = [(x.contiguous().pin_memory(), y.contiguous().pin_memory()) for x, y in batches]
+            step.prefetch(*host[0])
+            for j, (x, y) in enumerate(host):
+                step.run(x, y)
+                if j + 1 < len(host):
+                    step.prefetch(*host[j + 1])
+                step.loss().item()
+        torch.cuda.synchronize()
+        outs.append((m.engine.params.clone(), float(m.engine.scal[0])))
+    assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+
+
 # ---- the tensor-core kernels alone at the benched batch size ---------------------------------------------------------------------------
 @pytest.mark.parametrize("c,w", [(16, 32), (32, 16), (64, 8)])
 def test_conv3x3_tc_forward_b128(c, w):

@@ -27,7 +27,10 @@ def build(device, sync_vote):
     m = L2P(bb, device, init_cls_num=10, inc_cls_num=10, num_class=100, task_num=10, feat_dim=768, prompt_length=5, pool_size=10, top_k=5,
             pull_constraint_coeff=1.0, sync_vote=sync_vote)
     with torch.no_grad():
-        bb.prompt.prompt.copy_(prm); bb.prompt.prompt_key.copy_(key)
+        bb.prompt.prompt.copy_(prm)
+        # zero-mean keys: U(0, 1) keys share a large mean direction, every sample then ranks the prompts alike and a per-rank vote could not differ from the
+        # global one; with these the shards' histograms differ
+        bb.prompt.prompt_key.copy_(torch.randn(key.shape, generator=torch.Generator().manual_seed(5)))
         m.network.classifier.weight.copy_(fc_w); m.network.classifier.bias.copy_(fc_b)
     m.after_task(0, None, None, None); m.before_task(1, None, None, None)
     m.train()
@@ -75,12 +78,12 @@ def main():
         ids1 = torch.stack(ids1).cpu()
         th1 = m.theta.detach().clone().cpu()
         res = {"world": world, "global_batch": GLOBAL_B, "steps": K}
-        for name in out:
-            ids, th, loss = out[name]
-            res[name] = {"ids_equal_to_single_gpu_every_step": bool(torch.equal(ids, ids1)), "ids": ids.tolist(),
-                         "theta_rel_l2_vs_single_gpu": float((th - th1).norm() / th1.norm()), "final_loss_rank0_shard": loss}
         res["single_gpu_ids"] = ids1.tolist()
         res["single_gpu_final_loss"] = float(loss)
+        for name in out:
+            ids, th, shard_loss = out[name]
+            res[name] = {"ids_equal_to_single_gpu_every_step": bool(torch.equal(ids, ids1)), "ids": ids.tolist(),
+                         "theta_rel_l2_vs_single_gpu": float((th - th1).norm() / th1.norm()), "final_loss_rank0_shard": shard_loss}
         print(json.dumps(res))
     dist.barrier()
     dist.destroy_process_group()
