@@ -160,6 +160,8 @@ class GpuLoader:
     def _stage(self, slot: int, idx: np.ndarray):
         B = len(idx)
         draw, aux = self._draws(B)
+        if self.used_rec[slot]:
+            self.ev[slot].synchronize()          # the previous copy out of this pinned slot has left the host before it is overwritten
         self.h_idx[slot][:B].copy_(torch.from_numpy(idx))
         self.h_draw[slot][:B].copy_(torch.from_numpy(draw))
         has_aux = aux is not None
