@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(C) avgpool_fc_fwd_kernel(const float* act /*[B
     const int n = blockIdx.x, c = threadIdx.x;
     const float* src = act + (size_t)n * HW * C + c;
     float s = 0.f;
+#pragma unroll 16                                   // 16 row loads in flight; the additions keep their order
     for (int p = 0; p < HW; ++p) s += __ldg(src + (size_t)p * C);
     s = s / (float)HW;
     s_f[c] = s;
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(C) head_bwd_kernel(const float* dlogits, int l
     if ((int)blockIdx.x < ncls) {
         const int k = blockIdx.x;
         float acc = 0.f, bacc = 0.f;
+#pragma unroll 16                                   // these loops are chains of L2 latencies, not arithmetic: keep 16 loads in flight (same FMA order)
         for (int n = 0; n < B; ++n) {
             const float d = __ldg(dlogits + (size_t)n * ldl + k);
             acc = fmaf(d, __ldg(feat + (size_t)n * C + c), acc);
@@ -141,11 +143,13 @@ __global__ void __launch_bounds__(C) head_bwd_kernel(const float* dlogits, int l
     } else {
         const int n = blockIdx.x - ncls;
         float acc = 0.f;
+#pragma unroll 10
         for (int k = 0; k < ncls; ++k) acc = fmaf(__ldg(dlogits + (size_t)n * ldl + k), __ldg(W + (size_t)k * C + c), acc);
         dfeat[(size_t)n * C + c] = acc;
         if (gact != nullptr) {
             const float g = acc / (float)HW;
             float* dst = gact + (size_t)n * HW * C + c;
+#pragma unroll 16
             for (int p = 0; p < HW; ++p) dst[(size_t)p * C] = g;
         }
     }
@@ -158,6 +162,7 @@ __global__ void __launch_bounds__(C) avgpool_fwd_kernel(const float* act, int HW
     const int n = blockIdx.x, c = threadIdx.x;
     const float* src = act + (size_t)n * HW * C + c;
     float s = 0.f;
+#pragma unroll 16
     for (int p = 0; p < HW; ++p) s += __ldg(src + (size_t)p * C);
     feat[(size_t)n * C + c] = s / (float)HW;
 }
