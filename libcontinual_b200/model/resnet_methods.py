@@ -26,6 +26,7 @@ class _ArenaLoss(torch.autograd.Function):
     flat copy of the gradient arena scaled by the incoming gradient (one kernel).  Returning 101 tensors through the autograd engine instead costs
     ~0.5 ms of host time per step (a view object + an AccumulateGrad node each), a third of a whole 128-image ResNet32 step.  When a parameter already
     holds a gradient (no `zero_grad()` since the last backward: gradient accumulation) the new gradient is added to it, as autograd would.
+    The flat copy is reused by the next backward that follows a `zero_grad()`: a `p.grad` tensor kept across steps sees the new values (clone it to keep it).
     `LC_B200_AUTOGRAD_VIEWS=1` restores the engine-mediated hand-off (needed only for `torch.autograd.grad(loss, params)`-style callers)."""
 
     @staticmethod
