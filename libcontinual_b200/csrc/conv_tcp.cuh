@@ -48,9 +48,9 @@ struct ConvTcpCfg {
     static constexpr int EPI_WARP = 32 * ROWB;       // epilogue staging per warp
     static constexpr int NTHREADS = 608;             // 8 transform + 8 epilogue warps (one warp per scheduler cannot hide its own latencies) + 2 issuers + loader
     static constexpr int NTRANS = 256;
-    // Two measured-and-rejected variants stay behind compile-time switches (profiles/r3j_tcp_variants.txt, r3j_step_ab.txt): neither changes the kernel timed
-    // alone on cold inputs (8.5 us: it is bound by the arrival rate of its chunks), both cost ~0.7 us per launch inside the step, where the inputs come
-    // out of L2 and the staged -> MMA latency is exposed.
+    // Two measured-and-rejected variants stay behind compile-time switches (profiles/r3j_tcp_variants.txt, r3j / r3k_step_ab.txt): neither changes the kernel
+    // timed alone on cold inputs (it is bound by the arrival of its chunks and the shared-memory re-reads, not by barrier traffic or the transform's
+    // dependency chain); inside the step the elected arrival is neutral as well and the two groups cost 4.5 us per forward pass.
 #ifdef LC_TCP_TWO_GROUPS
     static constexpr int NGROUP = 2;                // transform warps 0-3 stage the even chunks, 4-7 the odd ones
 #else
@@ -58,7 +58,7 @@ struct ConvTcpCfg {
 #endif
     static constexpr int GTHREADS = NTRANS / NGROUP;
 #ifdef LC_TCP_ELECTED_ARRIVE
-    static constexpr int NARRIVE = GTHREADS / 32;   // one elected arrival per transform warp (the elected lane's serial arrivals sit on the critical path)
+    static constexpr int NARRIVE = GTHREADS / 32;   // one elected arrival per transform warp
 #else
     static constexpr int NARRIVE = GTHREADS;        // every transform thread arrives on empty[] / staged[] right behind its own proxy fence
 #endif
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(608, 1) conv3x3_tcp_kernel(ConvTcArgs a) {
         // warp initialises the barriers its copies complete on and the pixel offset of every chunk (one lane each), waits for the predecessor grid and has the
         // weights + a ring-full of chunks in flight before the CTA-wide barrier below.  Timed alone on cold inputs it wins (8.89 -> 8.44 us at C = 16,
         // 7.71 -> 7.38 at C = 32); inside the step, where programmatic dependent launch already hides the set-up under the predecessor's tail, the forward pass
-        // is 8 us SLOWER with it (354 -> 362 us over 20 launches, profiles/r3l_step_ab.txt), so it is off.
+        // is 8 us SLOWER with it (354 -> 362 us over 20 launches, profiles/r3l_step_ab.txt; 368 us when the refills recomputed the offsets), so it is off.
         if (lane < 1 + K::NS) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + lane)), "r"(1));          // wbar, full[]
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (lane <= nT + 1) s_lo[lane] = tcp_pixels_below<W>(Qbase + (lane * 128 < R ? lane * 128 : R), total);
