@@ -150,7 +150,7 @@ int wgrad_nsplit_tc(int c) {
     // chain — not alone, where more CTAs always win: LC_WGRAD_NSPLIT="n16,n32,n64" overrides for A/B runs.
     static int ns[3] = {0, 0, 0};
     if (ns[0] == 0) {
-        ns[0] = 296; ns[1] = 148; ns[2] = 34;
+        ns[0] = 222; ns[1] = 111; ns[2] = 34;      // profiles/r3w_wgrad_nsplit_sweep.txt: 296,148,34 -> 222,111,34 = backward 784 -> 768 us
         const char* e = getenv("LC_WGRAD_NSPLIT");
         int a = 0, b = 0, d = 0;
         if (e != nullptr && sscanf(e, "%d,%d,%d", &a, &b, &d) == 3 && a >= 1 && a <= 296 && b >= 1 && b <= 148 && d >= 1 && d <= 100) { ns[0] = a; ns[1] = b; ns[2] = d; }
